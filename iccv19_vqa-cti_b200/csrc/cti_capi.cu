@@ -1,0 +1,159 @@
+// extern "C" boundary of libcti_sm100.so (declared in include/cti_sm100.h).
+// Thin argument marshalling + thread-local error state; all work is in the kernel files.
+#include "../../include/cti_sm100.h"
+
+#include "cti_common.cuh"
+#include "cti_kernels.h"
+
+#include <cstdarg>
+#include <cstdio>
+
+namespace cti {
+
+namespace {
+thread_local char g_err[512] = {0};
+}
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
+  return 0;
+}
+
+}  // namespace cti
+
+extern "C" {
+
+int cti_version(void) { return 100; }   // 0.1.0
+
+const char* cti_last_error(void) { return cti::g_err; }
+
+int cti_cast_rows_mask(const float* x, void* out_bf16, uint8_t* rowmask, int64_t rows, int cols, void* stream) {
+  return cti::cast_rows_mask(x, static_cast<__nv_bfloat16*>(out_bf16), rowmask, rows, cols,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int cti_wn_pack(const float* v, const float* g, void* w_eff_bf16, float* sumsq, int n_groups, int rows_per_group,
+                int cols, void* stream) {
+  return cti::wn_pack(v, g, static_cast<__nv_bfloat16*>(w_eff_bf16), sumsq, n_groups, rows_per_group, cols,
+                      static_cast<cudaStream_t>(stream));
+}
+
+int cti_wn_grad(const float* dw_eff, const float* v, const float* g, const float* sumsq, float* dv, float* dg,
+                float* dot_ws, int n_groups, int rows_per_group, int cols, void* stream) {
+  return cti::wn_grad(dw_eff, v, g, sumsq, dv, dg, dot_ws, n_groups, rows_per_group, cols,
+                      static_cast<cudaStream_t>(stream));
+}
+
+int cti_gemm_bf16(const void* a, int lda, int a_mn_major, const void* b, int ldb, int b_mn_major, int M, int N, int K,
+                  float alpha, const float* bias, int relu, const void* relu_aux, int ld_aux, void* out_bf16,
+                  float* out_f32, int ldc, int atomic_f32, int k_splits, int tile_n, void* stream) {
+  cti::GemmArgs g;
+  g.a = static_cast<const __nv_bfloat16*>(a);
+  g.b = static_cast<const __nv_bfloat16*>(b);
+  g.M = M; g.N = N; g.K = K;
+  g.lda = lda; g.ldb = ldb;
+  g.a_mn_major = a_mn_major != 0;
+  g.b_mn_major = b_mn_major != 0;
+  g.bias = bias;
+  g.relu_aux = static_cast<const __nv_bfloat16*>(relu_aux);
+  g.ld_aux = ld_aux;
+  g.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16);
+  g.out_f32 = out_f32;
+  g.ldc = ldc;
+  g.relu = relu;
+  g.atomic_f32 = atomic_f32;
+  g.k_splits = k_splits;
+  g.alpha = alpha;
+  g.tile_n = tile_n;
+  return cti::gemm_bf16(g, static_cast<cudaStream_t>(stream));
+}
+
+int cti_act_bwd_bias(const void* dy, int dy_is_bf16, const void* y_bf16, void* dz_bf16, float* dbias_accum,
+                     int64_t rows, int cols, void* stream) {
+  return cti::act_bwd_bias(dy, dy_is_bf16, static_cast<const __nv_bfloat16*>(y_bf16),
+                           static_cast<__nv_bfloat16*>(dz_bf16), dbias_accum, rows, cols,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int cti_masked_softmax_fwd(const float* logits, float* p, int64_t rows, int len, void* stream) {
+  return cti::masked_softmax_fwd(logits, p, rows, len, static_cast<cudaStream_t>(stream));
+}
+
+int cti_masked_softmax_bwd(const float* p, const float* dp, int64_t dp_stride_b, int64_t dp_stride_g,
+                           int64_t dp_stride_e, float* dlogits, int64_t batch, int groups, int len, void* stream) {
+  return cti::masked_softmax_bwd(p, dp, dp_stride_b, dp_stride_g, dp_stride_e, dlogits, batch, groups, len,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+int cti_trilinear_logits_fwd(const void* vc, const void* qc, const void* ac, const void* tpack, const uint8_t* rowmask,
+                             float* logits, int B, int K, int Q, int A, int G, int R, void* stream) {
+  cti::TriDims d{B, K, Q, A, G, R};
+  return cti::trilinear_fwd(static_cast<const __nv_bfloat16*>(vc), static_cast<const __nv_bfloat16*>(qc),
+                            static_cast<const __nv_bfloat16*>(ac), static_cast<const __nv_bfloat16*>(tpack), rowmask,
+                            logits, d, static_cast<cudaStream_t>(stream));
+}
+
+size_t cti_trilinear_logits_bwd_workspace(int B, int K, int Q, int A, int G, int R) {
+  cti::TriDims d{B, K, Q, A, G, R};
+  return cti::trilinear_bwd_workspace(d);
+}
+
+int cti_trilinear_logits_bwd(const void* vc, const void* qc, const void* ac, const void* tpack, const float* dlogits,
+                             void* dzv, void* dzq, void* dza, float* dbv_accum, float* dbq_accum, float* dba_accum,
+                             float* dtpack_accum, void* workspace, size_t workspace_bytes, int B, int K, int Q, int A,
+                             int G, int R, void* stream) {
+  cti::TriDims d{B, K, Q, A, G, R};
+  return cti::trilinear_bwd(static_cast<const __nv_bfloat16*>(vc), static_cast<const __nv_bfloat16*>(qc),
+                            static_cast<const __nv_bfloat16*>(ac), static_cast<const __nv_bfloat16*>(tpack), dlogits,
+                            static_cast<__nv_bfloat16*>(dzv), static_cast<__nv_bfloat16*>(dzq),
+                            static_cast<__nv_bfloat16*>(dza), dbv_accum, dbq_accum, dba_accum, dtpack_accum, workspace,
+                            workspace_bytes, d, static_cast<cudaStream_t>(stream));
+}
+
+int cti_tri_pool_fwd(const void* v, const void* q, const void* a, const float* w, int64_t w_stride_b, float* out,
+                     int B, int K, int Q, int A, int C, void* stream) {
+  cti::PoolDims d{B, K, Q, A, C};
+  return cti::tri_pool_fwd(static_cast<const __nv_bfloat16*>(v), static_cast<const __nv_bfloat16*>(q),
+                           static_cast<const __nv_bfloat16*>(a), w, w_stride_b, out, d,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int cti_tri_pool_bwd(const void* v, const void* q, const void* a, const float* w, int64_t w_stride_b,
+                     const float* dout, void* dzv, void* dzq, void* dza, float* dbv_accum, float* dbq_accum,
+                     float* dba_accum, float* dw, int B, int K, int Q, int A, int C, void* stream) {
+  cti::PoolDims d{B, K, Q, A, C};
+  return cti::tri_pool_bwd(static_cast<const __nv_bfloat16*>(v), static_cast<const __nv_bfloat16*>(q),
+                           static_cast<const __nv_bfloat16*>(a), w, w_stride_b, dout,
+                           static_cast<__nv_bfloat16*>(dzv), static_cast<__nv_bfloat16*>(dzq),
+                           static_cast<__nv_bfloat16*>(dza), dbv_accum, dbq_accum, dba_accum, dw, d,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int cti_bilinear_logits_fwd(const void* vb, const void* qb, const float* hmat, const float* hbias,
+                            const uint8_t* rowmask, float* logits, int B, int K, int Q, int G, int C, void* stream) {
+  cti::BiDims d{B, K, Q, G, C};
+  return cti::bilinear_fwd(static_cast<const __nv_bfloat16*>(vb), static_cast<const __nv_bfloat16*>(qb), hmat, hbias,
+                           rowmask, logits, d, static_cast<cudaStream_t>(stream));
+}
+
+int cti_bilinear_logits_bwd(const void* vb, const void* qb, const float* hmat, const float* dlogits, void* dzv,
+                            void* dzq, float* dbv_accum, float* dbq_accum, float* dhmat_accum, float* dhbias_accum,
+                            int B, int K, int Q, int G, int C, void* stream) {
+  cti::BiDims d{B, K, Q, G, C};
+  return cti::bilinear_bwd(static_cast<const __nv_bfloat16*>(vb), static_cast<const __nv_bfloat16*>(qb), hmat, dlogits,
+                           static_cast<__nv_bfloat16*>(dzv), static_cast<__nv_bfloat16*>(dzq), dbv_accum, dbq_accum,
+                           dhmat_accum, dhbias_accum, d, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

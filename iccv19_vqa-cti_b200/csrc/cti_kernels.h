@@ -1,0 +1,78 @@
+// Internal C++ declarations shared by the kernel translation units and the C-ABI
+// wrapper (cti_capi.cu).  Not part of the public interface: see include/cti_sm100.h.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cti {
+
+struct GemmArgs {
+  const __nv_bfloat16* a = nullptr;   // A: logical (M x K). K-major: [M][lda]; MN-major: [K][lda]
+  const __nv_bfloat16* b = nullptr;   // B: logical (N x K). K-major: [N][ldb]; MN-major: [K][ldb]
+  int M = 0, N = 0, K = 0;
+  int lda = 0, ldb = 0;
+  bool a_mn_major = false, b_mn_major = false;
+  const float* bias = nullptr;
+  const __nv_bfloat16* relu_aux = nullptr;
+  int ld_aux = 0;
+  __nv_bfloat16* out_bf16 = nullptr;
+  float* out_f32 = nullptr;
+  int ldc = 0;
+  int relu = 0;
+  int atomic_f32 = 0;
+  int k_splits = 1;
+  float alpha = 1.f;
+  int tile_n = 0;      // 0 = heuristic, 128 or 256 = forced
+  int max_ctas = 0;    // 0 = one per SM
+};
+int gemm_bf16(const GemmArgs& g, cudaStream_t stream);
+
+// elementwise.cu
+int cast_rows_mask(const float* x, __nv_bfloat16* out, uint8_t* rowmask, long rows, int cols, cudaStream_t s);
+int wn_pack(const float* v, const float* g, __nv_bfloat16* w, float* sumsq, int n_groups, int rows_per_group, int cols,
+            cudaStream_t s);
+int wn_grad(const float* dw, const float* v, const float* g, const float* sumsq, float* dv, float* dg, float* dot_ws,
+            int n_groups, int rows_per_group, int cols, cudaStream_t s);
+int act_bwd_bias(const void* dy, int dy_is_bf16, const __nv_bfloat16* y, __nv_bfloat16* dz, float* dbias, long rows,
+                 int cols, cudaStream_t s);
+
+// softmax.cu
+int masked_softmax_fwd(const float* logits, float* p, long rows, int len, cudaStream_t s);
+int masked_softmax_bwd(const float* p, const float* dp, long dp_row_stride_b, long dp_row_stride_g, long dp_elem_stride,
+                       float* dlogits, long batch, int groups, int len, cudaStream_t s);
+
+// trilinear.cu
+struct TriDims {
+  int B, K, Q, A, G, R;   // d is fixed at 16
+};
+int trilinear_fwd(const __nv_bfloat16* vc, const __nv_bfloat16* qc, const __nv_bfloat16* ac, const __nv_bfloat16* tpack,
+                  const uint8_t* rowmask, float* logits, TriDims d, cudaStream_t s);
+size_t trilinear_bwd_workspace(TriDims d);
+int trilinear_bwd(const __nv_bfloat16* vc, const __nv_bfloat16* qc, const __nv_bfloat16* ac, const __nv_bfloat16* tpack,
+                  const float* dlogits, __nv_bfloat16* dzv, __nv_bfloat16* dzq, __nv_bfloat16* dza, float* dbv,
+                  float* dbq, float* dba, float* dtpack, void* workspace, size_t workspace_bytes, TriDims d,
+                  cudaStream_t s);
+
+// pool.cu  (A == 0 selects the bilinear pooling of BCNet.forward_with_weights)
+struct PoolDims {
+  int B, K, Q, A, C;
+};
+int tri_pool_fwd(const __nv_bfloat16* v, const __nv_bfloat16* q, const __nv_bfloat16* a, const float* w, long w_stride_b,
+                 float* out, PoolDims d, cudaStream_t s);
+int tri_pool_bwd(const __nv_bfloat16* v, const __nv_bfloat16* q, const __nv_bfloat16* a, const float* w, long w_stride_b,
+                 const float* dout, __nv_bfloat16* dzv, __nv_bfloat16* dzq, __nv_bfloat16* dza, float* dbv, float* dbq,
+                 float* dba, float* dw, PoolDims d, cudaStream_t s);
+
+// bilinear.cu
+struct BiDims {
+  int B, K, Q, G, C;
+};
+int bilinear_fwd(const __nv_bfloat16* vb, const __nv_bfloat16* qb, const float* hmat, const float* hbias,
+                 const uint8_t* rowmask, float* logits, BiDims d, cudaStream_t s);
+int bilinear_bwd(const __nv_bfloat16* vb, const __nv_bfloat16* qb, const float* hmat, const float* dlogits,
+                 __nv_bfloat16* dzv, __nv_bfloat16* dzq, float* dbv, float* dbq, float* dhmat, float* dhbias, BiDims d,
+                 cudaStream_t s);
+
+}  // namespace cti

@@ -1,0 +1,210 @@
+// HBM-bound helper kernels of the CTI hot path (sm_100a):
+//   cast_rows_mask : fp32 -> bf16 row cast fused with the zero-row mask of
+//                    reference src/attention.py:55 / :36  (v.abs().sum(2) == 0)
+//   wn_pack        : weight-norm fold  W_eff = V * g/||V||_F -> bf16  (src/fc.py:22,27, dim=None)
+//   wn_grad        : weight-norm backward  dV, dg from dW_eff          
+//   act_bwd_bias   : dz = dy * [y > 0]  (ReLU backward), bf16 out, fused bias gradient
+// All are single-pass, 128-bit vectorised and coalesced; grids are sized from the data.
+#include "cti_common.cuh"
+#include "cti_kernels.h"
+
+namespace cti {
+
+namespace {
+
+// ------------------------------------------------------------------------- //
+__global__ void __launch_bounds__(256) cast_rows_mask_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                             uint8_t* __restrict__ rowmask, long rows, int cols) {
+  const int lane = threadIdx.x & 31;
+  const long row = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * cols;
+  __nv_bfloat16* orow = out + row * cols;
+  bool nz = false;
+  if ((cols & 7) == 0) {
+    const float4* x4 = reinterpret_cast<const float4*>(xr);
+    uint4* o4 = reinterpret_cast<uint4*>(orow);
+    const int n8 = cols >> 3;
+#pragma unroll 4
+    for (int i = lane; i < n8; i += 32) {
+      const float4 a = __ldcs(x4 + 2 * i);
+      const float4 b = __ldcs(x4 + 2 * i + 1);
+      nz |= (a.x != 0.f) | (a.y != 0.f) | (a.z != 0.f) | (a.w != 0.f) | (b.x != 0.f) | (b.y != 0.f) | (b.z != 0.f) |
+            (b.w != 0.f);
+      uint4 u;
+      u.x = pack_bf16x2(a.x, a.y);
+      u.y = pack_bf16x2(a.z, a.w);
+      u.z = pack_bf16x2(b.x, b.y);
+      u.w = pack_bf16x2(b.z, b.w);
+      o4[i] = u;
+    }
+  } else {
+    for (int i = lane; i < cols; i += 32) {
+      const float f = xr[i];
+      nz |= (f != 0.f);
+      orow[i] = __float2bfloat16(f);
+    }
+  }
+  if (rowmask != nullptr) {
+    const unsigned any = __ballot_sync(0xffffffffu, nz);
+    if (lane == 0) rowmask[row] = (any == 0u) ? 1 : 0;
+  }
+}
+
+// ------------------------------------------------------------------------- //
+// weight norm.  A "group" is rows_per_group consecutive rows of the (n_groups*rows_per_group, cols)
+// matrix; each group has its own scalar g and Frobenius norm (one group = one nn.Linear).
+constexpr int kSeg = 4096;   // elements reduced by one block
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ v, const float* __restrict__ w2,
+                                                    float* __restrict__ acc, long group_elems, int segs_per_group) {
+  // acc[group] += sum v*w2 (w2 == v for the squared norm, == dW for the <dW,V> dot)
+  const int group = blockIdx.x / segs_per_group;
+  const int seg = blockIdx.x - group * segs_per_group;
+  const long base = static_cast<long>(group) * group_elems;
+  const long lo = static_cast<long>(seg) * kSeg;
+  const long hi = min(lo + kSeg, group_elems);
+  float s = 0.f;
+  for (long i = lo + threadIdx.x; i < hi; i += blockDim.x) s += v[base + i] * w2[base + i];
+  s = warp_sum(s);
+  __shared__ float part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) atomicAdd(acc + group, t);
+  }
+}
+
+__global__ void __launch_bounds__(256) wn_scale_kernel(const float* __restrict__ v, const float* __restrict__ g,
+                                                       const float* __restrict__ sumsq, __nv_bfloat16* __restrict__ w,
+                                                       long group_elems, long total) {
+  const long i = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i >= total) return;
+  const int group = static_cast<int>(i / group_elems);   // group_elems % 4 == 0 is required by the caller
+  const float s = g[group] * rsqrtf(sumsq[group]);
+  const float4 f = *reinterpret_cast<const float4*>(v + i);
+  uint2 u;
+  u.x = pack_bf16x2(f.x * s, f.y * s);
+  u.y = pack_bf16x2(f.z * s, f.w * s);
+  *reinterpret_cast<uint2*>(w + i) = u;
+}
+
+__global__ void __launch_bounds__(256) wn_grad_kernel(const float* __restrict__ dw, const float* __restrict__ v,
+                                                      const float* __restrict__ g, const float* __restrict__ sumsq,
+                                                      const float* __restrict__ dot, float* __restrict__ dv,
+                                                      float* __restrict__ dg, long group_elems, long total) {
+  const long i = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i >= total) return;
+  const int group = static_cast<int>(i / group_elems);
+  const float n2 = sumsq[group];
+  const float rn = rsqrtf(n2);
+  const float s = g[group] * rn;          // g / ||V||
+  const float dt = dot[group];            // <dW_eff, V>
+  const float c = dt / n2;
+  const float4 a = *reinterpret_cast<const float4*>(dw + i);
+  const float4 b = *reinterpret_cast<const float4*>(v + i);
+  float4 o;
+  o.x = s * (a.x - c * b.x);
+  o.y = s * (a.y - c * b.y);
+  o.z = s * (a.z - c * b.z);
+  o.w = s * (a.w - c * b.w);
+  *reinterpret_cast<float4*>(dv + i) = o;
+  if (i % group_elems == 0) dg[group] = dt * rn;
+}
+
+// ------------------------------------------------------------------------- //
+// dz[m,n] = dy[m,n] * (y[m,n] > 0);  dbias[n] += sum_m dz[m,n].
+// Block = 256 threads x 2 columns = 512-column slab, 32 rows per block.
+constexpr int kActRows = 32;
+
+template <bool DY_BF16>
+__global__ void __launch_bounds__(256) act_bwd_bias_kernel(const void* __restrict__ dy_, const __nv_bfloat16* __restrict__ y,
+                                                           __nv_bfloat16* __restrict__ dz, float* __restrict__ dbias,
+                                                           long rows, int cols) {
+  const int c = (blockIdx.x * 256 + threadIdx.x) * 2;
+  if (c >= cols) return;   // cols is even (checked by the caller)
+  const long r0 = static_cast<long>(blockIdx.y) * kActRows;
+  const long r1 = min(r0 + kActRows, rows);
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
+  for (long r = r0; r < r1; ++r) {
+    const long off = r * cols + c;
+    float2 d;
+    if (DY_BF16) {
+      d = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(static_cast<const __nv_bfloat16*>(dy_) + off));
+    } else {
+      d = *reinterpret_cast<const float2*>(static_cast<const float*>(dy_) + off);
+    }
+    if (y != nullptr) {
+      const float2 yy = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(y + off));
+      if (!(yy.x > 0.f)) d.x = 0.f;
+      if (!(yy.y > 0.f)) d.y = 0.f;
+    }
+    if (dz != nullptr) *reinterpret_cast<uint32_t*>(dz + off) = pack_bf16x2(d.x, d.y);
+    s0 += d.x;
+    s1 += d.y;
+  }
+  if (dbias != nullptr) {
+    atomicAdd(dbias + c, s0);
+    atomicAdd(dbias + c + 1, s1);
+  }
+}
+
+}  // namespace
+
+int cast_rows_mask(const float* x, __nv_bfloat16* out, uint8_t* rowmask, long rows, int cols, cudaStream_t s) {
+  CTI_REQUIRE(rows >= 0 && cols > 0, "cast_rows_mask: bad shape rows=%ld cols=%d", rows, cols);
+  if (rows == 0) return 0;
+  CTI_REQUIRE(((cols & 7) != 0) || (((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0),
+              "cast_rows_mask: buffers must be 16-byte aligned");
+  const int warps = 8;
+  const long blocks = (rows + warps - 1) / warps;
+  CTI_REQUIRE(blocks < (1l << 31), "cast_rows_mask: too many rows");
+  cast_rows_mask_kernel<<<(unsigned)blocks, warps * 32, 0, s>>>(x, out, rowmask, rows, cols);
+  return check_launch("cast_rows_mask_kernel");
+}
+
+int wn_pack(const float* v, const float* g, __nv_bfloat16* w, float* sumsq, int n_groups, int rows_per_group, int cols,
+            cudaStream_t s) {
+  const long ge = static_cast<long>(rows_per_group) * cols;
+  const long total = ge * n_groups;
+  CTI_REQUIRE(n_groups > 0 && ge > 0, "wn_pack: empty weight");
+  CTI_REQUIRE(ge % 4 == 0, "wn_pack: group size %ld must be a multiple of 4", ge);
+  cudaError_t e = cudaMemsetAsync(sumsq, 0, sizeof(float) * n_groups, s);
+  if (e != cudaSuccess) { set_error("wn_pack memset: %s", cudaGetErrorString(e)); return (int)e; }
+  const int segs = (int)((ge + kSeg - 1) / kSeg);
+  sumsq_kernel<<<n_groups * segs, 256, 0, s>>>(v, v, sumsq, ge, segs);
+  int rc = check_launch("sumsq_kernel");
+  if (rc) return rc;
+  wn_scale_kernel<<<(unsigned)((total / 4 + 255) / 256), 256, 0, s>>>(v, g, sumsq, w, ge, total);
+  return check_launch("wn_scale_kernel");
+}
+
+int wn_grad(const float* dw, const float* v, const float* g, const float* sumsq, float* dv, float* dg, float* dot_ws,
+            int n_groups, int rows_per_group, int cols, cudaStream_t s) {
+  const long ge = static_cast<long>(rows_per_group) * cols;
+  const long total = ge * n_groups;
+  CTI_REQUIRE(n_groups > 0 && ge > 0 && ge % 4 == 0, "wn_grad: bad group size %ld", ge);
+  cudaError_t e = cudaMemsetAsync(dot_ws, 0, sizeof(float) * n_groups, s);
+  if (e != cudaSuccess) { set_error("wn_grad memset: %s", cudaGetErrorString(e)); return (int)e; }
+  const int segs = (int)((ge + kSeg - 1) / kSeg);
+  sumsq_kernel<<<n_groups * segs, 256, 0, s>>>(dw, v, dot_ws, ge, segs);
+  int rc = check_launch("wn_dot_kernel");
+  if (rc) return rc;
+  wn_grad_kernel<<<(unsigned)((total / 4 + 255) / 256), 256, 0, s>>>(dw, v, g, sumsq, dot_ws, dv, dg, ge, total);
+  return check_launch("wn_grad_kernel");
+}
+
+int act_bwd_bias(const void* dy, int dy_is_bf16, const __nv_bfloat16* y, __nv_bfloat16* dz, float* dbias, long rows,
+                 int cols, cudaStream_t s) {
+  CTI_REQUIRE(rows > 0 && cols > 0 && (cols % 2) == 0, "act_bwd_bias: bad shape rows=%ld cols=%d (cols must be even)", rows,
+              cols);
+  dim3 grid((cols / 2 + 255) / 256, (unsigned)((rows + kActRows - 1) / kActRows));
+  if (dy_is_bf16) act_bwd_bias_kernel<true><<<grid, 256, 0, s>>>(dy, y, dz, dbias, rows, cols);
+  else            act_bwd_bias_kernel<false><<<grid, 256, 0, s>>>(dy, y, dz, dbias, rows, cols);
+  return check_launch("act_bwd_bias_kernel");
+}
+
+}  // namespace cti

@@ -1,0 +1,378 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> shared memory (128B swizzle)
+// -> tcgen05.mma (UMMA 128 x BLOCK_N x 16, cta_group::1) -> fp32 accumulators in TMEM
+// -> epilogue warps (tcgen05.ld) -> bias / ReLU / ReLU-mask / split-K atomics -> global.
+//
+// One kernel covers every dense projection on the CTI hot path:
+//   forward   Y  = act(X W_eff^T + b)          A = X   (K-major), B = W_eff (K-major)
+//   dgrad     dX = dZ W_eff                    A = dZ  (K-major), B = W_eff (MN-major)
+//   wgrad     dW = dZ^T X   (split over rows)  A = dZ  (MN-major), B = X    (MN-major)
+// which is the work of reference src/fc.py:33-34 (FCNet.forward) and its autograd.
+//
+// Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
+// allocator, warps 4..7 = epilogue (TMEM lane quarter = warp % 4).
+#include "cti_common.cuh"
+#include "cti_kernels.h"
+
+#include <cudaTypedefs.h>
+
+namespace cti {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;          // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kGemmThreads = 256;
+constexpr int kEpiWarp0 = 4;
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int ACC_STAGES = 2;
+  static constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;            // 512 or 256 (power of two)
+  static constexpr int BAR_BYTES = (2 * STAGES + 2 * ACC_STAGES) * 8 + 16;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // +1024: manual alignment
+};
+
+struct GemmDevParams {
+  int M, N, K;
+  int num_m_blocks, num_n_blocks, num_k_blocks, k_splits, k_blocks_per_split;
+  const float* bias;            // [N] or null
+  const __nv_bfloat16* relu_aux;   // [M, ld_aux] or null: out *= (aux > 0)
+  __nv_bfloat16* out_bf16;      // [M, ldc] or null
+  float* out_f32;               // [M, ldc] or null
+  int ldc, ld_aux;
+  int relu;                     // apply max(0, .) after bias
+  int atomic_f32;               // out_f32 += acc (split-K reduction)
+  float alpha;                  // acc scale applied before bias
+};
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmDevParams p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + Cfg::ACC_STAGES + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 2 * Cfg::ACC_STAGES);
+  auto smem_a = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
+  auto smem_b = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < Cfg::ACC_STAGES; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
+  const int total_tiles = tiles_mn * p.k_splits;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int ks = tile / tiles_mn;
+        const int mn = tile - ks * tiles_mn;
+        const int m_blk = mn / p.num_n_blocks;
+        const int n_blk = mn - m_blk * p.num_n_blocks;
+        const int kb0 = ks * p.k_blocks_per_split;
+        const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          if (!A_MN) {
+            tma_load_2d(&tmap_a, full_bar(stage), smem_a(stage), kb * BLOCK_K, m_blk * BLOCK_M);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BLOCK_M / 64; ++i)
+              tma_load_2d(&tmap_a, full_bar(stage), smem_a(stage) + i * 8192, m_blk * BLOCK_M + i * 64, kb * BLOCK_K);
+          }
+          if (!B_MN) {
+            tma_load_2d(&tmap_b, full_bar(stage), smem_b(stage), kb * BLOCK_K, n_blk * BLOCK_N);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BLOCK_N / 64; ++i)
+              tma_load_2d(&tmap_b, full_bar(stage), smem_b(stage) + i * 8192, n_blk * BLOCK_N + i * 64, kb * BLOCK_K);
+          }
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer --------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int ks = tile / tiles_mn;
+        const int kb0 = ks * p.k_blocks_per_split;
+        const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // K-major: advance 16 elements = 32 B inside the swizzle row.
+            // MN-major: advance 16 K-rows = 2 swizzle atoms = 2048 B.
+            const uint64_t da = A_MN ? make_smem_desc_sw128(smem_a(stage) + k * 2048, 8192, 1024)
+                                     : make_smem_desc_sw128(smem_a(stage) + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc_sw128(smem_b(stage) + k * 2048, 8192, 1024)
+                                     : make_smem_desc_sw128(smem_b(stage) + k * 32, 16, 1024);
+            umma_bf16_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));               // frees the smem slot when the MMAs retire
+          if (kb == kb1 - 1) umma_commit(tfull_bar(acc));   // accumulator complete
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        if (++acc == Cfg::ACC_STAGES) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ------------------------------ epilogue ----------------------------------
+    const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter+32)
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int ks = tile / tiles_mn;
+      const int mn = tile - ks * tiles_mn;
+      const int m_blk = mn / p.num_n_blocks;
+      const int n_blk = mn - m_blk * p.num_n_blocks;
+      const bool empty_split = (ks * p.k_blocks_per_split >= p.num_k_blocks);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const int row = m_blk * BLOCK_M + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + c * 32, r);
+        tmem_wait_ld();
+        const int col0 = n_blk * BLOCK_N + c * 32;
+        if (!row_ok || col0 >= p.N || empty_split) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+        const size_t off = static_cast<size_t>(row) * p.ldc + col0;
+        if (p.atomic_f32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) atomicAdd(p.out_f32 + off + j, v[j]);
+          continue;
+        }
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        const bool full = (col0 + 32 <= p.N);
+        if (p.relu_aux != nullptr) {
+          const __nv_bfloat16* aux = p.relu_aux + static_cast<size_t>(row) * p.ld_aux + col0;
+          if (full && (p.ld_aux % 8 == 0)) {
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              const uint4 a = __ldg(reinterpret_cast<const uint4*>(aux) + j8);
+              const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float2 f = unpack_bf16x2(w[t]);
+                if (!(f.x > 0.f)) v[j8 * 8 + 2 * t] = 0.f;
+                if (!(f.y > 0.f)) v[j8 * 8 + 2 * t + 1] = 0.f;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N && !(__bfloat162float(aux[j]) > 0.f)) v[j] = 0.f;
+          }
+        }
+        if (p.out_bf16 != nullptr) {
+          __nv_bfloat16* o = p.out_bf16 + off;
+          if (full && (p.ldc % 8 == 0)) {
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              uint4 u;
+              u.x = pack_bf16x2(v[j8 * 8 + 0], v[j8 * 8 + 1]);
+              u.y = pack_bf16x2(v[j8 * 8 + 2], v[j8 * 8 + 3]);
+              u.z = pack_bf16x2(v[j8 * 8 + 4], v[j8 * 8 + 5]);
+              u.w = pack_bf16x2(v[j8 * 8 + 6], v[j8 * 8 + 7]);
+              reinterpret_cast<uint4*>(o)[j8] = u;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) o[j] = __float2bfloat16(v[j]);
+          }
+        }
+        if (p.out_f32 != nullptr) {
+          float* o = p.out_f32 + off;
+          if (full && (p.ldc % 4 == 0)) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4)
+              reinterpret_cast<float4*>(o)[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) o[j] = v[j];
+          }
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      if (++acc == Cfg::ACC_STAGES) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ----------------------------- host side ---------------------------------- //
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess) return nullptr;
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map: `inner` contiguous elements per row, `outer` rows, row pitch ld elements.
+int make_tmap(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld_elems, uint32_t box_inner,
+              uint32_t box_outer) {
+  auto fn = get_encode_fn();
+  CTI_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  CTI_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand must be 16-byte aligned");
+  CTI_REQUIRE((ld_elems * 2) % 16 == 0, "TMA operand row pitch must be a multiple of 16 bytes (ld=%llu)",
+              (unsigned long long)ld_elems);
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstride[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CTI_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  CUtensorMap ta, tb;
+  int rc;
+  if (!A_MN) rc = make_tmap(&ta, g.a, g.K, g.M, g.lda, BLOCK_K, BLOCK_M);
+  else       rc = make_tmap(&ta, g.a, g.M, g.K, g.lda, 64, BLOCK_K);
+  if (rc) return rc;
+  if (!B_MN) rc = make_tmap(&tb, g.b, g.K, g.N, g.ldb, BLOCK_K, BLOCK_N);
+  else       rc = make_tmap(&tb, g.b, g.N, g.K, g.ldb, 64, BLOCK_K);
+  if (rc) return rc;
+
+  GemmDevParams p;
+  p.M = g.M; p.N = g.N; p.K = g.K;
+  p.num_m_blocks = (g.M + BLOCK_M - 1) / BLOCK_M;
+  p.num_n_blocks = (g.N + BLOCK_N - 1) / BLOCK_N;
+  p.num_k_blocks = (g.K + BLOCK_K - 1) / BLOCK_K;
+  int splits = g.k_splits < 1 ? 1 : g.k_splits;
+  if (splits > p.num_k_blocks) splits = p.num_k_blocks;
+  p.k_blocks_per_split = (p.num_k_blocks + splits - 1) / splits;
+  p.k_splits = (p.num_k_blocks + p.k_blocks_per_split - 1) / p.k_blocks_per_split;   // no empty splits
+  p.bias = g.bias; p.relu_aux = g.relu_aux; p.out_bf16 = g.out_bf16; p.out_f32 = g.out_f32;
+  p.ldc = g.ldc; p.ld_aux = g.ld_aux; p.relu = g.relu; p.atomic_f32 = g.atomic_f32; p.alpha = g.alpha;
+
+  static bool attr_set = false;
+  auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(gemm smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+  const long total = (long)p.num_m_blocks * p.num_n_blocks * p.k_splits;
+  int sms = g.max_ctas > 0 ? g.max_ctas : kNumSMsB200;
+  const int grid = (int)(total < sms ? total : sms);
+  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  return check_launch("gemm_bf16_kernel");
+}
+
+}  // namespace
+
+int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
+  CTI_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
+  CTI_REQUIRE(g.out_bf16 != nullptr || g.out_f32 != nullptr, "gemm: no output buffer");
+  CTI_REQUIRE(!g.atomic_f32 || g.out_f32 != nullptr, "gemm: split-K accumulation needs an fp32 output");
+  CTI_REQUIRE(g.atomic_f32 || g.k_splits <= 1, "gemm: k_splits > 1 needs atomic_f32");
+  // Small-N problems and small grids use the 128-wide tile so more CTAs get work.
+  const long tiles256 = (long)((g.M + BLOCK_M - 1) / BLOCK_M) * ((g.N + 255) / 256) * (g.k_splits < 1 ? 1 : g.k_splits);
+  const bool use256 = (g.tile_n == 256) || (g.tile_n == 0 && g.N >= 256 && tiles256 >= 2 * kNumSMsB200);
+  if (use256) {
+    if (!g.a_mn_major && !g.b_mn_major) return launch_gemm<256, false, false>(g, stream);
+    if (!g.a_mn_major && g.b_mn_major) return launch_gemm<256, false, true>(g, stream);
+    if (g.a_mn_major && g.b_mn_major) return launch_gemm<256, true, true>(g, stream);
+  } else {
+    if (!g.a_mn_major && !g.b_mn_major) return launch_gemm<128, false, false>(g, stream);
+    if (!g.a_mn_major && g.b_mn_major) return launch_gemm<128, false, true>(g, stream);
+    if (g.a_mn_major && g.b_mn_major) return launch_gemm<128, true, true>(g, stream);
+  }
+  set_error("gemm: A MN-major with B K-major is not instantiated");
+  return -1;
+}
+
+}  // namespace cti

@@ -1,0 +1,121 @@
+/* cti_sm100.h -- C ABI of libcti_sm100.so, the sm_100a (B200) kernels behind the drop-in
+ * FCNet / TCNet / TriAttention / BCNet / BiAttention modules.
+ *
+ * The reference (aioz-ai/ICCV19_VQA-CTI) is pure PyTorch: its "FFI" for this path is the set of
+ * ATen calls its five hot-path files make.  Each entry point below names the reference call
+ * site(s) it replaces (file:line under the reference tree).
+ *
+ * Conventions
+ *   - Plain C: raw device pointers and sizes only; no torch / ATen / pybind types.
+ *   - bf16 buffers are passed as `const void*` / `void*` (2 bytes per element, row-major).
+ *   - The caller owns every buffer (inputs, outputs, saved tensors, workspace) and keeps it
+ *     alive until `stream` has passed the call.  The library allocates nothing persistent.
+ *   - All launches are asynchronous on `stream` (a cudaStream_t passed as void*); no host sync.
+ *   - Return value: 0 = ok; negative = argument/shape/alignment error, nothing was launched;
+ *     positive = the cudaError_t reported by the launch.  `cti_last_error()` returns a
+ *     thread-local message for the last non-zero return on this thread.  Nothing throws or exits.
+ *   - Buffers named `*_accum` are accumulated into with atomics and must be zeroed by the caller.
+ *   - The device is the current device of the calling thread (one process per GPU for DP).
+ */
+#ifndef CTI_SM100_H_
+#define CTI_SM100_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Library version: major * 10000 + minor * 100 + patch. */
+int cti_version(void);
+/* Message for the last failing call on this thread ("" if none). */
+const char* cti_last_error(void);
+
+/* ---- row cast + zero-row mask -------------------------------------------------------------
+ * out[r,:] = bf16(x[r,:]);  rowmask[r] = (sum_c |x[r,c]| == 0)   (rowmask may be NULL)
+ * replaces: src/attention.py:55 and :36  `(0 == v.abs().sum(2))`, plus the fp32->bf16 operand cast. */
+int cti_cast_rows_mask(const float* x, void* out_bf16, uint8_t* rowmask, int64_t rows, int cols, void* stream);
+
+/* ---- weight-norm fold ----------------------------------------------------------------------
+ * A matrix of n_groups stacked nn.Linear weights, each (rows_per_group, cols), each with its own
+ * scalar g:  sumsq[i] = ||V_i||_F^2,  W_eff_i = bf16(V_i * g_i / ||V_i||_F).
+ * replaces: torch.nn.utils.weight_norm(nn.Linear, dim=None) as used by src/fc.py:22,27. */
+int cti_wn_pack(const float* v, const float* g, void* w_eff_bf16, float* sumsq, int n_groups, int rows_per_group,
+                int cols, void* stream);
+/* Backward of the fold: given dW_eff (fp32) returns dV and dg.  dot_ws: n_groups floats of scratch. */
+int cti_wn_grad(const float* dw_eff, const float* v, const float* g, const float* sumsq, float* dv, float* dg,
+                float* dot_ws, int n_groups, int rows_per_group, int cols, void* stream);
+
+/* ---- dense projection GEMM (tcgen05 / TMEM / TMA) --------------------------------------------
+ * C[M,N] = epilogue(alpha * A[M,K] . B[N,K]^T)
+ *   a_mn_major = 0: A stored [M][lda] (K contiguous);  1: stored [K][lda] (M contiguous)
+ *   b_mn_major = 0: B stored [N][ldb] (K contiguous);  1: stored [K][ldb] (N contiguous)
+ *   epilogue: + bias[N] (if non-NULL); ReLU (if relu); * (relu_aux[M,ld_aux] > 0) (if non-NULL);
+ *             store bf16 and/or fp32 with pitch ldc; or, with atomic_f32, out_f32 += result
+ *             (k_splits > 1 splits the K loop over CTAs; needs atomic_f32).
+ * replaces: nn.Linear inside FCNet.forward (src/fc.py:33-34), nn.ReLU (src/fc.py:29), and the
+ *           autograd dgrad / wgrad of the same layer. */
+int cti_gemm_bf16(const void* a, int lda, int a_mn_major, const void* b, int ldb, int b_mn_major, int M, int N, int K,
+                  float alpha, const float* bias, int relu, const void* relu_aux, int ld_aux, void* out_bf16,
+                  float* out_f32, int ldc, int atomic_f32, int k_splits, int tile_n, void* stream);
+
+/* ---- activation backward + bias gradient ----------------------------------------------------
+ * dz = dy * (y > 0) (y may be NULL: no activation), written as bf16 (dz may be NULL);
+ * dbias_accum[n] += sum_m dz[m,n].  dy is fp32 (dy_is_bf16 = 0) or bf16.
+ * replaces: autograd of nn.ReLU + the bias term of nn.Linear (src/fc.py:27-29). */
+int cti_act_bwd_bias(const void* dy, int dy_is_bf16, const void* y_bf16, void* dz_bf16, float* dbias_accum,
+                     int64_t rows, int cols, void* stream);
+
+/* ---- masked softmax over the flattened attention domain ---------------------------------------
+ * rows of `len` contiguous floats; masked positions already hold -inf.
+ * replaces: torch.softmax in src/attention.py:58 (TriAttention) and :39 (BiAttention). */
+int cti_masked_softmax_fwd(const float* logits, float* p, int64_t rows, int len, void* stream);
+/* dlogits = p * (dp - sum(p*dp)); p, dlogits are (batch, groups, len) contiguous; dp[b,g,e] is read at
+ * dp + b*dp_stride_b + g*dp_stride_g + e*dp_stride_e (element strides). */
+int cti_masked_softmax_bwd(const float* p, const float* dp, int64_t dp_stride_b, int64_t dp_stride_g,
+                           int64_t dp_stride_e, float* dlogits, int64_t batch, int groups, int len, void* stream);
+
+/* ---- trilinear logit map ----------------------------------------------------------------------
+ * vc (B,K,R*16), qc (B,Q,R*16), ac (B,A,R*16) bf16: the per-rank projections, column = r*16 + i.
+ * tpack (R,16,16*G*16) bf16: T_eff[r][l][(i,g,j)] (see DESIGN.md for the T_g -> T_eff permutation).
+ * logits (B,G,K,Q,A) fp32, -inf where rowmask[b*K+k] != 0 (rowmask may be NULL).
+ * replaces: the rank loop of TCNet.forward (src/tc.py:46-52) incl. Tensor.ModeProduct
+ *           (src/Tensor.py:3-19) and the masked_fill_ of src/attention.py:55-56. */
+int cti_trilinear_logits_fwd(const void* vc, const void* qc, const void* ac, const void* tpack, const uint8_t* rowmask,
+                             float* logits, int B, int K, int Q, int A, int G, int R, void* stream);
+size_t cti_trilinear_logits_bwd_workspace(int B, int K, int Q, int A, int G, int R);
+/* dz* are the PRE-activation gradients of the per-rank projections (ReLU masks applied);
+ * db*_accum (R*16 each) and dtpack_accum (same shape as tpack, fp32) are accumulated into. */
+int cti_trilinear_logits_bwd(const void* vc, const void* qc, const void* ac, const void* tpack, const float* dlogits,
+                             void* dzv, void* dzq, void* dza, float* dbv_accum, float* dbq_accum, float* dba_accum,
+                             float* dtpack_accum, void* workspace, size_t workspace_bytes, int B, int K, int Q, int A,
+                             int G, int R, void* stream);
+
+/* ---- attention-weighted pooling ---------------------------------------------------------------
+ * out[b,c] = sum_{k,q,a} V[b,k,c] w[b,k,q,a] Qp[b,q,c] Ap[b,a,c];  A = 0 drops the Ap factor.
+ * v (B,K,C), q (B,Q,C), a (B,A,C) bf16; w: (K,Q,A) contiguous per sample, samples w_stride_b floats apart.
+ * replaces: the einsum of TCNet.forward_with_weights (src/tc.py:59) and the two matmuls of
+ *           BCNet.forward_with_weights (src/bc.py:73). */
+int cti_tri_pool_fwd(const void* v, const void* q, const void* a, const float* w, int64_t w_stride_b, float* out,
+                     int B, int K, int Q, int A, int C, void* stream);
+/* dz* pre-activation gradients (ReLU masks of v, q, a applied); db*_accum (C each) accumulated into;
+ * dw (B,K,Q,A) contiguous fp32. */
+int cti_tri_pool_bwd(const void* v, const void* q, const void* a, const float* w, int64_t w_stride_b,
+                     const float* dout, void* dzv, void* dzq, void* dza, float* dbv_accum, float* dbq_accum,
+                     float* dba_accum, float* dw, int B, int K, int Q, int A, int C, void* stream);
+
+/* ---- bilinear attention logits (BAN) ------------------------------------------------------------
+ * logits[b,g,k,q] = sum_c Vb[b,k,c] h[g,c] Qb[b,q,c] + hbias[g]; -inf where rowmask[b*K+k] != 0.
+ * vb (B,K,C), qb (B,Q,C) bf16; hmat (G,C), hbias (G) fp32; logits (B,G,K,Q) fp32.
+ * replaces: BCNet.forward, h_out <= 32 branch (src/bc.py:52-58) and masked_fill_ of src/attention.py:36-37. */
+int cti_bilinear_logits_fwd(const void* vb, const void* qb, const float* hmat, const float* hbias,
+                            const uint8_t* rowmask, float* logits, int B, int K, int Q, int G, int C, void* stream);
+int cti_bilinear_logits_bwd(const void* vb, const void* qb, const float* hmat, const float* dlogits, void* dzv,
+                            void* dzq, float* dbv_accum, float* dbq_accum, float* dhmat_accum, float* dhbias_accum,
+                            int B, int K, int Q, int G, int C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTI_SM100_H_ */
