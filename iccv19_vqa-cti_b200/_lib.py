@@ -1,0 +1,68 @@
+"""ctypes binding of libcti_sm100.so (C ABI declared in include/cti_sm100.h).
+
+This is the only place the shared library is opened.  There is no fallback: if the
+library is missing or a call fails, a RuntimeError is raised (the reference trainer's
+OOM-skip logic, src/MC/trainer.py:184-190, relies on RuntimeError).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcti_sm100.so")
+
+# name -> (restype, argtypes); mirrors include/cti_sm100.h one to one.
+_P = c_void_p
+SIGNATURES = {
+    "cti_version": (c_int, []),
+    "cti_last_error": (c_char_p, []),
+    "cti_cast_rows_mask": (c_int, [_P, _P, _P, c_int64, c_int, _P]),
+    "cti_wn_pack": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "cti_wn_grad": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "cti_gemm_bf16": (c_int, [_P, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_float, _P, c_int, _P, c_int,
+                              _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "cti_act_bwd_bias": (c_int, [_P, c_int, _P, _P, _P, c_int64, c_int, _P]),
+    "cti_masked_softmax_fwd": (c_int, [_P, _P, c_int64, c_int, _P]),
+    "cti_masked_softmax_bwd": (c_int, [_P, _P, c_int64, c_int64, c_int64, _P, c_int64, c_int, c_int, _P]),
+    "cti_trilinear_logits_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "cti_trilinear_logits_bwd_workspace": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "cti_trilinear_logits_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, c_int, c_int,
+                                         c_int, c_int, c_int, c_int, _P]),
+    "cti_tri_pool_fwd": (c_int, [_P, _P, _P, _P, c_int64, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "cti_tri_pool_bwd": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int,
+                                 c_int, _P]),
+    "cti_bilinear_logits_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "cti_bilinear_logits_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Open libcti_sm100.so (once) and attach prototypes.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the CTI sm_100a kernels are not built. Run "
+            "`python __graft_entry__.py build` (or iccv19_vqa-cti_b200/build.py); there is no CPU/PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header / library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().cti_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        kind = "argument error" if rc < 0 else f"CUDA error {rc}"
+        raise RuntimeError(f"{what}: {kind}: {last_error()}")

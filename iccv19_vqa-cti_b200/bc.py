@@ -1,0 +1,84 @@
+"""Drop-in for the reference's ``src/bc.py``: ``BCNet`` -- the bilinear connect network of BAN
+(reference src/bc.py:16-78) that the distilled student uses.
+
+``forward`` implements the ``h_out <= 32`` branch (the only one the shipped builders reach, via
+``BiAttention``) as one fused kernel that applies ``h_mat[g]`` on the fly; ``forward_with_weights``
+is the bilinear pooling.  The ``h_out is None`` and ``h_out > 32`` branches keep their parameters
+(``h_net``) for state_dict compatibility but are not part of the accelerated path and raise.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import functions as F_
+from .fc import FCNet, WNLinear, cast_features, check_dropout
+
+
+class BCNet(nn.Module):
+    """Simple class for non-linear bilinear connect network (same signature as reference src/bc.py:19)."""
+
+    def __init__(self, v_dim, q_dim, h_dim, h_out, act='ReLU', dropout=[.2, .5], k=1):
+        super().__init__()
+        self.c = 32
+        self.k = k
+        self.v_dim = v_dim
+        self.q_dim = q_dim
+        self.h_dim = h_dim
+        self.h_out = h_out
+
+        self.v_net = FCNet([v_dim, h_dim * self.k], act=act, dropout=dropout[0])
+        self.q_net = FCNet([q_dim, h_dim * self.k], act=act, dropout=dropout[0])
+        self.dropout = nn.Dropout(dropout[1])                     # attention dropout on v_ (src/bc.py:53)
+        if 1 < k:
+            self.p_net = nn.AvgPool1d(self.k, stride=self.k)
+        if h_out is None:
+            pass
+        elif h_out <= self.c:
+            self.h_mat = nn.Parameter(torch.Tensor(1, h_out, 1, h_dim * self.k).normal_())
+            self.h_bias = nn.Parameter(torch.Tensor(1, h_out, 1, 1).normal_())
+        else:
+            self.h_net = WNLinear(h_dim * self.k, h_out)
+
+    def _effective_h_mat(self):
+        """h_mat, or its weight-normed form when BiAttention re-parametrised it (src/attention.py:19-20)."""
+        if 'h_mat_v' in self._parameters:
+            hv = self.h_mat_v
+            return hv * (self.h_mat_g / hv.norm())                 # 2*3072 elements: parameter plumbing
+        return self.h_mat
+
+    def _logits(self, v, q, rowmask_wanted: bool):
+        if self.h_out is None or self.h_out > self.c:
+            raise NotImplementedError("BCNet.forward: only the h_out <= 32 branch (reference src/bc.py:52-58) is "
+                                      "on the accelerated CTI/BAN path")
+        B, K = v.shape[0], v.shape[1]
+        Q = q.shape[1]
+        G, C = self.h_out, self.h_dim * self.k
+        v_bf16, rowmask = cast_features(v)
+        lv, pv = self.v_net.single()
+        lq, pq = self.q_net.single()
+        for p in (pv, pq, self.dropout.p):
+            check_dropout(self, p)
+        return F_.BiLogitsFn.apply((B, K, Q, G, C), [lv.packed(), lq.packed()], v_bf16,
+                                   rowmask if rowmask_wanted else None, q, self._effective_h_mat(), self.h_bias,
+                                   lv.weight_v, lv.weight_g, lv.bias, lq.weight_v, lq.weight_g, lq.bias)
+
+    def forward(self, v, q):
+        """v (B,K,v_dim), q (B,Q,q_dim) -> bilinear logits (B, h_out, K, Q)."""
+        return self._logits(v, q, False)
+
+    def forward_with_weights(self, v, q, w):
+        """Attention-weighted bilinear pooling: w (B,K,Q) -> (B, h_dim) (sum-pooled over k channel groups)."""
+        B, K = v.shape[0], v.shape[1]
+        Q = q.shape[1]
+        C = self.h_dim * self.k
+        v_bf16, _ = cast_features(v)
+        lv, pv = self.v_net.single()
+        lq, pq = self.q_net.single()
+        for p in (pv, pq):
+            check_dropout(self, p)
+        out = F_.PoolFn.apply((B, K, Q, 0, C), [lv.packed(), lq.packed()], v_bf16, q, None, w, lv.weight_v,
+                              lv.weight_g, lv.bias, lq.weight_v, lq.weight_g, lq.bias)
+        if 1 < self.k:
+            out = out.view(B, -1, self.k).sum(2)                   # AvgPool1d(k) * k (src/bc.py:75-77)
+        return out

@@ -1,0 +1,345 @@
+"""torch.autograd.Function wrappers: each one is a whole reference module call (forward and the
+hand-written backward) expressed as a sequence of C-ABI kernel launches.  No torch math op runs
+on activations here; torch supplies memory, streams and the autograd tape.
+
+Backward formulas: SURVEY.md appendix B (each verified against the reference's autograd there).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch.autograd import Function
+
+from . import kernels as K_
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+# --------------------------------------------------------------------------- #
+# one weight-normed linear layer group (reference src/fc.py:22-29): helpers, not autograd
+# --------------------------------------------------------------------------- #
+class Packed:
+    """bf16 effective weight W_eff = V g/||V|| of one layer group and the squared norms."""
+    __slots__ = ("w", "sumsq")
+
+    def __init__(self, w: torch.Tensor, sumsq: torch.Tensor):
+        self.w = w
+        self.sumsq = sumsq
+
+
+def pack_layer(V: torch.Tensor, g: torch.Tensor, n_groups: int) -> Packed:
+    w, sumsq = K_.wn_pack(V.detach().contiguous(), g.detach().reshape(n_groups).contiguous(), n_groups)
+    return Packed(w, sumsq)
+
+
+def lin_fwd(x: torch.Tensor, pk: Packed, bias: torch.Tensor, relu: bool, out_bf16: bool = True,
+            out_f32: bool = False):
+    """y = act(x W_eff^T + b); x (M, K_in) bf16 -> (bf16 | None, fp32 | None)."""
+    M, Kin = x.shape
+    N = pk.w.shape[0]
+    return K_.gemm(x, pk.w, M, N, Kin, bias=bias.detach(), relu=relu, out_bf16=out_bf16, out_f32=out_f32)
+
+
+def _pick_splits(tiles: int, k_blocks: int) -> int:
+    """Split-K factor for the wgrad GEMM: smallest split whose CTA count fills >= 85 % of its waves."""
+    best, best_eff = 1, 0.0
+    for s in range(1, 149):
+        if s > 1 and s * 4 > k_blocks:
+            break
+        units = tiles * s
+        eff = units / (-(-units // K_.NUM_SMS) * K_.NUM_SMS)
+        if eff > best_eff + 1e-9:
+            best, best_eff = s, eff
+        if eff >= 0.85:
+            return s
+    return best
+
+
+def lin_bwd(x: torch.Tensor, dz: torch.Tensor, V: torch.Tensor, g: torch.Tensor, pk: Packed, n_groups: int,
+            need_dx: bool, dx_relu_aux: Optional[torch.Tensor] = None, dx_f32: bool = False):
+    """Backward of one layer group given the pre-activation gradient dz (M, N) bf16.
+    Returns dV (like V), dg (like g), dx (bf16 masked by dx_relu_aux > 0, or fp32) or None."""
+    M, Kin = x.shape
+    N = dz.shape[1]
+    # wgrad: dW_eff[N, K_in] = dz^T x  -- both operands MN-major, split over the row (reduction) dimension
+    tile_n = 256 if Kin >= 256 else 128
+    tiles = -(-N // 128) * -(-Kin // tile_n)
+    splits = _pick_splits(tiles, -(-M // 64))
+    dw = torch.zeros((N, Kin), dtype=F32, device=x.device)
+    K_.gemm(dz, x, N, Kin, M, a_mn=True, b_mn=True, accum_f32=dw, k_splits=splits, tile_n=tile_n)
+    dV, dg = K_.wn_grad(dw, V.detach().contiguous(), g.detach().reshape(n_groups).contiguous(), pk.sumsq, n_groups)
+    dx = None
+    if need_dx:
+        # dgrad: dx[M, K_in] = dz W_eff  (W_eff stored [N][K_in] = MN-major B operand)
+        ob, of = K_.gemm(dz, pk.w, M, Kin, N, b_mn=True, relu_aux=dx_relu_aux, out_bf16=not dx_f32, out_f32=dx_f32)
+        dx = of if dx_f32 else ob
+    return dV, dg.reshape(g.shape), dx
+
+
+def _colsum(dz: torch.Tensor, n: int) -> torch.Tensor:
+    db = torch.zeros((n,), dtype=F32, device=dz.device)
+    K_.act_bwd_bias(dz, None, False, db)
+    return db
+
+
+# --------------------------------------------------------------------------- #
+# T_g <-> packed core  (reference src/Tensor.py:6-8 glimpse-axis re-view)
+# --------------------------------------------------------------------------- #
+_TPACK_IDX = {}
+
+
+def tpack_index(R: int, d: int, G: int, device) -> torch.Tensor:
+    """int64 index p such that tpack.flat = T_g.flat[p], tpack[r][l][(i,g,j)] = T_eff[r,i,j,l,g].
+    T_eff follows from pushing indices through the reference's own view chain: mode 1 flattens the
+    core in (l, j, g) order but re-reads that axis as (g', l', j')."""
+    key = (R, d, G, str(device))
+    if key not in _TPACK_IDX:
+        idx = torch.arange(R * d * d * d * G).view(R, d, d, d, G)            # (r,i,j,l,g) -> flat T_g offset
+        reread = idx.permute(0, 1, 3, 2, 4).reshape(R, d, G, d, d)           # (r,i,g',l',j')
+        teff = reread.permute(0, 1, 4, 3, 2)                                 # (r,i,j',l',g')
+        _TPACK_IDX[key] = teff.permute(0, 3, 1, 4, 2).reshape(-1).to(device)  # (r,l,i,g,j)
+    return _TPACK_IDX[key]
+
+
+def pack_core(T_g: torch.Tensor) -> torch.Tensor:
+    _, R, d, _, _, G, ho = T_g.shape
+    idx = tpack_index(R, d, G, T_g.device)
+    return T_g.detach().reshape(-1)[idx].to(BF16).view(R, d, d * G * d)
+
+
+def unpack_core_grad(dtpack: torch.Tensor, T_g: torch.Tensor) -> torch.Tensor:
+    _, R, d, _, _, G, ho = T_g.shape
+    idx = tpack_index(R, d, G, T_g.device)
+    out = torch.empty(T_g.numel(), dtype=F32, device=T_g.device)
+    out[idx] = dtpack.reshape(-1)
+    return out.view_as(T_g)
+
+
+# --------------------------------------------------------------------------- #
+class WNLinearFn(Function):
+    """y = act(x W^T + b), W = V g/||V||_F: one FCNet layer (reference src/fc.py:27-29,33-34).
+    x fp32 (M, K_in) -> fp32 (M, N)."""
+
+    @staticmethod
+    def forward(ctx, x, V, g, bias, relu: bool, pk: Optional[Packed]):
+        if pk is None:
+            pk = pack_layer(V, g, 1)
+        xb, _ = K_.cast_rows(x.detach().contiguous())
+        yb, yf = lin_fwd(xb, pk, bias, relu, out_bf16=relu, out_f32=True)
+        ctx.save_for_backward(xb, yb if relu else None, V, g)
+        ctx.pk = pk
+        ctx.relu = relu
+        ctx.need_dx = x.requires_grad
+        return yf
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, yb, V, g = ctx.saved_tensors
+        N = V.shape[0]
+        db = torch.zeros((N,), dtype=F32, device=dy.device)
+        dz = K_.act_bwd_bias(dy.contiguous(), yb if ctx.relu else None, True, db)
+        dV, dg, dx = lin_bwd(xb, dz, V, g, ctx.pk, 1, ctx.need_dx, dx_f32=True)
+        return dx, dV, dg, db, None, None
+
+
+# --------------------------------------------------------------------------- #
+class TriLogitsFn(Function):
+    """TCNet.forward (reference src/tc.py:41-52): tucker projections, R per-rank projections (one
+    grouped GEMM per modality), rank-R trilinear contraction; optional zero-row mask to -inf
+    (src/attention.py:55-56).  Returns the (B,K,Q,A,G) view of a (B,G,K,Q,A) buffer."""
+
+    @staticmethod
+    def forward(ctx, dims, packs, v_bf16, rowmask, q, a, T_g, *w):
+        B, K, Q, A, G, R = dims
+        # w = (V, g, b) x [v_tucker, q_tucker, a_tucker, v_net, q_net, a_net]
+        groups = (1, 1, 1, R, R, R)
+        pk: List[Packed] = [packs[i] if packs is not None else pack_layer(w[3 * i], w[3 * i + 1], groups[i])
+                            for i in range(6)]
+        xq, _ = K_.cast_rows(q.detach().reshape(B * Q, -1).contiguous())
+        xa, _ = K_.cast_rows(a.detach().reshape(B * A, -1).contiguous())
+        yv, _ = lin_fwd(v_bf16, pk[0], w[2], True)
+        yq, _ = lin_fwd(xq, pk[1], w[5], True)
+        ya, _ = lin_fwd(xa, pk[2], w[8], True)
+        vc, _ = lin_fwd(yv, pk[3], w[11], True)
+        qc, _ = lin_fwd(yq, pk[4], w[14], True)
+        ac, _ = lin_fwd(ya, pk[5], w[17], True)
+        tpack = pack_core(T_g)
+        logits = K_.trilinear_fwd(vc, qc, ac, tpack, rowmask, B, K, Q, A, G, R)
+        ctx.save_for_backward(v_bf16, xq, xa, yv, yq, ya, vc, qc, ac, tpack, T_g, *w)
+        ctx.pk = pk
+        ctx.dims = dims
+        ctx.need = (q.requires_grad, a.requires_grad)
+        return logits.permute(0, 2, 3, 4, 1)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        B, K, Q, A, G, R = ctx.dims
+        v_bf16, xq, xa, yv, yq, ya, vc, qc, ac, tpack, T_g = ctx.saved_tensors[:11]
+        w = ctx.saved_tensors[11:]
+        pk = ctx.pk
+        dl = dlogits.permute(0, 4, 1, 2, 3).contiguous()
+        dzv, dzq, dza, dbvn, dbqn, dban, dtpack = K_.trilinear_bwd(vc, qc, ac, tpack, dl, B, K, Q, A, G, R)
+        # per-rank nets: input = tucker output (post-ReLU), so dx is masked by it -> dz of the tucker layer
+        dVvn, dgvn, dzvt = lin_bwd(yv, dzv, w[9], w[10], pk[3], R, True, dx_relu_aux=yv)
+        dVqn, dgqn, dzqt = lin_bwd(yq, dzq, w[12], w[13], pk[4], R, True, dx_relu_aux=yq)
+        dVan, dgan, dzat = lin_bwd(ya, dza, w[15], w[16], pk[5], R, True, dx_relu_aux=ya)
+        H = yv.shape[1]
+        dbvt, dbqt, dbat = _colsum(dzvt, H), _colsum(dzqt, H), _colsum(dzat, H)
+        dVvt, dgvt, _ = lin_bwd(v_bf16, dzvt, w[0], w[1], pk[0], 1, False)
+        dVqt, dgqt, dq = lin_bwd(xq, dzqt, w[3], w[4], pk[1], 1, ctx.need[0], dx_f32=True)
+        dVat, dgat, da = lin_bwd(xa, dzat, w[6], w[7], pk[2], 1, ctx.need[1], dx_f32=True)
+        dT = unpack_core_grad(dtpack, T_g)
+        if dq is not None:
+            dq = dq.view(B, Q, -1)
+        if da is not None:
+            da = da.view(B, A, -1)
+        return (None, None, None, None, dq, da, dT,
+                dVvt, dgvt, dbvt, dVqt, dgqt, dbqt, dVat, dgat, dbat,
+                dVvn, dgvn, dbvn.view_as(w[11]), dVqn, dgqn, dbqn.view_as(w[14]), dVan, dgan, dban.view_as(w[17]))
+
+
+# --------------------------------------------------------------------------- #
+class MaskedSoftmaxFn(Function):
+    """softmax over the flattened attention domain per (b, g) (reference src/attention.py:58 / :39).
+    x: logical (B, *dom, G) view of a (B, G, L) buffer when g_last, else (B, G, *dom) contiguous."""
+
+    @staticmethod
+    def forward(ctx, x, g_last: bool):
+        if g_last:
+            nd = x.dim()
+            xi = x.permute(0, nd - 1, *range(1, nd - 1)).contiguous()        # (B, G, *dom): no copy in the native layout
+        else:
+            xi = x.contiguous()
+        B, G = xi.shape[0], xi.shape[1]
+        L = xi[0, 0].numel()
+        p = K_.softmax_fwd(xi, B * G, L)
+        ctx.save_for_backward(p)
+        ctx.g_last = g_last
+        if g_last:
+            nd = p.dim()
+            return p.permute(0, *range(2, nd), 1)
+        return p
+
+    @staticmethod
+    def backward(ctx, dp):
+        (p,) = ctx.saved_tensors
+        B, G = p.shape[0], p.shape[1]
+        L = p[0, 0].numel()
+        if ctx.g_last:
+            nd = dp.dim()
+            dpi = dp.permute(0, nd - 1, *range(1, nd - 1))                   # logical (B, G, *dom), any strides
+        else:
+            dpi = dp
+        # the kernel addresses dp[b,g,e] with three strides: the domain must flatten with one stride
+        dom_sizes, dom_strides = dpi.shape[2:], dpi.stride()[2:]
+        se = dom_strides[-1]
+        ok = dpi.dtype == F32
+        run = se
+        for sz, st in zip(reversed(dom_sizes), reversed(dom_strides)):
+            if sz != 1 and st != run:
+                ok = False
+            run *= sz
+        if not ok:
+            dpi = dpi.to(F32).contiguous()
+            se = 1
+        dl = K_.softmax_bwd(p, dpi, dpi.stride(0), dpi.stride(1), se, B, G, L)
+        if ctx.g_last:
+            nd = dl.dim()
+            return dl.permute(0, *range(2, nd), 1), None
+        return dl, None
+
+
+# --------------------------------------------------------------------------- #
+def _sample_contiguous(w: torch.Tensor) -> torch.Tensor:
+    """Attention weights must be contiguous within a sample (any batch stride)."""
+    run = 1
+    for sz, st in zip(reversed(w.shape[1:]), reversed(w.stride()[1:])):
+        if sz != 1 and st != run:
+            return w.contiguous()
+        run *= sz
+    return w
+
+
+class PoolFn(Function):
+    """TCNet.forward_with_weights (reference src/tc.py:54-61) and, with a = None,
+    BCNet.forward_with_weights (src/bc.py:70-74): projections + attention-weighted pooling."""
+
+    @staticmethod
+    def forward(ctx, dims, packs, v_bf16, q, a, wts, *w):
+        B, K, Q, A, C = dims
+        n = 3 if A > 0 else 2
+        pk = [packs[i] if packs is not None else pack_layer(w[3 * i], w[3 * i + 1], 1) for i in range(n)]
+        xq, _ = K_.cast_rows(q.detach().reshape(B * Q, -1).contiguous())
+        vp, _ = lin_fwd(v_bf16, pk[0], w[2], True)
+        qp, _ = lin_fwd(xq, pk[1], w[5], True)
+        xa = ap = None
+        if A > 0:
+            xa, _ = K_.cast_rows(a.detach().reshape(B * A, -1).contiguous())
+            ap, _ = lin_fwd(xa, pk[2], w[8], True)
+        wd = _sample_contiguous(wts.detach())
+        if wd.dtype != F32:
+            wd = wd.float()
+        out = K_.tri_pool_fwd(vp, qp, ap, wd, wd.stride(0), B, K, Q, A, C)
+        ctx.save_for_backward(v_bf16, xq, xa, vp, qp, ap, wd, *w)
+        ctx.pk = pk
+        ctx.dims = dims
+        ctx.need = (q.requires_grad, a is not None and a.requires_grad, wts.requires_grad)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, K, Q, A, C = ctx.dims
+        v_bf16, xq, xa, vp, qp, ap, wd = ctx.saved_tensors[:7]
+        w = ctx.saved_tensors[7:]
+        pk = ctx.pk
+        dzv, dzq, dza, dbv, dbq, dba, dw = K_.tri_pool_bwd(vp, qp, ap, wd, wd.stride(0), dout.contiguous(), B, K, Q, A,
+                                                          C)
+        dVv, dgv, _ = lin_bwd(v_bf16, dzv, w[0], w[1], pk[0], 1, False)
+        dVq, dgq, dq = lin_bwd(xq, dzq, w[3], w[4], pk[1], 1, ctx.need[0], dx_f32=True)
+        grads = [dVv, dgv, dbv, dVq, dgq, dbq]
+        da = None
+        if A > 0:
+            dVa, dga, da = lin_bwd(xa, dza, w[6], w[7], pk[2], 1, ctx.need[1], dx_f32=True)
+            grads += [dVa, dga, dba]
+            if da is not None:
+                da = da.view(B, A, -1)
+        if dq is not None:
+            dq = dq.view(B, Q, -1)
+        return (None, None, None, dq, da, dw if ctx.need[2] else None, *grads)
+
+
+# --------------------------------------------------------------------------- #
+class BiLogitsFn(Function):
+    """BCNet.forward, h_out <= 32 branch (reference src/bc.py:52-58), with the optional zero-row mask
+    of BiAttention (src/attention.py:36-37) written as -inf.  hmat (G, C) is the effective h_mat."""
+
+    @staticmethod
+    def forward(ctx, dims, packs, v_bf16, rowmask, q, hmat, hbias, *w):
+        B, K, Q, G, C = dims
+        pk = [packs[i] if packs is not None else pack_layer(w[3 * i], w[3 * i + 1], 1) for i in range(2)]
+        xq, _ = K_.cast_rows(q.detach().reshape(B * Q, -1).contiguous())
+        vb, _ = lin_fwd(v_bf16, pk[0], w[2], True)
+        qb, _ = lin_fwd(xq, pk[1], w[5], True)
+        hm = hmat.detach().reshape(G, C).contiguous()
+        hb = hbias.detach().reshape(G).contiguous()
+        logits = K_.bilinear_fwd(vb, qb, hm, hb, rowmask, B, K, Q, G, C)
+        ctx.save_for_backward(v_bf16, xq, vb, qb, hm, hmat, hbias, *w)
+        ctx.pk = pk
+        ctx.dims = dims
+        ctx.need_dq = q.requires_grad
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        B, K, Q, G, C = ctx.dims
+        v_bf16, xq, vb, qb, hm, hmat, hbias = ctx.saved_tensors[:7]
+        w = ctx.saved_tensors[7:]
+        pk = ctx.pk
+        dzv, dzq, dbv, dbq, dh, dhb = K_.bilinear_bwd(vb, qb, hm, dlogits.contiguous(), B, K, Q, G, C)
+        dVv, dgv, _ = lin_bwd(v_bf16, dzv, w[0], w[1], pk[0], 1, False)
+        dVq, dgq, dq = lin_bwd(xq, dzq, w[3], w[4], pk[1], 1, ctx.need_dq, dx_f32=True)
+        if dq is not None:
+            dq = dq.view(B, Q, -1)
+        return (None, None, None, None, dq, dh.view_as(hmat), dhb.view_as(hbias), dVv, dgv, dbv, dVq, dgq, dbq)

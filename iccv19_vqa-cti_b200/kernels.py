@@ -1,0 +1,201 @@
+"""Thin tensor-level wrappers over the C ABI of libcti_sm100.so.
+
+Every function takes CUDA torch tensors, checks dtype / contiguity, allocates the outputs from
+torch's caching allocator (the library allocates nothing) and launches on the current stream.
+PyTorch is plumbing here: device memory and streams only.  No function has a fallback path.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+NUM_SMS = 148
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (the CTI kernels have no CPU path)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name}: expected a contiguous tensor")
+
+
+# --------------------------------------------------------------------------- #
+def cast_rows(x: torch.Tensor, want_mask: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """fp32 (rows, cols) -> bf16, optionally with the zero-row mask of src/attention.py:55."""
+    _req(x, F32, "cast_rows.x")
+    rows, cols = x.shape
+    out = torch.empty((rows, cols), dtype=BF16, device=x.device)
+    mask = torch.empty((rows,), dtype=torch.uint8, device=x.device) if want_mask else None
+    _lib.check(_lib.load().cti_cast_rows_mask(x.data_ptr(), out.data_ptr(), _ptr(mask), rows, cols, _stream()),
+               "cti_cast_rows_mask")
+    return out, mask
+
+
+def wn_pack(v: torch.Tensor, g: torch.Tensor, n_groups: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """v (n_groups*rows_per_group, cols) fp32, g (n_groups,) fp32 -> (W_eff bf16, sumsq fp32[n_groups])."""
+    _req(v, F32, "wn_pack.v")
+    _req(g, F32, "wn_pack.g")
+    rows, cols = v.shape
+    w = torch.empty((rows, cols), dtype=BF16, device=v.device)
+    sumsq = torch.empty((n_groups,), dtype=F32, device=v.device)
+    _lib.check(_lib.load().cti_wn_pack(v.data_ptr(), g.data_ptr(), w.data_ptr(), sumsq.data_ptr(), n_groups,
+                                       rows // n_groups, cols, _stream()), "cti_wn_pack")
+    return w, sumsq
+
+
+def wn_grad(dw: torch.Tensor, v: torch.Tensor, g: torch.Tensor, sumsq: torch.Tensor,
+            n_groups: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    _req(dw, F32, "wn_grad.dw")
+    _req(v, F32, "wn_grad.v")
+    rows, cols = v.shape
+    dv = torch.empty_like(v)
+    dg = torch.empty((n_groups,), dtype=F32, device=v.device)
+    ws = torch.empty((n_groups,), dtype=F32, device=v.device)
+    _lib.check(_lib.load().cti_wn_grad(dw.data_ptr(), v.data_ptr(), g.data_ptr(), sumsq.data_ptr(), dv.data_ptr(),
+                                       dg.data_ptr(), ws.data_ptr(), n_groups, rows // n_groups, cols, _stream()),
+               "cti_wn_grad")
+    return dv, dg
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool = False, b_mn: bool = False,
+         bias: Optional[torch.Tensor] = None, relu: bool = False, relu_aux: Optional[torch.Tensor] = None,
+         out_bf16: bool = True, out_f32: bool = False, accum_f32: Optional[torch.Tensor] = None, k_splits: int = 1,
+         alpha: float = 1.0, tile_n: int = 0) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """C[M,N] = epilogue(alpha * A . B^T) on the tcgen05 GEMM.  a / b are 2-D bf16 row-major buffers:
+    K-major operands are stored [M or N][K], MN-major ones [K][M or N].
+    accum_f32: a zeroed (M,N) fp32 buffer to atomically accumulate into (split-K)."""
+    _req(a, BF16, "gemm.a")
+    _req(b, BF16, "gemm.b")
+    ob = torch.empty((M, N), dtype=BF16, device=a.device) if (out_bf16 and accum_f32 is None) else None
+    of = accum_f32 if accum_f32 is not None else (torch.empty((M, N), dtype=F32, device=a.device) if out_f32 else None)
+    if relu_aux is not None:
+        _req(relu_aux, BF16, "gemm.relu_aux")
+    _lib.check(_lib.load().cti_gemm_bf16(
+        a.data_ptr(), a.shape[1], int(a_mn), b.data_ptr(), b.shape[1], int(b_mn), M, N, K, float(alpha), _ptr(bias),
+        int(relu), _ptr(relu_aux), 0 if relu_aux is None else relu_aux.shape[1], _ptr(ob), _ptr(of), N,
+        int(accum_f32 is not None), int(k_splits), int(tile_n), _stream()), "cti_gemm_bf16")
+    return ob, of
+
+
+def act_bwd_bias(dy: torch.Tensor, y: Optional[torch.Tensor], want_dz: bool,
+                 dbias: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """dz = dy * (y > 0) as bf16 (if want_dz); dbias[n] += sum_m dz[m, n]."""
+    rows, cols = dy.shape
+    if dy.dtype not in (F32, BF16) or not dy.is_contiguous():
+        raise RuntimeError("act_bwd_bias.dy: expected contiguous fp32 / bf16")
+    dz = torch.empty((rows, cols), dtype=BF16, device=dy.device) if want_dz else None
+    _lib.check(_lib.load().cti_act_bwd_bias(dy.data_ptr(), int(dy.dtype == BF16), _ptr(y), _ptr(dz), _ptr(dbias), rows,
+                                            cols, _stream()), "cti_act_bwd_bias")
+    return dz
+
+
+def softmax_fwd(logits: torch.Tensor, rows: int, length: int) -> torch.Tensor:
+    _req(logits, F32, "softmax_fwd.logits")
+    p = torch.empty_like(logits)
+    _lib.check(_lib.load().cti_masked_softmax_fwd(logits.data_ptr(), p.data_ptr(), rows, length, _stream()),
+               "cti_masked_softmax_fwd")
+    return p
+
+
+def softmax_bwd(p: torch.Tensor, dp: torch.Tensor, sb: int, sg: int, se: int, batch: int, groups: int,
+                length: int) -> torch.Tensor:
+    _req(p, F32, "softmax_bwd.p")
+    if dp.dtype != F32:
+        raise RuntimeError("softmax_bwd.dp: expected fp32")
+    dl = torch.empty_like(p)
+    _lib.check(_lib.load().cti_masked_softmax_bwd(p.data_ptr(), dp.data_ptr(), sb, sg, se, dl.data_ptr(), batch, groups,
+                                                  length, _stream()), "cti_masked_softmax_bwd")
+    return dl
+
+
+def trilinear_fwd(vc, qc, ac, tpack, rowmask, B, K, Q, A, G, R) -> torch.Tensor:
+    for t, n in ((vc, "vc"), (qc, "qc"), (ac, "ac"), (tpack, "tpack")):
+        _req(t, BF16, "trilinear_fwd." + n)
+    logits = torch.empty((B, G, K, Q, A), dtype=F32, device=vc.device)
+    _lib.check(_lib.load().cti_trilinear_logits_fwd(vc.data_ptr(), qc.data_ptr(), ac.data_ptr(), tpack.data_ptr(),
+                                                    _ptr(rowmask), logits.data_ptr(), B, K, Q, A, G, R, _stream()),
+               "cti_trilinear_logits_fwd")
+    return logits
+
+
+def trilinear_bwd(vc, qc, ac, tpack, dlogits, B, K, Q, A, G, R):
+    """Returns dzv, dzq, dza (bf16, pre-activation), dbv, dbq, dba (fp32, R*16), dtpack (fp32)."""
+    _req(dlogits, F32, "trilinear_bwd.dlogits")
+    lib = _lib.load()
+    dev = vc.device
+    dzv, dzq, dza = torch.empty_like(vc), torch.empty_like(qc), torch.empty_like(ac)
+    zeros = torch.zeros((3 * R * 16 + tpack.numel(),), dtype=F32, device=dev)
+    dbv, dbq, dba = zeros[:R * 16], zeros[R * 16:2 * R * 16], zeros[2 * R * 16:3 * R * 16]
+    dtpack = zeros[3 * R * 16:]
+    nbytes = lib.cti_trilinear_logits_bwd_workspace(B, K, Q, A, G, R)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    _lib.check(lib.cti_trilinear_logits_bwd(vc.data_ptr(), qc.data_ptr(), ac.data_ptr(), tpack.data_ptr(),
+                                            dlogits.data_ptr(), dzv.data_ptr(), dzq.data_ptr(), dza.data_ptr(),
+                                            dbv.data_ptr(), dbq.data_ptr(), dba.data_ptr(), dtpack.data_ptr(),
+                                            ws.data_ptr(), nbytes, B, K, Q, A, G, R, _stream()),
+               "cti_trilinear_logits_bwd")
+    return dzv, dzq, dza, dbv, dbq, dba, dtpack
+
+
+def tri_pool_fwd(v, q, a, w, w_stride_b, B, K, Q, A, C) -> torch.Tensor:
+    out = torch.empty((B, C), dtype=F32, device=v.device)
+    _lib.check(_lib.load().cti_tri_pool_fwd(v.data_ptr(), q.data_ptr(), _ptr(a), w.data_ptr(), w_stride_b,
+                                            out.data_ptr(), B, K, Q, A, C, _stream()), "cti_tri_pool_fwd")
+    return out
+
+
+def tri_pool_bwd(v, q, a, w, w_stride_b, dout, B, K, Q, A, C):
+    """Returns dzv, dzq, dza (bf16), dbv, dbq, dba (fp32, C), dw (B,K,Q[,A]) fp32.  A == 0: bilinear."""
+    _req(dout, F32, "tri_pool_bwd.dout")
+    dev = v.device
+    dzv, dzq = torch.empty_like(v), torch.empty_like(q)
+    dza = torch.empty_like(a) if A > 0 else None
+    zeros = torch.zeros((3 * C,), dtype=F32, device=dev)
+    dbv, dbq, dba = zeros[:C], zeros[C:2 * C], zeros[2 * C:]
+    dw = torch.empty((B, K, Q, A) if A > 0 else (B, K, Q), dtype=F32, device=dev)
+    _lib.check(_lib.load().cti_tri_pool_bwd(v.data_ptr(), q.data_ptr(), _ptr(a), w.data_ptr(), w_stride_b,
+                                            dout.data_ptr(), dzv.data_ptr(), dzq.data_ptr(), _ptr(dza), dbv.data_ptr(),
+                                            dbq.data_ptr(), dba.data_ptr(), dw.data_ptr(), B, K, Q, A, C, _stream()),
+               "cti_tri_pool_bwd")
+    return dzv, dzq, dza, dbv, dbq, (dba if A > 0 else None), dw
+
+
+def bilinear_fwd(vb, qb, hmat, hbias, rowmask, B, K, Q, G, C) -> torch.Tensor:
+    _req(hmat, F32, "bilinear_fwd.hmat")
+    _req(hbias, F32, "bilinear_fwd.hbias")
+    logits = torch.empty((B, G, K, Q), dtype=F32, device=vb.device)
+    _lib.check(_lib.load().cti_bilinear_logits_fwd(vb.data_ptr(), qb.data_ptr(), hmat.data_ptr(), hbias.data_ptr(),
+                                                   _ptr(rowmask), logits.data_ptr(), B, K, Q, G, C, _stream()),
+               "cti_bilinear_logits_fwd")
+    return logits
+
+
+def bilinear_bwd(vb, qb, hmat, dlogits, B, K, Q, G, C):
+    """Returns dzv, dzq (bf16), dbv, dbq (C), dhmat (G,C), dhbias (G)."""
+    _req(dlogits, F32, "bilinear_bwd.dlogits")
+    dev = vb.device
+    dzv, dzq = torch.empty_like(vb), torch.empty_like(qb)
+    zeros = torch.zeros((2 * C + G * C + G,), dtype=F32, device=dev)
+    dbv, dbq = zeros[:C], zeros[C:2 * C]
+    dh = zeros[2 * C:2 * C + G * C].view(G, C)
+    dhb = zeros[2 * C + G * C:]
+    _lib.check(_lib.load().cti_bilinear_logits_bwd(vb.data_ptr(), qb.data_ptr(), hmat.data_ptr(), dlogits.data_ptr(),
+                                                   dzv.data_ptr(), dzq.data_ptr(), dbv.data_ptr(), dbq.data_ptr(),
+                                                   dh.data_ptr(), dhb.data_ptr(), B, K, Q, G, C, _stream()),
+               "cti_bilinear_logits_bwd")
+    return dzv, dzq, dbv, dbq, dh, dhb

@@ -1,0 +1,117 @@
+"""Drop-in for the reference's ``src/tc.py``: ``TCNet`` -- compact trilinear interaction
+(reference src/tc.py:9-61, with the mode products of src/Tensor.py:3-19 folded into one kernel).
+
+Constructor, attribute names, parameter names / shapes / registration order follow the reference,
+so ``state_dict()`` round-trips with reference checkpoints.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import functions as F_
+from .fc import FCNet, cast_features, check_dropout
+
+
+class TCNet(nn.Module):
+    def __init__(self, v_dim, q_dim, a_dim, h_dim, h_out, rank, glimpse, act='ReLU', dropout=[.2, .5], k=1):
+        super().__init__()
+        self.v_dim = v_dim
+        self.q_dim = q_dim
+        self.a_dim = a_dim
+        self.h_out = h_out
+        self.rank = rank
+        self.h_dim = h_dim * k
+        self.hv_dim = int(h_dim / rank)
+        self.hq_dim = int(h_dim / rank)
+        self.ha_dim = int(h_dim / rank)
+        self.glimpse = glimpse
+
+        self.v_tucker = FCNet([v_dim, self.h_dim], act=act, dropout=dropout[1])
+        self.q_tucker = FCNet([q_dim, self.h_dim], act=act, dropout=dropout[0])
+        self.a_tucker = FCNet([a_dim, self.h_dim], act=act, dropout=dropout[0])
+        if self.h_dim < 1024:                                       # reference src/tc.py:27
+            self.v_net = nn.ModuleList([FCNet([self.h_dim, self.hv_dim], act=act, dropout=dropout[1])
+                                        for _ in range(rank)])
+            self.q_net = nn.ModuleList([FCNet([self.h_dim, self.hq_dim], act=act, dropout=dropout[0])
+                                        for _ in range(rank)])
+            self.a_net = nn.ModuleList([FCNet([self.h_dim, self.ha_dim], act=act, dropout=dropout[0])
+                                        for _ in range(rank)])
+            if h_out > 1:
+                self.ho_dim = int(h_out / rank)
+                h_out = self.ho_dim
+            self.T_g = nn.Parameter(torch.Tensor(1, rank, self.hv_dim, self.hq_dim, self.ha_dim, glimpse,
+                                                 h_out).normal_())
+        self.dropout = nn.Dropout(dropout[1])                       # unused, as in the reference (src/tc.py:38)
+        self._rank_pack = None
+
+    # ------------------------------------------------------------------ #
+    def _rank_group(self, nets: nn.ModuleList):
+        """One grouped layer out of the R per-rank FCNets: V (R*d, H), g (R,), b (R*d,)."""
+        lins = [n.single()[0] for n in nets]
+        V = torch.cat([l.weight_v for l in lins], 0)
+        g = torch.stack([l.weight_g for l in lins], 0)
+        b = torch.cat([l.bias for l in lins], 0)
+        return V, g, b
+
+    def _check_trilinear(self):
+        if not hasattr(self, 'T_g'):
+            raise RuntimeError("TCNet.forward needs the per-rank nets and T_g (h_dim * k < 1024), "
+                               "as in the reference (src/tc.py:27,47)")
+        if self.T_g.shape[-1] != 1:
+            raise RuntimeError("TCNet.forward: h_out > 1 is unusable in the reference too "
+                               "(Tensor.ModeProduct cannot view the core)")
+        if self.hv_dim != 16:
+            raise RuntimeError(f"the sm_100a trilinear kernel is built for h_dim / rank == 16, got {self.hv_dim}")
+
+    def _logits(self, v, q, a, rowmask_wanted: bool):
+        self._check_trilinear()
+        B, K = v.shape[0], v.shape[1]
+        Q, A = q.shape[1], a.shape[1]
+        G = self.T_g.shape[5]
+        v_bf16, rowmask = cast_features(v)
+        lv, pv = self.v_tucker.single()
+        lq, pq = self.q_tucker.single()
+        la, pa = self.a_tucker.single()
+        for p in (pv, pq, pa, self.v_net[0].single()[1], self.q_net[0].single()[1], self.a_net[0].single()[1]):
+            check_dropout(self, p)
+        # weight packs are cached on the parameters' version counters (optimizer steps bump them)
+        rank_params = [p for nets in (self.v_net, self.q_net, self.a_net) for p in nets.parameters()]
+        key = tuple(p._version for p in rank_params) + (rank_params[0].data_ptr(),)
+        cache = self._rank_pack
+        if cache is not None and cache[0] == key and not torch.is_grad_enabled():
+            (Vvn, gvn, bvn), (Vqn, gqn, bqn), (Van, gan, ban) = cache[2]
+        else:
+            Vvn, gvn, bvn = self._rank_group(self.v_net)
+            Vqn, gqn, bqn = self._rank_group(self.q_net)
+            Van, gan, ban = self._rank_group(self.a_net)
+        if cache is None or cache[0] != key:
+            stacks = [tuple(t.detach() for t in grp) for grp in ((Vvn, gvn, bvn), (Vqn, gqn, bqn), (Van, gan, ban))]
+            cache = self._rank_pack = (key, [F_.pack_layer(Vvn, gvn, self.rank), F_.pack_layer(Vqn, gqn, self.rank),
+                                             F_.pack_layer(Van, gan, self.rank)], stacks)
+        packs = [lv.packed(), lq.packed(), la.packed()] + cache[1]
+        dims = (B, K, Q, A, G, self.rank)
+        return F_.TriLogitsFn.apply(dims, packs, v_bf16, rowmask if rowmask_wanted else None, q, a, self.T_g,
+                                    lv.weight_v, lv.weight_g, lv.bias, lq.weight_v, lq.weight_g, lq.bias,
+                                    la.weight_v, la.weight_g, la.bias, Vvn, gvn, bvn, Vqn, gqn, bqn, Van, gan, ban)
+
+    def forward(self, v, q, a):
+        """v (B,K,v_dim), q (B,Q,q_dim), a (B,A,a_dim) -> trilinear logit map (B,K,Q,A,G)."""
+        return self._logits(v, q, a, False)
+
+    def forward_with_weights(self, v, q, a, w):
+        """Attention-weighted trilinear pooling: w (B,K,Q,A) -> joint embedding (B, h_dim)."""
+        B, K = v.shape[0], v.shape[1]
+        Q, A = q.shape[1], a.shape[1]
+        v_bf16, _ = cast_features(v)
+        lv, pv = self.v_tucker.single()
+        lq, pq = self.q_tucker.single()
+        la, pa = self.a_tucker.single()
+        for p in (pv, pq, pa):
+            check_dropout(self, p)
+        packs = [lv.packed(), lq.packed(), la.packed()]
+        dims = (B, K, Q, A, self.h_dim)
+        return F_.PoolFn.apply(dims, packs, v_bf16, q, a, w, lv.weight_v, lv.weight_g, lv.bias, lq.weight_v,
+                               lq.weight_g, lq.bias, la.weight_v, la.weight_g, la.bias)

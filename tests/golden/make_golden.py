@@ -117,6 +117,7 @@ def main():
     tri_case("tri_small_g3", 2, 7, 4, 3, 32, 16, 16, 4, 3, 21, out)
     tri_case("tri_d16", 2, 10, 12, 6, 64, 48, 64, 4, 2, 31, out)   # d = 16 like the real model
     bi_case("bi_small", 3, 6, 4, 32, 16, 24, 2, 41, out)
+    bi_case("bi_c128", 3, 10, 12, 64, 48, 128, 2, 51, out)        # channel counts the CUDA kernels tile (x128)
     torch.save(out, OUT)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 

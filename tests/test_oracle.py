@@ -95,8 +95,9 @@ def test_tri_attention_and_pool(golden, name):
             assert torch.allclose(pool_p[i][k].grad, gr, rtol=1e-3, atol=1e-5), k
 
 
-def test_bi_attention_and_pool(golden):
-    g = golden["bi_small"]
+@pytest.mark.parametrize("name", ["bi_small", "bi_c128"])
+def test_bi_attention_and_pool(golden, name):
+    g = golden[name]
     G = g["cfg"]["G"]
     att_p = {k: v.clone().requires_grad_(True) for k, v in g["att_sd"].items()}
     pool_p = [{k: v.clone().requires_grad_(True) for k, v in sd.items()} for sd in g["pool_sd"]]
