@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Benchmark of the CTI hot path on B200 (contract: see the task brief / DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--rows B] [--impl b200|reference]
+
+A step = one forward + backward pass of the CTI multiple-choice hot path over one synthetic batch
+of ``rows`` module rows per GPU (TriAttention -> per glimpse TCNet.forward_with_weights + q_prj /
+a_prj residuals, reference src/MC/base_model.py:143-150; K=50 regions x 2048, 12 question tokens,
+6 answer tokens, 2 glimpses, rank 32, random init).  Dropout is off (eval-mode modules with
+gradients taken), which is the mode the parity tolerance is defined in.
+
+Prints ONE JSON line (rank 0).  ``value`` = rows/s with inputs resident in HBM; ``e2e`` = rows/s
+through the public module API with host (pinned) inputs, H2D and D2H inside the timed region.
+``--impl reference`` times the CPU oracle (a port of the reference's own op order; the reference is
+pure PyTorch and is not present on the GPU box) on the host cores for the same metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K_REGIONS, Q_TOK, A_TOK, GLIMPSE = 50, 12, 6, 2
+V_DIM, HID, H_MM, RANK = 2048, 1024, 512, 32
+METRIC = "cti_mc_hot_path_fwd_bwd_rows_per_s"
+UNIT = "rows/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--rows", type=int, default=1024, help="module rows per GPU per step (weak scaling)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-rows", type=int, default=128, help="rows per step of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(rows, n):
+    return {"workload": "CTI MC hot path fwd+bwd (TriAttention + 2x TCNet.forward_with_weights + q_prj/a_prj), "
+                        "dropout off", "rows_per_gpu": rows, "global_rows": rows * n, "K": K_REGIONS, "Q": Q_TOK,
+            "A": A_TOK, "glimpse": GLIMPSE, "rank": RANK, "h_mm": H_MM, "v_dim": V_DIM, "num_hid": HID,
+            "l2": "inputs larger than L2 (v alone is %.0f MB per step)" % (rows * K_REGIONS * V_DIM * 4 / 1e6),
+            "parallelism": f"dp{n}"}
+
+
+# --------------------------------------------------------------------------- #
+# CPU arm: the oracle (port of the reference's op order) on the host cores
+# --------------------------------------------------------------------------- #
+def cpu_rows_per_s(rows, steps, warmup):
+    import torch
+    from oracle import cti_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    params = {k: t.requires_grad_(True) for k, t in O.random_cti_params(glimpse=GLIMPSE, seed=1204).items()}
+    v, q, a = O.synthetic_inputs(rows, K_REGIONS, Q_TOK, A_TOK, seed=1204)
+    q.requires_grad_(True)
+    a.requires_grad_(True)
+    cot = torch.randn(rows, HID)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        for t in list(params.values()) + [q, a]:
+            t.grad = None
+        joint, _, _ = O.cti_hot_path(v, q, a, params, GLIMPSE)
+        (joint * cot).sum().backward()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    return rows / dt, cores, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+    val, cores, dt = cpu_rows_per_s(args.cpu_rows, steps, warmup)
+    sample = f"{steps} timed steps of {args.cpu_rows} rows after {warmup} warm-up (same model and shapes)"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.cpu_rows, 1),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- #
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                clk, mxv = float(f[0]), float(f[1])
+            except ValueError:
+                continue
+            mx = mxv
+            if t0 <= t <= t1 + 0.1:
+                sm.append(clk)
+                for n, val in zip(names, f[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import cti_b200
+    from cti_b200 import kernels as KS
+    from cti_b200.dp import GradAllReducer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.rows
+    torch.manual_seed(1204)                      # same replica on every rank
+    att = cti_b200.TriAttention(V_DIM, HID, HID, H_MM, 1, RANK, GLIMPSE, 1)
+    pools = [cti_b200.TCNet(V_DIM, HID, HID, H_MM, 1, RANK, 1, k=2) for _ in range(GLIMPSE)]
+    q_prj = [cti_b200.FCNet([HID, HID], '', .2) for _ in range(GLIMPSE)]
+    a_prj = [cti_b200.FCNet([HID, HID], '', .2) for _ in range(GLIMPSE)]
+    mods = torch.nn.ModuleList([att, *pools, *q_prj, *a_prj]).to(dev).eval()
+    params = [p for p in mods.parameters()]
+    reducer = GradAllReducer(params) if world > 1 else None
+
+    g = torch.Generator().manual_seed(1204 + rank)
+    v_h = torch.relu(torch.randn(B, K_REGIONS, V_DIM, generator=g))
+    nb = torch.randint(10, K_REGIONS + 1, (B,), generator=g)
+    v_h = (v_h * (torch.arange(K_REGIONS)[None, :] < nb[:, None]).float()[:, :, None]).pin_memory()
+    q_h = torch.tanh(torch.randn(B, Q_TOK, HID, generator=g)).pin_memory()
+    a_h = torch.tanh(torch.randn(B, A_TOK, HID, generator=g)).pin_memory()
+    cot = torch.randn(B, HID, generator=g).to(dev)
+    out_h = torch.empty(B, HID).pin_memory()
+
+    def step(v, q, a):
+        for p in params:
+            p.grad = None
+        q.requires_grad_(True)
+        a.requires_grad_(True)
+        p_att, _ = att(v, q, a)
+        qe, ae = q, a
+        for gi in range(GLIMPSE):
+            b_emb = pools[gi].forward_with_weights(v, qe, ae, p_att[:, :, :, :, gi])
+            qe = q_prj[gi](b_emb.unsqueeze(1)) + qe
+            ae = a_prj[gi](b_emb.unsqueeze(1)) + ae
+        joint = qe.sum(1) + ae.sum(1)
+        (joint * cot).sum().backward()
+        if reducer is not None:
+            reducer.finish()
+        return joint
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        w1 = time.perf_counter()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), w0, w1
+
+    # ---- device-resident arm -------------------------------------------------
+    v_d, q_d, a_d = v_h.to(dev), q_h.to(dev), a_h.to(dev)
+
+    def resident_step():
+        step(v_d, q_d.detach(), a_d.detach())
+
+    for _ in range(max(args.warmup, 3)):
+        resident_step()
+    sampler = ClockSampler(local) if rank == 0 else None
+    KS.STATS.launches = 0
+    ms, w0, w1 = timed(resident_step, args.steps)
+    launches = KS.STATS.launches
+    clocks = sampler.stop(w0, w1) if sampler else None
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- end-to-end arm: pinned host inputs -> H2D -> modules -> D2H ----------
+    def e2e_step():
+        v = v_h.to(dev, non_blocking=True)
+        q = q_h.to(dev, non_blocking=True)
+        a = a_h.to(dev, non_blocking=True)
+        joint = step(v, q, a)
+        out_h.copy_(joint.detach(), non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    ms_e2e, _, _ = timed(e2e_step, args.steps)
+    e2e = {"value": world * B * args.steps / (ms_e2e / 1e3), "unit": UNIT,
+           "h2d_bytes_per_step": (v_h.numel() + q_h.numel() + a_h.numel()) * 4, "d2h_bytes_per_step": out_h.numel() * 4,
+           "ms_per_step": ms_e2e / args.steps}
+
+    # ---- forward-only (config[1] of BASELINE.json) -----------------------------
+    def fwd_only():
+        with torch.no_grad():
+            p_att, _ = att(v_d, q_d, a_d)
+            qe, ae = q_d, a_d
+            for gi in range(GLIMPSE):
+                b_emb = pools[gi].forward_with_weights(v_d, qe, ae, p_att[:, :, :, :, gi])
+                qe = q_prj[gi](b_emb.unsqueeze(1)) + qe
+                ae = a_prj[gi](b_emb.unsqueeze(1)) + ae
+            return qe.sum(1) + ae.sum(1)
+
+    for _ in range(3):
+        fwd_only()
+    ms_f, _, _ = timed(fwd_only, args.steps)
+    fwd = {"value": world * B * args.steps / (ms_f / 1e3), "unit": UNIT, "ms_per_step": ms_f / args.steps}
+
+    # ---- per-kernel CUDA-event timing of the same step (rank 0) -----------------
+    roofline, kernels = None, None
+    if rank == 0 and not args.no_profile:
+        peaks = {}
+        pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk_path):
+            peaks = json.load(open(pk_path))
+        which = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+        tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        tf_burst = peaks.get("bf16_tflops", 1590.0)
+        bw_peak = peaks.get("hbm_gbs", 6650.0)
+        n_prof = 3
+        KS.STATS.prof = []
+        torch.cuda.synchronize()
+        for _ in range(n_prof):
+            resident_step()
+        torch.cuda.synchronize()
+        rec, KS.STATS.prof = KS.STATS.prof, None
+        agg = {}
+        for name, tag, flops, nbytes, e0, e1 in rec:
+            key = (name, tag)
+            d = agg.setdefault(key, [0, 0.0, flops, nbytes])
+            d[0] += 1
+            d[1] += e0.elapsed_time(e1)
+        total = sum(d[1] for d in agg.values())
+        kernels = []
+        for (name, tag), (n, t, flops, nbytes) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            avg = t / n
+            ent = {"kernel": name, "tag": tag, "launches_per_step": n // n_prof, "avg_ms": avg, "share": t / total}
+            if flops:
+                ent["tflops"] = flops / (avg * 1e-3) / 1e12
+                ent["frac_of_bf16_peak"] = ent["tflops"] / tf_peak
+            if nbytes:
+                ent["gbs"] = nbytes / (avg * 1e-3) / 1e9
+                ent["frac_of_hbm_peak"] = ent["gbs"] / bw_peak
+            kernels.append(ent)
+        gem = [(k, d) for k, d in agg.items() if k[0] == "cti_gemm_bf16"]
+        if gem:
+            gflops = sum(d[2] * d[0] for _, d in gem)
+            gms = sum(d[1] for _, d in gem)
+            (kname, ktag), d = max(gem, key=lambda kv: kv[1][1])
+            ach = d[2] / (d[1] / d[0] * 1e-3) / 1e12
+            roofline = {"kernel": f"gemm_bf16_kernel [{ktag}]", "bound": "tensor", "achieved": ach, "peak": tf_peak,
+                        "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": None,
+                        "peak_source": which + ", sustained bf16 (kernel timed inside a long step); burst %.0f" % tf_burst,
+                        "share_of_step": d[1] / total,
+                        "all_gemm_launches": {"tflops": gflops / (gms * 1e-3) / 1e12, "share_of_step": gms / total,
+                                              "frac": gflops / (gms * 1e-3) / 1e12 / tf_peak}}
+
+    cpu_baseline = None
+    if rank == 0 and not args.no_cpu_baseline:
+        val, cores, dt = cpu_rows_per_s(args.cpu_rows, 3, 1)
+        cpu_baseline = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"3 timed fwd+bwd steps of {args.cpu_rows} rows after 1 warm-up, oracle on host cores, "
+                                  f"{dt:.2f} s/step"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": workload_config(B, world), "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+                "fwd_only": fwd, "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,134 @@
+"""Batch-sharded data parallelism for the CTI hot path: one process per GPU, parameters
+replicated, rows sharded, and exactly one collective -- a sum all-reduce of the parameter
+gradients, bucketed and launched from autograd hooks so it overlaps the rest of backward.
+
+This is the collective the reference's ``Trainer._all_reduce_and_rescale`` names but never issues
+(reference src/MC/trainer.py:208-219: it only flattens, divides and clips).  NCCL over NVLink 5 /
+NVSwitch on GPUs; the same code runs on gloo for the CPU tests.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_rows(n_rows: int, rank: int, world: int, group: int = 1) -> slice:
+    """Contiguous row range of this rank.  ``group`` keeps rows that belong together on one rank
+    (MC folds the 4 answer candidates of a question into the batch, reference src/MC/train.py:75-79,
+    and scores them in groups of 4, src/MC/trainer.py:297)."""
+    if n_rows % group:
+        raise ValueError(f"{n_rows} rows do not divide into groups of {group}")
+    n_groups = n_rows // group
+    base, extra = divmod(n_groups, world)
+    lo = rank * base + min(rank, extra)
+    hi = lo + base + (1 if rank < extra else 0)
+    return slice(lo * group, hi * group)
+
+
+class _Bucket:
+    __slots__ = ("params", "flat", "views", "pending", "work")
+
+    def __init__(self, params: List[torch.nn.Parameter]):
+        self.params = params
+        n = sum(p.numel() for p in params)
+        self.flat = torch.zeros(n, dtype=params[0].dtype, device=params[0].device)
+        self.views, o = [], 0
+        for p in params:
+            self.views.append(self.flat[o:o + p.numel()].view_as(p))
+            o += p.numel()
+        self.pending = len(params)
+        self.work = None
+
+
+class GradAllReducer:
+    """Overlapped, bucketed gradient all-reduce.
+
+        reducer = GradAllReducer(model.parameters())
+        loss.backward()          # buckets are reduced as soon as their last gradient lands
+        reducer.finish()         # wait; every p.grad is now the cross-rank SUM (or mean) -- a view
+                                 # of the bucket's flat buffer, so a fused clip / optimizer can use
+                                 # reducer.flat_grads() directly
+
+    Buckets are filled in reverse registration order (the order backward produces gradients)."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 25 << 20,
+                 process_group: Optional[dist.ProcessGroup] = None, average: bool = False):
+        self.group = process_group
+        self.average = average
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        ps = [p for p in params if p.requires_grad]
+        self.buckets: List[_Bucket] = []
+        cur, cur_bytes = [], 0
+        for p in reversed(ps):
+            if cur and (cur_bytes + p.numel() * p.element_size() > bucket_bytes or p.dtype != cur[0].dtype):
+                self.buckets.append(_Bucket(cur))
+                cur, cur_bytes = [], 0
+            cur.append(p)
+            cur_bytes += p.numel() * p.element_size()
+        if cur:
+            self.buckets.append(_Bucket(cur))
+        self._of = {}
+        self._handles = []
+        for b in self.buckets:
+            for p in b.params:
+                self._of[p] = b
+                self._handles.append(p.register_post_accumulate_grad_hook(self._on_grad))
+
+    # ------------------------------------------------------------------ #
+    def _launch(self, b: _Bucket) -> None:
+        torch._foreach_copy_(b.views, [p.grad for p in b.params])        # one fused copy per bucket
+        for p, v in zip(b.params, b.views):
+            p.grad = v
+        if self.world > 1:
+            b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def _on_grad(self, p: torch.nn.Parameter) -> None:
+        b = self._of[p]
+        b.pending -= 1
+        if b.pending == 0:
+            self._launch(b)
+
+    def finish(self) -> None:
+        """Wait for every bucket; parameters that received no gradient this step count as zeros."""
+        for b in self.buckets:
+            if b.pending != 0:                                            # some grads never arrived (unused params)
+                for p, v in zip(b.params, b.views):
+                    if p.grad is None:
+                        v.zero_()
+                        p.grad = v
+                self._launch(b)
+        for b in self.buckets:
+            if b.work is not None:
+                b.work.wait()
+                b.work = None
+            if self.average and self.world > 1:
+                b.flat.div_(self.world)
+            b.pending = len(b.params)
+
+    def flat_grads(self) -> List[torch.Tensor]:
+        return [b.flat for b in self.buckets]
+
+    def zero_grad(self) -> None:
+        """Drop gradients so the next backward assigns fresh ones (the hooks re-point them at the buckets)."""
+        for b in self.buckets:
+            for p in b.params:
+                p.grad = None
+
+    def remove(self) -> None:
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+
+def clip_flat_grads_(flats: Sequence[torch.Tensor], max_norm: float, denom: float = 1.0) -> torch.Tensor:
+    """``grad /= denom`` then global-L2-norm clip, on the reduced flat buffers (what the reference does
+    on its own flat copy: src/MC/trainer.py:213-214, src/utils.py:323-328).  Returns the pre-clip norm."""
+    if denom != 1.0:
+        torch._foreach_div_(list(flats), denom)
+    norm = torch.linalg.vector_norm(torch.stack(torch._foreach_norm(list(flats))))
+    if max_norm > 0:
+        coef = (max_norm / (norm + 1e-6)).clamp(max=1.0)
+        torch._foreach_mul_(list(flats), coef)
+    return norm

@@ -21,6 +21,30 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class _Stats:
+    """Launch accounting (bench.py's ``gpu_launches``) and optional per-call CUDA-event timing."""
+    launches = 0          # CUDA kernels launched through the C ABI since the last reset
+    prof = None           # None, or a list receiving (name, tag, flops, bytes, start_event, end_event)
+
+
+STATS = _Stats()
+
+
+def _call(name: str, fn, args, kernels: int = 1, flops: float = 0.0, nbytes: float = 0.0, tag: str = "") -> None:
+    """One C-ABI call = `kernels` kernel launches on the current stream; algorithmic work for the roofline."""
+    STATS.launches += kernels
+    prof = STATS.prof
+    if prof is None:
+        _lib.check(fn(*args), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = fn(*args)
+    e1.record()
+    prof.append((name, tag, flops, nbytes, e0, e1))
+    _lib.check(rc, name)
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -34,6 +58,18 @@ def _req(t: torch.Tensor, dtype, name: str) -> None:
         raise RuntimeError(f"{name}: expected a contiguous tensor")
 
 
+def trilinear_min_flops(K: int, Q: int, A: int, G: int, R: int, d: int = 16) -> float:
+    """Algorithmic forward FLOPs per row of the trilinear contraction, cheapest order a -> q -> v
+    (T_min)."""
+    return R * (2.0 * d ** 3 * G * A + 2.0 * d * d * Q * A * G) + 2.0 * K * (R * d) * Q * A * G
+
+
+def pool_flops(K: int, Q: int, A: int, C: int) -> float:
+    """Algorithmic forward FLOPs per row of the attention-weighted pooling."""
+    An = max(A, 1)
+    return 2.0 * K * Q * An * C + Q * An * C + 2.0 * K * C
+
+
 # --------------------------------------------------------------------------- #
 def cast_rows(x: torch.Tensor, want_mask: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """fp32 (rows, cols) -> bf16, optionally with the zero-row mask of src/attention.py:55."""
@@ -41,8 +77,8 @@ def cast_rows(x: torch.Tensor, want_mask: bool = False) -> Tuple[torch.Tensor, O
     rows, cols = x.shape
     out = torch.empty((rows, cols), dtype=BF16, device=x.device)
     mask = torch.empty((rows,), dtype=torch.uint8, device=x.device) if want_mask else None
-    _lib.check(_lib.load().cti_cast_rows_mask(x.data_ptr(), out.data_ptr(), _ptr(mask), rows, cols, _stream()),
-               "cti_cast_rows_mask")
+    _call("cti_cast_rows_mask", _lib.load().cti_cast_rows_mask,
+          (x.data_ptr(), out.data_ptr(), _ptr(mask), rows, cols, _stream()), nbytes=6.0 * rows * cols)
     return out, mask
 
 
@@ -53,8 +89,9 @@ def wn_pack(v: torch.Tensor, g: torch.Tensor, n_groups: int) -> Tuple[torch.Tens
     rows, cols = v.shape
     w = torch.empty((rows, cols), dtype=BF16, device=v.device)
     sumsq = torch.empty((n_groups,), dtype=F32, device=v.device)
-    _lib.check(_lib.load().cti_wn_pack(v.data_ptr(), g.data_ptr(), w.data_ptr(), sumsq.data_ptr(), n_groups,
-                                       rows // n_groups, cols, _stream()), "cti_wn_pack")
+    _call("cti_wn_pack", _lib.load().cti_wn_pack, (v.data_ptr(), g.data_ptr(), w.data_ptr(), sumsq.data_ptr(), n_groups,
+                                                   rows // n_groups, cols, _stream()), kernels=2,
+          nbytes=10.0 * rows * cols)
     return w, sumsq
 
 
@@ -66,9 +103,9 @@ def wn_grad(dw: torch.Tensor, v: torch.Tensor, g: torch.Tensor, sumsq: torch.Ten
     dv = torch.empty_like(v)
     dg = torch.empty((n_groups,), dtype=F32, device=v.device)
     ws = torch.empty((n_groups,), dtype=F32, device=v.device)
-    _lib.check(_lib.load().cti_wn_grad(dw.data_ptr(), v.data_ptr(), g.data_ptr(), sumsq.data_ptr(), dv.data_ptr(),
-                                       dg.data_ptr(), ws.data_ptr(), n_groups, rows // n_groups, cols, _stream()),
-               "cti_wn_grad")
+    _call("cti_wn_grad", _lib.load().cti_wn_grad,
+          (dw.data_ptr(), v.data_ptr(), g.data_ptr(), sumsq.data_ptr(), dv.data_ptr(), dg.data_ptr(), ws.data_ptr(),
+           n_groups, rows // n_groups, cols, _stream()), kernels=2, nbytes=20.0 * rows * cols)
     return dv, dg
 
 
@@ -85,10 +122,11 @@ def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool
     of = accum_f32 if accum_f32 is not None else (torch.empty((M, N), dtype=F32, device=a.device) if out_f32 else None)
     if relu_aux is not None:
         _req(relu_aux, BF16, "gemm.relu_aux")
-    _lib.check(_lib.load().cti_gemm_bf16(
+    _call("cti_gemm_bf16", _lib.load().cti_gemm_bf16, (
         a.data_ptr(), a.shape[1], int(a_mn), b.data_ptr(), b.shape[1], int(b_mn), M, N, K, float(alpha), _ptr(bias),
         int(relu), _ptr(relu_aux), 0 if relu_aux is None else relu_aux.shape[1], _ptr(ob), _ptr(of), N,
-        int(accum_f32 is not None), int(k_splits), int(tile_n), _stream()), "cti_gemm_bf16")
+        int(accum_f32 is not None), int(k_splits), int(tile_n), _stream()), flops=2.0 * M * N * K,
+        tag=f"{'wgrad' if a_mn else ('dgrad' if b_mn else 'fwd')} M={M} N={N} K={K}")
     return ob, of
 
 
@@ -99,16 +137,17 @@ def act_bwd_bias(dy: torch.Tensor, y: Optional[torch.Tensor], want_dz: bool,
     if dy.dtype not in (F32, BF16) or not dy.is_contiguous():
         raise RuntimeError("act_bwd_bias.dy: expected contiguous fp32 / bf16")
     dz = torch.empty((rows, cols), dtype=BF16, device=dy.device) if want_dz else None
-    _lib.check(_lib.load().cti_act_bwd_bias(dy.data_ptr(), int(dy.dtype == BF16), _ptr(y), _ptr(dz), _ptr(dbias), rows,
-                                            cols, _stream()), "cti_act_bwd_bias")
+    _call("cti_act_bwd_bias", _lib.load().cti_act_bwd_bias,
+          (dy.data_ptr(), int(dy.dtype == BF16), _ptr(y), _ptr(dz), _ptr(dbias), rows, cols, _stream()),
+          nbytes=float(rows) * cols * (dy.element_size() + (2 if y is not None else 0) + (2 if want_dz else 0)))
     return dz
 
 
 def softmax_fwd(logits: torch.Tensor, rows: int, length: int) -> torch.Tensor:
     _req(logits, F32, "softmax_fwd.logits")
     p = torch.empty_like(logits)
-    _lib.check(_lib.load().cti_masked_softmax_fwd(logits.data_ptr(), p.data_ptr(), rows, length, _stream()),
-               "cti_masked_softmax_fwd")
+    _call("cti_masked_softmax_fwd", _lib.load().cti_masked_softmax_fwd,
+          (logits.data_ptr(), p.data_ptr(), rows, length, _stream()), nbytes=8.0 * rows * length)
     return p
 
 
@@ -118,8 +157,9 @@ def softmax_bwd(p: torch.Tensor, dp: torch.Tensor, sb: int, sg: int, se: int, ba
     if dp.dtype != F32:
         raise RuntimeError("softmax_bwd.dp: expected fp32")
     dl = torch.empty_like(p)
-    _lib.check(_lib.load().cti_masked_softmax_bwd(p.data_ptr(), dp.data_ptr(), sb, sg, se, dl.data_ptr(), batch, groups,
-                                                  length, _stream()), "cti_masked_softmax_bwd")
+    _call("cti_masked_softmax_bwd", _lib.load().cti_masked_softmax_bwd,
+          (p.data_ptr(), dp.data_ptr(), sb, sg, se, dl.data_ptr(), batch, groups, length, _stream()),
+          nbytes=12.0 * batch * groups * length)
     return dl
 
 
@@ -127,9 +167,9 @@ def trilinear_fwd(vc, qc, ac, tpack, rowmask, B, K, Q, A, G, R) -> torch.Tensor:
     for t, n in ((vc, "vc"), (qc, "qc"), (ac, "ac"), (tpack, "tpack")):
         _req(t, BF16, "trilinear_fwd." + n)
     logits = torch.empty((B, G, K, Q, A), dtype=F32, device=vc.device)
-    _lib.check(_lib.load().cti_trilinear_logits_fwd(vc.data_ptr(), qc.data_ptr(), ac.data_ptr(), tpack.data_ptr(),
-                                                    _ptr(rowmask), logits.data_ptr(), B, K, Q, A, G, R, _stream()),
-               "cti_trilinear_logits_fwd")
+    _call("cti_trilinear_logits_fwd", _lib.load().cti_trilinear_logits_fwd,
+          (vc.data_ptr(), qc.data_ptr(), ac.data_ptr(), tpack.data_ptr(), _ptr(rowmask), logits.data_ptr(), B, K, Q, A, G,
+           R, _stream()), flops=float(B) * trilinear_min_flops(K, Q, A, G, R))
     return logits
 
 
@@ -144,18 +184,19 @@ def trilinear_bwd(vc, qc, ac, tpack, dlogits, B, K, Q, A, G, R):
     dtpack = zeros[3 * R * 16:]
     nbytes = lib.cti_trilinear_logits_bwd_workspace(B, K, Q, A, G, R)
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
-    _lib.check(lib.cti_trilinear_logits_bwd(vc.data_ptr(), qc.data_ptr(), ac.data_ptr(), tpack.data_ptr(),
-                                            dlogits.data_ptr(), dzv.data_ptr(), dzq.data_ptr(), dza.data_ptr(),
-                                            dbv.data_ptr(), dbq.data_ptr(), dba.data_ptr(), dtpack.data_ptr(),
-                                            ws.data_ptr(), nbytes, B, K, Q, A, G, R, _stream()),
-               "cti_trilinear_logits_bwd")
+    _call("cti_trilinear_logits_bwd", lib.cti_trilinear_logits_bwd,
+          (vc.data_ptr(), qc.data_ptr(), ac.data_ptr(), tpack.data_ptr(), dlogits.data_ptr(), dzv.data_ptr(),
+           dzq.data_ptr(), dza.data_ptr(), dbv.data_ptr(), dbq.data_ptr(), dba.data_ptr(), dtpack.data_ptr(),
+           ws.data_ptr(), nbytes, B, K, Q, A, G, R, _stream()), kernels=2,
+          flops=2.0 * B * trilinear_min_flops(K, Q, A, G, R))
     return dzv, dzq, dza, dbv, dbq, dba, dtpack
 
 
 def tri_pool_fwd(v, q, a, w, w_stride_b, B, K, Q, A, C) -> torch.Tensor:
     out = torch.empty((B, C), dtype=F32, device=v.device)
-    _lib.check(_lib.load().cti_tri_pool_fwd(v.data_ptr(), q.data_ptr(), _ptr(a), w.data_ptr(), w_stride_b,
-                                            out.data_ptr(), B, K, Q, A, C, _stream()), "cti_tri_pool_fwd")
+    _call("cti_tri_pool_fwd", _lib.load().cti_tri_pool_fwd,
+          (v.data_ptr(), q.data_ptr(), _ptr(a), w.data_ptr(), w_stride_b, out.data_ptr(), B, K, Q, A, C, _stream()),
+          flops=float(B) * pool_flops(K, Q, A, C))
     return out
 
 
@@ -168,10 +209,10 @@ def tri_pool_bwd(v, q, a, w, w_stride_b, dout, B, K, Q, A, C):
     zeros = torch.zeros((3 * C,), dtype=F32, device=dev)
     dbv, dbq, dba = zeros[:C], zeros[C:2 * C], zeros[2 * C:]
     dw = torch.empty((B, K, Q, A) if A > 0 else (B, K, Q), dtype=F32, device=dev)
-    _lib.check(_lib.load().cti_tri_pool_bwd(v.data_ptr(), q.data_ptr(), _ptr(a), w.data_ptr(), w_stride_b,
-                                            dout.data_ptr(), dzv.data_ptr(), dzq.data_ptr(), _ptr(dza), dbv.data_ptr(),
-                                            dbq.data_ptr(), dba.data_ptr(), dw.data_ptr(), B, K, Q, A, C, _stream()),
-               "cti_tri_pool_bwd")
+    _call("cti_tri_pool_bwd", _lib.load().cti_tri_pool_bwd,
+          (v.data_ptr(), q.data_ptr(), _ptr(a), w.data_ptr(), w_stride_b, dout.data_ptr(), dzv.data_ptr(), dzq.data_ptr(),
+           _ptr(dza), dbv.data_ptr(), dbq.data_ptr(), dba.data_ptr(), dw.data_ptr(), B, K, Q, A, C, _stream()),
+          flops=2.0 * B * pool_flops(K, Q, A, C))
     return dzv, dzq, dza, dbv, dbq, (dba if A > 0 else None), dw
 
 
@@ -179,9 +220,9 @@ def bilinear_fwd(vb, qb, hmat, hbias, rowmask, B, K, Q, G, C) -> torch.Tensor:
     _req(hmat, F32, "bilinear_fwd.hmat")
     _req(hbias, F32, "bilinear_fwd.hbias")
     logits = torch.empty((B, G, K, Q), dtype=F32, device=vb.device)
-    _lib.check(_lib.load().cti_bilinear_logits_fwd(vb.data_ptr(), qb.data_ptr(), hmat.data_ptr(), hbias.data_ptr(),
-                                                   _ptr(rowmask), logits.data_ptr(), B, K, Q, G, C, _stream()),
-               "cti_bilinear_logits_fwd")
+    _call("cti_bilinear_logits_fwd", _lib.load().cti_bilinear_logits_fwd,
+          (vb.data_ptr(), qb.data_ptr(), hmat.data_ptr(), hbias.data_ptr(), _ptr(rowmask), logits.data_ptr(), B, K, Q, G,
+           C, _stream()), flops=2.0 * B * K * Q * G * C)
     return logits
 
 
@@ -194,8 +235,8 @@ def bilinear_bwd(vb, qb, hmat, dlogits, B, K, Q, G, C):
     dbv, dbq = zeros[:C], zeros[C:2 * C]
     dh = zeros[2 * C:2 * C + G * C].view(G, C)
     dhb = zeros[2 * C + G * C:]
-    _lib.check(_lib.load().cti_bilinear_logits_bwd(vb.data_ptr(), qb.data_ptr(), hmat.data_ptr(), dlogits.data_ptr(),
-                                                   dzv.data_ptr(), dzq.data_ptr(), dbv.data_ptr(), dbq.data_ptr(),
-                                                   dh.data_ptr(), dhb.data_ptr(), B, K, Q, G, C, _stream()),
-               "cti_bilinear_logits_bwd")
+    _call("cti_bilinear_logits_bwd", _lib.load().cti_bilinear_logits_bwd,
+          (vb.data_ptr(), qb.data_ptr(), hmat.data_ptr(), dlogits.data_ptr(), dzv.data_ptr(), dzq.data_ptr(),
+           dbv.data_ptr(), dbq.data_ptr(), dh.data_ptr(), dhb.data_ptr(), B, K, Q, G, C, _stream()),
+          flops=4.0 * B * K * Q * G * C)
     return dzv, dzq, dbv, dbq, dh, dhb

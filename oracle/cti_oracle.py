@@ -36,6 +36,54 @@ import torch
 
 Params = Dict[str, torch.Tensor]
 
+# --------------------------------------------------------------------------- #
+# Optional bf16 rounding points.  By default every function below is the plain fp32 restatement
+# of the reference.  Inside ``with bf16_rounding():`` the operands the CUDA kernels hold in bf16
+# (cast inputs, folded weights, stored layer outputs, the packed core and the two on-chip
+# intermediates of the contraction, the attention weights fed to the pooling) are rounded to bf16
+# with a straight-through gradient.  The values then differ from the fp32 oracle by the bf16
+# quantisation the kernels are allowed (north_star: "bf16 inputs, fp32 accumulate"), but every ReLU
+# sees the same pre-activation sign as the kernels do, so autograd of this variant is the reference
+# for the hand-written BACKWARD kernels (see tests/test_gpu_modules.py on why the ReLU masks matter).
+# --------------------------------------------------------------------------- #
+_ROUND = [False]
+
+
+class bf16_rounding:
+    def __enter__(self):
+        self.prev = _ROUND[0]
+        _ROUND[0] = True
+
+    def __exit__(self, *exc):
+        _ROUND[0] = self.prev
+
+
+def _r(x: torch.Tensor) -> torch.Tensor:
+    if not _ROUND[0]:
+        return x
+    return x + (x.to(torch.bfloat16).to(x.dtype) - x).detach()
+
+
+# Optional externally supplied ReLU masks, keyed by the layer's parameter prefix
+# (e.g. ``'v_att.TriAtt.v_net.3.main.1.'``).  A layer with an entry computes ``z * mask`` instead of
+# ``relu(z)``: the oracle is then evaluated on the same linear piece of the network as the
+# implementation whose masks were recorded, which removes the only discontinuous step of the path
+# from a gradient comparison (a pre-activation within rounding distance of zero may get a different
+# sign in bf16 arithmetic than in fp32; each such flip switches a gradient entry on or off).
+_MASKS = [None]
+
+
+class relu_masks:
+    def __init__(self, masks: Dict[str, torch.Tensor]):
+        self.masks = masks
+
+    def __enter__(self):
+        self.prev = _MASKS[0]
+        _MASKS[0] = self.masks
+
+    def __exit__(self, *exc):
+        _MASKS[0] = self.prev
+
 
 # --------------------------------------------------------------------------- #
 # FCNet (reference src/fc.py:10-34)
@@ -52,10 +100,13 @@ def wn_linear(x: torch.Tensor, p: Params, prefix: str, act: str = "ReLU") -> tor
     v = p[prefix + "weight_v"]
     g = p[prefix + "weight_g"]
     b = p[prefix + "bias"]
-    w = v * (g / v.norm())
-    y = torch.matmul(x, w.t()) + b
+    w = _r(v * (g / v.norm()))
+    y = torch.matmul(_r(x), w.t()) + b
     if act == "ReLU":
-        y = torch.relu(y)
+        if _MASKS[0] is not None and prefix in _MASKS[0]:
+            y = _r(y * _MASKS[0][prefix].reshape(y.shape).to(y.dtype))
+        else:
+            y = _r(torch.relu(y))      # fused layers store their (post-ReLU) output in bf16
     elif act != "":
         raise ValueError("oracle covers act in {'ReLU',''} only")
     return y
@@ -151,8 +202,8 @@ def tcnet_logits_closed(v, q, a, p: Params, prefix: str = "") -> torch.Tensor:
 def trilinear_closed(vc, qc, ac, t_eff) -> torch.Tensor:
     """logits[b,k,q,a,g] = sum_{r,i,j,l} T_eff[r,i,j,l,g] Vc[b,k,r,i] Qc[b,q,r,j] Ac[b,a,r,l],
     contracted a -> q -> v (the minimal-FLOP order)."""
-    n1 = torch.einsum("balr,rijlg->barijg", ac.permute(0, 1, 3, 2), t_eff)
-    m = torch.einsum("bqrj,barijg->briqag", qc, n1)
+    n1 = _r(torch.einsum("balr,rijlg->barijg", ac.permute(0, 1, 3, 2), _r(t_eff)))
+    m = _r(torch.einsum("bqrj,barijg->briqag", qc, n1))
     return torch.einsum("bkri,briqag->bkqag", vc, m)
 
 
@@ -164,7 +215,8 @@ def zero_row_mask(v: torch.Tensor) -> torch.Tensor:
 def tri_attention(v, q, a, p: Params, prefix: str = "TriAtt.") -> Tuple[torch.Tensor, torch.Tensor]:
     """``TriAttention.forward`` (src/attention.py:49-59): logits, zero-row mask to
     -inf, softmax over the flattened (k,q,a) axis per (b,g). Returns (p, logits)."""
-    logits = tcnet_logits(v, q, a, p, prefix)
+    # with rounding points on, follow the kernels' contraction order (a -> q -> v) so they apply
+    logits = tcnet_logits_closed(v, q, a, p, prefix) if _ROUND[0] else tcnet_logits(v, q, a, p, prefix)
     B, K, Q, A, G = logits.shape
     logits = logits.masked_fill(zero_row_mask(v)[:, :, None, None, None], float("-inf"))
     att = torch.softmax(logits.reshape(B, K * Q * A, G), 1).view(B, K, Q, A, G)
@@ -181,7 +233,7 @@ def tcnet_pool(v, q, a, w, p: Params, prefix: str = "") -> torch.Tensor:
 
 
 def trilinear_pool(vp, qp, ap, w) -> torch.Tensor:
-    return torch.einsum("bkc,bkqa,bqc,bac->bc", vp, w, qp, ap)
+    return torch.einsum("bkc,bkqa,bqc,bac->bc", vp, _r(w), qp, ap)
 
 
 # --------------------------------------------------------------------------- #
@@ -203,6 +255,9 @@ def bcnet_logits(v, q, p: Params, prefix: str = "", h_mat: torch.Tensor | None =
 
 
 def bilinear_closed(vb, qb, h_mat, h_bias) -> torch.Tensor:
+    if _ROUND[0]:                                    # the kernel folds h_mat into the question operand
+        hq = _r(qb.unsqueeze(1) * h_mat)             # (B,G,Q,C)
+        return torch.matmul(vb.unsqueeze(1), hq.transpose(2, 3)) + h_bias
     hv = vb.unsqueeze(1) * h_mat                     # (B,G,K,C)
     return torch.matmul(hv, qb.unsqueeze(1).transpose(2, 3)) + h_bias
 
@@ -223,7 +278,7 @@ def bcnet_pool(v, q, w, p: Params, prefix: str = "", k: int = 1) -> torch.Tensor
     k are sum-pooled (AvgPool1d(k) * k, :75-77)."""
     vp = fcnet(v, p, prefix + "v_net.", dropout=0.2)
     qp = fcnet(q, p, prefix + "q_net.", dropout=0.2)
-    out = torch.einsum("bkc,bkq,bqc->bc", vp, w, qp)
+    out = torch.einsum("bkc,bkq,bqc->bc", vp, _r(w), qp)
     if k > 1:
         out = out.view(out.shape[0], -1, k).sum(2)
     return out
