@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--cpu-rows", type=int, default=128, help="rows per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--resident-only", action="store_true", help="skip the e2e / forward-only arms (for ncu runs)")
     return ap.parse_args()
 
 
@@ -240,12 +241,14 @@ def run_b200(args):
         joint = step(v, q, a)
         out_h.copy_(joint.detach(), non_blocking=True)
 
-    for _ in range(3):
-        e2e_step()
-    ms_e2e, _, _ = timed(e2e_step, args.steps)
-    e2e = {"value": world * B * args.steps / (ms_e2e / 1e3), "unit": UNIT,
-           "h2d_bytes_per_step": (v_h.numel() + q_h.numel() + a_h.numel()) * 4, "d2h_bytes_per_step": out_h.numel() * 4,
-           "ms_per_step": ms_e2e / args.steps}
+    e2e = fwd = None
+    if not args.resident_only:
+        for _ in range(3):
+            e2e_step()
+        ms_e2e, _, _ = timed(e2e_step, args.steps)
+        e2e = {"value": world * B * args.steps / (ms_e2e / 1e3), "unit": UNIT,
+               "h2d_bytes_per_step": (v_h.numel() + q_h.numel() + a_h.numel()) * 4,
+               "d2h_bytes_per_step": out_h.numel() * 4, "ms_per_step": ms_e2e / args.steps}
 
     # ---- forward-only (config[1] of BASELINE.json) -----------------------------
     def fwd_only():
@@ -258,10 +261,11 @@ def run_b200(args):
                 ae = a_prj[gi](b_emb.unsqueeze(1)) + ae
             return qe.sum(1) + ae.sum(1)
 
-    for _ in range(3):
-        fwd_only()
-    ms_f, _, _ = timed(fwd_only, args.steps)
-    fwd = {"value": world * B * args.steps / (ms_f / 1e3), "unit": UNIT, "ms_per_step": ms_f / args.steps}
+    if not args.resident_only:
+        for _ in range(3):
+            fwd_only()
+        ms_f, _, _ = timed(fwd_only, args.steps)
+        fwd = {"value": world * B * args.steps / (ms_f / 1e3), "unit": UNIT, "ms_per_step": ms_f / args.steps}
 
     # ---- per-kernel CUDA-event timing of the same step (rank 0) -----------------
     roofline, kernels = None, None
