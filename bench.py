@@ -327,7 +327,7 @@ def run_b200(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": workload_config(B, world), "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+                "config": workload_config(B, world), "e2e": e2e, "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps, "clocks": clocks,
                 "fwd_only": fwd, "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -1,372 +1,407 @@
-// Attention-weighted trilinear / bilinear pooling to the joint embedding (sm_100a):
+// Attention-weighted trilinear / bilinear pooling to the joint embedding (sm_100a, tcgen05):
 //   TCNet.forward_with_weights  (reference src/tc.py:54-61)
 //       out[b,c] = sum_{k,q,a} V[b,k,c] w[b,k,q,a] Qp[b,q,c] Ap[b,a,c]
 //   BCNet.forward_with_weights  (reference src/bc.py:70-74)  -- the A == 0 case, Ap == 1
-//       out[b,c] = sum_{k,q}   V[b,k,c] w[b,k,q]   Qp[b,q,c]
 //
-// Forward, per sample and per 128-channel chunk, on tensor cores:
-//   Z[(q,a), c] = sum_k w[k,(q,a)] V[k,c]          (QA x K) . (K x 128)
-//   out[c]      = sum_{(q,a)} Qp[q,c] Ap[a,c] Z[(q,a),c]       (Khatri-Rao dot, in the epilogue)
-// so the (B,C,K,Q,A) broadcast product of the reference's einsum never exists.
+// Per sample and per 128-channel chunk (TMEM lane = channel c, column n = a*16 + q):
+//   forward   Z[c,n]   = sum_k V[k,c] w[k,n]                      tcgen05.mma 128 x NC x 16, K = tokens
+//             out[c]   = sum_a Ap[a,c] sum_q Qp[q,c] Z[c,(a,q)]   epilogue: a per-thread dot product
+//   backward  dQp, dAp from Z (same epilogue shape);  KRd[c,n] = do[c] Qp[q,c] Ap[a,c] written to
+//             shared memory ONCE and used by two more MMAs:
+//             dV[c,k]  = sum_n KRd[c,n] w[k,n]                     128 x 64 x 16, K = columns n
+//             dw[k,n] += sum_c V[k,c] KRd[c,n]                     128 x NC x 16, K = channels (all chunks)
+// The (B,C,K,Q,A) broadcast product of the reference's einsum never exists; V is read from HBM
+// once per pass (TMA, 128B swizzle).  Every operand tile lives in shared memory in the TMA
+// swizzle layout, so the SAME buffer is consumed K-major by one MMA and MN-major by another
+// (tc_tiles.cuh): V as A(MN) for Z and A(K) for dw; w as B(MN) for Z and B(K) for dV; KRd as A(K)
+// for dV and B(MN) for dw.
 //
-// Backward (appendix B of SURVEY.md), same tiling:
-//   dQp[q,c] = do[c] sum_a Ap[a,c] Z[(q,a),c]     dAp[a,c] = do[c] sum_q Qp[q,c] Z[(q,a),c]
-//   dV[k,c]  = sum_{(q,a)} w[k,(q,a)] KRd[(q,a),c]                  KRd = do * Qp * Ap
-//   dw[k,(q,a)] = sum_c V[k,c] KRd[(q,a),c]
-// The ReLU masks of the producing projections are applied here (V, Qp, Ap are post-ReLU), so
-// the outputs are pre-activation gradients dz*, plus their bias gradients.
+// The ReLU masks of the producing projections are applied here (V, Qp, Ap are post-ReLU), so the
+// backward outputs are pre-activation gradients dz* plus their bias gradients.
+//
+// Roles (384 threads): warp 0 TMA producer (V tiles) | warp 1 MMA issuer | warp 2 TMEM allocator |
+// warps 4-7 epilogue (TMEM lane quarter = warp % 4) | warps 8-11 build the bf16 w tile of the next sample.
 #include "cti_common.cuh"
 #include "cti_kernels.h"
-
-#include "wmma_tiles.cuh"
+#include "tc_tiles.cuh"
 
 namespace cti {
 
 namespace {
 
-using namespace tiles;
+using bf16 = __nv_bfloat16;
 
-constexpr int kCC = 128;            // channels per chunk (one 16-wide tile per warp)
-constexpr int kLdC = kCC + 8;
+constexpr int kThreads = 384;
+constexpr int kEpiWarp0 = 4;
+constexpr int kBuildWarp0 = 8;
+constexpr int CCH = 128;                       // channels per chunk = TMEM lanes
+constexpr int KP = 64;                         // token rows per tile
+constexpr int V_STAGES = 4;
+constexpr int V_STAGE_BYTES = 2 * KP * 128;    // two 64-channel halves
+constexpr int W_BYTES = 2 * KP * 128;          // two 64-column chunks
+constexpr int KRD_BYTES = 2 * CCH * 128;       // two 64-column chunks x 128 channel rows
+constexpr int MAX_C = 1024;
 
-struct PoolShape {
-  int B, K, Q, A, C;
-  int An;      // max(A, 1)
-  int QA;      // Q * An
-  int QAT;     // ceil(QA / 16)
-  int MT;      // ceil(K / 16)
-  int LDW;     // QAT * 16 + 8
-  int NCH;     // C / kCC
+// TMEM column map
+constexpr uint32_t TM_Z = 0, TM_DV = 256, TM_DW = 384;     // Z: 2 x 128, dV: 2 x 64, dw: 128
+
+struct PoolParams {
+  const bf16* q;
+  const bf16* a;
+  const float* w;
+  long w_stride_b;
+  float* out;            // forward
+  const float* dout;     // backward
+  bf16 *dzv, *dzq, *dza;
+  float *dbv, *dbq, *dba, *dw;
+  int B, K, Q, A, An, C, NC, nchunks;
 };
 
-__host__ __device__ inline PoolShape make_pool_shape(PoolDims d) {
-  PoolShape s;
-  s.B = d.B; s.K = d.K; s.Q = d.Q; s.A = d.A; s.C = d.C;
-  s.An = d.A > 0 ? d.A : 1;
-  s.QA = d.Q * s.An;
-  s.QAT = (s.QA + 15) / 16;
-  s.MT = (d.K + 15) / 16;
-  s.LDW = s.QAT * 16 + 8;
-  s.NCH = d.C / kCC;
-  return s;
-}
-
-struct PoolSmem {
-  size_t off_w, off_v, off_q, off_a, off_kr, off_scr, off_do, off_db, total;
+struct Smem {
+  uint32_t v, w, krd, db, bars;
 };
+// barrier indices
+enum { B_VFULL = 0, B_VEMPTY = 4, B_WFULL = 8, B_WEMPTY = 10, B_ZFULL = 12, B_ZEMPTY = 14, B_KFULL = 16, B_KEMPTY = 18,
+       B_DFULL = 20, B_DEMPTY = 22, B_DWFULL = 24, B_DWEMPTY = 25, B_COUNT = 26 };
 
-__host__ __device__ inline PoolSmem pool_smem(const PoolShape& s, bool bwd) {
-  PoolSmem m;
-  size_t o = 0;
-  m.off_w = o; o = align_up(o + (size_t)s.MT * 16 * s.LDW * 2, 128);
-  m.off_v = o; o = align_up(o + (size_t)2 * s.MT * 16 * kLdC * 2, 128);
-  m.off_q = o; o = align_up(o + (size_t)s.Q * s.C * 2, 128);
-  m.off_a = o; o = align_up(o + (size_t)s.An * s.C * 2, 128);
-  m.off_kr = o; if (bwd) o = align_up(o + (size_t)s.QAT * 16 * kLdC * 2, 128);
-  m.off_scr = o; o = align_up(o + (size_t)kWarps * kScrFloats * 4, 128);
-  m.off_do = o; if (bwd) o = align_up(o + (size_t)s.C * 4, 128);
-  m.off_db = o; if (bwd) o = align_up(o + (size_t)3 * s.C * 4, 128);
-  m.total = o;
-  return m;
+__host__ __device__ inline size_t pool_smem_bytes(bool bwd) {
+  size_t o = V_STAGES * V_STAGE_BYTES + 2 * W_BYTES;
+  if (bwd) o += 2 * KRD_BYTES + 3 * MAX_C * 4;
+  return o + B_COUNT * 8 + 16 + 1024;
 }
 
-// Stage one 128-channel chunk of V (K rows) with cp.async; pad rows were zeroed once.
-__device__ __forceinline__ void prefetch_v_chunk(bf16* dst, const bf16* v_sample, int K, int C, int c0) {
-  for (int c = threadIdx.x; c < K * (kCC / 8); c += kThreads) {
-    const int row = c / (kCC / 8), col = (c - row * (kCC / 8)) * 8;
-    cp_async16(smem_u32(dst + (size_t)row * kLdC + col), v_sample + (size_t)row * C + c0 + col);
-  }
-  cp_async_commit();
-}
-
-// Load w (K x QA fp32) as the bf16 matrix sW[k][qa] (zero padded), Qp and Ap rows.
-__device__ __forceinline__ void stage_sample(const PoolShape& s, bf16* sW, bf16* sQ, bf16* sA, const float* w_sample,
-                                             const bf16* q_sample, const bf16* a_sample) {
-  for (int e = threadIdx.x; e < s.K * s.QA; e += kThreads) {
-    const int k = e / s.QA, qa = e - k * s.QA;
-    sW[(size_t)k * s.LDW + qa] = __float2bfloat16(__ldg(w_sample + e));
-  }
-  const int rc = s.C / 8;
-  for (int c = threadIdx.x; c < s.Q * rc; c += kThreads)
-    reinterpret_cast<uint4*>(sQ)[c] = __ldg(reinterpret_cast<const uint4*>(q_sample) + c);
-  if (s.A > 0) {
-    for (int c = threadIdx.x; c < s.A * rc; c += kThreads)
-      reinterpret_cast<uint4*>(sA)[c] = __ldg(reinterpret_cast<const uint4*>(a_sample) + c);
-  }
-}
-
-// --------------------------------------------------------------------------- //
-__global__ void __launch_bounds__(kThreads)
-tri_pool_fwd_kernel(const bf16* __restrict__ v, const bf16* __restrict__ q, const bf16* __restrict__ a,
-                    const float* __restrict__ w, long w_stride_b, float* __restrict__ out, const PoolDims dims) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  const PoolShape s = make_pool_shape(dims);
-  const PoolSmem lay = pool_smem(s, false);
-  bf16* sW = reinterpret_cast<bf16*>(smem + lay.off_w);
-  bf16* sV = reinterpret_cast<bf16*>(smem + lay.off_v);
-  bf16* sQ = reinterpret_cast<bf16*>(smem + lay.off_q);
-  bf16* sA = reinterpret_cast<bf16*>(smem + lay.off_a);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* scr = reinterpret_cast<float*>(smem + lay.off_scr) + warp * kScrFloats;
-  const int KP = s.MT * 16;
-
-  for (size_t i = threadIdx.x; i < lay.off_q / 4; i += kThreads) reinterpret_cast<uint32_t*>(smem)[i] = 0u;   // sW, sV pads
-  __syncthreads();
-
-  int it = 0;
-  for (int b = blockIdx.x; b < s.B; b += gridDim.x) {
-    const bf16* vb = v + (size_t)b * s.K * s.C;
-    __syncthreads();                                   // previous sample done with sW / sQ / sA / sV
-    stage_sample(s, sW, sQ, sA, w + (size_t)b * w_stride_b, q + (size_t)b * s.Q * s.C,
-                 s.A > 0 ? a + (size_t)b * s.A * s.C : nullptr);
-    prefetch_v_chunk(sV + (size_t)(it & 1) * KP * kLdC, vb, s.K, s.C, 0);
-    for (int ch = 0; ch < s.NCH; ++ch, ++it) {
-      cp_async_wait_all();
-      __syncthreads();
-      if (ch + 1 < s.NCH) prefetch_v_chunk(sV + (size_t)((it + 1) & 1) * KP * kLdC, vb, s.K, s.C, (ch + 1) * kCC);
-      const bf16* vch = sV + (size_t)(it & 1) * KP * kLdC + warp * 16;
-      FragC acc[kMaxAcc];
-#pragma unroll
-      for (int u = 0; u < kMaxAcc; ++u) wmma::fill_fragment(acc[u], 0.f);
-      for (int ks = 0; ks < s.MT; ++ks) {
-        FragBR fb;                                     // (k = k, n = c)
-        wmma::load_matrix_sync(fb, vch + (size_t)ks * 16 * kLdC, kLdC);
-#pragma unroll
-        for (int u = 0; u < kMaxAcc; ++u) {
-          if (u < s.QAT) {
-            FragAC fa;                                 // (m = qa, k = k) at sW[k][qa]
-            wmma::load_matrix_sync(fa, sW + (size_t)ks * 16 * s.LDW + u * 16, s.LDW);
-            wmma::mma_sync(acc[u], fa, fb, acc[u]);
-          }
-        }
-      }
-      const int c = ch * kCC + warp * 16 + (lane & 15);
-      float part = 0.f;
-#pragma unroll
-      for (int u = 0; u < kMaxAcc; ++u) {
-        if (u < s.QAT) {
-          wmma::store_matrix_sync(scr, acc[u], kScrLd, wmma::mem_row_major);   // scr[qa_local][c_local]
-          __syncwarp();
-          for (int row = lane >> 4; row < 16; row += 2) {
-            const int qa = u * 16 + row;
-            if (qa < s.QA) {
-              const int qi = qa / s.An, ai = qa - qi * s.An;
-              float kr = __bfloat162float(sQ[(size_t)qi * s.C + c]);
-              if (s.A > 0) kr *= __bfloat162float(sA[(size_t)ai * s.C + c]);
-              part += kr * scr[row * kScrLd + (lane & 15)];
-            }
-          }
-          __syncwarp();
-        }
-      }
-      part += __shfl_xor_sync(0xffffffffu, part, 16);
-      if (lane < 16) out[(size_t)b * s.C + c] = part;
-    }
-  }
-  cp_async_wait_all();
-}
-
-// --------------------------------------------------------------------------- //
+template <bool BWD>
 __global__ void __launch_bounds__(kThreads, 1)
-tri_pool_bwd_kernel(const bf16* __restrict__ v, const bf16* __restrict__ q, const bf16* __restrict__ a,
-                    const float* __restrict__ w, long w_stride_b, const float* __restrict__ dout,
-                    bf16* __restrict__ dzv, bf16* __restrict__ dzq, bf16* __restrict__ dza, float* __restrict__ dbv,
-                    float* __restrict__ dbq, float* __restrict__ dba, float* __restrict__ dw, const PoolDims dims) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  const PoolShape s = make_pool_shape(dims);
-  const PoolSmem lay = pool_smem(s, true);
-  bf16* sW = reinterpret_cast<bf16*>(smem + lay.off_w);
-  bf16* sV = reinterpret_cast<bf16*>(smem + lay.off_v);
-  bf16* sQ = reinterpret_cast<bf16*>(smem + lay.off_q);
-  bf16* sA = reinterpret_cast<bf16*>(smem + lay.off_a);
-  bf16* sKR = reinterpret_cast<bf16*>(smem + lay.off_kr);
-  float* sDo = reinterpret_cast<float*>(smem + lay.off_do);
-  float* sDb = reinterpret_cast<float*>(smem + lay.off_db);     // [3][C]
+pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const PoolParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sV = base;
+  const uint32_t sW = sV + V_STAGES * V_STAGE_BYTES;
+  const uint32_t sK = sW + 2 * W_BYTES;
+  const uint32_t sDb = sK + (BWD ? 2 * KRD_BYTES : 0);
+  const uint32_t sBar = sDb + (BWD ? 3 * MAX_C * 4 : 0);
+  const uint32_t tmem_slot = sBar + B_COUNT * 8;
+  auto bar = [&](int i) { return sBar + 8u * i; };
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));     // generic pointer to the aligned base
+  float* db_acc = reinterpret_cast<float*>(gen + (sDb - base));
+
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* scr = reinterpret_cast<float*>(smem + lay.off_scr) + warp * kScrFloats;
-  const int KP = s.MT * 16;
-  const int dw_tiles = s.MT * s.QAT;
 
-  for (size_t i = threadIdx.x; i < lay.total / 4; i += kThreads) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+  // zero the w tiles (pad rows / columns stay zero for the whole kernel) and the bias accumulators
+  for (uint32_t i = threadIdx.x; i < 2 * W_BYTES / 16; i += kThreads) st_shared_v4(sW + i * 16, 0, 0, 0, 0);
+  if (BWD)
+    for (int i = threadIdx.x; i < 3 * MAX_C; i += kThreads) db_acc[i] = 0.f;
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_v);
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < V_STAGES; ++s) {
+      mbar_init(bar(B_VFULL + s), 1);
+      mbar_init(bar(B_VEMPTY + s), BWD ? 5 : 1);      // MMA commit (+ the 4 epilogue warps that read V in backward)
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar(B_WFULL + s), 128);
+      mbar_init(bar(B_WEMPTY + s), 1);
+      mbar_init(bar(B_ZFULL + s), 1);
+      mbar_init(bar(B_ZEMPTY + s), 4);
+      mbar_init(bar(B_KFULL + s), 4);
+      mbar_init(bar(B_KEMPTY + s), 1);
+      mbar_init(bar(B_DFULL + s), 1);
+      mbar_init(bar(B_DEMPTY + s), 4);
+    }
+    mbar_init(bar(B_DWFULL), 1);
+    mbar_init(bar(B_DWEMPTY), 4);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();          // zero fill of sW visible to the async proxy
+  tcgen05_fence_before();
   __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  int it = 0;
-  for (int b = blockIdx.x; b < s.B; b += gridDim.x) {
-    const bf16* vb = v + (size_t)b * s.K * s.C;
-    __syncthreads();
-    stage_sample(s, sW, sQ, sA, w + (size_t)b * w_stride_b, q + (size_t)b * s.Q * s.C,
-                 s.A > 0 ? a + (size_t)b * s.A * s.C : nullptr);
-    for (int c = threadIdx.x; c < s.C; c += kThreads) sDo[c] = __ldg(dout + (size_t)b * s.C + c);
-    prefetch_v_chunk(sV + (size_t)(it & 1) * KP * kLdC, vb, s.K, s.C, 0);
-    FragC accW[3];                                      // dw tiles owned by this warp (<= 3: MT*QAT <= 24)
-#pragma unroll
-    for (int u = 0; u < 3; ++u) wmma::fill_fragment(accW[u], 0.f);
+  const int n_my = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total = n_my * p.nchunks;
+  const int ktok = (p.K + 15) >> 4;         // K steps over tokens
+  const int kcol = p.NC >> 4;               // K steps over columns
 
-    for (int ch = 0; ch < s.NCH; ++ch, ++it) {
-      const int c0 = ch * kCC;
-      __syncthreads();                                  // previous chunk's readers of sKR are done; sDo/sQ/sA visible
-      // KRd[(q,a)][c] = do[c] Qp[q,c] Ap[a,c] for this chunk (pad rows stay zero)
-      for (int e = threadIdx.x; e < s.QA * kCC; e += kThreads) {
-        const int qa = e / kCC, cl = e - qa * kCC;
-        const int qi = qa / s.An, ai = qa - qi * s.An;
-        float kr = sDo[c0 + cl] * __bfloat162float(sQ[(size_t)qi * s.C + c0 + cl]);
-        if (s.A > 0) kr *= __bfloat162float(sA[(size_t)ai * s.C + c0 + cl]);
-        sKR[(size_t)qa * kLdC + cl] = __float2bfloat16(kr);
+  if (warp == 0) {
+    // ------------------------------ TMA producer: V tiles ------------------------------
+    if (lane == 0) {
+      for (int g = 0; g < total; ++g) {
+        const int b = blockIdx.x + (g / p.nchunks) * gridDim.x, ch = g % p.nchunks;
+        const int st = g % V_STAGES;
+        mbar_wait(bar(B_VEMPTY + st), ((g / V_STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(bar(B_VFULL + st), V_STAGE_BYTES);
+        tma_load_3d(&tmap_v, bar(B_VFULL + st), sV + st * V_STAGE_BYTES, ch * CCH, 0, b);
+        tma_load_3d(&tmap_v, bar(B_VFULL + st), sV + st * V_STAGE_BYTES + KP * 128, ch * CCH + 64, 0, b);
       }
-      cp_async_wait_all();
-      __syncthreads();
-      if (ch + 1 < s.NCH) prefetch_v_chunk(sV + (size_t)((it + 1) & 1) * KP * kLdC, vb, s.K, s.C, c0 + kCC);
-      const bf16* vbuf = sV + (size_t)(it & 1) * KP * kLdC;
-      const int cl = warp * 16 + (lane & 15);
-      const int c = c0 + cl;
-      const float doc = sDo[c];
-
-      // ---- (1) Z tiles -> dQp, dAp ----
-      {
-        FragC acc[kMaxAcc];
-#pragma unroll
-        for (int u = 0; u < kMaxAcc; ++u) wmma::fill_fragment(acc[u], 0.f);
-        for (int ks = 0; ks < s.MT; ++ks) {
-          FragBR fb;
-          wmma::load_matrix_sync(fb, vbuf + (size_t)ks * 16 * kLdC + warp * 16, kLdC);
-#pragma unroll
-          for (int u = 0; u < kMaxAcc; ++u) {
-            if (u < s.QAT) {
-              FragAC fa;
-              wmma::load_matrix_sync(fa, sW + (size_t)ks * 16 * s.LDW + u * 16, s.LDW);
-              wmma::mma_sync(acc[u], fa, fb, acc[u]);
-            }
-          }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------------------
+    if (lane == 0) {
+      const uint32_t id_z = make_idesc_rt(128, p.NC, 1, 1);
+      const uint32_t id_dv = make_idesc_rt(128, 64, 0, 0);
+      const uint32_t id_dw = make_idesc_rt(128, p.NC, 0, 1);
+      auto issue_z = [&](int g) {
+        const int sl = g / p.nchunks, ch = g % p.nchunks;
+        const uint32_t wbuf = sW + (sl & 1) * W_BYTES;
+        if (ch == 0) mbar_wait(bar(B_WFULL + (sl & 1)), (sl >> 1) & 1);
+        mbar_wait(bar(B_VFULL + g % V_STAGES), (g / V_STAGES) & 1);
+        mbar_wait(bar(B_ZEMPTY + (g & 1)), ((g >> 1) & 1) ^ 1);
+        tcgen05_fence_after();
+        const uint32_t vst = sV + (g % V_STAGES) * V_STAGE_BYTES;
+        for (int ks = 0; ks < ktok; ++ks)
+          umma_bf16_ss(tmem_base + TM_Z + (g & 1) * 128, desc_mnmajor(vst, ks, KP * 128), desc_mnmajor(wbuf, ks, KP * 128),
+                       id_z, ks > 0 ? 1u : 0u);
+        umma_commit(bar(B_ZFULL + (g & 1)));
+        if (!BWD) {
+          umma_commit(bar(B_VEMPTY + g % V_STAGES));
+          if (ch == p.nchunks - 1) umma_commit(bar(B_WEMPTY + (sl & 1)));
         }
-        float dq[16], da[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) { dq[i] = 0.f; da[i] = 0.f; }
-#pragma unroll
-        for (int u = 0; u < kMaxAcc; ++u) {
-          if (u < s.QAT) {
-            wmma::store_matrix_sync(scr, acc[u], kScrLd, wmma::mem_row_major);
-            __syncwarp();
-            for (int row = lane >> 4; row < 16; row += 2) {
-              const int qa = u * 16 + row;
-              if (qa < s.QA) {
-                const int qi = qa / s.An, ai = qa - qi * s.An;
-                const float z = scr[row * kScrLd + (lane & 15)];
-                const float qv = __bfloat162float(sQ[(size_t)qi * s.C + c]);
-                const float av = s.A > 0 ? __bfloat162float(sA[(size_t)ai * s.C + c]) : 1.f;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  if (i == qi) dq[i] += av * z;
-                  if (i == ai) da[i] += qv * z;
-                }
-              }
-            }
-            __syncwarp();
-          }
+      };
+      if (total > 0) issue_z(0);
+      for (int g = 0; g < total; ++g) {
+        if (g + 1 < total) issue_z(g + 1);
+        if (!BWD) continue;
+        const int sl = g / p.nchunks, ch = g % p.nchunks;
+        const uint32_t wbuf = sW + (sl & 1) * W_BYTES;
+        const uint32_t krd = sK + (g & 1) * KRD_BYTES;
+        const uint32_t vst = sV + (g % V_STAGES) * V_STAGE_BYTES;
+        mbar_wait(bar(B_KFULL + (g & 1)), (g >> 1) & 1);
+        mbar_wait(bar(B_DEMPTY + (g & 1)), ((g >> 1) & 1) ^ 1);
+        tcgen05_fence_after();
+        for (int ks = 0; ks < kcol; ++ks)
+          umma_bf16_ss(tmem_base + TM_DV + (g & 1) * 64, desc_kmajor(krd + (ks >> 2) * (CCH * 128), ks & 3),
+                       desc_kmajor(wbuf + (ks >> 2) * (KP * 128), ks & 3), id_dv, ks > 0 ? 1u : 0u);
+        umma_commit(bar(B_DFULL + (g & 1)));
+        if (ch == 0) {
+          mbar_wait(bar(B_DWEMPTY), (sl & 1) ^ 1);
+          tcgen05_fence_after();
         }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          dq[i] += __shfl_xor_sync(0xffffffffu, dq[i], 16);
-          da[i] += __shfl_xor_sync(0xffffffffu, da[i], 16);
-        }
-        if (lane < 16) {
-          float sq = 0.f, sa = 0.f;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            if (i < s.Q) {
-              float g = doc * dq[i];
-              if (!(__bfloat162float(sQ[(size_t)i * s.C + c]) > 0.f)) g = 0.f;
-              dzq[((size_t)b * s.Q + i) * s.C + c] = __float2bfloat16(g);
-              sq += g;
-            }
-            if (i < s.A) {
-              float g = doc * da[i];
-              if (!(__bfloat162float(sA[(size_t)i * s.C + c]) > 0.f)) g = 0.f;
-              dza[((size_t)b * s.A + i) * s.C + c] = __float2bfloat16(g);
-              sa += g;
-            }
-          }
-          sDb[s.C + c] += sq;          // column c is owned by exactly one lane of one warp
-          if (s.A > 0) sDb[2 * s.C + c] += sa;
-        }
-      }
-      // ---- (2) dV[k, c] = sum_qa w[k,qa] KRd[qa,c]  (already scaled by do) ----
-      {
-        float colsum = 0.f;
-        for (int mt = 0; mt < s.MT; ++mt) {
-          FragC cU;
-          wmma::fill_fragment(cU, 0.f);
-          for (int ks = 0; ks < s.QAT; ++ks) {
-            FragAR fa;                                  // (m = k, k = qa) at sW[k][qa]
-            FragBR fb;                                  // (k = qa, n = c)
-            wmma::load_matrix_sync(fa, sW + (size_t)mt * 16 * s.LDW + ks * 16, s.LDW);
-            wmma::load_matrix_sync(fb, sKR + (size_t)ks * 16 * kLdC + warp * 16, kLdC);
-            wmma::mma_sync(cU, fa, fb, cU);
-          }
-          wmma::store_matrix_sync(scr, cU, kScrLd, wmma::mem_row_major);     // scr[k_local][c_local]
-          __syncwarp();
-          for (int row = lane >> 4; row < 16; row += 2) {
-            const int k = mt * 16 + row;
-            if (k < s.K) {
-              float g = scr[row * kScrLd + (lane & 15)];
-              if (!(__bfloat162float(vbuf[(size_t)k * kLdC + cl]) > 0.f)) g = 0.f;
-              dzv[((size_t)b * s.K + k) * s.C + c] = __float2bfloat16(g);
-              colsum += g;
-            }
-          }
-          __syncwarp();
-        }
-        colsum += __shfl_xor_sync(0xffffffffu, colsum, 16);
-        if (lane < 16) sDb[c] += colsum;
-      }
-      // ---- (3) dw[k, qa] += sum_{c in chunk} V[k,c] KRd[qa,c] ----
-#pragma unroll
-      for (int u = 0; u < 3; ++u) {
-        const int t = warp + u * kWarps;
-        if (t < dw_tiles) {
-          const int mt = t % s.MT, nt = t / s.MT;
-          for (int ks = 0; ks < kCC / 16; ++ks) {
-            FragAR fa;                                  // (m = k, k = c)
-            FragBC fb;                                  // (k = c, n = qa) at sKR[qa][c]
-            wmma::load_matrix_sync(fa, vbuf + (size_t)mt * 16 * kLdC + ks * 16, kLdC);
-            wmma::load_matrix_sync(fb, sKR + (size_t)nt * 16 * kLdC + ks * 16, kLdC);
-            wmma::mma_sync(accW[u], fa, fb, accW[u]);
-          }
+        for (int ks = 0; ks < CCH / 16; ++ks)
+          umma_bf16_ss(tmem_base + TM_DW, desc_kmajor(vst + (ks >> 2) * (KP * 128), ks & 3),
+                       desc_mnmajor(krd, ks, CCH * 128), id_dw, (ch > 0 || ks > 0) ? 1u : 0u);
+        umma_commit(bar(B_KEMPTY + (g & 1)));
+        umma_commit(bar(B_VEMPTY + g % V_STAGES));
+        if (ch == p.nchunks - 1) {
+          umma_commit(bar(B_DWFULL));
+          umma_commit(bar(B_WEMPTY + (sl & 1)));
         }
       }
     }
-    // ---- write dw for this sample ----
-#pragma unroll
-    for (int u = 0; u < 3; ++u) {
-      const int t = warp + u * kWarps;
-      if (t < dw_tiles) {
-        const int mt = t % s.MT, nt = t / s.MT;
-        wmma::store_matrix_sync(scr, accW[u], kScrLd, wmma::mem_row_major);   // scr[k_local][qa_local]
-        __syncwarp();
-        for (int e = lane; e < 256; e += 32) {
-          const int k = mt * 16 + (e >> 4), qa = nt * 16 + (e & 15);
-          if (k < s.K && qa < s.QA) dw[((size_t)b * s.K + k) * s.QA + qa] = scr[(e >> 4) * kScrLd + (e & 15)];
-        }
-        __syncwarp();
+  } else if (warp >= kBuildWarp0) {
+    // ------------------------------ w tile builder ----------------------------------------
+    const int t = threadIdx.x - kBuildWarp0 * 32;
+    const int per_k = p.Q * p.An;
+    const int n_el = p.K * per_k;
+    for (int sl = 0; sl < n_my; ++sl) {
+      const int b = blockIdx.x + sl * gridDim.x;
+      const float* src = p.w + (size_t)b * p.w_stride_b;
+      const uint32_t wbuf = sW + (sl & 1) * W_BYTES;
+      mbar_wait(bar(B_WEMPTY + (sl & 1)), ((sl >> 1) & 1) ^ 1);
+      for (int e = t; e < n_el; e += 128) {
+        const int k = e / per_k, rem = e - k * per_k;
+        const int qi = rem / p.An, ai = rem - qi * p.An;
+        const int col = ai * 16 + qi;
+        const __nv_bfloat16 hv = __float2bfloat16(__ldg(src + e));
+        st_shared_u16(wbuf + (col >> 6) * (KP * 128) + sw128_off(k, col & 63), *reinterpret_cast<const uint16_t*>(&hv));
       }
+      fence_proxy_async_smem();
+      mbar_arrive(bar(B_WFULL + (sl & 1)));
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ------------------------------ epilogue ------------------------------------------------
+    const int qd = warp & 3;
+    const int cl = qd * 32 + lane;                       // channel within the chunk = TMEM lane
+    const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
+
+    struct Side { float qp[16]; float ap[8]; float dout; };
+    auto load_side = [&](int g, Side& s) {
+      const int b = blockIdx.x + (g / p.nchunks) * gridDim.x, c = (g % p.nchunks) * CCH + cl;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        s.qp[i] = (i < p.Q) ? __bfloat162float(__ldg(p.q + ((size_t)b * p.Q + i) * p.C + c)) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        s.ap[i] = (p.A == 0) ? 1.f : ((i < p.A) ? __bfloat162float(__ldg(p.a + ((size_t)b * p.A + i) * p.C + c)) : 0.f);
+      s.dout = BWD ? __ldg(p.dout + (size_t)b * p.C + c) : 0.f;
+    };
+
+    auto epi_b = [&](int h) {          // dV of chunk h: ReLU mask from the V tile, dzv, bias gradient; then dw
+      const int sl = h / p.nchunks, ch = h % p.nchunks;
+      const int b = blockIdx.x + sl * gridDim.x, c = ch * CCH + cl;
+      mbar_wait(bar(B_DFULL + (h & 1)), (h >> 1) & 1);
+      tcgen05_fence_after();
+      const uint32_t vst = sV + (h % V_STAGES) * V_STAGE_BYTES + (cl >> 6) * (KP * 128);
+      float colsum = 0.f;
+      for (int kk = 0; kk < ktok; ++kk) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(tmem_base + lane_addr + TM_DV + (h & 1) * 64 + kk * 16, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int k = kk * 16 + j;
+          if (k < p.K) {
+            const float vv = bf16_bits_to_float(ld_shared_u16(vst + sw128_off(k, cl & 63)));
+            const float gv = vv > 0.f ? __uint_as_float(r[j]) : 0.f;
+            p.dzv[((size_t)b * p.K + k) * p.C + c] = __float2bfloat16(gv);
+            colsum += gv;
+          }
+        }
+      }
+      db_acc[c] += colsum;
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar(B_DEMPTY + (h & 1)));
+        mbar_arrive(bar(B_VEMPTY + h % V_STAGES));
+      }
+      if (ch == p.nchunks - 1) {       // the sample's dw tile is complete: lane = token
+        mbar_wait(bar(B_DWFULL), sl & 1);
+        tcgen05_fence_after();
+        const int k = cl;
+        for (int ai = 0; ai < p.An; ++ai) {
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(tmem_base + lane_addr + TM_DW + ai * 16, r);
+          tmem_wait_ld();
+          if (k < p.K) {
+#pragma unroll
+            for (int qi = 0; qi < 16; ++qi)
+              if (qi < p.Q) p.dw[(((size_t)b * p.K + k) * p.Q + qi) * p.An + ai] = __uint_as_float(r[qi]);
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_DWEMPTY));
+      }
+    };
+
+    Side cur, nxt;
+    if (total > 0) load_side(0, cur);
+    for (int g = 0; g < total; ++g) {
+      if (g + 1 < total) load_side(g + 1, nxt);
+      const int sl = g / p.nchunks, ch = g % p.nchunks;
+      const int b = blockIdx.x + sl * gridDim.x, c = ch * CCH + cl;
+      mbar_wait(bar(B_ZFULL + (g & 1)), (g >> 1) & 1);
+      tcgen05_fence_after();
+      if (BWD) mbar_wait(bar(B_KEMPTY + (g & 1)), ((g >> 1) & 1) ^ 1);
+      const uint32_t krd = sK + (g & 1) * KRD_BYTES;
+      float acc = 0.f, dq[16], sum_a = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) dq[i] = 0.f;
+#pragma unroll
+      for (int ai = 0; ai < 8; ++ai) {
+        if (ai < p.An) {
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(tmem_base + lane_addr + TM_Z + (g & 1) * 128 + ai * 16, r);
+          tmem_wait_ld();
+          const float apv = cur.ap[ai];
+          float s = 0.f;
+#pragma unroll
+          for (int qi = 0; qi < 16; ++qi) s = fmaf(cur.qp[qi], __uint_as_float(r[qi]), s);
+          if (!BWD) {
+            acc = fmaf(apv, s, acc);
+          } else {
+#pragma unroll
+            for (int qi = 0; qi < 16; ++qi) dq[qi] = fmaf(apv, __uint_as_float(r[qi]), dq[qi]);
+            if (p.A > 0) {
+              const float ga = apv > 0.f ? cur.dout * s : 0.f;
+              p.dza[((size_t)b * p.A + ai) * p.C + c] = __float2bfloat16(ga);
+              sum_a += ga;
+            }
+            // KRd[c, (ai, q)] = do * Qp[q] * Ap[ai]: one 32-byte piece of this thread's operand row
+            const float da = cur.dout * apv;
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(da * cur.qp[2 * j], da * cur.qp[2 * j + 1]);
+            const uint32_t tile = krd + (ai >> 2) * (CCH * 128);
+            const uint32_t col0 = (ai & 3) * 16;
+            st_shared_v4(tile + sw128_off(cl, col0), pk[0], pk[1], pk[2], pk[3]);
+            st_shared_v4(tile + sw128_off(cl, col0 + 8), pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+      }
+      if (!BWD) {
+        p.out[(size_t)b * p.C + c] = acc;
+      } else {
+        float sum_q = 0.f;
+#pragma unroll
+        for (int qi = 0; qi < 16; ++qi) {
+          if (qi < p.Q) {
+            const float gq = cur.qp[qi] > 0.f ? cur.dout * dq[qi] : 0.f;
+            p.dzq[((size_t)b * p.Q + qi) * p.C + c] = __float2bfloat16(gq);
+            sum_q += gq;
+          }
+        }
+        db_acc[MAX_C + c] += sum_q;
+        db_acc[2 * MAX_C + c] += sum_a;
+        fence_proxy_async_smem();        // KRd rows written with st.shared are read by tcgen05.mma
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (BWD) mbar_arrive(bar(B_KFULL + (g & 1)));
+        mbar_arrive(bar(B_ZEMPTY + (g & 1)));
+      }
+      if (BWD && g > 0) epi_b(g - 1);
+      cur = nxt;
+    }
+    if (BWD && total > 0) epi_b(total - 1);
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (BWD) {
+    for (int c = threadIdx.x; c < p.C; c += kThreads) {
+      atomicAdd(p.dbv + c, db_acc[c]);
+      atomicAdd(p.dbq + c, db_acc[MAX_C + c]);
+      if (p.A > 0) atomicAdd(p.dba + c, db_acc[2 * MAX_C + c]);
     }
   }
-  cp_async_wait_all();
-  __syncthreads();
-  for (int c = threadIdx.x; c < s.C; c += kThreads) {
-    atomicAdd(dbv + c, sDb[c]);
-    atomicAdd(dbq + c, sDb[s.C + c]);
-    if (s.A > 0) atomicAdd(dba + c, sDb[2 * s.C + c]);
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
 int check_pool(const PoolDims& d, const char* who) {
   CTI_REQUIRE(d.B >= 0 && d.K > 0 && d.Q > 0 && d.A >= 0 && d.C > 0, "%s: bad dims", who);
-  CTI_REQUIRE(d.C % kCC == 0, "%s: channel count %d must be a multiple of %d", who, d.C, kCC);
-  CTI_REQUIRE(d.Q <= 16 && d.A <= 16, "%s: Q and A must be <= 16 (Q=%d A=%d)", who, d.Q, d.A);
-  const PoolShape s = make_pool_shape(d);
-  CTI_REQUIRE(s.QAT <= kMaxAcc, "%s: Q*A = %d exceeds %d", who, s.QA, kMaxAcc * 16);
-  CTI_REQUIRE(s.MT * s.QAT <= 3 * kWarps, "%s: K*Q*A too large (K=%d, Q*A=%d)", who, d.K, s.QA);
+  CTI_REQUIRE(d.C % CCH == 0 && d.C <= MAX_C, "%s: channel count %d must be a multiple of %d and <= %d", who, d.C, CCH,
+              MAX_C);
+  CTI_REQUIRE(d.K <= KP, "%s: at most %d regions per sample (K=%d)", who, KP, d.K);
+  CTI_REQUIRE(d.Q <= 16 && d.A <= 8, "%s: Q <= 16 and A <= 8 are supported (Q=%d A=%d)", who, d.Q, d.A);
   return 0;
+}
+
+template <bool BWD>
+int launch_pool(const bf16* v, PoolParams p, cudaStream_t stream, const char* who) {
+  CUtensorMap tv;
+  if (int rc = make_tmap_3d(&tv, v, p.C, p.K, p.B, p.C, (uint64_t)p.K * p.C, 64, KP)) return rc;
+  const size_t smem = pool_smem_bytes(BWD);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(pool_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("%s smem attr: %s", who, cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+  const int grid = p.B < kNumSMsB200 ? p.B : kNumSMsB200;
+  pool_kernel<BWD><<<grid, kThreads, smem, stream>>>(tv, p);
+  return check_launch(who);
+}
+
+PoolParams make_params(const bf16* q, const bf16* a, const float* w, long w_stride_b, PoolDims d) {
+  PoolParams p{};
+  p.q = q; p.a = a; p.w = w; p.w_stride_b = w_stride_b;
+  p.B = d.B; p.K = d.K; p.Q = d.Q; p.A = d.A; p.An = d.A > 0 ? d.A : 1; p.C = d.C;
+  p.NC = 16 * p.An;
+  p.nchunks = d.C / CCH;
+  return p;
 }
 
 }  // namespace
@@ -375,16 +410,9 @@ int tri_pool_fwd(const bf16* v, const bf16* q, const bf16* a, const float* w, lo
                  cudaStream_t stream) {
   if (int rc = check_pool(d, "tri_pool_fwd")) return rc;
   if (d.B == 0) return 0;
-  const PoolShape s = make_pool_shape(d);
-  const PoolSmem lay = pool_smem(s, false);
-  CTI_REQUIRE(lay.total <= 227 * 1024, "tri_pool_fwd: needs %zu bytes of shared memory", lay.total);
-  cudaError_t e = cudaFuncSetAttribute(tri_pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
-  if (e != cudaSuccess) { set_error("tri_pool_fwd smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-  const int per_sm = (lay.total <= 110 * 1024) ? 2 : 1;
-  const int cap = kNumSMsB200 * per_sm;
-  const int grid = d.B < cap ? d.B : cap;
-  tri_pool_fwd_kernel<<<grid, kThreads, lay.total, stream>>>(v, q, a, w, w_stride_b, out, d);
-  return check_launch("tri_pool_fwd_kernel");
+  PoolParams p = make_params(q, a, w, w_stride_b, d);
+  p.out = out;
+  return launch_pool<false>(v, p, stream, "tri_pool_fwd");
 }
 
 int tri_pool_bwd(const bf16* v, const bf16* q, const bf16* a, const float* w, long w_stride_b, const float* dout,
@@ -392,15 +420,9 @@ int tri_pool_bwd(const bf16* v, const bf16* q, const bf16* a, const float* w, lo
                  cudaStream_t stream) {
   if (int rc = check_pool(d, "tri_pool_bwd")) return rc;
   if (d.B == 0) return 0;
-  const PoolShape s = make_pool_shape(d);
-  const PoolSmem lay = pool_smem(s, true);
-  CTI_REQUIRE(lay.total <= 227 * 1024, "tri_pool_bwd: needs %zu bytes of shared memory", lay.total);
-  cudaError_t e = cudaFuncSetAttribute(tri_pool_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
-  if (e != cudaSuccess) { set_error("tri_pool_bwd smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-  const int grid = d.B < kNumSMsB200 ? d.B : kNumSMsB200;
-  tri_pool_bwd_kernel<<<grid, kThreads, lay.total, stream>>>(v, q, a, w, w_stride_b, dout, dzv, dzq, dza, dbv, dbq, dba,
-                                                           dw, d);
-  return check_launch("tri_pool_bwd_kernel");
+  PoolParams p = make_params(q, a, w, w_stride_b, d);
+  p.dout = dout; p.dzv = dzv; p.dzq = dzq; p.dza = dza; p.dbv = dbv; p.dbq = dbq; p.dba = dba; p.dw = dw;
+  return launch_pool<true>(v, p, stream, "tri_pool_bwd");
 }
 
 }  // namespace cti
