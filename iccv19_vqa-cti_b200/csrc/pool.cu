@@ -37,7 +37,11 @@ constexpr int kBuildWarp0 = 8;
 constexpr int CCH = 128;                       // channels per chunk = TMEM lanes
 constexpr int KP = 64;                         // token rows per tile
 constexpr int V_STAGES = 4;
-constexpr int V_STAGE_BYTES = 2 * KP * 128;    // two 64-channel halves
+constexpr int V_TILE_BYTES = 2 * KP * 128;     // V: two 64-channel halves (128B swizzle)
+constexpr int ST_Q = V_TILE_BYTES;             // Qp chunk [16 q][128 c] bf16, rows >= Q zero (TMA OOB fill)
+constexpr int ST_A = ST_Q + 16 * CCH * 2;      // Ap chunk [8 a][128 c] bf16
+constexpr int ST_DO = ST_A + 8 * CCH * 2;      // dout chunk [128] fp32 (backward)
+constexpr int V_STAGE_BYTES = 23 * 1024;       // one pipeline stage: V + Qp + Ap + dout (+ pad to keep 1024B alignment)
 constexpr int W_BYTES = 2 * KP * 128;          // two 64-column chunks
 constexpr int KRD_BYTES = 2 * CCH * 128;       // two 64-column chunks x 128 channel rows
 constexpr int MAX_C = 1024;
@@ -72,7 +76,8 @@ __host__ __device__ inline size_t pool_smem_bytes(bool bwd) {
 
 template <bool BWD>
 __global__ void __launch_bounds__(kThreads, 1)
-pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const PoolParams p) {
+pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_q,
+            const __grid_constant__ CUtensorMap tmap_a, const PoolParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sV = base;
@@ -91,11 +96,15 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const PoolParams p) {
   for (uint32_t i = threadIdx.x; i < 2 * W_BYTES / 16; i += kThreads) st_shared_v4(sW + i * 16, 0, 0, 0, 0);
   if (BWD)
     for (int i = threadIdx.x; i < 3 * MAX_C; i += kThreads) db_acc[i] = 0.f;
-  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_v);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_v);
+    tma_prefetch_desc(&tmap_q);
+    if (p.A > 0) tma_prefetch_desc(&tmap_a);
+  }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < V_STAGES; ++s) {
       mbar_init(bar(B_VFULL + s), 1);
-      mbar_init(bar(B_VEMPTY + s), BWD ? 5 : 1);      // MMA commit (+ the 4 epilogue warps that read V in backward)
+      mbar_init(bar(B_VEMPTY + s), 5);                // MMA commit + the 4 epilogue warps that read the stage
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar(B_WFULL + s), 128);
@@ -134,9 +143,13 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const PoolParams p) {
         const int b = blockIdx.x + (g / p.nchunks) * gridDim.x, ch = g % p.nchunks;
         const int st = g % V_STAGES;
         mbar_wait(bar(B_VEMPTY + st), ((g / V_STAGES) & 1) ^ 1);
-        mbar_arrive_expect_tx(bar(B_VFULL + st), V_STAGE_BYTES);
-        tma_load_3d(&tmap_v, bar(B_VFULL + st), sV + st * V_STAGE_BYTES, ch * CCH, 0, b);
-        tma_load_3d(&tmap_v, bar(B_VFULL + st), sV + st * V_STAGE_BYTES + KP * 128, ch * CCH + 64, 0, b);
+        const uint32_t dst = sV + st * V_STAGE_BYTES;
+        mbar_arrive_expect_tx(bar(B_VFULL + st), V_TILE_BYTES + 16 * CCH * 2 + (p.A > 0 ? 8 * CCH * 2 : 0) + (BWD ? CCH * 4 : 0));
+        tma_load_3d(&tmap_v, bar(B_VFULL + st), dst, ch * CCH, 0, b);
+        tma_load_3d(&tmap_v, bar(B_VFULL + st), dst + KP * 128, ch * CCH + 64, 0, b);
+        tma_load_3d(&tmap_q, bar(B_VFULL + st), dst + ST_Q, ch * CCH, 0, b);
+        if (p.A > 0) tma_load_3d(&tmap_a, bar(B_VFULL + st), dst + ST_A, ch * CCH, 0, b);
+        if (BWD) bulk_load_1d(dst + ST_DO, p.dout + (size_t)b * p.C + ch * CCH, CCH * 4, bar(B_VFULL + st));
       }
     }
   } else if (warp == 1) {
@@ -194,20 +207,63 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const PoolParams p) {
     }
   } else if (warp >= kBuildWarp0) {
     // ------------------------------ w tile builder ----------------------------------------
+    // w[k][q][a] fp32 (contiguous per sample) -> bf16 tile element (row k, column a*16 + q).  All global
+    // loads of a batch are issued before the first shared-memory store so their latencies overlap.
     const int t = threadIdx.x - kBuildWarp0 * 32;
     const int per_k = p.Q * p.An;
     const int n_el = p.K * per_k;
+    // floor(e / d) = umulhi(e, ceil(2^32 / d)) for e < 2^16, d >= 2 (d == 1 handled apart: the magic overflows)
+    const uint32_t m_perk = 0xFFFFFFFFu / per_k + 1, m_an = 0xFFFFFFFFu / p.An + 1;
+    auto put = [&](uint32_t wbuf, int e, float val) {
+      const int k = per_k == 1 ? e : (int)__umulhi((uint32_t)e, m_perk), rem = e - k * per_k;
+      const int qi = p.An == 1 ? rem : (int)__umulhi((uint32_t)rem, m_an), ai = rem - qi * p.An;
+      const int col = ai * 16 + qi;
+      const __nv_bfloat16 hv = __float2bfloat16(val);
+      st_shared_u16(wbuf + (col >> 6) * (KP * 128) + sw128_off(k, col & 63), *reinterpret_cast<const uint16_t*>(&hv));
+    };
     for (int sl = 0; sl < n_my; ++sl) {
       const int b = blockIdx.x + sl * gridDim.x;
       const float* src = p.w + (size_t)b * p.w_stride_b;
       const uint32_t wbuf = sW + (sl & 1) * W_BYTES;
-      mbar_wait(bar(B_WEMPTY + (sl & 1)), ((sl >> 1) & 1) ^ 1);
-      for (int e = t; e < n_el; e += 128) {
-        const int k = e / per_k, rem = e - k * per_k;
-        const int qi = rem / p.An, ai = rem - qi * p.An;
-        const int col = ai * 16 + qi;
-        const __nv_bfloat16 hv = __float2bfloat16(__ldg(src + e));
-        st_shared_u16(wbuf + (col >> 6) * (KP * 128) + sw128_off(k, col & 63), *reinterpret_cast<const uint16_t*>(&hv));
+      const bool vec = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((n_el & 3) == 0);
+      constexpr int U = 8;
+      if (vec) {
+        const int n4 = n_el >> 2;
+        for (int i0 = t; i0 < n4; i0 += 128 * U) {
+          float4 r[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * 128;
+            r[u] = (i < n4) ? __ldg(reinterpret_cast<const float4*>(src) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          if (i0 == t) mbar_wait(bar(B_WEMPTY + (sl & 1)), ((sl >> 1) & 1) ^ 1);   // buffer free (loads already in flight)
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * 128;
+            if (i < n4) {
+              put(wbuf, 4 * i, r[u].x);
+              put(wbuf, 4 * i + 1, r[u].y);
+              put(wbuf, 4 * i + 2, r[u].z);
+              put(wbuf, 4 * i + 3, r[u].w);
+            }
+          }
+        }
+        if (t >= n4) mbar_wait(bar(B_WEMPTY + (sl & 1)), ((sl >> 1) & 1) ^ 1);
+      } else {
+        mbar_wait(bar(B_WEMPTY + (sl & 1)), ((sl >> 1) & 1) ^ 1);
+        for (int e0 = t; e0 < n_el; e0 += 128 * U) {
+          float r[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * 128;
+            r[u] = (e < n_el) ? __ldg(src + e) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * 128;
+            if (e < n_el) put(wbuf, e, r[u]);
+          }
+        }
       }
       fence_proxy_async_smem();
       mbar_arrive(bar(B_WFULL + (sl & 1)));
@@ -219,15 +275,14 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const PoolParams p) {
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
 
     struct Side { float qp[16]; float ap[8]; float dout; };
-    auto load_side = [&](int g, Side& s) {
-      const int b = blockIdx.x + (g / p.nchunks) * gridDim.x, c = (g % p.nchunks) * CCH + cl;
+    auto load_side = [&](int g, Side& s) {      // this thread's channel of the Qp / Ap / dout chunk that came with the V tile
+      const uint32_t st = sV + (g % V_STAGES) * V_STAGE_BYTES;
 #pragma unroll
-      for (int i = 0; i < 16; ++i)
-        s.qp[i] = (i < p.Q) ? __bfloat162float(__ldg(p.q + ((size_t)b * p.Q + i) * p.C + c)) : 0.f;
+      for (int i = 0; i < 16; ++i) s.qp[i] = bf16_bits_to_float(ld_shared_u16(st + ST_Q + (i * CCH + cl) * 2));
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        s.ap[i] = (p.A == 0) ? 1.f : ((i < p.A) ? __bfloat162float(__ldg(p.a + ((size_t)b * p.A + i) * p.C + c)) : 0.f);
-      s.dout = BWD ? __ldg(p.dout + (size_t)b * p.C + c) : 0.f;
+        s.ap[i] = (p.A == 0) ? 1.f : bf16_bits_to_float(ld_shared_u16(st + ST_A + (i * CCH + cl) * 2));
+      s.dout = BWD ? ld_shared_f32(st + ST_DO + cl * 4) : 0.f;
     };
 
     auto epi_b = [&](int h) {          // dV of chunk h: ReLU mask from the V tile, dzv, bias gradient; then dw
@@ -279,12 +334,16 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const PoolParams p) {
       }
     };
 
-    Side cur, nxt;
-    if (total > 0) load_side(0, cur);
+    Side cur;
     for (int g = 0; g < total; ++g) {
-      if (g + 1 < total) load_side(g + 1, nxt);
       const int sl = g / p.nchunks, ch = g % p.nchunks;
       const int b = blockIdx.x + sl * gridDim.x, c = ch * CCH + cl;
+      mbar_wait(bar(B_VFULL + g % V_STAGES), (g / V_STAGES) & 1);      // TMA data of this stage visible to this thread
+      load_side(g, cur);
+      if (!BWD) {                                                    // forward: the stage is not read again
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_VEMPTY + g % V_STAGES));
+      }
       mbar_wait(bar(B_ZFULL + (g & 1)), (g >> 1) & 1);
       tcgen05_fence_after();
       if (BWD) mbar_wait(bar(B_KEMPTY + (g & 1)), ((g >> 1) & 1) ^ 1);
@@ -347,7 +406,6 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const PoolParams p) {
         mbar_arrive(bar(B_ZEMPTY + (g & 1)));
       }
       if (BWD && g > 0) epi_b(g - 1);
-      cur = nxt;
     }
     if (BWD && total > 0) epi_b(total - 1);
   }
@@ -378,8 +436,15 @@ int check_pool(const PoolDims& d, const char* who) {
 
 template <bool BWD>
 int launch_pool(const bf16* v, PoolParams p, cudaStream_t stream, const char* who) {
-  CUtensorMap tv;
+  CUtensorMap tv, tq, ta;
   if (int rc = make_tmap_3d(&tv, v, p.C, p.K, p.B, p.C, (uint64_t)p.K * p.C, 64, KP)) return rc;
+  if (int rc = make_tmap_3d(&tq, p.q, p.C, p.Q, p.B, p.C, (uint64_t)p.Q * p.C, CCH, 16, false)) return rc;
+  if (p.A > 0) {
+    if (int rc = make_tmap_3d(&ta, p.a, p.C, p.A, p.B, p.C, (uint64_t)p.A * p.C, CCH, 8, false)) return rc;
+  } else {
+    ta = tq;
+  }
+  if (BWD) CTI_REQUIRE((reinterpret_cast<uintptr_t>(p.dout) & 15) == 0, "%s: dout must be 16-byte aligned", who);
   const size_t smem = pool_smem_bytes(BWD);
   static bool attr_set = false;
   if (!attr_set) {
@@ -391,7 +456,7 @@ int launch_pool(const bf16* v, PoolParams p, cudaStream_t stream, const char* wh
     attr_set = true;
   }
   const int grid = p.B < kNumSMsB200 ? p.B : kNumSMsB200;
-  pool_kernel<BWD><<<grid, kThreads, smem, stream>>>(tv, p);
+  pool_kernel<BWD><<<grid, kThreads, smem, stream>>>(tv, tq, ta, p);
   return check_launch(who);
 }
 

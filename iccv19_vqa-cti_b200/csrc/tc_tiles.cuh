@@ -51,6 +51,18 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar
       : "memory");
 }
 
+// 1-D bulk copy global -> shared (bytes % 16 == 0, both 16-byte aligned), completes on an mbarrier.
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -77,6 +89,6 @@ struct Ring {
 
 // host side (defined in gemm_tcgen05.cu)
 int make_tmap_3d(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
-                 uint64_t stride2_elems, uint32_t box0, uint32_t box1);
+                 uint64_t stride2_elems, uint32_t box0, uint32_t box1, bool swizzle128 = true);
 
 }  // namespace cti
