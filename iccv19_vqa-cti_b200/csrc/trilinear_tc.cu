@@ -16,8 +16,8 @@
 // Operands arrive by TMA: the packed core T_r (16 KB per rank, L2 resident, ring of 3) and, per four
 // ranks, one 64-column chunk of the sample's Vc / Qc / Ac rows (ring of 3).
 //
-// Roles (384 threads): warp 0 TMA | warp 1 MMA issuer | warp 2 TMEM allocator | warps 4-7 N1 tiles |
-// warps 8-11 M tiles + per-sample epilogue (mask, coalesced (B,G,K,Q,A) store).
+// Roles (384 threads): warp 0 TMA | warps 1, 3, 2 one MMA issuer per stage (warp 2 also owns TMEM) |
+// warps 4-7 N1 tiles | warps 8-11 M tiles + per-sample epilogue (mask, coalesced (B,G,K,Q,A) store).
 #include "cti_common.cuh"
 #include "cti_kernels.h"
 #include "tc_tiles.cuh"
@@ -114,72 +114,92 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
+      uint32_t tslot = 0, tph = 0, oslot = 0, oph = 0;
+      int r = 0, b = blockIdx.x;
       for (int u = 0; u < U; ++u) {
-        const int sl = u / p.R, r = u - sl * p.R;
-        const int b = blockIdx.x + sl * gridDim.x;
         if ((r & 3) == 0) {
-          const int qi = u >> 2, slot = qi % OP_RING;
-          mbar_wait(bar(B_OPEMPTY + slot), ((qi / OP_RING) & 1) ^ 1);
-          mbar_arrive_expect_tx(bar(B_OPFULL + slot), OP_BYTES);
-          const uint32_t dst = sOp + slot * OP_BYTES;
-          tma_load_3d(&tmap_v, bar(B_OPFULL + slot), dst + OP_V, r * 16, 0, b);
-          tma_load_3d(&tmap_q, bar(B_OPFULL + slot), dst + OP_Q, r * 16, 0, b);
-          tma_load_3d(&tmap_a, bar(B_OPFULL + slot), dst + OP_A, r * 16, 0, b);
+          mbar_wait(bar(B_OPEMPTY + oslot), oph ^ 1u);
+          mbar_arrive_expect_tx(bar(B_OPFULL + oslot), OP_BYTES);
+          const uint32_t dst = sOp + oslot * OP_BYTES;
+          tma_load_3d(&tmap_v, bar(B_OPFULL + oslot), dst + OP_V, r * 16, 0, b);
+          tma_load_3d(&tmap_q, bar(B_OPFULL + oslot), dst + OP_Q, r * 16, 0, b);
+          tma_load_3d(&tmap_a, bar(B_OPFULL + oslot), dst + OP_A, r * 16, 0, b);
+          if (++oslot == OP_RING) { oslot = 0; oph ^= 1u; }
         }
-        const int slot = u % T_RING;
-        mbar_wait(bar(B_TEMPTY + slot), ((u / T_RING) & 1) ^ 1);
-        mbar_arrive_expect_tx(bar(B_TFULL + slot), T_BYTES);
+        mbar_wait(bar(B_TEMPTY + tslot), tph ^ 1u);
+        mbar_arrive_expect_tx(bar(B_TFULL + tslot), T_BYTES);
 #pragma unroll
         for (int c = 0; c < 8; ++c)
-          tma_load_3d(&tmap_t, bar(B_TFULL + slot), sT + slot * T_BYTES + c * 2048, c * 64, r * 16, 0);
+          tma_load_3d(&tmap_t, bar(B_TFULL + tslot), sT + tslot * T_BYTES + c * 2048, c * 64, r * 16, 0);
+        if (++tslot == T_RING) { tslot = 0; tph ^= 1u; }
+        if (++r == p.R) { r = 0; b += gridDim.x; }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------ MMA issuer ------------------------------------
+    // ------------------------------ MMA issuer 1: F1(u)  N1^T = T_r^T . Ac_r^T ------------------------
+    // (three issuing threads, one per stage: a single thread's serial descriptor / barrier code was the
+    //  bottleneck of the first version; tcgen05.commit tracks the MMAs of the committing thread only)
     if (lane == 0) {
       const uint32_t id_f1 = make_idesc_rt(128, 16, 1, 0);
-      const uint32_t id_f2 = make_idesc_rt(128, 16, 0, 0);
-      const uint32_t id_3 = make_idesc_rt(128, p.N, 0, 1);
-      for (int it = 0; it < U + 2; ++it) {
-        if (it < U) {                                    // ---- F1(u): N1^T = T_r^T . Ac_r^T
-          const int u = it, r = u % p.R;
-          const uint32_t tt = sT + (u % T_RING) * T_BYTES;
-          const uint32_t op = sOp + ((u >> 2) % OP_RING) * OP_BYTES;
-          mbar_wait(bar(B_TFULL + u % T_RING), (u / T_RING) & 1);
-          if ((r & 3) == 0) mbar_wait(bar(B_OPFULL + (u >> 2) % OP_RING), ((u >> 2) / OP_RING) & 1);
-          mbar_wait(bar(B_F1EMPTY + (u & 1)), ((u >> 1) & 1) ^ 1);
-          tcgen05_fence_after();
+      uint32_t tslot = 0, tph = 0, oslot = 0, oph = 0;
+      int r = 0;
+      for (int u = 0; u < U; ++u) {
+        const uint32_t tt = sT + tslot * T_BYTES;
+        mbar_wait(bar(B_TFULL + tslot), tph);
+        if ((r & 3) == 0) mbar_wait(bar(B_OPFULL + oslot), oph);
+        mbar_wait(bar(B_F1EMPTY + (u & 1)), ((u >> 1) & 1) ^ 1);
+        tcgen05_fence_after();
+        const uint64_t db = desc_kmajor(sOp + oslot * OP_BYTES + OP_A, r & 3);
+        const uint64_t da = desc_mnmajor(tt, 0, 2048);
 #pragma unroll
-          for (int t = 0; t < 4; ++t)
-            umma_bf16_ss(tmem_base + TM_F1 + (u & 1) * 64 + t * 16, desc_mnmajor(tt + 2 * t * 2048, 0, 2048),
-                         desc_kmajor(op + OP_A, r & 3), id_f1, 0u);
-          umma_commit(bar(B_F1FULL + (u & 1)));
-          umma_commit(bar(B_TEMPTY + u % T_RING));
-        }
-        if (it >= 1 && it - 1 < U) {                     // ---- F2(u): M = N1 . Qc_r^T
-          const int u = it - 1, r = u % p.R;
-          const uint32_t op = sOp + ((u >> 2) % OP_RING) * OP_BYTES;
-          mbar_wait(bar(B_N1FULL + (u & 1)), (u >> 1) & 1);
-          mbar_wait(bar(B_F2EMPTY + (u & 1)), ((u >> 1) & 1) ^ 1);
-          tcgen05_fence_after();
-          for (int t2 = 0; t2 < nt2; ++t2)
-            umma_bf16_ss(tmem_base + TM_F2 + (u & 1) * 32 + t2 * 16, desc_kmajor(sN1 + (u & 1) * N1_BYTES + t2 * 16384, 0),
-                         desc_kmajor(op + OP_Q, r & 3), id_f2, 0u);
-          umma_commit(bar(B_F2FULL + (u & 1)));
-          umma_commit(bar(B_N1EMPTY + (u & 1)));
-        }
-        if (it >= 2) {                                   // ---- III(u): L += Vc_r . M
-          const int u = it - 2, sl = u / p.R, r = u - sl * p.R;
-          const uint32_t op = sOp + ((u >> 2) % OP_RING) * OP_BYTES;
-          mbar_wait(bar(B_MFULL + (u & 1)), (u >> 1) & 1);
-          if (r == 0) mbar_wait(bar(B_ACCEMPTY), (sl & 1) ^ 1);
-          tcgen05_fence_after();
-          umma_bf16_ss(tmem_base + TM_ACC, desc_kmajor(op + OP_V, r & 3), desc_mnmajor(sM + (u & 1) * M_BYTES, 0, 2048),
-                       id_3, r > 0 ? 1u : 0u);
-          umma_commit(bar(B_MEMPTY + (u & 1)));
-          if ((r & 3) == 3) umma_commit(bar(B_OPEMPTY + (u >> 2) % OP_RING));
-          if (r == p.R - 1) umma_commit(bar(B_ACCFULL));
-        }
+        for (int t = 0; t < 4; ++t)
+          umma_bf16_ss(tmem_base + TM_F1 + (u & 1) * 64 + t * 16, da + (uint64_t)(2 * t * 2048 >> 4), db, id_f1, 0u);
+        umma_commit(bar(B_F1FULL + (u & 1)));
+        umma_commit(bar(B_TEMPTY + tslot));
+        if (++tslot == T_RING) { tslot = 0; tph ^= 1u; }
+        if (++r == p.R) r = 0;
+        if ((r & 3) == 0 && ++oslot == OP_RING) { oslot = 0; oph ^= 1u; }
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------ MMA issuer 2: F2(u)  M = N1 . Qc_r^T ---------------------------------
+    if (lane == 0) {
+      const uint32_t id_f2 = make_idesc_rt(128, 16, 0, 0);
+      uint32_t oslot = 0, oph = 0;
+      int r = 0;
+      for (int u = 0; u < U; ++u) {
+        if ((r & 3) == 0) mbar_wait(bar(B_OPFULL + oslot), oph);
+        mbar_wait(bar(B_N1FULL + (u & 1)), (u >> 1) & 1);
+        mbar_wait(bar(B_F2EMPTY + (u & 1)), ((u >> 1) & 1) ^ 1);
+        tcgen05_fence_after();
+        const uint64_t db = desc_kmajor(sOp + oslot * OP_BYTES + OP_Q, r & 3);
+        const uint64_t da = desc_kmajor(sN1 + (u & 1) * N1_BYTES, 0);
+        for (int t2 = 0; t2 < nt2; ++t2)
+          umma_bf16_ss(tmem_base + TM_F2 + (u & 1) * 32 + t2 * 16, da + (uint64_t)(t2 * 16384 >> 4), db, id_f2, 0u);
+        umma_commit(bar(B_F2FULL + (u & 1)));
+        umma_commit(bar(B_N1EMPTY + (u & 1)));
+        if (++r == p.R) r = 0;
+        if ((r & 3) == 0 && ++oslot == OP_RING) { oslot = 0; oph ^= 1u; }
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------ MMA issuer 3: III(u)  L += Vc_r . M  (this warp also owns TMEM) --------
+    if (lane == 0) {
+      const uint32_t id_3 = make_idesc_rt(128, p.N, 0, 1);
+      uint32_t oslot = 0, oph = 0;
+      int r = 0, sl = 0;
+      for (int u = 0; u < U; ++u) {
+        if ((r & 3) == 0) mbar_wait(bar(B_OPFULL + oslot), oph);
+        mbar_wait(bar(B_MFULL + (u & 1)), (u >> 1) & 1);
+        if (r == 0) mbar_wait(bar(B_ACCEMPTY), (sl & 1) ^ 1);
+        tcgen05_fence_after();
+        umma_bf16_ss(tmem_base + TM_ACC, desc_kmajor(sOp + oslot * OP_BYTES + OP_V, r & 3),
+                     desc_mnmajor(sM + (u & 1) * M_BYTES, 0, 2048), id_3, r > 0 ? 1u : 0u);
+        umma_commit(bar(B_MEMPTY + (u & 1)));
+        if ((r & 3) == 3) umma_commit(bar(B_OPEMPTY + oslot));
+        if (r == p.R - 1) umma_commit(bar(B_ACCFULL));
+        if (++r == p.R) { r = 0; ++sl; }
+        if ((r & 3) == 0 && ++oslot == OP_RING) { oslot = 0; oph ^= 1u; }
       }
     }
   } else if (warp >= 4 && warp < 8) {
@@ -193,18 +213,19 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
       tcgen05_fence_after();
       mbar_wait(bar(B_N1EMPTY + slot), ((u >> 1) & 1) ^ 1);
       const uint32_t n1 = sN1 + slot * N1_BYTES;
+      uint32_t v[4][8];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) tmem_ld_32x32b_x8(tmem_base + lane_addr + TM_F1 + slot * 64 + t * 16, v[t]);
+      tmem_wait_ld();
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        uint32_t v[8];
-        tmem_ld_32x32b_x8(tmem_base + lane_addr + TM_F1 + slot * 64 + t * 16, v);
-        tmem_wait_ld();
         const int i = 4 * t + (L >> 5);
         // row = a*32 + g*16 + i  ->  row>>3 = a*4 + g*2 + (i>>3),  row&7 = i&7
         const uint32_t off = (g * 2 + (i >> 3)) * 1024u + (i & 7) * 128u + ((((j >> 3) & 1) ^ (i & 7)) << 4) + (j & 7) * 2u;
 #pragma unroll
         for (int a = 0; a < 8; ++a) {
           if (a < p.A) {
-            const __nv_bfloat16 h = __float2bfloat16(__uint_as_float(v[a]));
+            const __nv_bfloat16 h = __float2bfloat16(__uint_as_float(v[t][a]));
             st_shared_u16(n1 + a * 4096u + off, *reinterpret_cast<const uint16_t*>(&h));
           }
         }
@@ -223,8 +244,10 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
     const int et = threadIdx.x - 8 * 32;                  // 0..127 within the group
     const int per_g = p.K * p.Q * p.A;
+    int r = -1, sl = 0;
     for (int u = 0; u < U; ++u) {
-      const int slot = u & 1, sl = u / p.R, r = u - sl * p.R;
+      const int slot = u & 1;
+      if (++r == p.R) { r = 0; ++sl; }
       mbar_wait(bar(B_F2FULL + slot), (u >> 1) & 1);
       tcgen05_fence_after();
       mbar_wait(bar(B_MEMPTY + slot), ((u >> 1) & 1) ^ 1);
