@@ -614,9 +614,18 @@ int trilinear_fwd(const bf16* vc, const bf16* qc, const bf16* ac, const bf16* tp
   return check_launch("trilinear_fwd_kernel");
 }
 
-size_t trilinear_bwd_workspace(TriDims d) {
+size_t trilinear_bwd_tc_workspace(TriDims d);                                   // trilinear_bwd_tc.cu
+int trilinear_bwd_tc(const bf16* vc, const bf16* qc, const bf16* ac, const bf16* tpack, const bf16* dlm, bf16* dn1,
+                     bf16* dzv, bf16* dzq, bf16* dza, float* dbv, float* dbq, float* dba, float* dtpack, TriDims d,
+                     cudaStream_t stream);
+
+static size_t dlm_bytes(TriDims d) {
   const TriShape s = make_shape(d);
-  return (size_t)d.B * d.K * s.NT * 16 * sizeof(bf16);
+  return align_up((size_t)d.B * d.K * s.NT * 16 * sizeof(bf16), 1024);
+}
+
+size_t trilinear_bwd_workspace(TriDims d) {      // dLm (bf16 matrix form of dlogits) + dN1 of the tcgen05 path
+  return dlm_bytes(d) + trilinear_bwd_tc_workspace(d);
 }
 
 int trilinear_bwd(const bf16* vc, const bf16* qc, const bf16* ac, const bf16* tpack, const float* dlogits, bf16* dzv,
@@ -632,6 +641,11 @@ int trilinear_bwd(const bf16* vc, const bf16* qc, const bf16* ac, const bf16* tp
   bf16* dlm = static_cast<bf16*>(workspace);
   dlogits_to_dlm_kernel<<<kNumSMsB200 * 4, 256, 0, stream>>>(dlogits, dlm, d);
   if (int rc = check_launch("dlogits_to_dlm_kernel")) return rc;
+  {   // tcgen05 fast path (G == 2, A <= 6, K <= 64); other shapes use the generic tensor-core kernel below
+    bf16* dn1 = reinterpret_cast<bf16*>(static_cast<uint8_t*>(workspace) + dlm_bytes(d));
+    const int rc = trilinear_bwd_tc(vc, qc, ac, tpack, dlm, dn1, dzv, dzq, dza, dbv, dbq, dba, dtpack, d, stream);
+    if (rc != -100) return rc;
+  }
   cudaError_t e = cudaFuncSetAttribute(trilinear_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
   if (e != cudaSuccess) { set_error("trilinear_bwd smem attr: %s", cudaGetErrorString(e)); return (int)e; }
   const int grid = d.B < kNumSMsB200 ? d.B : kNumSMsB200;
