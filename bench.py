@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--resident-only", action="store_true", help="skip the e2e / forward-only arms (for ncu runs)")
+    ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly from Python (no CUDA graph)")
     return ap.parse_args()
 
 
@@ -211,6 +212,7 @@ def run_b200(args):
         for _ in range(steps):
             fn()
         e1.record()
+        timed.host_ms = (time.perf_counter() - w0) * 1e3 / steps      # host time to ISSUE a step (launch-bound check)
         barrier()
         w1 = time.perf_counter()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -226,10 +228,28 @@ def run_b200(args):
 
     for _ in range(max(args.warmup, 3)):
         resident_step()
-    sampler = ClockSampler(local) if rank == 0 else None
+    # launches of one step (counted on an eager step: a graph replay issues the same kernels without Python)
     KS.STATS.launches = 0
-    ms, w0, w1 = timed(resident_step, args.steps)
-    launches = KS.STATS.launches
+    resident_step()
+    launches_per_step = KS.STATS.launches
+    use_graph = not args.no_graph and world == 1          # multi-GPU steps (NCCL inside the step) are issued eagerly
+    eager_ms = None
+    run_resident = resident_step
+    if use_graph:
+        ms_eager, _, _ = timed(resident_step, max(3, args.steps // 4))
+        eager_ms = {"ms_per_step": ms_eager / max(3, args.steps // 4), "host_issue_ms_per_step": timed.host_ms}
+        try:
+            graphed = cti_b200.GraphedStep(resident_step, [mods], [v_d])
+            run_resident = graphed.replay
+            for _ in range(3):
+                run_resident()
+        except Exception as exc:                                  # e.g. NCCL without graph support: stay eager
+            use_graph = False
+            eager_ms["graph_capture_failed"] = repr(exc)[:200]
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, w0, w1 = timed(run_resident, args.steps)
+    host_ms = timed.host_ms
+    launches = launches_per_step * args.steps
     clocks = sampler.stop(w0, w1) if sampler else None
     value = world * B * args.steps / (ms / 1e3)
 
@@ -245,7 +265,15 @@ def run_b200(args):
     if not args.resident_only:
         for _ in range(3):
             e2e_step()
-        ms_e2e, _, _ = timed(e2e_step, args.steps)
+        run_e2e = e2e_step
+        if use_graph:
+            try:
+                run_e2e = cti_b200.GraphedStep(e2e_step, [mods], []).replay
+                for _ in range(3):
+                    run_e2e()
+            except Exception:
+                run_e2e = e2e_step
+        ms_e2e, _, _ = timed(run_e2e, args.steps)
         e2e = {"value": world * B * args.steps / (ms_e2e / 1e3), "unit": UNIT,
                "h2d_bytes_per_step": (v_h.numel() + q_h.numel() + a_h.numel()) * 4,
                "d2h_bytes_per_step": out_h.numel() * 4, "ms_per_step": ms_e2e / args.steps}
@@ -264,7 +292,15 @@ def run_b200(args):
     if not args.resident_only:
         for _ in range(3):
             fwd_only()
-        ms_f, _, _ = timed(fwd_only, args.steps)
+        run_fwd = fwd_only
+        if use_graph:
+            try:
+                run_fwd = cti_b200.GraphedStep(fwd_only, [mods], [v_d]).replay
+                for _ in range(3):
+                    run_fwd()
+            except Exception:
+                run_fwd = fwd_only
+        ms_f, _, _ = timed(run_fwd, args.steps)
         fwd = {"value": world * B * args.steps / (ms_f / 1e3), "unit": UNIT, "ms_per_step": ms_f / args.steps}
 
     # ---- per-kernel CUDA-event timing of the same step (rank 0) -----------------
@@ -325,9 +361,10 @@ def run_b200(args):
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "host_issue_ms_per_step": host_ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": workload_config(B, world), "e2e": e2e, "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps, "clocks": clocks,
+                "config": dict(workload_config(B, world), launch="cuda_graph_replay" if use_graph else "eager"),
+                "eager": eager_ms, "e2e": e2e, "gpu_launches": launches, "gpu_launches_per_step": launches_per_step, "clocks": clocks,
                 "fwd_only": fwd, "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels}
         print(json.dumps(line), flush=True)
     if world > 1:

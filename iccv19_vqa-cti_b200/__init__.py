@@ -13,9 +13,10 @@ from .attention import BiAttention, TriAttention
 from .bc import BCNet
 from .dropin import install, uninstall
 from .fc import FCNet, WNLinear
+from .graphs import GraphedStep, reset_caches
 from .tc import TCNet
 
-__all__ = ["FCNet", "WNLinear", "TCNet", "TriAttention", "BCNet", "BiAttention", "install", "uninstall",
+__all__ = ["FCNet", "WNLinear", "TCNet", "TriAttention", "BCNet", "BiAttention", "install", "uninstall", "GraphedStep", "reset_caches",
            "library_path", "version"]
 
 

@@ -61,7 +61,7 @@ __device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
 // =========================================================================== //
 // kernel 1
 // =========================================================================== //
-constexpr int kThreads1 = 512;
+constexpr int kThreads1 = 576;     // 18 warps: TMA, 5 single-thread MMA issuers (1, 2, 3, 16, 17), 3 x 4 converter / epilogue warps
 constexpr int T_BYTES = 16 * 1024, T_RING = 2;
 constexpr int OP_V = 0, OP_Q = 8192, OP_A = 10240, OP_BYTES = 12288, OP_RING = 3;
 constexpr int N1_BYTES = 32 * 1024;
@@ -69,7 +69,11 @@ constexpr int M_BYTES = 8 * 1024;
 constexpr int DL_CHUNKS = 3, DL_BYTES = DL_CHUNKS * 8192;     // dL tile [64 k][192 n]
 constexpr int D_BYTES = 6 * 1024;                             // D tile [16 q][192 (a,g,i)]
 constexpr int DB_FLOATS = 512;                                // bias-gradient accumulators (R * 16 <= 512)
-constexpr uint32_t TM_F1 = 0, TM_F2 = 128, TM_B1 = 192, TM_B2 = 224, TM_B3 = 288, TM_B4 = 320;
+// B1 / B3 contract over 12 K steps into a 16-column tile: a single accumulator would be a chain of 12 dependent
+// tcgen05.mma (latency bound, ~90 cycles each for N = 16), so the K steps are dealt round-robin to KP partial
+// accumulators (independent chains of 3) that the epilogue adds up.  Those two stages are single-slot.
+constexpr int KP = 4;
+constexpr uint32_t TM_F1 = 0, TM_F2 = 128, TM_B1 = 192, TM_B3 = 256, TM_B2 = 320, TM_B4 = 384;
 
 enum { A_TFULL = 0, A_TEMPTY = 2, A_OPFULL = 4, A_OPEMPTY = 7, A_DLFULL = 10, A_DLEMPTY = 12, A_F1FULL = 14, A_F1EMPTY = 16,
        A_N1FULL = 18, A_N1EMPTY = 20, A_F2FULL = 22, A_F2EMPTY = 24, A_MFULL = 26, A_MEMPTY = 28, A_B1FULL = 30,
@@ -120,11 +124,11 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
       mbar_init(bar(A_TFULL + s), 1);
       mbar_init(bar(A_TEMPTY + s), 1);
       mbar_init(bar(A_DLFULL + s), 1);
-      mbar_init(bar(A_DLEMPTY + s), 1);
+      mbar_init(bar(A_DLEMPTY + s), 2);       // B1 and B2 issuers
       mbar_init(bar(A_F1FULL + s), 1);
       mbar_init(bar(A_F1EMPTY + s), 4);
       mbar_init(bar(A_N1FULL + s), 4);
-      mbar_init(bar(A_N1EMPTY + s), 1);
+      mbar_init(bar(A_N1EMPTY + s), 2);       // F2 and B3 issuers
       mbar_init(bar(A_F2FULL + s), 1);
       mbar_init(bar(A_F2EMPTY + s), 4);
       mbar_init(bar(A_MFULL + s), 4);
@@ -142,7 +146,7 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
     }
     for (int s = 0; s < 3; ++s) {
       mbar_init(bar(A_OPFULL + s), 1);
-      mbar_init(bar(A_OPEMPTY + s), 5);       // MMA commit + the 4 epilogue warps that read Vc / Qc for the ReLU masks
+      mbar_init(bar(A_OPEMPTY + s), 6);       // F2 and B4 issuers + the 4 epilogue warps that read Vc / Qc (ReLU masks)
     }
     fence_barrier_init();
   }
@@ -219,10 +223,9 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
       }
     }
   } else if (warp == 2) {
-    // ------------------------------ issuer: B2 (D^T = dL^T Vc), B1 (dVc = dL M^T) ------------------
+    // ------------------------------ issuer: B2 (D^T = dL^T Vc) -- depends on TMA data only, runs ahead -------
     if (lane == 0) {
       const uint32_t id_b2 = make_idesc_rt(128, 16, 1, 1);
-      const uint32_t id_b1 = make_idesc_rt(128, 16, 0, 0);
       uint32_t oslot = 0, oph = 0;
       int r = 0, sl = 0;
       for (int u = 0; u < U; ++u) {
@@ -231,61 +234,86 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
         if (r == 0) mbar_wait(bar(A_DLFULL + (sl & 1)), (sl >> 1) & 1);
         mbar_wait(bar(A_B2EMPTY + (u & 1)), ((u >> 1) & 1) ^ 1);
         tcgen05_fence_after();
-        const uint32_t vchunk = sOp + oslot * OP_BYTES + OP_V + (r & 3) * 32;
-        for (int t = 0; t < ntn; ++t)
+        const uint64_t db0 = desc_mnmajor(sOp + oslot * OP_BYTES + OP_V + (r & 3) * 32, 0, 0);
+        for (int t = 0; t < ntn; ++t) {
+          const uint64_t da0 = desc_mnmajor(dl + 2 * t * 8192, 0, 8192);
           for (int ks = 0; ks < ktok; ++ks)
-            umma_bf16_ss(tmem_base + TM_B2 + (u & 1) * 32 + t * 16, desc_mnmajor(dl + 2 * t * 8192, ks, 8192),
-                         desc_mnmajor(vchunk, ks, 0), id_b2, ks > 0 ? 1u : 0u);
+            umma_bf16_ss(tmem_base + TM_B2 + (u & 1) * 32 + t * 16, da0 + (uint64_t)(ks * 2048 >> 4),
+                         db0 + (uint64_t)(ks * 2048 >> 4), id_b2, ks > 0 ? 1u : 0u);
+        }
         umma_commit(bar(A_B2FULL + (u & 1)));
-        mbar_wait(bar(A_MFULL + (u & 1)), (u >> 1) & 1);
-        mbar_wait(bar(A_B1EMPTY + (u & 1)), ((u >> 1) & 1) ^ 1);
-        tcgen05_fence_after();
-        const uint32_t mt = sM + (u & 1) * M_BYTES;
-        for (int ks = 0; ks < kn; ++ks)
-          umma_bf16_ss(tmem_base + TM_B1 + (u & 1) * 16, desc_kmajor(dl + (ks >> 2) * 8192, ks & 3),
-                       desc_kmajor(mt + (ks >> 2) * 2048, ks & 3), id_b1, ks > 0 ? 1u : 0u);
-        umma_commit(bar(A_B1FULL + (u & 1)));
-        umma_commit(bar(A_MEMPTY + (u & 1)));
         if (r == p.R - 1) umma_commit(bar(A_DLEMPTY + (sl & 1)));
         if (++r == p.R) { r = 0; ++sl; }
         if ((r & 3) == 0 && ++oslot == OP_RING) { oslot = 0; oph ^= 1u; }
       }
     }
+  } else if (warp == 16) {
+    // ------------------------------ issuer: B1 (dVc = dL M^T) ---------------------------------------------
+    if (lane == 0) {
+      const uint32_t id_b1 = make_idesc_rt(128, 16, 0, 0);
+      int r = 0, sl = 0;
+      for (int u = 0; u < U; ++u) {
+        const uint32_t dl = sDL + (sl & 1) * DL_BYTES;
+        if (r == 0) mbar_wait(bar(A_DLFULL + (sl & 1)), (sl >> 1) & 1);
+        mbar_wait(bar(A_MFULL + (u & 1)), (u >> 1) & 1);
+        mbar_wait(bar(A_B1EMPTY), (u & 1) ^ 1);
+        tcgen05_fence_after();
+        const uint64_t da0 = desc_kmajor(dl, 0), db0 = desc_kmajor(sM + (u & 1) * M_BYTES, 0);
+        for (int ks = 0; ks < kn; ++ks)
+          umma_bf16_ss(tmem_base + TM_B1 + (ks & (KP - 1)) * 16, da0 + (uint64_t)(((ks >> 2) * 8192 + (ks & 3) * 32) >> 4),
+                       db0 + (uint64_t)(((ks >> 2) * 2048 + (ks & 3) * 32) >> 4), id_b1, ks >= KP ? 1u : 0u);
+        umma_commit(bar(A_B1FULL));
+        umma_commit(bar(A_MEMPTY + (u & 1)));
+        if (r == p.R - 1) umma_commit(bar(A_DLEMPTY + (sl & 1)));
+        if (++r == p.R) { r = 0; ++sl; }
+      }
+    }
   } else if (warp == 3) {
-    // ------------------------------ issuer: F2 (M = N1 Qc^T), B3 (dQc = D N1), B4 (dN1 = D^T Qc) -------
+    // ------------------------------ issuer: F2 (M = N1 Qc^T) ------------------------------------------------
     if (lane == 0) {
       const uint32_t id_f2 = make_idesc_rt(128, 16, 0, 0);
+      uint32_t oslot = 0, oph = 0;
+      int r = 0;
+      for (int u = 0; u < U; ++u) {
+        if ((r & 3) == 0) mbar_wait(bar(A_OPFULL + oslot), oph);
+        mbar_wait(bar(A_N1FULL + (u & 1)), (u >> 1) & 1);
+        mbar_wait(bar(A_F2EMPTY + (u & 1)), ((u >> 1) & 1) ^ 1);
+        tcgen05_fence_after();
+        const uint64_t db = desc_kmajor(sOp + oslot * OP_BYTES + OP_Q, r & 3);
+        const uint64_t da = desc_kmajor(sN1 + (u & 1) * N1_BYTES, 0);
+        for (int t2 = 0; t2 < nt2; ++t2)
+          umma_bf16_ss(tmem_base + TM_F2 + (u & 1) * 32 + t2 * 16, da + (uint64_t)(t2 * 16384 >> 4), db, id_f2, 0u);
+        umma_commit(bar(A_F2FULL + (u & 1)));
+        umma_commit(bar(A_N1EMPTY + (u & 1)));
+        if ((r & 3) == 3) umma_commit(bar(A_OPEMPTY + oslot));
+        if (++r == p.R) r = 0;
+        if ((r & 3) == 0 && ++oslot == OP_RING) { oslot = 0; oph ^= 1u; }
+      }
+    }
+  } else if (warp == 17) {
+    // ------------------------------ issuer: B3 (dQc = D N1), B4 (dN1 = D^T Qc) ---------------------------------
+    if (lane == 0) {
       const uint32_t id_b3 = make_idesc_rt(128, 16, 0, 1);
       const uint32_t id_b4 = make_idesc_rt(128, 16, 1, 1);
       uint32_t oslot = 0, oph = 0;
       int r = 0;
       for (int u = 0; u < U; ++u) {
         const uint32_t op = sOp + oslot * OP_BYTES;
-        const uint32_t n1 = sN1 + (u & 1) * N1_BYTES;
         if ((r & 3) == 0) mbar_wait(bar(A_OPFULL + oslot), oph);
         mbar_wait(bar(A_N1FULL + (u & 1)), (u >> 1) & 1);
-        mbar_wait(bar(A_F2EMPTY + (u & 1)), ((u >> 1) & 1) ^ 1);
-        tcgen05_fence_after();
-        {
-          const uint64_t db = desc_kmajor(op + OP_Q, r & 3);
-          const uint64_t da = desc_kmajor(n1, 0);
-          for (int t2 = 0; t2 < nt2; ++t2)
-            umma_bf16_ss(tmem_base + TM_F2 + (u & 1) * 32 + t2 * 16, da + (uint64_t)(t2 * 16384 >> 4), db, id_f2, 0u);
-        }
-        umma_commit(bar(A_F2FULL + (u & 1)));
         mbar_wait(bar(A_DFULL + (u & 1)), (u >> 1) & 1);
-        mbar_wait(bar(A_B3EMPTY + (u & 1)), ((u >> 1) & 1) ^ 1);
+        mbar_wait(bar(A_B3EMPTY), (u & 1) ^ 1);
         mbar_wait(bar(A_B4EMPTY + (u & 1)), ((u >> 1) & 1) ^ 1);
         tcgen05_fence_after();
         const uint32_t dt = sD + (u & 1) * D_BYTES;
+        const uint64_t da0 = desc_kmajor(dt, 0), db0 = desc_mnmajor(sN1 + (u & 1) * N1_BYTES, 0, 0);
         for (int ks = 0; ks < kn; ++ks)
-          umma_bf16_ss(tmem_base + TM_B3 + (u & 1) * 16, desc_kmajor(dt + (ks >> 2) * 2048, ks & 3), desc_mnmajor(n1, ks, 0),
-                       id_b3, ks > 0 ? 1u : 0u);
-        umma_commit(bar(A_B3FULL + (u & 1)));
-        const uint32_t qchunk = op + OP_Q + (r & 3) * 32;
+          umma_bf16_ss(tmem_base + TM_B3 + (ks & (KP - 1)) * 16, da0 + (uint64_t)(((ks >> 2) * 2048 + (ks & 3) * 32) >> 4),
+                       db0 + (uint64_t)((ks * 2048) >> 4), id_b3, ks >= KP ? 1u : 0u);
+        umma_commit(bar(A_B3FULL));
+        const uint64_t dq = desc_mnmajor(op + OP_Q + (r & 3) * 32, 0, 0);
         for (int t = 0; t < nt2; ++t)
-          umma_bf16_ss(tmem_base + TM_B4 + (u & 1) * 32 + t * 16, desc_mnmajor(dt + 2 * t * 2048, 0, 2048),
-                       desc_mnmajor(qchunk, 0, 0), id_b4, 0u);
+          umma_bf16_ss(tmem_base + TM_B4 + (u & 1) * 32 + t * 16, desc_mnmajor(dt + 2 * t * 2048, 0, 2048), dq, id_b4, 0u);
         umma_commit(bar(A_B4FULL + (u & 1)));
         umma_commit(bar(A_DEMPTY + (u & 1)));
         umma_commit(bar(A_N1EMPTY + (u & 1)));
@@ -395,7 +423,7 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
         }
       }
     }
-  } else {
+  } else if (warp < 16) {
     // ------------------------------ G3: epilogues  dVc -> dzv, dQc -> dzq, dN1 -> workspace -----------
     const int qd = warp & 3, L = qd * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
@@ -419,14 +447,26 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
         }
       };
       {   // E1: dVc[k, i]
-        mbar_wait(bar(A_B1FULL + slot), (u >> 1) & 1);
+        mbar_wait(bar(A_B1FULL), u & 1);
         tcgen05_fence_after();
         uint32_t v[16];
-        tmem_ld_32x32b_x16(tmem_base + lane_addr + TM_B1 + slot * 16, v);
-        tmem_wait_ld();
+        {
+          uint32_t w[KP][16];
+#pragma unroll
+          for (int x = 0; x < KP; ++x) tmem_ld_32x32b_x16(tmem_base + lane_addr + TM_B1 + x * 16, w[x]);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            float acc = 0.f;
+#pragma unroll
+            for (int x = 0; x < KP; ++x)
+              if (x < kn) acc += __uint_as_float(w[x][c]);
+            v[c] = __float_as_uint(acc);
+          }
+        }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(A_B1EMPTY + slot));
+        if (lane == 0) mbar_arrive(bar(A_B1EMPTY));
         float gv[16];
         if (L < p.K) {
           float act[16];
@@ -449,14 +489,26 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
         }
       }
       {   // E3: dQc[q, j]
-        mbar_wait(bar(A_B3FULL + slot), (u >> 1) & 1);
+        mbar_wait(bar(A_B3FULL), u & 1);
         tcgen05_fence_after();
         uint32_t v[16];
-        tmem_ld_32x32b_x16(tmem_base + lane_addr + TM_B3 + slot * 16, v);
-        tmem_wait_ld();
+        {
+          uint32_t w[KP][16];
+#pragma unroll
+          for (int x = 0; x < KP; ++x) tmem_ld_32x32b_x16(tmem_base + lane_addr + TM_B3 + x * 16, w[x]);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            float acc = 0.f;
+#pragma unroll
+            for (int x = 0; x < KP; ++x)
+              if (x < kn) acc += __uint_as_float(w[x][c]);
+            v[c] = __float_as_uint(acc);
+          }
+        }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(A_B3EMPTY + slot));
+        if (lane == 0) mbar_arrive(bar(A_B3EMPTY));
         if (qd == 0) {
           float gv[16];
           if (L < p.Q) {
@@ -532,7 +584,8 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
 // =========================================================================== //
 constexpr int kThreads2 = 256;
 constexpr int S2_DN1 = 0, S2_AC = 16384, S2_BYTES = 18432, S2_RING = 3;
-constexpr uint32_t TM2_D5 = 0, TM2_D6 = 32;
+constexpr int KP2 = 8;                                   // partial accumulators of B5 (32 K steps -> chains of 4)
+constexpr uint32_t TM2_D5 = 0, TM2_D6 = 256;             // D5: 2 slots x KP2 x 16 columns
 enum { C_TTFULL = 0, C_SFULL = 1, C_SEMPTY = 4, C_D5FULL = 7, C_D5EMPTY = 9, C_D6FULL = 11, C_COUNT = 12 };
 
 struct Bwd2Params {
@@ -575,7 +628,7 @@ trilinear_bwd2_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 128);
+    tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
   tcgen05_fence_before();
@@ -618,9 +671,14 @@ trilinear_bwd2_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
         mbar_wait(bar(C_D5EMPTY + (pi & 1)), ((pi >> 1) & 1) ^ 1);
         tcgen05_fence_after();
         // B5: dAc^T[l, (s,a)] = T_r[l, x] . dN1[(s,a), x]^T      (x = (i,g,j), 512 = 32 K steps)
-        for (int ks = 0; ks < 32; ++ks)
-          umma_bf16_ss(tmem_base + TM2_D5 + (pi & 1) * 16, desc_kmajor(sT + (ks >> 2) * 2048, ks & 3),
-                       desc_kmajor(st + S2_DN1 + (ks >> 2) * 2048, ks & 3), id_b5, ks > 0 ? 1u : 0u);
+        {
+          const uint64_t da0 = desc_kmajor(sT, 0), db0 = desc_kmajor(st + S2_DN1, 0);
+#pragma unroll
+          for (int ks = 0; ks < 32; ++ks)
+            umma_bf16_ss(tmem_base + TM2_D5 + (pi & 1) * (KP2 * 16) + (ks & (KP2 - 1)) * 16,
+                         da0 + (uint64_t)(((ks >> 2) * 2048 + (ks & 3) * 32) >> 4),
+                         db0 + (uint64_t)(((ks >> 2) * 2048 + (ks & 3) * 32) >> 4), id_b5, ks >= KP2 ? 1u : 0u);
+        }
         umma_commit(bar(C_D5FULL + (pi & 1)));
         // B6: dT_r^T[x, l] += dN1[(s,a), x]^T . Ac_r[(s,a), l]
         for (int t = 0; t < 4; ++t)
@@ -641,8 +699,22 @@ trilinear_bwd2_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
       mbar_wait(bar(C_D5FULL + (pi & 1)), (pi >> 1) & 1);
       tcgen05_fence_after();
       uint32_t v[16];
-      tmem_ld_32x32b_x16(tmem_base + lane_addr + TM2_D5 + (pi & 1) * 16, v);
-      tmem_wait_ld();
+      {
+        float acc[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+#pragma unroll
+        for (int x = 0; x < KP2; x += 2) {
+          uint32_t w0[16], w1[16];
+          tmem_ld_32x32b_x16(tmem_base + lane_addr + TM2_D5 + (pi & 1) * (KP2 * 16) + x * 16, w0);
+          tmem_ld_32x32b_x16(tmem_base + lane_addr + TM2_D5 + (pi & 1) * (KP2 * 16) + (x + 1) * 16, w1);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 16; ++c) acc[c] += __uint_as_float(w0[c]) + __uint_as_float(w1[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] = __float_as_uint(acc[c]);
+      }
       tcgen05_fence_before();
       if (qd == 0 && lane < 16) {
 #pragma unroll
@@ -685,7 +757,7 @@ trilinear_bwd2_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
   __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, 128);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -710,12 +782,16 @@ int trilinear_bwd_tc(const bf16* vc, const bf16* qc, const bf16* ac, const bf16*
   if (int rc = make_tmap_3d(&tdn, dn1, 512, d.A, (uint64_t)d.B * d.R, 512, (uint64_t)d.A * 512, 64, 8)) return rc;
   if (int rc = make_tmap_3d(&ta8, ac, RD, d.A, d.B, RD, (uint64_t)d.A * RD, 64, 8)) return rc;
 
-  cudaError_t e = cudaFuncSetAttribute(trilinear_bwd1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem1);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(trilinear_bwd2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem2);
-  if (e != cudaSuccess) {
-    set_error("trilinear_bwd_tc smem attr: %s", cudaGetErrorString(e));
-    return (int)e;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(trilinear_bwd1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem1);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(trilinear_bwd2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem2);
+    if (e != cudaSuccess) {
+      set_error("trilinear_bwd_tc smem attr: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
   }
   Bwd1Params p1{dzv, dzq, dn1, dbv, dbq, d.B, d.K, d.Q, d.A, d.R, N};
   const int grid1 = d.B < kNumSMsB200 ? d.B : kNumSMsB200;

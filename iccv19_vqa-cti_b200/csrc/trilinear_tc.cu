@@ -329,10 +329,14 @@ int trilinear_fwd_tc(const bf16* vc, const bf16* qc, const bf16* ac, const bf16*
   if (int rc = make_tmap_3d(&tq, qc, RD, d.Q, d.B, RD, (uint64_t)d.Q * RD, 64, 16)) return rc;
   if (int rc = make_tmap_3d(&ta, ac, RD, d.A, d.B, RD, (uint64_t)d.A * RD, 64, 16)) return rc;
   TriTcParams p{rowmask, logits, d.B, d.K, d.Q, d.A, d.R, 32 * d.A};
-  cudaError_t e = cudaFuncSetAttribute(trilinear_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) {
-    set_error("trilinear_fwd_tc smem attr: %s", cudaGetErrorString(e));
-    return (int)e;
+  static size_t smem_set = 0;          // raise the dynamic shared memory limit once per size (not a stream operation)
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(trilinear_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("trilinear_fwd_tc smem attr: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    smem_set = smem;
   }
   const int grid = d.B < kNumSMsB200 ? d.B : kNumSMsB200;
   trilinear_fwd_tc_kernel<<<grid, kThreads, smem, stream>>>(tt, tv, tq, ta, p);

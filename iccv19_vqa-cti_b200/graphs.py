@@ -1,0 +1,58 @@
+"""CUDA-graph capture of a whole hot-path step (forward, backward, gradient all-reduce).
+
+The path launches ~100 of its own kernels plus PyTorch's allocator / autograd bookkeeping per step;
+issued eagerly from Python that is several milliseconds of host time, more than the kernels take.
+Capturing the step once and replaying it removes the host from the loop (no tracing compiler: the
+graph holds exactly the kernels the eager step launched, on the stream they were launched on).
+
+Every launch goes through the C ABI on ``torch.cuda.current_stream()``, tensor maps are passed by
+value, and all buffers come from torch's caching allocator (graph-private pool during capture), so
+the step is capturable as is.  The only host-side state that must not leak into a capture are the
+version-keyed caches (bf16 weight packs, the bf16 copy of the image features): they are dropped
+before capture so that the pack / cast kernels are part of the graph and re-run on every replay.
+"""
+from __future__ import annotations
+
+from typing import Callable, Iterable
+
+import torch
+
+from . import fc as _fc
+
+
+def reset_caches(modules: Iterable[torch.nn.Module], tensors: Iterable[torch.Tensor] = ()) -> None:
+    for root in modules:
+        for m in root.modules():
+            if hasattr(m, "_pack"):
+                m._pack = None
+            if hasattr(m, "_rank_pack"):
+                m._rank_pack = None
+    for t in tensors:
+        if hasattr(t, _fc._FEAT_ATTR):
+            delattr(t, _fc._FEAT_ATTR)
+
+
+class GraphedStep:
+    """``GraphedStep(step, modules, static_tensors)``: warm ``step`` up on a side stream, capture it, then
+    ``replay()``.  ``step`` must read its inputs from static tensors (copy new data into them before a
+    replay, or make the host-to-device copies part of ``step``) and must set ``p.grad = None`` itself if it
+    runs a backward pass."""
+
+    def __init__(self, step: Callable[[], object], modules: Iterable[torch.nn.Module],
+                 static_tensors: Iterable[torch.Tensor] = (), warmup: int = 3):
+        modules, static_tensors = list(modules), list(static_tensors)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        reset_caches(modules, static_tensors)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.output = step()
+
+    def replay(self):
+        self.graph.replay()
+        return self.output
