@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from . import functions as F_
-from .fc import FCNet, WNLinear, cast_features, check_dropout
+from .fc import FCNet, WNLinear, cast_features, features_f32_2d
 
 
 class BCNet(nn.Module):
@@ -57,9 +57,12 @@ class BCNet(nn.Module):
         v_bf16, rowmask = cast_features(v)
         lv, pv = self.v_net.single()
         lq, pq = self.q_net.single()
-        for p in (pv, pq, self.dropout.p):
-            check_dropout(self, p)
-        return F_.BiLogitsFn.apply((B, K, Q, G, C), [lv.packed(), lq.packed()], v_bf16,
+        drops = None
+        if self.training:
+            sites = [F_.new_drop(p, True) for p in (pv, pq, self.dropout.p)]
+            if any(d is not None for d in sites):
+                drops = (features_f32_2d(v) if sites[0] is not None else None, *sites)
+        return F_.BiLogitsFn.apply((B, K, Q, G, C), [lv.packed(), lq.packed()], drops, v_bf16,
                                    rowmask if rowmask_wanted else None, q, self._effective_h_mat(), self.h_bias,
                                    lv.weight_v, lv.weight_g, lv.bias, lq.weight_v, lq.weight_g, lq.bias)
 
@@ -75,9 +78,12 @@ class BCNet(nn.Module):
         v_bf16, _ = cast_features(v)
         lv, pv = self.v_net.single()
         lq, pq = self.q_net.single()
-        for p in (pv, pq):
-            check_dropout(self, p)
-        out = F_.PoolFn.apply((B, K, Q, 0, C), [lv.packed(), lq.packed()], v_bf16, q, None, w, lv.weight_v,
+        drops = None
+        if self.training:
+            sites = [F_.new_drop(p, True) for p in (pv, pq)]
+            if any(d is not None for d in sites):
+                drops = (features_f32_2d(v) if sites[0] is not None else None, *sites, None)
+        out = F_.PoolFn.apply((B, K, Q, 0, C), [lv.packed(), lq.packed()], drops, v_bf16, q, None, w, lv.weight_v,
                               lv.weight_g, lv.bias, lq.weight_v, lq.weight_g, lq.bias)
         if 1 < self.k:
             out = out.view(B, -1, self.k).sum(2)                   # AvgPool1d(k) * k (src/bc.py:75-77)

@@ -43,6 +43,21 @@ int cti_cast_rows_mask(const float* x, void* out_bf16, uint8_t* rowmask, int64_t
                              static_cast<cudaStream_t>(stream));
 }
 
+int cti_cast_rows_dropout(const float* x, void* out_bf16, uint8_t* rowmask, int64_t rows, int cols, float p,
+                          uint64_t seed, uint64_t offset, void* stream) {
+  return cti::cast_rows_dropout(x, static_cast<__nv_bfloat16*>(out_bf16), rowmask, rows, cols, p, seed, offset,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int cti_dropout_f32(float* x, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream) {
+  return cti::dropout_f32(x, n, p, seed, offset, static_cast<cudaStream_t>(stream));
+}
+
+int cti_dropout_bf16(const void* x, void* out, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream) {
+  return cti::dropout_bf16(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), n, p, seed, offset,
+                           static_cast<cudaStream_t>(stream));
+}
+
 int cti_wn_pack(const float* v, const float* g, void* w_eff_bf16, float* sumsq, int n_groups, int rows_per_group,
                 int cols, void* stream) {
   return cti::wn_pack(v, g, static_cast<__nv_bfloat16*>(w_eff_bf16), sumsq, n_groups, rows_per_group, cols,

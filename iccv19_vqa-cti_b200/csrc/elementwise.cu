@@ -52,6 +52,97 @@ __global__ void __launch_bounds__(256) cast_rows_mask_kernel(const float* __rest
 }
 
 // ------------------------------------------------------------------------- //
+// Dropout (training mode): keep mask = Philox4x32-10(seed, (element / 4, offset)) word (element % 4) >= p * 2^32,
+// kept values scaled by 1 / (1 - p).  The mask is a pure function of (seed, offset, element index), so the
+// backward kernels regenerate it instead of storing it (reference: nn.Dropout on the FCNet input, src/fc.py:25-26).
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+
+struct DropoutRng {
+  uint2 key;
+  uint32_t offset, threshold;
+  float scale;
+};
+__host__ inline DropoutRng make_rng(float p, uint64_t seed, uint64_t offset) {
+  DropoutRng r;
+  r.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  r.offset = (uint32_t)offset;
+  const double t = (double)p * 4294967296.0;
+  r.threshold = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+  r.scale = p < 1.f ? 1.f / (1.f - p) : 0.f;
+  return r;
+}
+// keep flags (times scale) of the 4 consecutive elements starting at element index 4 * quad
+__device__ __forceinline__ float4 dropout_scale4(const DropoutRng& r, uint64_t quad) {
+  const uint4 w = philox4x32_10(make_uint4((uint32_t)quad, (uint32_t)(quad >> 32), r.offset, 0u), r.key);
+  return make_float4(w.x >= r.threshold ? r.scale : 0.f, w.y >= r.threshold ? r.scale : 0.f,
+                     w.z >= r.threshold ? r.scale : 0.f, w.w >= r.threshold ? r.scale : 0.f);
+}
+
+// out = bf16(dropout(x)), rowmask from the UNDROPPED row (cols % 8 == 0)
+__global__ void __launch_bounds__(256) cast_rows_dropout_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                                uint8_t* __restrict__ rowmask, long rows, int cols,
+                                                                const DropoutRng rng) {
+  const int lane = threadIdx.x & 31;
+  const long row = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* x4 = reinterpret_cast<const float4*>(x + row * cols);
+  uint4* o4 = reinterpret_cast<uint4*>(out + row * cols);
+  const uint64_t quad0 = static_cast<uint64_t>(row) * (cols >> 2);
+  const int n8 = cols >> 3;
+  bool nz = false;
+  for (int i = lane; i < n8; i += 32) {
+    const float4 a = __ldcs(x4 + 2 * i), b = __ldcs(x4 + 2 * i + 1);
+    nz |= (a.x != 0.f) | (a.y != 0.f) | (a.z != 0.f) | (a.w != 0.f) | (b.x != 0.f) | (b.y != 0.f) | (b.z != 0.f) | (b.w != 0.f);
+    const float4 ka = dropout_scale4(rng, quad0 + 2 * i), kb = dropout_scale4(rng, quad0 + 2 * i + 1);
+    uint4 u;
+    u.x = pack_bf16x2(a.x * ka.x, a.y * ka.y);
+    u.y = pack_bf16x2(a.z * ka.z, a.w * ka.w);
+    u.z = pack_bf16x2(b.x * kb.x, b.y * kb.y);
+    u.w = pack_bf16x2(b.z * kb.z, b.w * kb.w);
+    o4[i] = u;
+  }
+  if (rowmask != nullptr) {
+    const unsigned any = __ballot_sync(0xffffffffu, nz);
+    if (lane == 0) rowmask[row] = (any == 0u) ? 1 : 0;
+  }
+}
+
+// x[e] *= keep(e) / (1 - p), fp32 in place: backward of the input dropout (n % 4 == 0)
+__global__ void __launch_bounds__(256) dropout_f32_kernel(float* __restrict__ x, long n4, const DropoutRng rng) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 v = reinterpret_cast<float4*>(x)[i];
+  const float4 k = dropout_scale4(rng, (uint64_t)i);
+  v.x *= k.x; v.y *= k.y; v.z *= k.z; v.w *= k.w;
+  reinterpret_cast<float4*>(x)[i] = v;
+}
+
+// out = dropout(x), bf16 (n % 4 == 0); out may alias x
+__global__ void __launch_bounds__(256) dropout_bf16_kernel(const __nv_bfloat16* x, __nv_bfloat16* out, long n4,
+                                                           const DropoutRng rng) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const uint2 u = reinterpret_cast<const uint2*>(x)[i];
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+  const float4 k = dropout_scale4(rng, (uint64_t)i);
+  uint2 o;
+  o.x = pack_bf16x2(a.x * k.x, a.y * k.y);
+  o.y = pack_bf16x2(b.x * k.z, b.y * k.w);
+  reinterpret_cast<uint2*>(out)[i] = o;
+}
+
+// ------------------------------------------------------------------------- //
 // weight norm.  A "group" is rows_per_group consecutive rows of the (n_groups*rows_per_group, cols)
 // matrix; each group has its own scalar g and Frobenius norm (one group = one nn.Linear).
 constexpr int kSeg = 4096;   // elements reduced by one block
@@ -164,6 +255,33 @@ int cast_rows_mask(const float* x, __nv_bfloat16* out, uint8_t* rowmask, long ro
   CTI_REQUIRE(blocks < (1l << 31), "cast_rows_mask: too many rows");
   cast_rows_mask_kernel<<<(unsigned)blocks, warps * 32, 0, s>>>(x, out, rowmask, rows, cols);
   return check_launch("cast_rows_mask_kernel");
+}
+
+int cast_rows_dropout(const float* x, __nv_bfloat16* out, uint8_t* rowmask, long rows, int cols, float p, uint64_t seed,
+                      uint64_t offset, cudaStream_t s) {
+  CTI_REQUIRE(rows >= 0 && cols > 0 && (cols & 7) == 0, "cast_rows_dropout: cols=%d must be a multiple of 8", cols);
+  CTI_REQUIRE(p >= 0.f && p < 1.f, "cast_rows_dropout: p=%f outside [0, 1)", p);
+  if (rows == 0) return 0;
+  CTI_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0, "cast_rows_dropout: buffers must be 16-byte aligned");
+  const long blocks = (rows + 7) / 8;
+  CTI_REQUIRE(blocks < (1l << 31), "cast_rows_dropout: too many rows");
+  cast_rows_dropout_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, out, rowmask, rows, cols, make_rng(p, seed, offset));
+  return check_launch("cast_rows_dropout_kernel");
+}
+
+int dropout_f32(float* x, long n, float p, uint64_t seed, uint64_t offset, cudaStream_t s) {
+  CTI_REQUIRE(n >= 0 && (n & 3) == 0 && p >= 0.f && p < 1.f, "dropout_f32: bad arguments (n=%ld, p=%f)", n, p);
+  if (n == 0) return 0;
+  dropout_f32_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, s>>>(x, n / 4, make_rng(p, seed, offset));
+  return check_launch("dropout_f32_kernel");
+}
+
+int dropout_bf16(const __nv_bfloat16* x, __nv_bfloat16* out, long n, float p, uint64_t seed, uint64_t offset,
+                 cudaStream_t s) {
+  CTI_REQUIRE(n >= 0 && (n & 3) == 0 && p >= 0.f && p < 1.f, "dropout_bf16: bad arguments (n=%ld, p=%f)", n, p);
+  if (n == 0) return 0;
+  dropout_bf16_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, s>>>(x, out, n / 4, make_rng(p, seed, offset));
+  return check_launch("dropout_bf16_kernel");
 }
 
 int wn_pack(const float* v, const float* g, __nv_bfloat16* w, float* sumsq, int n_groups, int rows_per_group, int cols,

@@ -45,11 +45,12 @@ class WNLinear(nn.Module):
         return self._pack[1]
 
 
-def check_dropout(module: nn.Module, p: float) -> None:
-    if module.training and p > 0:
-        raise NotImplementedError(
-            "cti_b200: training-mode dropout (p > 0) is not implemented in the sm_100a kernels yet; "
-            "call .eval() (gradients are still available) or build the module with dropout 0")
+def features_f32_2d(v: torch.Tensor) -> torch.Tensor:
+    """(B, K, Dv) features as a contiguous fp32 (B*K, Dv) matrix (input of the fused cast + dropout kernel)."""
+    x = v.detach()
+    if x.dtype != torch.float32:
+        x = x.float()
+    return x.reshape(-1, x.shape[-1]).contiguous()
 
 
 class FCNet(nn.Module):
@@ -72,10 +73,10 @@ class FCNet(nn.Module):
         shape = x.shape
         y = x.reshape(-1, shape[-1])
         for p, idx, act in self._plan:
-            check_dropout(self, p)
             lin = self.main[idx]
             fused = act in ('', 'ReLU')
-            y = F_.WNLinearFn.apply(y, lin.weight_v, lin.weight_g, lin.bias, act == 'ReLU', lin.packed())
+            y = F_.WNLinearFn.apply(y, lin.weight_v, lin.weight_g, lin.bias, act == 'ReLU', lin.packed(),
+                                    F_.new_drop(p, self.training))
             if not fused:                                 # activations other than ReLU are not on the CTI path
                 y = self.main[idx + 1](y)
         return y.view(*shape[:-1], y.shape[-1])

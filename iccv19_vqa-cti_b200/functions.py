@@ -57,8 +57,31 @@ def _pick_splits(tiles: int, k_blocks: int) -> int:
     return best
 
 
+# --------------------------------------------------------------------------- #
+# training-mode dropout: a site is (p, seed, offset); the kernels regenerate the Philox mask from it
+# --------------------------------------------------------------------------- #
+_DROP_SITES = [0]
+
+
+def new_drop(p: float, training: bool):
+    """A fresh dropout site, or None when dropout is the identity (eval mode / p == 0).  Masks are a pure function
+    of (torch.initial_seed(), site counter, element index): deterministic under torch.manual_seed and call order."""
+    if not training or p <= 0:
+        return None
+    _DROP_SITES[0] += 1
+    return (float(p), torch.initial_seed() & 0x7FFFFFFFFFFFFFFF, _DROP_SITES[0])
+
+
+def cast_in(x2d: torch.Tensor, drop):
+    x2d = x2d.detach().contiguous()
+    if x2d.dtype != F32:
+        x2d = x2d.float()
+    return K_.cast_rows(x2d)[0] if drop is None else K_.cast_rows_dropout(x2d, drop)[0]
+
+
 def lin_bwd(x: torch.Tensor, dz: torch.Tensor, V: torch.Tensor, g: torch.Tensor, pk: Packed, n_groups: int,
-            need_dx: bool, dx_relu_aux: Optional[torch.Tensor] = None, dx_f32: bool = False):
+            need_dx: bool, dx_relu_aux: Optional[torch.Tensor] = None, dx_f32: bool = False, alpha: float = 1.0,
+            dx_alpha: float = 1.0):
     """Backward of one layer group given the pre-activation gradient dz (M, N) bf16.
     Returns dV (like V), dg (like g), dx (bf16 masked by dx_relu_aux > 0, or fp32) or None."""
     M, Kin = x.shape
@@ -68,12 +91,13 @@ def lin_bwd(x: torch.Tensor, dz: torch.Tensor, V: torch.Tensor, g: torch.Tensor,
     tiles = -(-N // 128) * -(-Kin // tile_n)
     splits = _pick_splits(tiles, -(-M // 64))
     dw = torch.zeros((N, Kin), dtype=F32, device=x.device)
-    K_.gemm(dz, x, N, Kin, M, a_mn=True, b_mn=True, accum_f32=dw, k_splits=splits, tile_n=tile_n)
+    K_.gemm(dz, x, N, Kin, M, a_mn=True, b_mn=True, accum_f32=dw, k_splits=splits, tile_n=tile_n, alpha=alpha)
     dV, dg = K_.wn_grad(dw, V.detach().contiguous(), g.detach().reshape(n_groups).contiguous(), pk.sumsq, n_groups)
     dx = None
     if need_dx:
         # dgrad: dx[M, K_in] = dz W_eff  (W_eff stored [N][K_in] = MN-major B operand)
-        ob, of = K_.gemm(dz, pk.w, M, Kin, N, b_mn=True, relu_aux=dx_relu_aux, out_bf16=not dx_f32, out_f32=dx_f32)
+        ob, of = K_.gemm(dz, pk.w, M, Kin, N, b_mn=True, relu_aux=dx_relu_aux, out_bf16=not dx_f32, out_f32=dx_f32,
+                         alpha=dx_alpha)
         dx = of if dx_f32 else ob
     return dV, dg.reshape(g.shape), dx
 
@@ -123,10 +147,11 @@ class WNLinearFn(Function):
     x fp32 (M, K_in) -> fp32 (M, N)."""
 
     @staticmethod
-    def forward(ctx, x, V, g, bias, relu: bool, pk: Optional[Packed]):
+    def forward(ctx, x, V, g, bias, relu: bool, pk: Optional[Packed], drop=None):
         if pk is None:
             pk = pack_layer(V, g, 1)
-        xb, _ = K_.cast_rows(x.detach().contiguous())
+        xb = cast_in(x, drop)
+        ctx.drop = drop
         yb, yf = lin_fwd(xb, pk, bias, relu, out_bf16=relu, out_f32=True)
         ctx.save_for_backward(xb, yb if relu else None, V, g)
         ctx.pk = pk
@@ -141,7 +166,9 @@ class WNLinearFn(Function):
         db = torch.zeros((N,), dtype=F32, device=dy.device)
         dz = K_.act_bwd_bias(dy.contiguous(), yb if ctx.relu else None, True, db)
         dV, dg, dx = lin_bwd(xb, dz, V, g, ctx.pk, 1, ctx.need_dx, dx_f32=True)
-        return dx, dV, dg, db, None, None
+        if dx is not None and ctx.drop is not None:
+            K_.dropout_f32_(dx, ctx.drop)
+        return dx, dV, dg, db, None, None, None
 
 
 # --------------------------------------------------------------------------- #
@@ -151,17 +178,32 @@ class TriLogitsFn(Function):
     (src/attention.py:55-56).  Returns the (B,K,Q,A,G) view of a (B,G,K,Q,A) buffer."""
 
     @staticmethod
-    def forward(ctx, dims, packs, v_bf16, rowmask, q, a, T_g, *w):
+    def forward(ctx, dims, packs, drops, v_bf16, rowmask, q, a, T_g, *w):
+        """drops: None (eval) or (v_f32_2d, dv, dq, da, dvn, dqn, dan) -- input dropout of the three tucker nets and of
+        the per-rank nets (one mask per modality shared by its R per-rank nets)."""
         B, K, Q, A, G, R = dims
+        dv = dq = da = dvn = dqn = dan = None
+        if drops is not None:
+            v_f32, dv, dq, da, dvn, dqn, dan = drops
+            if dv is not None:
+                v_bf16 = K_.cast_rows_dropout(v_f32, dv)[0]
         # w = (V, g, b) x [v_tucker, q_tucker, a_tucker, v_net, q_net, a_net]
         groups = (1, 1, 1, R, R, R)
         pk: List[Packed] = [packs[i] if packs is not None else pack_layer(w[3 * i], w[3 * i + 1], groups[i])
                             for i in range(6)]
-        xq, _ = K_.cast_rows(q.detach().reshape(B * Q, -1).contiguous())
-        xa, _ = K_.cast_rows(a.detach().reshape(B * A, -1).contiguous())
+        xq = cast_in(q.reshape(B * Q, -1), dq)
+        xa = cast_in(a.reshape(B * A, -1), da)
         yv, _ = lin_fwd(v_bf16, pk[0], w[2], True)
         yq, _ = lin_fwd(xq, pk[1], w[5], True)
         ya, _ = lin_fwd(xa, pk[2], w[8], True)
+        # dropped copies double as the ReLU-and-dropout mask of the dgrad epilogue (x_d > 0 <=> kept and active)
+        if dvn is not None:
+            yv = K_.dropout_bf16(yv, dvn)
+        if dqn is not None:
+            yq = K_.dropout_bf16(yq, dqn)
+        if dan is not None:
+            ya = K_.dropout_bf16(ya, dan)
+        ctx.drops = (dq, da, dvn, dqn, dan)
         vc, _ = lin_fwd(yv, pk[3], w[11], True)
         qc, _ = lin_fwd(yq, pk[4], w[14], True)
         ac, _ = lin_fwd(ya, pk[5], w[17], True)
@@ -182,9 +224,11 @@ class TriLogitsFn(Function):
         dl = dlogits.permute(0, 4, 1, 2, 3).contiguous()
         dzv, dzq, dza, dbvn, dbqn, dban, dtpack = K_.trilinear_bwd(vc, qc, ac, tpack, dl, B, K, Q, A, G, R)
         # per-rank nets: input = tucker output (post-ReLU), so dx is masked by it -> dz of the tucker layer
-        dVvn, dgvn, dzvt = lin_bwd(yv, dzv, w[9], w[10], pk[3], R, True, dx_relu_aux=yv)
-        dVqn, dgqn, dzqt = lin_bwd(yq, dzq, w[12], w[13], pk[4], R, True, dx_relu_aux=yq)
-        dVan, dgan, dzat = lin_bwd(ya, dza, w[15], w[16], pk[5], R, True, dx_relu_aux=ya)
+        dq_drop, da_drop, dvn, dqn, dan = ctx.drops
+        sc = lambda d: 1.0 if d is None else 1.0 / (1.0 - d[0])
+        dVvn, dgvn, dzvt = lin_bwd(yv, dzv, w[9], w[10], pk[3], R, True, dx_relu_aux=yv, dx_alpha=sc(dvn))
+        dVqn, dgqn, dzqt = lin_bwd(yq, dzq, w[12], w[13], pk[4], R, True, dx_relu_aux=yq, dx_alpha=sc(dqn))
+        dVan, dgan, dzat = lin_bwd(ya, dza, w[15], w[16], pk[5], R, True, dx_relu_aux=ya, dx_alpha=sc(dan))
         H = yv.shape[1]
         dbvt, dbqt, dbat = _colsum(dzvt, H), _colsum(dzqt, H), _colsum(dzat, H)
         dVvt, dgvt, _ = lin_bwd(v_bf16, dzvt, w[0], w[1], pk[0], 1, False)
@@ -192,10 +236,14 @@ class TriLogitsFn(Function):
         dVat, dgat, da = lin_bwd(xa, dzat, w[6], w[7], pk[2], 1, ctx.need[1], dx_f32=True)
         dT = unpack_core_grad(dtpack, T_g)
         if dq is not None:
+            if dq_drop is not None:
+                K_.dropout_f32_(dq, dq_drop)
             dq = dq.view(B, Q, -1)
         if da is not None:
+            if da_drop is not None:
+                K_.dropout_f32_(da, da_drop)
             da = da.view(B, A, -1)
-        return (None, None, None, None, dq, da, dT,
+        return (None, None, None, None, None, dq, da, dT,
                 dVvt, dgvt, dbvt, dVqt, dgqt, dbqt, dVat, dgat, dbat,
                 dVvn, dgvn, dbvn.view_as(w[11]), dVqn, dgqn, dbqn.view_as(w[14]), dVan, dgan, dban.view_as(w[17]))
 
@@ -267,16 +315,23 @@ class PoolFn(Function):
     BCNet.forward_with_weights (src/bc.py:70-74): projections + attention-weighted pooling."""
 
     @staticmethod
-    def forward(ctx, dims, packs, v_bf16, q, a, wts, *w):
+    def forward(ctx, dims, packs, drops, v_bf16, q, a, wts, *w):
+        """drops: None (eval) or (v_f32_2d, dv, dq, da): input dropout of the three projections."""
         B, K, Q, A, C = dims
         n = 3 if A > 0 else 2
         pk = [packs[i] if packs is not None else pack_layer(w[3 * i], w[3 * i + 1], 1) for i in range(n)]
-        xq, _ = K_.cast_rows(q.detach().reshape(B * Q, -1).contiguous())
+        dq_drop = da_drop = None
+        if drops is not None:
+            v_f32, dv, dq_drop, da_drop = drops
+            if dv is not None:
+                v_bf16 = K_.cast_rows_dropout(v_f32, dv)[0]
+        ctx.drops = (dq_drop, da_drop)
+        xq = cast_in(q.reshape(B * Q, -1), dq_drop)
         vp, _ = lin_fwd(v_bf16, pk[0], w[2], True)
         qp, _ = lin_fwd(xq, pk[1], w[5], True)
         xa = ap = None
         if A > 0:
-            xa, _ = K_.cast_rows(a.detach().reshape(B * A, -1).contiguous())
+            xa = cast_in(a.reshape(B * A, -1), da_drop)
             ap, _ = lin_fwd(xa, pk[2], w[8], True)
         wd = _sample_contiguous(wts.detach())
         if wd.dtype != F32:
@@ -304,10 +359,14 @@ class PoolFn(Function):
             dVa, dga, da = lin_bwd(xa, dza, w[6], w[7], pk[2], 1, ctx.need[1], dx_f32=True)
             grads += [dVa, dga, dba]
             if da is not None:
+                if ctx.drops[1] is not None:
+                    K_.dropout_f32_(da, ctx.drops[1])
                 da = da.view(B, A, -1)
         if dq is not None:
+            if ctx.drops[0] is not None:
+                K_.dropout_f32_(dq, ctx.drops[0])
             dq = dq.view(B, Q, -1)
-        return (None, None, None, dq, da, dw if ctx.need[2] else None, *grads)
+        return (None, None, None, None, dq, da, dw if ctx.need[2] else None, *grads)
 
 
 # --------------------------------------------------------------------------- #
@@ -316,11 +375,21 @@ class BiLogitsFn(Function):
     of BiAttention (src/attention.py:36-37) written as -inf.  hmat (G, C) is the effective h_mat."""
 
     @staticmethod
-    def forward(ctx, dims, packs, v_bf16, rowmask, q, hmat, hbias, *w):
+    def forward(ctx, dims, packs, drops, v_bf16, rowmask, q, hmat, hbias, *w):
+        """drops: None (eval) or (v_f32_2d, dv, dq, datt): input dropout of v_net / q_net and the attention dropout on
+        the v projection (reference src/bc.py:53)."""
         B, K, Q, G, C = dims
         pk = [packs[i] if packs is not None else pack_layer(w[3 * i], w[3 * i + 1], 1) for i in range(2)]
-        xq, _ = K_.cast_rows(q.detach().reshape(B * Q, -1).contiguous())
+        dq_drop = datt = None
+        if drops is not None:
+            v_f32, dv, dq_drop, datt = drops
+            if dv is not None:
+                v_bf16 = K_.cast_rows_dropout(v_f32, dv)[0]
+        ctx.drops = (dq_drop, datt)
+        xq = cast_in(q.reshape(B * Q, -1), dq_drop)
         vb, _ = lin_fwd(v_bf16, pk[0], w[2], True)
+        if datt is not None:
+            vb = K_.dropout_bf16(vb, datt)             # the kernels' (vb > 0) mask then also carries the dropout mask
         qb, _ = lin_fwd(xq, pk[1], w[5], True)
         hm = hmat.detach().reshape(G, C).contiguous()
         hb = hbias.detach().reshape(G).contiguous()
@@ -338,8 +407,14 @@ class BiLogitsFn(Function):
         w = ctx.saved_tensors[7:]
         pk = ctx.pk
         dzv, dzq, dbv, dbq, dh, dhb = K_.bilinear_bwd(vb, qb, hm, dlogits.contiguous(), B, K, Q, G, C)
-        dVv, dgv, _ = lin_bwd(v_bf16, dzv, w[0], w[1], pk[0], 1, False)
+        dq_drop, datt = ctx.drops
+        sc = 1.0 if datt is None else 1.0 / (1.0 - datt[0])
+        dVv, dgv, _ = lin_bwd(v_bf16, dzv, w[0], w[1], pk[0], 1, False, alpha=sc)
+        if datt is not None:
+            dbv = dbv * sc
         dVq, dgq, dq = lin_bwd(xq, dzq, w[3], w[4], pk[1], 1, ctx.need_dq, dx_f32=True)
         if dq is not None:
+            if dq_drop is not None:
+                K_.dropout_f32_(dq, dq_drop)
             dq = dq.view(B, Q, -1)
-        return (None, None, None, None, dq, dh.view_as(hmat), dhb.view_as(hbias), dVv, dgv, dbv, dVq, dgq, dbq)
+        return (None, None, None, None, None, dq, dh.view_as(hmat), dhb.view_as(hbias), dVv, dgv, dbv, dVq, dgq, dbq)

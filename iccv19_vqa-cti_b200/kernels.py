@@ -82,6 +82,34 @@ def cast_rows(x: torch.Tensor, want_mask: bool = False) -> Tuple[torch.Tensor, O
     return out, mask
 
 
+def cast_rows_dropout(x: torch.Tensor, drop, want_mask: bool = False):
+    """bf16(dropout(x)) for fp32 (rows, cols); drop = (p, seed, offset).  The zero-row mask is of the undropped rows."""
+    _req(x, F32, "cast_rows_dropout.x")
+    rows, cols = x.shape
+    out = torch.empty((rows, cols), dtype=BF16, device=x.device)
+    mask = torch.empty((rows,), dtype=torch.uint8, device=x.device) if want_mask else None
+    _call("cti_cast_rows_dropout", _lib.load().cti_cast_rows_dropout,
+          (x.data_ptr(), out.data_ptr(), _ptr(mask), rows, cols, drop[0], drop[1], drop[2], _stream()),
+          nbytes=6.0 * rows * cols)
+    return out, mask
+
+
+def dropout_f32_(x: torch.Tensor, drop) -> torch.Tensor:
+    """In place x *= keep / (1 - p): backward of cast_rows_dropout with the same (p, seed, offset)."""
+    _req(x, F32, "dropout_f32_.x")
+    _call("cti_dropout_f32", _lib.load().cti_dropout_f32, (x.data_ptr(), x.numel(), drop[0], drop[1], drop[2], _stream()),
+          nbytes=8.0 * x.numel())
+    return x
+
+
+def dropout_bf16(x: torch.Tensor, drop) -> torch.Tensor:
+    _req(x, BF16, "dropout_bf16.x")
+    out = torch.empty_like(x)
+    _call("cti_dropout_bf16", _lib.load().cti_dropout_bf16,
+          (x.data_ptr(), out.data_ptr(), x.numel(), drop[0], drop[1], drop[2], _stream()), nbytes=4.0 * x.numel())
+    return out
+
+
 def wn_pack(v: torch.Tensor, g: torch.Tensor, n_groups: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """v (n_groups*rows_per_group, cols) fp32, g (n_groups,) fp32 -> (W_eff bf16, sumsq fp32[n_groups])."""
     _req(v, F32, "wn_pack.v")

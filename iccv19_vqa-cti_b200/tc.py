@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from . import functions as F_
-from .fc import FCNet, cast_features, check_dropout
+from .fc import FCNet, cast_features, features_f32_2d
 
 
 class TCNet(nn.Module):
@@ -75,8 +75,14 @@ class TCNet(nn.Module):
         lv, pv = self.v_tucker.single()
         lq, pq = self.q_tucker.single()
         la, pa = self.a_tucker.single()
-        for p in (pv, pq, pa, self.v_net[0].single()[1], self.q_net[0].single()[1], self.a_net[0].single()[1]):
-            check_dropout(self, p)
+        drops = None
+        if self.training:
+            # input dropout of the tucker nets and of the per-rank nets.  The R per-rank nets of a modality share ONE
+            # mask here (the reference draws R independent ones, src/tc.py:29-31): see DESIGN.md section 7.
+            sites = [F_.new_drop(p, True) for p in (pv, pq, pa, self.v_net[0].single()[1], self.q_net[0].single()[1],
+                                                    self.a_net[0].single()[1])]
+            if any(d is not None for d in sites):
+                drops = (features_f32_2d(v) if sites[0] is not None else None, *sites)
         # weight packs are cached on the parameters' version counters (optimizer steps bump them)
         rank_params = [p for nets in (self.v_net, self.q_net, self.a_net) for p in nets.parameters()]
         key = tuple(p._version for p in rank_params) + (rank_params[0].data_ptr(),)
@@ -93,7 +99,7 @@ class TCNet(nn.Module):
                                              F_.pack_layer(Van, gan, self.rank)], stacks)
         packs = [lv.packed(), lq.packed(), la.packed()] + cache[1]
         dims = (B, K, Q, A, G, self.rank)
-        return F_.TriLogitsFn.apply(dims, packs, v_bf16, rowmask if rowmask_wanted else None, q, a, self.T_g,
+        return F_.TriLogitsFn.apply(dims, packs, drops, v_bf16, rowmask if rowmask_wanted else None, q, a, self.T_g,
                                     lv.weight_v, lv.weight_g, lv.bias, lq.weight_v, lq.weight_g, lq.bias,
                                     la.weight_v, la.weight_g, la.bias, Vvn, gvn, bvn, Vqn, gqn, bqn, Van, gan, ban)
 
@@ -109,9 +115,12 @@ class TCNet(nn.Module):
         lv, pv = self.v_tucker.single()
         lq, pq = self.q_tucker.single()
         la, pa = self.a_tucker.single()
-        for p in (pv, pq, pa):
-            check_dropout(self, p)
+        drops = None
+        if self.training:
+            sites = [F_.new_drop(p, True) for p in (pv, pq, pa)]
+            if any(d is not None for d in sites):
+                drops = (features_f32_2d(v) if sites[0] is not None else None, *sites)
         packs = [lv.packed(), lq.packed(), la.packed()]
         dims = (B, K, Q, A, self.h_dim)
-        return F_.PoolFn.apply(dims, packs, v_bf16, q, a, w, lv.weight_v, lv.weight_g, lv.bias, lq.weight_v,
+        return F_.PoolFn.apply(dims, packs, drops, v_bf16, q, a, w, lv.weight_v, lv.weight_g, lv.bias, lq.weight_v,
                                lq.weight_g, lq.bias, la.weight_v, la.weight_g, la.bias)

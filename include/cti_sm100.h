@@ -37,6 +37,19 @@ const char* cti_last_error(void);
  * replaces: src/attention.py:55 and :36  `(0 == v.abs().sum(2))`, plus the fp32->bf16 operand cast. */
 int cti_cast_rows_mask(const float* x, void* out_bf16, uint8_t* rowmask, int64_t rows, int cols, void* stream);
 
+/* ---- training-mode dropout -------------------------------------------------------------------
+ * The keep mask is a pure function of (seed, offset, element index): Philox4x32-10 keyed by `seed`, counter
+ * (element / 4, offset); kept values are scaled by 1 / (1 - p).  Backward regenerates the mask from the same
+ * (seed, offset) instead of storing it.
+ * replaces: nn.Dropout on the FCNet input (src/fc.py:25-26) and BCNet's attention dropout (src/bc.py:53). */
+/* out = bf16(dropout(x)); rowmask (may be NULL) is computed from the undropped rows; cols % 8 == 0. */
+int cti_cast_rows_dropout(const float* x, void* out_bf16, uint8_t* rowmask, int64_t rows, int cols, float p,
+                          uint64_t seed, uint64_t offset, void* stream);
+/* x *= keep / (1 - p) in place, fp32: backward of an input dropout applied by cti_cast_rows_dropout (n % 4 == 0). */
+int cti_dropout_f32(float* x, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
+/* out = dropout(x) on bf16 data (n % 4 == 0); out may alias x. */
+int cti_dropout_bf16(const void* x, void* out, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
+
 /* ---- weight-norm fold ----------------------------------------------------------------------
  * A matrix of n_groups stacked nn.Linear weights, each (rows_per_group, cols), each with its own
  * scalar g:  sumsq[i] = ||V_i||_F^2,  W_eff_i = bf16(V_i * g_i / ||V_i||_F).
