@@ -232,7 +232,7 @@ def run_b200(args):
     KS.STATS.launches = 0
     resident_step()
     launches_per_step = KS.STATS.launches
-    use_graph = not args.no_graph and world == 1          # multi-GPU steps (NCCL inside the step) are issued eagerly
+    use_graph = not args.no_graph and world == 1          # multi-GPU: NCCL launched from autograd hooks did not capture (hang); issued eagerly
     eager_ms = None
     run_resident = resident_step
     if use_graph:

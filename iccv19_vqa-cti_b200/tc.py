@@ -50,7 +50,10 @@ class TCNet(nn.Module):
     # ------------------------------------------------------------------ #
     def _rank_group(self, nets: nn.ModuleList):
         """One grouped layer out of the R per-rank FCNets: V (R*d, H), g (R,), b (R*d,)."""
-        lins = [n.single()[0] for n in nets]
+        cache = self.__dict__.setdefault("_rank_lins", {})
+        lins = cache.get(id(nets))
+        if lins is None:
+            lins = cache[id(nets)] = [n.single()[0] for n in nets]
         V = torch.cat([l.weight_v for l in lins], 0)
         g = torch.stack([l.weight_g for l in lins], 0)
         b = torch.cat([l.bias for l in lins], 0)
@@ -84,7 +87,10 @@ class TCNet(nn.Module):
             if any(d is not None for d in sites):
                 drops = (features_f32_2d(v) if sites[0] is not None else None, *sites)
         # weight packs are cached on the parameters' version counters (optimizer steps bump them)
-        rank_params = [p for nets in (self.v_net, self.q_net, self.a_net) for p in nets.parameters()]
+        rank_params = self.__dict__.get("_rank_params")
+        if rank_params is None:                      # module traversal is slow: list the per-rank parameters once
+            rank_params = [p for nets in (self.v_net, self.q_net, self.a_net) for p in nets.parameters()]
+            self.__dict__["_rank_params"] = rank_params
         key = tuple(p._version for p in rank_params) + (rank_params[0].data_ptr(),)
         cache = self._rank_pack
         if cache is not None and cache[0] == key and not torch.is_grad_enabled():
