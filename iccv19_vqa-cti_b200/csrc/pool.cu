@@ -31,7 +31,8 @@ namespace {
 
 using bf16 = __nv_bfloat16;
 
-constexpr int kThreads = 384;
+constexpr int kThreads = 384;                 // forward
+constexpr int kThreadsBwd = 640;              // backward: warps 12-15 handle dV / dw, warps 16-19 share the Z epilogue (odd chunks)
 constexpr int kEpiWarp0 = 4;
 constexpr int kBuildWarp0 = 8;
 constexpr int CCH = 128;                       // channels per chunk = TMEM lanes
@@ -75,7 +76,7 @@ __host__ __device__ inline size_t pool_smem_bytes(bool bwd) {
 }
 
 template <bool BWD>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(BWD ? kThreadsBwd : kThreads, 1)
 pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_q,
             const __grid_constant__ CUtensorMap tmap_a, const PoolParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -93,9 +94,9 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // zero the w tiles (pad rows / columns stay zero for the whole kernel) and the bias accumulators
-  for (uint32_t i = threadIdx.x; i < 2 * W_BYTES / 16; i += kThreads) st_shared_v4(sW + i * 16, 0, 0, 0, 0);
+  for (uint32_t i = threadIdx.x; i < 2 * W_BYTES / 16; i += blockDim.x) st_shared_v4(sW + i * 16, 0, 0, 0, 0);
   if (BWD)
-    for (int i = threadIdx.x; i < 3 * MAX_C; i += kThreads) db_acc[i] = 0.f;
+    for (int i = threadIdx.x; i < 3 * MAX_C; i += blockDim.x) db_acc[i] = 0.f;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_v);
     tma_prefetch_desc(&tmap_q);
@@ -104,7 +105,7 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < V_STAGES; ++s) {
       mbar_init(bar(B_VFULL + s), 1);
-      mbar_init(bar(B_VEMPTY + s), 5);                // MMA commit + the 4 epilogue warps that read the stage
+      mbar_init(bar(B_VEMPTY + s), BWD ? 9 : 5);      // MMA commit + every epilogue warp that reads the stage
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar(B_WFULL + s), 128);
@@ -205,7 +206,7 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ 
         }
       }
     }
-  } else if (warp >= kBuildWarp0) {
+  } else if (warp >= kBuildWarp0 && warp < kBuildWarp0 + 4) {
     // ------------------------------ w tile builder ----------------------------------------
     // w[k][q][a] fp32 (contiguous per sample) -> bf16 tile element (row k, column a*16 + q).  All global
     // loads of a batch are issued before the first shared-memory store so their latencies overlap.
@@ -268,7 +269,7 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ 
       fence_proxy_async_smem();
       mbar_arrive(bar(B_WFULL + (sl & 1)));
     }
-  } else if (warp >= kEpiWarp0) {
+  } else if (warp >= kEpiWarp0) {      // warps 4-7: Z epilogue (forward output / dQp, dAp, KRd); warps 12-15 (backward): dV, dw
     // ------------------------------ epilogue ------------------------------------------------
     const int qd = warp & 3;
     const int cl = qd * 32 + lane;                       // channel within the chunk = TMEM lane
@@ -334,16 +335,21 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ 
       }
     };
 
+    if (BWD && warp >= 12 && warp < 16) {
+      for (int h = 0; h < total; ++h) {
+        mbar_wait(bar(B_VFULL + h % V_STAGES), (h / V_STAGES) & 1);      // TMA data of the stage visible to this thread
+        epi_b(h);
+      }
+    } else {
     Side cur;
-    for (int g = 0; g < total; ++g) {
+    // backward: two warp groups alternate over the chunks (Z / KRd are double buffered on the chunk parity)
+    for (int g = (BWD && warp >= 16) ? 1 : 0; g < total; g += BWD ? 2 : 1) {
       const int sl = g / p.nchunks, ch = g % p.nchunks;
       const int b = blockIdx.x + sl * gridDim.x, c = ch * CCH + cl;
       mbar_wait(bar(B_VFULL + g % V_STAGES), (g / V_STAGES) & 1);      // TMA data of this stage visible to this thread
       load_side(g, cur);
-      if (!BWD) {                                                    // forward: the stage is not read again
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(B_VEMPTY + g % V_STAGES));
-      }
+      __syncwarp();                                                  // this group does not read the stage again
+      if (lane == 0) mbar_arrive(bar(B_VEMPTY + g % V_STAGES));
       mbar_wait(bar(B_ZFULL + (g & 1)), (g >> 1) & 1);
       tcgen05_fence_after();
       if (BWD) mbar_wait(bar(B_KEMPTY + (g & 1)), ((g >> 1) & 1) ^ 1);
@@ -395,8 +401,8 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ 
             sum_q += gq;
           }
         }
-        db_acc[MAX_C + c] += sum_q;
-        db_acc[2 * MAX_C + c] += sum_a;
+        atomicAdd(db_acc + MAX_C + c, sum_q);        // the two Z-epilogue groups may own the same channel in turn
+        atomicAdd(db_acc + 2 * MAX_C + c, sum_a);
         fence_proxy_async_smem();        // KRd rows written with st.shared are read by tcgen05.mma
       }
       tcgen05_fence_before();
@@ -405,15 +411,14 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ 
         if (BWD) mbar_arrive(bar(B_KFULL + (g & 1)));
         mbar_arrive(bar(B_ZEMPTY + (g & 1)));
       }
-      if (BWD && g > 0) epi_b(g - 1);
     }
-    if (BWD && total > 0) epi_b(total - 1);
+    }
   }
 
   tcgen05_fence_before();
   __syncthreads();
   if (BWD) {
-    for (int c = threadIdx.x; c < p.C; c += kThreads) {
+    for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
       atomicAdd(p.dbv + c, db_acc[c]);
       atomicAdd(p.dbq + c, db_acc[MAX_C + c]);
       if (p.A > 0) atomicAdd(p.dba + c, db_acc[2 * MAX_C + c]);
@@ -456,7 +461,7 @@ int launch_pool(const bf16* v, PoolParams p, cudaStream_t stream, const char* wh
     attr_set = true;
   }
   const int grid = p.B < kNumSMsB200 ? p.B : kNumSMsB200;
-  pool_kernel<BWD><<<grid, kThreads, smem, stream>>>(tv, tq, ta, p);
+  pool_kernel<BWD><<<grid, BWD ? kThreadsBwd : kThreads, smem, stream>>>(tv, tq, ta, p);
   return check_launch(who);
 }
 

@@ -61,7 +61,7 @@ __device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
 // =========================================================================== //
 // kernel 1
 // =========================================================================== //
-constexpr int kThreads1 = 576;     // 18 warps: TMA, 5 single-thread MMA issuers (1, 2, 3, 16, 17), 3 x 4 converter / epilogue warps
+constexpr int kThreads1 = 704;     // 22 warps: TMA, 5 single-thread MMA issuers (1, 2, 3, 16, 17), 4 x 4 converter / epilogue warps
 constexpr int T_BYTES = 16 * 1024, T_RING = 2;
 constexpr int OP_V = 0, OP_Q = 8192, OP_A = 10240, OP_BYTES = 12288, OP_RING = 3;
 constexpr int N1_BYTES = 32 * 1024;
@@ -69,11 +69,7 @@ constexpr int M_BYTES = 8 * 1024;
 constexpr int DL_CHUNKS = 3, DL_BYTES = DL_CHUNKS * 8192;     // dL tile [64 k][192 n]
 constexpr int D_BYTES = 6 * 1024;                             // D tile [16 q][192 (a,g,i)]
 constexpr int DB_FLOATS = 512;                                // bias-gradient accumulators (R * 16 <= 512)
-// B1 / B3 contract over 12 K steps into a 16-column tile: a single accumulator would be a chain of 12 dependent
-// tcgen05.mma (latency bound, ~90 cycles each for N = 16), so the K steps are dealt round-robin to KP partial
-// accumulators (independent chains of 3) that the epilogue adds up.  Those two stages are single-slot.
-constexpr int KP = 4;
-constexpr uint32_t TM_F1 = 0, TM_F2 = 128, TM_B1 = 192, TM_B3 = 256, TM_B2 = 320, TM_B4 = 384;
+constexpr uint32_t TM_F1 = 0, TM_F2 = 128, TM_B1 = 192, TM_B2 = 224, TM_B3 = 288, TM_B4 = 320;   // all double buffered
 
 enum { A_TFULL = 0, A_TEMPTY = 2, A_OPFULL = 4, A_OPEMPTY = 7, A_DLFULL = 10, A_DLEMPTY = 12, A_F1FULL = 14, A_F1EMPTY = 16,
        A_N1FULL = 18, A_N1EMPTY = 20, A_F2FULL = 22, A_F2EMPTY = 24, A_MFULL = 26, A_MEMPTY = 28, A_B1FULL = 30,
@@ -146,7 +142,7 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
     }
     for (int s = 0; s < 3; ++s) {
       mbar_init(bar(A_OPFULL + s), 1);
-      mbar_init(bar(A_OPEMPTY + s), 6);       // F2 and B4 issuers + the 4 epilogue warps that read Vc / Qc (ReLU masks)
+      mbar_init(bar(A_OPEMPTY + s), 10);      // F2 and B4 issuers + the 8 epilogue warps that read Vc / Qc (ReLU masks)
     }
     fence_barrier_init();
   }
@@ -256,13 +252,13 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
         const uint32_t dl = sDL + (sl & 1) * DL_BYTES;
         if (r == 0) mbar_wait(bar(A_DLFULL + (sl & 1)), (sl >> 1) & 1);
         mbar_wait(bar(A_MFULL + (u & 1)), (u >> 1) & 1);
-        mbar_wait(bar(A_B1EMPTY), (u & 1) ^ 1);
+        mbar_wait(bar(A_B1EMPTY + (u & 1)), ((u >> 1) & 1) ^ 1);
         tcgen05_fence_after();
         const uint64_t da0 = desc_kmajor(dl, 0), db0 = desc_kmajor(sM + (u & 1) * M_BYTES, 0);
         for (int ks = 0; ks < kn; ++ks)
-          umma_bf16_ss(tmem_base + TM_B1 + (ks & (KP - 1)) * 16, da0 + (uint64_t)(((ks >> 2) * 8192 + (ks & 3) * 32) >> 4),
-                       db0 + (uint64_t)(((ks >> 2) * 2048 + (ks & 3) * 32) >> 4), id_b1, ks >= KP ? 1u : 0u);
-        umma_commit(bar(A_B1FULL));
+          umma_bf16_ss(tmem_base + TM_B1 + (u & 1) * 16, da0 + (uint64_t)(((ks >> 2) * 8192 + (ks & 3) * 32) >> 4),
+                       db0 + (uint64_t)(((ks >> 2) * 2048 + (ks & 3) * 32) >> 4), id_b1, ks > 0 ? 1u : 0u);
+        umma_commit(bar(A_B1FULL + (u & 1)));
         umma_commit(bar(A_MEMPTY + (u & 1)));
         if (r == p.R - 1) umma_commit(bar(A_DLEMPTY + (sl & 1)));
         if (++r == p.R) { r = 0; ++sl; }
@@ -302,15 +298,15 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
         if ((r & 3) == 0) mbar_wait(bar(A_OPFULL + oslot), oph);
         mbar_wait(bar(A_N1FULL + (u & 1)), (u >> 1) & 1);
         mbar_wait(bar(A_DFULL + (u & 1)), (u >> 1) & 1);
-        mbar_wait(bar(A_B3EMPTY), (u & 1) ^ 1);
+        mbar_wait(bar(A_B3EMPTY + (u & 1)), ((u >> 1) & 1) ^ 1);
         mbar_wait(bar(A_B4EMPTY + (u & 1)), ((u >> 1) & 1) ^ 1);
         tcgen05_fence_after();
         const uint32_t dt = sD + (u & 1) * D_BYTES;
         const uint64_t da0 = desc_kmajor(dt, 0), db0 = desc_mnmajor(sN1 + (u & 1) * N1_BYTES, 0, 0);
         for (int ks = 0; ks < kn; ++ks)
-          umma_bf16_ss(tmem_base + TM_B3 + (ks & (KP - 1)) * 16, da0 + (uint64_t)(((ks >> 2) * 2048 + (ks & 3) * 32) >> 4),
-                       db0 + (uint64_t)((ks * 2048) >> 4), id_b3, ks >= KP ? 1u : 0u);
-        umma_commit(bar(A_B3FULL));
+          umma_bf16_ss(tmem_base + TM_B3 + (u & 1) * 16, da0 + (uint64_t)(((ks >> 2) * 2048 + (ks & 3) * 32) >> 4),
+                       db0 + (uint64_t)((ks * 2048) >> 4), id_b3, ks > 0 ? 1u : 0u);
+        umma_commit(bar(A_B3FULL + (u & 1)));
         const uint64_t dq = desc_mnmajor(op + OP_Q + (r & 3) * 32, 0, 0);
         for (int t = 0; t < nt2; ++t)
           umma_bf16_ss(tmem_base + TM_B4 + (u & 1) * 32 + t * 16, desc_mnmajor(dt + 2 * t * 2048, 0, 2048), dq, id_b4, 0u);
@@ -423,8 +419,10 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
         }
       }
     }
-  } else if (warp < 16) {
-    // ------------------------------ G3: epilogues  dVc -> dzv, dQc -> dzq, dN1 -> workspace -----------
+  } else if (warp < 16 || warp >= 18) {
+    // warps 12-15: E1 (dVc -> dzv); warps 18-21: E3 (dQc -> dzq) and E4 (dN1 -> workspace)
+    const bool do_e1 = warp < 16;
+    // ------------------------------ G3 / G4: epilogues  dVc -> dzv, dQc -> dzq, dN1 -> workspace -----------
     const int qd = warp & 3, L = qd * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
     const int RD = p.R * 16;
@@ -446,27 +444,15 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
           out[2 * x] = f0.x; out[2 * x + 1] = f0.y; out[8 + 2 * x] = f1.x; out[8 + 2 * x + 1] = f1.y;
         }
       };
-      {   // E1: dVc[k, i]
-        mbar_wait(bar(A_B1FULL), u & 1);
+      if (do_e1) {   // E1: dVc[k, i]
+        mbar_wait(bar(A_B1FULL + slot), (u >> 1) & 1);
         tcgen05_fence_after();
         uint32_t v[16];
-        {
-          uint32_t w[KP][16];
-#pragma unroll
-          for (int x = 0; x < KP; ++x) tmem_ld_32x32b_x16(tmem_base + lane_addr + TM_B1 + x * 16, w[x]);
-          tmem_wait_ld();
-#pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            float acc = 0.f;
-#pragma unroll
-            for (int x = 0; x < KP; ++x)
-              if (x < kn) acc += __uint_as_float(w[x][c]);
-            v[c] = __float_as_uint(acc);
-          }
-        }
+        tmem_ld_32x32b_x16(tmem_base + lane_addr + TM_B1 + slot * 16, v);
+        tmem_wait_ld();
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(A_B1EMPTY));
+        if (lane == 0) mbar_arrive(bar(A_B1EMPTY + slot));
         float gv[16];
         if (L < p.K) {
           float act[16];
@@ -488,27 +474,15 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
           if ((lane & 1) == 0) atomicAdd(db_acc + r * 16 + (lane >> 1), s);
         }
       }
-      {   // E3: dQc[q, j]
-        mbar_wait(bar(A_B3FULL), u & 1);
+      if (!do_e1) {   // E3: dQc[q, j]
+        mbar_wait(bar(A_B3FULL + slot), (u >> 1) & 1);
         tcgen05_fence_after();
         uint32_t v[16];
-        {
-          uint32_t w[KP][16];
-#pragma unroll
-          for (int x = 0; x < KP; ++x) tmem_ld_32x32b_x16(tmem_base + lane_addr + TM_B3 + x * 16, w[x]);
-          tmem_wait_ld();
-#pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            float acc = 0.f;
-#pragma unroll
-            for (int x = 0; x < KP; ++x)
-              if (x < kn) acc += __uint_as_float(w[x][c]);
-            v[c] = __float_as_uint(acc);
-          }
-        }
+        tmem_ld_32x32b_x16(tmem_base + lane_addr + TM_B3 + slot * 16, v);
+        tmem_wait_ld();
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(A_B3EMPTY));
+        if (lane == 0) mbar_arrive(bar(A_B3EMPTY + slot));
         if (qd == 0) {
           float gv[16];
           if (L < p.Q) {
@@ -530,7 +504,7 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
           if ((lane & 1) == 0) atomicAdd(db_acc + DB_FLOATS + r * 16 + (lane >> 1), s);
         }
       }
-      {   // E4: dN1[(a,g,i), j] -> workspace [b][r][a][(i,g,j)] bf16
+      if (!do_e1) {   // E4: dN1[(a,g,i), j] -> workspace [b][r][a][(i,g,j)] bf16
         mbar_wait(bar(A_B4FULL + slot), (u >> 1) & 1);
         tcgen05_fence_after();
         for (int t = 0; t < nt2; ++t) {
@@ -583,10 +557,11 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
 // kernel 2
 // =========================================================================== //
 constexpr int kThreads2 = 256;
-constexpr int S2_DN1 = 0, S2_AC = 16384, S2_BYTES = 18432, S2_RING = 3;
+constexpr int S2_DN1 = 0, S2_AC = 16384, S2_BYTES = 18432, S2_RING = 8;      // deep ring: the kernel is a stream of small TMA boxes
 constexpr int KP2 = 8;                                   // partial accumulators of B5 (32 K steps -> chains of 4)
 constexpr uint32_t TM2_D5 = 0, TM2_D6 = 256;             // D5: 2 slots x KP2 x 16 columns
-enum { C_TTFULL = 0, C_SFULL = 1, C_SEMPTY = 4, C_D5FULL = 7, C_D5EMPTY = 9, C_D6FULL = 11, C_COUNT = 12 };
+enum { C_TTFULL = 0, C_SFULL = 1, C_SEMPTY = 1 + S2_RING, C_D5FULL = 1 + 2 * S2_RING, C_D5EMPTY = 3 + 2 * S2_RING,
+       C_D6FULL = 5 + 2 * S2_RING, C_COUNT = 6 + 2 * S2_RING };
 
 struct Bwd2Params {
   bf16* dza;
@@ -616,7 +591,7 @@ trilinear_bwd2_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
   }
   if (warp == 1 && lane == 0) {
     mbar_init(bar(C_TTFULL), 1);
-    for (int s = 0; s < 3; ++s) {
+    for (int s = 0; s < S2_RING; ++s) {
       mbar_init(bar(C_SFULL + s), 1);
       mbar_init(bar(C_SEMPTY + s), 5);
     }
@@ -661,7 +636,7 @@ trilinear_bwd2_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t id_b5 = make_idesc_rt(128, 16, 0, 0);
+      const uint32_t id_b5 = make_idesc_rt(64, 16, 0, 0);     // only rows l < 16 are valid: M = 64 halves the A-operand read
       const uint32_t id_b6 = make_idesc_rt(128, 16, 1, 1);
       mbar_wait(bar(C_TTFULL), 0);
       for (int pi = 0; pi < n_pairs; ++pi) {
