@@ -195,9 +195,11 @@ def run_b200(args):
             ae = a_prj[gi](b_emb.unsqueeze(1)) + ae
         joint = qe.sum(1) + ae.sum(1)
         (joint * cot).sum().backward()
-        if reducer is not None:
+        if reducer is not None and not step.graphed:
             reducer.finish()
         return joint
+
+    step.graphed = False
 
     def barrier():
         if world > 1:
@@ -232,19 +234,32 @@ def run_b200(args):
     KS.STATS.launches = 0
     resident_step()
     launches_per_step = KS.STATS.launches
-    use_graph = not args.no_graph and world == 1          # multi-GPU: NCCL launched from autograd hooks did not capture (hang); issued eagerly
+    use_graph = not args.no_graph
     eager_ms = None
     run_resident = resident_step
     if use_graph:
         ms_eager, _, _ = timed(resident_step, max(3, args.steps // 4))
         eager_ms = {"ms_per_step": ms_eager / max(3, args.steps // 4), "host_issue_ms_per_step": timed.host_ms}
         try:
+            # multi-GPU: forward + backward are replayed from the graph, the bucketed NCCL all-reduce is issued
+            # eagerly right after (capturing NCCL launched from autograd hooks hung)
+            if reducer is not None:
+                reducer.set_hooks_enabled(False)
+                step.graphed = True
             graphed = cti_b200.GraphedStep(resident_step, [mods], [v_d])
-            run_resident = graphed.replay
+            if reducer is None:
+                run_resident = graphed.replay
+            else:
+                def run_resident():
+                    graphed.replay()
+                    reducer.reduce_now()
             for _ in range(3):
                 run_resident()
-        except Exception as exc:                                  # e.g. NCCL without graph support: stay eager
+        except Exception as exc:
             use_graph = False
+            step.graphed = False
+            if reducer is not None:
+                reducer.set_hooks_enabled(True)
             eager_ms["graph_capture_failed"] = repr(exc)[:200]
     sampler = ClockSampler(local) if rank == 0 else None
     ms, w0, w1 = timed(run_resident, args.steps)
@@ -268,7 +283,13 @@ def run_b200(args):
         run_e2e = e2e_step
         if use_graph:
             try:
-                run_e2e = cti_b200.GraphedStep(e2e_step, [mods], []).replay
+                g_e2e = cti_b200.GraphedStep(e2e_step, [mods], [])
+                if reducer is None:
+                    run_e2e = g_e2e.replay
+                else:
+                    def run_e2e():
+                        g_e2e.replay()
+                        reducer.reduce_now()
                 for _ in range(3):
                     run_e2e()
             except Exception:
@@ -295,7 +316,7 @@ def run_b200(args):
         run_fwd = fwd_only
         if use_graph:
             try:
-                run_fwd = cti_b200.GraphedStep(fwd_only, [mods], [v_d]).replay
+                run_fwd = cti_b200.GraphedStep(fwd_only, [], [v_d]).replay     # inference: weight packs stay cached
                 for _ in range(3):
                     run_fwd()
             except Exception:

@@ -85,6 +85,8 @@ class GradAllReducer:
             b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def _on_grad(self, p: torch.nn.Parameter) -> None:
+        if not getattr(self, "_enabled", True):
+            return
         b = self._of[p]
         b.pending -= 1
         if b.pending == 0:
@@ -106,6 +108,36 @@ class GradAllReducer:
             if self.average and self.world > 1:
                 b.flat.div_(self.world)
             b.pending = len(b.params)
+
+    def reduce_now(self) -> None:
+        """All-reduce the gradients that are sitting in ``p.grad`` right now, without hooks: used after a CUDA-graph
+        replay of forward + backward (the replay re-fills the same gradient tensors, so the autograd hooks never
+        fire).  One fused copy into each flat bucket, all buckets reduced asynchronously, one wait; the reduced
+        values are copied back into the (graph-owned) gradient tensors.  The hot path's 11.5 M fp32 gradients are
+        46 MB -- ~0.1 ms on NVLink against a step of several ms, so the lost overlap is negligible."""
+        works = []
+        for b in self.buckets:
+            grads = [p.grad for p in b.params]
+            for g, v in zip(grads, b.views):
+                if g is None:
+                    v.zero_()
+            live = [(v, g) for v, g in zip(b.views, grads) if g is not None and g.data_ptr() != v.data_ptr()]
+            if live:
+                torch._foreach_copy_([v for v, _ in live], [g for _, g in live])
+            if self.world > 1:
+                works.append(dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        for w in works:
+            w.wait()
+        for b in self.buckets:
+            if self.average and self.world > 1:
+                b.flat.div_(self.world)
+            live = [(v, p.grad) for v, p in zip(b.views, b.params) if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
+            if live:
+                torch._foreach_copy_([g for _, g in live], [v for v, _ in live])
+            b.pending = len(b.params)
+
+    def set_hooks_enabled(self, enabled: bool) -> None:
+        self._enabled = enabled
 
     def flat_grads(self) -> List[torch.Tensor]:
         return [b.flat for b in self.buckets]

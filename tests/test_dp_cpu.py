@@ -38,6 +38,19 @@ def _worker(rank, world, port, bucket_bytes, out):
         loss = ((model(x[sl]) - y[sl]) ** 2).sum()
         loss.backward()
         red.finish()
+    # hook-free path used after a CUDA-graph replay: gradients already sit in p.grad
+    red.set_hooks_enabled(False)
+    for p in model.parameters():
+        p.grad = None
+    ((model(x[sl]) - y[sl]) ** 2).sum().backward()
+    red.reduce_now()
+    again = [p.grad.clone() for p in model.parameters()]
+    red.set_hooks_enabled(True)
+    red.zero_grad()
+    ((model(x[sl]) - y[sl]) ** 2).sum().backward()
+    red.finish()
+    for a_, p in zip(again, model.parameters()):
+        assert torch.allclose(a_, p.grad, rtol=1e-6, atol=1e-7)
     grads = [p.grad.clone() for p in model.parameters()]
     norm = clip_flat_grads_(red.flat_grads(), 0.25, denom=float(x.shape[0]))
     clipped = [p.grad.clone() for p in model.parameters()]
