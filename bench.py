@@ -295,9 +295,63 @@ def run_b200(args):
             except Exception:
                 run_e2e = e2e_step
         ms_e2e, _, _ = timed(run_e2e, args.steps)
-        e2e = {"value": world * B * args.steps / (ms_e2e / 1e3), "unit": UNIT,
-               "h2d_bytes_per_step": (v_h.numel() + q_h.numel() + a_h.numel()) * 4,
-               "d2h_bytes_per_step": out_h.numel() * 4, "ms_per_step": ms_e2e / args.steps}
+        h2d = (v_h.numel() + q_h.numel() + a_h.numel()) * 4
+        e2e_serial = {"value": world * B * args.steps / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps}
+        e2e = dict(e2e_serial, h2d_bytes_per_step=h2d, d2h_bytes_per_step=out_h.numel() * 4, mode="serial")
+
+        # Same per-step work, but the host->device copy of step i+1 runs on a copy stream while step i computes
+        # (two sets of static input buffers, one captured graph per set) -- what a prefetching loader gives a user.
+        try:
+            copy_stream = torch.cuda.Stream()
+            bufs = [(torch.empty_like(v_d), torch.empty_like(q_d), torch.empty_like(a_d)) for _ in range(2)]
+            outs = [torch.empty(B, HID).pin_memory() for _ in range(2)]
+            ev_copied = [torch.cuda.Event() for _ in range(2)]
+            ev_done = [torch.cuda.Event() for _ in range(2)]
+
+            def make_compute(i):
+                vb, qb, ab = bufs[i]
+
+                def compute():
+                    joint = step(vb, qb.detach(), ab.detach())
+                    outs[i].copy_(joint.detach(), non_blocking=True)
+                return compute
+            computes = [make_compute(i) for i in range(2)]
+            if use_graph:
+                graphs = [cti_b200.GraphedStep(computes[i], [mods], [bufs[i][0]]) for i in range(2)]
+                computes = [g.replay for g in graphs]
+            state = {"i": 0, "primed": False}
+
+            def h2d_into(i):
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(ev_done[i])             # the buffers' previous consumer has finished
+                    for dst, src in zip(bufs[i], (v_h, q_h, a_h)):
+                        dst.copy_(src, non_blocking=True)
+                    ev_copied[i].record(copy_stream)
+
+            def pipelined_step():
+                i = state["i"] & 1
+                if not state["primed"]:
+                    h2d_into(i)
+                    state["primed"] = True
+                main = torch.cuda.current_stream()
+                main.wait_event(ev_copied[i])
+                computes[i]()
+                if reducer is not None and use_graph:
+                    reducer.reduce_now()
+                ev_done[i].record(main)
+                h2d_into(i ^ 1)                                    # prefetch the next step's inputs
+                state["i"] += 1
+            for _ in range(4):
+                pipelined_step()
+            torch.cuda.synchronize()
+            state["primed"] = False                                # the timed region pays its own first copy
+            ms_p, _, _ = timed(pipelined_step, args.steps)
+            e2e = {"value": world * B * args.steps / (ms_p / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": out_h.numel() * 4, "ms_per_step": ms_p / args.steps,
+                   "mode": "H2D of step i+1 overlapped with compute of step i (double-buffered inputs)",
+                   "serial": e2e_serial}
+        except Exception as exc:
+            e2e["pipelined_failed"] = repr(exc)[:200]
 
     # ---- forward-only (config[1] of BASELINE.json) -----------------------------
     def fwd_only():
