@@ -33,12 +33,24 @@ constexpr int T_BYTES = 16 * 1024;            // T_r: [16 l][512 (i,g,j)] bf16 =
 constexpr int T_RING = 3;
 constexpr int OP_V = 0, OP_Q = 8192, OP_A = 10240, OP_BYTES = 12288;   // Vc [64][64], Qc [16][64], Ac [16][64]
 constexpr int OP_RING = 3;
-constexpr int N1_BYTES = 32 * 1024;           // [(a8,g,i) 256 rows][64 cols] (columns 0..15 = j used)
+constexpr int N1_BYTES = 32 * 1024;           // [(a8,g,i) 256 rows][64 cols]: columns (r % 4) * 16 + j -- one tile holds 4 ranks
 constexpr int M_BYTES = 8 * 1024;             // [16 i][<= 256 (a,g,q16)] = 4 chunks x [16 rows][128 B]
-constexpr uint32_t TM_F1 = 0, TM_F2 = 128, TM_ACC = 256;
+// Ring depths.  The per-(sample, rank) chain F1 -> convert -> F2 -> convert -> III is several thousand cycles of
+// latency (TMEM load, smem store, proxy fence, mbarrier hand-offs), so throughput = steps in flight / latency.
+constexpr int F1_RING = 3, N1_RING = 8, F2_RING = 4, M_RING = 4;
+constexpr uint32_t TM_F1 = 0, TM_F2 = F1_RING * 64, TM_ACC = TM_F2 + F2_RING * 32;      // 192 + 128 + N (<= 192) columns
 
-enum { B_TFULL = 0, B_TEMPTY = 3, B_OPFULL = 6, B_OPEMPTY = 9, B_F1FULL = 12, B_F1EMPTY = 14, B_N1FULL = 16, B_N1EMPTY = 18,
-       B_F2FULL = 20, B_F2EMPTY = 22, B_MFULL = 24, B_MEMPTY = 26, B_ACCFULL = 28, B_ACCEMPTY = 29, B_COUNT = 30 };
+enum { B_TFULL = 0, B_TEMPTY = 3, B_OPFULL = 6, B_OPEMPTY = 9, B_F1FULL = 12, B_F1EMPTY = B_F1FULL + F1_RING,
+       B_N1FULL = B_F1EMPTY + F1_RING, B_N1EMPTY = B_N1FULL + N1_RING, B_F2FULL = B_N1EMPTY + N1_RING,
+       B_F2EMPTY = B_F2FULL + F2_RING, B_MFULL = B_F2EMPTY + F2_RING, B_MEMPTY = B_MFULL + M_RING,
+       B_ACCFULL = B_MEMPTY + M_RING, B_ACCEMPTY = B_ACCFULL + 1, B_COUNT = B_ACCEMPTY + 1 };
+
+struct RingPos {                               // slot / phase of a D-deep mbarrier ring
+  uint32_t slot = 0, ph = 0;
+  __device__ __forceinline__ void next(uint32_t depth) {
+    if (++slot == depth) { slot = 0; ph ^= 1u; }
+  }
+};
 
 struct TriTcParams {
   const uint8_t* rowmask;
@@ -47,7 +59,7 @@ struct TriTcParams {
 };
 
 __host__ __device__ inline size_t tri_tc_smem(int K, int Q, int A) {
-  return (size_t)T_RING * T_BYTES + OP_RING * OP_BYTES + 2 * N1_BYTES + 2 * M_BYTES + (size_t)2 * K * Q * A * 4 + 16 +
+  return (size_t)T_RING * T_BYTES + OP_RING * OP_BYTES + 2 * N1_BYTES + M_RING * M_BYTES + (size_t)2 * K * Q * A * 4 + 16 +
          B_COUNT * 8 + 16 + 1024;
 }
 
@@ -61,7 +73,7 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
   const uint32_t sOp = sT + T_RING * T_BYTES;
   const uint32_t sN1 = sOp + OP_RING * OP_BYTES;
   const uint32_t sM = sN1 + 2 * N1_BYTES;
-  const uint32_t sOut = sM + 2 * M_BYTES;
+  const uint32_t sOut = sM + M_RING * M_BYTES;
   const int out_floats = 2 * p.K * p.Q * p.A;
   const uint32_t sBar = (sOut + out_floats * 4 + 15u) & ~15u;
   const uint32_t tmem_slot = sBar + B_COUNT * 8;
@@ -83,13 +95,19 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
       mbar_init(bar(B_OPFULL + s), 1);
       mbar_init(bar(B_OPEMPTY + s), 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < F1_RING; ++s) {
       mbar_init(bar(B_F1FULL + s), 1);
       mbar_init(bar(B_F1EMPTY + s), 4);
+    }
+    for (int s = 0; s < N1_RING; ++s) {
       mbar_init(bar(B_N1FULL + s), 4);
       mbar_init(bar(B_N1EMPTY + s), 1);
+    }
+    for (int s = 0; s < F2_RING; ++s) {
       mbar_init(bar(B_F2FULL + s), 1);
       mbar_init(bar(B_F2EMPTY + s), 4);
+    }
+    for (int s = 0; s < M_RING; ++s) {
       mbar_init(bar(B_MFULL + s), 4);
       mbar_init(bar(B_MEMPTY + s), 1);
     }
@@ -141,21 +159,23 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
     //  bottleneck of the first version; tcgen05.commit tracks the MMAs of the committing thread only)
     if (lane == 0) {
       const uint32_t id_f1 = make_idesc_rt(128, 16, 1, 0);
+      RingPos f1;
       uint32_t tslot = 0, tph = 0, oslot = 0, oph = 0;
       int r = 0;
       for (int u = 0; u < U; ++u) {
         const uint32_t tt = sT + tslot * T_BYTES;
         mbar_wait(bar(B_TFULL + tslot), tph);
         if ((r & 3) == 0) mbar_wait(bar(B_OPFULL + oslot), oph);
-        mbar_wait(bar(B_F1EMPTY + (u & 1)), ((u >> 1) & 1) ^ 1);
+        mbar_wait(bar(B_F1EMPTY + f1.slot), f1.ph ^ 1u);
         tcgen05_fence_after();
         const uint64_t db = desc_kmajor(sOp + oslot * OP_BYTES + OP_A, r & 3);
         const uint64_t da = desc_mnmajor(tt, 0, 2048);
 #pragma unroll
         for (int t = 0; t < 4; ++t)
-          umma_bf16_ss(tmem_base + TM_F1 + (u & 1) * 64 + t * 16, da + (uint64_t)(2 * t * 2048 >> 4), db, id_f1, 0u);
-        umma_commit(bar(B_F1FULL + (u & 1)));
+          umma_bf16_ss(tmem_base + TM_F1 + f1.slot * 64 + t * 16, da + (uint64_t)(2 * t * 2048 >> 4), db, id_f1, 0u);
+        umma_commit(bar(B_F1FULL + f1.slot));
         umma_commit(bar(B_TEMPTY + tslot));
+        f1.next(F1_RING);
         if (++tslot == T_RING) { tslot = 0; tph ^= 1u; }
         if (++r == p.R) r = 0;
         if ((r & 3) == 0 && ++oslot == OP_RING) { oslot = 0; oph ^= 1u; }
@@ -165,19 +185,22 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
     // ------------------------------ MMA issuer 2: F2(u)  M = N1 . Qc_r^T ---------------------------------
     if (lane == 0) {
       const uint32_t id_f2 = make_idesc_rt(128, 16, 0, 0);
+      RingPos n1, f2;
       uint32_t oslot = 0, oph = 0;
       int r = 0;
       for (int u = 0; u < U; ++u) {
         if ((r & 3) == 0) mbar_wait(bar(B_OPFULL + oslot), oph);
-        mbar_wait(bar(B_N1FULL + (u & 1)), (u >> 1) & 1);
-        mbar_wait(bar(B_F2EMPTY + (u & 1)), ((u >> 1) & 1) ^ 1);
+        mbar_wait(bar(B_N1FULL + n1.slot), n1.ph);
+        mbar_wait(bar(B_F2EMPTY + f2.slot), f2.ph ^ 1u);
         tcgen05_fence_after();
         const uint64_t db = desc_kmajor(sOp + oslot * OP_BYTES + OP_Q, r & 3);
-        const uint64_t da = desc_kmajor(sN1 + (u & 1) * N1_BYTES, 0);
+        const uint64_t da = desc_kmajor(sN1 + (n1.slot >> 2) * N1_BYTES, n1.slot & 3);     // K step = rank within the quad tile
         for (int t2 = 0; t2 < nt2; ++t2)
-          umma_bf16_ss(tmem_base + TM_F2 + (u & 1) * 32 + t2 * 16, da + (uint64_t)(t2 * 16384 >> 4), db, id_f2, 0u);
-        umma_commit(bar(B_F2FULL + (u & 1)));
-        umma_commit(bar(B_N1EMPTY + (u & 1)));
+          umma_bf16_ss(tmem_base + TM_F2 + f2.slot * 32 + t2 * 16, da + (uint64_t)(t2 * 16384 >> 4), db, id_f2, 0u);
+        umma_commit(bar(B_F2FULL + f2.slot));
+        umma_commit(bar(B_N1EMPTY + n1.slot));
+        n1.next(N1_RING);
+        f2.next(F2_RING);
         if (++r == p.R) r = 0;
         if ((r & 3) == 0 && ++oslot == OP_RING) { oslot = 0; oph ^= 1u; }
       }
@@ -186,16 +209,18 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
     // ------------------------------ MMA issuer 3: III(u)  L += Vc_r . M  (this warp also owns TMEM) --------
     if (lane == 0) {
       const uint32_t id_3 = make_idesc_rt(128, p.N, 0, 1);
+      RingPos mr;
       uint32_t oslot = 0, oph = 0;
       int r = 0, sl = 0;
       for (int u = 0; u < U; ++u) {
         if ((r & 3) == 0) mbar_wait(bar(B_OPFULL + oslot), oph);
-        mbar_wait(bar(B_MFULL + (u & 1)), (u >> 1) & 1);
+        mbar_wait(bar(B_MFULL + mr.slot), mr.ph);
         if (r == 0) mbar_wait(bar(B_ACCEMPTY), (sl & 1) ^ 1);
         tcgen05_fence_after();
         umma_bf16_ss(tmem_base + TM_ACC, desc_kmajor(sOp + oslot * OP_BYTES + OP_V, r & 3),
-                     desc_mnmajor(sM + (u & 1) * M_BYTES, 0, 2048), id_3, r > 0 ? 1u : 0u);
-        umma_commit(bar(B_MEMPTY + (u & 1)));
+                     desc_mnmajor(sM + mr.slot * M_BYTES, 0, 2048), id_3, r > 0 ? 1u : 0u);
+        umma_commit(bar(B_MEMPTY + mr.slot));
+        mr.next(M_RING);
         if ((r & 3) == 3) umma_commit(bar(B_OPEMPTY + oslot));
         if (r == p.R - 1) umma_commit(bar(B_ACCFULL));
         if (++r == p.R) { r = 0; ++sl; }
@@ -207,21 +232,22 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
     const int qd = warp & 3, L = qd * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
     const int j = L & 15, g = (L >> 4) & 1;
+    RingPos f1, n1r;
     for (int u = 0; u < U; ++u) {
-      const int slot = u & 1;
-      mbar_wait(bar(B_F1FULL + slot), (u >> 1) & 1);
+      mbar_wait(bar(B_F1FULL + f1.slot), f1.ph);
       tcgen05_fence_after();
-      mbar_wait(bar(B_N1EMPTY + slot), ((u >> 1) & 1) ^ 1);
-      const uint32_t n1 = sN1 + slot * N1_BYTES;
+      mbar_wait(bar(B_N1EMPTY + n1r.slot), n1r.ph ^ 1u);
+      const uint32_t n1 = sN1 + (n1r.slot >> 2) * N1_BYTES;
+      const uint32_t sub = n1r.slot & 3;                       // rank within the quad tile: columns sub * 16 + j
       uint32_t v[4][8];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) tmem_ld_32x32b_x8(tmem_base + lane_addr + TM_F1 + slot * 64 + t * 16, v[t]);
+      for (int t = 0; t < 4; ++t) tmem_ld_32x32b_x8(tmem_base + lane_addr + TM_F1 + f1.slot * 64 + t * 16, v[t]);
       tmem_wait_ld();
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const int i = 4 * t + (L >> 5);
         // row = a*32 + g*16 + i  ->  row>>3 = a*4 + g*2 + (i>>3),  row&7 = i&7
-        const uint32_t off = (g * 2 + (i >> 3)) * 1024u + (i & 7) * 128u + ((((j >> 3) & 1) ^ (i & 7)) << 4) + (j & 7) * 2u;
+        const uint32_t off = (g * 2 + (i >> 3)) * 1024u + (i & 7) * 128u + (((sub * 2 + ((j >> 3) & 1)) ^ (i & 7)) << 4) + (j & 7) * 2u;
 #pragma unroll
         for (int a = 0; a < 8; ++a) {
           if (a < p.A) {
@@ -234,9 +260,11 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(bar(B_N1FULL + slot));
-        mbar_arrive(bar(B_F1EMPTY + slot));
+        mbar_arrive(bar(B_N1FULL + n1r.slot));
+        mbar_arrive(bar(B_F1EMPTY + f1.slot));
       }
+      f1.next(F1_RING);
+      n1r.next(N1_RING);
     }
   } else if (warp >= 8) {
     // ------------------------------ C2: M (TMEM) -> M tile [i][(a,g,q16)];  per-sample epilogue ------
@@ -245,16 +273,16 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
     const int et = threadIdx.x - 8 * 32;                  // 0..127 within the group
     const int per_g = p.K * p.Q * p.A;
     int r = -1, sl = 0;
+    RingPos f2, mr;
     for (int u = 0; u < U; ++u) {
-      const int slot = u & 1;
       if (++r == p.R) { r = 0; ++sl; }
-      mbar_wait(bar(B_F2FULL + slot), (u >> 1) & 1);
+      mbar_wait(bar(B_F2FULL + f2.slot), f2.ph);
       tcgen05_fence_after();
-      mbar_wait(bar(B_MEMPTY + slot), ((u >> 1) & 1) ^ 1);
-      const uint32_t mt = sM + slot * M_BYTES;
+      mbar_wait(bar(B_MEMPTY + mr.slot), mr.ph ^ 1u);
+      const uint32_t mt = sM + mr.slot * M_BYTES;
       for (int t2 = 0; t2 < nt2; ++t2) {
         uint32_t v[16];
-        tmem_ld_32x32b_x16(tmem_base + lane_addr + TM_F2 + slot * 32 + t2 * 16, v);
+        tmem_ld_32x32b_x16(tmem_base + lane_addr + TM_F2 + f2.slot * 32 + t2 * 16, v);
         tmem_wait_ld();
         const int rho = t2 * 128 + L;
         const int a = rho >> 5, i = rho & 15;
@@ -273,9 +301,11 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(bar(B_MFULL + slot));
-        mbar_arrive(bar(B_F2EMPTY + slot));
+        mbar_arrive(bar(B_MFULL + mr.slot));
+        mbar_arrive(bar(B_F2EMPTY + f2.slot));
       }
+      f2.next(F2_RING);
+      mr.next(M_RING);
       if (r == p.R - 1) {
         // ---- sample epilogue: TMEM lane = region k, column (a,g,q16) -> (G,K,Q,A) order, mask, coalesced store
         const int b = blockIdx.x + sl * gridDim.x;
@@ -319,7 +349,7 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
 // Returns -100 when the shape is outside the fast path (caller falls back to the generic kernel).
 int trilinear_fwd_tc(const bf16* vc, const bf16* qc, const bf16* ac, const bf16* tpack, const uint8_t* rowmask,
                      float* logits, TriDims d, cudaStream_t stream) {
-  if (d.G != 2 || d.K > 64 || d.Q > 16 || d.A > 8 || (d.R & 3) != 0) return -100;
+  if (d.G != 2 || d.K > 64 || d.Q > 16 || d.A > 6 || (d.R & 3) != 0) return -100;      // TMEM: 320 + 32 A columns
   const size_t smem = tri_tc_smem(d.K, d.Q, d.A);
   if (smem > 227 * 1024) return -100;
   const int RD = d.R * 16;
