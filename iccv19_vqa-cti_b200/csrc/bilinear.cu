@@ -326,10 +326,19 @@ int check_bi(const BiDims& d, const char* who) {
 
 }  // namespace
 
+int bilinear_fwd_tc(const bf16* vb, const bf16* qb, const float* hmat, const float* hbias, const uint8_t* rowmask,
+                    float* logits, BiDims d, cudaStream_t stream);                         // bilinear_tc.cu
+int bilinear_bwd_tc(const bf16* vb, const bf16* qb, const float* hmat, const float* dlogits, bf16* dzv, bf16* dzq,
+                    float* dbv, float* dbq, float* dhmat, float* dhbias, BiDims d, cudaStream_t stream);
+
 int bilinear_fwd(const bf16* vb, const bf16* qb, const float* hmat, const float* hbias, const uint8_t* rowmask,
                  float* logits, BiDims d, cudaStream_t stream) {
   if (int rc = check_bi(d, "bilinear_fwd")) return rc;
   if (d.B == 0) return 0;
+  {   // tcgen05 fast path (G <= 4, K <= 64, C <= 3072); other shapes use the generic tensor-core kernel below
+    const int rc = bilinear_fwd_tc(vb, qb, hmat, hbias, rowmask, logits, d, stream);
+    if (rc != -100) return rc;
+  }
   const BiShape s = make_bi_shape(d);
   const BiSmem lay = bi_smem(s, false);
   const size_t out_bytes = (size_t)s.MT * 16 * (s.G * 16 + 4) * 4;
@@ -348,6 +357,10 @@ int bilinear_bwd(const bf16* vb, const bf16* qb, const float* hmat, const float*
                  float* dbv, float* dbq, float* dhmat, float* dhbias, BiDims d, cudaStream_t stream) {
   if (int rc = check_bi(d, "bilinear_bwd")) return rc;
   if (d.B == 0) return 0;
+  {
+    const int rc = bilinear_bwd_tc(vb, qb, hmat, dlogits, dzv, dzq, dbv, dbq, dhmat, dhbias, d, stream);
+    if (rc != -100) return rc;
+  }
   const BiShape s = make_bi_shape(d);
   const BiSmem lay = bi_smem(s, true);
   CTI_REQUIRE(lay.total <= 227 * 1024, "bilinear_bwd: needs %zu bytes of shared memory", lay.total);
