@@ -22,6 +22,8 @@ SIGNATURES = {
     "cti_cast_rows_dropout": (c_int, [_P, _P, _P, c_int64, c_int, c_float, ctypes.c_uint64, ctypes.c_uint64, _P]),
     "cti_dropout_f32": (c_int, [_P, c_int64, c_float, ctypes.c_uint64, ctypes.c_uint64, _P]),
     "cti_dropout_bf16": (c_int, [_P, _P, c_int64, c_float, ctypes.c_uint64, ctypes.c_uint64, _P]),
+    "cti_dropout_expand": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, c_float, ctypes.c_uint64, ctypes.c_uint64, _P]),
+    "cti_dropout_reduce": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, c_float, ctypes.c_uint64, ctypes.c_uint64, _P]),
     "cti_wn_pack": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "cti_wn_grad": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "cti_gemm_bf16": (c_int, [_P, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_float, _P, c_int, _P, c_int,

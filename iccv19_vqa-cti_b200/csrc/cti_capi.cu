@@ -58,6 +58,18 @@ int cti_dropout_bf16(const void* x, void* out, int64_t n, float p, uint64_t seed
                            static_cast<cudaStream_t>(stream));
 }
 
+int cti_dropout_expand(const void* x, void* xt, int64_t rows, int cols, int rank_group, int r0, float p, uint64_t seed,
+                       uint64_t offset, void* stream) {
+  return cti::dropout_expand(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(xt), rows, cols, rank_group,
+                             r0, p, seed, offset, static_cast<cudaStream_t>(stream));
+}
+
+int cti_dropout_reduce(const void* dxt, float* acc, int64_t rows, int cols, int rank_group, int r0, float p, uint64_t seed,
+                       uint64_t offset, void* stream) {
+  return cti::dropout_reduce(static_cast<const __nv_bfloat16*>(dxt), acc, rows, cols, rank_group, r0, p, seed, offset,
+                             static_cast<cudaStream_t>(stream));
+}
+
 int cti_wn_pack(const float* v, const float* g, void* w_eff_bf16, float* sumsq, int n_groups, int rows_per_group,
                 int cols, void* stream) {
   return cti::wn_pack(v, g, static_cast<__nv_bfloat16*>(w_eff_bf16), sumsq, n_groups, rows_per_group, cols,

@@ -36,6 +36,10 @@ int cast_rows_dropout(const float* x, __nv_bfloat16* out, uint8_t* rowmask, long
 int dropout_f32(float* x, long n, float p, uint64_t seed, uint64_t offset, cudaStream_t s);
 int dropout_bf16(const __nv_bfloat16* x, __nv_bfloat16* out, long n, float p, uint64_t seed, uint64_t offset,
                  cudaStream_t s);
+int dropout_expand(const __nv_bfloat16* x, __nv_bfloat16* xt, long rows, int cols, int RG, int r0, float p, uint64_t seed,
+                   uint64_t offset, cudaStream_t s);
+int dropout_reduce(const __nv_bfloat16* dxt, float* acc, long rows, int cols, int RG, int r0, float p, uint64_t seed,
+                   uint64_t offset, cudaStream_t s);
 int wn_pack(const float* v, const float* g, __nv_bfloat16* w, float* sumsq, int n_groups, int rows_per_group, int cols,
             cudaStream_t s);
 int wn_grad(const float* dw, const float* v, const float* g, const float* sumsq, float* dv, float* dg, float* dot_ws,

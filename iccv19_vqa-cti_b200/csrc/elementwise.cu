@@ -142,6 +142,43 @@ __global__ void __launch_bounds__(256) dropout_bf16_kernel(const __nv_bfloat16* 
   reinterpret_cast<uint2*>(out)[i] = o;
 }
 
+// Per-rank input dropout of the R per-rank nets (reference src/tc.py:29-31, 47-49): rank r sees x * keep_r with its
+// OWN mask.  Mask of (rank r, row, column c): dropout element index (r * rows + row) * cols + c.
+//   expand: xt[row, j * cols + c] = x[row, c] * keep_{r0 + j}[row, c] / (1 - p)       j < RG   (bf16)
+//   reduce: acc[row, c] += sum_j dxt[row, j * cols + c] * keep_{r0 + j}[row, c] / (1 - p)       (fp32 accumulate)
+__global__ void __launch_bounds__(256) dropout_expand_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ xt,
+                                                             long rows, int cols4, int RG, int r0, const DropoutRng rng) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;      // (row, quad of 4 columns)
+  if (i >= rows * cols4) return;
+  const long row = i / cols4;
+  const int c4 = static_cast<int>(i - row * cols4);
+  const uint2 u = reinterpret_cast<const uint2*>(x)[i];
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+  for (int j = 0; j < RG; ++j) {
+    const float4 k = dropout_scale4(rng, (static_cast<uint64_t>(r0 + j) * rows + row) * cols4 + c4);
+    uint2 o;
+    o.x = pack_bf16x2(a.x * k.x, a.y * k.y);
+    o.y = pack_bf16x2(b.x * k.z, b.y * k.w);
+    reinterpret_cast<uint2*>(xt)[(row * RG + j) * cols4 + c4] = o;
+  }
+}
+
+__global__ void __launch_bounds__(256) dropout_reduce_kernel(const __nv_bfloat16* __restrict__ dxt, float* __restrict__ acc,
+                                                             long rows, int cols4, int RG, int r0, const DropoutRng rng) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * cols4) return;
+  const long row = i / cols4;
+  const int c4 = static_cast<int>(i - row * cols4);
+  float4 s = reinterpret_cast<float4*>(acc)[i];
+  for (int j = 0; j < RG; ++j) {
+    const uint2 u = reinterpret_cast<const uint2*>(dxt)[(row * RG + j) * cols4 + c4];
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+    const float4 k = dropout_scale4(rng, (static_cast<uint64_t>(r0 + j) * rows + row) * cols4 + c4);
+    s.x += a.x * k.x; s.y += a.y * k.y; s.z += b.x * k.z; s.w += b.y * k.w;
+  }
+  reinterpret_cast<float4*>(acc)[i] = s;
+}
+
 // ------------------------------------------------------------------------- //
 // weight norm.  A "group" is rows_per_group consecutive rows of the (n_groups*rows_per_group, cols)
 // matrix; each group has its own scalar g and Frobenius norm (one group = one nn.Linear).
@@ -282,6 +319,24 @@ int dropout_bf16(const __nv_bfloat16* x, __nv_bfloat16* out, long n, float p, ui
   if (n == 0) return 0;
   dropout_bf16_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, s>>>(x, out, n / 4, make_rng(p, seed, offset));
   return check_launch("dropout_bf16_kernel");
+}
+
+int dropout_expand(const __nv_bfloat16* x, __nv_bfloat16* xt, long rows, int cols, int RG, int r0, float p, uint64_t seed,
+                   uint64_t offset, cudaStream_t s) {
+  CTI_REQUIRE(rows >= 0 && cols > 0 && (cols & 3) == 0 && RG > 0 && r0 >= 0 && p >= 0.f && p < 1.f, "dropout_expand: bad arguments");
+  if (rows == 0) return 0;
+  const long n = rows * (cols / 4);
+  dropout_expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, xt, rows, cols / 4, RG, r0, make_rng(p, seed, offset));
+  return check_launch("dropout_expand_kernel");
+}
+
+int dropout_reduce(const __nv_bfloat16* dxt, float* acc, long rows, int cols, int RG, int r0, float p, uint64_t seed,
+                   uint64_t offset, cudaStream_t s) {
+  CTI_REQUIRE(rows >= 0 && cols > 0 && (cols & 3) == 0 && RG > 0 && r0 >= 0 && p >= 0.f && p < 1.f, "dropout_reduce: bad arguments");
+  if (rows == 0) return 0;
+  const long n = rows * (cols / 4);
+  dropout_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dxt, acc, rows, cols / 4, RG, r0, make_rng(p, seed, offset));
+  return check_launch("dropout_reduce_kernel");
 }
 
 int wn_pack(const float* v, const float* g, __nv_bfloat16* w, float* sumsq, int n_groups, int rows_per_group, int cols,

@@ -61,6 +61,9 @@ def _pick_splits(tiles: int, k_blocks: int) -> int:
 # training-mode dropout: a site is (p, seed, offset); the kernels regenerate the Philox mask from it
 # --------------------------------------------------------------------------- #
 _DROP_SITES = [0]
+# Input dropout of the R per-rank nets of a TCNet: "independent" = one mask per rank, the reference's semantics
+# (src/tc.py:29-31); "shared" = one mask per modality shared by its R nets (same marginals, ~1.6x faster training step).
+RANK_DROPOUT = "independent"
 
 
 def new_drop(p: float, training: bool):
@@ -100,6 +103,62 @@ def lin_bwd(x: torch.Tensor, dz: torch.Tensor, V: torch.Tensor, g: torch.Tensor,
                          alpha=dx_alpha)
         dx = of if dx_f32 else ob
     return dV, dg.reshape(g.shape), dx
+
+
+# --------------------------------------------------------------------------- #
+# per-rank nets with INDEPENDENT input dropout masks (reference src/tc.py:29-31: each of the R FCNets owns a Dropout)
+# --------------------------------------------------------------------------- #
+RANK_GROUP = 4          # ranks handled per GEMM: the masked copies of the input are materialised 4 ranks at a time
+
+
+def _block_diag_weights(w_eff: torch.Tensor, R: int, rg: int) -> torch.Tensor:
+    """(R*d, H) -> (R/rg, rg*d, rg*H): group g's weight is block diagonal, block j = W_eff of rank g*rg + j."""
+    d, H = w_eff.shape[0] // R, w_eff.shape[1]
+    src = w_eff.view(R // rg, rg, d, H)
+    out = torch.zeros((R // rg, rg * d, rg * H), dtype=w_eff.dtype, device=w_eff.device)
+    for j in range(rg):
+        out[:, j * d:(j + 1) * d, j * H:(j + 1) * H] = src[:, j]
+    return out
+
+
+def rank_proj_fwd(y: torch.Tensor, pk: Packed, bias: torch.Tensor, drop, R: int) -> torch.Tensor:
+    """Vc[:, r*d:(r+1)*d] = relu(W_r (keep_r * y) / (1-p) + b_r) with one mask per rank: the masked copies of y are
+    materialised RANK_GROUP ranks at a time and multiplied with a block-diagonal weight by the ordinary GEMM."""
+    M, H = y.shape
+    N = pk.w.shape[0]
+    d = N // R
+    rg = RANK_GROUP if R % RANK_GROUP == 0 else 1
+    wt = _block_diag_weights(pk.w, R, rg)
+    out = torch.empty((M, N), dtype=BF16, device=y.device)
+    b = bias.detach()
+    for gi in range(R // rg):
+        xt = K_.dropout_expand(y, rg, gi * rg, drop)
+        K_.gemm(xt, wt[gi], M, rg * d, rg * H, bias=b[gi * rg * d:(gi + 1) * rg * d], relu=True,
+                out=out[:, gi * rg * d:(gi + 1) * rg * d])
+    return out
+
+
+def rank_proj_bwd(y: torch.Tensor, dz: torch.Tensor, V: torch.Tensor, g: torch.Tensor, pk: Packed, drop, R: int):
+    """Backward of rank_proj_fwd.  Returns dV, dg and the fp32 gradient w.r.t. y (before y's own ReLU mask)."""
+    M, H = y.shape
+    N = pk.w.shape[0]
+    d = N // R
+    rg = RANK_GROUP if R % RANK_GROUP == 0 else 1
+    wt = _block_diag_weights(pk.w, R, rg)
+    dw = torch.empty((N, H), dtype=F32, device=y.device)
+    acc = torch.zeros((M, H), dtype=F32, device=y.device)
+    splits = _pick_splits(-(-rg * d // 128) * -(-rg * H // 256), -(-M // 64))
+    for gi in range(R // rg):
+        xt = K_.dropout_expand(y, rg, gi * rg, drop)                     # same masks as the forward
+        dzg = dz[:, gi * rg * d:(gi + 1) * rg * d]
+        dwt = torch.zeros((rg * d, rg * H), dtype=F32, device=y.device)
+        K_.gemm(dzg, xt, rg * d, rg * H, M, a_mn=True, b_mn=True, accum_f32=dwt, k_splits=splits, tile_n=256)
+        for j in range(rg):
+            dw[(gi * rg + j) * d:(gi * rg + j + 1) * d] = dwt[j * d:(j + 1) * d, j * H:(j + 1) * H]
+        dxt, _ = K_.gemm(dzg, wt[gi], M, rg * H, rg * d, b_mn=True)
+        K_.dropout_reduce_(dxt, acc, rg, gi * rg, drop)
+    dV, dg = K_.wn_grad(dw, V.detach().contiguous(), g.detach().reshape(R).contiguous(), pk.sumsq, R)
+    return dV, dg.reshape(g.shape), acc
 
 
 def _colsum(dz: torch.Tensor, n: int) -> torch.Tensor:
@@ -196,17 +255,21 @@ class TriLogitsFn(Function):
         yv, _ = lin_fwd(v_bf16, pk[0], w[2], True)
         yq, _ = lin_fwd(xq, pk[1], w[5], True)
         ya, _ = lin_fwd(xa, pk[2], w[8], True)
-        # dropped copies double as the ReLU-and-dropout mask of the dgrad epilogue (x_d > 0 <=> kept and active)
-        if dvn is not None:
-            yv = K_.dropout_bf16(yv, dvn)
-        if dqn is not None:
-            yq = K_.dropout_bf16(yq, dqn)
-        if dan is not None:
-            ya = K_.dropout_bf16(ya, dan)
+        independent = RANK_DROPOUT == "independent"
+        ctx.independent = independent
         ctx.drops = (dq, da, dvn, dqn, dan)
-        vc, _ = lin_fwd(yv, pk[3], w[11], True)
-        qc, _ = lin_fwd(yq, pk[4], w[14], True)
-        ac, _ = lin_fwd(ya, pk[5], w[17], True)
+
+        def rank_nets(y, pki, bias, drop):
+            if drop is None:
+                return y, lin_fwd(y, pki, bias, True)[0]
+            if independent:                                   # one mask per rank, as in the reference
+                return y, rank_proj_fwd(y, pki, bias, drop, R)
+            # shared mask: the dropped copy doubles as the ReLU-and-dropout mask of the dgrad epilogue
+            yd = K_.dropout_bf16(y, drop)
+            return yd, lin_fwd(yd, pki, bias, True)[0]
+        yv, vc = rank_nets(yv, pk[3], w[11], dvn)
+        yq, qc = rank_nets(yq, pk[4], w[14], dqn)
+        ya, ac = rank_nets(ya, pk[5], w[17], dan)
         tpack = pack_core(T_g)
         logits = K_.trilinear_fwd(vc, qc, ac, tpack, rowmask, B, K, Q, A, G, R)
         ctx.save_for_backward(v_bf16, xq, xa, yv, yq, ya, vc, qc, ac, tpack, T_g, *w)
@@ -226,11 +289,19 @@ class TriLogitsFn(Function):
         # per-rank nets: input = tucker output (post-ReLU), so dx is masked by it -> dz of the tucker layer
         dq_drop, da_drop, dvn, dqn, dan = ctx.drops
         sc = lambda d: 1.0 if d is None else 1.0 / (1.0 - d[0])
-        dVvn, dgvn, dzvt = lin_bwd(yv, dzv, w[9], w[10], pk[3], R, True, dx_relu_aux=yv, dx_alpha=sc(dvn))
-        dVqn, dgqn, dzqt = lin_bwd(yq, dzq, w[12], w[13], pk[4], R, True, dx_relu_aux=yq, dx_alpha=sc(dqn))
-        dVan, dgan, dzat = lin_bwd(ya, dza, w[15], w[16], pk[5], R, True, dx_relu_aux=ya, dx_alpha=sc(dan))
         H = yv.shape[1]
-        dbvt, dbqt, dbat = _colsum(dzvt, H), _colsum(dzqt, H), _colsum(dzat, H)
+
+        def rank_nets_bwd(y, dz, V, g, pki, drop):
+            """-> dV, dg, pre-activation gradient of the tucker layer (bf16) and its bias gradient"""
+            if drop is not None and ctx.independent:
+                dV_, dg_, acc = rank_proj_bwd(y, dz, V, g, pki, drop, R)
+                db = torch.zeros((H,), dtype=F32, device=y.device)
+                return dV_, dg_, K_.act_bwd_bias(acc, y, True, db), db
+            dV_, dg_, dzt = lin_bwd(y, dz, V, g, pki, R, True, dx_relu_aux=y, dx_alpha=sc(drop))
+            return dV_, dg_, dzt, _colsum(dzt, H)
+        dVvn, dgvn, dzvt, dbvt = rank_nets_bwd(yv, dzv, w[9], w[10], pk[3], dvn)
+        dVqn, dgqn, dzqt, dbqt = rank_nets_bwd(yq, dzq, w[12], w[13], pk[4], dqn)
+        dVan, dgan, dzat, dbat = rank_nets_bwd(ya, dza, w[15], w[16], pk[5], dan)
         dVvt, dgvt, _ = lin_bwd(v_bf16, dzvt, w[0], w[1], pk[0], 1, False)
         dVqt, dgqt, dq = lin_bwd(xq, dzqt, w[3], w[4], pk[1], 1, ctx.need[0], dx_f32=True)
         dVat, dgat, da = lin_bwd(xa, dzat, w[6], w[7], pk[2], 1, ctx.need[1], dx_f32=True)

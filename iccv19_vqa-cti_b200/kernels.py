@@ -116,6 +116,27 @@ def dropout_bf16(x: torch.Tensor, drop) -> torch.Tensor:
     return out
 
 
+def dropout_expand(x: torch.Tensor, rank_group: int, r0: int, drop) -> torch.Tensor:
+    """(M, H) bf16 -> (M, rank_group * H): column block j holds x masked with rank (r0 + j)'s own dropout mask."""
+    _req(x, BF16, "dropout_expand.x")
+    M, H = x.shape
+    xt = torch.empty((M, rank_group * H), dtype=BF16, device=x.device)
+    _call("cti_dropout_expand", _lib.load().cti_dropout_expand,
+          (x.data_ptr(), xt.data_ptr(), M, H, rank_group, r0, drop[0], drop[1], drop[2], _stream()),
+          nbytes=2.0 * M * H * (1 + rank_group))
+    return xt
+
+
+def dropout_reduce_(dxt: torch.Tensor, acc: torch.Tensor, rank_group: int, r0: int, drop) -> None:
+    """acc (M, H) fp32 += sum_j dxt[:, j*H:(j+1)*H] * mask_{r0+j}: backward of dropout_expand."""
+    _req(dxt, BF16, "dropout_reduce_.dxt")
+    _req(acc, F32, "dropout_reduce_.acc")
+    M, H = acc.shape
+    _call("cti_dropout_reduce", _lib.load().cti_dropout_reduce,
+          (dxt.data_ptr(), acc.data_ptr(), M, H, rank_group, r0, drop[0], drop[1], drop[2], _stream()),
+          nbytes=2.0 * M * H * rank_group + 8.0 * M * H)
+
+
 def wn_pack(v: torch.Tensor, g: torch.Tensor, n_groups: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """v (n_groups*rows_per_group, cols) fp32, g (n_groups,) fp32 -> (W_eff bf16, sumsq fp32[n_groups])."""
     _req(v, F32, "wn_pack.v")
@@ -143,22 +164,35 @@ def wn_grad(dw: torch.Tensor, v: torch.Tensor, g: torch.Tensor, sumsq: torch.Ten
     return dv, dg
 
 
+def _req_rows(t: torch.Tensor, name: str) -> None:
+    """2-D bf16 CUDA tensor whose rows are contiguous (a column slice of a wider matrix is fine: pitch = stride(0))."""
+    if not t.is_cuda or t.dtype != BF16 or t.dim() != 2 or t.stride(1) != 1:
+        raise RuntimeError(f"{name}: expected a 2-D bf16 CUDA tensor with unit column stride")
+
+
 def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool = False, b_mn: bool = False,
          bias: Optional[torch.Tensor] = None, relu: bool = False, relu_aux: Optional[torch.Tensor] = None,
          out_bf16: bool = True, out_f32: bool = False, accum_f32: Optional[torch.Tensor] = None, k_splits: int = 1,
-         alpha: float = 1.0, tile_n: int = 0) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
-    """C[M,N] = epilogue(alpha * A . B^T) on the tcgen05 GEMM.  a / b are 2-D bf16 row-major buffers:
-    K-major operands are stored [M or N][K], MN-major ones [K][M or N].
-    accum_f32: a zeroed (M,N) fp32 buffer to atomically accumulate into (split-K)."""
-    _req(a, BF16, "gemm.a")
-    _req(b, BF16, "gemm.b")
-    ob = torch.empty((M, N), dtype=BF16, device=a.device) if (out_bf16 and accum_f32 is None) else None
+         alpha: float = 1.0, tile_n: int = 0,
+         out: Optional[torch.Tensor] = None) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """C[M,N] = epilogue(alpha * A . B^T) on the tcgen05 GEMM.  a / b are 2-D bf16 row-major buffers (row pitch =
+    stride(0), so column slices work): K-major operands are stored [M or N][K], MN-major ones [K][M or N].
+    accum_f32: a zeroed (M,N) fp32 buffer to atomically accumulate into (split-K).
+    out: optional preallocated bf16 (M,N) view with unit column stride (e.g. a column block of a wider matrix)."""
+    _req_rows(a, "gemm.a")
+    _req_rows(b, "gemm.b")
+    ldc = N
+    if out is not None:
+        _req_rows(out, "gemm.out")
+        ob, ldc = out, out.stride(0)
+    else:
+        ob = torch.empty((M, N), dtype=BF16, device=a.device) if (out_bf16 and accum_f32 is None) else None
     of = accum_f32 if accum_f32 is not None else (torch.empty((M, N), dtype=F32, device=a.device) if out_f32 else None)
     if relu_aux is not None:
         _req(relu_aux, BF16, "gemm.relu_aux")
     _call("cti_gemm_bf16", _lib.load().cti_gemm_bf16, (
-        a.data_ptr(), a.shape[1], int(a_mn), b.data_ptr(), b.shape[1], int(b_mn), M, N, K, float(alpha), _ptr(bias),
-        int(relu), _ptr(relu_aux), 0 if relu_aux is None else relu_aux.shape[1], _ptr(ob), _ptr(of), N,
+        a.data_ptr(), a.stride(0), int(a_mn), b.data_ptr(), b.stride(0), int(b_mn), M, N, K, float(alpha), _ptr(bias),
+        int(relu), _ptr(relu_aux), 0 if relu_aux is None else relu_aux.shape[1], _ptr(ob), _ptr(of), ldc,
         int(accum_f32 is not None), int(k_splits), int(tile_n), _stream()), flops=2.0 * M * N * K,
         tag=f"{'wgrad' if a_mn else ('dgrad' if b_mn else 'fwd')} M={M} N={N} K={K}")
     return ob, of

@@ -50,6 +50,15 @@ int cti_dropout_f32(float* x, int64_t n, float p, uint64_t seed, uint64_t offset
 /* out = dropout(x) on bf16 data (n % 4 == 0); out may alias x. */
 int cti_dropout_bf16(const void* x, void* out, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
 
+/* Per-rank input dropout of the R per-rank nets (src/tc.py:29-31,47-49): every rank r masks the shared input with
+ * its own mask keep_r; element index of (r, row, c) is (r * rows + row) * cols + c.
+ *   expand: xt[row, j*cols + c] = x[row, c] * keep_{r0+j}[row, c] / (1-p),  j < rank_group      (bf16, (rows, rank_group*cols))
+ *   reduce: acc[row, c] += sum_j dxt[row, j*cols + c] * keep_{r0+j}[row, c] / (1-p)              (fp32 accumulator) */
+int cti_dropout_expand(const void* x, void* xt, int64_t rows, int cols, int rank_group, int r0, float p, uint64_t seed,
+                       uint64_t offset, void* stream);
+int cti_dropout_reduce(const void* dxt, float* acc, int64_t rows, int cols, int rank_group, int r0, float p, uint64_t seed,
+                       uint64_t offset, void* stream);
+
 /* ---- weight-norm fold ----------------------------------------------------------------------
  * A matrix of n_groups stacked nn.Linear weights, each (rows_per_group, cols), each with its own
  * scalar g:  sumsq[i] = ||V_i||_F^2,  W_eff_i = bf16(V_i * g_i / ||V_i||_F).

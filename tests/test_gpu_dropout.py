@@ -132,3 +132,58 @@ def test_dropout_zero_in_train_mode_equals_eval():
         att.eval()
         p2, _ = att(v, q, a)
     assert torch.equal(p1, p2)
+
+
+def test_per_rank_nets_draw_independent_masks_and_match_autograd():
+    """The R per-rank FCNets each own a Dropout in the reference (src/tc.py:29-31).  The masks the kernels use are
+    recovered by pushing ones through the expand kernel; forward and backward are then compared with autograd of
+    the same masked computation in fp32."""
+    torch.manual_seed(0)
+    M, H, R, d, p = 300, 512, 32, 16, 0.5
+    site = (p, 99, 5)
+    y = torch.relu(torch.randn(M, H, device=DEV)).to(torch.bfloat16)
+    V = (torch.randn(R * d, H, device=DEV) / H ** 0.5).requires_grad_(True)
+    g = V.detach().view(R, -1).norm(dim=1).clone().requires_grad_(True)
+    bias = (torch.randn(R * d, device=DEV) * 0.1).requires_grad_(True)
+    pk = F_.pack_layer(V, g, R)
+    out = F_.rank_proj_fwd(y, pk, bias, site, R)
+    masks = torch.stack([K_.dropout_expand(torch.ones_like(y), 1, r, site) for r in range(R)], 0).float()   # (R,M,H): 0 or 2
+    assert set(masks.unique().tolist()) == {0.0, 1 / (1 - p)}
+    assert abs((masks != 0).float().mean().item() - (1 - p)) < 5e-3
+    same = ((masks[0] != 0) == (masks[1] != 0)).float().mean().item()
+    assert abs(same - 0.5) < 0.02                                          # ranks 0 and 1: independent masks
+    yl = y.float().requires_grad_(True)
+    w_eff = (V.view(R, -1) * (g / V.view(R, -1).norm(dim=1))[:, None]).view(R, d, H)
+    ref = torch.relu(torch.einsum("rmh,rdh->mrd", yl[None] * masks, w_eff.to(torch.bfloat16).float()) + bias.view(R, d))
+    ref = ref.reshape(M, R * d)
+    assert ((out.float() - ref).abs().max() / ref.abs().max()).item() < 1e-2
+    cot = torch.randn(M, R * d, device=DEV)
+    (ref * cot).sum().backward()
+    dz = (cot * (out.float() > 0)).to(torch.bfloat16)
+    dV, dg, dy = F_.rank_proj_bwd(y, dz, V.detach(), g.detach(), pk, site, R)
+    rel = lambda a, b: ((a.float() - b.float()).abs().max() / b.float().abs().max()).item()
+    assert rel(dy, yl.grad) < 3e-2
+    assert rel(dV, V.grad) < 3e-2
+    assert ((dg - g.grad).abs().max() / V.grad.view(R, -1).norm(dim=1).max()).item() < 3e-2
+
+
+def test_rank_dropout_modes_both_run():
+    B, K, Q, A, G = 4, 50, 12, 6, 2
+    torch.manual_seed(1204)
+    att = cti_b200.TriAttention(2048, 1024, 1024, 512, 1, 32, G, 1).to(DEV).train()
+    v, q, a = [t.to(DEV) for t in O.synthetic_inputs(B, K, Q, A, seed=3)]
+    outs = {}
+    for mode in ("independent", "shared"):
+        F_.RANK_DROPOUT = mode
+        try:
+            qd = q.clone().requires_grad_(True)
+            for prm in att.parameters():
+                prm.grad = None
+            p, _ = _seeded(lambda: att(v, qd, a))
+            (p * torch.arange(p.numel(), device=DEV).view_as(p).float()).sum().backward()
+            assert torch.isfinite(qd.grad).all()
+            assert all(prm.grad is not None and torch.isfinite(prm.grad).all() for prm in att.parameters())
+            outs[mode] = p.detach().clone()
+        finally:
+            F_.RANK_DROPOUT = "independent"
+    assert not torch.equal(outs["independent"], outs["shared"])
