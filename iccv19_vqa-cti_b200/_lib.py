@@ -24,6 +24,7 @@ SIGNATURES = {
     "cti_dropout_bf16": (c_int, [_P, _P, c_int64, c_float, ctypes.c_uint64, ctypes.c_uint64, _P]),
     "cti_dropout_expand": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, c_float, ctypes.c_uint64, ctypes.c_uint64, _P]),
     "cti_dropout_reduce": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, c_float, ctypes.c_uint64, ctypes.c_uint64, _P]),
+    "cti_sum_row_groups": (c_int, [_P, _P, c_int64, c_int, c_int64, _P]),
     "cti_wn_pack": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "cti_wn_grad": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "cti_gemm_bf16": (c_int, [_P, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_float, _P, c_int, _P, c_int,
@@ -31,13 +32,13 @@ SIGNATURES = {
     "cti_act_bwd_bias": (c_int, [_P, c_int, _P, _P, _P, c_int64, c_int, _P]),
     "cti_masked_softmax_fwd": (c_int, [_P, _P, c_int64, c_int, _P]),
     "cti_masked_softmax_bwd": (c_int, [_P, _P, c_int64, c_int64, c_int64, _P, c_int64, c_int, c_int, _P]),
-    "cti_trilinear_logits_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "cti_trilinear_logits_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "cti_trilinear_logits_bwd_workspace": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "cti_trilinear_logits_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, c_int, c_int,
-                                         c_int, c_int, c_int, c_int, _P]),
-    "cti_tri_pool_fwd": (c_int, [_P, _P, _P, _P, c_int64, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+                                         c_int, c_int, c_int, c_int, c_int, _P]),
+    "cti_tri_pool_fwd": (c_int, [_P, _P, _P, _P, c_int64, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "cti_tri_pool_bwd": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int,
-                                 c_int, _P]),
+                                 c_int, c_int, _P]),
     "cti_bilinear_logits_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "cti_bilinear_logits_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
 }

@@ -52,6 +52,8 @@ class BCNet(nn.Module):
             raise NotImplementedError("BCNet.forward: only the h_out <= 32 branch (reference src/bc.py:52-58) is "
                                       "on the accelerated CTI/BAN path")
         B, K = v.shape[0], v.shape[1]
+        if q.shape[0] != B:
+            raise RuntimeError(f"batch mismatch: v has {B} samples, q {q.shape[0]}")
         Q = q.shape[1]
         G, C = self.h_out, self.h_dim * self.k
         v_bf16, rowmask = cast_features(v)
@@ -73,6 +75,8 @@ class BCNet(nn.Module):
     def forward_with_weights(self, v, q, w):
         """Attention-weighted bilinear pooling: w (B,K,Q) -> (B, h_dim) (sum-pooled over k channel groups)."""
         B, K = v.shape[0], v.shape[1]
+        if q.shape[0] != B:
+            raise RuntimeError(f"batch mismatch: v has {B} samples, q {q.shape[0]}")
         Q = q.shape[1]
         C = self.h_dim * self.k
         v_bf16, _ = cast_features(v)

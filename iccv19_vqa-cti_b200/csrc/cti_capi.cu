@@ -34,7 +34,7 @@ int check_launch(const char* what) {
 
 extern "C" {
 
-int cti_version(void) { return 100; }   // 0.1.0
+int cti_version(void) { return 101; }   // 0.1.1: v_rep (rows sharing one v sample), cti_sum_row_groups
 
 const char* cti_last_error(void) { return cti::g_err; }
 
@@ -113,6 +113,11 @@ int cti_act_bwd_bias(const void* dy, int dy_is_bf16, const void* y_bf16, void* d
                            static_cast<cudaStream_t>(stream));
 }
 
+int cti_sum_row_groups(const void* x_bf16, void* out_bf16, int64_t groups, int rep, int64_t row_elems, void* stream) {
+  return cti::sum_row_groups(static_cast<const __nv_bfloat16*>(x_bf16), static_cast<__nv_bfloat16*>(out_bf16), groups, rep,
+                             row_elems, static_cast<cudaStream_t>(stream));
+}
+
 int cti_masked_softmax_fwd(const float* logits, float* p, int64_t rows, int len, void* stream) {
   return cti::masked_softmax_fwd(logits, p, rows, len, static_cast<cudaStream_t>(stream));
 }
@@ -124,8 +129,8 @@ int cti_masked_softmax_bwd(const float* p, const float* dp, int64_t dp_stride_b,
 }
 
 int cti_trilinear_logits_fwd(const void* vc, const void* qc, const void* ac, const void* tpack, const uint8_t* rowmask,
-                             float* logits, int B, int K, int Q, int A, int G, int R, void* stream) {
-  cti::TriDims d{B, K, Q, A, G, R};
+                             float* logits, int B, int K, int Q, int A, int G, int R, int v_rep, void* stream) {
+  cti::TriDims d{B, K, Q, A, G, R, v_rep};
   return cti::trilinear_fwd(static_cast<const __nv_bfloat16*>(vc), static_cast<const __nv_bfloat16*>(qc),
                             static_cast<const __nv_bfloat16*>(ac), static_cast<const __nv_bfloat16*>(tpack), rowmask,
                             logits, d, static_cast<cudaStream_t>(stream));
@@ -139,8 +144,8 @@ size_t cti_trilinear_logits_bwd_workspace(int B, int K, int Q, int A, int G, int
 int cti_trilinear_logits_bwd(const void* vc, const void* qc, const void* ac, const void* tpack, const float* dlogits,
                              void* dzv, void* dzq, void* dza, float* dbv_accum, float* dbq_accum, float* dba_accum,
                              float* dtpack_accum, void* workspace, size_t workspace_bytes, int B, int K, int Q, int A,
-                             int G, int R, void* stream) {
-  cti::TriDims d{B, K, Q, A, G, R};
+                             int G, int R, int v_rep, void* stream) {
+  cti::TriDims d{B, K, Q, A, G, R, v_rep};
   return cti::trilinear_bwd(static_cast<const __nv_bfloat16*>(vc), static_cast<const __nv_bfloat16*>(qc),
                             static_cast<const __nv_bfloat16*>(ac), static_cast<const __nv_bfloat16*>(tpack), dlogits,
                             static_cast<__nv_bfloat16*>(dzv), static_cast<__nv_bfloat16*>(dzq),
@@ -149,8 +154,8 @@ int cti_trilinear_logits_bwd(const void* vc, const void* qc, const void* ac, con
 }
 
 int cti_tri_pool_fwd(const void* v, const void* q, const void* a, const float* w, int64_t w_stride_b, float* out,
-                     int B, int K, int Q, int A, int C, void* stream) {
-  cti::PoolDims d{B, K, Q, A, C};
+                     int B, int K, int Q, int A, int C, int v_rep, void* stream) {
+  cti::PoolDims d{B, K, Q, A, C, v_rep};
   return cti::tri_pool_fwd(static_cast<const __nv_bfloat16*>(v), static_cast<const __nv_bfloat16*>(q),
                            static_cast<const __nv_bfloat16*>(a), w, w_stride_b, out, d,
                            static_cast<cudaStream_t>(stream));
@@ -158,8 +163,8 @@ int cti_tri_pool_fwd(const void* v, const void* q, const void* a, const float* w
 
 int cti_tri_pool_bwd(const void* v, const void* q, const void* a, const float* w, int64_t w_stride_b,
                      const float* dout, void* dzv, void* dzq, void* dza, float* dbv_accum, float* dbq_accum,
-                     float* dba_accum, float* dw, int B, int K, int Q, int A, int C, void* stream) {
-  cti::PoolDims d{B, K, Q, A, C};
+                     float* dba_accum, float* dw, int B, int K, int Q, int A, int C, int v_rep, void* stream) {
+  cti::PoolDims d{B, K, Q, A, C, v_rep};
   return cti::tri_pool_bwd(static_cast<const __nv_bfloat16*>(v), static_cast<const __nv_bfloat16*>(q),
                            static_cast<const __nv_bfloat16*>(a), w, w_stride_b, dout,
                            static_cast<__nv_bfloat16*>(dzv), static_cast<__nv_bfloat16*>(dzq),

@@ -40,6 +40,7 @@ int dropout_expand(const __nv_bfloat16* x, __nv_bfloat16* xt, long rows, int col
                    uint64_t offset, cudaStream_t s);
 int dropout_reduce(const __nv_bfloat16* dxt, float* acc, long rows, int cols, int RG, int r0, float p, uint64_t seed,
                    uint64_t offset, cudaStream_t s);
+int sum_row_groups(const __nv_bfloat16* x, __nv_bfloat16* out, long groups, int rep, long row_elems, cudaStream_t s);
 int wn_pack(const float* v, const float* g, __nv_bfloat16* w, float* sumsq, int n_groups, int rows_per_group, int cols,
             cudaStream_t s);
 int wn_grad(const float* dw, const float* v, const float* g, const float* sumsq, float* dv, float* dg, float* dot_ws,
@@ -55,6 +56,7 @@ int masked_softmax_bwd(const float* p, const float* dp, long dp_row_stride_b, lo
 // trilinear.cu
 struct TriDims {
   int B, K, Q, A, G, R;   // d is fixed at 16
+  int VR = 1;             // v_rep: rows b of q / a / logits use row b / VR of vc and rowmask (vc has B / VR samples)
 };
 int trilinear_fwd(const __nv_bfloat16* vc, const __nv_bfloat16* qc, const __nv_bfloat16* ac, const __nv_bfloat16* tpack,
                   const uint8_t* rowmask, float* logits, TriDims d, cudaStream_t s);
@@ -67,6 +69,7 @@ int trilinear_bwd(const __nv_bfloat16* vc, const __nv_bfloat16* qc, const __nv_b
 // pool.cu  (A == 0 selects the bilinear pooling of BCNet.forward_with_weights)
 struct PoolDims {
   int B, K, Q, A, C;
+  int VR = 1;             // v_rep: row b uses sample b / VR of v (v has B / VR samples); dzv stays per row b
 };
 int tri_pool_fwd(const __nv_bfloat16* v, const __nv_bfloat16* q, const __nv_bfloat16* a, const float* w, long w_stride_b,
                  float* out, PoolDims d, cudaStream_t s);

@@ -185,8 +185,9 @@ __global__ void __launch_bounds__(256) dropout_reduce_kernel(const __nv_bfloat16
 constexpr int kSeg = 4096;   // elements reduced by one block
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ v, const float* __restrict__ w2,
-                                                    float* __restrict__ acc, long group_elems, int segs_per_group) {
-  // acc[group] += sum v*w2 (w2 == v for the squared norm, == dW for the <dW,V> dot)
+                                                    float* __restrict__ partial, long group_elems, int segs_per_group) {
+  // partial[group * segs + seg] = sum over the segment of v*w2 (w2 == v for the squared norm, == dW for <dW,V>).
+  // No atomics: the same weights always give the same norm, hence the same bf16 pack (runs are reproducible).
   const int group = blockIdx.x / segs_per_group;
   const int seg = blockIdx.x - group * segs_per_group;
   const long base = static_cast<long>(group) * group_elems;
@@ -201,8 +202,18 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ v,
   if (threadIdx.x < 32) {
     float t = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
     t = warp_sum(t);
-    if (threadIdx.x == 0) atomicAdd(acc + group, t);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
   }
+}
+
+// acc[group] = sum of the group's segment partials, in a fixed order (one warp per group).
+__global__ void __launch_bounds__(32) sum_partials_kernel(const float* __restrict__ partial, float* __restrict__ acc,
+                                                          int segs_per_group) {
+  const float* p = partial + static_cast<long>(blockIdx.x) * segs_per_group;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < segs_per_group; i += 32) s += p[i];
+  s = warp_sum(s);
+  if (threadIdx.x == 0) acc[blockIdx.x] = s;
 }
 
 __global__ void __launch_bounds__(256) wn_scale_kernel(const float* __restrict__ v, const float* __restrict__ g,
@@ -280,6 +291,32 @@ __global__ void __launch_bounds__(256) act_bwd_bias_kernel(const void* __restric
   }
 }
 
+// out[g, e] = sum_{j < rep} x[g * rep + j, e]  (bf16 in / out, fp32 sum): folds the per-row gradients of rows that share
+// one v sample (v_rep of the contraction / pooling kernels) back onto that sample.  8 elements (16 bytes) per thread.
+__global__ void __launch_bounds__(256)
+sum_row_groups_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, long groups, int rep, long row_vec) {
+  const long i = blockIdx.x * 256l + threadIdx.x;
+  if (i >= groups * row_vec) return;
+  const long g = i / row_vec, e = i - g * row_vec;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int j = 0; j < rep; ++j) {
+    const uint4 u = __ldg(x + (g * rep + j) * row_vec + e);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 f = unpack_bf16x2(w[t]);
+      acc[2 * t] += f.x;
+      acc[2 * t + 1] += f.y;
+    }
+  }
+  uint4 o;
+  o.x = pack_bf16x2(acc[0], acc[1]);
+  o.y = pack_bf16x2(acc[2], acc[3]);
+  o.z = pack_bf16x2(acc[4], acc[5]);
+  o.w = pack_bf16x2(acc[6], acc[7]);
+  out[i] = o;
+}
+
 }  // namespace
 
 int cast_rows_mask(const float* x, __nv_bfloat16* out, uint8_t* rowmask, long rows, int cols, cudaStream_t s) {
@@ -304,6 +341,18 @@ int cast_rows_dropout(const float* x, __nv_bfloat16* out, uint8_t* rowmask, long
   CTI_REQUIRE(blocks < (1l << 31), "cast_rows_dropout: too many rows");
   cast_rows_dropout_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, out, rowmask, rows, cols, make_rng(p, seed, offset));
   return check_launch("cast_rows_dropout_kernel");
+}
+
+int sum_row_groups(const __nv_bfloat16* x, __nv_bfloat16* out, long groups, int rep, long row_elems, cudaStream_t s) {
+  CTI_REQUIRE(groups >= 0 && rep >= 1 && row_elems > 0 && (row_elems & 7) == 0, "sum_row_groups: bad arguments (row_elems=%ld)",
+              row_elems);
+  if (groups == 0) return 0;
+  CTI_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0, "sum_row_groups: buffers must be 16-byte aligned");
+  const long n = groups * (row_elems / 8);
+  CTI_REQUIRE((n + 255) / 256 < (1l << 31), "sum_row_groups: too many elements");
+  sum_row_groups_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(x),
+                                                                   reinterpret_cast<uint4*>(out), groups, rep, row_elems / 8);
+  return check_launch("sum_row_groups_kernel");
 }
 
 int dropout_f32(float* x, long n, float p, uint64_t seed, uint64_t offset, cudaStream_t s) {
@@ -345,11 +394,13 @@ int wn_pack(const float* v, const float* g, __nv_bfloat16* w, float* sumsq, int 
   const long total = ge * n_groups;
   CTI_REQUIRE(n_groups > 0 && ge > 0, "wn_pack: empty weight");
   CTI_REQUIRE(ge % 4 == 0, "wn_pack: group size %ld must be a multiple of 4", ge);
-  cudaError_t e = cudaMemsetAsync(sumsq, 0, sizeof(float) * n_groups, s);
-  if (e != cudaSuccess) { set_error("wn_pack memset: %s", cudaGetErrorString(e)); return (int)e; }
   const int segs = (int)((ge + kSeg - 1) / kSeg);
-  sumsq_kernel<<<n_groups * segs, 256, 0, s>>>(v, v, sumsq, ge, segs);
+  float* partial = reinterpret_cast<float*>(w);      // the output buffer doubles as scratch until wn_scale overwrites it
+  sumsq_kernel<<<n_groups * segs, 256, 0, s>>>(v, v, partial, ge, segs);
   int rc = check_launch("sumsq_kernel");
+  if (rc) return rc;
+  sum_partials_kernel<<<n_groups, 32, 0, s>>>(partial, sumsq, segs);
+  rc = check_launch("sum_partials_kernel");
   if (rc) return rc;
   wn_scale_kernel<<<(unsigned)((total / 4 + 255) / 256), 256, 0, s>>>(v, g, sumsq, w, ge, total);
   return check_launch("wn_scale_kernel");
@@ -360,11 +411,13 @@ int wn_grad(const float* dw, const float* v, const float* g, const float* sumsq,
   const long ge = static_cast<long>(rows_per_group) * cols;
   const long total = ge * n_groups;
   CTI_REQUIRE(n_groups > 0 && ge > 0 && ge % 4 == 0, "wn_grad: bad group size %ld", ge);
-  cudaError_t e = cudaMemsetAsync(dot_ws, 0, sizeof(float) * n_groups, s);
-  if (e != cudaSuccess) { set_error("wn_grad memset: %s", cudaGetErrorString(e)); return (int)e; }
   const int segs = (int)((ge + kSeg - 1) / kSeg);
-  sumsq_kernel<<<n_groups * segs, 256, 0, s>>>(dw, v, dot_ws, ge, segs);
+  float* partial = dv;                               // scratch until wn_grad_kernel overwrites it
+  sumsq_kernel<<<n_groups * segs, 256, 0, s>>>(dw, v, partial, ge, segs);
   int rc = check_launch("wn_dot_kernel");
+  if (rc) return rc;
+  sum_partials_kernel<<<n_groups, 32, 0, s>>>(partial, dot_ws, segs);
+  rc = check_launch("sum_partials_kernel");
   if (rc) return rc;
   wn_grad_kernel<<<(unsigned)((total / 4 + 255) / 256), 256, 0, s>>>(dw, v, g, sumsq, dot_ws, dv, dg, ge, total);
   return check_launch("wn_grad_kernel");

@@ -60,6 +60,7 @@ struct PoolParams {
   bf16 *dzv, *dzq, *dza;
   float *dbv, *dbq, *dba, *dw;
   int B, K, Q, A, An, C, NC, nchunks;
+  int VR;                // rows b share the v tile of row b / VR (dzv stays per row b)
 };
 
 struct Smem {
@@ -146,8 +147,8 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ 
         mbar_wait(bar(B_VEMPTY + st), ((g / V_STAGES) & 1) ^ 1);
         const uint32_t dst = sV + st * V_STAGE_BYTES;
         mbar_arrive_expect_tx(bar(B_VFULL + st), V_TILE_BYTES + 16 * CCH * 2 + (p.A > 0 ? 8 * CCH * 2 : 0) + (BWD ? CCH * 4 : 0));
-        tma_load_3d(&tmap_v, bar(B_VFULL + st), dst, ch * CCH, 0, b);
-        tma_load_3d(&tmap_v, bar(B_VFULL + st), dst + KP * 128, ch * CCH + 64, 0, b);
+        tma_load_3d(&tmap_v, bar(B_VFULL + st), dst, ch * CCH, 0, b / p.VR);
+        tma_load_3d(&tmap_v, bar(B_VFULL + st), dst + KP * 128, ch * CCH + 64, 0, b / p.VR);
         tma_load_3d(&tmap_q, bar(B_VFULL + st), dst + ST_Q, ch * CCH, 0, b);
         if (p.A > 0) tma_load_3d(&tmap_a, bar(B_VFULL + st), dst + ST_A, ch * CCH, 0, b);
         if (BWD) bulk_load_1d(dst + ST_DO, p.dout + (size_t)b * p.C + ch * CCH, CCH * 4, bar(B_VFULL + st));
@@ -432,6 +433,7 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ 
 
 int check_pool(const PoolDims& d, const char* who) {
   CTI_REQUIRE(d.B >= 0 && d.K > 0 && d.Q > 0 && d.A >= 0 && d.C > 0, "%s: bad dims", who);
+  CTI_REQUIRE(d.VR >= 1 && d.B % d.VR == 0, "%s: B=%d rows do not divide into groups of v_rep=%d", who, d.B, d.VR);
   CTI_REQUIRE(d.C % CCH == 0 && d.C <= MAX_C, "%s: channel count %d must be a multiple of %d and <= %d", who, d.C, CCH,
               MAX_C);
   CTI_REQUIRE(d.K <= KP, "%s: at most %d regions per sample (K=%d)", who, KP, d.K);
@@ -442,7 +444,7 @@ int check_pool(const PoolDims& d, const char* who) {
 template <bool BWD>
 int launch_pool(const bf16* v, PoolParams p, cudaStream_t stream, const char* who) {
   CUtensorMap tv, tq, ta;
-  if (int rc = make_tmap_3d(&tv, v, p.C, p.K, p.B, p.C, (uint64_t)p.K * p.C, 64, KP)) return rc;
+  if (int rc = make_tmap_3d(&tv, v, p.C, p.K, p.B / p.VR, p.C, (uint64_t)p.K * p.C, 64, KP)) return rc;
   if (int rc = make_tmap_3d(&tq, p.q, p.C, p.Q, p.B, p.C, (uint64_t)p.Q * p.C, CCH, 16, false)) return rc;
   if (p.A > 0) {
     if (int rc = make_tmap_3d(&ta, p.a, p.C, p.A, p.B, p.C, (uint64_t)p.A * p.C, CCH, 8, false)) return rc;
@@ -471,6 +473,7 @@ PoolParams make_params(const bf16* q, const bf16* a, const float* w, long w_stri
   p.B = d.B; p.K = d.K; p.Q = d.Q; p.A = d.A; p.An = d.A > 0 ? d.A : 1; p.C = d.C;
   p.NC = 16 * p.An;
   p.nchunks = d.C / CCH;
+  p.VR = d.VR;
   return p;
 }
 

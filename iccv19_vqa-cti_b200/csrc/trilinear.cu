@@ -125,7 +125,7 @@ trilinear_fwd_kernel(const bf16* __restrict__ vc, const bf16* __restrict__ qc, c
     for (int c = threadIdx.x; c < s.MT * 16 * row_chunks; c += kThreads) {
       const int row = c / row_chunks, col = (c - row * row_chunks) * 8;
       uint4 val = make_uint4(0, 0, 0, 0);
-      if (row < s.K) val = __ldg(reinterpret_cast<const uint4*>(vc + ((size_t)b * s.K + row) * s.RD + col));
+      if (row < s.K) val = __ldg(reinterpret_cast<const uint4*>(vc + ((size_t)(b / dims.VR) * s.K + row) * s.RD + col));
       *reinterpret_cast<uint4*>(sV + (size_t)row * s.LDH + col) = val;
     }
     for (int c = threadIdx.x; c < s.Q * row_chunks; c += kThreads) {
@@ -229,7 +229,7 @@ trilinear_fwd_kernel(const bf16* __restrict__ vc, const bf16* __restrict__ qc, c
       const int qa = rem - k * QA;
       const int q = qa / s.A, a = qa - q * s.A;
       float val = sOut[(size_t)k * out_ld + (a * s.G + g) * 16 + q];
-      if (rowmask != nullptr && rowmask[(size_t)b * s.K + k]) val = -INFINITY;
+      if (rowmask != nullptr && rowmask[(size_t)(b / dims.VR) * s.K + k]) val = -INFINITY;
       dst[e] = val;
     }
   }
@@ -322,7 +322,7 @@ trilinear_bwd_kernel(const bf16* __restrict__ vc, const bf16* __restrict__ qc, c
     bf16* v = sVr + (size_t)buf * KP * kLdS;
     for (int c = threadIdx.x; c < s.K * 2; c += kThreads) {
       const int row = c >> 1, col = (c & 1) * 8;
-      cp_async16(smem_u32(v + (size_t)row * kLdS + col), vc + ((size_t)b * s.K + row) * s.RD + r * 16 + col);
+      cp_async16(smem_u32(v + (size_t)row * kLdS + col), vc + ((size_t)(b / dims.VR) * s.K + row) * s.RD + r * 16 + col);
     }
     bf16* q = sQr + (size_t)buf * 16 * kLdS;
     for (int c = threadIdx.x; c < s.Q * 2; c += kThreads) {
@@ -582,6 +582,7 @@ trilinear_bwd_kernel(const bf16* __restrict__ vc, const bf16* __restrict__ qc, c
 
 int check_dims(const TriDims& d, const char* who) {
   CTI_REQUIRE(d.B >= 0 && d.K > 0 && d.Q > 0 && d.A > 0 && d.G > 0 && d.R > 0, "%s: bad dims", who);
+  CTI_REQUIRE(d.VR >= 1 && d.B % d.VR == 0, "%s: B=%d rows do not divide into groups of v_rep=%d", who, d.B, d.VR);
   CTI_REQUIRE(d.Q <= 16, "%s: at most 16 question tokens are supported (Q=%d)", who, d.Q);
   CTI_REQUIRE(d.A <= 16, "%s: at most 16 answer tokens are supported (A=%d)", who, d.A);
   CTI_REQUIRE(d.G <= 4, "%s: at most 4 glimpses are supported (G=%d)", who, d.G);

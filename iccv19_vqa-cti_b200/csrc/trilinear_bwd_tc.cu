@@ -80,6 +80,7 @@ struct Bwd1Params {
   bf16 *dzv, *dzq, *dn1;
   float *dbv, *dbq;
   int B, K, Q, A, R, N;
+  int VR;        // rows b share the v operand of row b / VR (dzv stays per row b)
 };
 
 constexpr size_t kSmem1 = (size_t)T_RING * T_BYTES + OP_RING * OP_BYTES + 2 * N1_BYTES + 2 * M_BYTES + 2 * DL_BYTES +
@@ -181,7 +182,7 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
           mbar_wait(bar(A_OPEMPTY + oslot), oph ^ 1u);
           mbar_arrive_expect_tx(bar(A_OPFULL + oslot), OP_BYTES);
           const uint32_t dst = sOp + oslot * OP_BYTES;
-          tma_load_3d(&tmap_v, bar(A_OPFULL + oslot), dst + OP_V, r * 16, 0, b);
+          tma_load_3d(&tmap_v, bar(A_OPFULL + oslot), dst + OP_V, r * 16, 0, b / p.VR);
           tma_load_3d(&tmap_q, bar(A_OPFULL + oslot), dst + OP_Q, r * 16, 0, b);
           tma_load_3d(&tmap_a, bar(A_OPFULL + oslot), dst + OP_A, r * 16, 0, b);
           if (++oslot == OP_RING) { oslot = 0; oph ^= 1u; }
@@ -750,7 +751,7 @@ int trilinear_bwd_tc(const bf16* vc, const bf16* qc, const bf16* ac, const bf16*
   const int RD = d.R * 16, N = 32 * d.A;
   CUtensorMap tt, tv, tq, ta, tdl, tdn, ta8;
   if (int rc = make_tmap_3d(&tt, tpack, 512, (uint64_t)d.R * 16, 1, 512, (uint64_t)d.R * 16 * 512, 64, 16)) return rc;
-  if (int rc = make_tmap_3d(&tv, vc, RD, d.K, d.B, RD, (uint64_t)d.K * RD, 64, 64)) return rc;
+  if (int rc = make_tmap_3d(&tv, vc, RD, d.K, d.B / d.VR, RD, (uint64_t)d.K * RD, 64, 64)) return rc;
   if (int rc = make_tmap_3d(&tq, qc, RD, d.Q, d.B, RD, (uint64_t)d.Q * RD, 64, 16)) return rc;
   if (int rc = make_tmap_3d(&ta, ac, RD, d.A, d.B, RD, (uint64_t)d.A * RD, 64, 16)) return rc;
   if (int rc = make_tmap_3d(&tdl, dlm, N, d.K, d.B, N, (uint64_t)d.K * N, 64, 64)) return rc;
@@ -768,7 +769,7 @@ int trilinear_bwd_tc(const bf16* vc, const bf16* qc, const bf16* ac, const bf16*
     }
     attr_set = true;
   }
-  Bwd1Params p1{dzv, dzq, dn1, dbv, dbq, d.B, d.K, d.Q, d.A, d.R, N};
+  Bwd1Params p1{dzv, dzq, dn1, dbv, dbq, d.B, d.K, d.Q, d.A, d.R, N, d.VR};
   const int grid1 = d.B < kNumSMsB200 ? d.B : kNumSMsB200;
   trilinear_bwd1_tc_kernel<<<grid1, kThreads1, kSmem1, stream>>>(tt, tv, tq, ta, tdl, p1);
   if (int rc = check_launch("trilinear_bwd1_tc_kernel")) return rc;

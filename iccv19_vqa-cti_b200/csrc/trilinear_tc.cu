@@ -56,6 +56,7 @@ struct TriTcParams {
   const uint8_t* rowmask;
   float* logits;
   int B, K, Q, A, R, N;      // N = 32 * A columns (a, g, q16)
+  int VR;                    // rows b share the v operand (and mask) of row b / VR
 };
 
 __host__ __device__ inline size_t tri_tc_smem(int K, int Q, int A) {
@@ -139,7 +140,7 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
           mbar_wait(bar(B_OPEMPTY + oslot), oph ^ 1u);
           mbar_arrive_expect_tx(bar(B_OPFULL + oslot), OP_BYTES);
           const uint32_t dst = sOp + oslot * OP_BYTES;
-          tma_load_3d(&tmap_v, bar(B_OPFULL + oslot), dst + OP_V, r * 16, 0, b);
+          tma_load_3d(&tmap_v, bar(B_OPFULL + oslot), dst + OP_V, r * 16, 0, b / p.VR);
           tma_load_3d(&tmap_q, bar(B_OPFULL + oslot), dst + OP_Q, r * 16, 0, b);
           tma_load_3d(&tmap_a, bar(B_OPFULL + oslot), dst + OP_A, r * 16, 0, b);
           if (++oslot == OP_RING) { oslot = 0; oph ^= 1u; }
@@ -312,7 +313,7 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
         mbar_wait(bar(B_ACCFULL), sl & 1);
         tcgen05_fence_after();
         const int k = L;
-        const bool masked = (k < p.K) && p.rowmask != nullptr && p.rowmask[(size_t)b * p.K + k] != 0;
+        const bool masked = (k < p.K) && p.rowmask != nullptr && p.rowmask[(size_t)(b / p.VR) * p.K + k] != 0;
         for (int ag = 0; ag < 2 * p.A; ++ag) {
           uint32_t v[16];
           tmem_ld_32x32b_x16(tmem_base + lane_addr + TM_ACC + ag * 16, v);
@@ -355,10 +356,10 @@ int trilinear_fwd_tc(const bf16* vc, const bf16* qc, const bf16* ac, const bf16*
   const int RD = d.R * 16;
   CUtensorMap tt, tv, tq, ta;
   if (int rc = make_tmap_3d(&tt, tpack, 512, (uint64_t)d.R * 16, 1, 512, (uint64_t)d.R * 16 * 512, 64, 16)) return rc;
-  if (int rc = make_tmap_3d(&tv, vc, RD, d.K, d.B, RD, (uint64_t)d.K * RD, 64, 64)) return rc;
+  if (int rc = make_tmap_3d(&tv, vc, RD, d.K, d.B / d.VR, RD, (uint64_t)d.K * RD, 64, 64)) return rc;
   if (int rc = make_tmap_3d(&tq, qc, RD, d.Q, d.B, RD, (uint64_t)d.Q * RD, 64, 16)) return rc;
   if (int rc = make_tmap_3d(&ta, ac, RD, d.A, d.B, RD, (uint64_t)d.A * RD, 64, 16)) return rc;
-  TriTcParams p{rowmask, logits, d.B, d.K, d.Q, d.A, d.R, 32 * d.A};
+  TriTcParams p{rowmask, logits, d.B, d.K, d.Q, d.A, d.R, 32 * d.A, d.VR};
   static size_t smem_set = 0;          // raise the dynamic shared memory limit once per size (not a stream operation)
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(trilinear_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -241,6 +241,8 @@ class TriLogitsFn(Function):
         """drops: None (eval) or (v_f32_2d, dv, dq, da, dvn, dqn, dan) -- input dropout of the three tucker nets and of
         the per-rank nets (one mask per modality shared by its R per-rank nets)."""
         B, K, Q, A, G, R = dims
+        vr = (B * K) // v_bf16.shape[0]               # rows sharing one image (v has B / vr samples; see tc.py)
+        ctx.vr = vr
         dv = dq = da = dvn = dqn = dan = None
         if drops is not None:
             v_f32, dv, dq, da, dvn, dqn, dan = drops
@@ -271,7 +273,7 @@ class TriLogitsFn(Function):
         yq, qc = rank_nets(yq, pk[4], w[14], dqn)
         ya, ac = rank_nets(ya, pk[5], w[17], dan)
         tpack = pack_core(T_g)
-        logits = K_.trilinear_fwd(vc, qc, ac, tpack, rowmask, B, K, Q, A, G, R)
+        logits = K_.trilinear_fwd(vc, qc, ac, tpack, rowmask, B, K, Q, A, G, R, vr)
         ctx.save_for_backward(v_bf16, xq, xa, yv, yq, ya, vc, qc, ac, tpack, T_g, *w)
         ctx.pk = pk
         ctx.dims = dims
@@ -285,7 +287,7 @@ class TriLogitsFn(Function):
         w = ctx.saved_tensors[11:]
         pk = ctx.pk
         dl = dlogits.permute(0, 4, 1, 2, 3).contiguous()
-        dzv, dzq, dza, dbvn, dbqn, dban, dtpack = K_.trilinear_bwd(vc, qc, ac, tpack, dl, B, K, Q, A, G, R)
+        dzv, dzq, dza, dbvn, dbqn, dban, dtpack = K_.trilinear_bwd(vc, qc, ac, tpack, dl, B, K, Q, A, G, R, ctx.vr)
         # per-rank nets: input = tucker output (post-ReLU), so dx is masked by it -> dz of the tucker layer
         dq_drop, da_drop, dvn, dqn, dan = ctx.drops
         sc = lambda d: 1.0 if d is None else 1.0 / (1.0 - d[0])
@@ -389,6 +391,8 @@ class PoolFn(Function):
     def forward(ctx, dims, packs, drops, v_bf16, q, a, wts, *w):
         """drops: None (eval) or (v_f32_2d, dv, dq, da): input dropout of the three projections."""
         B, K, Q, A, C = dims
+        vr = (B * K) // v_bf16.shape[0]               # rows sharing one image
+        ctx.vr = vr
         n = 3 if A > 0 else 2
         pk = [packs[i] if packs is not None else pack_layer(w[3 * i], w[3 * i + 1], 1) for i in range(n)]
         dq_drop = da_drop = None
@@ -407,7 +411,7 @@ class PoolFn(Function):
         wd = _sample_contiguous(wts.detach())
         if wd.dtype != F32:
             wd = wd.float()
-        out = K_.tri_pool_fwd(vp, qp, ap, wd, wd.stride(0), B, K, Q, A, C)
+        out = K_.tri_pool_fwd(vp, qp, ap, wd, wd.stride(0), B, K, Q, A, C, vr)
         ctx.save_for_backward(v_bf16, xq, xa, vp, qp, ap, wd, *w)
         ctx.pk = pk
         ctx.dims = dims
@@ -421,7 +425,7 @@ class PoolFn(Function):
         w = ctx.saved_tensors[7:]
         pk = ctx.pk
         dzv, dzq, dza, dbv, dbq, dba, dw = K_.tri_pool_bwd(vp, qp, ap, wd, wd.stride(0), dout.contiguous(), B, K, Q, A,
-                                                          C)
+                                                          C, ctx.vr)
         dVv, dgv, _ = lin_bwd(v_bf16, dzv, w[0], w[1], pk[0], 1, False)
         dVq, dgq, dq = lin_bwd(xq, dzq, w[3], w[4], pk[1], 1, ctx.need[0], dx_f32=True)
         grads = [dVv, dgv, dbv, dVq, dgq, dbq]

@@ -145,7 +145,7 @@ def wn_pack(v: torch.Tensor, g: torch.Tensor, n_groups: int) -> Tuple[torch.Tens
     w = torch.empty((rows, cols), dtype=BF16, device=v.device)
     sumsq = torch.empty((n_groups,), dtype=F32, device=v.device)
     _call("cti_wn_pack", _lib.load().cti_wn_pack, (v.data_ptr(), g.data_ptr(), w.data_ptr(), sumsq.data_ptr(), n_groups,
-                                                   rows // n_groups, cols, _stream()), kernels=2,
+                                                   rows // n_groups, cols, _stream()), kernels=3,
           nbytes=10.0 * rows * cols)
     return w, sumsq
 
@@ -160,7 +160,7 @@ def wn_grad(dw: torch.Tensor, v: torch.Tensor, g: torch.Tensor, sumsq: torch.Ten
     ws = torch.empty((n_groups,), dtype=F32, device=v.device)
     _call("cti_wn_grad", _lib.load().cti_wn_grad,
           (dw.data_ptr(), v.data_ptr(), g.data_ptr(), sumsq.data_ptr(), dv.data_ptr(), dg.data_ptr(), ws.data_ptr(),
-           n_groups, rows // n_groups, cols, _stream()), kernels=2, nbytes=20.0 * rows * cols)
+           n_groups, rows // n_groups, cols, _stream()), kernels=3, nbytes=20.0 * rows * cols)
     return dv, dg
 
 
@@ -231,22 +231,34 @@ def softmax_bwd(p: torch.Tensor, dp: torch.Tensor, sb: int, sg: int, se: int, ba
     return dl
 
 
-def trilinear_fwd(vc, qc, ac, tpack, rowmask, B, K, Q, A, G, R) -> torch.Tensor:
+def sum_row_groups(x: torch.Tensor, rep: int, row_elems: int) -> torch.Tensor:
+    """x (groups*rep rows of row_elems) bf16 -> (groups rows) bf16: sum of each run of `rep` rows (fp32 accumulate)."""
+    _req(x, BF16, "sum_row_groups.x")
+    groups = x.numel() // (rep * row_elems)
+    out = torch.empty((groups * row_elems // x.shape[-1], x.shape[-1]), dtype=BF16, device=x.device)
+    _call("cti_sum_row_groups", _lib.load().cti_sum_row_groups,
+          (x.data_ptr(), out.data_ptr(), groups, rep, row_elems, _stream()), nbytes=2.0 * (rep + 1) * groups * row_elems)
+    return out
+
+
+def trilinear_fwd(vc, qc, ac, tpack, rowmask, B, K, Q, A, G, R, v_rep: int = 1) -> torch.Tensor:
+    """vc (and rowmask) hold B / v_rep samples: rows b*v_rep .. b*v_rep + v_rep - 1 of qc / ac share image b."""
     for t, n in ((vc, "vc"), (qc, "qc"), (ac, "ac"), (tpack, "tpack")):
         _req(t, BF16, "trilinear_fwd." + n)
     logits = torch.empty((B, G, K, Q, A), dtype=F32, device=vc.device)
     _call("cti_trilinear_logits_fwd", _lib.load().cti_trilinear_logits_fwd,
           (vc.data_ptr(), qc.data_ptr(), ac.data_ptr(), tpack.data_ptr(), _ptr(rowmask), logits.data_ptr(), B, K, Q, A, G,
-           R, _stream()), flops=float(B) * trilinear_min_flops(K, Q, A, G, R))
+           R, v_rep, _stream()), flops=float(B) * trilinear_min_flops(K, Q, A, G, R))
     return logits
 
 
-def trilinear_bwd(vc, qc, ac, tpack, dlogits, B, K, Q, A, G, R):
-    """Returns dzv, dzq, dza (bf16, pre-activation), dbv, dbq, dba (fp32, R*16), dtpack (fp32)."""
+def trilinear_bwd(vc, qc, ac, tpack, dlogits, B, K, Q, A, G, R, v_rep: int = 1):
+    """Returns dzv, dzq, dza (bf16, pre-activation), dbv, dbq, dba (fp32, R*16), dtpack (fp32).
+    v_rep > 1: the per-row dzv is folded onto the B / v_rep shared images before it is returned."""
     _req(dlogits, F32, "trilinear_bwd.dlogits")
     lib = _lib.load()
     dev = vc.device
-    dzv, dzq, dza = torch.empty_like(vc), torch.empty_like(qc), torch.empty_like(ac)
+    dzv, dzq, dza = torch.empty((B * K, R * 16), dtype=BF16, device=dev), torch.empty_like(qc), torch.empty_like(ac)
     zeros = torch.zeros((3 * R * 16 + tpack.numel(),), dtype=F32, device=dev)
     dbv, dbq, dba = zeros[:R * 16], zeros[R * 16:2 * R * 16], zeros[2 * R * 16:3 * R * 16]
     dtpack = zeros[3 * R * 16:]
@@ -255,32 +267,36 @@ def trilinear_bwd(vc, qc, ac, tpack, dlogits, B, K, Q, A, G, R):
     _call("cti_trilinear_logits_bwd", lib.cti_trilinear_logits_bwd,
           (vc.data_ptr(), qc.data_ptr(), ac.data_ptr(), tpack.data_ptr(), dlogits.data_ptr(), dzv.data_ptr(),
            dzq.data_ptr(), dza.data_ptr(), dbv.data_ptr(), dbq.data_ptr(), dba.data_ptr(), dtpack.data_ptr(),
-           ws.data_ptr(), nbytes, B, K, Q, A, G, R, _stream()), kernels=2,
+           ws.data_ptr(), nbytes, B, K, Q, A, G, R, v_rep, _stream()), kernels=2,
           flops=2.0 * B * trilinear_min_flops(K, Q, A, G, R))
+    if v_rep > 1:
+        dzv = sum_row_groups(dzv, v_rep, K * R * 16)
     return dzv, dzq, dza, dbv, dbq, dba, dtpack
 
 
-def tri_pool_fwd(v, q, a, w, w_stride_b, B, K, Q, A, C) -> torch.Tensor:
+def tri_pool_fwd(v, q, a, w, w_stride_b, B, K, Q, A, C, v_rep: int = 1) -> torch.Tensor:
     out = torch.empty((B, C), dtype=F32, device=v.device)
     _call("cti_tri_pool_fwd", _lib.load().cti_tri_pool_fwd,
-          (v.data_ptr(), q.data_ptr(), _ptr(a), w.data_ptr(), w_stride_b, out.data_ptr(), B, K, Q, A, C, _stream()),
+          (v.data_ptr(), q.data_ptr(), _ptr(a), w.data_ptr(), w_stride_b, out.data_ptr(), B, K, Q, A, C, v_rep, _stream()),
           flops=float(B) * pool_flops(K, Q, A, C))
     return out
 
 
-def tri_pool_bwd(v, q, a, w, w_stride_b, dout, B, K, Q, A, C):
+def tri_pool_bwd(v, q, a, w, w_stride_b, dout, B, K, Q, A, C, v_rep: int = 1):
     """Returns dzv, dzq, dza (bf16), dbv, dbq, dba (fp32, C), dw (B,K,Q[,A]) fp32.  A == 0: bilinear."""
     _req(dout, F32, "tri_pool_bwd.dout")
     dev = v.device
-    dzv, dzq = torch.empty_like(v), torch.empty_like(q)
+    dzv, dzq = torch.empty((B * K, C), dtype=BF16, device=dev), torch.empty_like(q)
     dza = torch.empty_like(a) if A > 0 else None
     zeros = torch.zeros((3 * C,), dtype=F32, device=dev)
     dbv, dbq, dba = zeros[:C], zeros[C:2 * C], zeros[2 * C:]
     dw = torch.empty((B, K, Q, A) if A > 0 else (B, K, Q), dtype=F32, device=dev)
     _call("cti_tri_pool_bwd", _lib.load().cti_tri_pool_bwd,
           (v.data_ptr(), q.data_ptr(), _ptr(a), w.data_ptr(), w_stride_b, dout.data_ptr(), dzv.data_ptr(), dzq.data_ptr(),
-           _ptr(dza), dbv.data_ptr(), dbq.data_ptr(), dba.data_ptr(), dw.data_ptr(), B, K, Q, A, C, _stream()),
+           _ptr(dza), dbv.data_ptr(), dbq.data_ptr(), dba.data_ptr(), dw.data_ptr(), B, K, Q, A, C, v_rep, _stream()),
           flops=2.0 * B * pool_flops(K, Q, A, C))
+    if v_rep > 1:
+        dzv = sum_row_groups(dzv, v_rep, K * C)
     return dzv, dzq, dza, dbv, dbq, (dba if A > 0 else None), dw
 
 

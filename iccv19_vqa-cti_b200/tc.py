@@ -15,6 +15,18 @@ from . import functions as F_
 from .fc import FCNet, cast_features, features_f32_2d
 
 
+def _rows(v, q, a) -> int:
+    """Batch rows of a call.  Extension of the reference interface: ``v`` may hold B / n images when each run of n
+    consecutive rows of q / a asks about the same image -- the multiple-choice trainer clones every image once per
+    answer candidate (reference src/MC/train.py:75-76); handing the un-cloned features in gives identical outputs
+    (the clones' projections are identical) with the image-side GEMMs, casts and activations done once per image."""
+    B = q.shape[0]
+    if a.shape[0] != B or v.shape[0] < 1 or B % v.shape[0] != 0:
+        raise RuntimeError(f"batch mismatch: v has {v.shape[0]} samples, q {q.shape[0]}, a {a.shape[0]} "
+                           "(v must have as many rows as q and a, or a divisor of it)")
+    return B
+
+
 class TCNet(nn.Module):
     def __init__(self, v_dim, q_dim, a_dim, h_dim, h_out, rank, glimpse, act='ReLU', dropout=[.2, .5], k=1):
         super().__init__()
@@ -71,7 +83,7 @@ class TCNet(nn.Module):
 
     def _logits(self, v, q, a, rowmask_wanted: bool):
         self._check_trilinear()
-        B, K = v.shape[0], v.shape[1]
+        B, K = _rows(v, q, a), v.shape[1]
         Q, A = q.shape[1], a.shape[1]
         G = self.T_g.shape[5]
         v_bf16, rowmask = cast_features(v)
@@ -110,12 +122,13 @@ class TCNet(nn.Module):
                                     la.weight_v, la.weight_g, la.bias, Vvn, gvn, bvn, Vqn, gqn, bqn, Van, gan, ban)
 
     def forward(self, v, q, a):
-        """v (B,K,v_dim), q (B,Q,q_dim), a (B,A,a_dim) -> trilinear logit map (B,K,Q,A,G)."""
+        """v (B,K,v_dim), q (B,Q,q_dim), a (B,A,a_dim) -> trilinear logit map (B,K,Q,A,G).
+        v may also hold B / n images when every run of n consecutive (q, a) rows belongs to one image (see _rows)."""
         return self._logits(v, q, a, False)
 
     def forward_with_weights(self, v, q, a, w):
         """Attention-weighted trilinear pooling: w (B,K,Q,A) -> joint embedding (B, h_dim)."""
-        B, K = v.shape[0], v.shape[1]
+        B, K = _rows(v, q, a), v.shape[1]
         Q, A = q.shape[1], a.shape[1]
         v_bf16, _ = cast_features(v)
         lv, pv = self.v_tucker.single()

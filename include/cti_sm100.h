@@ -61,7 +61,8 @@ int cti_dropout_reduce(const void* dxt, float* acc, int64_t rows, int cols, int 
 
 /* ---- weight-norm fold ----------------------------------------------------------------------
  * A matrix of n_groups stacked nn.Linear weights, each (rows_per_group, cols), each with its own
- * scalar g:  sumsq[i] = ||V_i||_F^2,  W_eff_i = bf16(V_i * g_i / ||V_i||_F).
+ * scalar g:  sumsq[i] = ||V_i||_F^2,  W_eff_i = bf16(V_i * g_i / ||V_i||_F).  The norm is reduced in a fixed order
+ * (no atomics): equal weights give bit-equal packs.  w_eff_bf16 / dv double as scratch before they are written.
  * replaces: torch.nn.utils.weight_norm(nn.Linear, dim=None) as used by src/fc.py:22,27. */
 int cti_wn_pack(const float* v, const float* g, void* w_eff_bf16, float* sumsq, int n_groups, int rows_per_group,
                 int cols, void* stream);
@@ -98,34 +99,44 @@ int cti_masked_softmax_fwd(const float* logits, float* p, int64_t rows, int len,
 int cti_masked_softmax_bwd(const float* p, const float* dp, int64_t dp_stride_b, int64_t dp_stride_g,
                            int64_t dp_stride_e, float* dlogits, int64_t batch, int groups, int len, void* stream);
 
+/* out[g,e] = sum_{j<rep} x[g*rep+j, e]: x (groups*rep, row_elems) bf16 -> out (groups, row_elems) bf16, fp32 sum;
+ * row_elems % 8 == 0.  Folds per-row dzv back onto the shared image (the gradient of the expand() in
+ * src/MC/train.py:75). */
+int cti_sum_row_groups(const void* x_bf16, void* out_bf16, int64_t groups, int rep, int64_t row_elems, void* stream);
+
 /* ---- trilinear logit map ----------------------------------------------------------------------
  * vc (B,K,R*16), qc (B,Q,R*16), ac (B,A,R*16) bf16: the per-rank projections, column = r*16 + i.
  * tpack (R,16,16*G*16) bf16: T_eff[r][l][(i,g,j)] (see DESIGN.md for the T_g -> T_eff permutation).
  * logits (B,G,K,Q,A) fp32, -inf where rowmask[b*K+k] != 0 (rowmask may be NULL).
+ * v_rep >= 1 (B % v_rep == 0): rows b*v_rep .. b*v_rep+v_rep-1 share ONE image -- vc and rowmask then hold B/v_rep
+ *   samples and row b reads sample b / v_rep.  This is the MC x4 candidate clone of src/MC/train.py:75-76 without the
+ *   copies; v_rep = 1 is the reference layout.  The backward still writes dzv per row b, (B,K,R*16): fold it with
+ *   cti_sum_row_groups before the v-side wgrad.
  * replaces: the rank loop of TCNet.forward (src/tc.py:46-52) incl. Tensor.ModeProduct
  *           (src/Tensor.py:3-19) and the masked_fill_ of src/attention.py:55-56. */
 int cti_trilinear_logits_fwd(const void* vc, const void* qc, const void* ac, const void* tpack, const uint8_t* rowmask,
-                             float* logits, int B, int K, int Q, int A, int G, int R, void* stream);
+                             float* logits, int B, int K, int Q, int A, int G, int R, int v_rep, void* stream);
 size_t cti_trilinear_logits_bwd_workspace(int B, int K, int Q, int A, int G, int R);
 /* dz* are the PRE-activation gradients of the per-rank projections (ReLU masks applied);
  * db*_accum (R*16 each) and dtpack_accum (same shape as tpack, fp32) are accumulated into. */
 int cti_trilinear_logits_bwd(const void* vc, const void* qc, const void* ac, const void* tpack, const float* dlogits,
                              void* dzv, void* dzq, void* dza, float* dbv_accum, float* dbq_accum, float* dba_accum,
                              float* dtpack_accum, void* workspace, size_t workspace_bytes, int B, int K, int Q, int A,
-                             int G, int R, void* stream);
+                             int G, int R, int v_rep, void* stream);
 
 /* ---- attention-weighted pooling ---------------------------------------------------------------
  * out[b,c] = sum_{k,q,a} V[b,k,c] w[b,k,q,a] Qp[b,q,c] Ap[b,a,c];  A = 0 drops the Ap factor.
- * v (B,K,C), q (B,Q,C), a (B,A,C) bf16; w: (K,Q,A) contiguous per sample, samples w_stride_b floats apart.
+ * v (B/v_rep,K,C), q (B,Q,C), a (B,A,C) bf16; w: (K,Q,A) contiguous per sample, samples w_stride_b floats apart.
+ * v_rep as for cti_trilinear_logits_fwd (row b pools image b / v_rep); dzv of the backward is per row b, (B,K,C).
  * replaces: the einsum of TCNet.forward_with_weights (src/tc.py:59) and the two matmuls of
  *           BCNet.forward_with_weights (src/bc.py:73). */
 int cti_tri_pool_fwd(const void* v, const void* q, const void* a, const float* w, int64_t w_stride_b, float* out,
-                     int B, int K, int Q, int A, int C, void* stream);
+                     int B, int K, int Q, int A, int C, int v_rep, void* stream);
 /* dz* pre-activation gradients (ReLU masks of v, q, a applied); db*_accum (C each) accumulated into;
  * dw (B,K,Q,A) contiguous fp32. */
 int cti_tri_pool_bwd(const void* v, const void* q, const void* a, const float* w, int64_t w_stride_b,
                      const float* dout, void* dzv, void* dzq, void* dza, float* dbv_accum, float* dbq_accum,
-                     float* dba_accum, float* dw, int B, int K, int Q, int A, int C, void* stream);
+                     float* dba_accum, float* dw, int B, int K, int Q, int A, int C, int v_rep, void* stream);
 
 /* ---- bilinear attention logits (BAN) ------------------------------------------------------------
  * logits[b,g,k,q] = sum_c Vb[b,k,c] h[g,c] Qb[b,q,c] + hbias[g]; -inf where rowmask[b*K+k] != 0.
