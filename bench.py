@@ -53,6 +53,7 @@ def workload_config(rows, n):
     return {"workload": "CTI MC hot path fwd+bwd (TriAttention + 2x TCNet.forward_with_weights + q_prj/a_prj), "
                         "dropout off", "rows_per_gpu": rows, "global_rows": rows * n, "K": K_REGIONS, "Q": Q_TOK,
             "A": A_TOK, "glimpse": GLIMPSE, "rank": RANK, "h_mm": H_MM, "v_dim": V_DIM, "num_hid": HID,
+            "rows_are": "rows/4 questions x 4 answer candidates, image features cloned per candidate",
             "l2": "inputs larger than L2 (v alone is %.0f MB per step)" % (rows * K_REGIONS * V_DIM * 4 / 1e6),
             "parallelism": f"dp{n}"}
 
@@ -173,10 +174,17 @@ def run_b200(args):
     params = [p for p in mods.parameters()]
     reducer = GradAllReducer(params) if world > 1 else None
 
+    # multiple-choice batch: B rows = B / 4 questions x 4 answer candidates; the loader yields ONE feature tensor per
+    # question and the trainer clones it per candidate on the device (reference src/MC/train.py:69-76)
+    CLONE = 4 if B % 4 == 0 else 1
+    Bq = B // CLONE
     g = torch.Generator().manual_seed(1204 + rank)
-    v_h = torch.relu(torch.randn(B, K_REGIONS, V_DIM, generator=g))
-    nb = torch.randint(10, K_REGIONS + 1, (B,), generator=g)
+    v_h = torch.relu(torch.randn(Bq, K_REGIONS, V_DIM, generator=g))
+    nb = torch.randint(10, K_REGIONS + 1, (Bq,), generator=g)
     v_h = (v_h * (torch.arange(K_REGIONS)[None, :] < nb[:, None]).float()[:, :, None]).pin_memory()
+
+    def clone_rows(v):                           # v.unsqueeze(1).expand(...).contiguous().view(...) of train.py:75-76
+        return v.unsqueeze(1).expand(Bq, CLONE, K_REGIONS, V_DIM).contiguous().view(B, K_REGIONS, V_DIM)
     q_h = torch.tanh(torch.randn(B, Q_TOK, HID, generator=g)).pin_memory()
     a_h = torch.tanh(torch.randn(B, A_TOK, HID, generator=g)).pin_memory()
     cot = torch.randn(B, HID, generator=g).to(dev)
@@ -223,10 +231,14 @@ def run_b200(args):
         return ms.item(), w0, w1
 
     # ---- device-resident arm -------------------------------------------------
-    v_d, q_d, a_d = v_h.to(dev), q_h.to(dev), a_h.to(dev)
+    vq_d, q_d, a_d = v_h.to(dev), q_h.to(dev), a_h.to(dev)
+    v_d = clone_rows(vq_d)                       # the cloned (B, K, 2048) tensor the reference's model receives
 
     def resident_step():
         step(v_d, q_d.detach(), a_d.detach())
+
+    def shared_step():                           # extension: the un-cloned features go straight in
+        step(vq_d, q_d.detach(), a_d.detach())
 
     for _ in range(max(args.warmup, 3)):
         resident_step()
@@ -268,9 +280,33 @@ def run_b200(args):
     clocks = sampler.stop(w0, w1) if sampler else None
     value = world * B * args.steps / (ms / 1e3)
 
+    # ---- same step with the un-cloned image features handed in (rows of one question share the image) ----------
+    shared = None
+    if CLONE > 1 and not args.resident_only:
+        try:
+            for _ in range(3):
+                shared_step()
+            run_shared = shared_step
+            if use_graph:
+                g_sh = cti_b200.GraphedStep(shared_step, [mods], [vq_d])
+                if reducer is None:
+                    run_shared = g_sh.replay
+                else:
+                    def run_shared():
+                        g_sh.replay()
+                        reducer.reduce_now()
+                for _ in range(3):
+                    run_shared()
+            ms_sh, _, _ = timed(run_shared, args.steps)
+            shared = {"value": world * B * args.steps / (ms_sh / 1e3), "unit": UNIT, "ms_per_step": ms_sh / args.steps,
+                      "note": "v passed once per question (B/4 samples), no x4 clone: identical outputs, image-side "
+                              "GEMMs once per image; needs the clone line of src/MC/train.py:75-76 removed"}
+        except Exception as exc:
+            shared = {"failed": repr(exc)[:200]}
+
     # ---- end-to-end arm: pinned host inputs -> H2D -> modules -> D2H ----------
     def e2e_step():
-        v = v_h.to(dev, non_blocking=True)
+        v = clone_rows(v_h.to(dev, non_blocking=True))               # H2D per question, clone on the device
         q = q_h.to(dev, non_blocking=True)
         a = a_h.to(dev, non_blocking=True)
         joint = step(v, q, a)
@@ -303,22 +339,26 @@ def run_b200(args):
         # (two sets of static input buffers, one captured graph per set) -- what a prefetching loader gives a user.
         try:
             copy_stream = torch.cuda.Stream()
-            bufs = [(torch.empty_like(v_d), torch.empty_like(q_d), torch.empty_like(a_d)) for _ in range(2)]
+            bufs = [(torch.empty_like(vq_d), torch.empty_like(q_d), torch.empty_like(a_d)) for _ in range(2)]
             outs = [torch.empty(B, HID).pin_memory() for _ in range(2)]
             ev_copied = [torch.cuda.Event() for _ in range(2)]
             ev_done = [torch.cuda.Event() for _ in range(2)]
 
-            def make_compute(i):
+            def make_compute(i, share):
                 vb, qb, ab = bufs[i]
 
                 def compute():
-                    joint = step(vb, qb.detach(), ab.detach())
+                    joint = step(vb if share else clone_rows(vb), qb.detach(), ab.detach())
                     outs[i].copy_(joint.detach(), non_blocking=True)
                 return compute
-            computes = [make_compute(i) for i in range(2)]
-            if use_graph:
-                graphs = [cti_b200.GraphedStep(computes[i], [mods], [bufs[i][0]]) for i in range(2)]
-                computes = [g.replay for g in graphs]
+
+            def build_computes(share):
+                cs = [make_compute(i, share) for i in range(2)]
+                if use_graph:
+                    graphs = [cti_b200.GraphedStep(cs[i], [mods], [bufs[i][0]]) for i in range(2)]
+                    cs = [g.replay for g in graphs]
+                return cs
+            computes = build_computes(False)
             state = {"i": 0, "primed": False}
 
             def h2d_into(i):
@@ -348,8 +388,20 @@ def run_b200(args):
             ms_p, _, _ = timed(pipelined_step, args.steps)
             e2e = {"value": world * B * args.steps / (ms_p / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": out_h.numel() * 4, "ms_per_step": ms_p / args.steps,
-                   "mode": "H2D of step i+1 overlapped with compute of step i (double-buffered inputs)",
+                   "mode": "host v per question -> H2D -> x4 clone on the device (src/MC/train.py:69-76) -> modules; "
+                           "H2D of step i+1 overlapped with compute of step i (double-buffered inputs)",
                    "serial": e2e_serial}
+            if CLONE > 1:
+                computes[:] = build_computes(True)
+                state.update(i=0, primed=False)
+                for _ in range(4):
+                    pipelined_step()
+                torch.cuda.synchronize()
+                state["primed"] = False
+                ms_ps, _, _ = timed(pipelined_step, args.steps)
+                e2e["shared_v"] = {"value": world * B * args.steps / (ms_ps / 1e3), "unit": UNIT,
+                                   "ms_per_step": ms_ps / args.steps,
+                                   "note": "same host buffers, un-cloned v handed to the modules"}
         except Exception as exc:
             e2e["pipelined_failed"] = repr(exc)[:200]
 
@@ -443,7 +495,7 @@ def run_b200(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": dict(workload_config(B, world), launch="cuda_graph_replay" if use_graph else "eager"),
                 "eager": eager_ms, "e2e": e2e, "gpu_launches": launches, "gpu_launches_per_step": launches_per_step, "clocks": clocks,
-                "fwd_only": fwd, "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels}
+                "fwd_only": fwd, "shared_v": shared, "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
