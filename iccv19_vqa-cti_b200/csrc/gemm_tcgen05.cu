@@ -34,8 +34,9 @@ struct GemmCfg {
   static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
   static constexpr int ACC_STAGES = 2;
   static constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;            // 512 or 256 (power of two)
+  static constexpr int OUT_BYTES = 4 * 2 * 4096;      // per epilogue warp: two 32-row x 128-byte staging boxes
   static constexpr int BAR_BYTES = (2 * STAGES + 2 * ACC_STAGES) * 8 + 16;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // +1024: manual alignment
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES + 1024;   // +1024: manual alignment
 };
 
 struct GemmDevParams {
@@ -49,16 +50,20 @@ struct GemmDevParams {
   int relu;                     // apply max(0, .) after bias
   int atomic_f32;               // out_f32 += acc (split-K reduction)
   float alpha;                  // acc scale applied before bias
+  int tma_out;                  // 0: direct stores; 1: bf16 via TMA store; 2: fp32 via TMA store; 3: fp32 TMA reduce-add
 };
+
+enum { kOutDirect = 0, kOutTmaBf16 = 1, kOutTmaF32 = 2, kOutTmaAddF32 = 3 };
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const GemmDevParams p) {
+                 const __grid_constant__ CUtensorMap tmap_c, const GemmDevParams p) {
   using Cfg = GemmCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  const uint32_t smem_out = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;          // 1024-byte aligned
+  const uint32_t bar_base = smem_out + Cfg::OUT_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };
@@ -73,6 +78,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (p.tma_out != kOutDirect) tma_prefetch_desc(&tmap_c);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
@@ -173,7 +179,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else if (warp >= kEpiWarp0) {
     // ------------------------------ epilogue ----------------------------------
+    // Thread = one accumulator row (TMEM lane), 32 columns per tcgen05.ld.  The next chunk's TMEM load is in flight
+    // while the current one is processed; results are staged in this warp's swizzled 32-row x 128-byte boxes and
+    // leave through TMA (store, or reduce-add for split-K), so global writes are full lines and asynchronous.
+    constexpr int NCH = BLOCK_N / 32;
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter+32)
+    const uint32_t stage0 = smem_out + quarter * 8192;
+    const uint32_t my_row = stage0 + lane * 128;  // this thread's 128-byte row inside a staging box
+    const uint32_t sw = lane & 7;
+    uint32_t obuf = 0;
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int ks = tile / tiles_mn;
@@ -181,38 +195,33 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int m_blk = mn / p.num_n_blocks;
       const int n_blk = mn - m_blk * p.num_n_blocks;
       const bool empty_split = (ks * p.k_blocks_per_split >= p.num_k_blocks);
+      const int row0 = m_blk * BLOCK_M + quarter * 32;
+      const int row = row0 + lane;
+      const bool row_ok = row < p.M;
+      const int n0 = n_blk * BLOCK_N;
+      // bias: lane l holds column (chunk base + l); the first two chunks' loads are issued before the accumulator is
+      // ready, the following ones one iteration ahead (the chunk loop stays rolled: unrolled it overflows the i-cache)
+      auto load_bias = [&](int c) {
+        const int col = n0 + c * 32 + lane;
+        return (p.bias != nullptr && c < NCH && col < p.N) ? __ldg(p.bias + col) : 0.f;
+      };
+      float b0 = load_bias(0), b1 = load_bias(1);
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
-      const int row = m_blk * BLOCK_M + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + c * 32, r);
-        tmem_wait_ld();
-        const int col0 = n_blk * BLOCK_N + c * 32;
-        if (!row_ok || col0 >= p.N || empty_split) continue;
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
+
+      auto process = [&](const int c, uint32_t (&r)[32], const float bias_l) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N || empty_split) return;               // warp-uniform
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-        const size_t off = static_cast<size_t>(row) * p.ldc + col0;
-        if (p.atomic_f32) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) atomicAdd(p.out_f32 + off + j, v[j]);
-          continue;
-        }
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
-        }
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), p.alpha, __shfl_sync(0xffffffffu, bias_l, j));
         if (p.relu) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
         const bool full = (col0 + 32 <= p.N);
-        if (p.relu_aux != nullptr) {
+        if (p.relu_aux != nullptr && row_ok) {
           const __nv_bfloat16* aux = p.relu_aux + static_cast<size_t>(row) * p.ld_aux + col0;
           if (full && (p.ld_aux % 8 == 0)) {
 #pragma unroll
@@ -232,44 +241,112 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               if (col0 + j < p.N && !(__bfloat162float(aux[j]) > 0.f)) v[j] = 0.f;
           }
         }
+        const size_t off = static_cast<size_t>(row) * p.ldc + col0;
+        // ---- bf16 output
         if (p.out_bf16 != nullptr) {
-          __nv_bfloat16* o = p.out_bf16 + off;
-          if (full && (p.ldc % 8 == 0)) {
-#pragma unroll
-            for (int j8 = 0; j8 < 4; ++j8) {
-              uint4 u;
-              u.x = pack_bf16x2(v[j8 * 8 + 0], v[j8 * 8 + 1]);
-              u.y = pack_bf16x2(v[j8 * 8 + 2], v[j8 * 8 + 3]);
-              u.z = pack_bf16x2(v[j8 * 8 + 4], v[j8 * 8 + 5]);
-              u.w = pack_bf16x2(v[j8 * 8 + 6], v[j8 * 8 + 7]);
-              reinterpret_cast<uint4*>(o)[j8] = u;
+          if (p.tma_out == kOutTmaBf16) {
+            // 64-column slab = two chunks = one 128-byte row per thread; 16-byte piece q sits at q ^ (row & 7)
+            const uint32_t half = static_cast<uint32_t>(c & 1) * 4u;
+            if (half == 0) {
+              if (lane == 0) bulk_wait_group_read<1>();        // the box written two slabs ago has been read out
+              __syncwarp();
             }
-          } else {
+            const uint32_t dst = my_row + obuf * 4096;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) o[j] = __float2bfloat16(v[j]);
+            for (uint32_t q4 = 0; q4 < 4; ++q4)
+              st_shared_v4(dst + (((half + q4) ^ sw) << 4), pack_bf16x2(v[q4 * 8 + 0], v[q4 * 8 + 1]),
+                           pack_bf16x2(v[q4 * 8 + 2], v[q4 * 8 + 3]), pack_bf16x2(v[q4 * 8 + 4], v[q4 * 8 + 5]),
+                           pack_bf16x2(v[q4 * 8 + 6], v[q4 * 8 + 7]));
+            if (half != 0 || col0 + 32 >= p.N) {              // slab complete (or the row of tiles ends here)
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tmap_c, stage0 + obuf * 4096, n0 + (c >> 1) * 64, row0);
+                bulk_commit_group();
+              }
+              obuf ^= 1u;
+            }
+          } else if (row_ok) {
+            __nv_bfloat16* o = p.out_bf16 + off;
+            if (full && (p.ldc % 8 == 0)) {
+#pragma unroll
+              for (int j8 = 0; j8 < 4; ++j8) {
+                uint4 u;
+                u.x = pack_bf16x2(v[j8 * 8 + 0], v[j8 * 8 + 1]);
+                u.y = pack_bf16x2(v[j8 * 8 + 2], v[j8 * 8 + 3]);
+                u.z = pack_bf16x2(v[j8 * 8 + 4], v[j8 * 8 + 5]);
+                u.w = pack_bf16x2(v[j8 * 8 + 6], v[j8 * 8 + 7]);
+                reinterpret_cast<uint4*>(o)[j8] = u;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) o[j] = __float2bfloat16(v[j]);
+            }
           }
         }
+        // ---- fp32 output (plain, or accumulated over the K splits)
         if (p.out_f32 != nullptr) {
-          float* o = p.out_f32 + off;
-          if (full && (p.ldc % 4 == 0)) {
+          if (p.tma_out >= kOutTmaF32) {
+            if (lane == 0) bulk_wait_group_read<1>();
+            __syncwarp();
+            const uint32_t dst = my_row + obuf * 4096;
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4)
-              reinterpret_cast<float4*>(o)[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-          } else {
+            for (uint32_t q8 = 0; q8 < 8; ++q8)
+              st_shared_v4(dst + ((q8 ^ sw) << 4), __float_as_uint(v[q8 * 4]), __float_as_uint(v[q8 * 4 + 1]),
+                           __float_as_uint(v[q8 * 4 + 2]), __float_as_uint(v[q8 * 4 + 3]));
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (p.tma_out == kOutTmaAddF32) tma_reduce_add_2d(&tmap_c, stage0 + obuf * 4096, col0, row0);
+              else                            tma_store_2d(&tmap_c, stage0 + obuf * 4096, col0, row0);
+              bulk_commit_group();
+            }
+            obuf ^= 1u;
+          } else if (row_ok) {
+            float* o = p.out_f32 + off;
+            if (p.atomic_f32) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) o[j] = v[j];
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) atomicAdd(o + j, v[j]);
+            } else if (full && (p.ldc % 4 == 0)) {
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4)
+                reinterpret_cast<float4*>(o)[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) o[j] = v[j];
+            }
           }
         }
+      };
+
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32b_x32(t_addr, ra);
+#pragma unroll 1
+      for (int c = 0; c < NCH; c += 2) {
+        const float nb0 = load_bias(c + 2), nb1 = load_bias(c + 3);
+        tmem_wait_ld_regs(ra);
+        tmem_ld_32x32b_x32(t_addr + (c + 1) * 32, rb);
+        process(c, ra, b0);
+        tmem_wait_ld_regs(rb);
+        if (c + 2 < NCH) {
+          tmem_ld_32x32b_x32(t_addr + (c + 2) * 32, ra);
+        } else {
+          tcgen05_fence_before();                 // every TMEM read of this tile has completed
+          mbar_arrive(tempty_bar(acc));
+        }
+        process(c + 1, rb, b1);
+        b0 = nb0;
+        b1 = nb1;
       }
-      tcgen05_fence_before();
-      mbar_arrive(tempty_bar(acc));
       if (++acc == Cfg::ACC_STAGES) {
         acc = 0;
         acc_phase ^= 1u;
       }
     }
+    if (lane == 0) bulk_wait_group_all();         // staged boxes must be drained before the CTA's smem goes away
   }
 
   tcgen05_fence_before();
@@ -295,19 +372,20 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 // 2-D bf16 tensor map: `inner` contiguous elements per row, `outer` rows, row pitch ld elements.
 int make_tmap(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld_elems, uint32_t box_inner,
-              uint32_t box_outer) {
+              uint32_t box_outer, bool f32 = false) {
   auto fn = get_encode_fn();
   CTI_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
   CTI_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand must be 16-byte aligned");
-  CTI_REQUIRE((ld_elems * 2) % 16 == 0, "TMA operand row pitch must be a multiple of 16 bytes (ld=%llu)",
+  const uint64_t esz = f32 ? 4 : 2;
+  CTI_REQUIRE((ld_elems * esz) % 16 == 0, "TMA operand row pitch must be a multiple of 16 bytes (ld=%llu)",
               (unsigned long long)ld_elems);
   cuuint64_t gdim[2] = {inner, outer};
-  cuuint64_t gstride[1] = {ld_elems * 2};
+  cuuint64_t gstride[1] = {ld_elems * esz};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr),
+                  gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CTI_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;
 }
@@ -335,6 +413,20 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   p.k_splits = (p.num_k_blocks + p.k_blocks_per_split - 1) / p.k_blocks_per_split;   // no empty splits
   p.bias = g.bias; p.relu_aux = g.relu_aux; p.out_bf16 = g.out_bf16; p.out_f32 = g.out_f32;
   p.ldc = g.ldc; p.ld_aux = g.ld_aux; p.relu = g.relu; p.atomic_f32 = g.atomic_f32; p.alpha = g.alpha;
+  // Output through TMA when the buffer allows it (16-byte aligned base and row pitch); with both outputs requested
+  // the fp32 one takes the TMA path.  Each epilogue warp stores 32-row boxes of 128 bytes (64 bf16 / 32 fp32).
+  auto tma_ok = [&](const void* ptr, int esz) {
+    return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (static_cast<long>(g.ldc) * esz) % 16 == 0;
+  };
+  CUtensorMap tc = ta;
+  p.tma_out = kOutDirect;
+  if (g.out_f32 != nullptr && tma_ok(g.out_f32, 4)) {
+    p.tma_out = g.atomic_f32 ? kOutTmaAddF32 : kOutTmaF32;
+    if ((rc = make_tmap(&tc, g.out_f32, g.N, g.M, g.ldc, 32, 32, true))) return rc;
+  } else if (g.out_bf16 != nullptr && g.out_f32 == nullptr && tma_ok(g.out_bf16, 2)) {
+    p.tma_out = kOutTmaBf16;
+    if ((rc = make_tmap(&tc, g.out_bf16, g.N, g.M, g.ldc, 64, 32))) return rc;
+  }
 
   static bool attr_set = false;
   auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN>;
@@ -349,7 +441,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   const long total = (long)p.num_m_blocks * p.num_n_blocks * p.k_splits;
   int sms = g.max_ctas > 0 ? g.max_ctas : kNumSMsB200;
   const int grid = (int)(total < sms ? total : sms);
-  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(ta, tb, tc, p);
   return check_launch("gemm_bf16_kernel");
 }
 
