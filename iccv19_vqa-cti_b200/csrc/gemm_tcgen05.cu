@@ -8,8 +8,8 @@
 //   wgrad     dW = dZ^T X   (split over rows)  A = dZ  (MN-major), B = X    (MN-major)
 // which is the work of reference src/fc.py:33-34 (FCNet.forward) and its autograd.
 //
-// Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
-// allocator, warps 4..7 = epilogue (TMEM lane quarter = warp % 4).
+// Roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
+// allocator, warps 4..11 = epilogue (TMEM lane quarter = warp % 4, two warps per quarter).
 #include "cti_common.cuh"
 #include "cti_kernels.h"
 #include "tc_tiles.cuh"
@@ -23,7 +23,8 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;          // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;      // warps 0-2: TMA / MMA / TMEM alloc, warp 3 idle, warps 4-11: epilogue
+constexpr int kEpiWarps = 8;
 constexpr int kEpiWarp0 = 4;
 
 template <int BLOCK_N>
@@ -34,7 +35,7 @@ struct GemmCfg {
   static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
   static constexpr int ACC_STAGES = 2;
   static constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;            // 512 or 256 (power of two)
-  static constexpr int OUT_BYTES = 4 * 2 * 4096;      // per epilogue warp: two 32-row x 128-byte staging boxes
+  static constexpr int OUT_BYTES = kEpiWarps * 4096;  // per epilogue warp: one 32-row x 128-byte staging box
   static constexpr int BAR_BYTES = (2 * STAGES + 2 * ACC_STAGES) * 8 + 16;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES + 1024;   // +1024: manual alignment
 };
@@ -87,7 +88,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int s = 0; s < Cfg::ACC_STAGES; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 128);
+      mbar_init(tempty_bar(s), kEpiWarps * 32);
     }
     fence_barrier_init();
   }
@@ -182,12 +183,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // Thread = one accumulator row (TMEM lane), 32 columns per tcgen05.ld.  The next chunk's TMEM load is in flight
     // while the current one is processed; results are staged in this warp's swizzled 32-row x 128-byte boxes and
     // leave through TMA (store, or reduce-add for split-K), so global writes are full lines and asynchronous.
-    constexpr int NCH = BLOCK_N / 32;
+    // Two warps per TMEM lane quarter, each taking half of the tile's columns: the per-thread work is a long dependent
+    // chain (tcgen05.ld -> shuffle -> fma -> pack -> st.shared), so two warps per scheduler hide each other's latency.
+    constexpr int NCH = BLOCK_N / 64;             // 32-column chunks per warp
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter+32)
-    const uint32_t stage0 = smem_out + quarter * 8192;
-    const uint32_t my_row = stage0 + lane * 128;  // this thread's 128-byte row inside a staging box
+    const int chalf = (warp - kEpiWarp0) >> 2;    // which half of the tile's columns
+    const uint32_t stage0 = smem_out + (warp - kEpiWarp0) * 4096;
+    const uint32_t my_row = stage0 + lane * 128;  // this thread's 128-byte row inside the staging box
     const uint32_t sw = lane & 7;
-    uint32_t obuf = 0;
+    constexpr uint32_t obuf = 0;
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int ks = tile / tiles_mn;
@@ -198,7 +202,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int row0 = m_blk * BLOCK_M + quarter * 32;
       const int row = row0 + lane;
       const bool row_ok = row < p.M;
-      const int n0 = n_blk * BLOCK_N;
+      const int n0 = n_blk * BLOCK_N + chalf * (BLOCK_N / 2);
       // bias: lane l holds column (chunk base + l); the first two chunks' loads are issued before the accumulator is
       // ready, the following ones one iteration ahead (the chunk loop stays rolled: unrolled it overflows the i-cache)
       auto load_bias = [&](int c) {
@@ -208,7 +212,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       float b0 = load_bias(0), b1 = load_bias(1);
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + chalf * (BLOCK_N / 2);
 
       auto process = [&](const int c, uint32_t (&r)[32], const float bias_l) {
         const int col0 = n0 + c * 32;
@@ -248,7 +252,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             // 64-column slab = two chunks = one 128-byte row per thread; 16-byte piece q sits at q ^ (row & 7)
             const uint32_t half = static_cast<uint32_t>(c & 1) * 4u;
             if (half == 0) {
-              if (lane == 0) bulk_wait_group_read<1>();        // the box written two slabs ago has been read out
+              if (lane == 0) bulk_wait_group_read<0>();        // the previous box has been read out
               __syncwarp();
             }
             const uint32_t dst = my_row + obuf * 4096;
@@ -264,7 +268,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 tma_store_2d(&tmap_c, stage0 + obuf * 4096, n0 + (c >> 1) * 64, row0);
                 bulk_commit_group();
               }
-              obuf ^= 1u;
             }
           } else if (row_ok) {
             __nv_bfloat16* o = p.out_bf16 + off;
@@ -288,7 +291,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // ---- fp32 output (plain, or accumulated over the K splits)
         if (p.out_f32 != nullptr) {
           if (p.tma_out >= kOutTmaF32) {
-            if (lane == 0) bulk_wait_group_read<1>();
+            if (lane == 0) bulk_wait_group_read<0>();
             __syncwarp();
             const uint32_t dst = my_row + obuf * 4096;
 #pragma unroll
@@ -302,7 +305,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               else                            tma_store_2d(&tmap_c, stage0 + obuf * 4096, col0, row0);
               bulk_commit_group();
             }
-            obuf ^= 1u;
           } else if (row_ok) {
             float* o = p.out_f32 + off;
             if (p.atomic_f32) {
