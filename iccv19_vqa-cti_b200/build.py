@@ -21,6 +21,8 @@ SOURCES = ["cti_capi.cu", "gemm_tcgen05.cu", "elementwise.cu", "softmax.cu", "tr
 HEADERS = ["cti_common.cuh", "cti_kernels.h", "wmma_tiles.cuh", "tc_tiles.cuh", os.path.join("..", "..", "include", "cti_sm100.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+if os.environ.get("CTI_WATCHDOG"):                 # debug: mbarrier watchdog (see csrc/cti_common.cuh)
+    NVCC_FLAGS.append("-DCTI_WATCHDOG=" + os.environ["CTI_WATCHDOG"])
 
 
 def _nvcc() -> str:

@@ -11,7 +11,11 @@
 #include <stdio.h>
 
 #ifndef CTI_WATCHDOG
-#define CTI_WATCHDOG 1   // trap instead of hanging forever if a pipeline barrier never flips
+// 0 (default): plain mbarrier wait loops.  1: trap instead of hanging forever if a pipeline barrier never flips;
+// 2: also printf which one.  Debug builds only (CTI_WATCHDOG=1 python build.py --force): the spin counter in every wait
+// loop costs ~5 % of a training step, and the inlined printf call sites another ~5 % (i-cache and issue slots of the
+// role warps that share a scheduler with the waiting ones).
+#define CTI_WATCHDOG 0
 #endif
 
 namespace cti {
@@ -107,8 +111,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 20)) {   // many seconds: a broken pipeline, not a slow one
+#if CTI_WATCHDOG > 1              // bring-up only: every inlined printf call site costs ~30 instructions of i-cache
       printf("cti: mbarrier watchdog fired (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar,
              parity);
+#endif
       __trap();
     }
   }
