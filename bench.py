@@ -475,8 +475,8 @@ def run_b200(args):
             roofline = {"kernel": f"gemm_bf16_kernel [{ktag}]", "bound": "tensor", "achieved": ach, "peak": tf_peak,
                         "unit": "TFLOP/s", "frac": ach / tf_peak,
                         # dram__bytes_read.sum + dram__bytes_write.sum of this launch in the committed ncu --set full
-                        # capture (profiles/r01_ncu_full_step_table.md row 36: 214.0 + 72.0 MB); algorithmic 210 + 105 MB
-                        "traffic": 286.0e6 if ktag == "fwd M=51200 N=1024 K=2048" else None,
+                        # capture (profiles/r01_ncu_gemm_dominant.md: 214.0 + 76.9 MB); algorithmic 210 + 4 + 105 MB
+                        "traffic": 290.9e6 if ktag == "fwd M=51200 N=1024 K=2048" else None,
                         "peak_source": which + ", sustained bf16 (kernel timed inside a long step); burst %.0f" % tf_burst,
                         "share_of_step": d[1] / total,
                         "all_gemm_launches": {"tflops": gflops / (gms * 1e-3) / 1e12, "share_of_step": gms / total,
