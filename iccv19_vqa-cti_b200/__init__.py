@@ -11,12 +11,14 @@ or eager-PyTorch fallback: without the built library, or on non-CUDA tensors, ca
 from . import _lib
 from .attention import BiAttention, TriAttention
 from .bc import BCNet
+from .classifier import SimpleClassifier
 from .dropin import install, uninstall
 from .fc import FCNet, WNLinear
 from .graphs import GraphedStep, reset_caches
+from .optim import FusedClipAdamax
 from .tc import TCNet
 
-__all__ = ["FCNet", "WNLinear", "TCNet", "TriAttention", "BCNet", "BiAttention", "install", "uninstall", "GraphedStep", "reset_caches",
+__all__ = ["FCNet", "WNLinear", "TCNet", "TriAttention", "BCNet", "BiAttention", "SimpleClassifier", "FusedClipAdamax", "install", "uninstall", "GraphedStep", "reset_caches",
            "library_path", "version"]
 
 

@@ -25,6 +25,9 @@ SIGNATURES = {
     "cti_dropout_expand": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, c_float, ctypes.c_uint64, ctypes.c_uint64, _P]),
     "cti_dropout_reduce": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, c_float, ctypes.c_uint64, ctypes.c_uint64, _P]),
     "cti_sum_row_groups": (c_int, [_P, _P, c_int64, c_int, c_int64, _P]),
+    "cti_grad_sumsq_multi": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, _P, _P]),
+    "cti_adamax_multi": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P, c_float, c_float, c_float, c_float, c_float,
+                                 c_float, _P, _P]),
     "cti_wn_pack": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "cti_wn_grad": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "cti_gemm_bf16": (c_int, [_P, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_float, _P, c_int, _P, c_int,

@@ -118,6 +118,27 @@ int cti_sum_row_groups(const void* x_bf16, void* out_bf16, int64_t groups, int r
                              row_elems, static_cast<cudaStream_t>(stream));
 }
 
+int cti_grad_sumsq_multi(const void* g_ptrs_dev, const int64_t* numel_dev, const int32_t* chunk_tensor_dev,
+                         const int64_t* chunk_start_dev, int n_chunks, int chunk_elems, float* partials, float* sumsq,
+                         void* stream) {
+  return cti::grad_sumsq_multi(static_cast<const float* const*>(g_ptrs_dev), reinterpret_cast<const long*>(numel_dev),
+                               chunk_tensor_dev, reinterpret_cast<const long*>(chunk_start_dev), n_chunks, chunk_elems,
+                               partials, sumsq, static_cast<cudaStream_t>(stream));
+}
+
+int cti_adamax_multi(const void* p_ptrs_dev, const void* g_ptrs_dev, const void* m_ptrs_dev, const void* u_ptrs_dev,
+                     const int64_t* numel_dev, const int32_t* chunk_tensor_dev, const int64_t* chunk_start_dev,
+                     int n_chunks, int chunk_elems, const float* sumsq, float inv_denom, float clip_norm, float clr,
+                     float beta1, float beta2, float eps, float* norm_out, void* stream) {
+  return cti::adamax_multi(static_cast<float* const*>(const_cast<void*>(p_ptrs_dev)),
+                           static_cast<const float* const*>(g_ptrs_dev),
+                           static_cast<float* const*>(const_cast<void*>(m_ptrs_dev)),
+                           static_cast<float* const*>(const_cast<void*>(u_ptrs_dev)),
+                           reinterpret_cast<const long*>(numel_dev), chunk_tensor_dev,
+                           reinterpret_cast<const long*>(chunk_start_dev), n_chunks, chunk_elems, sumsq, inv_denom,
+                           clip_norm, clr, beta1, beta2, eps, norm_out, static_cast<cudaStream_t>(stream));
+}
+
 int cti_masked_softmax_fwd(const float* logits, float* p, int64_t rows, int len, void* stream) {
   return cti::masked_softmax_fwd(logits, p, rows, len, static_cast<cudaStream_t>(stream));
 }

@@ -48,6 +48,14 @@ int wn_grad(const float* dw, const float* v, const float* g, const float* sumsq,
 int act_bwd_bias(const void* dy, int dy_is_bf16, const __nv_bfloat16* y, __nv_bfloat16* dz, float* dbias, long rows,
                  int cols, cudaStream_t s);
 
+// optim.cu  (multi-tensor trainer tail; pointer / chunk tables live in device memory)
+int grad_sumsq_multi(const float* const* g_ptrs, const long* numel, const int* chunk_tensor, const long* chunk_start,
+                     int n_chunks, int chunk_elems, float* partials, float* sumsq, cudaStream_t s);
+int adamax_multi(float* const* p_ptrs, const float* const* g_ptrs, float* const* m_ptrs, float* const* u_ptrs,
+                 const long* numel, const int* chunk_tensor, const long* chunk_start, int n_chunks, int chunk_elems,
+                 const float* sumsq, float inv_denom, float clip_norm, float clr, float beta1, float beta2, float eps,
+                 float* norm_out, cudaStream_t s);
+
 // softmax.cu
 int masked_softmax_fwd(const float* logits, float* p, long rows, int len, cudaStream_t s);
 int masked_softmax_bwd(const float* p, const float* dp, long dp_row_stride_b, long dp_row_stride_g, long dp_elem_stride,

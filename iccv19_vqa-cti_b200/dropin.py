@@ -14,6 +14,7 @@ _TARGETS = {
     "src.tc": ("TCNet",),
     "src.bc": ("BCNet",),
     "src.attention": ("BiAttention", "TriAttention"),
+    "src.classifier": ("SimpleClassifier",),
 }
 # modules that did ``from src.x import Name`` and hold their own binding
 _IMPORTERS = ("src.MC.base_model", "src.FFOE.base_model", "src.attention", "src.tc", "src.bc")
@@ -21,9 +22,9 @@ _IMPORTERS = ("src.MC.base_model", "src.FFOE.base_model", "src.attention", "src.
 
 def install() -> None:
     """Patch the reference package (must be importable as ``src``) to use the sm_100a modules."""
-    from . import attention, bc, fc, tc
+    from . import attention, bc, classifier, fc, tc
     ours = {"FCNet": fc.FCNet, "TCNet": tc.TCNet, "BCNet": bc.BCNet, "BiAttention": attention.BiAttention,
-            "TriAttention": attention.TriAttention}
+            "TriAttention": attention.TriAttention, "SimpleClassifier": classifier.SimpleClassifier}
     for modname, names in _TARGETS.items():
         mod = importlib.import_module(modname)
         for n in names:

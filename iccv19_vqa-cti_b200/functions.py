@@ -30,16 +30,27 @@ class Packed:
 
 
 def pack_layer(V: torch.Tensor, g: torch.Tensor, n_groups: int) -> Packed:
-    w, sumsq = K_.wn_pack(V.detach().contiguous(), g.detach().reshape(n_groups).contiguous(), n_groups)
+    """Single layers are padded with zero rows to a multiple of 8 outputs (classifier heads: 2 or 3129 classes)."""
+    w, sumsq = K_.wn_pack(V.detach().contiguous(), g.detach().reshape(n_groups).contiguous(), n_groups,
+                          pad_rows_to=8 if n_groups == 1 else 1)
     return Packed(w, sumsq)
+
+
+def _pad_cols(x: torch.Tensor, n: int) -> torch.Tensor:
+    """x (..., c) -> (..., n) with zero columns appended (no-op when c == n)."""
+    if x.shape[-1] == n:
+        return x
+    out = torch.zeros((*x.shape[:-1], n), dtype=x.dtype, device=x.device)
+    out[..., :x.shape[-1]] = x
+    return out
 
 
 def lin_fwd(x: torch.Tensor, pk: Packed, bias: torch.Tensor, relu: bool, out_bf16: bool = True,
             out_f32: bool = False):
     """y = act(x W_eff^T + b); x (M, K_in) bf16 -> (bf16 | None, fp32 | None)."""
     M, Kin = x.shape
-    N = pk.w.shape[0]
-    return K_.gemm(x, pk.w, M, N, Kin, bias=bias.detach(), relu=relu, out_bf16=out_bf16, out_f32=out_f32)
+    N = pk.w.shape[0]                                    # padded width of the pack
+    return K_.gemm(x, pk.w, M, N, Kin, bias=_pad_cols(bias.detach(), N), relu=relu, out_bf16=out_bf16, out_f32=out_f32)
 
 
 def _pick_splits(tiles: int, k_blocks: int) -> int:
@@ -95,7 +106,8 @@ def lin_bwd(x: torch.Tensor, dz: torch.Tensor, V: torch.Tensor, g: torch.Tensor,
     splits = _pick_splits(tiles, -(-M // 64))
     dw = torch.zeros((N, Kin), dtype=F32, device=x.device)
     K_.gemm(dz, x, N, Kin, M, a_mn=True, b_mn=True, accum_f32=dw, k_splits=splits, tile_n=tile_n, alpha=alpha)
-    dV, dg = K_.wn_grad(dw, V.detach().contiguous(), g.detach().reshape(n_groups).contiguous(), pk.sumsq, n_groups)
+    dV, dg = K_.wn_grad(dw[:V.shape[0]], V.detach().contiguous(), g.detach().reshape(n_groups).contiguous(), pk.sumsq,
+                        n_groups)
     dx = None
     if need_dx:
         # dgrad: dx[M, K_in] = dz W_eff  (W_eff stored [N][K_in] = MN-major B operand)
@@ -216,18 +228,18 @@ class WNLinearFn(Function):
         ctx.pk = pk
         ctx.relu = relu
         ctx.need_dx = x.requires_grad
-        return yf
+        return yf if yf.shape[1] == V.shape[0] else yf[:, :V.shape[0]]
 
     @staticmethod
     def backward(ctx, dy):
         xb, yb, V, g = ctx.saved_tensors
-        N = V.shape[0]
-        db = torch.zeros((N,), dtype=F32, device=dy.device)
-        dz = K_.act_bwd_bias(dy.contiguous(), yb if ctx.relu else None, True, db)
+        N, Np = V.shape[0], ctx.pk.w.shape[0]
+        db = torch.zeros((Np,), dtype=F32, device=dy.device)
+        dz = K_.act_bwd_bias(_pad_cols(dy, Np).contiguous(), yb if ctx.relu else None, True, db)
         dV, dg, dx = lin_bwd(xb, dz, V, g, ctx.pk, 1, ctx.need_dx, dx_f32=True)
         if dx is not None and ctx.drop is not None:
             K_.dropout_f32_(dx, ctx.drop)
-        return dx, dV, dg, db, None, None, None
+        return dx, dV, dg, db[:N], None, None, None
 
 
 # --------------------------------------------------------------------------- #

@@ -137,12 +137,18 @@ def dropout_reduce_(dxt: torch.Tensor, acc: torch.Tensor, rank_group: int, r0: i
           nbytes=2.0 * M * H * rank_group + 8.0 * M * H)
 
 
-def wn_pack(v: torch.Tensor, g: torch.Tensor, n_groups: int) -> Tuple[torch.Tensor, torch.Tensor]:
-    """v (n_groups*rows_per_group, cols) fp32, g (n_groups,) fp32 -> (W_eff bf16, sumsq fp32[n_groups])."""
+def wn_pack(v: torch.Tensor, g: torch.Tensor, n_groups: int, pad_rows_to: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:
+    """v (n_groups*rows_per_group, cols) fp32, g (n_groups,) fp32 -> (W_eff bf16, sumsq fp32[n_groups]).
+    pad_rows_to: the pack gets zero rows up to a multiple of it (output widths that are not a multiple of 8 elements
+    cannot be a TMA operand pitch in the backward GEMMs; the padded outputs are exact zeros)."""
     _req(v, F32, "wn_pack.v")
     _req(g, F32, "wn_pack.g")
     rows, cols = v.shape
-    w = torch.empty((rows, cols), dtype=BF16, device=v.device)
+    rows_p = -(-rows // pad_rows_to) * pad_rows_to
+    if rows_p != rows:
+        w = torch.zeros((rows_p, cols), dtype=BF16, device=v.device)
+    else:
+        w = torch.empty((rows, cols), dtype=BF16, device=v.device)
     sumsq = torch.empty((n_groups,), dtype=F32, device=v.device)
     _call("cti_wn_pack", _lib.load().cti_wn_pack, (v.data_ptr(), g.data_ptr(), w.data_ptr(), sumsq.data_ptr(), n_groups,
                                                    rows // n_groups, cols, _stream()), kernels=3,

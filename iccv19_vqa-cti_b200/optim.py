@@ -1,0 +1,122 @@
+"""The reference trainer's update tail as three kernel launches over all parameters:
+
+    flat_grads.div_(grad_denom); clip_grad_norm_(flat_grads, clip_norm); copy back     (src/MC/trainer.py:208-219)
+    torch.optim.Adamax(...).step()                                                      (src/MC/train.py:32, trainer.py:252-256)
+
+``FusedClipAdamax`` keeps the interface the trainer touches -- ``param_groups[0]['lr']`` (the warm-up / decay schedule
+of src/MC/train.py:59-66 writes it), ``step()``, ``zero_grad()``, ``state_dict()`` -- and adds ``grad_denom`` /
+``clip_norm`` to ``step`` so the flatten / clip / un-flatten passes disappear: gradients are read where autograd (or
+the all-reduce buckets of ``dp.GradAllReducer``) left them.  fp32 state, same arithmetic as the reference; the
+pre-clip gradient norm comes back as a device scalar (no host synchronisation inside ``step``).
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional
+
+import torch
+
+from . import _lib
+from . import kernels as K_
+
+_CHUNK = 8192          # elements per thread block
+
+
+class FusedClipAdamax:
+    def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 2e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 clip_norm: float = 0.25):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("optimizer got an empty parameter list")
+        for p in self.params:
+            if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError("FusedClipAdamax: parameters must be contiguous fp32 CUDA tensors (no CPU path)")
+        dev = self.params[0].device
+        self.param_groups = [{"params": self.params, "lr": lr, "betas": tuple(betas), "eps": eps, "clip_norm": clip_norm}]
+        self.step_count = 0
+        total = sum(p.numel() for p in self.params)
+        self._state = torch.zeros(2 * total, dtype=torch.float32, device=dev)      # exp_avg | exp_inf, flat
+        self.exp_avg, self.exp_inf, o = [], [], 0
+        for p in self.params:
+            n = p.numel()
+            self.exp_avg.append(self._state[o:o + n].view_as(p))
+            self.exp_inf.append(self._state[total + o:total + o + n].view_as(p))
+            o += n
+        chunk_tensor, chunk_start = [], []
+        for t, p in enumerate(self.params):
+            for s in range(0, p.numel(), _CHUNK):
+                chunk_tensor.append(t)
+                chunk_start.append(s)
+        self.n_chunks = len(chunk_tensor)
+        i64 = lambda xs: torch.tensor(xs, dtype=torch.int64, device=dev)
+        self._numel = i64([p.numel() for p in self.params])
+        self._chunk_tensor = torch.tensor(chunk_tensor, dtype=torch.int32, device=dev)
+        self._chunk_start = i64(chunk_start)
+        self._p_ptrs = i64([p.data_ptr() for p in self.params])
+        self._m_ptrs = i64([m.data_ptr() for m in self.exp_avg])
+        self._u_ptrs = i64([u.data_ptr() for u in self.exp_inf])
+        self._g_ptrs = torch.zeros(len(self.params), dtype=torch.int64, device=dev)
+        self._g_host = torch.zeros(len(self.params), dtype=torch.int64).pin_memory()
+        self._g_key: Optional[tuple] = None
+        self._partials = torch.empty(self.n_chunks, dtype=torch.float32, device=dev)
+        self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)            # pre-clip norm of the last step
+
+    # ------------------------------------------------------------------ #
+    def _refresh_grad_table(self) -> None:
+        grads = []
+        for p in self.params:
+            g = p.grad
+            if g is None:
+                raise RuntimeError("Model parameter did not receive gradient (reference src/MC/trainer.py:226-228)")
+            if g.dtype != torch.float32 or not g.is_contiguous():
+                raise RuntimeError("FusedClipAdamax: gradients must be contiguous fp32")
+            grads.append(g.data_ptr())
+        key = tuple(grads)
+        if key != self._g_key:                   # bucket views / graph-owned gradients keep their addresses: no copy
+            self._g_host.copy_(torch.tensor(grads, dtype=torch.int64))
+            self._g_ptrs.copy_(self._g_host, non_blocking=True)
+            self._g_key = key
+
+    @torch.no_grad()
+    def step(self, grad_denom: float = 1.0) -> torch.Tensor:
+        """p.grad / grad_denom -> clip to ``clip_norm`` by global L2 norm -> Adamax.  Returns the pre-clip norm (device)."""
+        grp = self.param_groups[0]
+        self._refresh_grad_table()
+        self.step_count += 1
+        beta1, beta2 = grp["betas"]
+        clr = grp["lr"] / (1.0 - beta1 ** self.step_count)
+        lib = _lib.load()
+        s = K_._stream()
+        n = sum(p.numel() for p in self.params)
+        K_._call("cti_grad_sumsq_multi", lib.cti_grad_sumsq_multi,
+                 (self._g_ptrs.data_ptr(), self._numel.data_ptr(), self._chunk_tensor.data_ptr(),
+                  self._chunk_start.data_ptr(), self.n_chunks, _CHUNK, self._partials.data_ptr(), self._sumsq.data_ptr(), s),
+                 kernels=2, nbytes=4.0 * n)
+        K_._call("cti_adamax_multi", lib.cti_adamax_multi,
+                 (self._p_ptrs.data_ptr(), self._g_ptrs.data_ptr(), self._m_ptrs.data_ptr(), self._u_ptrs.data_ptr(),
+                  self._numel.data_ptr(), self._chunk_tensor.data_ptr(), self._chunk_start.data_ptr(), self.n_chunks, _CHUNK,
+                  self._sumsq.data_ptr(), 1.0 / float(grad_denom), float(grp["clip_norm"]), float(clr), float(beta1),
+                  float(beta2), float(grp["eps"]), self.grad_norm.data_ptr(), s), nbytes=28.0 * n)
+        # the kernel wrote through raw pointers: tell autograd / the weight-pack caches that the parameters changed
+        torch.autograd.graph.increment_version(self.params)
+        return self.grad_norm
+
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        for p in self.params:
+            if set_to_none:
+                p.grad = None
+            elif p.grad is not None:
+                p.grad.zero_()
+
+    def state_dict(self) -> dict:
+        return {"step": self.step_count, "exp_avg": [m.clone() for m in self.exp_avg],
+                "exp_inf": [u.clone() for u in self.exp_inf],
+                "param_groups": [{k: v for k, v in self.param_groups[0].items() if k != "params"}]}
+
+    def load_state_dict(self, sd: dict) -> None:
+        self.step_count = int(sd["step"])
+        for dst, src in zip(self.exp_avg, sd["exp_avg"]):
+            dst.copy_(src)
+        for dst, src in zip(self.exp_inf, sd["exp_inf"]):
+            dst.copy_(src)
+        self.param_groups[0].update(sd["param_groups"][0])

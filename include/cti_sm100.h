@@ -104,6 +104,24 @@ int cti_masked_softmax_bwd(const float* p, const float* dp, int64_t dp_stride_b,
  * src/MC/train.py:75). */
 int cti_sum_row_groups(const void* x_bf16, void* out_bf16, int64_t groups, int rep, int64_t row_elems, void* stream);
 
+/* ---- trainer tail: gradient norm, rescale + clip + Adamax, multi-tensor ---------------------------------
+ * Tables in DEVICE memory: g_ptrs / p_ptrs / m_ptrs / u_ptrs = arrays of n_tensors device pointers (fp32 tensors of
+ * numel[t] elements: gradient, parameter, Adamax exp_avg and exp_inf); chunk c covers elements
+ * [chunk_start[c], chunk_start[c] + chunk_elems) of tensor chunk_tensor[c] (clipped to numel).
+ * cti_grad_sumsq_multi: sumsq[0] = sum over all tensors of g^2 (partials: n_chunks floats of scratch; fixed order).
+ * cti_adamax_multi: norm = sqrt(sumsq) * inv_denom -> norm_out (may be NULL); g' = g * inv_denom * coef with
+ *   coef = clip_norm / (norm + 1e-6) if norm > clip_norm > 0 else 1; m = b1 m + (1-b1) g'; u = max(b2 u, |g'| + eps);
+ *   p -= clr * m / u  (clr = lr / (1 - b1^t)).
+ * replaces: Trainer._all_reduce_and_rescale + clip_grad_norm_ + torch.optim.Adamax.step
+ *           (src/MC/trainer.py:208-219,252-256; src/utils.py:323-328; src/MC/train.py:32). */
+int cti_grad_sumsq_multi(const void* g_ptrs_dev, const int64_t* numel_dev, const int32_t* chunk_tensor_dev,
+                         const int64_t* chunk_start_dev, int n_chunks, int chunk_elems, float* partials, float* sumsq,
+                         void* stream);
+int cti_adamax_multi(const void* p_ptrs_dev, const void* g_ptrs_dev, const void* m_ptrs_dev, const void* u_ptrs_dev,
+                     const int64_t* numel_dev, const int32_t* chunk_tensor_dev, const int64_t* chunk_start_dev,
+                     int n_chunks, int chunk_elems, const float* sumsq, float inv_denom, float clip_norm, float clr,
+                     float beta1, float beta2, float eps, float* norm_out, void* stream);
+
 /* ---- trilinear logit map ----------------------------------------------------------------------
  * vc (B,K,R*16), qc (B,Q,R*16), ac (B,A,R*16) bf16: the per-rank projections, column = r*16 + i.
  * tpack (R,16,16*G*16) bf16: T_eff[r][l][(i,g,j)] (see DESIGN.md for the T_g -> T_eff permutation).

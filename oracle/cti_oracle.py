@@ -315,6 +315,38 @@ def ban_hot_path(v, q_emb, p: Params, glimpse: int):
     return joint, att, logits
 
 
+
+# --------------------------------------------------------------------------- #
+# Right after the hot path: classifier and the trainer's update tail
+# --------------------------------------------------------------------------- #
+def simple_classifier(x: torch.Tensor, p: Params, prefix: str = "classifier.") -> torch.Tensor:
+    """``SimpleClassifier.forward`` in eval mode with ``activation='relu'`` (src/classifier.py:19-28):
+    weight_norm(Linear) -> ReLU -> Dropout (identity in eval) -> weight_norm(Linear); modules main.0 and main.3."""
+    h = wn_linear(x, p, prefix + "main.0.", "ReLU")
+    return wn_linear(h, p, prefix + "main.3.", "")
+
+
+def trainer_update(params, grads, exp_avg, exp_inf, step: int, lr: float, grad_denom: float, clip_norm: float,
+                   beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8) -> float:
+    """One update of the reference trainer's tail, in place on lists of fp32 tensors; returns the pre-clip norm.
+
+    ``Trainer._all_reduce_and_rescale`` (src/MC/trainer.py:208-219): the flat gradient is divided by ``grad_denom``
+    and clipped by its global L2 norm, ``coef = clip_norm / (norm + 1e-6)`` applied only if ``norm > clip_norm > 0``
+    (``clip_grad_norm_``, src/utils.py:323-328).  Then ``torch.optim.Adamax`` (src/MC/train.py:32; third-party,
+    requirements.txt pins torch==1.1.0; Kingma & Ba 2015, algorithm 2): ``m = b1 m + (1-b1) g``,
+    ``u = max(b2 u, |g| + eps)``, ``p -= lr / (1 - b1^t) * m / u`` with t = ``step`` counted from 1."""
+    flat = torch.cat([g.reshape(-1) for g in grads]) / grad_denom
+    norm = float(flat.norm())
+    coef = clip_norm / (norm + 1e-6) if norm > clip_norm > 0 else 1.0
+    clr = lr / (1.0 - beta1 ** step)
+    for prm, g, m, u in zip(params, grads, exp_avg, exp_inf):
+        gg = g / grad_denom * coef
+        m.mul_(beta1).add_(gg, alpha=1.0 - beta1)
+        torch.maximum(u * beta2, gg.abs() + eps, out=u)
+        prm.addcdiv_(m, u, value=-clr)
+    return norm
+
+
 def distillation_loss(x, teacher, target, T: float, alpha: float) -> torch.Tensor:
     """``Distillation_Loss.forward`` (src/loss_function.py:20-25)."""
     logp = torch.log_softmax(x / T, dim=1)

@@ -1,0 +1,82 @@
+"""Golden vectors for the components right after the hot path, made by running the
+REFERENCE's own code.  Build container only (needs /root/reference, read-only):
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden_next.py
+
+Writes tests/golden/next_golden.pt:
+  * ``clf_*``   -- ``SimpleClassifier`` (src/classifier.py:11-29) forward + backward in eval mode,
+  * ``trainer`` -- three update steps of the reference trainer's tail: gradients / grad_denom, global-norm clip with
+                   ``src.utils.clip_grad_norm_`` (src/utils.py:323-328, called from src/MC/trainer.py:208-219) and
+                   ``torch.optim.Adamax`` (src/MC/train.py:32) on a handful of odd-sized parameters.
+"""
+import collections
+import collections.abc
+import os
+import sys
+import types
+import warnings
+
+import torch
+
+warnings.filterwarnings("ignore")
+sys.dont_write_bytecode = True
+REF = os.environ.get("CTI_REFERENCE", "/root/reference")
+sys.path.insert(0, REF)
+six = types.ModuleType("torch._six")
+six.string_classes = (str, bytes)
+sys.modules.setdefault("torch._six", six)
+sys.modules.setdefault("h5py", types.ModuleType("h5py"))
+collections.Mapping, collections.Sequence = collections.abc.Mapping, collections.abc.Sequence
+
+from src.classifier import SimpleClassifier  # noqa: E402
+import src.utils as ref_utils  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "next_golden.pt")
+
+
+def main():
+    out = {}
+    torch.manual_seed(5)
+    args = types.SimpleNamespace(activation="relu", dropout=0.5)
+    for name, (i, h, o, rows) in {"clf_mc": (64, 128, 2, (6,)), "clf_ffoe": (48, 96, 40, (3, 5))}.items():
+        m = SimpleClassifier(i, h, o, args).eval()
+        m.main[2].inplace = False             # in-place dropout after ReLU trips torch-2 autograd checks; same numbers
+        x = torch.randn(*rows, i, requires_grad=True)
+        y = m(x)
+        c = torch.randn(y.shape)
+        (y * c).sum().backward()
+        out[name] = {"sd": {k: t.detach().clone() for k, t in m.state_dict().items()}, "x": x.detach().clone(),
+                     "y": y.detach().clone(), "cot": c, "dx": x.grad.clone(),
+                     "grads": {k: p.grad.detach().clone() for k, p in m.named_parameters()}, "dims": (i, h, o)}
+
+    # ---- trainer tail: rescale, clip, Adamax ------------------------------------------------------
+    g = torch.Generator().manual_seed(9)
+    shapes = [(7, 33), (), (129,), (16, 16, 3), (1, 5, 1, 64), (4097,)]
+    params = [torch.nn.Parameter(torch.randn(s, generator=g)) for s in shapes]
+    opt = torch.optim.Adamax(params, lr=7e-4)                      # src/MC/train.py:32 (lr_default = 7e-4 there too)
+    clip_norm, steps = 0.25, []
+    p0 = [p.detach().clone() for p in params]
+    for step, (scale, denom) in enumerate([(3.0, 64.0), (0.01, 4.0), (50.0, 256.0)]):
+        grads = [scale * torch.randn(s, generator=g) for s in shapes]
+        for p, gr in zip(params, grads):
+            p.grad = gr.clone()
+        # Trainer._all_reduce_and_rescale (src/MC/trainer.py:208-219) on the flat buffer
+        flat = torch.cat([p.grad.view(-1) for p in params])
+        flat.div_(denom)
+        norm = ref_utils.clip_grad_norm_(flat, clip_norm)
+        off = 0
+        for p in params:
+            n = p.numel()
+            p.grad.copy_(flat[off:off + n].view_as(p.grad))
+            off += n
+        opt.step()
+        steps.append({"grads": grads, "denom": denom, "norm": float(norm),
+                      "params": [p.detach().clone() for p in params]})
+    out["trainer"] = {"shapes": shapes, "p0": p0, "lr": 7e-4, "clip_norm": clip_norm, "steps": steps,
+                      "betas": (0.9, 0.999), "eps": 1e-8}
+    torch.save(out, OUT)
+    print("wrote", OUT, os.path.getsize(OUT), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,124 @@
+"""Components right after the hot path on the B200:
+  * ``SimpleClassifier`` drop-in against the reference's golden forward / backward (tests/golden/next_golden.pt) and
+    against the oracle at the model's sizes (1024 -> 2048 -> 2 for MC, -> 3129 for FFOE/VQA),
+  * ``FusedClipAdamax`` (gradient norm, rescale, clip, Adamax in three launches) against the reference trainer's own
+    numbers (golden) bit-for-bit up to fp32 rounding, and against torch.optim.Adamax + the reference clip at size.
+"""
+import os
+import sys
+import types
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+pytestmark = pytest.mark.gpu
+
+import cti_b200  # noqa: E402
+from oracle import cti_oracle as O  # noqa: E402
+from test_gpu_modules import ABS_TOL, maxabs, normrel, rel  # noqa: E402
+
+DEV = "cuda"
+NEXT = os.path.join(ROOT, "tests", "golden", "next_golden.pt")
+ARGS = types.SimpleNamespace(activation="relu", dropout=0.5)
+
+
+@pytest.mark.parametrize("name", ["clf_mc", "clf_ffoe"])
+def test_classifier_against_reference_golden(name):
+    g = torch.load(NEXT)[name]
+    i, h, o = g["dims"]
+    m = cti_b200.SimpleClassifier(i, h, o, ARGS)
+    assert list(m.state_dict().keys()) == list(g["sd"].keys())
+    m.load_state_dict(g["sd"])
+    m.to(DEV).eval()
+    x = g["x"].to(DEV).requires_grad_(True)
+    y = m(x)
+    assert y.shape == g["y"].shape
+    assert rel(y, g["y"]) <= ABS_TOL
+    (y * g["cot"].to(DEV)).sum().backward()
+    assert normrel(x.grad, g["dx"]) <= 0.12
+    for k, p in m.named_parameters():
+        if g["grads"][k].numel() > 1:
+            assert normrel(p.grad, g["grads"][k]) <= 0.12, k
+
+
+@pytest.mark.parametrize("n_out,rows", [(2, 1024), (3129, 256)])
+def test_classifier_against_oracle_at_model_size(n_out, rows):
+    gen = torch.Generator().manual_seed(n_out)
+    m = cti_b200.SimpleClassifier(1024, 2048, n_out, ARGS)
+    params = {"classifier." + k: v.detach().clone() for k, v in m.state_dict().items()}
+    m.to(DEV).eval()
+    x = torch.randn(rows, 1024, generator=gen)
+    cot = torch.randn(rows, n_out, generator=gen)
+    pl = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    xl = x.clone().requires_grad_(True)
+    y_ref = O.simple_classifier(xl, pl)
+    (y_ref * cot).sum().backward()
+    xd = x.to(DEV).requires_grad_(True)
+    y = m(xd)
+    assert rel(y, y_ref.detach()) <= ABS_TOL
+    assert (y.argmax(1).cpu() == y_ref.argmax(1)).float().mean() >= 0.99
+    (y * cot.to(DEV)).sum().backward()
+    assert normrel(xd.grad, xl.grad) <= 0.12
+    for k, p in m.named_parameters():
+        ref = pl["classifier." + k].grad
+        if ref.numel() > 1:
+            assert normrel(p.grad, ref) <= 0.12, k
+    m.train()                                   # dropout on: still runs, and a dropped hidden unit gives zero gradient rows
+    y2 = m(xd)
+    assert torch.isfinite(y2).all() and not torch.equal(y2, y)
+
+
+def test_fused_clip_adamax_reproduces_reference_trainer_steps():
+    t = torch.load(NEXT)["trainer"]
+    params = [torch.nn.Parameter(p.clone().to(DEV)) for p in t["p0"]]
+    opt = cti_b200.FusedClipAdamax(params, lr=t["lr"], betas=t["betas"], eps=t["eps"], clip_norm=t["clip_norm"])
+    for st in t["steps"]:
+        for p, g in zip(params, st["grads"]):
+            p.grad = g.clone().to(DEV)
+        v0 = params[0]._version
+        norm = opt.step(grad_denom=st["denom"])
+        assert params[0]._version > v0                         # weight-pack caches must see the update
+        assert abs(norm.item() - st["norm"]) <= 1e-5 * max(1.0, st["norm"])
+        for p, ref in zip(params, st["params"]):
+            assert maxabs(p, ref) <= 2e-6, tuple(p.shape)      # same fp32 arithmetic up to fma contraction
+
+
+def test_fused_clip_adamax_against_torch_at_model_size_and_bucket_views():
+    """11.5 M hot-path parameters, gradients living in the all-reduce buckets of dp.GradAllReducer."""
+    from cti_b200.dp import GradAllReducer
+    torch.manual_seed(3)
+    mods = torch.nn.ModuleList([cti_b200.TriAttention(2048, 1024, 1024, 512, 1, 32, 2, 1),
+                                cti_b200.TCNet(2048, 1024, 1024, 512, 1, 32, 1, k=2)]).to(DEV)
+    params = list(mods.parameters())
+    ref_params = [torch.nn.Parameter(p.detach().clone()) for p in params]
+    ref_opt = torch.optim.Adamax(ref_params, lr=1e-3)
+    opt = cti_b200.FusedClipAdamax(params, lr=1e-3, clip_norm=0.25)
+    red = GradAllReducer(params)                                # world size 1: buckets only
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    for step, (scale, denom) in enumerate([(1.0, 256.0), (1e-4, 1.0), (10.0, 64.0)]):
+        grads = [scale * torch.randn(p.shape, device=DEV, generator=gen) for p in params]
+        for p, g in zip(params, grads):
+            p.grad = g.clone()
+        red.reduce_now()                                        # copies into the flat buckets (what DP training does)
+        for p, v in zip((q for b in red.buckets for q in b.params), (v for b in red.buckets for v in b.views)):
+            p.grad = v
+        norm = opt.step(grad_denom=denom)
+        flat = torch.cat([g.reshape(-1) for g in grads]) / denom
+        n_ref = flat.norm()
+        coef = 0.25 / (n_ref + 1e-6) if n_ref > 0.25 else 1.0
+        for rp, g in zip(ref_params, grads):
+            rp.grad = g / denom * coef
+        ref_opt.step()
+        assert abs(norm.item() - n_ref.item()) <= 1e-4 * n_ref.item()
+        for p, rp in zip(params, ref_params):
+            assert (p.detach() - rp.detach()).abs().max().item() <= 1e-6, (step, tuple(p.shape))
+
+
+def test_fused_clip_adamax_requires_gradients():
+    p = torch.nn.Parameter(torch.zeros(10, device=DEV))
+    opt = cti_b200.FusedClipAdamax([p])
+    with pytest.raises(RuntimeError, match="did not receive gradient"):
+        opt.step()

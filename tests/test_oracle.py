@@ -145,3 +145,35 @@ def test_oracle_vs_live_reference_real_dims():
     scale = l_ref[fin].abs().max()
     assert (l[fin] - l_ref[fin]).abs().max() <= 1e-5 * scale
     assert torch.allclose(p, p_ref, rtol=1e-3, atol=1e-7)
+
+
+# --------------------------------------------------------------------------- #
+# components right after the hot path (tests/golden/next_golden.pt, made by tests/golden/make_golden_next.py)
+# --------------------------------------------------------------------------- #
+NEXT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "next_golden.pt")
+
+
+@pytest.mark.parametrize("name", ["clf_mc", "clf_ffoe"])
+def test_simple_classifier_matches_reference(name):
+    g = torch.load(NEXT)[name]
+    params = {"classifier." + k: v.clone().requires_grad_(True) for k, v in g["sd"].items()}
+    x = g["x"].clone().requires_grad_(True)
+    y = O.simple_classifier(x, params)
+    assert (y - g["y"]).abs().max() < 1e-5
+    (y * g["cot"]).sum().backward()
+    assert (x.grad - g["dx"]).abs().max() < 1e-5
+    for k, ref in g["grads"].items():
+        assert (params["classifier." + k].grad - ref).abs().max() <= 1e-5 * max(1.0, ref.abs().max().item()), k
+
+
+def test_trainer_update_matches_reference_clip_and_adamax():
+    t = torch.load(NEXT)["trainer"]
+    params = [p.clone() for p in t["p0"]]
+    m = [torch.zeros_like(p) for p in params]
+    u = [torch.zeros_like(p) for p in params]
+    for i, st in enumerate(t["steps"]):
+        norm = O.trainer_update(params, st["grads"], m, u, i + 1, t["lr"], st["denom"], t["clip_norm"], *t["betas"],
+                                t["eps"])
+        assert abs(norm - st["norm"]) <= 1e-5 * max(1.0, st["norm"])
+        for p, ref in zip(params, st["params"]):
+            assert (p - ref).abs().max() < 1e-6
