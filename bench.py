@@ -430,6 +430,40 @@ def run_b200(args):
         ms_f, _, _ = timed(run_fwd, args.steps)
         fwd = {"value": world * B * args.steps / (ms_f / 1e3), "unit": UNIT, "ms_per_step": ms_f / args.steps}
 
+    # ---- trainer tail on the hot path's parameters: fused clip + Adamax vs the reference's sequence (rank 0) -------
+    tail = None
+    if rank == 0 and not args.resident_only:
+        try:
+            resident_step()                                     # leaves eager gradients in p.grad
+            gparams = [p for p in params if p.grad is not None]
+            n_el = sum(p.numel() for p in gparams)
+            fused = cti_b200.FusedClipAdamax(gparams, lr=1e-3, clip_norm=0.25)
+            ms_fused, _, _ = timed(lambda: fused.step(grad_denom=float(B)), args.steps)
+            ref_opt = torch.optim.Adamax(gparams, lr=1e-3)
+
+            def ref_tail():                                     # src/MC/trainer.py:208-219 + optimizer.step()
+                flat = torch.cat([p.grad.reshape(-1) for p in gparams])
+                flat.div_(float(B))
+                norm = flat.norm()
+                flat.mul_(torch.clamp(0.25 / (norm + 1e-6), max=1.0))
+                off = 0
+                for p in gparams:
+                    p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
+                    off += p.numel()
+                ref_opt.step()
+            for _ in range(2):
+                ref_tail()
+            ms_ref, _, _ = timed(ref_tail, max(3, args.steps // 4))
+            peaks_ = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+                os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+            bw = peaks_.get("hbm_gbs", 6650.0)
+            gbs = 32.0 * n_el / (ms_fused / args.steps * 1e-3) / 1e9
+            tail = {"params": n_el, "fused_ms": ms_fused / args.steps, "bytes_per_param": 32, "gbs": gbs,
+                    "frac_of_hbm_peak": gbs / bw, "torch_sequence_ms": ms_ref / max(3, args.steps // 4),
+                    "note": "rescale + global-norm clip + Adamax over the hot path's parameters; not part of `value`"}
+        except Exception as exc:
+            tail = {"failed": repr(exc)[:200]}
+
     # ---- per-kernel CUDA-event timing of the same step (rank 0) -----------------
     roofline, kernels = None, None
     if rank == 0 and not args.no_profile:
@@ -495,7 +529,7 @@ def run_b200(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": dict(workload_config(B, world), launch="cuda_graph_replay" if use_graph else "eager"),
                 "eager": eager_ms, "e2e": e2e, "gpu_launches": launches, "gpu_launches_per_step": launches_per_step, "clocks": clocks,
-                "fwd_only": fwd, "shared_v": shared, "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels}
+                "fwd_only": fwd, "shared_v": shared, "trainer_tail": tail, "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -28,6 +28,7 @@ SIGNATURES = {
     "cti_grad_sumsq_multi": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, _P, _P]),
     "cti_adamax_multi": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P, c_float, c_float, c_float, c_float, c_float,
                                  c_float, _P, _P]),
+    "cti_wn_scratch_floats": (c_size_t, [c_int, c_int, c_int]),
     "cti_wn_pack": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "cti_wn_grad": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "cti_gemm_bf16": (c_int, [_P, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_float, _P, c_int, _P, c_int,

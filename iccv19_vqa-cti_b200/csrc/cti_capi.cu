@@ -70,6 +70,10 @@ int cti_dropout_reduce(const void* dxt, float* acc, int64_t rows, int cols, int 
                              static_cast<cudaStream_t>(stream));
 }
 
+size_t cti_wn_scratch_floats(int n_groups, int rows_per_group, int cols) {
+  return cti::wn_scratch_floats(n_groups, rows_per_group, cols);
+}
+
 int cti_wn_pack(const float* v, const float* g, void* w_eff_bf16, float* sumsq, int n_groups, int rows_per_group,
                 int cols, void* stream) {
   return cti::wn_pack(v, g, static_cast<__nv_bfloat16*>(w_eff_bf16), sumsq, n_groups, rows_per_group, cols,

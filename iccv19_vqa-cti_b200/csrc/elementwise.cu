@@ -206,23 +206,45 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ v,
   }
 }
 
-// acc[group] = sum of the group's segment partials, in a fixed order (one warp per group).
-__global__ void __launch_bounds__(32) sum_partials_kernel(const float* __restrict__ partial, float* __restrict__ acc,
-                                                          int segs_per_group) {
-  const float* p = partial + static_cast<long>(blockIdx.x) * segs_per_group;
+// Total of one group's segment partials, computed redundantly (and identically) by every consumer block instead of
+// by a third launch: the block reduces the partials of the group its first element belongs to; a thread whose element
+// lies in a later group (only when a group is smaller than, or not aligned to, the block's 1024 elements) sums its
+// group's partials itself.  Fixed summation order: the same weights always give the same norm.
+__device__ __forceinline__ float group_total(const float* __restrict__ partial, int segs, int block_group, int my_group,
+                                             float* sh /* 9 floats */) {
+  const float* p = partial + static_cast<long>(block_group) * segs;
   float s = 0.f;
-  for (int i = threadIdx.x; i < segs_per_group; i += 32) s += p[i];
+  for (int i = threadIdx.x; i < segs; i += 256) s += p[i];
   s = warp_sum(s);
-  if (threadIdx.x == 0) acc[blockIdx.x] = s;
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    sh[8] = t;
+  }
+  __syncthreads();
+  if (my_group == block_group) return sh[8];
+  const float* q = partial + static_cast<long>(my_group) * segs;
+  float t = 0.f;
+  for (int i = 0; i < segs; ++i) t += q[i];
+  return t;
 }
 
 __global__ void __launch_bounds__(256) wn_scale_kernel(const float* __restrict__ v, const float* __restrict__ g,
-                                                       const float* __restrict__ sumsq, __nv_bfloat16* __restrict__ w,
-                                                       long group_elems, long total) {
-  const long i = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
-  if (i >= total) return;
+                                                       float* __restrict__ sumsq, const float* __restrict__ partial, int segs,
+                                                       __nv_bfloat16* __restrict__ w, long group_elems, long total) {
+  __shared__ float sh[9];
+  const long i0 = static_cast<long>(blockIdx.x) * 1024;
+  long i = i0 + threadIdx.x * 4;
+  const bool live = i < total;
+  if (!live) i = total - 4;
   const int group = static_cast<int>(i / group_elems);   // group_elems % 4 == 0 is required by the caller
-  const float s = g[group] * rsqrtf(sumsq[group]);
+  const float n2 = group_total(partial, segs, static_cast<int>(i0 / group_elems), group, sh);
+  if (!live) return;
+  if (i % group_elems == 0) sumsq[group] = n2;            // kept for the backward of the fold
+  const float s = g[group] * rsqrtf(n2);
   const float4 f = *reinterpret_cast<const float4*>(v + i);
   uint2 u;
   u.x = pack_bf16x2(f.x * s, f.y * s);
@@ -232,15 +254,19 @@ __global__ void __launch_bounds__(256) wn_scale_kernel(const float* __restrict__
 
 __global__ void __launch_bounds__(256) wn_grad_kernel(const float* __restrict__ dw, const float* __restrict__ v,
                                                       const float* __restrict__ g, const float* __restrict__ sumsq,
-                                                      const float* __restrict__ dot, float* __restrict__ dv,
+                                                      const float* __restrict__ partial, int segs, float* __restrict__ dv,
                                                       float* __restrict__ dg, long group_elems, long total) {
-  const long i = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
-  if (i >= total) return;
+  __shared__ float sh[9];
+  const long i0 = static_cast<long>(blockIdx.x) * 1024;
+  long i = i0 + threadIdx.x * 4;
+  const bool live = i < total;
+  if (!live) i = total - 4;
   const int group = static_cast<int>(i / group_elems);
+  const float dt = group_total(partial, segs, static_cast<int>(i0 / group_elems), group, sh);   // <dW_eff, V>
+  if (!live) return;
   const float n2 = sumsq[group];
   const float rn = rsqrtf(n2);
   const float s = g[group] * rn;          // g / ||V||
-  const float dt = dot[group];            // <dW_eff, V>
   const float c = dt / n2;
   const float4 a = *reinterpret_cast<const float4*>(dw + i);
   const float4 b = *reinterpret_cast<const float4*>(v + i);
@@ -388,6 +414,12 @@ int dropout_reduce(const __nv_bfloat16* dxt, float* acc, long rows, int cols, in
   return check_launch("dropout_reduce_kernel");
 }
 
+size_t wn_scratch_floats(int n_groups, int rows_per_group, int cols) {
+  const long ge = static_cast<long>(rows_per_group) * cols;
+  return static_cast<size_t>(n_groups) * (1 + (ge + kSeg - 1) / kSeg);
+}
+
+// sumsq: wn_scratch_floats() floats -- [0, n_groups) the squared norms (output), the rest per-segment partial sums.
 int wn_pack(const float* v, const float* g, __nv_bfloat16* w, float* sumsq, int n_groups, int rows_per_group, int cols,
             cudaStream_t s) {
   const long ge = static_cast<long>(rows_per_group) * cols;
@@ -395,31 +427,26 @@ int wn_pack(const float* v, const float* g, __nv_bfloat16* w, float* sumsq, int 
   CTI_REQUIRE(n_groups > 0 && ge > 0, "wn_pack: empty weight");
   CTI_REQUIRE(ge % 4 == 0, "wn_pack: group size %ld must be a multiple of 4", ge);
   const int segs = (int)((ge + kSeg - 1) / kSeg);
-  float* partial = reinterpret_cast<float*>(w);      // the output buffer doubles as scratch until wn_scale overwrites it
+  float* partial = sumsq + n_groups;
   sumsq_kernel<<<n_groups * segs, 256, 0, s>>>(v, v, partial, ge, segs);
   int rc = check_launch("sumsq_kernel");
   if (rc) return rc;
-  sum_partials_kernel<<<n_groups, 32, 0, s>>>(partial, sumsq, segs);
-  rc = check_launch("sum_partials_kernel");
-  if (rc) return rc;
-  wn_scale_kernel<<<(unsigned)((total / 4 + 255) / 256), 256, 0, s>>>(v, g, sumsq, w, ge, total);
+  wn_scale_kernel<<<(unsigned)((total + 1023) / 1024), 256, 0, s>>>(v, g, sumsq, partial, segs, w, ge, total);
   return check_launch("wn_scale_kernel");
 }
 
+// dot_ws: wn_scratch_floats() floats of scratch.
 int wn_grad(const float* dw, const float* v, const float* g, const float* sumsq, float* dv, float* dg, float* dot_ws,
             int n_groups, int rows_per_group, int cols, cudaStream_t s) {
   const long ge = static_cast<long>(rows_per_group) * cols;
   const long total = ge * n_groups;
   CTI_REQUIRE(n_groups > 0 && ge > 0 && ge % 4 == 0, "wn_grad: bad group size %ld", ge);
   const int segs = (int)((ge + kSeg - 1) / kSeg);
-  float* partial = dv;                               // scratch until wn_grad_kernel overwrites it
+  float* partial = dot_ws + n_groups;
   sumsq_kernel<<<n_groups * segs, 256, 0, s>>>(dw, v, partial, ge, segs);
   int rc = check_launch("wn_dot_kernel");
   if (rc) return rc;
-  sum_partials_kernel<<<n_groups, 32, 0, s>>>(partial, dot_ws, segs);
-  rc = check_launch("sum_partials_kernel");
-  if (rc) return rc;
-  wn_grad_kernel<<<(unsigned)((total / 4 + 255) / 256), 256, 0, s>>>(dw, v, g, sumsq, dot_ws, dv, dg, ge, total);
+  wn_grad_kernel<<<(unsigned)((total + 1023) / 1024), 256, 0, s>>>(dw, v, g, sumsq, partial, segs, dv, dg, ge, total);
   return check_launch("wn_grad_kernel");
 }
 

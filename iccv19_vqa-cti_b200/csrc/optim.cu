@@ -22,9 +22,12 @@ grad_sumsq_multi_kernel(const float* const* __restrict__ g_ptrs, const long* __r
   const long hi = min(lo + chunk_elems, numel[t]);
   const float* g = g_ptrs[t];
   float s = 0.f;
-  for (long i = lo + threadIdx.x; i < hi; i += 256) {
-    const float x = g[i];
-    s = fmaf(x, x, s);
+  for (long base = lo + threadIdx.x; base < hi; base += 4 * 256) {      // four independent loads in flight per thread
+    float x[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) x[k] = (base + k * 256 < hi) ? g[base + k * 256] : 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s = fmaf(x[k], x[k], s);
   }
   s = warp_sum(s);
   __shared__ float part[8];
@@ -70,13 +73,29 @@ adamax_multi_kernel(float* const* __restrict__ p_ptrs, const float* const* __res
   float* m = m_ptrs[t];
   float* u = u_ptrs[t];
   const float omb1 = 1.f - beta1;
-  for (long i = lo + threadIdx.x; i < hi; i += 256) {
-    const float gg = g[i] * scale;
-    const float mi = fmaf(omb1, gg - m[i], m[i]);            // exp_avg.lerp_(grad, 1 - beta1)
-    const float ui = fmaxf(u[i] * beta2, fabsf(gg) + eps);   // exp_inf = max(beta2 * exp_inf, |grad| + eps)
-    m[i] = mi;
-    u[i] = ui;
-    p[i] = p[i] - clr * (mi / ui);                           // param.addcdiv_(exp_avg, exp_inf, value=-clr)
+  for (long base = lo + threadIdx.x; base < hi; base += 4 * 256) {      // 16 independent loads in flight per thread
+    float gv[4], mv[4], uv[4], pv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long i = base + k * 256;
+      const bool ok = i < hi;
+      gv[k] = ok ? g[i] : 0.f;
+      mv[k] = ok ? m[i] : 0.f;
+      uv[k] = ok ? u[i] : 1.f;
+      pv[k] = ok ? p[i] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long i = base + k * 256;
+      if (i < hi) {
+        const float gg = gv[k] * scale;
+        const float mi = fmaf(omb1, gg - mv[k], mv[k]);            // exp_avg.lerp_(grad, 1 - beta1)
+        const float ui = fmaxf(uv[k] * beta2, fabsf(gg) + eps);    // exp_inf = max(beta2 * exp_inf, |grad| + eps)
+        m[i] = mi;
+        u[i] = ui;
+        p[i] = pv[k] - clr * (mi / ui);                            // param.addcdiv_(exp_avg, exp_inf, value=-clr)
+      }
+    }
   }
 }
 

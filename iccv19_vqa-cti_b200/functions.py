@@ -93,18 +93,32 @@ def cast_in(x2d: torch.Tensor, drop):
     return K_.cast_rows(x2d)[0] if drop is None else K_.cast_rows_dropout(x2d, drop)[0]
 
 
+def zero_slab(device, shapes: Sequence[Tuple[int, ...]]) -> List[torch.Tensor]:
+    """fp32 zero tensors of the given shapes carved out of ONE allocation / ONE fill kernel (the split-K accumulators
+    and bias-gradient sums of a whole backward call; each is 16-byte aligned for the TMA reduce-add)."""
+    sizes = [-(-int(torch.Size(sh).numel()) // 4) * 4 for sh in shapes]
+    slab = torch.zeros((sum(sizes),), dtype=F32, device=device)
+    out, o = [], 0
+    for sh, n in zip(shapes, sizes):
+        out.append(slab[o:o + int(torch.Size(sh).numel())].view(sh))
+        o += n
+    return out
+
+
 def lin_bwd(x: torch.Tensor, dz: torch.Tensor, V: torch.Tensor, g: torch.Tensor, pk: Packed, n_groups: int,
             need_dx: bool, dx_relu_aux: Optional[torch.Tensor] = None, dx_f32: bool = False, alpha: float = 1.0,
-            dx_alpha: float = 1.0):
+            dx_alpha: float = 1.0, dw: Optional[torch.Tensor] = None):
     """Backward of one layer group given the pre-activation gradient dz (M, N) bf16.
-    Returns dV (like V), dg (like g), dx (bf16 masked by dx_relu_aux > 0, or fp32) or None."""
+    Returns dV (like V), dg (like g), dx (bf16 masked by dx_relu_aux > 0, or fp32) or None.
+    dw: optional zeroed (N, K_in) fp32 accumulator (see zero_slab)."""
     M, Kin = x.shape
     N = dz.shape[1]
     # wgrad: dW_eff[N, K_in] = dz^T x  -- both operands MN-major, split over the row (reduction) dimension
     tile_n = 256 if Kin >= 256 else 128
     tiles = -(-N // 128) * -(-Kin // tile_n)
     splits = _pick_splits(tiles, -(-M // 64))
-    dw = torch.zeros((N, Kin), dtype=F32, device=x.device)
+    if dw is None:
+        dw = torch.zeros((N, Kin), dtype=F32, device=x.device)
     K_.gemm(dz, x, N, Kin, M, a_mn=True, b_mn=True, accum_f32=dw, k_splits=splits, tile_n=tile_n, alpha=alpha)
     dV, dg = K_.wn_grad(dw[:V.shape[0]], V.detach().contiguous(), g.detach().reshape(n_groups).contiguous(), pk.sumsq,
                         n_groups)
@@ -173,8 +187,9 @@ def rank_proj_bwd(y: torch.Tensor, dz: torch.Tensor, V: torch.Tensor, g: torch.T
     return dV, dg.reshape(g.shape), acc
 
 
-def _colsum(dz: torch.Tensor, n: int) -> torch.Tensor:
-    db = torch.zeros((n,), dtype=F32, device=dz.device)
+def _colsum(dz: torch.Tensor, n: int, db: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if db is None:
+        db = torch.zeros((n,), dtype=F32, device=dz.device)
     K_.act_bwd_bias(dz, None, False, db)
     return db
 
@@ -305,20 +320,23 @@ class TriLogitsFn(Function):
         sc = lambda d: 1.0 if d is None else 1.0 / (1.0 - d[0])
         H = yv.shape[1]
 
-        def rank_nets_bwd(y, dz, V, g, pki, drop):
+        # every split-K accumulator and bias-gradient sum of this call: one allocation, one fill kernel
+        RD = R * 16
+        zs = zero_slab(yv.device, [(RD, H)] * 3 + [(H,)] * 3 + [(H, v_bf16.shape[1]), (H, xq.shape[1]), (H, xa.shape[1])])
+
+        def rank_nets_bwd(y, dz, V, g, pki, drop, dw_, db_):
             """-> dV, dg, pre-activation gradient of the tucker layer (bf16) and its bias gradient"""
             if drop is not None and ctx.independent:
                 dV_, dg_, acc = rank_proj_bwd(y, dz, V, g, pki, drop, R)
-                db = torch.zeros((H,), dtype=F32, device=y.device)
-                return dV_, dg_, K_.act_bwd_bias(acc, y, True, db), db
-            dV_, dg_, dzt = lin_bwd(y, dz, V, g, pki, R, True, dx_relu_aux=y, dx_alpha=sc(drop))
-            return dV_, dg_, dzt, _colsum(dzt, H)
-        dVvn, dgvn, dzvt, dbvt = rank_nets_bwd(yv, dzv, w[9], w[10], pk[3], dvn)
-        dVqn, dgqn, dzqt, dbqt = rank_nets_bwd(yq, dzq, w[12], w[13], pk[4], dqn)
-        dVan, dgan, dzat, dbat = rank_nets_bwd(ya, dza, w[15], w[16], pk[5], dan)
-        dVvt, dgvt, _ = lin_bwd(v_bf16, dzvt, w[0], w[1], pk[0], 1, False)
-        dVqt, dgqt, dq = lin_bwd(xq, dzqt, w[3], w[4], pk[1], 1, ctx.need[0], dx_f32=True)
-        dVat, dgat, da = lin_bwd(xa, dzat, w[6], w[7], pk[2], 1, ctx.need[1], dx_f32=True)
+                return dV_, dg_, K_.act_bwd_bias(acc, y, True, db_), db_
+            dV_, dg_, dzt = lin_bwd(y, dz, V, g, pki, R, True, dx_relu_aux=y, dx_alpha=sc(drop), dw=dw_)
+            return dV_, dg_, dzt, _colsum(dzt, H, db_)
+        dVvn, dgvn, dzvt, dbvt = rank_nets_bwd(yv, dzv, w[9], w[10], pk[3], dvn, zs[0], zs[3])
+        dVqn, dgqn, dzqt, dbqt = rank_nets_bwd(yq, dzq, w[12], w[13], pk[4], dqn, zs[1], zs[4])
+        dVan, dgan, dzat, dbat = rank_nets_bwd(ya, dza, w[15], w[16], pk[5], dan, zs[2], zs[5])
+        dVvt, dgvt, _ = lin_bwd(v_bf16, dzvt, w[0], w[1], pk[0], 1, False, dw=zs[6])
+        dVqt, dgqt, dq = lin_bwd(xq, dzqt, w[3], w[4], pk[1], 1, ctx.need[0], dx_f32=True, dw=zs[7])
+        dVat, dgat, da = lin_bwd(xa, dzat, w[6], w[7], pk[2], 1, ctx.need[1], dx_f32=True, dw=zs[8])
         dT = unpack_core_grad(dtpack, T_g)
         if dq is not None:
             if dq_drop is not None:
@@ -438,12 +456,13 @@ class PoolFn(Function):
         pk = ctx.pk
         dzv, dzq, dza, dbv, dbq, dba, dw = K_.tri_pool_bwd(vp, qp, ap, wd, wd.stride(0), dout.contiguous(), B, K, Q, A,
                                                           C, ctx.vr)
-        dVv, dgv, _ = lin_bwd(v_bf16, dzv, w[0], w[1], pk[0], 1, False)
-        dVq, dgq, dq = lin_bwd(xq, dzq, w[3], w[4], pk[1], 1, ctx.need[0], dx_f32=True)
+        zs = zero_slab(vp.device, [(C, v_bf16.shape[1]), (C, xq.shape[1])] + ([(C, xa.shape[1])] if A > 0 else []))
+        dVv, dgv, _ = lin_bwd(v_bf16, dzv, w[0], w[1], pk[0], 1, False, dw=zs[0])
+        dVq, dgq, dq = lin_bwd(xq, dzq, w[3], w[4], pk[1], 1, ctx.need[0], dx_f32=True, dw=zs[1])
         grads = [dVv, dgv, dbv, dVq, dgq, dbq]
         da = None
         if A > 0:
-            dVa, dga, da = lin_bwd(xa, dza, w[6], w[7], pk[2], 1, ctx.need[1], dx_f32=True)
+            dVa, dga, da = lin_bwd(xa, dza, w[6], w[7], pk[2], 1, ctx.need[1], dx_f32=True, dw=zs[2])
             grads += [dVa, dga, dba]
             if da is not None:
                 if ctx.drops[1] is not None:

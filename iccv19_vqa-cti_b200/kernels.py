@@ -149,11 +149,11 @@ def wn_pack(v: torch.Tensor, g: torch.Tensor, n_groups: int, pad_rows_to: int = 
         w = torch.zeros((rows_p, cols), dtype=BF16, device=v.device)
     else:
         w = torch.empty((rows, cols), dtype=BF16, device=v.device)
-    sumsq = torch.empty((n_groups,), dtype=F32, device=v.device)
-    _call("cti_wn_pack", _lib.load().cti_wn_pack, (v.data_ptr(), g.data_ptr(), w.data_ptr(), sumsq.data_ptr(), n_groups,
-                                                   rows // n_groups, cols, _stream()), kernels=3,
-          nbytes=10.0 * rows * cols)
-    return w, sumsq
+    lib = _lib.load()
+    sumsq = torch.empty((lib.cti_wn_scratch_floats(n_groups, rows // n_groups, cols),), dtype=F32, device=v.device)
+    _call("cti_wn_pack", lib.cti_wn_pack, (v.data_ptr(), g.data_ptr(), w.data_ptr(), sumsq.data_ptr(), n_groups,
+                                           rows // n_groups, cols, _stream()), kernels=2, nbytes=10.0 * rows * cols)
+    return w, sumsq[:n_groups]
 
 
 def wn_grad(dw: torch.Tensor, v: torch.Tensor, g: torch.Tensor, sumsq: torch.Tensor,
@@ -163,10 +163,11 @@ def wn_grad(dw: torch.Tensor, v: torch.Tensor, g: torch.Tensor, sumsq: torch.Ten
     rows, cols = v.shape
     dv = torch.empty_like(v)
     dg = torch.empty((n_groups,), dtype=F32, device=v.device)
-    ws = torch.empty((n_groups,), dtype=F32, device=v.device)
-    _call("cti_wn_grad", _lib.load().cti_wn_grad,
+    lib = _lib.load()
+    ws = torch.empty((lib.cti_wn_scratch_floats(n_groups, rows // n_groups, cols),), dtype=F32, device=v.device)
+    _call("cti_wn_grad", lib.cti_wn_grad,
           (dw.data_ptr(), v.data_ptr(), g.data_ptr(), sumsq.data_ptr(), dv.data_ptr(), dg.data_ptr(), ws.data_ptr(),
-           n_groups, rows // n_groups, cols, _stream()), kernels=3, nbytes=20.0 * rows * cols)
+           n_groups, rows // n_groups, cols, _stream()), kernels=2, nbytes=20.0 * rows * cols)
     return dv, dg
 
 

@@ -62,11 +62,15 @@ int cti_dropout_reduce(const void* dxt, float* acc, int64_t rows, int cols, int 
 /* ---- weight-norm fold ----------------------------------------------------------------------
  * A matrix of n_groups stacked nn.Linear weights, each (rows_per_group, cols), each with its own
  * scalar g:  sumsq[i] = ||V_i||_F^2,  W_eff_i = bf16(V_i * g_i / ||V_i||_F).  The norm is reduced in a fixed order
- * (no atomics): equal weights give bit-equal packs.  w_eff_bf16 / dv double as scratch before they are written.
+ * (no atomics): equal weights give bit-equal packs.  `sumsq` (and `dot_ws` of the backward) must hold
+ * cti_wn_scratch_floats(...) floats: the first n_groups are the result, the rest per-segment partial sums that every
+ * consumer block re-reduces itself (two launches per call instead of three).
  * replaces: torch.nn.utils.weight_norm(nn.Linear, dim=None) as used by src/fc.py:22,27. */
+size_t cti_wn_scratch_floats(int n_groups, int rows_per_group, int cols);
 int cti_wn_pack(const float* v, const float* g, void* w_eff_bf16, float* sumsq, int n_groups, int rows_per_group,
                 int cols, void* stream);
-/* Backward of the fold: given dW_eff (fp32) returns dV and dg.  dot_ws: n_groups floats of scratch. */
+/* Backward of the fold: given dW_eff (fp32) returns dV and dg.  dot_ws: cti_wn_scratch_floats() floats of scratch;
+ * sumsq: the buffer cti_wn_pack filled. */
 int cti_wn_grad(const float* dw_eff, const float* v, const float* g, const float* sumsq, float* dv, float* dg,
                 float* dot_ws, int n_groups, int rows_per_group, int cols, void* stream);
 
