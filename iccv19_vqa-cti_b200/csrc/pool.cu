@@ -32,7 +32,7 @@ namespace {
 using bf16 = __nv_bfloat16;
 
 constexpr int kThreads = 384;                 // forward
-constexpr int kThreadsBwd = 640;              // backward: warps 12-15 handle dV / dw, warps 16-19 share the Z epilogue (odd chunks)
+constexpr int kThreadsBwd = 768;              // backward: warps 12-15 and 20-23 split the dV epilogue (12-15 also dw), warps 16-19 share the Z epilogue (odd chunks)
 constexpr int kEpiWarp0 = 4;
 constexpr int kBuildWarp0 = 8;
 constexpr int CCH = 128;                       // channels per chunk = TMEM lanes
@@ -106,7 +106,7 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < V_STAGES; ++s) {
       mbar_init(bar(B_VFULL + s), 1);
-      mbar_init(bar(B_VEMPTY + s), BWD ? 9 : 5);      // MMA commit + every epilogue warp that reads the stage
+      mbar_init(bar(B_VEMPTY + s), BWD ? 13 : 5);     // MMA commit + every epilogue warp that reads the stage
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar(B_WFULL + s), 128);
@@ -116,7 +116,7 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ 
       mbar_init(bar(B_KFULL + s), 4);
       mbar_init(bar(B_KEMPTY + s), 1);
       mbar_init(bar(B_DFULL + s), 1);
-      mbar_init(bar(B_DEMPTY + s), 4);
+      mbar_init(bar(B_DEMPTY + s), 8);
     }
     mbar_init(bar(B_DWFULL), 1);
     mbar_init(bar(B_DWEMPTY), 4);
@@ -287,14 +287,17 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ 
       s.dout = BWD ? ld_shared_f32(st + ST_DO + cl * 4) : 0.f;
     };
 
-    auto epi_b = [&](int h) {          // dV of chunk h: ReLU mask from the V tile, dzv, bias gradient; then dw
+    // two warp groups split the token blocks of the dV tile (the slowest stage of the pipeline: 64 masked 2-byte
+    // stores per thread and chunk); group 0 also drains the sample's dw tile
+    auto epi_b = [&](int h, int half) {          // dV of chunk h: ReLU mask from the V tile, dzv, bias gradient; then dw
       const int sl = h / p.nchunks, ch = h % p.nchunks;
       const int b = blockIdx.x + sl * gridDim.x, c = ch * CCH + cl;
       mbar_wait(bar(B_DFULL + (h & 1)), (h >> 1) & 1);
       tcgen05_fence_after();
       const uint32_t vst = sV + (h % V_STAGES) * V_STAGE_BYTES + (cl >> 6) * (KP * 128);
       float colsum = 0.f;
-      for (int kk = 0; kk < ktok; ++kk) {
+      const int kk_mid = (ktok + 1) >> 1;
+      for (int kk = half ? kk_mid : 0; kk < (half ? ktok : kk_mid); ++kk) {
         uint32_t r[16];
         tmem_ld_32x32b_x16(tmem_base + lane_addr + TM_DV + (h & 1) * 64 + kk * 16, r);
         tmem_wait_ld();
@@ -309,14 +312,14 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ 
           }
         }
       }
-      db_acc[c] += colsum;
+      atomicAdd(db_acc + c, colsum);         // the two groups own the same channel
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(bar(B_DEMPTY + (h & 1)));
         mbar_arrive(bar(B_VEMPTY + h % V_STAGES));
       }
-      if (ch == p.nchunks - 1) {       // the sample's dw tile is complete: lane = token
+      if (half == 0 && ch == p.nchunks - 1) {       // the sample's dw tile is complete: lane = token
         mbar_wait(bar(B_DWFULL), sl & 1);
         tcgen05_fence_after();
         const int k = cl;
@@ -336,10 +339,11 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ 
       }
     };
 
-    if (BWD && warp >= 12 && warp < 16) {
+    if (BWD && ((warp >= 12 && warp < 16) || warp >= 20)) {
+      const int half = warp >= 20 ? 1 : 0;
       for (int h = 0; h < total; ++h) {
         mbar_wait(bar(B_VFULL + h % V_STAGES), (h / V_STAGES) & 1);      // TMA data of the stage visible to this thread
-        epi_b(h);
+        epi_b(h, half);
       }
     } else {
     Side cur;
