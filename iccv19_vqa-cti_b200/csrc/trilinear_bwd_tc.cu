@@ -355,40 +355,13 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
       }
     }
   } else if (warp < 12) {
-    // ------------------------------ G2: D^T -> D tile [q][(a,g,i)];  M -> M tile [i][(a,g,q16)] -------
+    // ------------------------------ G2: M (TMEM) -> M tile [i][(a,g,q16)].  (The D^T -> D tile conversion used to
+    // live here too and made this group the busiest stage of the pipeline; it now runs on the E1 warps, which
+    // otherwise wait for B1 most of the time.) -------
     const int qd = warp & 3, L = qd * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
     for (int u = 0; u < U; ++u) {
       const int slot = u & 1;
-      {   // C3
-        mbar_wait(bar(A_B2FULL + slot), (u >> 1) & 1);
-        tcgen05_fence_after();
-        mbar_wait(bar(A_DEMPTY + slot), ((u >> 1) & 1) ^ 1);
-        const uint32_t dt = sD + slot * D_BYTES;
-        for (int t = 0; t < ntn; ++t) {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(tmem_base + lane_addr + TM_B2 + slot * 32 + t * 16, v);
-          tmem_wait_ld();
-          const int n = t * 128 + L;
-          if (n < p.N) {
-            const int ag = n >> 4, q = n & 15;
-            uint32_t pk[8];
-#pragma unroll
-            for (int x = 0; x < 8; ++x) pk[x] = pack_bf16x2(__uint_as_float(v[2 * x]), __uint_as_float(v[2 * x + 1]));
-            const uint32_t tile = dt + (ag >> 2) * 2048u;
-            const uint32_t c0 = (ag & 3) * 16;
-            st_shared_v4(tile + sw128_off(q, c0), pk[0], pk[1], pk[2], pk[3]);
-            st_shared_v4(tile + sw128_off(q, c0 + 8), pk[4], pk[5], pk[6], pk[7]);
-          }
-        }
-        fence_proxy_async_smem();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(bar(A_DFULL + slot));
-          mbar_arrive(bar(A_B2EMPTY + slot));
-        }
-      }
       {   // C2
         mbar_wait(bar(A_F2FULL + slot), (u >> 1) & 1);
         tcgen05_fence_after();
@@ -445,6 +418,35 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
           out[2 * x] = f0.x; out[2 * x + 1] = f0.y; out[8 + 2 * x] = f1.x; out[8 + 2 * x + 1] = f1.y;
         }
       };
+      if (do_e1) {   // C3: D^T (TMEM) -> D tile [q][(a,g,i)]; B2 runs ahead of the chain, so this is ready early
+        mbar_wait(bar(A_B2FULL + slot), (u >> 1) & 1);
+        tcgen05_fence_after();
+        mbar_wait(bar(A_DEMPTY + slot), ((u >> 1) & 1) ^ 1);
+        const uint32_t dt = sD + slot * D_BYTES;
+        for (int t = 0; t < ntn; ++t) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(tmem_base + lane_addr + TM_B2 + slot * 32 + t * 16, v);
+          tmem_wait_ld();
+          const int n = t * 128 + L;
+          if (n < p.N) {
+            const int ag = n >> 4, q = n & 15;
+            uint32_t pk[8];
+#pragma unroll
+            for (int x = 0; x < 8; ++x) pk[x] = pack_bf16x2(__uint_as_float(v[2 * x]), __uint_as_float(v[2 * x + 1]));
+            const uint32_t tile = dt + (ag >> 2) * 2048u;
+            const uint32_t c0 = (ag & 3) * 16;
+            st_shared_v4(tile + sw128_off(q, c0), pk[0], pk[1], pk[2], pk[3]);
+            st_shared_v4(tile + sw128_off(q, c0 + 8), pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+        fence_proxy_async_smem();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(bar(A_DFULL + slot));
+          mbar_arrive(bar(A_B2EMPTY + slot));
+        }
+      }
       if (do_e1) {   // E1: dVc[k, i]
         mbar_wait(bar(A_B1FULL + slot), (u >> 1) & 1);
         tcgen05_fence_after();
