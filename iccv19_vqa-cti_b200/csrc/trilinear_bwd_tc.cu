@@ -71,10 +71,13 @@ constexpr int D_BYTES = 6 * 1024;                             // D tile [16 q][1
 constexpr int DB_FLOATS = 512;                                // bias-gradient accumulators (R * 16 <= 512)
 constexpr uint32_t TM_F1 = 0, TM_F2 = 128, TM_B1 = 192, TM_B2 = 224, TM_B3 = 288, TM_B4 = 320;   // all double buffered
 
+constexpr int N1_RING = 8;     // one 32 KB N1 tile holds the 16-column blocks of 4 consecutive ranks: 2 tiles = 8 units in flight
 enum { A_TFULL = 0, A_TEMPTY = 2, A_OPFULL = 4, A_OPEMPTY = 7, A_DLFULL = 10, A_DLEMPTY = 12, A_F1FULL = 14, A_F1EMPTY = 16,
-       A_N1FULL = 18, A_N1EMPTY = 20, A_F2FULL = 22, A_F2EMPTY = 24, A_MFULL = 26, A_MEMPTY = 28, A_B1FULL = 30,
-       A_B1EMPTY = 32, A_B2FULL = 34, A_B2EMPTY = 36, A_DFULL = 38, A_DEMPTY = 40, A_B3FULL = 42, A_B3EMPTY = 44,
-       A_B4FULL = 46, A_B4EMPTY = 48, A_COUNT = 50 };
+       A_N1FULL = 18, A_N1EMPTY = A_N1FULL + N1_RING, A_F2FULL = A_N1EMPTY + N1_RING, A_F2EMPTY = A_F2FULL + 2,
+       A_MFULL = A_F2EMPTY + 2, A_MEMPTY = A_MFULL + 2, A_B1FULL = A_MEMPTY + 2, A_B1EMPTY = A_B1FULL + 2,
+       A_B2FULL = A_B1EMPTY + 2, A_B2EMPTY = A_B2FULL + 2, A_DFULL = A_B2EMPTY + 2, A_DEMPTY = A_DFULL + 2,
+       A_B3FULL = A_DEMPTY + 2, A_B3EMPTY = A_B3FULL + 2, A_B4FULL = A_B3EMPTY + 2, A_B4EMPTY = A_B4FULL + 2,
+       A_COUNT = A_B4EMPTY + 2 };
 
 struct Bwd1Params {
   bf16 *dzv, *dzq, *dn1;
@@ -124,8 +127,6 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
       mbar_init(bar(A_DLEMPTY + s), 2);       // B1 and B2 issuers
       mbar_init(bar(A_F1FULL + s), 1);
       mbar_init(bar(A_F1EMPTY + s), 4);
-      mbar_init(bar(A_N1FULL + s), 4);
-      mbar_init(bar(A_N1EMPTY + s), 2);       // F2 and B3 issuers
       mbar_init(bar(A_F2FULL + s), 1);
       mbar_init(bar(A_F2EMPTY + s), 4);
       mbar_init(bar(A_MFULL + s), 4);
@@ -140,6 +141,10 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
       mbar_init(bar(A_B3EMPTY + s), 4);
       mbar_init(bar(A_B4FULL + s), 1);
       mbar_init(bar(A_B4EMPTY + s), 4);
+    }
+    for (int s = 0; s < N1_RING; ++s) {
+      mbar_init(bar(A_N1FULL + s), 4);
+      mbar_init(bar(A_N1EMPTY + s), 2);       // F2 and B3 issuers
     }
     for (int s = 0; s < 3; ++s) {
       mbar_init(bar(A_OPFULL + s), 1);
@@ -273,15 +278,15 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
       int r = 0;
       for (int u = 0; u < U; ++u) {
         if ((r & 3) == 0) mbar_wait(bar(A_OPFULL + oslot), oph);
-        mbar_wait(bar(A_N1FULL + (u & 1)), (u >> 1) & 1);
+        mbar_wait(bar(A_N1FULL + (u & 7)), (u >> 3) & 1);
         mbar_wait(bar(A_F2EMPTY + (u & 1)), ((u >> 1) & 1) ^ 1);
         tcgen05_fence_after();
         const uint64_t db = desc_kmajor(sOp + oslot * OP_BYTES + OP_Q, r & 3);
-        const uint64_t da = desc_kmajor(sN1 + (u & 1) * N1_BYTES, 0);
+        const uint64_t da = desc_kmajor(sN1 + ((u >> 2) & 1) * N1_BYTES, u & 3);     // K step = rank within the quad tile
         for (int t2 = 0; t2 < nt2; ++t2)
           umma_bf16_ss(tmem_base + TM_F2 + (u & 1) * 32 + t2 * 16, da + (uint64_t)(t2 * 16384 >> 4), db, id_f2, 0u);
         umma_commit(bar(A_F2FULL + (u & 1)));
-        umma_commit(bar(A_N1EMPTY + (u & 1)));
+        umma_commit(bar(A_N1EMPTY + (u & 7)));
         if ((r & 3) == 3) umma_commit(bar(A_OPEMPTY + oslot));
         if (++r == p.R) r = 0;
         if ((r & 3) == 0 && ++oslot == OP_RING) { oslot = 0; oph ^= 1u; }
@@ -297,13 +302,13 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
       for (int u = 0; u < U; ++u) {
         const uint32_t op = sOp + oslot * OP_BYTES;
         if ((r & 3) == 0) mbar_wait(bar(A_OPFULL + oslot), oph);
-        mbar_wait(bar(A_N1FULL + (u & 1)), (u >> 1) & 1);
+        mbar_wait(bar(A_N1FULL + (u & 7)), (u >> 3) & 1);
         mbar_wait(bar(A_DFULL + (u & 1)), (u >> 1) & 1);
         mbar_wait(bar(A_B3EMPTY + (u & 1)), ((u >> 1) & 1) ^ 1);
         mbar_wait(bar(A_B4EMPTY + (u & 1)), ((u >> 1) & 1) ^ 1);
         tcgen05_fence_after();
         const uint32_t dt = sD + (u & 1) * D_BYTES;
-        const uint64_t da0 = desc_kmajor(dt, 0), db0 = desc_mnmajor(sN1 + (u & 1) * N1_BYTES, 0, 0);
+        const uint64_t da0 = desc_kmajor(dt, 0), db0 = desc_mnmajor(sN1 + ((u >> 2) & 1) * N1_BYTES + (u & 3) * 32, 0, 0);
         for (int ks = 0; ks < kn; ++ks)
           umma_bf16_ss(tmem_base + TM_B3 + (u & 1) * 16, da0 + (uint64_t)(((ks >> 2) * 2048 + (ks & 3) * 32) >> 4),
                        db0 + (uint64_t)((ks * 2048) >> 4), id_b3, ks > 0 ? 1u : 0u);
@@ -313,7 +318,7 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
           umma_bf16_ss(tmem_base + TM_B4 + (u & 1) * 32 + t * 16, desc_mnmajor(dt + 2 * t * 2048, 0, 2048), dq, id_b4, 0u);
         umma_commit(bar(A_B4FULL + (u & 1)));
         umma_commit(bar(A_DEMPTY + (u & 1)));
-        umma_commit(bar(A_N1EMPTY + (u & 1)));
+        umma_commit(bar(A_N1EMPTY + (u & 7)));
         if ((r & 3) == 3) umma_commit(bar(A_OPEMPTY + oslot));
         if (++r == p.R) r = 0;
         if ((r & 3) == 0 && ++oslot == OP_RING) { oslot = 0; oph ^= 1u; }
@@ -328,8 +333,9 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
       const int slot = u & 1;
       mbar_wait(bar(A_F1FULL + slot), (u >> 1) & 1);
       tcgen05_fence_after();
-      mbar_wait(bar(A_N1EMPTY + slot), ((u >> 1) & 1) ^ 1);
-      const uint32_t n1 = sN1 + slot * N1_BYTES;
+      mbar_wait(bar(A_N1EMPTY + (u & 7)), ((u >> 3) & 1) ^ 1);
+      const uint32_t n1 = sN1 + ((u >> 2) & 1) * N1_BYTES;
+      const uint32_t sub = u & 3;                                // rank within the quad tile: columns sub * 16 + j
       uint32_t v[4][8];
 #pragma unroll
       for (int t = 0; t < 4; ++t) tmem_ld_32x32b_x8(tmem_base + lane_addr + TM_F1 + slot * 64 + t * 16, v[t]);
@@ -337,7 +343,7 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const int i = 4 * t + (L >> 5);
-        const uint32_t off = (g * 2 + (i >> 3)) * 1024u + (i & 7) * 128u + ((((j >> 3) & 1) ^ (i & 7)) << 4) + (j & 7) * 2u;
+        const uint32_t off = (g * 2 + (i >> 3)) * 1024u + (i & 7) * 128u + (((sub * 2 + ((j >> 3) & 1)) ^ (i & 7)) << 4) + (j & 7) * 2u;
 #pragma unroll
         for (int a = 0; a < 8; ++a) {
           if (a < p.A) {
@@ -350,7 +356,7 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(bar(A_N1FULL + slot));
+        mbar_arrive(bar(A_N1FULL + (u & 7)));
         mbar_arrive(bar(A_F1EMPTY + slot));
       }
     }
