@@ -143,6 +143,25 @@ int cti_adamax_multi(const void* p_ptrs_dev, const void* g_ptrs_dev, const void*
                            clip_norm, clr, beta1, beta2, eps, norm_out, static_cast<cudaStream_t>(stream));
 }
 
+int cti_gru_gate_fwd(const float* gx, int64_t gx_row_stride, const float* gh, const float* h_prev, int64_t hp_row_stride,
+                     float* h_out, int64_t ho_row_stride, void* h_bf16, void* r_bf16, void* z_bf16, void* n_bf16,
+                     void* ghn_bf16, int64_t rows, int H, void* stream) {
+  using b16 = __nv_bfloat16;
+  return cti::gru_gate_fwd(gx, gx_row_stride, gh, h_prev, hp_row_stride, h_out, ho_row_stride, static_cast<b16*>(h_bf16),
+                           static_cast<b16*>(r_bf16), static_cast<b16*>(z_bf16), static_cast<b16*>(n_bf16),
+                           static_cast<b16*>(ghn_bf16), rows, H, static_cast<cudaStream_t>(stream));
+}
+
+int cti_gru_gate_bwd(float* dh, const float* dout, int64_t do_row_stride, const float* h_prev, int64_t hp_row_stride,
+                     const void* r_bf16, const void* z_bf16, const void* n_bf16, const void* ghn_bf16, void* dgx_bf16,
+                     int64_t dgx_row_stride, void* dgh_bf16, int64_t rows, int H, void* stream) {
+  using b16 = __nv_bfloat16;
+  return cti::gru_gate_bwd(dh, dout, do_row_stride, h_prev, hp_row_stride, static_cast<const b16*>(r_bf16),
+                           static_cast<const b16*>(z_bf16), static_cast<const b16*>(n_bf16),
+                           static_cast<const b16*>(ghn_bf16), static_cast<b16*>(dgx_bf16), dgx_row_stride,
+                           static_cast<b16*>(dgh_bf16), rows, H, static_cast<cudaStream_t>(stream));
+}
+
 int cti_masked_softmax_fwd(const float* logits, float* p, int64_t rows, int len, void* stream) {
   return cti::masked_softmax_fwd(logits, p, rows, len, static_cast<cudaStream_t>(stream));
 }

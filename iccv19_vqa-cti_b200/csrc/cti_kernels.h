@@ -57,6 +57,14 @@ int adamax_multi(float* const* p_ptrs, const float* const* g_ptrs, float* const*
                  const float* sumsq, float inv_denom, float clip_norm, float clr, float beta1, float beta2, float eps,
                  float* norm_out, cudaStream_t s);
 
+// gru.cu  (pointwise stages of a GRU timestep; the products run on gemm_bf16)
+int gru_gate_fwd(const float* gx, long gx_row_stride, const float* gh, const float* h_prev, long hp_row_stride, float* h_out,
+                 long ho_row_stride, __nv_bfloat16* h_bf16, __nv_bfloat16* r_s, __nv_bfloat16* z_s, __nv_bfloat16* n_s,
+                 __nv_bfloat16* ghn_s, long rows, int H, cudaStream_t s);
+int gru_gate_bwd(float* dh, const float* dout, long do_row_stride, const float* h_prev, long hp_row_stride,
+                 const __nv_bfloat16* r_s, const __nv_bfloat16* z_s, const __nv_bfloat16* n_s, const __nv_bfloat16* ghn_s,
+                 __nv_bfloat16* dgx, long dgx_row_stride, __nv_bfloat16* dgh, long rows, int H, cudaStream_t s);
+
 // softmax.cu
 int masked_softmax_fwd(const float* logits, float* p, long rows, int len, cudaStream_t s);
 int masked_softmax_bwd(const float* p, const float* dp, long dp_row_stride_b, long dp_row_stride_g, long dp_elem_stride,

@@ -15,6 +15,7 @@ _TARGETS = {
     "src.bc": ("BCNet",),
     "src.attention": ("BiAttention", "TriAttention"),
     "src.classifier": ("SimpleClassifier",),
+    "src.language_model": ("QuestionEmbedding",),
 }
 # modules that did ``from src.x import Name`` and hold their own binding
 _IMPORTERS = ("src.MC.base_model", "src.FFOE.base_model", "src.attention", "src.tc", "src.bc")
@@ -22,9 +23,10 @@ _IMPORTERS = ("src.MC.base_model", "src.FFOE.base_model", "src.attention", "src.
 
 def install() -> None:
     """Patch the reference package (must be importable as ``src``) to use the sm_100a modules."""
-    from . import attention, bc, classifier, fc, tc
+    from . import attention, bc, classifier, fc, language_model, tc
     ours = {"FCNet": fc.FCNet, "TCNet": tc.TCNet, "BCNet": bc.BCNet, "BiAttention": attention.BiAttention,
-            "TriAttention": attention.TriAttention, "SimpleClassifier": classifier.SimpleClassifier}
+            "TriAttention": attention.TriAttention, "SimpleClassifier": classifier.SimpleClassifier,
+            "QuestionEmbedding": language_model.QuestionEmbedding}
     for modname, names in _TARGETS.items():
         mod = importlib.import_module(modname)
         for n in names:

@@ -524,3 +524,77 @@ class BiLogitsFn(Function):
                 K_.dropout_f32_(dq, dq_drop)
             dq = dq.view(B, Q, -1)
         return (None, None, None, None, None, dq, dh.view_as(hmat), dhb.view_as(hbias), dVv, dgv, dbv, dVq, dgq, dbq)
+
+
+# --------------------------------------------------------------------------- #
+class GRUFn(Function):
+    """One-layer unidirectional GRU over a short sequence, zero initial state: ``nn.GRU(in, H, 1, batch_first=True)``
+    as used by QuestionEmbedding.forward_all (reference src/language_model.py:56-61,93-98).  x (B, T, in) fp32 ->
+    all hidden states (B, T, H) fp32.  x W_ih^T for every timestep is one GEMM; each step is one GEMM (h W_hh^T) and
+    one pointwise kernel; backward is BPTT with one accumulating GEMM + one pointwise kernel per step and three GEMMs
+    over the stacked steps for dW_hh, dW_ih, dx.  Gate order r, z, n (PyTorch's)."""
+
+    @staticmethod
+    def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, packs):
+        B, T, Din = x.shape
+        H = w_hh.shape[1]
+        dev = x.device
+        wih_b, whh_b = packs if packs is not None else gru_pack(w_ih, w_hh)
+        Dp = wih_b.shape[1]                                   # in_dim padded to a multiple of 8 (TMA pitch)
+        x2 = x.detach().reshape(B * T, Din)
+        if Dp != Din:
+            x2 = _pad_cols(x2, Dp)
+        xb = cast_in(x2, None)
+        bih, bhh = b_ih.detach().contiguous(), b_hh.detach().contiguous()
+        _, gx = K_.gemm(xb, wih_b, B * T, 3 * H, Dp, bias=bih, out_bf16=False, out_f32=True)
+        gx = gx.view(B, T, 3 * H)
+        out = torch.empty((B, T, H), dtype=F32, device=dev)
+        hb = torch.zeros((T + 1, B, H), dtype=BF16, device=dev)          # hb[t] = h_{t-1} in bf16; hb[0] = 0
+        gates = torch.empty((4, T, B, H), dtype=BF16, device=dev)        # r, z, n, gh_n per step
+        for t in range(T):
+            _, gh = K_.gemm(hb[t], whh_b, B, 3 * H, H, bias=bhh, out_bf16=False, out_f32=True)
+            K_.gru_gate_fwd(gx[:, t], gh, out[:, t - 1] if t > 0 else None, out[:, t], hb[t + 1], gates[0, t], gates[1, t],
+                            gates[2, t], gates[3, t])
+        ctx.save_for_backward(xb, hb, gates, out, wih_b, whh_b, w_ih, w_hh)
+        ctx.dims = (B, T, Din, Dp, H)
+        ctx.need_dx = x.requires_grad
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xb, hb, gates, out, wih_b, whh_b, w_ih, w_hh = ctx.saved_tensors
+        B, T, Din, Dp, H = ctx.dims
+        dev = dout.device
+        dout = dout.contiguous() if dout.stride(2) != 1 else dout
+        if dout.dtype != F32:
+            dout = dout.float()
+        dgx = torch.empty((B, T, 3 * H), dtype=BF16, device=dev)
+        dgh = torch.empty((T, B, 3 * H), dtype=BF16, device=dev)
+        dh, dwhh, dwih, dbih, dbhh = zero_slab(dev, [(B, H), (3 * H, H), (3 * H, Dp), (3 * H,), (3 * H,)])
+        splits_h = _pick_splits(-(-B // 128) * -(-H // 256), 3 * H // 64)
+        for t in range(T - 1, -1, -1):
+            K_.gru_gate_bwd(dh, dout[:, t], out[:, t - 1] if t > 0 else None, gates[0, t], gates[1, t], gates[2, t],
+                            gates[3, t], dgx[:, t], dgh[t])
+            if t > 0:                                          # dh_{t-1} += dgh_t W_hh   (W_hh stored [3H][H] = MN-major B)
+                K_.gemm(dgh[t], whh_b, B, H, 3 * H, b_mn=True, accum_f32=dh, k_splits=splits_h, tile_n=256)
+        dgx2, dgh2 = dgx.view(B * T, 3 * H), dgh.view(T * B, 3 * H)
+        hprev = hb[:T].view(T * B, H)
+        kb = -(-B * T // 64)
+        K_.gemm(dgh2, hprev, 3 * H, H, T * B, a_mn=True, b_mn=True, accum_f32=dwhh,
+                k_splits=_pick_splits(-(-3 * H // 128) * -(-H // 256), kb), tile_n=256)
+        K_.gemm(dgx2, xb, 3 * H, Dp, B * T, a_mn=True, b_mn=True, accum_f32=dwih,
+                k_splits=_pick_splits(-(-3 * H // 128) * -(-Dp // 256), kb), tile_n=256)
+        K_.act_bwd_bias(dgx2, None, False, dbih)
+        K_.act_bwd_bias(dgh2, None, False, dbhh)
+        dx = None
+        if ctx.need_dx:
+            _, dx = K_.gemm(dgx2, wih_b, B * T, Dp, 3 * H, b_mn=True, out_bf16=False, out_f32=True)
+            dx = (dx if Dp == Din else dx[:, :Din]).reshape(B, T, Din)
+        return dx, (dwih if Dp == Din else dwih[:, :Din]), dwhh, dbih, dbhh, None
+
+
+def gru_pack(w_ih: torch.Tensor, w_hh: torch.Tensor):
+    """bf16 copies of the GRU weights; the input width is zero-padded to a multiple of 8 (300-d embeddings)."""
+    Din = w_ih.shape[1]
+    Dp = -(-Din // 8) * 8
+    return (K_.cast_rows(_pad_cols(w_ih.detach(), Dp).contiguous())[0], K_.cast_rows(w_hh.detach().contiguous())[0])

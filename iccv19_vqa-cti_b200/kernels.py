@@ -331,3 +331,35 @@ def bilinear_bwd(vb, qb, hmat, dlogits, B, K, Q, G, C):
            dbv.data_ptr(), dbq.data_ptr(), dh.data_ptr(), dhb.data_ptr(), B, K, Q, G, C, _stream()),
           flops=4.0 * B * K * Q * G * C)
     return dzv, dzq, dbv, dbq, dh, dhb
+
+
+# --------------------------------------------------------------------------- #
+# GRU timestep, pointwise part (the products are gemm() calls)
+# --------------------------------------------------------------------------- #
+def gru_gate_fwd(gx_t: torch.Tensor, gh: torch.Tensor, h_prev: Optional[torch.Tensor], h_out_t: torch.Tensor,
+                 h_bf16: torch.Tensor, r: torch.Tensor, z: torch.Tensor, n: torch.Tensor, ghn: torch.Tensor) -> None:
+    """gx_t (B, 3H) fp32 view with any row stride, gh (B, 3H) fp32 contiguous, h_prev / h_out_t (B, H) fp32 views with
+    any row stride (h_prev None = zeros); h_bf16, r, z, n, ghn (B, H) bf16 contiguous outputs."""
+    B, H = h_bf16.shape
+    for t, name in ((gx_t, "gx"), (h_out_t, "h_out")) + (((h_prev, "h_prev"),) if h_prev is not None else ()):
+        if t.dtype != F32 or t.stride(1) != 1:
+            raise RuntimeError(f"gru_gate_fwd.{name}: expected fp32 with unit column stride")
+    _req(gh, F32, "gru_gate_fwd.gh")
+    _call("cti_gru_gate_fwd", _lib.load().cti_gru_gate_fwd,
+          (gx_t.data_ptr(), gx_t.stride(0), gh.data_ptr(), _ptr(h_prev), 0 if h_prev is None else h_prev.stride(0),
+           h_out_t.data_ptr(), h_out_t.stride(0), h_bf16.data_ptr(), r.data_ptr(), z.data_ptr(), n.data_ptr(), ghn.data_ptr(),
+           B, H, _stream()), nbytes=float(B) * H * (6 * 4 + 4 + 4 + 5 * 2))
+
+
+def gru_gate_bwd(dh: torch.Tensor, dout_t: torch.Tensor, h_prev: Optional[torch.Tensor], r, z, n, ghn,
+                 dgx_t: torch.Tensor, dgh: torch.Tensor) -> None:
+    """In place on dh (B, H) fp32 (see include/cti_sm100.h); dgx_t (B, 3H) bf16 view with any row stride, dgh contiguous."""
+    B, H = dh.shape
+    _req(dh, F32, "gru_gate_bwd.dh")
+    _req(dgh, BF16, "gru_gate_bwd.dgh")
+    if dout_t.dtype != F32 or dout_t.stride(1) != 1 or dgx_t.dtype != BF16 or dgx_t.stride(1) != 1:
+        raise RuntimeError("gru_gate_bwd: dout must be fp32, dgx bf16, both with unit column stride")
+    _call("cti_gru_gate_bwd", _lib.load().cti_gru_gate_bwd,
+          (dh.data_ptr(), dout_t.data_ptr(), dout_t.stride(0), _ptr(h_prev), 0 if h_prev is None else h_prev.stride(0),
+           r.data_ptr(), z.data_ptr(), n.data_ptr(), ghn.data_ptr(), dgx_t.data_ptr(), dgx_t.stride(0), dgh.data_ptr(), B, H,
+           _stream()), nbytes=float(B) * H * (4 * 3 + 4 * 2 + 6 * 2 + 4))

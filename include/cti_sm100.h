@@ -108,6 +108,21 @@ int cti_masked_softmax_bwd(const float* p, const float* dp, int64_t dp_stride_b,
  * src/MC/train.py:75). */
 int cti_sum_row_groups(const void* x_bf16, void* out_bf16, int64_t groups, int rep, int64_t row_elems, void* stream);
 
+/* ---- GRU timestep, pointwise part (the products are cti_gemm_bf16 calls) --------------------------------
+ * gx (row stride gx_row_stride floats) = x_t W_ih^T + b_ih and gh (rows, 3H) = h_{t-1} W_hh^T + b_hh, gate order r,z,n.
+ * fwd: r = sigmoid(gx_r+gh_r), z = sigmoid(gx_z+gh_z), n = tanh(gx_n + r*gh_n), h = (1-z) n + z h_prev
+ *      -> h_out fp32 (row stride ho_row_stride), h_bf16 / r / z / n / gh_n (rows, H) bf16.  h_prev NULL = zeros.
+ * bwd: on entry dh (rows,H) = gradient carried from step t+1; dout = this step's output gradient (added inside);
+ *      writes dgx (row stride dgx_row_stride) and dgh (rows, 3H) bf16 and leaves dh = dh*z (the direct part of the
+ *      gradient w.r.t. h_{t-1}; the caller adds dgh W_hh with an accumulating GEMM).
+ * replaces: the cuDNN GRU behind nn.GRU in QuestionEmbedding (src/language_model.py:56-61,93-98). */
+int cti_gru_gate_fwd(const float* gx, int64_t gx_row_stride, const float* gh, const float* h_prev, int64_t hp_row_stride,
+                     float* h_out, int64_t ho_row_stride, void* h_bf16, void* r_bf16, void* z_bf16, void* n_bf16,
+                     void* ghn_bf16, int64_t rows, int H, void* stream);
+int cti_gru_gate_bwd(float* dh, const float* dout, int64_t do_row_stride, const float* h_prev, int64_t hp_row_stride,
+                     const void* r_bf16, const void* z_bf16, const void* n_bf16, const void* ghn_bf16, void* dgx_bf16,
+                     int64_t dgx_row_stride, void* dgh_bf16, int64_t rows, int H, void* stream);
+
 /* ---- trainer tail: gradient norm, rescale + clip + Adamax, multi-tensor ---------------------------------
  * Tables in DEVICE memory: g_ptrs / p_ptrs / m_ptrs / u_ptrs = arrays of n_tensors device pointers (fp32 tensors of
  * numel[t] elements: gradient, parameter, Adamax exp_avg and exp_inf); chunk c covers elements

@@ -326,6 +326,29 @@ def simple_classifier(x: torch.Tensor, p: Params, prefix: str = "classifier.") -
     return wn_linear(h, p, prefix + "main.3.", "")
 
 
+def gru_forward_all(x: torch.Tensor, p: Params, prefix: str = "rnn.") -> torch.Tensor:
+    """``QuestionEmbedding.forward_all`` (src/language_model.py:93-98): ``nn.GRU(in, H, 1, batch_first=True)`` from a zero
+    initial state, every hidden state returned, (B, T, in) -> (B, T, H).  The cell arithmetic is third-party
+    (torch.nn.GRU; requirements.txt pins torch==1.1.0), restated from its documented equations, gate order r, z, n:
+    r = s(W_ir x + b_ir + W_hr h + b_hr), z = s(W_iz x + b_iz + W_hz h + b_hz),
+    n = tanh(W_in x + b_in + r * (W_hn h + b_hn)), h' = (1 - z) n + z h.  ``forward`` (:80-91) is ``[:, -1]`` of this."""
+    w_ih, w_hh = p[prefix + "weight_ih_l0"], p[prefix + "weight_hh_l0"]
+    b_ih, b_hh = p[prefix + "bias_ih_l0"], p[prefix + "bias_hh_l0"]
+    B, T, _ = x.shape
+    H = w_hh.shape[1]
+    gx = torch.matmul(_r(x), _r(w_ih).t()) + b_ih
+    h = x.new_zeros(B, H)
+    outs = []
+    for t in range(T):
+        gh = torch.matmul(_r(h), _r(w_hh).t()) + b_hh
+        r = torch.sigmoid(gx[:, t, :H] + gh[:, :H])
+        z = torch.sigmoid(gx[:, t, H:2 * H] + gh[:, H:2 * H])
+        n = torch.tanh(gx[:, t, 2 * H:] + r * gh[:, 2 * H:])
+        h = (1 - z) * n + z * h
+        outs.append(h)
+    return torch.stack(outs, 1)
+
+
 def trainer_update(params, grads, exp_avg, exp_inf, step: int, lr: float, grad_denom: float, clip_norm: float,
                    beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8) -> float:
     """One update of the reference trainer's tail, in place on lists of fp32 tensors; returns the pre-clip norm.

@@ -5,6 +5,8 @@ REFERENCE's own code.  Build container only (needs /root/reference, read-only):
 
 Writes tests/golden/next_golden.pt:
   * ``clf_*``   -- ``SimpleClassifier`` (src/classifier.py:11-29) forward + backward in eval mode,
+  * ``gru_*``   -- ``QuestionEmbedding.forward_all`` / ``forward`` (src/language_model.py:50-98; nn.GRU on the CPU) forward +
+                   backward, including a 300-wide input (not a multiple of 8),
   * ``trainer`` -- three update steps of the reference trainer's tail: gradients / grad_denom, global-norm clip with
                    ``src.utils.clip_grad_norm_`` (src/utils.py:323-328, called from src/MC/trainer.py:208-219) and
                    ``torch.optim.Adamax`` (src/MC/train.py:32) on a handful of odd-sized parameters.
@@ -29,6 +31,7 @@ sys.modules.setdefault("h5py", types.ModuleType("h5py"))
 collections.Mapping, collections.Sequence = collections.abc.Mapping, collections.abc.Sequence
 
 from src.classifier import SimpleClassifier  # noqa: E402
+from src.language_model import QuestionEmbedding  # noqa: E402
 import src.utils as ref_utils  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "next_golden.pt")
@@ -74,6 +77,18 @@ def main():
                       "params": [p.detach().clone() for p in params]})
     out["trainer"] = {"shapes": shapes, "p0": p0, "lr": 7e-4, "clip_norm": clip_norm, "steps": steps,
                       "betas": (0.9, 0.999), "eps": 1e-8}
+    # ---- QuestionEmbedding (appended last so the cases above keep their RNG streams) -------------------
+    torch.manual_seed(21)
+    for name, (din, hid, rows, T) in {"gru_small": (24, 32, 3, 5), "gru_300": (300, 64, 4, 7)}.items():
+        m = QuestionEmbedding(din, hid, 1, False, .0).eval()
+        x = torch.randn(rows, T, din, requires_grad=True)
+        y = m.forward_all(x)
+        last = m.forward(x)
+        c = torch.randn(y.shape)
+        (y * c).sum().backward()
+        out[name] = {"sd": {k: t.detach().clone() for k, t in m.state_dict().items()}, "x": x.detach().clone(),
+                     "y": y.detach().clone(), "last": last.detach().clone(), "cot": c, "dx": x.grad.clone(),
+                     "grads": {k: p.grad.detach().clone() for k, p in m.named_parameters()}, "dims": (din, hid)}
     torch.save(out, OUT)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 

@@ -60,6 +60,7 @@ def test_reference_builders_construct_with_dropin_modules():
         assert isinstance(new_mc.q_prj[0], cti_b200.FCNet)
         assert isinstance(new_mc.classifier, cti_b200.SimpleClassifier)
         assert isinstance(new_ban.classifier, cti_b200.SimpleClassifier)
+        assert isinstance(new_mc.q_emb, cti_b200.QuestionEmbedding) and isinstance(new_mc.ans_emb, cti_b200.QuestionEmbedding)
         assert isinstance(new_ban.v_att, cti_b200.BiAttention) and isinstance(new_ban.b_net[0], cti_b200.BCNet)
         for ref, new in ((ref_mc, new_mc), (ref_ban, new_ban), (ref_ff, new_ff)):
             rk = [(k, tuple(v.shape)) for k, v in ref.state_dict().items()]

@@ -122,3 +122,64 @@ def test_fused_clip_adamax_requires_gradients():
     opt = cti_b200.FusedClipAdamax([p])
     with pytest.raises(RuntimeError, match="did not receive gradient"):
         opt.step()
+
+
+# --------------------------------------------------------------------------- #
+# QuestionEmbedding / GRU.  No ReLU on this path, so the north_star's gradient tolerance
+# (3e-2 relative) is checked directly against the fp32 oracle / the reference's golden gradients.
+# --------------------------------------------------------------------------- #
+GRU_GRAD_TOL = 3e-2
+
+
+@pytest.mark.parametrize("name", ["gru_small", "gru_300"])
+def test_question_embedding_against_reference_golden(name):
+    g = torch.load(NEXT)[name]
+    din, hid = g["dims"]
+    m = cti_b200.QuestionEmbedding(din, hid, 1, False, .0)
+    assert list(m.state_dict().keys()) == list(g["sd"].keys())
+    m.load_state_dict(g["sd"])
+    m.to(DEV).eval()
+    x = g["x"].to(DEV).requires_grad_(True)
+    y = m.forward_all(x)
+    assert y.shape == g["y"].shape
+    assert maxabs(y, g["y"]) <= ABS_TOL
+    assert maxabs(m.forward(x), g["last"]) <= ABS_TOL
+    (y * g["cot"].to(DEV)).sum().backward()
+    assert normrel(x.grad, g["dx"]) <= GRU_GRAD_TOL
+    for k, p in m.named_parameters():
+        assert normrel(p.grad, g["grads"][k]) <= GRU_GRAD_TOL, k
+
+
+@pytest.mark.parametrize("B,T", [(64, 12), (40, 6), (9, 3)])
+def test_question_embedding_against_oracle_at_model_size(B, T):
+    """600 -> 1024 (op 'c'), T = 12 question tokens / 6 or 3 answer tokens."""
+    torch.manual_seed(B)
+    m = cti_b200.QuestionEmbedding(600, 1024, 1, False, .0)
+    params = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m.to(DEV).eval()
+    gen = torch.Generator().manual_seed(T)
+    x = 0.5 * torch.randn(B, T, 600, generator=gen)                 # GloVe-scale inputs
+    cot = torch.randn(B, T, 1024, generator=gen)
+    pl = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    xl = x.clone().requires_grad_(True)
+    y_ref = O.gru_forward_all(xl, pl)
+    (y_ref * cot).sum().backward()
+    xd = x.to(DEV).requires_grad_(True)
+    y = m.forward_all(xd)
+    assert maxabs(y, y_ref.detach()) <= ABS_TOL
+    (y * cot.to(DEV)).sum().backward()
+    assert normrel(xd.grad, xl.grad) <= GRU_GRAD_TOL
+    for k, p in m.named_parameters():
+        assert normrel(p.grad, pl[k].grad) <= GRU_GRAD_TOL, k
+    # sequence-level properties: hidden states stay inside (-1, 1); a longer sequence has the shorter one as a prefix
+    assert y.abs().max().item() < 1.0
+    if T > 3:
+        with torch.no_grad():
+            assert torch.equal(m.forward_all(xd[:, :3]), y[:, :3].detach())
+
+
+def test_question_embedding_rejects_what_the_builders_never_build():
+    with pytest.raises(NotImplementedError):
+        cti_b200.QuestionEmbedding(600, 1024, 2, False, .0)
+    with pytest.raises(NotImplementedError):
+        cti_b200.QuestionEmbedding(600, 1024, 1, True, .0)

@@ -177,3 +177,17 @@ def test_trainer_update_matches_reference_clip_and_adamax():
         assert abs(norm - st["norm"]) <= 1e-5 * max(1.0, st["norm"])
         for p, ref in zip(params, st["params"]):
             assert (p - ref).abs().max() < 1e-6
+
+
+@pytest.mark.parametrize("name", ["gru_small", "gru_300"])
+def test_gru_matches_reference_question_embedding(name):
+    g = torch.load(NEXT)[name]
+    params = {k: v.clone().requires_grad_(True) for k, v in g["sd"].items()}
+    x = g["x"].clone().requires_grad_(True)
+    y = O.gru_forward_all(x, params)
+    assert (y - g["y"]).abs().max() < 1e-5
+    assert (y[:, -1] - g["last"]).abs().max() < 1e-5
+    (y * g["cot"]).sum().backward()
+    assert (x.grad - g["dx"]).abs().max() < 1e-5
+    for k, ref in g["grads"].items():
+        assert (params[k].grad - ref).abs().max() <= 1e-5 * max(1.0, ref.abs().max().item()), k
