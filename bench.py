@@ -464,6 +464,44 @@ def run_b200(args):
         except Exception as exc:
             tail = {"failed": repr(exc)[:200]}
 
+    # ---- the step before the path: the two GRUs that produce q and a (rank 0; not part of `value`) ---------------
+    gru = None
+    if rank == 0 and not args.resident_only:
+        try:
+            torch.manual_seed(7)
+            ours = [cti_b200.QuestionEmbedding(600, HID, 1, False, .0).to(dev) for _ in range(2)]
+            refs = [torch.nn.GRU(600, HID, 1, batch_first=True).to(dev) for _ in range(2)]
+            xs = [torch.randn(B, T_, 600, device=dev, requires_grad=True) for T_ in (Q_TOK, A_TOK)]
+            cots = [torch.randn(B, T_, HID, device=dev) for T_ in (Q_TOK, A_TOK)]
+
+            def run_pair(mods_, call):
+                for m_ in mods_:
+                    for p_ in m_.parameters():
+                        p_.grad = None
+                loss = 0
+                for m_, x_, c_ in zip(mods_, xs, cots):
+                    x_.grad = None
+                    loss = loss + (call(m_, x_) * c_).sum()
+                loss.backward()
+            ours_step = lambda: run_pair(ours, lambda m_, x_: m_.forward_all(x_))
+            ref_step = lambda: run_pair(refs, lambda m_, x_: m_(x_)[0])
+            for _ in range(3):
+                ours_step()
+                ref_step()
+            run_ours = ours_step
+            if use_graph:
+                try:
+                    run_ours = cti_b200.GraphedStep(ours_step, [], []).replay
+                except Exception:
+                    run_ours = ours_step
+            ms_o, _, _ = timed(run_ours, args.steps)
+            ms_r, _, _ = timed(ref_step, max(3, args.steps // 4))
+            gru = {"rows": B, "tokens": [Q_TOK, A_TOK], "in_dim": 600, "hidden": HID,
+                   "ours_fwd_bwd_ms": ms_o / args.steps, "torch_cudnn_fp32_fwd_bwd_ms": ms_r / max(3, args.steps // 4),
+                   "note": "question + answer GRU, forward_all + backward; not part of `value`"}
+        except Exception as exc:
+            gru = {"failed": repr(exc)[:200]}
+
     # ---- per-kernel CUDA-event timing of the same step (rank 0) -----------------
     roofline, kernels = None, None
     if rank == 0 and not args.no_profile:
@@ -529,7 +567,7 @@ def run_b200(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": dict(workload_config(B, world), launch="cuda_graph_replay" if use_graph else "eager"),
                 "eager": eager_ms, "e2e": e2e, "gpu_launches": launches, "gpu_launches_per_step": launches_per_step, "clocks": clocks,
-                "fwd_only": fwd, "shared_v": shared, "trainer_tail": tail, "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels}
+                "fwd_only": fwd, "shared_v": shared, "trainer_tail": tail, "gru": gru, "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
