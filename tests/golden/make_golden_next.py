@@ -89,6 +89,36 @@ def main():
         out[name] = {"sd": {k: t.detach().clone() for k, t in m.state_dict().items()}, "x": x.detach().clone(),
                      "y": y.detach().clone(), "last": last.detach().clone(), "cot": c, "dx": x.grad.clone(),
                      "grads": {k: p.grad.detach().clone() for k, p in m.named_parameters()}, "dims": (din, hid)}
+    # ---- the whole multiple-choice model, small but with the real structure (d = h_mm / rank = 16, k = 2 pooling) ------
+    import src.MC.base_model as mc
+    torch.manual_seed(33)
+    ds = types.SimpleNamespace(dictionary=types.SimpleNamespace(ntoken=50), v_dim=64, num_ans_candidates=4)
+    margs = types.SimpleNamespace(op="c", num_hid=128, gamma=2, h_mm=64, h_out=1, rank=4, k=1, activation="relu",
+                                  dropout=0.5, use_counter=False, num_stacks=2)
+    model = mc.build_cti(margs, ds).eval()
+    model.classifier.main[2].inplace = False
+    with torch.no_grad():
+        model.w_emb.emb_.weight.normal_()                 # the frozen table is filled from GloVe in the reference
+        model.wa_emb.emb_.weight.normal_()
+    gq = torch.Generator().manual_seed(34)
+    nq, K = 3, 12
+    v = torch.relu(torch.randn(nq, K, 64, generator=gq))
+    nb = torch.randint(6, K + 1, (nq,), generator=gq)
+    v = v * (torch.arange(K)[None, :] < nb[:, None]).float()[:, :, None]
+    v4 = v.unsqueeze(1).expand(nq, 4, K, 64).contiguous().view(nq * 4, K, 64)      # src/MC/train.py:75-76
+    q_tok = torch.randint(0, 50, (nq, 12), generator=gq)
+    q4 = q_tok.unsqueeze(1).expand(nq, 4, 12).contiguous().view(nq * 4, 12)
+    a_tok = torch.randint(0, 51, (nq * 4, 6), generator=gq)                          # 50 = padding id
+    labels = torch.zeros(nq * 4, 2)
+    labels[torch.arange(nq * 4), torch.randint(0, 2, (nq * 4,), generator=gq)] = 1.0
+    logits, att = model(v4, None, q4, a_tok)
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, labels, reduction="sum") / labels.size(0)
+    loss.backward()
+    out["mc_model"] = {"args": dict(ntoken=50, v_dim=64, num_hid=128, h_mm=64, rank=4, gamma=2),
+                       "sd": {k: t.detach().clone() for k, t in model.state_dict().items()},
+                       "v": v, "q_tok": q4, "a_tok": a_tok, "labels": labels, "logits": logits.detach().clone(),
+                       "att": att.detach().clone().contiguous(), "loss": loss.detach().clone(),
+                       "grads": {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}}
     torch.save(out, OUT)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 

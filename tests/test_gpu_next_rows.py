@@ -183,3 +183,34 @@ def test_question_embedding_rejects_what_the_builders_never_build():
         cti_b200.QuestionEmbedding(600, 1024, 2, False, .0)
     with pytest.raises(NotImplementedError):
         cti_b200.QuestionEmbedding(600, 1024, 1, True, .0)
+
+
+# --------------------------------------------------------------------------- #
+# Everything together: the reference's whole multiple-choice model (word embeddings -> GRUs -> TriAttention ->
+# 2 x pooling + q_prj / a_prj -> classifier -> BCE), golden made by the reference's own build_cti + TanModel.forward
+# (tests/golden/make_golden_next.py), reproduced from the drop-ins (tools/mc_model.py mirrors TanModel).
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("shared_v", [False, True])
+def test_whole_mc_model_against_reference_golden(shared_v):
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from mc_model import MCModel
+    from test_gpu_modules import check_grads_fp32
+    g = torch.load(NEXT)["mc_model"]
+    model = MCModel(**g["args"])
+    assert list(model.state_dict().keys()) == list(g["sd"].keys())          # the reference checkpoint loads as is
+    model.load_state_dict(g["sd"])
+    model.to(DEV).eval()
+    v = g["v"].to(DEV)                                                       # one row per question
+    if not shared_v:                                                         # src/MC/train.py:75-76
+        v = v.unsqueeze(1).expand(v.size(0), 4, v.size(1), v.size(2)).contiguous().view(v.size(0) * 4, v.size(1), v.size(2))
+    logits, att = model(v, None, g["q_tok"].to(DEV), g["a_tok"].to(DEV))
+    assert maxabs(logits, g["logits"]) <= ABS_TOL
+    assert maxabs(att, g["att"]) <= ABS_TOL
+    assert (logits.argmax(1).cpu() == g["logits"].argmax(1)).all()
+    labels = g["labels"].to(DEV)
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, labels, reduction="sum") / labels.size(0)
+    assert abs(loss.item() - g["loss"].item()) <= ABS_TOL
+    loss.backward()
+    named = [(k, p.grad) for k, p in model.named_parameters() if k in g["grads"]]
+    assert len(named) == len(g["grads"]) and all(gr is not None for _, gr in named)   # every parameter gets a gradient
+    check_grads_fp32(named, g["grads"])
