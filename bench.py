@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--resident-only", action="store_true", help="skip the e2e / forward-only arms (for ncu runs)")
+    ap.add_argument("--hot-only", action="store_true", help="skip the legs outside the hot path (trainer tail, GRUs, whole model)")
     ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly from Python (no CUDA graph)")
     return ap.parse_args()
 
@@ -432,7 +433,7 @@ def run_b200(args):
 
     # ---- trainer tail on the hot path's parameters: fused clip + Adamax vs the reference's sequence (rank 0) -------
     tail = None
-    if rank == 0 and not args.resident_only:
+    if rank == 0 and not args.resident_only and not args.hot_only:
         try:
             resident_step()                                     # leaves eager gradients in p.grad
             gparams = [p for p in params if p.grad is not None]
@@ -466,7 +467,7 @@ def run_b200(args):
 
     # ---- the step before the path: the two GRUs that produce q and a (rank 0; not part of `value`) ---------------
     gru = None
-    if rank == 0 and not args.resident_only:
+    if rank == 0 and not args.resident_only and not args.hot_only:
         try:
             torch.manual_seed(7)
             ours = [cti_b200.QuestionEmbedding(600, HID, 1, False, .0).to(dev) for _ in range(2)]
@@ -504,7 +505,7 @@ def run_b200(args):
 
     # ---- the whole MC model (embeddings -> GRUs -> hot path -> classifier -> BCE -> clip + Adamax), rank 0 ---------
     full = None
-    if rank == 0 and not args.resident_only:
+    if rank == 0 and not args.resident_only and not args.hot_only:
         try:
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             from mc_model import MCModel

@@ -266,7 +266,7 @@ class TriLogitsFn(Function):
     @staticmethod
     def forward(ctx, dims, packs, drops, v_bf16, rowmask, q, a, T_g, *w):
         """drops: None (eval) or (v_f32_2d, dv, dq, da, dvn, dqn, dan) -- input dropout of the three tucker nets and of
-        the per-rank nets (one mask per modality shared by its R per-rank nets)."""
+        the per-rank nets (RANK_DROPOUT: one mask per rank as in the reference, or one per modality)."""
         B, K, Q, A, G, R = dims
         vr = (B * K) // v_bf16.shape[0]               # rows sharing one image (v has B / vr samples; see tc.py)
         ctx.vr = vr

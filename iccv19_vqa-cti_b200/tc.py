@@ -92,8 +92,8 @@ class TCNet(nn.Module):
         la, pa = self.a_tucker.single()
         drops = None
         if self.training:
-            # input dropout of the tucker nets and of the per-rank nets.  The R per-rank nets of a modality share ONE
-            # mask here (the reference draws R independent ones, src/tc.py:29-31): see DESIGN.md section 7.
+            # input dropout of the tucker nets and of the per-rank nets: one site per modality; functions.RANK_DROPOUT
+            # decides whether the R per-rank nets draw independent masks from it (the reference's semantics, src/tc.py:29-31)
             sites = [F_.new_drop(p, True) for p in (pv, pq, pa, self.v_net[0].single()[1], self.q_net[0].single()[1],
                                                     self.a_net[0].single()[1])]
             if any(d is not None for d in sites):

@@ -14,7 +14,7 @@
  *   - Return value: 0 = ok; negative = argument/shape/alignment error, nothing was launched;
  *     positive = the cudaError_t reported by the launch.  `cti_last_error()` returns a
  *     thread-local message for the last non-zero return on this thread.  Nothing throws or exits.
- *   - Buffers named `*_accum` are accumulated into with atomics and must be zeroed by the caller.
+ *   - Buffers named `*_accum` are accumulated into (fp32 atomics or TMA reduce-add) and must be zeroed by the caller.
  *   - The device is the current device of the calling thread (one process per GPU for DP).
  */
 #ifndef CTI_SM100_H_
