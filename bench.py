@@ -215,8 +215,11 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        barrier()
+    def timed(fn, steps, all_ranks=True):
+        """CUDA-event time of `steps` calls.  all_ranks: barrier on both sides and the max over ranks (the contract's
+        timing); rank-0-only legs pass False -- a collective there would wait for ranks that never call it."""
+        sync = barrier if all_ranks else torch.cuda.synchronize
+        sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0 = time.perf_counter()
         e0.record()
@@ -224,10 +227,10 @@ def run_b200(args):
             fn()
         e1.record()
         timed.host_ms = (time.perf_counter() - w0) * 1e3 / steps      # host time to ISSUE a step (launch-bound check)
-        barrier()
+        sync()
         w1 = time.perf_counter()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
+        if world > 1 and all_ranks:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item(), w0, w1
 
@@ -433,13 +436,13 @@ def run_b200(args):
 
     # ---- trainer tail on the hot path's parameters: fused clip + Adamax vs the reference's sequence (rank 0) -------
     tail = None
-    if rank == 0 and not args.resident_only and not args.hot_only:
+    if world == 1 and not args.resident_only and not args.hot_only:
         try:
             resident_step()                                     # leaves eager gradients in p.grad
             gparams = [p for p in params if p.grad is not None]
             n_el = sum(p.numel() for p in gparams)
             fused = cti_b200.FusedClipAdamax(gparams, lr=1e-3, clip_norm=0.25)
-            ms_fused, _, _ = timed(lambda: fused.step(grad_denom=float(B)), args.steps)
+            ms_fused, _, _ = timed(lambda: fused.step(grad_denom=float(B)), args.steps, all_ranks=False)
             ref_opt = torch.optim.Adamax(gparams, lr=1e-3)
 
             def ref_tail():                                     # src/MC/trainer.py:208-219 + optimizer.step()
@@ -454,7 +457,7 @@ def run_b200(args):
                 ref_opt.step()
             for _ in range(2):
                 ref_tail()
-            ms_ref, _, _ = timed(ref_tail, max(3, args.steps // 4))
+            ms_ref, _, _ = timed(ref_tail, max(3, args.steps // 4), all_ranks=False)
             peaks_ = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
                 os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
             bw = peaks_.get("hbm_gbs", 6650.0)
@@ -467,7 +470,7 @@ def run_b200(args):
 
     # ---- the step before the path: the two GRUs that produce q and a (rank 0; not part of `value`) ---------------
     gru = None
-    if rank == 0 and not args.resident_only and not args.hot_only:
+    if world == 1 and not args.resident_only and not args.hot_only:
         try:
             torch.manual_seed(7)
             ours = [cti_b200.QuestionEmbedding(600, HID, 1, False, .0).to(dev) for _ in range(2)]
@@ -495,8 +498,8 @@ def run_b200(args):
                     run_ours = cti_b200.GraphedStep(ours_step, [], []).replay
                 except Exception:
                     run_ours = ours_step
-            ms_o, _, _ = timed(run_ours, args.steps)
-            ms_r, _, _ = timed(ref_step, args.steps)
+            ms_o, _, _ = timed(run_ours, args.steps, all_ranks=False)
+            ms_r, _, _ = timed(ref_step, args.steps, all_ranks=False)
             gru = {"rows": B, "tokens": [Q_TOK, A_TOK], "in_dim": 600, "hidden": HID,
                    "ours_fwd_bwd_ms": ms_o / args.steps, "torch_cudnn_fp32_fwd_bwd_ms": ms_r / args.steps,
                    "note": "question + answer GRU, forward_all + backward; not part of `value`"}
@@ -505,7 +508,7 @@ def run_b200(args):
 
     # ---- the whole MC model (embeddings -> GRUs -> hot path -> classifier -> BCE -> clip + Adamax), rank 0 ---------
     full = None
-    if rank == 0 and not args.resident_only and not args.hot_only:
+    if world == 1 and not args.resident_only and not args.hot_only:
         try:
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             from mc_model import MCModel
@@ -544,7 +547,7 @@ def run_b200(args):
                     opt.step(grad_denom=1.0)
                 for _ in range(2):
                     train_step()
-                ms_t, _, _ = timed(train_step, args.steps)
+                ms_t, _, _ = timed(train_step, args.steps, all_ranks=False)
                 full[key] = {"ms_per_step": ms_t / args.steps, "rows_per_s": B * args.steps / (ms_t / 1e3),
                              "questions_per_s": Bq * args.steps / (ms_t / 1e3)}
         except Exception as exc:
@@ -603,7 +606,7 @@ def run_b200(args):
                                               "frac": gflops / (gms * 1e-3) / 1e12 / tf_peak}}
 
     cpu_baseline = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline:
         val, cores, dt = cpu_rows_per_s(args.cpu_rows, 3, 1)
         cpu_baseline = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"3 timed fwd+bwd steps of {args.cpu_rows} rows after 1 warm-up, oracle on host cores, "
@@ -618,6 +621,7 @@ def run_b200(args):
                 "fwd_only": fwd, "shared_v": shared, "trainer_tail": tail, "gru": gru, "full_model": full, "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels}
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
