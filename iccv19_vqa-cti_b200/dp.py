@@ -30,10 +30,10 @@ def shard_rows(n_rows: int, rank: int, world: int, group: int = 1) -> slice:
 class _Bucket:
     __slots__ = ("params", "flat", "views", "pending", "work")
 
-    def __init__(self, params: List[torch.nn.Parameter]):
+    def __init__(self, params: List[torch.nn.Parameter], flat: Optional[torch.Tensor] = None):
         self.params = params
         n = sum(p.numel() for p in params)
-        self.flat = torch.zeros(n, dtype=params[0].dtype, device=params[0].device)
+        self.flat = flat if flat is not None else torch.zeros(n, dtype=params[0].dtype, device=params[0].device)
         self.views, o = [], 0
         for p in params:
             self.views.append(self.flat[o:o + p.numel()].view_as(p))
@@ -59,16 +59,28 @@ class GradAllReducer:
         self.average = average
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         ps = [p for p in params if p.requires_grad]
-        self.buckets: List[_Bucket] = []
+        groups: List[List[torch.nn.Parameter]] = []
         cur, cur_bytes = [], 0
         for p in reversed(ps):
             if cur and (cur_bytes + p.numel() * p.element_size() > bucket_bytes or p.dtype != cur[0].dtype):
-                self.buckets.append(_Bucket(cur))
+                groups.append(cur)
                 cur, cur_bytes = [], 0
             cur.append(p)
             cur_bytes += p.numel() * p.element_size()
         if cur:
-            self.buckets.append(_Bucket(cur))
+            groups.append(cur)
+        # the buckets are consecutive pieces of ONE buffer when every gradient has the same dtype (always, on this path):
+        # the hook-free path can then reduce everything with a single collective
+        self.slab: Optional[torch.Tensor] = None
+        if ps and all(p.dtype == ps[0].dtype and p.device == ps[0].device for p in ps):
+            self.slab = torch.zeros(sum(p.numel() for p in ps), dtype=ps[0].dtype, device=ps[0].device)
+        self.buckets: List[_Bucket] = []
+        o = 0
+        for grp in groups:
+            n = sum(p.numel() for p in grp)
+            self.buckets.append(_Bucket(grp, None if self.slab is None else self.slab[o:o + n]))
+            o += n
+        self._src = {}                                    # param -> gradient tensor produced by backward (graph-owned under replay)
         self._of = {}
         self._handles = []
         for b in self.buckets:
@@ -110,31 +122,43 @@ class GradAllReducer:
             b.pending = len(b.params)
 
     def reduce_now(self) -> None:
-        """All-reduce the gradients that are sitting in ``p.grad`` right now, without hooks: used after a CUDA-graph
-        replay of forward + backward (the replay re-fills the same gradient tensors, so the autograd hooks never
-        fire).  One fused copy into each flat bucket, all buckets reduced asynchronously, one wait; the reduced
-        values are copied back into the (graph-owned) gradient tensors.  The hot path's 11.5 M fp32 gradients are
-        46 MB -- ~0.1 ms on NVLink against a step of several ms, so the lost overlap is negligible."""
-        works = []
+        """All-reduce the gradients backward has just produced, without hooks: used after a CUDA-graph replay of
+        forward + backward (the replay re-fills the same gradient tensors, so the autograd hooks never fire).
+        One fused copy into the flat buffer, ONE all-reduce of the whole buffer (the buckets are pieces of it), and
+        ``p.grad`` is left pointing at the reduced bucket views -- no copy back.  The tensors backward writes into are
+        remembered, so the next call (after the next replay, which refills them) finds its sources even though
+        ``p.grad`` now names the views (or was reset to None); an eager backward simply assigns fresh ``p.grad`` tensors,
+        which take over.  ``forget_sources()`` drops the remembered tensors (after re-capturing a graph)."""
+        dsts, srcs = [], []
         for b in self.buckets:
-            grads = [p.grad for p in b.params]
-            for g, v in zip(grads, b.views):
-                if g is None:
-                    v.zero_()
-            live = [(v, g) for v, g in zip(b.views, grads) if g is not None and g.data_ptr() != v.data_ptr()]
-            if live:
-                torch._foreach_copy_([v for v, _ in live], [g for _, g in live])
-            if self.world > 1:
-                works.append(dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
-        for w in works:
-            w.wait()
+            for p, v in zip(b.params, b.views):
+                g = p.grad
+                if g is not None and g.data_ptr() != v.data_ptr():
+                    self._src[p] = g                                   # fresh from backward
+                src = self._src.get(p)                                 # p.grad is None or the view: the remembered tensor
+                if src is None:
+                    v.zero_()                                         # no gradient this step counts as zeros
+                else:
+                    dsts.append(v)
+                    srcs.append(src)
+        if dsts:
+            torch._foreach_copy_(dsts, srcs)
+        if self.world > 1:
+            if self.slab is not None:
+                dist.all_reduce(self.slab, op=dist.ReduceOp.SUM, group=self.group)
+            else:
+                works = [dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True) for b in self.buckets]
+                for w in works:
+                    w.wait()
         for b in self.buckets:
             if self.average and self.world > 1:
                 b.flat.div_(self.world)
-            live = [(v, p.grad) for v, p in zip(b.views, b.params) if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
-            if live:
-                torch._foreach_copy_([g for _, g in live], [v for v, _ in live])
+            for p, v in zip(b.params, b.views):
+                p.grad = v
             b.pending = len(b.params)
+
+    def forget_sources(self) -> None:
+        self._src.clear()
 
     def set_hooks_enabled(self, enabled: bool) -> None:
         self._enabled = enabled
