@@ -119,6 +119,40 @@ def main():
                        "v": v, "q_tok": q4, "a_tok": a_tok, "labels": labels, "logits": logits.detach().clone(),
                        "att": att.detach().clone().contiguous(), "loss": loss.detach().clone(),
                        "grads": {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}}
+    # ---- the BAN distillation student (BASELINE config 3 in miniature): build_ban + Distillation_Loss(T=5, alpha=0.005) ----
+    import src.FFOE.base_model as ff
+    from src.loss_function import Distillation_Loss
+    torch.manual_seed(44)
+    n_ans = 37
+    ds = types.SimpleNamespace(dictionary=types.SimpleNamespace(ntoken=50), v_dim=64, num_ans_candidates=n_ans)
+    bargs = types.SimpleNamespace(op="c", num_hid=128, gamma=2, h_mm=64, h_out=1, rank=4, k=1, activation="relu",
+                                  dropout=0.5, use_counter=False, num_stacks=2)
+    ban = ff.build_ban(bargs, ds).eval()
+    ban.classifier.main[2].inplace = False
+    with torch.no_grad():
+        ban.w_emb.emb_.weight.normal_()
+    gb = torch.Generator().manual_seed(45)
+    Bn, K = 5, 12
+    v = torch.relu(torch.randn(Bn, K, 64, generator=gb))
+    nb = torch.randint(6, K + 1, (Bn,), generator=gb)
+    v = v * (torch.arange(K)[None, :] < nb[:, None]).float()[:, :, None]
+    boxes = torch.rand(Bn, K, 6, generator=gb)
+    q_tok = torch.randint(0, 51, (Bn, 12), generator=gb)
+    teacher = torch.randn(Bn, n_ans, generator=gb).half().float()             # fp16 teacher logits (src/FFOE/test.py:129)
+    target = torch.zeros(Bn, n_ans)
+    target[torch.arange(Bn), torch.randint(0, n_ans, (Bn,), generator=gb)] = 1.0
+    target[torch.arange(Bn), torch.randint(0, n_ans, (Bn,), generator=gb)] += 0.3  # soft scores (tools/compute_softscore.py:86-96)
+    target.clamp_(max=1.0)
+    logits, att = ban(v, boxes, q_tok, None)
+    loss = Distillation_Loss(T=5, alpha=0.005)(logits, teacher, target)
+    loss.backward()
+    out["ban_model"] = {"args": dict(ntoken=50, v_dim=64, num_hid=128, gamma=2, n_ans=n_ans),
+                        "sd": {k: t.detach().clone() for k, t in ban.state_dict().items()},
+                        "v": v, "boxes": boxes, "q_tok": q_tok, "teacher": teacher, "target": target,
+                        "logits": logits.detach().clone(), "att": att.detach().clone().contiguous(),
+                        "loss": loss.detach().clone(),
+                        "grads": {k: p.grad.detach().clone().bfloat16() for k, p in ban.named_parameters()
+                                  if p.grad is not None}}
     torch.save(out, OUT)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 

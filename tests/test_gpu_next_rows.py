@@ -214,3 +214,26 @@ def test_whole_mc_model_against_reference_golden(shared_v):
     named = [(k, p.grad) for k, p in model.named_parameters() if k in g["grads"]]
     assert len(named) == len(g["grads"]) and all(gr is not None for _, gr in named)   # every parameter gets a gradient
     check_grads_fp32(named, g["grads"])
+
+
+def test_whole_ban_student_with_distillation_loss_against_reference_golden():
+    """BASELINE config 3 in miniature: the reference's build_ban (no counter) + Distillation_Loss(T=5, alpha=0.005)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from mc_model import BanStudent
+    from test_gpu_modules import check_grads_fp32
+    g = torch.load(NEXT)["ban_model"]
+    model = BanStudent(**g["args"])
+    assert list(model.state_dict().keys()) == list(g["sd"].keys())
+    model.load_state_dict(g["sd"])
+    model.to(DEV).eval()
+    logits, att = model(g["v"].to(DEV), g["boxes"].to(DEV), g["q_tok"].to(DEV), None)
+    assert maxabs(att, g["att"]) <= ABS_TOL
+    # class logits come out of the whole chain with |logit| up to ~4: 2e-2 relative to that scale (measured 5e-3)
+    assert rel(logits, g["logits"]) <= ABS_TOL
+    assert (logits.argmax(1).cpu() == g["logits"].argmax(1)).all()
+    loss = O.distillation_loss(logits, g["teacher"].to(DEV), g["target"].to(DEV), 5.0, 0.005)   # src/loss_function.py:20-25
+    assert abs(loss.item() - g["loss"].item()) <= 2e-2 * abs(g["loss"].item())
+    loss.backward()
+    named = [(k, p.grad) for k, p in model.named_parameters() if k in g["grads"]]
+    assert len(named) == len(g["grads"]) and all(gr is not None for _, gr in named)
+    check_grads_fp32(named, {k: t.float() for k, t in g["grads"].items()})

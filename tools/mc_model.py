@@ -1,5 +1,6 @@
-"""The reference's multiple-choice CTI model (``TanModel`` + ``build_cti``, reference src/MC/base_model.py:112-152,186-208)
-assembled from the cti_b200 drop-ins, for end-to-end tests and the full-model bench leg.  Host glue, not product: with
+"""The reference's models assembled from the cti_b200 drop-ins, for end-to-end tests and the full-model bench leg:
+``MCModel`` = the multiple-choice CTI model (``TanModel`` + ``build_cti``, reference src/MC/base_model.py:112-152,186-208),
+``BanStudent`` = the free-form BAN student without counter (``BanModel`` + ``build_ban``, src/FFOE/base_model.py:21-66,145-163).  Host glue, not product: with
 the reference tree present one calls ``cti_b200.install()`` and the reference's own builder instead.
 Attribute names equal the reference's, so a reference ``state_dict`` loads unchanged."""
 import os
@@ -58,3 +59,28 @@ class MCModel(nn.Module):
             q_emb = self.q_prj[g](b_emb.unsqueeze(1)) + q_emb
             ans_emb = self.a_prj[g](b_emb.unsqueeze(1)) + ans_emb
         return self.classifier(q_emb.sum(1) + ans_emb.sum(1)), att
+
+
+class BanStudent(nn.Module):
+    """reference src/FFOE/base_model.py:21-66 with ``use_counter=False`` (the distillation student, README.md:49)."""
+
+    def __init__(self, ntoken, v_dim, num_hid, gamma, n_ans, op='c', activation='relu', dropout=0.5):
+        super().__init__()
+        args = type("Args", (), {"activation": activation, "dropout": dropout})()
+        self.glimpse = gamma
+        self.w_emb = WordEmbedding(ntoken, 300, .0, op)
+        self.q_emb = cti_b200.QuestionEmbedding(300 if 'c' not in op else 600, num_hid, 1, False, .0)
+        self.v_att = cti_b200.BiAttention(v_dim, num_hid, num_hid, gamma)
+        self.b_net = nn.ModuleList([cti_b200.BCNet(v_dim, num_hid, num_hid, None, k=1) for _ in range(gamma)])
+        self.q_prj = nn.ModuleList([cti_b200.FCNet([num_hid, num_hid], '', .2) for _ in range(gamma)])
+        self.classifier = cti_b200.SimpleClassifier(num_hid, num_hid * 2, n_ans, args)
+
+    def forward(self, v, b, q, labels=None):
+        q_emb = self.q_emb.forward_all(self.w_emb(q))
+        att, _ = self.v_att.forward_all(v, q_emb)
+        q_list = []
+        for g in range(self.glimpse):
+            b_emb = self.b_net[g].forward_with_weights(v, q_emb, att[:, g, :, :])
+            q_emb = self.q_prj[g](b_emb.unsqueeze(1)) + q_emb
+            q_list.append(q_emb)
+        return self.classifier(torch.stack(q_list, 1).sum(1).sum(1)), att
