@@ -145,3 +145,25 @@ def test_batch_mismatch_raises():
     _, q4, a4 = O.synthetic_inputs(4, 20, 5, 3, seed=2)
     with pytest.raises(RuntimeError, match="batch mismatch"):
         att(v.to(DEV), q4.to(DEV), a4.to(DEV))
+
+
+def test_shared_images_in_train_mode_with_dropout_run_and_give_every_parameter_a_gradient():
+    Bq, rep, K, Q, A, G = 2, 4, 30, 12, 6, 2
+    B = Bq * rep
+    params = O.random_cti_params(glimpse=G, seed=5)
+    v_q, _, _ = O.synthetic_inputs(Bq, K, Q, A, seed=11)
+    _, q, a = O.synthetic_inputs(B, K, Q, A, seed=12)
+    att, pools, prj = build_cti(params, G, DEV)
+    mods = [att] + pools + [m for pr in prj for m in pr]
+    for m in mods:
+        m.train()
+    torch.manual_seed(0)
+    qd, ad = q.to(DEV).requires_grad_(True), a.to(DEV).requires_grad_(True)
+    joint, p, logits = cti_forward(att, pools, prj, v_q.to(DEV), qd, ad)
+    assert torch.isfinite(joint).all() and torch.isfinite(p).all()
+    assert torch.allclose(p.sum(dim=(1, 2, 3)), torch.ones(B, G, device=DEV), atol=1e-4)
+    joint.sum().backward()
+    assert torch.isfinite(qd.grad).all() and torch.isfinite(ad.grad).all()
+    for m in mods:
+        for name, t in m.named_parameters():
+            assert t.grad is not None and torch.isfinite(t.grad).all(), name
