@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(kThreads)
 bilinear_fwd_kernel(const bf16* __restrict__ vb, const bf16* __restrict__ qb, const float* __restrict__ hmat,
                     const float* __restrict__ hbias, const uint8_t* __restrict__ rowmask, float* __restrict__ logits,
                     const BiDims dims) {
+  pdl_prologue_done();
   extern __shared__ __align__(128) uint8_t smem[];
   const BiShape s = make_bi_shape(dims);
   const BiSmem lay = bi_smem(s, false);
@@ -170,6 +171,7 @@ bilinear_bwd_kernel(const bf16* __restrict__ vb, const bf16* __restrict__ qb, co
                     const float* __restrict__ dlogits, bf16* __restrict__ dzv, bf16* __restrict__ dzq,
                     float* __restrict__ dbv, float* __restrict__ dbq, float* __restrict__ dhmat,
                     float* __restrict__ dhbias, const BiDims dims) {
+  pdl_prologue_done();
   extern __shared__ __align__(128) uint8_t smem[];
   const BiShape s = make_bi_shape(dims);
   const BiSmem lay = bi_smem(s, true);
@@ -349,7 +351,7 @@ int bilinear_fwd(const bf16* vb, const bf16* qb, const float* hmat, const float*
   const int per_sm = (lay.total <= 110 * 1024) ? 2 : 1;
   const int cap = kNumSMsB200 * per_sm;
   const int grid = d.B < cap ? d.B : cap;
-  bilinear_fwd_kernel<<<grid, kThreads, lay.total, stream>>>(vb, qb, hmat, hbias, rowmask, logits, d);
+  launch_pdl(bilinear_fwd_kernel, dim3(grid), dim3(kThreads), lay.total, stream, vb, qb, hmat, hbias, rowmask, logits, d);
   return check_launch("bilinear_fwd_kernel");
 }
 
@@ -367,7 +369,7 @@ int bilinear_bwd(const bf16* vb, const bf16* qb, const float* hmat, const float*
   cudaError_t e = cudaFuncSetAttribute(bilinear_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
   if (e != cudaSuccess) { set_error("bilinear_bwd smem attr: %s", cudaGetErrorString(e)); return (int)e; }
   const int grid = d.B < kNumSMsB200 ? d.B : kNumSMsB200;
-  bilinear_bwd_kernel<<<grid, kThreads, lay.total, stream>>>(vb, qb, hmat, dlogits, dzv, dzq, dbv, dbq, dhmat, dhbias, d);
+  launch_pdl(bilinear_bwd_kernel, dim3(grid), dim3(kThreads), lay.total, stream, vb, qb, hmat, dlogits, dzv, dzq, dbv, dbq, dhmat, dhbias, d);
   return check_launch("bilinear_bwd_kernel");
 }
 

@@ -107,6 +107,7 @@ bilinear_tc_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_cons
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_prologue_done();      // everything above touched only this CTA's shared memory / TMEM
 
   const int n_my = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int total = n_my * p.nchunks;
@@ -374,7 +375,7 @@ int launch_bi(const bf16* vb, const bf16* qb, BiTcParams p, cudaStream_t stream,
     attr_set = true;
   }
   const int grid = p.B < kNumSMsB200 ? p.B : kNumSMsB200;
-  bilinear_tc_kernel<BWD><<<grid, BWD ? 512 : 384, smem, stream>>>(tv, tq, p);
+  launch_pdl(bilinear_tc_kernel<BWD>, dim3(grid), dim3(BWD ? 512 : 384), smem, stream, tv, tq, p);
   return check_launch(who);
 }
 

@@ -66,6 +66,35 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // --------------------------------------------------------------------------- //
+// Programmatic dependent launch.  Every kernel of the library is launched with launch_pdl(): it may begin (block
+// scheduling, and in the TMA / tcgen05 kernels the prologue: barrier init, TMEM allocation, descriptor prefetch)
+// while the previous kernel of the stream is still draining.  pdl_wait() returns once that kernel has completed and
+// its writes are visible -- it precedes the first global-memory access of every kernel; pdl_launch_dependents() lets
+// the NEXT kernel start early in the same way.  Both are no-ops when the neighbour is not a PDL launch.
+// --------------------------------------------------------------------------- //
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue_done() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);      // errors surface in check_launch()
+}
+
+// --------------------------------------------------------------------------- //
 // mbarrier
 // --------------------------------------------------------------------------- //
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {

@@ -15,6 +15,7 @@ namespace {
 // ------------------------------------------------------------------------- //
 __global__ void __launch_bounds__(256) cast_rows_mask_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                              uint8_t* __restrict__ rowmask, long rows, int cols) {
+  pdl_prologue_done();
   const int lane = threadIdx.x & 31;
   const long row = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -93,6 +94,7 @@ __device__ __forceinline__ float4 dropout_scale4(const DropoutRng& r, uint64_t q
 __global__ void __launch_bounds__(256) cast_rows_dropout_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                                 uint8_t* __restrict__ rowmask, long rows, int cols,
                                                                 const DropoutRng rng) {
+  pdl_prologue_done();
   const int lane = threadIdx.x & 31;
   const long row = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -120,6 +122,7 @@ __global__ void __launch_bounds__(256) cast_rows_dropout_kernel(const float* __r
 
 // x[e] *= keep(e) / (1 - p), fp32 in place: backward of the input dropout (n % 4 == 0)
 __global__ void __launch_bounds__(256) dropout_f32_kernel(float* __restrict__ x, long n4, const DropoutRng rng) {
+  pdl_prologue_done();
   const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   float4 v = reinterpret_cast<float4*>(x)[i];
@@ -131,6 +134,7 @@ __global__ void __launch_bounds__(256) dropout_f32_kernel(float* __restrict__ x,
 // out = dropout(x), bf16 (n % 4 == 0); out may alias x
 __global__ void __launch_bounds__(256) dropout_bf16_kernel(const __nv_bfloat16* x, __nv_bfloat16* out, long n4,
                                                            const DropoutRng rng) {
+  pdl_prologue_done();
   const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const uint2 u = reinterpret_cast<const uint2*>(x)[i];
@@ -148,6 +152,7 @@ __global__ void __launch_bounds__(256) dropout_bf16_kernel(const __nv_bfloat16* 
 //   reduce: acc[row, c] += sum_j dxt[row, j * cols + c] * keep_{r0 + j}[row, c] / (1 - p)       (fp32 accumulate)
 __global__ void __launch_bounds__(256) dropout_expand_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ xt,
                                                              long rows, int cols4, int RG, int r0, const DropoutRng rng) {
+  pdl_prologue_done();
   const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;      // (row, quad of 4 columns)
   if (i >= rows * cols4) return;
   const long row = i / cols4;
@@ -165,6 +170,7 @@ __global__ void __launch_bounds__(256) dropout_expand_kernel(const __nv_bfloat16
 
 __global__ void __launch_bounds__(256) dropout_reduce_kernel(const __nv_bfloat16* __restrict__ dxt, float* __restrict__ acc,
                                                              long rows, int cols4, int RG, int r0, const DropoutRng rng) {
+  pdl_prologue_done();
   const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= rows * cols4) return;
   const long row = i / cols4;
@@ -186,6 +192,7 @@ constexpr int kSeg = 4096;   // elements reduced by one block
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ v, const float* __restrict__ w2,
                                                     float* __restrict__ partial, long group_elems, int segs_per_group) {
+  pdl_prologue_done();
   // partial[group * segs + seg] = sum over the segment of v*w2 (w2 == v for the squared norm, == dW for <dW,V>).
   // No atomics: the same weights always give the same norm, hence the same bf16 pack (runs are reproducible).
   const int group = blockIdx.x / segs_per_group;
@@ -235,6 +242,7 @@ __device__ __forceinline__ float group_total(const float* __restrict__ partial, 
 __global__ void __launch_bounds__(256) wn_scale_kernel(const float* __restrict__ v, const float* __restrict__ g,
                                                        float* __restrict__ sumsq, const float* __restrict__ partial, int segs,
                                                        __nv_bfloat16* __restrict__ w, long group_elems, long total) {
+  pdl_prologue_done();
   __shared__ float sh[9];
   const long i0 = static_cast<long>(blockIdx.x) * 1024;
   long i = i0 + threadIdx.x * 4;
@@ -256,6 +264,7 @@ __global__ void __launch_bounds__(256) wn_grad_kernel(const float* __restrict__ 
                                                       const float* __restrict__ g, const float* __restrict__ sumsq,
                                                       const float* __restrict__ partial, int segs, float* __restrict__ dv,
                                                       float* __restrict__ dg, long group_elems, long total) {
+  pdl_prologue_done();
   __shared__ float sh[9];
   const long i0 = static_cast<long>(blockIdx.x) * 1024;
   long i = i0 + threadIdx.x * 4;
@@ -288,6 +297,7 @@ template <bool DY_BF16>
 __global__ void __launch_bounds__(256) act_bwd_bias_kernel(const void* __restrict__ dy_, const __nv_bfloat16* __restrict__ y,
                                                            __nv_bfloat16* __restrict__ dz, float* __restrict__ dbias,
                                                            long rows, int cols) {
+  pdl_prologue_done();
   const int c = (blockIdx.x * 256 + threadIdx.x) * 2;
   if (c >= cols) return;   // cols is even (checked by the caller)
   const long r0 = static_cast<long>(blockIdx.y) * kActRows;
@@ -321,6 +331,7 @@ __global__ void __launch_bounds__(256) act_bwd_bias_kernel(const void* __restric
 // one v sample (v_rep of the contraction / pooling kernels) back onto that sample.  8 elements (16 bytes) per thread.
 __global__ void __launch_bounds__(256)
 sum_row_groups_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, long groups, int rep, long row_vec) {
+  pdl_prologue_done();
   const long i = blockIdx.x * 256l + threadIdx.x;
   if (i >= groups * row_vec) return;
   const long g = i / row_vec, e = i - g * row_vec;
@@ -353,7 +364,7 @@ int cast_rows_mask(const float* x, __nv_bfloat16* out, uint8_t* rowmask, long ro
   const int warps = 8;
   const long blocks = (rows + warps - 1) / warps;
   CTI_REQUIRE(blocks < (1l << 31), "cast_rows_mask: too many rows");
-  cast_rows_mask_kernel<<<(unsigned)blocks, warps * 32, 0, s>>>(x, out, rowmask, rows, cols);
+  launch_pdl(cast_rows_mask_kernel, dim3((unsigned)blocks), dim3(warps * 32), 0, s, x, out, rowmask, rows, cols);
   return check_launch("cast_rows_mask_kernel");
 }
 
@@ -365,7 +376,7 @@ int cast_rows_dropout(const float* x, __nv_bfloat16* out, uint8_t* rowmask, long
   CTI_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0, "cast_rows_dropout: buffers must be 16-byte aligned");
   const long blocks = (rows + 7) / 8;
   CTI_REQUIRE(blocks < (1l << 31), "cast_rows_dropout: too many rows");
-  cast_rows_dropout_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, out, rowmask, rows, cols, make_rng(p, seed, offset));
+  launch_pdl(cast_rows_dropout_kernel, dim3((unsigned)blocks), dim3(256), 0, s, x, out, rowmask, rows, cols, make_rng(p, seed, offset));
   return check_launch("cast_rows_dropout_kernel");
 }
 
@@ -376,7 +387,7 @@ int sum_row_groups(const __nv_bfloat16* x, __nv_bfloat16* out, long groups, int 
   CTI_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0, "sum_row_groups: buffers must be 16-byte aligned");
   const long n = groups * (row_elems / 8);
   CTI_REQUIRE((n + 255) / 256 < (1l << 31), "sum_row_groups: too many elements");
-  sum_row_groups_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(x),
+  launch_pdl(sum_row_groups_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, reinterpret_cast<const uint4*>(x),
                                                                    reinterpret_cast<uint4*>(out), groups, rep, row_elems / 8);
   return check_launch("sum_row_groups_kernel");
 }
@@ -384,7 +395,7 @@ int sum_row_groups(const __nv_bfloat16* x, __nv_bfloat16* out, long groups, int 
 int dropout_f32(float* x, long n, float p, uint64_t seed, uint64_t offset, cudaStream_t s) {
   CTI_REQUIRE(n >= 0 && (n & 3) == 0 && p >= 0.f && p < 1.f, "dropout_f32: bad arguments (n=%ld, p=%f)", n, p);
   if (n == 0) return 0;
-  dropout_f32_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, s>>>(x, n / 4, make_rng(p, seed, offset));
+  launch_pdl(dropout_f32_kernel, dim3((unsigned)((n / 4 + 255) / 256)), dim3(256), 0, s, x, n / 4, make_rng(p, seed, offset));
   return check_launch("dropout_f32_kernel");
 }
 
@@ -392,7 +403,7 @@ int dropout_bf16(const __nv_bfloat16* x, __nv_bfloat16* out, long n, float p, ui
                  cudaStream_t s) {
   CTI_REQUIRE(n >= 0 && (n & 3) == 0 && p >= 0.f && p < 1.f, "dropout_bf16: bad arguments (n=%ld, p=%f)", n, p);
   if (n == 0) return 0;
-  dropout_bf16_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, s>>>(x, out, n / 4, make_rng(p, seed, offset));
+  launch_pdl(dropout_bf16_kernel, dim3((unsigned)((n / 4 + 255) / 256)), dim3(256), 0, s, x, out, n / 4, make_rng(p, seed, offset));
   return check_launch("dropout_bf16_kernel");
 }
 
@@ -401,7 +412,7 @@ int dropout_expand(const __nv_bfloat16* x, __nv_bfloat16* xt, long rows, int col
   CTI_REQUIRE(rows >= 0 && cols > 0 && (cols & 3) == 0 && RG > 0 && r0 >= 0 && p >= 0.f && p < 1.f, "dropout_expand: bad arguments");
   if (rows == 0) return 0;
   const long n = rows * (cols / 4);
-  dropout_expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, xt, rows, cols / 4, RG, r0, make_rng(p, seed, offset));
+  launch_pdl(dropout_expand_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, x, xt, rows, cols / 4, RG, r0, make_rng(p, seed, offset));
   return check_launch("dropout_expand_kernel");
 }
 
@@ -410,7 +421,7 @@ int dropout_reduce(const __nv_bfloat16* dxt, float* acc, long rows, int cols, in
   CTI_REQUIRE(rows >= 0 && cols > 0 && (cols & 3) == 0 && RG > 0 && r0 >= 0 && p >= 0.f && p < 1.f, "dropout_reduce: bad arguments");
   if (rows == 0) return 0;
   const long n = rows * (cols / 4);
-  dropout_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dxt, acc, rows, cols / 4, RG, r0, make_rng(p, seed, offset));
+  launch_pdl(dropout_reduce_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, dxt, acc, rows, cols / 4, RG, r0, make_rng(p, seed, offset));
   return check_launch("dropout_reduce_kernel");
 }
 
@@ -428,10 +439,10 @@ int wn_pack(const float* v, const float* g, __nv_bfloat16* w, float* sumsq, int 
   CTI_REQUIRE(ge % 4 == 0, "wn_pack: group size %ld must be a multiple of 4", ge);
   const int segs = (int)((ge + kSeg - 1) / kSeg);
   float* partial = sumsq + n_groups;
-  sumsq_kernel<<<n_groups * segs, 256, 0, s>>>(v, v, partial, ge, segs);
+  launch_pdl(sumsq_kernel, dim3(n_groups * segs), dim3(256), 0, s, v, v, partial, ge, segs);
   int rc = check_launch("sumsq_kernel");
   if (rc) return rc;
-  wn_scale_kernel<<<(unsigned)((total + 1023) / 1024), 256, 0, s>>>(v, g, sumsq, partial, segs, w, ge, total);
+  launch_pdl(wn_scale_kernel, dim3((unsigned)((total + 1023) / 1024)), dim3(256), 0, s, v, g, sumsq, partial, segs, w, ge, total);
   return check_launch("wn_scale_kernel");
 }
 
@@ -443,10 +454,10 @@ int wn_grad(const float* dw, const float* v, const float* g, const float* sumsq,
   CTI_REQUIRE(n_groups > 0 && ge > 0 && ge % 4 == 0, "wn_grad: bad group size %ld", ge);
   const int segs = (int)((ge + kSeg - 1) / kSeg);
   float* partial = dot_ws + n_groups;
-  sumsq_kernel<<<n_groups * segs, 256, 0, s>>>(dw, v, partial, ge, segs);
+  launch_pdl(sumsq_kernel, dim3(n_groups * segs), dim3(256), 0, s, dw, v, partial, ge, segs);
   int rc = check_launch("wn_dot_kernel");
   if (rc) return rc;
-  wn_grad_kernel<<<(unsigned)((total + 1023) / 1024), 256, 0, s>>>(dw, v, g, sumsq, partial, segs, dv, dg, ge, total);
+  launch_pdl(wn_grad_kernel, dim3((unsigned)((total + 1023) / 1024)), dim3(256), 0, s, dw, v, g, sumsq, partial, segs, dv, dg, ge, total);
   return check_launch("wn_grad_kernel");
 }
 
@@ -455,8 +466,8 @@ int act_bwd_bias(const void* dy, int dy_is_bf16, const __nv_bfloat16* y, __nv_bf
   CTI_REQUIRE(rows > 0 && cols > 0 && (cols % 2) == 0, "act_bwd_bias: bad shape rows=%ld cols=%d (cols must be even)", rows,
               cols);
   dim3 grid((cols / 2 + 255) / 256, (unsigned)((rows + kActRows - 1) / kActRows));
-  if (dy_is_bf16) act_bwd_bias_kernel<true><<<grid, 256, 0, s>>>(dy, y, dz, dbias, rows, cols);
-  else            act_bwd_bias_kernel<false><<<grid, 256, 0, s>>>(dy, y, dz, dbias, rows, cols);
+  if (dy_is_bf16) launch_pdl(act_bwd_bias_kernel<true>, dim3(grid), dim3(256), 0, s, dy, y, dz, dbias, rows, cols);
+  else            launch_pdl(act_bwd_bias_kernel<false>, dim3(grid), dim3(256), 0, s, dy, y, dz, dbias, rows, cols);
   return check_launch("act_bwd_bias_kernel");
 }
 

@@ -101,6 +101,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_prologue_done();      // everything above touched only this CTA's shared memory / TMEM
 
   const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
   const int total_tiles = tiles_mn * p.k_splits;
@@ -443,7 +444,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   const long total = (long)p.num_m_blocks * p.num_n_blocks * p.k_splits;
   int sms = g.max_ctas > 0 ? g.max_ctas : kNumSMsB200;
   const int grid = (int)(total < sms ? total : sms);
-  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(ta, tb, tc, p);
+  launch_pdl(kern, dim3(grid), dim3(kGemmThreads), Cfg::SMEM_BYTES, stream, ta, tb, tc, p);
   return check_launch("gemm_bf16_kernel");
 }
 

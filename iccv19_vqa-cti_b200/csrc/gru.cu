@@ -21,6 +21,7 @@ gru_gate_fwd_kernel(const float* __restrict__ gx, long gx_row_stride, const floa
                     const float* __restrict__ h_prev, long hp_row_stride, float* __restrict__ h_out, long ho_row_stride,
                     __nv_bfloat16* __restrict__ h_bf16, __nv_bfloat16* __restrict__ r_s, __nv_bfloat16* __restrict__ z_s,
                     __nv_bfloat16* __restrict__ n_s, __nv_bfloat16* __restrict__ ghn_s, long rows, int H) {
+  pdl_prologue_done();
   const long i = blockIdx.x * 256l + threadIdx.x;
   if (i >= rows * H) return;
   const long b = i / H;
@@ -49,6 +50,7 @@ gru_gate_bwd_kernel(float* __restrict__ dh, const float* __restrict__ dout, long
                     const __nv_bfloat16* __restrict__ z_s, const __nv_bfloat16* __restrict__ n_s,
                     const __nv_bfloat16* __restrict__ ghn_s, __nv_bfloat16* __restrict__ dgx, long dgx_row_stride,
                     __nv_bfloat16* __restrict__ dgh, long rows, int H) {
+  pdl_prologue_done();
   const long i = blockIdx.x * 256l + threadIdx.x;
   if (i >= rows * H) return;
   const long b = i / H;
@@ -80,7 +82,7 @@ int gru_gate_fwd(const float* gx, long gx_row_stride, const float* gh, const flo
   CTI_REQUIRE(rows > 0 && H > 0, "gru_gate_fwd: empty problem");
   const long n = rows * H;
   CTI_REQUIRE((n + 255) / 256 < (1l << 31), "gru_gate_fwd: too many elements");
-  gru_gate_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(gx, gx_row_stride, gh, h_prev, hp_row_stride, h_out,
+  launch_pdl(gru_gate_fwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, gx, gx_row_stride, gh, h_prev, hp_row_stride, h_out,
                                                                   ho_row_stride, h_bf16, r_s, z_s, n_s, ghn_s, rows, H);
   return check_launch("gru_gate_fwd_kernel");
 }
@@ -91,7 +93,7 @@ int gru_gate_bwd(float* dh, const float* dout, long do_row_stride, const float* 
   CTI_REQUIRE(rows > 0 && H > 0, "gru_gate_bwd: empty problem");
   const long n = rows * H;
   CTI_REQUIRE((n + 255) / 256 < (1l << 31), "gru_gate_bwd: too many elements");
-  gru_gate_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dh, dout, do_row_stride, h_prev, hp_row_stride, r_s, z_s,
+  launch_pdl(gru_gate_bwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, dh, dout, do_row_stride, h_prev, hp_row_stride, r_s, z_s,
                                                                   n_s, ghn_s, dgx, dgx_row_stride, dgh, rows, H);
   return check_launch("gru_gate_bwd_kernel");
 }

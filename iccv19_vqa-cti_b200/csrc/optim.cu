@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(256)
 grad_sumsq_multi_kernel(const float* const* __restrict__ g_ptrs, const long* __restrict__ numel,
                         const int* __restrict__ chunk_tensor, const long* __restrict__ chunk_start, int chunk_elems,
                         float* __restrict__ partials) {
+  pdl_prologue_done();
   const int t = chunk_tensor[blockIdx.x];
   const long lo = chunk_start[blockIdx.x];
   const long hi = min(lo + chunk_elems, numel[t]);
@@ -42,6 +43,7 @@ grad_sumsq_multi_kernel(const float* const* __restrict__ g_ptrs, const long* __r
 
 // sumsq[0] = sum of the partials in a fixed order (one block)
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partials, int n, float* __restrict__ sumsq) {
+  pdl_prologue_done();
   float s = 0.f;
   for (int i = threadIdx.x; i < n; i += 256) s += partials[i];
   s = warp_sum(s);
@@ -60,6 +62,7 @@ adamax_multi_kernel(float* const* __restrict__ p_ptrs, const float* const* __res
                     float* const* __restrict__ u_ptrs, const long* __restrict__ numel, const int* __restrict__ chunk_tensor,
                     const long* __restrict__ chunk_start, int chunk_elems, const float* __restrict__ sumsq, float inv_denom,
                     float clip_norm, float clr, float beta1, float beta2, float eps, float* __restrict__ norm_out) {
+  pdl_prologue_done();
   const int t = chunk_tensor[blockIdx.x];
   const long lo = chunk_start[blockIdx.x];
   const long hi = min(lo + chunk_elems, numel[t]);
@@ -104,10 +107,10 @@ adamax_multi_kernel(float* const* __restrict__ p_ptrs, const float* const* __res
 int grad_sumsq_multi(const float* const* g_ptrs, const long* numel, const int* chunk_tensor, const long* chunk_start,
                      int n_chunks, int chunk_elems, float* partials, float* sumsq, cudaStream_t s) {
   CTI_REQUIRE(n_chunks > 0 && chunk_elems > 0, "grad_sumsq_multi: empty chunk table");
-  grad_sumsq_multi_kernel<<<n_chunks, 256, 0, s>>>(g_ptrs, numel, chunk_tensor, chunk_start, chunk_elems, partials);
+  launch_pdl(grad_sumsq_multi_kernel, dim3(n_chunks), dim3(256), 0, s, g_ptrs, numel, chunk_tensor, chunk_start, chunk_elems, partials);
   int rc = check_launch("grad_sumsq_multi_kernel");
   if (rc) return rc;
-  reduce_partials_kernel<<<1, 256, 0, s>>>(partials, n_chunks, sumsq);
+  launch_pdl(reduce_partials_kernel, dim3(1), dim3(256), 0, s, partials, n_chunks, sumsq);
   return check_launch("reduce_partials_kernel");
 }
 
@@ -117,7 +120,7 @@ int adamax_multi(float* const* p_ptrs, const float* const* g_ptrs, float* const*
                  float* norm_out, cudaStream_t s) {
   CTI_REQUIRE(n_chunks > 0 && chunk_elems > 0, "adamax_multi: empty chunk table");
   CTI_REQUIRE(sumsq != nullptr, "adamax_multi: the squared gradient norm (cti_grad_sumsq_multi) is required");
-  adamax_multi_kernel<<<n_chunks, 256, 0, s>>>(p_ptrs, g_ptrs, m_ptrs, u_ptrs, numel, chunk_tensor, chunk_start, chunk_elems,
+  launch_pdl(adamax_multi_kernel, dim3(n_chunks), dim3(256), 0, s, p_ptrs, g_ptrs, m_ptrs, u_ptrs, numel, chunk_tensor, chunk_start, chunk_elems,
                                                sumsq, inv_denom, clip_norm, clr, beta1, beta2, eps, norm_out);
   return check_launch("adamax_multi_kernel");
 }

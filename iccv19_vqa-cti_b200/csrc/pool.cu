@@ -132,6 +132,7 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ 
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_prologue_done();      // everything above touched only this CTA's shared memory / TMEM
 
   const int n_my = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int total = n_my * p.nchunks;
@@ -467,7 +468,7 @@ int launch_pool(const bf16* v, PoolParams p, cudaStream_t stream, const char* wh
     attr_set = true;
   }
   const int grid = p.B < kNumSMsB200 ? p.B : kNumSMsB200;
-  pool_kernel<BWD><<<grid, BWD ? kThreadsBwd : kThreads, smem, stream>>>(tv, tq, ta, p);
+  launch_pdl(pool_kernel<BWD>, dim3(grid), dim3(BWD ? kThreadsBwd : kThreads), smem, stream, tv, tq, ta, p);
   return check_launch(who);
 }
 

@@ -29,6 +29,7 @@ __device__ __forceinline__ float block_reduce(float v, bool is_max, float* sh) {
 // Vector path: len % 4 == 0, len <= kMaxRegLen.
 __global__ void __launch_bounds__(kThreads) softmax_fwd_vec_kernel(const float* __restrict__ logits,
                                                                    float* __restrict__ p, int len) {
+  pdl_prologue_done();
   __shared__ float sh[8];
   const float4* in = reinterpret_cast<const float4*>(logits + static_cast<size_t>(blockIdx.x) * len);
   float4* out = reinterpret_cast<float4*>(p + static_cast<size_t>(blockIdx.x) * len);
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(kThreads) softmax_fwd_vec_kernel(const float* 
 // Generic path: any length, three passes over global/L2.
 __global__ void __launch_bounds__(kThreads) softmax_fwd_gen_kernel(const float* __restrict__ logits,
                                                                    float* __restrict__ p, int len) {
+  pdl_prologue_done();
   __shared__ float sh[8];
   const float* in = logits + static_cast<size_t>(blockIdx.x) * len;
   float* out = p + static_cast<size_t>(blockIdx.x) * len;
@@ -89,6 +91,7 @@ __global__ void __launch_bounds__(kThreads) softmax_fwd_gen_kernel(const float* 
 __global__ void __launch_bounds__(kThreads) softmax_bwd_kernel(const float* __restrict__ p, const float* __restrict__ dp,
                                                                long sb, long sg, long se, float* __restrict__ dlogits,
                                                                int groups, int len, int vec_ok) {
+  pdl_prologue_done();
   __shared__ float sh[8];
   const long b = blockIdx.x / groups;
   const int g = blockIdx.x - static_cast<int>(b) * groups;
@@ -133,8 +136,8 @@ int masked_softmax_fwd(const float* logits, float* p, long rows, int len, cudaSt
   if (rows == 0) return 0;
   CTI_REQUIRE(rows < (1l << 31), "masked_softmax_fwd: too many rows");
   const bool vec = (len % 4 == 0) && len <= kMaxRegLen && (((uintptr_t)logits | (uintptr_t)p) & 15) == 0;
-  if (vec) softmax_fwd_vec_kernel<<<(unsigned)rows, kThreads, 0, s>>>(logits, p, len);
-  else     softmax_fwd_gen_kernel<<<(unsigned)rows, kThreads, 0, s>>>(logits, p, len);
+  if (vec) launch_pdl(softmax_fwd_vec_kernel, dim3((unsigned)rows), dim3(kThreads), 0, s, logits, p, len);
+  else     launch_pdl(softmax_fwd_gen_kernel, dim3((unsigned)rows), dim3(kThreads), 0, s, logits, p, len);
   return check_launch("masked_softmax_fwd");
 }
 
@@ -144,7 +147,7 @@ int masked_softmax_bwd(const float* p, const float* dp, long sb, long sg, long s
   if (batch == 0) return 0;
   CTI_REQUIRE(batch * groups < (1l << 31), "masked_softmax_bwd: too many rows");
   const int aligned = ((((uintptr_t)p | (uintptr_t)dp | (uintptr_t)dlogits) & 15) == 0) ? 1 : 0;
-  softmax_bwd_kernel<<<(unsigned)(batch * groups), kThreads, 0, s>>>(p, dp, sb, sg, se, dlogits, groups, len, aligned);
+  launch_pdl(softmax_bwd_kernel, dim3((unsigned)(batch * groups)), dim3(kThreads), 0, s, p, dp, sb, sg, se, dlogits, groups, len, aligned);
   return check_launch("masked_softmax_bwd");
 }
 

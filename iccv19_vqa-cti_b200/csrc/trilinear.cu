@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 trilinear_fwd_kernel(const bf16* __restrict__ vc, const bf16* __restrict__ qc, const bf16* __restrict__ ac,
                      const bf16* __restrict__ tpack, const uint8_t* __restrict__ rowmask, float* __restrict__ logits,
                      const TriDims dims) {
+  pdl_prologue_done();
   extern __shared__ __align__(128) uint8_t smem[];
   const TriShape s = make_shape(dims);
   const FwdSmem lay = fwd_smem(s);
@@ -242,6 +243,7 @@ trilinear_fwd_kernel(const bf16* __restrict__ vc, const bf16* __restrict__ qc, c
 // dLm[b][k (MT*16)][(a,g,q16)] bf16, zero padded: the matrix form of dlogits (B,G,K,Q,A) fp32.
 __global__ void __launch_bounds__(256) dlogits_to_dlm_kernel(const float* __restrict__ dlogits, bf16* __restrict__ dlm,
                                                              const TriDims d) {
+  pdl_prologue_done();
   const TriShape s = make_shape(d);
   const int NL = s.NT * 16;
   const size_t total = (size_t)s.B * s.K * NL;
@@ -285,6 +287,7 @@ trilinear_bwd_kernel(const bf16* __restrict__ vc, const bf16* __restrict__ qc, c
                      const bf16* __restrict__ tpack, const bf16* __restrict__ dlm, bf16* __restrict__ dzv,
                      bf16* __restrict__ dzq, bf16* __restrict__ dza, float* __restrict__ dbv, float* __restrict__ dbq,
                      float* __restrict__ dba, float* __restrict__ dtpack, const TriDims dims) {
+  pdl_prologue_done();
   extern __shared__ __align__(128) uint8_t smem[];
   const TriShape s = make_shape(dims);
   const BwdSmem lay = bwd_smem(s);
@@ -611,7 +614,7 @@ int trilinear_fwd(const bf16* vc, const bf16* qc, const bf16* ac, const bf16* tp
   cudaError_t e = cudaFuncSetAttribute(trilinear_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
   if (e != cudaSuccess) { set_error("trilinear_fwd smem attr: %s", cudaGetErrorString(e)); return (int)e; }
   const int grid = d.B < kNumSMsB200 ? d.B : kNumSMsB200;
-  trilinear_fwd_kernel<<<grid, kThreads, lay.total, stream>>>(vc, qc, ac, tpack, rowmask, logits, d);
+  launch_pdl(trilinear_fwd_kernel, dim3(grid), dim3(kThreads), lay.total, stream, vc, qc, ac, tpack, rowmask, logits, d);
   return check_launch("trilinear_fwd_kernel");
 }
 
@@ -640,7 +643,7 @@ int trilinear_bwd(const bf16* vc, const bf16* qc, const bf16* ac, const bf16* tp
   const BwdSmem lay = bwd_smem(s);
   CTI_REQUIRE(lay.total <= 227 * 1024, "trilinear_bwd: needs %zu bytes of shared memory (> 227 KB)", lay.total);
   bf16* dlm = static_cast<bf16*>(workspace);
-  dlogits_to_dlm_kernel<<<kNumSMsB200 * 4, 256, 0, stream>>>(dlogits, dlm, d);
+  launch_pdl(dlogits_to_dlm_kernel, dim3(kNumSMsB200 * 4), dim3(256), 0, stream, dlogits, dlm, d);
   if (int rc = check_launch("dlogits_to_dlm_kernel")) return rc;
   {   // tcgen05 fast path (G == 2, A <= 6, K <= 64); other shapes use the generic tensor-core kernel below
     bf16* dn1 = reinterpret_cast<bf16*>(static_cast<uint8_t*>(workspace) + dlm_bytes(d));
@@ -650,7 +653,7 @@ int trilinear_bwd(const bf16* vc, const bf16* qc, const bf16* ac, const bf16* tp
   cudaError_t e = cudaFuncSetAttribute(trilinear_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
   if (e != cudaSuccess) { set_error("trilinear_bwd smem attr: %s", cudaGetErrorString(e)); return (int)e; }
   const int grid = d.B < kNumSMsB200 ? d.B : kNumSMsB200;
-  trilinear_bwd_kernel<<<grid, kThreads, lay.total, stream>>>(vc, qc, ac, tpack, dlm, dzv, dzq, dza, dbv, dbq, dba,
+  launch_pdl(trilinear_bwd_kernel, dim3(grid), dim3(kThreads), lay.total, stream, vc, qc, ac, tpack, dlm, dzv, dzq, dza, dbv, dbq, dba,
                                                             dtpack, d);
   return check_launch("trilinear_bwd_kernel");
 }

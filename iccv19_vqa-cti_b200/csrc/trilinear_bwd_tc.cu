@@ -161,6 +161,7 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_prologue_done();      // everything above touched only this CTA's shared memory / TMEM
 
   const int n_my = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int U = n_my * p.R;
@@ -620,6 +621,7 @@ trilinear_bwd2_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_prologue_done();      // everything above touched only this CTA's shared memory / TMEM
 
   const int n_my = (p.B - chunk + p.n_chunks - 1) / p.n_chunks;      // samples chunk, chunk + n_chunks, ...
   const int n_pairs = (n_my + 1) >> 1;
@@ -779,14 +781,14 @@ int trilinear_bwd_tc(const bf16* vc, const bf16* qc, const bf16* ac, const bf16*
   }
   Bwd1Params p1{dzv, dzq, dn1, dbv, dbq, d.B, d.K, d.Q, d.A, d.R, N, d.VR};
   const int grid1 = d.B < kNumSMsB200 ? d.B : kNumSMsB200;
-  trilinear_bwd1_tc_kernel<<<grid1, kThreads1, kSmem1, stream>>>(tt, tv, tq, ta, tdl, p1);
+  launch_pdl(trilinear_bwd1_tc_kernel, dim3(grid1), dim3(kThreads1), kSmem1, stream, tt, tv, tq, ta, tdl, p1);
   if (int rc = check_launch("trilinear_bwd1_tc_kernel")) return rc;
   int n_chunks = kNumSMsB200 / d.R;
   if (n_chunks < 1) n_chunks = 1;
   if (n_chunks > (d.B + 1) / 2) n_chunks = (d.B + 1) / 2;
   if (n_chunks < 1) n_chunks = 1;
   Bwd2Params p2{dza, dba, dtpack, d.B, d.A, d.R, n_chunks};
-  trilinear_bwd2_tc_kernel<<<d.R * n_chunks, kThreads2, kSmem2, stream>>>(tt, tdn, ta8, p2);
+  launch_pdl(trilinear_bwd2_tc_kernel, dim3(d.R * n_chunks), dim3(kThreads2), kSmem2, stream, tt, tdn, ta8, p2);
   return check_launch("trilinear_bwd2_tc_kernel");
 }
 

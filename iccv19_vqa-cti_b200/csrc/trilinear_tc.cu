@@ -125,6 +125,7 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_prologue_done();      // everything above touched only this CTA's shared memory / TMEM
 
   const int n_my = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int U = n_my * p.R;                       // (sample, rank) steps of this CTA
@@ -370,7 +371,7 @@ int trilinear_fwd_tc(const bf16* vc, const bf16* qc, const bf16* ac, const bf16*
     smem_set = smem;
   }
   const int grid = d.B < kNumSMsB200 ? d.B : kNumSMsB200;
-  trilinear_fwd_tc_kernel<<<grid, kThreads, smem, stream>>>(tt, tv, tq, ta, p);
+  launch_pdl(trilinear_fwd_tc_kernel, dim3(grid), dim3(kThreads), smem, stream, tt, tv, tq, ta, p);
   return check_launch("trilinear_fwd_tc_kernel");
 }
 
