@@ -290,20 +290,21 @@ __global__ void __launch_bounds__(256) wn_grad_kernel(const float* __restrict__ 
 
 // ------------------------------------------------------------------------- //
 // dz[m,n] = dy[m,n] * (y[m,n] > 0);  dbias[n] += sum_m dz[m,n].
-// Block = 256 threads x 2 columns = 512-column slab, 32 rows per block.
-constexpr int kActRows = 32;
+// Block = 256 threads x 2 columns = 512-column slab, rows_per_block rows (chosen by the host so that the grid is a
+// few waves of 148 SMs: every block ends with one atomic per column, and 1600 blocks hammering the same 512 addresses
+// held the column-sum pass at 1.3 TB/s).
 
 template <bool DY_BF16>
 __global__ void __launch_bounds__(256) act_bwd_bias_kernel(const void* __restrict__ dy_, const __nv_bfloat16* __restrict__ y,
                                                            __nv_bfloat16* __restrict__ dz, float* __restrict__ dbias,
-                                                           long rows, int cols) {
+                                                           long rows, int cols, int rows_per_block) {
   pdl_prologue_done();
   const int c = (blockIdx.x * 256 + threadIdx.x) * 2;
   if (c >= cols) return;   // cols is even (checked by the caller)
-  const long r0 = static_cast<long>(blockIdx.y) * kActRows;
-  const long r1 = min(r0 + kActRows, rows);
+  const long r0 = static_cast<long>(blockIdx.y) * rows_per_block;
+  const long r1 = min(r0 + rows_per_block, rows);
   float s0 = 0.f, s1 = 0.f;
-#pragma unroll 4
+#pragma unroll 8
   for (long r = r0; r < r1; ++r) {
     const long off = r * cols + c;
     float2 d;
@@ -465,9 +466,12 @@ int act_bwd_bias(const void* dy, int dy_is_bf16, const __nv_bfloat16* y, __nv_bf
                  int cols, cudaStream_t s) {
   CTI_REQUIRE(rows > 0 && cols > 0 && (cols % 2) == 0, "act_bwd_bias: bad shape rows=%ld cols=%d (cols must be even)", rows,
               cols);
-  dim3 grid((cols / 2 + 255) / 256, (unsigned)((rows + kActRows - 1) / kActRows));
-  if (dy_is_bf16) launch_pdl(act_bwd_bias_kernel<true>, dim3(grid), dim3(256), 0, s, dy, y, dz, dbias, rows, cols);
-  else            launch_pdl(act_bwd_bias_kernel<false>, dim3(grid), dim3(256), 0, s, dy, y, dz, dbias, rows, cols);
+  const int gx = (cols / 2 + 255) / 256;
+  long rpb = (rows * gx + 4 * kNumSMsB200 - 1) / (4 * kNumSMsB200);       // ~4 waves of blocks
+  rpb = rpb < 32 ? 32 : (rpb > 512 ? 512 : rpb);
+  dim3 grid(gx, (unsigned)((rows + rpb - 1) / rpb));
+  if (dy_is_bf16) launch_pdl(act_bwd_bias_kernel<true>, dim3(grid), dim3(256), 0, s, dy, y, dz, dbias, rows, cols, (int)rpb);
+  else            launch_pdl(act_bwd_bias_kernel<false>, dim3(grid), dim3(256), 0, s, dy, y, dz, dbias, rows, cols, (int)rpb);
   return check_launch("act_bwd_bias_kernel");
 }
 
