@@ -7,7 +7,6 @@ DESIGN.md): attention maps are views of a (B, G, domain) buffer, so ``att[..., g
 """
 from __future__ import annotations
 
-import torch
 import torch.nn as nn
 
 from . import functions as F_

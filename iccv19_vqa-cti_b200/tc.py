@@ -6,7 +6,6 @@ so ``state_dict()`` round-trips with reference checkpoints.
 """
 from __future__ import annotations
 
-from typing import List, Optional
 
 import torch
 import torch.nn as nn

@@ -1,5 +1,5 @@
 """Timing of the BAN student's hot path (BiAttention + 2 x BCNet pooling + q_prj), fwd+bwd, BASELINE config 3."""
-import os, sys, time
+import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch, cti_b200
