@@ -426,7 +426,7 @@ def run_b200(args):
         run_fwd = fwd_only
         if use_graph:
             try:
-                run_fwd = cti_b200.GraphedStep(fwd_only, [], [v_d]).replay     # inference: weight packs stay cached
+                run_fwd = cti_b200.GraphedStep(fwd_only, [], [v_d, q_d, a_d]).replay   # inference: weight packs stay cached
                 for _ in range(3):
                     run_fwd()
             except Exception:

@@ -28,15 +28,18 @@ def reset_caches(modules: Iterable[torch.nn.Module], tensors: Iterable[torch.Ten
             if hasattr(m, "_rank_pack"):
                 m._rank_pack = None
     for t in tensors:
-        if hasattr(t, _fc._FEAT_ATTR):
-            delattr(t, _fc._FEAT_ATTR)
+        for attr in (_fc._FEAT_ATTR, "_cti_b200_tok"):
+            if hasattr(t, attr):
+                delattr(t, attr)
 
 
 class GraphedStep:
     """``GraphedStep(step, modules, static_tensors)``: warm ``step`` up on a side stream, capture it, then
     ``replay()``.  ``step`` must read its inputs from static tensors (copy new data into them before a
     replay, or make the host-to-device copies part of ``step``) and must set ``p.grad = None`` itself if it
-    runs a backward pass."""
+    runs a backward pass.  List every input tensor object the step hands to the modules in ``static_tensors``:
+    their cached bf16 copies (image features, question / answer tokens) are dropped before capture so that the
+    casts are part of the graph."""
 
     def __init__(self, step: Callable[[], object], modules: Iterable[torch.nn.Module],
                  static_tensors: Iterable[torch.Tensor] = (), warmup: int = 3):
