@@ -146,3 +146,80 @@ def test_split_heuristic_fills_waves():
         if tiles < 148:
             assert units / (-(-units // 148) * 148) >= 0.8
     assert F_._pick_splits(4, 4) == 1                                      # too few k-blocks to split
+
+
+# --------------------------------------------------------------------------- #
+# the header is a C interface; the rows next to the path keep the reference's parameter names
+# --------------------------------------------------------------------------- #
+def test_header_is_plain_c(tmp_path):
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "cti_sm100.h"\nint main(void) { int (*f)(void) = cti_version; (void)f; return 0; }\n')
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+NEXT = os.path.join(ROOT, "tests", "golden", "next_golden.pt")
+
+
+def test_next_row_modules_keep_reference_state_dict_keys():
+    import types
+    g = torch.load(NEXT)
+    args = types.SimpleNamespace(activation="relu", dropout=0.5)
+    i, h, o = g["clf_mc"]["dims"]
+    clf = cti_b200.SimpleClassifier(i, h, o, args)
+    assert [(k, tuple(v.shape)) for k, v in clf.state_dict().items()] == \
+        [(k, tuple(v.shape)) for k, v in g["clf_mc"]["sd"].items()]
+    din, hid = g["gru_small"]["dims"]
+    qe = cti_b200.QuestionEmbedding(din, hid, 1, False, .0)
+    assert [(k, tuple(v.shape)) for k, v in qe.state_dict().items()] == \
+        [(k, tuple(v.shape)) for k, v in g["gru_small"]["sd"].items()]
+    assert qe.init_hidden(3).shape == (1, 3, hid)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from mc_model import BanStudent, MCModel
+    for cls, key in ((MCModel, "mc_model"), (BanStudent, "ban_model")):
+        m = cls(**g[key]["args"])
+        assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == \
+            [(k, tuple(v.shape)) for k, v in g[key]["sd"].items()], key
+        m.load_state_dict(g[key]["sd"])                     # the reference's checkpoint loads as is
+
+
+def test_next_row_modules_refuse_cpu_and_unsupported_variants():
+    qe = cti_b200.QuestionEmbedding(24, 32, 1, False, .0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        qe.forward_all(torch.randn(2, 3, 24))
+    with pytest.raises(NotImplementedError):
+        cti_b200.QuestionEmbedding(24, 32, 1, False, .0, rnn_type="LSTM")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        cti_b200.FusedClipAdamax([torch.nn.Parameter(torch.zeros(4))])
+    with pytest.raises(AssertionError):
+        import types
+        cti_b200.SimpleClassifier(8, 16, 2, types.SimpleNamespace(activation="gelu", dropout=0.1))
+
+
+def test_reduce_now_leaves_gradients_on_the_bucket_views_and_remembers_sources():
+    """Hook-free path of the reducer (what follows a CUDA-graph replay), single process."""
+    from cti_b200.dp import GradAllReducer
+    ps = [torch.nn.Parameter(torch.zeros(n)) for n in (5, 3, 7)]
+    red = GradAllReducer(ps, bucket_bytes=16)
+    red.set_hooks_enabled(False)
+    src = [torch.full((n,), float(i + 1)) for i, n in enumerate((5, 3, 7))]
+    for p, s in zip(ps, src):
+        p.grad = s
+    red.reduce_now()
+    assert red.slab is not None and red.slab.numel() == 15
+    for p, s in zip(ps, src):
+        assert torch.equal(p.grad, s) and p.grad.data_ptr() != s.data_ptr()          # now a view of the slab
+    for s in src:                                                                    # a "replay" refills the same tensors
+        s.mul_(3.0)
+    red.reduce_now()
+    for i, p in enumerate(ps):
+        assert torch.equal(p.grad, torch.full_like(p.grad, 3.0 * (i + 1)))
+    ps[1].grad = torch.full((3,), -1.0)                                              # an eager backward takes over
+    red.reduce_now()
+    assert torch.equal(ps[1].grad, torch.full((3,), -1.0))
