@@ -474,9 +474,12 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
   CTI_REQUIRE(g.out_bf16 != nullptr || g.out_f32 != nullptr, "gemm: no output buffer");
   CTI_REQUIRE(!g.atomic_f32 || g.out_f32 != nullptr, "gemm: split-K accumulation needs an fp32 output");
   CTI_REQUIRE(g.atomic_f32 || g.k_splits <= 1, "gemm: k_splits > 1 needs atomic_f32");
-  // Small-N problems and small grids use the 128-wide tile so more CTAs get work.
+  // Small-N problems and very small grids use the 128-wide tile so more CTAs get work.  Measured (tools/tile_sweep.py):
+  // the 256-wide tile wins from ~64 tiles on (6144 x 512 x 1024: 11.3 vs 15.0 us; the GRU step 1024 x 3072 x 1024:
+  // 11.4 vs 15.4 us) even though the grid no longer fills 148 SMs -- half as many B-operand bytes per FLOP; below
+  // that (1024 x 1024 x 1024, 32 tiles) the narrow tile is ahead by ~1 us.
   const long tiles256 = (long)((g.M + BLOCK_M - 1) / BLOCK_M) * ((g.N + 255) / 256) * (g.k_splits < 1 ? 1 : g.k_splits);
-  const bool use256 = (g.tile_n == 256) || (g.tile_n == 0 && g.N >= 256 && tiles256 >= 2 * kNumSMsB200);
+  const bool use256 = (g.tile_n == 256) || (g.tile_n == 0 && g.N >= 256 && tiles256 >= 64);
   if (use256) {
     if (!g.a_mn_major && !g.b_mn_major) return launch_gemm<256, false, false>(g, stream);
     if (!g.a_mn_major && g.b_mn_major) return launch_gemm<256, false, true>(g, stream);
