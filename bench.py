@@ -192,7 +192,8 @@ def run_b200(args):
     out_h = torch.empty(B, HID).pin_memory()
 
     def step(v, q, a):
-        for p in params:
+        cti_b200.prepack(mods)                   # every weight-norm fold of the step in two launches (a training step
+        for p in params:                         # would do this right after the optimizer update)
             p.grad = None
         q.requires_grad_(True)
         a.requires_grad_(True)

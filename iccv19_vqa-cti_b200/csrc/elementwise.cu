@@ -328,6 +328,58 @@ __global__ void __launch_bounds__(256) act_bwd_bias_kernel(const void* __restric
   }
 }
 
+// ------------------------------------------------------------------------- //
+// The fold of MANY layers in two launches (one entry = one group with its own scalar g; the R per-rank nets of a
+// TCNet modality are R entries that write into one stacked pack).  Same arithmetic, in the same order, as
+// sumsq_kernel + wn_scale_kernel: a layer packed here is bit-identical to the same layer packed on its own.
+struct WnMultiTable {
+  const float* const* v;        // [entries] weight_v of the entry
+  const float* const* g;        // [entries] its scalar weight_g
+  __nv_bfloat16* const* w;      // [entries] where its bf16 W_eff goes
+  float* const* sumsq;          // [entries] where ||V||_F^2 goes (kept for the backward)
+  const long* elems;            // [entries] elements of the entry (multiple of 4)
+  const int* first_seg;         // [entries] index of its first partial
+  const int* n_seg;             // [entries] number of kSeg-element segments
+};
+
+__global__ void __launch_bounds__(256) wn_multi_sumsq_kernel(const WnMultiTable t, const int* __restrict__ seg_entry,
+                                                             const int* __restrict__ seg_index, float* __restrict__ partial) {
+  pdl_prologue_done();
+  const int e = seg_entry[blockIdx.x];
+  const float* v = t.v[e];
+  const long lo = static_cast<long>(seg_index[blockIdx.x]) * kSeg;
+  const long hi = min(lo + kSeg, t.elems[e]);
+  float s = 0.f;
+  for (long i = lo + threadIdx.x; i < hi; i += blockDim.x) s += v[i] * v[i];
+  s = warp_sum(s);
+  __shared__ float part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float x = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
+    x = warp_sum(x);
+    if (threadIdx.x == 0) partial[blockIdx.x] = x;
+  }
+}
+
+__global__ void __launch_bounds__(256) wn_multi_scale_kernel(const WnMultiTable t, const int* __restrict__ blk_entry,
+                                                             const int* __restrict__ blk_index,
+                                                             const float* __restrict__ partial) {
+  pdl_prologue_done();
+  __shared__ float sh[9];
+  const int e = blk_entry[blockIdx.x];
+  const float n2 = group_total(partial + t.first_seg[e], t.n_seg[e], 0, 0, sh);     // the entry's partials, fixed order
+  const long i = static_cast<long>(blk_index[blockIdx.x]) * 1024 + threadIdx.x * 4;
+  if (i >= t.elems[e]) return;
+  if (i == 0) *t.sumsq[e] = n2;
+  const float s = *t.g[e] * rsqrtf(n2);
+  const float4 f = *reinterpret_cast<const float4*>(t.v[e] + i);
+  uint2 u;
+  u.x = pack_bf16x2(f.x * s, f.y * s);
+  u.y = pack_bf16x2(f.z * s, f.w * s);
+  *reinterpret_cast<uint2*>(t.w[e] + i) = u;
+}
+
 // out[g, e] = sum_{j < rep} x[g * rep + j, e]  (bf16 in / out, fp32 sum): folds the per-row gradients of rows that share
 // one v sample (v_rep of the contraction / pooling kernels) back onto that sample.  8 elements (16 bytes) per thread.
 __global__ void __launch_bounds__(256)
@@ -424,6 +476,23 @@ int dropout_reduce(const __nv_bfloat16* dxt, float* acc, long rows, int cols, in
   const long n = rows * (cols / 4);
   launch_pdl(dropout_reduce_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, dxt, acc, rows, cols / 4, RG, r0, make_rng(p, seed, offset));
   return check_launch("dropout_reduce_kernel");
+}
+
+int wn_pack_multi(const void* v_ptrs, const void* g_ptrs, const void* w_ptrs, const void* sumsq_ptrs, const long* elems,
+                  const int* first_seg, const int* n_seg, const int* seg_entry, const int* seg_index, int n_segs,
+                  const int* blk_entry, const int* blk_index, int n_blks, float* partials, cudaStream_t s) {
+  CTI_REQUIRE(n_segs > 0 && n_blks > 0, "wn_pack_multi: empty table");
+  WnMultiTable t;
+  t.v = static_cast<const float* const*>(v_ptrs);
+  t.g = static_cast<const float* const*>(g_ptrs);
+  t.w = static_cast<__nv_bfloat16* const*>(w_ptrs);
+  t.sumsq = static_cast<float* const*>(sumsq_ptrs);
+  t.elems = elems; t.first_seg = first_seg; t.n_seg = n_seg;
+  launch_pdl(wn_multi_sumsq_kernel, dim3(n_segs), dim3(256), 0, s, t, seg_entry, seg_index, partials);
+  int rc = check_launch("wn_multi_sumsq_kernel");
+  if (rc) return rc;
+  launch_pdl(wn_multi_scale_kernel, dim3(n_blks), dim3(256), 0, s, t, blk_entry, blk_index, static_cast<const float*>(partials));
+  return check_launch("wn_multi_scale_kernel");
 }
 
 size_t wn_scratch_floats(int n_groups, int rows_per_group, int cols) {

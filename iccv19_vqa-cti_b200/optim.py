@@ -23,7 +23,10 @@ _CHUNK = 8192          # elements per thread block
 
 class FusedClipAdamax:
     def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 2e-3, betas=(0.9, 0.999), eps: float = 1e-8,
-                 clip_norm: float = 0.25):
+                 clip_norm: float = 0.25, modules=None):
+        """modules: optional module (or list of modules) whose weight-norm packs are rebuilt right after every update
+        (``prepack``: two launches for all layers instead of two per layer during the next forward pass)."""
+        self.modules = modules
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("optimizer got an empty parameter list")
@@ -99,6 +102,9 @@ class FusedClipAdamax:
                   float(beta2), float(grp["eps"]), self.grad_norm.data_ptr(), s), nbytes=28.0 * n)
         # the kernel wrote through raw pointers: tell autograd / the weight-pack caches that the parameters changed
         torch.autograd.graph.increment_version(self.params)
+        if self.modules is not None:
+            from .prepack import prepack
+            prepack(self.modules)
         return self.grad_norm
 
     def zero_grad(self, set_to_none: bool = True) -> None:

@@ -104,12 +104,15 @@ class TCNet(nn.Module):
             self.__dict__["_rank_params"] = rank_params
         key = tuple(p._version for p in rank_params) + (rank_params[0].data_ptr(),)
         cache = self._rank_pack
-        if cache is not None and cache[0] == key and not torch.is_grad_enabled():
+        if cache is not None and cache[0] == key and cache[2] is not None and not torch.is_grad_enabled():
             (Vvn, gvn, bvn), (Vqn, gqn, bqn), (Van, gan, ban) = cache[2]
         else:
             Vvn, gvn, bvn = self._rank_group(self.v_net)
             Vqn, gqn, bqn = self._rank_group(self.q_net)
             Van, gan, ban = self._rank_group(self.a_net)
+            if cache is not None and cache[0] == key and cache[2] is None:      # packs came from prepack(): add the stacks
+                stacks = [tuple(t.detach() for t in grp) for grp in ((Vvn, gvn, bvn), (Vqn, gqn, bqn), (Van, gan, ban))]
+                cache = self._rank_pack = (key, cache[1], stacks)
         if cache is None or cache[0] != key:
             stacks = [tuple(t.detach() for t in grp) for grp in ((Vvn, gvn, bvn), (Vqn, gqn, bqn), (Van, gan, ban))]
             cache = self._rank_pack = (key, [F_.pack_layer(Vvn, gvn, self.rank), F_.pack_layer(Vqn, gqn, self.rank),

@@ -67,6 +67,16 @@ int cti_dropout_reduce(const void* dxt, float* acc, int64_t rows, int cols, int 
  * consumer block re-reduces itself (two launches per call instead of three).
  * replaces: torch.nn.utils.weight_norm(nn.Linear, dim=None) as used by src/fc.py:22,27. */
 size_t cti_wn_scratch_floats(int n_groups, int rows_per_group, int cols);
+/* The fold of many layers in two launches (all weight packs of a model after an optimizer step).  One entry = one
+ * group: v_ptrs / g_ptrs / w_ptrs / sumsq_ptrs are DEVICE arrays of n_entries device pointers (fp32 weight_v, scalar
+ * weight_g, bf16 destination, fp32 destination of ||V||^2), elems its element count (multiple of 4).  Segment table:
+ * segment s (4096 elements) = (seg_entry[s], seg_index[s]), the segments of an entry are consecutive and start at
+ * first_seg[entry] (n_seg[entry] of them); block table: block b (1024 elements) = (blk_entry[b], blk_index[b]).
+ * partials: n_segs floats of scratch.  Bit-identical to cti_wn_pack of each entry on its own. */
+int cti_wn_pack_multi(const void* v_ptrs_dev, const void* g_ptrs_dev, const void* w_ptrs_dev, const void* sumsq_ptrs_dev,
+                      const int64_t* elems_dev, const int32_t* first_seg_dev, const int32_t* n_seg_dev,
+                      const int32_t* seg_entry_dev, const int32_t* seg_index_dev, int n_segs, const int32_t* blk_entry_dev,
+                      const int32_t* blk_index_dev, int n_blks, float* partials, void* stream);
 int cti_wn_pack(const float* v, const float* g, void* w_eff_bf16, float* sumsq, int n_groups, int rows_per_group,
                 int cols, void* stream);
 /* Backward of the fold: given dW_eff (fp32) returns dV and dg.  dot_ws: cti_wn_scratch_floats() floats of scratch;

@@ -237,3 +237,50 @@ def test_whole_ban_student_with_distillation_loss_against_reference_golden():
     named = [(k, p.grad) for k, p in model.named_parameters() if k in g["grads"]]
     assert len(named) == len(g["grads"]) and all(gr is not None for _, gr in named)
     check_grads_fp32(named, {k: t.float() for k, t in g["grads"].items()})
+
+
+def test_prepack_builds_the_same_packs_as_the_lazy_path_in_two_launches():
+    from cti_b200 import kernels as KS
+    torch.manual_seed(11)
+    mods = torch.nn.ModuleList([cti_b200.TriAttention(2048, 1024, 1024, 512, 1, 32, 2, 1),
+                                cti_b200.TCNet(2048, 1024, 1024, 512, 1, 32, 1, k=2),
+                                cti_b200.FCNet([1024, 1024], '', .2),
+                                cti_b200.SimpleClassifier(1024, 2048, 3129, ARGS)]).to(DEV).eval()
+    att, pool, prj, clf = mods
+    v, q, a = (t.to(DEV) for t in O.synthetic_inputs(4, 20, 12, 6, seed=3))
+
+    def run():
+        p, logits = att(v, q, a)
+        b = pool.forward_with_weights(v, q, a, p[:, :, :, :, 0])
+        return p, logits, clf(prj(b))
+    with torch.no_grad():
+        ref = run()                                              # lazy packs
+    lazy = {id(m): m._pack[1] for m in mods.modules() if isinstance(m, cti_b200.WNLinear) and m._pack is not None}
+    lazy_rank = att.TriAtt._rank_pack[1]
+    cti_b200.reset_caches([mods], [v])
+    KS.STATS.launches = 0
+    cti_b200.prepack(mods)
+    assert KS.STATS.launches == 2
+    n_single = 0
+    for m in mods.modules():
+        if isinstance(m, cti_b200.WNLinear) and id(m) in lazy:
+            assert torch.equal(m._pack[1].w, lazy[id(m)].w) and torch.equal(m._pack[1].sumsq, lazy[id(m)].sumsq)
+            n_single += 1
+    assert n_single == 3 + 3 + 1 + 2                             # tucker x3 (attention), x3 (pooling), q_prj, classifier x2
+    for got, want in zip(att.TriAtt._rank_pack[1], lazy_rank):
+        assert torch.equal(got.w, want.w) and torch.equal(got.sumsq, want.sumsq)
+    with torch.no_grad():
+        again = run()
+    for x, y in zip(again, ref):
+        assert torch.equal(x, y)
+    # training step on primed packs: gradients flow, and an update invalidates / re-primes the caches
+    opt = cti_b200.FusedClipAdamax(mods.parameters(), lr=1e-3, modules=mods)
+    qd = q.clone().requires_grad_(True)
+    p, _ = att(v, qd, a)
+    out = clf(prj(pool.forward_with_weights(v, qd, a, p[:, :, :, :, 1])))
+    out.square().mean().backward()
+    w_before = att.TriAtt.v_tucker.main[1]._pack[1].w.clone()
+    opt.step()
+    lin = att.TriAtt.v_tucker.main[1]
+    assert lin._pack[0] == (lin.weight_v._version, lin.weight_g._version, lin.weight_v.data_ptr())
+    assert not torch.equal(lin._pack[1].w, w_before)
