@@ -526,6 +526,7 @@ def run_b200(args):
 
             def make_fb(vv):
                 def fb():
+                    cti_b200.prepack(model)      # all weight-norm folds of the model, two launches
                     for p in tparams:
                         p.grad = None
                     logits, _ = model(vv, None, q_tok, a_tok)
