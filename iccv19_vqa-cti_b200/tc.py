@@ -44,6 +44,9 @@ class TCNet(nn.Module):
         self.q_tucker = FCNet([q_dim, self.h_dim], act=act, dropout=dropout[0])
         self.a_tucker = FCNet([a_dim, self.h_dim], act=act, dropout=dropout[0])
         if self.h_dim < 1024:                                       # reference src/tc.py:27
+            # the reference builds a_tucker a second time in this branch (src/tc.py:28); doing the same keeps the RNG
+            # consumption -- hence every initial weight under a given seed -- identical to the reference's
+            self.a_tucker = FCNet([a_dim, self.h_dim], act=act, dropout=dropout[0])
             self.v_net = nn.ModuleList([FCNet([self.h_dim, self.hv_dim], act=act, dropout=dropout[1])
                                         for _ in range(rank)])
             self.q_net = nn.ModuleList([FCNet([self.h_dim, self.hq_dim], act=act, dropout=dropout[0])

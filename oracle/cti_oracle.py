@@ -50,16 +50,25 @@ _ROUND = [False]
 
 
 class bf16_rounding:
+    """``keep``: optional predicate on the rounding site's name; sites it rejects stay fp32.  Site names are
+    ``<layer prefix>{x,w,y}`` for the input, folded weight and stored output of a weight-normed layer, and
+    ``core``, ``n1``, ``m``, ``att_w``, ``hq`` for the contraction / pooling operands -- used by
+    tests/test_bf16_emulation_cpu.py to attribute the gradient error to individual rounding points."""
+
+    def __init__(self, keep=None):
+        self.keep = keep
+
     def __enter__(self):
         self.prev = _ROUND[0]
-        _ROUND[0] = True
+        _ROUND[0] = self.keep if self.keep is not None else True
 
     def __exit__(self, *exc):
         _ROUND[0] = self.prev
 
 
-def _r(x: torch.Tensor) -> torch.Tensor:
-    if not _ROUND[0]:
+def _r(x: torch.Tensor, site: str = "") -> torch.Tensor:
+    mode = _ROUND[0]
+    if not mode or (mode is not True and not mode(site)):
         return x
     return x + (x.to(torch.bfloat16).to(x.dtype) - x).detach()
 
@@ -100,13 +109,13 @@ def wn_linear(x: torch.Tensor, p: Params, prefix: str, act: str = "ReLU") -> tor
     v = p[prefix + "weight_v"]
     g = p[prefix + "weight_g"]
     b = p[prefix + "bias"]
-    w = _r(v * (g / v.norm()))
-    y = torch.matmul(_r(x), w.t()) + b
+    w = _r(v * (g / v.norm()), prefix + "w")
+    y = torch.matmul(_r(x, prefix + "x"), w.t()) + b
     if act == "ReLU":
         if _MASKS[0] is not None and prefix in _MASKS[0]:
-            y = _r(y * _MASKS[0][prefix].reshape(y.shape).to(y.dtype))
+            y = _r(y * _MASKS[0][prefix].reshape(y.shape).to(y.dtype), prefix + "y")
         else:
-            y = _r(torch.relu(y))      # fused layers store their (post-ReLU) output in bf16
+            y = _r(torch.relu(y), prefix + "y")      # fused layers store their (post-ReLU) output in bf16
     elif act != "":
         raise ValueError("oracle covers act in {'ReLU',''} only")
     return y
@@ -202,8 +211,8 @@ def tcnet_logits_closed(v, q, a, p: Params, prefix: str = "") -> torch.Tensor:
 def trilinear_closed(vc, qc, ac, t_eff) -> torch.Tensor:
     """logits[b,k,q,a,g] = sum_{r,i,j,l} T_eff[r,i,j,l,g] Vc[b,k,r,i] Qc[b,q,r,j] Ac[b,a,r,l],
     contracted a -> q -> v (the minimal-FLOP order)."""
-    n1 = _r(torch.einsum("balr,rijlg->barijg", ac.permute(0, 1, 3, 2), _r(t_eff)))
-    m = _r(torch.einsum("bqrj,barijg->briqag", qc, n1))
+    n1 = _r(torch.einsum("balr,rijlg->barijg", ac.permute(0, 1, 3, 2), _r(t_eff, "core")), "n1")
+    m = _r(torch.einsum("bqrj,barijg->briqag", qc, n1), "m")
     return torch.einsum("bkri,briqag->bkqag", vc, m)
 
 
@@ -233,7 +242,7 @@ def tcnet_pool(v, q, a, w, p: Params, prefix: str = "") -> torch.Tensor:
 
 
 def trilinear_pool(vp, qp, ap, w) -> torch.Tensor:
-    return torch.einsum("bkc,bkqa,bqc,bac->bc", vp, _r(w), qp, ap)
+    return torch.einsum("bkc,bkqa,bqc,bac->bc", vp, _r(w, "att_w"), qp, ap)
 
 
 # --------------------------------------------------------------------------- #
@@ -256,7 +265,7 @@ def bcnet_logits(v, q, p: Params, prefix: str = "", h_mat: torch.Tensor | None =
 
 def bilinear_closed(vb, qb, h_mat, h_bias) -> torch.Tensor:
     if _ROUND[0]:                                    # the kernel folds h_mat into the question operand
-        hq = _r(qb.unsqueeze(1) * h_mat)             # (B,G,Q,C)
+        hq = _r(qb.unsqueeze(1) * h_mat, "hq")       # (B,G,Q,C)
         return torch.matmul(vb.unsqueeze(1), hq.transpose(2, 3)) + h_bias
     hv = vb.unsqueeze(1) * h_mat                     # (B,G,K,C)
     return torch.matmul(hv, qb.unsqueeze(1).transpose(2, 3)) + h_bias
@@ -278,7 +287,7 @@ def bcnet_pool(v, q, w, p: Params, prefix: str = "", k: int = 1) -> torch.Tensor
     k are sum-pooled (AvgPool1d(k) * k, :75-77)."""
     vp = fcnet(v, p, prefix + "v_net.", dropout=0.2)
     qp = fcnet(q, p, prefix + "q_net.", dropout=0.2)
-    out = torch.einsum("bkc,bkq,bqc->bc", vp, _r(w), qp)
+    out = torch.einsum("bkc,bkq,bqc->bc", vp, _r(w, "att_w"), qp)
     if k > 1:
         out = out.view(out.shape[0], -1, k).sum(2)
     return out
@@ -336,11 +345,11 @@ def gru_forward_all(x: torch.Tensor, p: Params, prefix: str = "rnn.") -> torch.T
     b_ih, b_hh = p[prefix + "bias_ih_l0"], p[prefix + "bias_hh_l0"]
     B, T, _ = x.shape
     H = w_hh.shape[1]
-    gx = torch.matmul(_r(x), _r(w_ih).t()) + b_ih
+    gx = torch.matmul(_r(x, prefix + "x"), _r(w_ih, prefix + "w").t()) + b_ih
     h = x.new_zeros(B, H)
     outs = []
     for t in range(T):
-        gh = torch.matmul(_r(h), _r(w_hh).t()) + b_hh
+        gh = torch.matmul(_r(h, prefix + "h"), _r(w_hh, prefix + "w").t()) + b_hh
         r = torch.sigmoid(gx[:, t, :H] + gh[:, :H])
         z = torch.sigmoid(gx[:, t, H:2 * H] + gh[:, H:2 * H])
         n = torch.tanh(gx[:, t, 2 * H:] + r * gh[:, 2 * H:])

@@ -276,3 +276,34 @@ def test_bilinear_logits_fwd_bwd(B, K, Q, G, C):
     assert rel_err(dbv.cpu(), wv.sum(0)) < 2e-2 and rel_err(dbq.cpu(), wq.sum(0)) < 2e-2
     assert rel_err(dh.cpu(), leaves[2].grad.reshape(G, C)) < 2e-2
     assert rel_err(dhb.cpu(), leaves[3].grad.reshape(G)) < 1e-3
+
+
+# --------------------------------------------------------------------------- #
+def test_pool_kernels_are_bit_repeatable_at_bench_size():
+    """racecheck reports the cp.async.bulk write of the per-stage `dout` chunk against the epilogue's read of it in
+    pool_kernel (tc_tiles.cuh bulk_load_1d vs ld_shared_f32); the two are ordered by the stage's mbarrier
+    (complete_tx -> try_wait on the full barrier, read-side arrive on the empty barrier), which the tool does not
+    model.  A real race would make some of these outputs depend on timing: 100 back-to-back launches at the bench size
+    (1024 rows, the grid wraps 7 times) on two streams' worth of load must be bit-identical.  dbv / dbq / dba are
+    excluded: they are cross-CTA float atomics, whose order is not fixed by design."""
+    B, K, Q, A, C = 1024, 50, 12, 6, 1024
+    g = torch.Generator(device=DEV).manual_seed(11)
+    mk = lambda n: torch.relu(torch.randn(B * n, C, generator=g, device=DEV)).to(torch.bfloat16)
+    v, q, a = mk(K), mk(Q), mk(A)
+    att = torch.softmax(torch.randn(B, 2, K * Q * A, generator=g, device=DEV), 2)
+    w = att[:, 1]
+    dout = torch.randn(B, C, generator=g, device=DEV)
+    out0 = K_.tri_pool_fwd(v, q, a, w, w.stride(0), B, K, Q, A, C)
+    ref = K_.tri_pool_bwd(v, q, a, w, w.stride(0), dout, B, K, Q, A, C)
+    noise = torch.empty(64 << 20, device=DEV)
+    side = torch.cuda.Stream()
+    for it in range(100):
+        if it % 2:                                   # perturb timing: a bandwidth hog on another stream
+            with torch.cuda.stream(side):
+                noise.normal_()
+        out = K_.tri_pool_fwd(v, q, a, w, w.stride(0), B, K, Q, A, C)
+        assert torch.equal(out, out0), it
+        got = K_.tri_pool_bwd(v, q, a, w, w.stride(0), dout, B, K, Q, A, C)
+        for i in (0, 1, 2, 6):                       # dzv, dzq, dza, dw
+            assert torch.equal(got[i], ref[i]), (it, i)
+    torch.cuda.synchronize()

@@ -85,6 +85,7 @@ def check_grads_fp32(named_grads, ref_grads, tol=GRAD_TOL_FP32):
     non-negligible share of the gradient norm."""
     num = sum((g.detach().float().cpu() - ref_grads[k]).pow(2).sum().item() for k, g in named_grads)
     den = sum(ref_grads[k].pow(2).sum().item() for k, _ in named_grads)
+    print(f"\n[flat gradient vs fp32 reference] L2-rel {(num / den) ** 0.5:.4f} (tol {tol})")
     assert (num / den) ** 0.5 <= tol, ("all gradients", (num / den) ** 0.5)
     bad = [(k, round(normrel(g, ref_grads[k]), 4)) for k, g in named_grads
            if ref_grads[k].numel() > 64 and ref_grads[k].pow(2).sum().item() > 1e-4 * den
