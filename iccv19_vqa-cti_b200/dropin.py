@@ -21,15 +21,21 @@ _TARGETS = {
 _IMPORTERS = ("src.MC.base_model", "src.FFOE.base_model", "src.attention", "src.tc", "src.bc")
 
 
-def install() -> None:
-    """Patch the reference package (must be importable as ``src``) to use the sm_100a modules."""
+def install(hot_path_only: bool = False) -> None:
+    """Patch the reference package (must be importable as ``src``) to use the sm_100a modules.
+    hot_path_only: substitute only the classes the north_star names (FCNet, TCNet, TriAttention, BCNet, BiAttention) and
+    leave the rows next to the path -- the GRU ``QuestionEmbedding`` and ``SimpleClassifier`` -- on the reference's own
+    fp32 implementations."""
     from . import attention, bc, classifier, fc, language_model, tc
     ours = {"FCNet": fc.FCNet, "TCNet": tc.TCNet, "BCNet": bc.BCNet, "BiAttention": attention.BiAttention,
-            "TriAttention": attention.TriAttention, "SimpleClassifier": classifier.SimpleClassifier,
-            "QuestionEmbedding": language_model.QuestionEmbedding}
+            "TriAttention": attention.TriAttention}
+    if not hot_path_only:
+        ours.update({"SimpleClassifier": classifier.SimpleClassifier, "QuestionEmbedding": language_model.QuestionEmbedding})
     for modname, names in _TARGETS.items():
         mod = importlib.import_module(modname)
         for n in names:
+            if n not in ours:
+                continue
             _SAVED.setdefault((modname, n), getattr(mod, n))
             setattr(mod, n, ours[n])
     for modname in _IMPORTERS:

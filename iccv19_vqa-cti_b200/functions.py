@@ -30,8 +30,13 @@ class Packed:
 
 
 def pack_layer(V: torch.Tensor, g: torch.Tensor, n_groups: int) -> Packed:
-    """Single layers are padded with zero rows to a multiple of 8 outputs (classifier heads: 2 or 3129 classes)."""
-    w, sumsq = K_.wn_pack(V.detach().contiguous(), g.detach().reshape(n_groups).contiguous(), n_groups,
+    """Single layers are padded with zero rows to a multiple of 8 outputs (classifier heads: 2 or 3129 classes) and
+    with zero columns to a multiple of 8 inputs (``c_prj = FCNet([11, num_hid])``, reference src/MC/base_model.py:176):
+    a TMA operand's row pitch must be a multiple of 16 bytes.  Zero columns leave ||V||_F unchanged."""
+    Vd = V.detach()
+    if n_groups == 1 and Vd.shape[1] % 8:
+        Vd = _pad_cols(Vd, -(-Vd.shape[1] // 8) * 8)
+    w, sumsq = K_.wn_pack(Vd.contiguous(), g.detach().reshape(n_groups).contiguous(), n_groups,
                           pad_rows_to=8 if n_groups == 1 else 1)
     return Packed(w, sumsq)
 
@@ -258,7 +263,9 @@ class WNLinearFn(Function):
     def forward(ctx, x, V, g, bias, relu: bool, pk: Optional[Packed], drop=None):
         if pk is None:
             pk = pack_layer(V, g, 1)
-        xb = cast_in(x, drop)
+        Kp = pk.w.shape[1]                                  # input width padded to a multiple of 8 (zero columns)
+        ctx.kin = x.shape[1]
+        xb = cast_in(x if Kp == x.shape[1] else _pad_cols(x.detach(), Kp), drop)
         ctx.drop = drop
         yb, yf = lin_fwd(xb, pk, bias, relu, out_bf16=relu, out_f32=True)
         ctx.save_for_backward(xb, yb if relu else None, V, g)
@@ -273,9 +280,14 @@ class WNLinearFn(Function):
         N, Np = V.shape[0], ctx.pk.w.shape[0]
         db = torch.zeros((Np,), dtype=F32, device=dy.device)
         dz = K_.act_bwd_bias(_pad_cols(dy, Np).contiguous(), yb if ctx.relu else None, True, db)
-        dV, dg, dx = lin_bwd(xb, dz, V, g, ctx.pk, 1, ctx.need_dx, dx_f32=True)
+        Kin, Kp = ctx.kin, ctx.pk.w.shape[1]
+        Vp = V if Kp == Kin else _pad_cols(V.detach(), Kp)
+        dV, dg, dx = lin_bwd(xb, dz, Vp, g, ctx.pk, 1, ctx.need_dx, dx_f32=True)
         if dx is not None and ctx.drop is not None:
             K_.dropout_f32_(dx, ctx.drop)
+        if Kp != Kin:
+            dV = dV[:, :Kin].contiguous()
+            dx = None if dx is None else dx[:, :Kin].contiguous()
         return dx, dV, dg, db[:N], None, None, None
 
 

@@ -42,8 +42,17 @@ class GraphedStep:
     casts are part of the graph."""
 
     def __init__(self, step: Callable[[], object], modules: Iterable[torch.nn.Module],
-                 static_tensors: Iterable[torch.Tensor] = (), warmup: int = 3):
+                 static_tensors: Iterable[torch.Tensor] = (), warmup: int = 3, allow_fixed_dropout: bool = False):
         modules, static_tensors = list(modules), list(static_tensors)
+        # dropout sites (p, seed, offset) are host scalars baked into the captured launches: a graph captured in
+        # train() mode would replay the SAME masks on every step.  Refuse unless the caller asks for exactly that.
+        if not allow_fixed_dropout:
+            for root in modules:
+                for m in root.modules():
+                    if isinstance(m, torch.nn.Dropout) and m.training and m.p > 0:
+                        raise RuntimeError("GraphedStep: a module is in train() mode with dropout p > 0; a replay would "
+                                           "reuse the captured dropout masks on every step.  Capture in eval() mode, run "
+                                           "the training step eagerly, or pass allow_fixed_dropout=True")
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):

@@ -46,6 +46,9 @@ class GRUParams(nn.Module):
         """(output, h_n) like nn.GRU; ``hidden`` must be None or zeros (all the reference ever passes)."""
         if not x.is_cuda:
             raise RuntimeError("cti_b200 modules run on CUDA tensors only (no CPU fallback)")
+        if hidden is not None and (hidden.requires_grad or bool(torch.count_nonzero(hidden).item())):
+            raise RuntimeError("the accelerated GRU starts from a zero state (reference src/language_model.py:83-84,"
+                               "95-96 always passes init_hidden()); a non-zero or differentiable `hidden` is not supported")
         out = F_.GRUFn.apply(x if x.dtype == torch.float32 else x.float(), self.weight_ih_l0, self.weight_hh_l0,
                              self.bias_ih_l0, self.bias_hh_l0, self.packed())
         return out, out[:, -1].unsqueeze(0)

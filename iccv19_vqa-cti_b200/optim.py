@@ -58,7 +58,12 @@ class FusedClipAdamax:
         self._m_ptrs = i64([m.data_ptr() for m in self.exp_avg])
         self._u_ptrs = i64([u.data_ptr() for u in self.exp_inf])
         self._g_ptrs = torch.zeros(len(self.params), dtype=torch.int64, device=dev)
-        self._g_host = torch.zeros(len(self.params), dtype=torch.int64).pin_memory()
+        # the gradient-pointer table reaches the device by an async copy from pinned memory; the host may run several
+        # steps ahead of the GPU, so the staging buffer is double-buffered and each half is only rewritten after the
+        # copy that last read it has completed (an event per half)
+        self._g_host = [torch.zeros(len(self.params), dtype=torch.int64).pin_memory() for _ in range(2)]
+        self._g_copied = [None, None]
+        self._g_turn = 0
         self._g_key: Optional[tuple] = None
         self._partials = torch.empty(self.n_chunks, dtype=torch.float32, device=dev)
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -76,8 +81,15 @@ class FusedClipAdamax:
             grads.append(g.data_ptr())
         key = tuple(grads)
         if key != self._g_key:                   # bucket views / graph-owned gradients keep their addresses: no copy
-            self._g_host.copy_(torch.tensor(grads, dtype=torch.int64))
-            self._g_ptrs.copy_(self._g_host, non_blocking=True)
+            i = self._g_turn
+            self._g_turn ^= 1
+            if self._g_copied[i] is not None:
+                self._g_copied[i].synchronize()  # the DMA that last read this half is done
+            self._g_host[i].copy_(torch.tensor(grads, dtype=torch.int64))
+            self._g_ptrs.copy_(self._g_host[i], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._g_copied[i] = ev
             self._g_key = key
 
     @torch.no_grad()
@@ -115,14 +127,40 @@ class FusedClipAdamax:
                 p.grad.zero_()
 
     def state_dict(self) -> dict:
-        return {"step": self.step_count, "exp_avg": [m.clone() for m in self.exp_avg],
-                "exp_inf": [u.clone() for u in self.exp_inf],
-                "param_groups": [{k: v for k, v in self.param_groups[0].items() if k != "params"}]}
+        """The layout of ``torch.optim.Adamax.state_dict()`` -- what the reference saves as ``optimizer_state`` and
+        reloads (src/MC/main.py:120, src/FFOE/main.py:127): ``state[i] = {step, exp_avg, exp_inf}`` per parameter in
+        registration order, ``param_groups[0]`` with lr / betas / eps / weight_decay and the parameter indices.
+        ``clip_norm`` rides along as an extra group key (torch ignores unknown keys on load)."""
+        grp = self.param_groups[0]
+        state = {}
+        if self.step_count > 0:
+            for i, (m, u) in enumerate(zip(self.exp_avg, self.exp_inf)):
+                state[i] = {"step": torch.tensor(float(self.step_count)), "exp_avg": m.clone(), "exp_inf": u.clone()}
+        group = {"lr": grp["lr"], "betas": tuple(grp["betas"]), "eps": grp["eps"], "weight_decay": 0, "foreach": None,
+                 "maximize": False, "differentiable": False, "capturable": False, "clip_norm": grp["clip_norm"],
+                 "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group]}
 
     def load_state_dict(self, sd: dict) -> None:
-        self.step_count = int(sd["step"])
-        for dst, src in zip(self.exp_avg, sd["exp_avg"]):
-            dst.copy_(src)
-        for dst, src in zip(self.exp_inf, sd["exp_inf"]):
-            dst.copy_(src)
-        self.param_groups[0].update(sd["param_groups"][0])
+        """Accepts ``torch.optim.Adamax.state_dict()`` (torch 1.1 ... 2.x: ``step`` an int or a tensor) written by the
+        reference trainer or by this class."""
+        groups = sd["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(self.params):
+            raise ValueError("loaded state dict has a different number of parameter groups / parameters")
+        if groups[0].get("weight_decay", 0) != 0:
+            raise ValueError("FusedClipAdamax has no weight decay (the reference trains with weight_decay=0)")
+        steps = set()
+        self._state.zero_()
+        for j, idx in enumerate(groups[0]["params"]):
+            st = sd["state"].get(idx, sd["state"].get(str(idx)))
+            if st is None:
+                continue
+            steps.add(int(st["step"].item() if torch.is_tensor(st["step"]) else st["step"]))
+            self.exp_avg[j].copy_(st["exp_avg"])
+            self.exp_inf[j].copy_(st["exp_inf"])
+        if len(steps) > 1:
+            raise ValueError(f"parameters carry different step counts {sorted(steps)}: the fused update keeps one")
+        self.step_count = steps.pop() if steps else 0
+        for k in ("lr", "betas", "eps", "clip_norm"):
+            if k in groups[0]:
+                self.param_groups[0][k] = tuple(groups[0][k]) if k == "betas" else groups[0][k]

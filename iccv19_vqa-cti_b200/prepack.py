@@ -38,7 +38,10 @@ class _Plan:
                             in_rank.update(id(x) for x in n.modules())
         for root in roots:
             for m in root.modules():
-                if isinstance(m, WNLinear) and id(m) not in in_rank and all(m is not s for s in self.singles):
+                # input widths that are not a multiple of 8 get zero-padded packs (functions.pack_layer): left to the
+                # lazy per-layer path
+                if isinstance(m, WNLinear) and id(m) not in in_rank and m.in_features % 8 == 0 \
+                        and all(m is not s for s in self.singles):
                     self.singles.append(m)
         if not self.singles and not self.tcnets:
             raise RuntimeError("prepack: no weight-normed layers found")

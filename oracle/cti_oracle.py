@@ -358,6 +358,30 @@ def gru_forward_all(x: torch.Tensor, p: Params, prefix: str = "rnn.") -> torch.T
     return torch.stack(outs, 1)
 
 
+def word_embedding(tokens: torch.Tensor, p: Params, prefix: str = "w_emb.") -> torch.Tensor:
+    """``WordEmbedding.forward`` with op 'c' in eval mode (src/language_model.py:42-47): the trainable table and the
+    frozen one, concatenated -> (B, T, 600)."""
+    emb = torch.nn.functional.embedding(tokens, p[prefix + "emb.weight"])
+    if prefix + "emb_.weight" in p:
+        emb = torch.cat((emb, torch.nn.functional.embedding(tokens, p[prefix + "emb_.weight"])), 2)
+    return emb
+
+
+def mc_model_logits(v, q_tok, a_tok, p: Params, glimpse: int):
+    """``TanModel.forward`` (src/MC/base_model.py:134-152): word embeddings -> the two GRUs -> the hot path ->
+    classifier.  Keys as in the reference's ``state_dict()``.  Returns (class logits (B, 2), att)."""
+    q_emb = gru_forward_all(word_embedding(q_tok, p, "w_emb."), p, "q_emb.rnn.")
+    a_emb = gru_forward_all(word_embedding(a_tok, p, "wa_emb."), p, "ans_emb.rnn.")
+    joint, att, _ = cti_hot_path(v, q_emb, a_emb, p, glimpse)
+    return simple_classifier(joint, p, "classifier."), att
+
+
+def mc_answers(logits: torch.Tensor) -> torch.Tensor:
+    """The chosen candidate of each question: argmax over its 4 rows of softmax(logits)[:, 0]
+    (``compute_score_mc``, src/MC/trainer.py:292-299)."""
+    return torch.softmax(logits, 1)[:, 0].view(-1, 4).argmax(1)
+
+
 def trainer_update(params, grads, exp_avg, exp_inf, step: int, lr: float, grad_denom: float, clip_norm: float,
                    beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8) -> float:
     """One update of the reference trainer's tail, in place on lists of fp32 tensors; returns the pre-clip norm.

@@ -9,11 +9,15 @@ Gradients are checked on two tiers, because every projection on this path ends i
   * GRAD_TOL = 3e-2 (max-abs error / max-abs of the reference gradient) against autograd of the oracle
     evaluated with the kernels' bf16 rounding points (``O.bf16_rounding()``): same pre-activation signs,
     hence the same ReLU masks -- this isolates the hand-written backward kernels.
-  * GRAD_TOL_FP32 = 0.12 (L2-norm relative) against the plain fp32 oracle / the reference's own golden
-    gradients.  Rounding the GEMM operands to bf16 flips the sign of ~0.1 % of near-zero pre-activations
-    per layer; each flip switches a gradient entry on or off, which alone costs sqrt(flip fraction) ~ 5 %
-    in norm.  The CPU-only emulation (fp32 oracle vs the same oracle with bf16 operand rounding, no kernel
-    involved) shows the same 5-6 %, see DESIGN.md "Parity".  No bf16-operand forward can meet 3e-2 there."""
+  * GRAD_TOL_FP32 = 3e-2 (the north_star's bound; L2-relative, over the whole flat gradient -- every parameter and
+    dq / da as one vector, which is what the clip and the optimizer consume) against the plain fp32 oracle / the
+    reference's own golden gradients.  Measured on the B200 (round 2): 0.6 % for the hot path at full size, 2.2 % /
+    1.4 % on the small golden models.  Individual small tensors are looser (PER_TENSOR_TOL): rounding the GEMM
+    operands to bf16 flips the sign of ~0.1 % of near-zero pre-activations per layer and each flip switches gradient
+    entries on or off; tests/test_bf16_emulation_cpu.py pins that effect without any kernel and
+    tests/test_gpu_baseline_sizes.py holds every parameter class to 1.5 x the emulated error + 1e-2.
+    BAN (GRAD_TOL_FP32_BAN = 4.5e-2): the depth-3072 bilinear logits reach |logit| ~ 18 in front of a softmax; bf16
+    operand rounding alone gives 3.75 % there (kernels: 3.69 %)."""
 import os
 import sys
 
@@ -31,7 +35,9 @@ from oracle import cti_oracle as O  # noqa: E402
 DEV = "cuda"
 ABS_TOL = 2e-2
 GRAD_TOL = 3e-2
-GRAD_TOL_FP32 = 0.12
+GRAD_TOL_FP32 = 3e-2
+GRAD_TOL_FP32_BAN = 4.5e-2
+PER_TENSOR_TOL = 0.24
 
 
 def rel(x, ref):
@@ -80,7 +86,7 @@ class record_relu_outputs:
         return out
 
 
-def check_grads_fp32(named_grads, ref_grads, tol=GRAD_TOL_FP32):
+def check_grads_fp32(named_grads, ref_grads, tol=GRAD_TOL_FP32, per_tensor=PER_TENSOR_TOL):
     """L2-relative error over all (got, ref) pairs taken together, and per tensor for those that carry a
     non-negligible share of the gradient norm."""
     num = sum((g.detach().float().cpu() - ref_grads[k]).pow(2).sum().item() for k, g in named_grads)
@@ -89,7 +95,7 @@ def check_grads_fp32(named_grads, ref_grads, tol=GRAD_TOL_FP32):
     assert (num / den) ** 0.5 <= tol, ("all gradients", (num / den) ** 0.5)
     bad = [(k, round(normrel(g, ref_grads[k]), 4)) for k, g in named_grads
            if ref_grads[k].numel() > 64 and ref_grads[k].pow(2).sum().item() > 1e-4 * den
-           and normrel(g, ref_grads[k]) > 2 * tol]
+           and normrel(g, ref_grads[k]) > per_tensor]
     assert not bad, bad
 
 
@@ -171,10 +177,10 @@ def pool_prefixes(pre, tri=True):
     return [fc_prefix(pre + "v_net."), fc_prefix(pre + "q_net.")]
 
 
-def compare_all(named, leaf_names, leaves32, g32, leaves16, g16, mods):
+def compare_all(named, leaf_names, leaves32, g32, leaves16, g16, mods, tol32=GRAD_TOL_FP32):
     """tier 2 (fp32 oracle / reference, norm-wise) then tier 1 (same rounding points and ReLU masks, element-wise)."""
     refs32 = {**dict(zip(leaf_names, leaves32)), **g32}
-    check_grads_fp32(named, refs32)
+    check_grads_fp32(named, refs32, tol32)
     got = dict(named)
     for n, ref in zip(leaf_names, leaves16):
         assert rel(got[n], ref) <= GRAD_TOL, (n, rel(got[n], ref))
@@ -264,7 +270,7 @@ def test_bi_attention_and_pool_against_reference_golden(golden):
         return sum((o * ct).sum() for o, ct in zip(outs, g["cot"])), outs
     masks = rec.masks(pool_prefixes("att.logits.", False) + sum([pool_prefixes(f"pool{i}.", False) for i in range(G)], []))
     _, lv16, g16 = run_oracle(fn, params, [g["q"]], rounding=True, masks=masks)
-    compare_all(named, ["dq"], [g["dq"]], g32, lv16, g16, mods)
+    compare_all(named, ["dq"], [g["dq"]], g32, lv16, g16, mods, GRAD_TOL_FP32_BAN)
 
 
 # --------------------------------------------------------------------------- #
@@ -366,7 +372,7 @@ def test_ban_hot_path_against_oracle_full_size():
     masks = rec.masks(pool_prefixes("v_att.logits.", False)
                       + sum([pool_prefixes(f"b_net.{i}.", False) + [None] for i in range(G)], []))
     _, lv16, g16 = run_oracle(fn, params, [q], rounding=True, masks=masks)
-    compare_all(named, ["dq"], lv32, g32, lv16, g16, mods)
+    compare_all(named, ["dq"], lv32, g32, lv16, g16, mods, GRAD_TOL_FP32_BAN)
 
 
 def test_attention_properties_at_bench_size():
