@@ -16,11 +16,12 @@ from .dropin import install, uninstall
 from .fc import FCNet, WNLinear
 from .graphs import GraphedStep, reset_caches
 from .language_model import QuestionEmbedding
+from .loss_function import Distillation_Loss
 from .optim import FusedClipAdamax
 from .prepack import prepack
 from .tc import TCNet
 
-__all__ = ["FCNet", "WNLinear", "TCNet", "TriAttention", "BCNet", "BiAttention", "SimpleClassifier", "QuestionEmbedding", "FusedClipAdamax", "prepack", "install", "uninstall", "GraphedStep", "reset_caches",
+__all__ = ["FCNet", "WNLinear", "TCNet", "TriAttention", "BCNet", "BiAttention", "SimpleClassifier", "QuestionEmbedding", "Distillation_Loss", "FusedClipAdamax", "prepack", "install", "uninstall", "GraphedStep", "reset_caches",
            "library_path", "version"]
 
 

@@ -37,6 +37,7 @@ SIGNATURES = {
     "cti_gemm_bf16": (c_int, [_P, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_float, _P, c_int, _P, c_int,
                               _P, _P, c_int, c_int, c_int, c_int, _P]),
     "cti_act_bwd_bias": (c_int, [_P, c_int, _P, _P, _P, c_int64, c_int, _P]),
+    "cti_kd_loss": (c_int, [_P, _P, c_int, _P, _P, _P, _P, c_int, c_int, c_float, c_float, _P]),
     "cti_masked_softmax_fwd": (c_int, [_P, _P, c_int64, c_int, _P]),
     "cti_masked_softmax_bwd": (c_int, [_P, _P, c_int64, c_int64, c_int64, _P, c_int64, c_int, c_int, _P]),
     "cti_trilinear_logits_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),

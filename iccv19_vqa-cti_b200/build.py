@@ -17,10 +17,12 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcti_sm100.so")
-SOURCES = ["cti_capi.cu", "gemm_tcgen05.cu", "elementwise.cu", "softmax.cu", "trilinear.cu", "trilinear_tc.cu", "trilinear_bwd_tc.cu", "pool.cu", "bilinear.cu", "bilinear_tc.cu", "optim.cu", "gru.cu"]
+SOURCES = ["cti_capi.cu", "gemm_tcgen05.cu", "elementwise.cu", "softmax.cu", "trilinear.cu", "trilinear_tc.cu", "trilinear_bwd_tc.cu", "pool.cu", "bilinear.cu", "bilinear_tc.cu", "optim.cu", "gru.cu", "loss.cu"]
 HEADERS = ["cti_common.cuh", "cti_kernels.h", "wmma_tiles.cuh", "tc_tiles.cuh", os.path.join("..", "..", "include", "cti_sm100.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+if os.environ.get("CTI_PROF"):                     # debug: per-role cycle counters in the contraction kernel
+    NVCC_FLAGS.append("-DCTI_PROF=1")
 if os.environ.get("CTI_WATCHDOG"):                 # debug: mbarrier watchdog (see csrc/cti_common.cuh)
     NVCC_FLAGS.append("-DCTI_WATCHDOG=" + os.environ["CTI_WATCHDOG"])
 
@@ -44,6 +46,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     hdrs = [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]
+    stamp = os.path.join(objdir, "flags.txt")            # a change of flags (debug builds) rebuilds everything
+    flags = " ".join(NVCC_FLAGS)
+    if not os.path.exists(stamp) or open(stamp).read() != flags:
+        force = True
     jobs = []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
@@ -62,6 +68,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         for s, log in ex.map(compile_one, jobs):
             if verbose:
                 print(f"== {os.path.basename(s)}\n{log}")
+    with open(stamp, "w") as f:
+        f.write(flags)
     objs = [os.path.join(objdir, src.replace(".cu", ".o")) for src in SOURCES]
     if force or jobs or _stale(LIB, objs):
         r = subprocess.run([nvcc, "-shared", "-o", LIB, *objs, "-cudart", "static"], capture_output=True, text=True)

@@ -171,6 +171,12 @@ int cti_gru_gate_bwd(float* dh, const float* dout, int64_t do_row_stride, const 
                            static_cast<b16*>(dgh_bf16), rows, H, static_cast<cudaStream_t>(stream));
 }
 
+int cti_kd_loss(const float* x, const void* teacher, int teacher_is_fp16, const float* target, float* dx, float* row_loss,
+                float* loss, int B, int N, float T, float alpha, void* stream) {
+  return cti::kd_loss(x, teacher, teacher_is_fp16, target, dx, row_loss, loss, B, N, T, alpha,
+                      static_cast<cudaStream_t>(stream));
+}
+
 int cti_masked_softmax_fwd(const float* logits, float* p, int64_t rows, int len, void* stream) {
   return cti::masked_softmax_fwd(logits, p, rows, len, static_cast<cudaStream_t>(stream));
 }
@@ -188,6 +194,8 @@ int cti_trilinear_logits_fwd(const void* vc, const void* qc, const void* ac, con
                             static_cast<const __nv_bfloat16*>(ac), static_cast<const __nv_bfloat16*>(tpack), rowmask,
                             logits, d, static_cast<cudaStream_t>(stream));
 }
+
+int cti_debug_prof_read(unsigned long long* host_dst, int n) { return cti::debug_prof_read(host_dst, n); }
 
 size_t cti_trilinear_logits_bwd_workspace(int B, int K, int Q, int A, int G, int R) {
   cti::TriDims d{B, K, Q, A, G, R};

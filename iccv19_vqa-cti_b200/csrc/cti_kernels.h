@@ -68,6 +68,10 @@ int gru_gate_bwd(float* dh, const float* dout, long do_row_stride, const float* 
                  const __nv_bfloat16* r_s, const __nv_bfloat16* z_s, const __nv_bfloat16* n_s, const __nv_bfloat16* ghn_s,
                  __nv_bfloat16* dgx, long dgx_row_stride, __nv_bfloat16* dgh, long rows, int H, cudaStream_t s);
 
+// loss.cu
+int kd_loss(const float* x, const void* teacher, int teacher_is_fp16, const float* target, float* dx, float* row_loss,
+            float* loss, int B, int N, float T, float alpha, cudaStream_t s);
+
 // softmax.cu
 int masked_softmax_fwd(const float* logits, float* p, long rows, int len, cudaStream_t s);
 int masked_softmax_bwd(const float* p, const float* dp, long dp_row_stride_b, long dp_row_stride_g, long dp_elem_stride,
@@ -81,6 +85,7 @@ struct TriDims {
 int trilinear_fwd(const __nv_bfloat16* vc, const __nv_bfloat16* qc, const __nv_bfloat16* ac, const __nv_bfloat16* tpack,
                   const uint8_t* rowmask, float* logits, TriDims d, cudaStream_t s);
 size_t trilinear_bwd_workspace(TriDims d);
+int debug_prof_read(unsigned long long* host_dst, int n);   // CTI_PROF builds only (returns -1 otherwise)
 int trilinear_bwd(const __nv_bfloat16* vc, const __nv_bfloat16* qc, const __nv_bfloat16* ac, const __nv_bfloat16* tpack,
                   const float* dlogits, __nv_bfloat16* dzv, __nv_bfloat16* dzq, __nv_bfloat16* dza, float* dbv,
                   float* dbq, float* dba, float* dtpack, void* workspace, size_t workspace_bytes, TriDims d,

@@ -28,6 +28,25 @@ namespace {
 
 using bf16 = __nv_bfloat16;
 
+// Debug build (CTI_PROF=1 python build.py --force): per-role cycle accounting of the forward kernel, read back with
+// cti_debug_prof_read().  Slot layout: [block][role 0..7][counter 0..7].
+#ifdef CTI_PROF
+__device__ unsigned long long g_prof[148 * 64];
+#define PROF_DECL unsigned long long prof_t0 = 0, prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; (void)prof_t0;
+#define PROF_T0() (prof_t0 = clock64())
+#define PROF_ADD(i) (prof_acc[i] += clock64() - prof_t0)
+#define PROF_FLUSH(role)                                                                         \
+  do {                                                                                           \
+    if ((threadIdx.x & 31) == 0)                                                                 \
+      for (int i_ = 0; i_ < 8; ++i_) g_prof[(blockIdx.x * 8 + (role)) * 8 + i_] = prof_acc[i_]; \
+  } while (0)
+#else
+#define PROF_DECL
+#define PROF_T0()
+#define PROF_ADD(i)
+#define PROF_FLUSH(role)
+#endif
+
 constexpr int kThreads = 384;
 constexpr int T_BYTES = 16 * 1024;            // T_r: [16 l][512 (i,g,j)] bf16 = 8 chunks x [16 rows][128 B]
 constexpr int T_RING = 3;
@@ -134,11 +153,14 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
+      PROF_DECL
       uint32_t tslot = 0, tph = 0, oslot = 0, oph = 0;
       int r = 0, b = blockIdx.x;
       for (int u = 0; u < U; ++u) {
         if ((r & 3) == 0) {
+          PROF_T0();
           mbar_wait(bar(B_OPEMPTY + oslot), oph ^ 1u);
+          PROF_ADD(0);
           mbar_arrive_expect_tx(bar(B_OPFULL + oslot), OP_BYTES);
           const uint32_t dst = sOp + oslot * OP_BYTES;
           tma_load_3d(&tmap_v, bar(B_OPFULL + oslot), dst + OP_V, r * 16, 0, b / p.VR);
@@ -146,7 +168,9 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
           tma_load_3d(&tmap_a, bar(B_OPFULL + oslot), dst + OP_A, r * 16, 0, b);
           if (++oslot == OP_RING) { oslot = 0; oph ^= 1u; }
         }
+        PROF_T0();
         mbar_wait(bar(B_TEMPTY + tslot), tph ^ 1u);
+        PROF_ADD(1);
         mbar_arrive_expect_tx(bar(B_TFULL + tslot), T_BYTES);
 #pragma unroll
         for (int c = 0; c < 8; ++c)
@@ -154,6 +178,7 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
         if (++tslot == T_RING) { tslot = 0; tph ^= 1u; }
         if (++r == p.R) { r = 0; b += gridDim.x; }
       }
+      PROF_FLUSH(0);
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer 1: F1(u)  N1^T = T_r^T . Ac_r^T ------------------------
@@ -162,13 +187,21 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
     if (lane == 0) {
       const uint32_t id_f1 = make_idesc_rt(128, 16, 1, 0);
       RingPos f1;
+      PROF_DECL
       uint32_t tslot = 0, tph = 0, oslot = 0, oph = 0;
       int r = 0;
       for (int u = 0; u < U; ++u) {
         const uint32_t tt = sT + tslot * T_BYTES;
+        PROF_T0();
         mbar_wait(bar(B_TFULL + tslot), tph);
+        PROF_ADD(0);
+        PROF_T0();
         if ((r & 3) == 0) mbar_wait(bar(B_OPFULL + oslot), oph);
+        PROF_ADD(1);
+        PROF_T0();
         mbar_wait(bar(B_F1EMPTY + f1.slot), f1.ph ^ 1u);
+        PROF_ADD(2);
+        PROF_T0();
         tcgen05_fence_after();
         const uint64_t db = desc_kmajor(sOp + oslot * OP_BYTES + OP_A, r & 3);
         const uint64_t da = desc_mnmajor(tt, 0, 2048);
@@ -181,19 +214,29 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
         if (++tslot == T_RING) { tslot = 0; tph ^= 1u; }
         if (++r == p.R) r = 0;
         if ((r & 3) == 0 && ++oslot == OP_RING) { oslot = 0; oph ^= 1u; }
+        PROF_ADD(3);
       }
+      PROF_FLUSH(1);
     }
   } else if (warp == 3) {
     // ------------------------------ MMA issuer 2: F2(u)  M = N1 . Qc_r^T ---------------------------------
     if (lane == 0) {
       const uint32_t id_f2 = make_idesc_rt(128, 16, 0, 0);
       RingPos n1, f2;
+      PROF_DECL
       uint32_t oslot = 0, oph = 0;
       int r = 0;
       for (int u = 0; u < U; ++u) {
+        PROF_T0();
         if ((r & 3) == 0) mbar_wait(bar(B_OPFULL + oslot), oph);
+        PROF_ADD(0);
+        PROF_T0();
         mbar_wait(bar(B_N1FULL + n1.slot), n1.ph);
+        PROF_ADD(1);
+        PROF_T0();
         mbar_wait(bar(B_F2EMPTY + f2.slot), f2.ph ^ 1u);
+        PROF_ADD(2);
+        PROF_T0();
         tcgen05_fence_after();
         const uint64_t db = desc_kmajor(sOp + oslot * OP_BYTES + OP_Q, r & 3);
         const uint64_t da = desc_kmajor(sN1 + (n1.slot >> 2) * N1_BYTES, n1.slot & 3);     // K step = rank within the quad tile
@@ -205,19 +248,29 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
         f2.next(F2_RING);
         if (++r == p.R) r = 0;
         if ((r & 3) == 0 && ++oslot == OP_RING) { oslot = 0; oph ^= 1u; }
+        PROF_ADD(3);
       }
+      PROF_FLUSH(2);
     }
   } else if (warp == 2) {
     // ------------------------------ MMA issuer 3: III(u)  L += Vc_r . M  (this warp also owns TMEM) --------
     if (lane == 0) {
       const uint32_t id_3 = make_idesc_rt(128, p.N, 0, 1);
       RingPos mr;
+      PROF_DECL
       uint32_t oslot = 0, oph = 0;
       int r = 0, sl = 0;
       for (int u = 0; u < U; ++u) {
+        PROF_T0();
         if ((r & 3) == 0) mbar_wait(bar(B_OPFULL + oslot), oph);
+        PROF_ADD(0);
+        PROF_T0();
         mbar_wait(bar(B_MFULL + mr.slot), mr.ph);
+        PROF_ADD(1);
+        PROF_T0();
         if (r == 0) mbar_wait(bar(B_ACCEMPTY), (sl & 1) ^ 1);
+        PROF_ADD(2);
+        PROF_T0();
         tcgen05_fence_after();
         umma_bf16_ss(tmem_base + TM_ACC, desc_kmajor(sOp + oslot * OP_BYTES + OP_V, r & 3),
                      desc_mnmajor(sM + mr.slot * M_BYTES, 0, 2048), id_3, r > 0 ? 1u : 0u);
@@ -227,7 +280,9 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
         if (r == p.R - 1) umma_commit(bar(B_ACCFULL));
         if (++r == p.R) { r = 0; ++sl; }
         if ((r & 3) == 0 && ++oslot == OP_RING) { oslot = 0; oph ^= 1u; }
+        PROF_ADD(3);
       }
+      PROF_FLUSH(3);
     }
   } else if (warp >= 4 && warp < 8) {
     // ------------------------------ C1: N1^T (TMEM) -> N1 tile rows (a,g,i), columns j --------------
@@ -235,10 +290,16 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
     const int j = L & 15, g = (L >> 4) & 1;
     RingPos f1, n1r;
+    PROF_DECL
     for (int u = 0; u < U; ++u) {
+      PROF_T0();
       mbar_wait(bar(B_F1FULL + f1.slot), f1.ph);
+      PROF_ADD(0);
       tcgen05_fence_after();
+      PROF_T0();
       mbar_wait(bar(B_N1EMPTY + n1r.slot), n1r.ph ^ 1u);
+      PROF_ADD(1);
+      PROF_T0();
       const uint32_t n1 = sN1 + (n1r.slot >> 2) * N1_BYTES;
       const uint32_t sub = n1r.slot & 3;                       // rank within the quad tile: columns sub * 16 + j
       uint32_t v[4][8];
@@ -267,7 +328,9 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
       }
       f1.next(F1_RING);
       n1r.next(N1_RING);
+      PROF_ADD(2);
     }
+    if (warp == 4) PROF_FLUSH(4);
   } else if (warp >= 8) {
     // ------------------------------ C2: M (TMEM) -> M tile [i][(a,g,q16)];  per-sample epilogue ------
     const int qd = warp & 3, L = qd * 32 + lane;
@@ -276,11 +339,17 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
     const int per_g = p.K * p.Q * p.A;
     int r = -1, sl = 0;
     RingPos f2, mr;
+    PROF_DECL
     for (int u = 0; u < U; ++u) {
       if (++r == p.R) { r = 0; ++sl; }
+      PROF_T0();
       mbar_wait(bar(B_F2FULL + f2.slot), f2.ph);
+      PROF_ADD(0);
       tcgen05_fence_after();
+      PROF_T0();
       mbar_wait(bar(B_MEMPTY + mr.slot), mr.ph ^ 1u);
+      PROF_ADD(1);
+      PROF_T0();
       const uint32_t mt = sM + mr.slot * M_BYTES;
       for (int t2 = 0; t2 < nt2; ++t2) {
         uint32_t v[16];
@@ -308,10 +377,14 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
       }
       f2.next(F2_RING);
       mr.next(M_RING);
+      PROF_ADD(2);
       if (r == p.R - 1) {
         // ---- sample epilogue: TMEM lane = region k, column (a,g,q16) -> (G,K,Q,A) order, mask, coalesced store
         const int b = blockIdx.x + sl * gridDim.x;
+        PROF_T0();
         mbar_wait(bar(B_ACCFULL), sl & 1);
+        PROF_ADD(3);
+        PROF_T0();
         tcgen05_fence_after();
         const int k = L;
         const bool masked = (k < p.K) && p.rowmask != nullptr && p.rowmask[(size_t)(b / p.VR) * p.K + k] != 0;
@@ -334,8 +407,10 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
         float* gdst = p.logits + (size_t)b * 2 * per_g;
         for (int e = et; e < 2 * per_g; e += 128) gdst[e] = out_stage[e];
         named_bar_sync(1, 128);
+        PROF_ADD(4);
       }
     }
+    if (warp == 8) PROF_FLUSH(5);
   }
 
   tcgen05_fence_before();
@@ -347,6 +422,15 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
 }
 
 }  // namespace
+
+int debug_prof_read(unsigned long long* host_dst, int n) {
+#ifdef CTI_PROF
+  return (int)cudaMemcpyFromSymbol(host_dst, g_prof, sizeof(unsigned long long) * (n < 148 * 64 ? n : 148 * 64));
+#else
+  (void)host_dst; (void)n;
+  return -1;
+#endif
+}
 
 // Returns -100 when the shape is outside the fast path (caller falls back to the generic kernel).
 int trilinear_fwd_tc(const bf16* vc, const bf16* qc, const bf16* ac, const bf16* tpack, const uint8_t* rowmask,

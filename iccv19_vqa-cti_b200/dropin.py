@@ -16,9 +16,11 @@ _TARGETS = {
     "src.attention": ("BiAttention", "TriAttention"),
     "src.classifier": ("SimpleClassifier",),
     "src.language_model": ("QuestionEmbedding",),
+    "src.loss_function": ("Distillation_Loss",),
 }
 # modules that did ``from src.x import Name`` and hold their own binding
-_IMPORTERS = ("src.MC.base_model", "src.FFOE.base_model", "src.attention", "src.tc", "src.bc")
+_IMPORTERS = ("src.MC.base_model", "src.FFOE.base_model", "src.attention", "src.tc", "src.bc", "src.FFOE.train",
+              "src.FFOE.main")
 
 
 def install(hot_path_only: bool = False) -> None:
@@ -26,11 +28,12 @@ def install(hot_path_only: bool = False) -> None:
     hot_path_only: substitute only the classes the north_star names (FCNet, TCNet, TriAttention, BCNet, BiAttention) and
     leave the rows next to the path -- the GRU ``QuestionEmbedding`` and ``SimpleClassifier`` -- on the reference's own
     fp32 implementations."""
-    from . import attention, bc, classifier, fc, language_model, tc
+    from . import attention, bc, classifier, fc, language_model, loss_function, tc
     ours = {"FCNet": fc.FCNet, "TCNet": tc.TCNet, "BCNet": bc.BCNet, "BiAttention": attention.BiAttention,
             "TriAttention": attention.TriAttention}
     if not hot_path_only:
-        ours.update({"SimpleClassifier": classifier.SimpleClassifier, "QuestionEmbedding": language_model.QuestionEmbedding})
+        ours.update({"SimpleClassifier": classifier.SimpleClassifier, "QuestionEmbedding": language_model.QuestionEmbedding,
+                     "Distillation_Loss": loss_function.Distillation_Loss})
     for modname, names in _TARGETS.items():
         mod = importlib.import_module(modname)
         for n in names:

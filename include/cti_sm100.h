@@ -104,6 +104,15 @@ int cti_gemm_bf16(const void* a, int lda, int a_mn_major, const void* b, int ldb
 int cti_act_bwd_bias(const void* dy, int dy_is_bf16, const void* y_bf16, void* dz_bf16, float* dbias_accum,
                      int64_t rows, int cols, void* stream);
 
+/* ---- distillation loss, forward + gradient in one pass -----------------------------------------
+ * loss = mean_b KL(softmax(teacher/T) || softmax(x/T)) * alpha T^2 + sum BCEWithLogits(x, target) / B * (1 - alpha);
+ * dx = d loss / d x.  x, target, dx: (B, N) fp32; teacher: (B, N) fp16 (teacher_is_fp16 != 0) or fp32; row_loss: B floats
+ * of scratch; loss: one float.  2 launches.
+ * replaces: Distillation_Loss.forward, src/loss_function.py:20-25 (nn.KLDivLoss + log_softmax + softmax +
+ * nn.BCEWithLogitsLoss and their autograd). */
+int cti_kd_loss(const float* x, const void* teacher, int teacher_is_fp16, const float* target, float* dx,
+                float* row_loss, float* loss, int B, int N, float T, float alpha, void* stream);
+
 /* ---- masked softmax over the flattened attention domain ---------------------------------------
  * rows of `len` contiguous floats; masked positions already hold -inf.
  * replaces: torch.softmax in src/attention.py:58 (TriAttention) and :39 (BiAttention). */

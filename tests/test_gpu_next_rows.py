@@ -366,3 +366,28 @@ def test_graphed_step_refuses_to_freeze_dropout_masks():
     m.eval()
     g = cti_b200.GraphedStep(lambda: m(x), [m], [x])
     assert torch.equal(g.replay(), m(x))
+
+
+@pytest.mark.parametrize("n_ans,half_teacher", [(3129, True), (1484, False), (37, True)])
+def test_distillation_loss_dropin_against_reference_formula(n_ans, half_teacher):
+    """Row 8a-11: ``Distillation_Loss(T=5, alpha=0.005)`` (reference src/loss_function.py:12-25; README.md:49) as one
+    fused forward + gradient kernel, against the oracle's restatement (itself pinned to the reference-made golden loss
+    in test_whole_ban_student_with_distillation_loss_against_reference_golden) and torch autograd."""
+    B = 256
+    gen = torch.Generator().manual_seed(n_ans)
+    x = torch.randn(B, n_ans, generator=gen) * 2
+    teacher = torch.randn(B, n_ans, generator=gen).half() if half_teacher else torch.randn(B, n_ans, generator=gen)
+    target = torch.zeros(B, n_ans)
+    target[torch.arange(B), torch.randint(0, n_ans, (B,), generator=gen)] = 1.0
+    target[torch.arange(B), torch.randint(0, n_ans, (B,), generator=gen)] = 0.6       # soft scores (compute_softscore.py)
+    xl = x.clone().requires_grad_(True)
+    ref = O.distillation_loss(xl, teacher.float(), target, 5.0, 0.005)
+    (ref * 3.0).backward()
+    crit = cti_b200.Distillation_Loss(5, 0.005)
+    xd = x.to(DEV).requires_grad_(True)
+    loss = crit(xd, teacher.to(DEV), target.to(DEV))
+    (loss * 3.0).backward()
+    assert loss.dim() == 0 and abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    assert (xd.grad.cpu() - xl.grad).abs().max().item() <= 1e-5 * xl.grad.abs().max().item() + 1e-9
+    loss2 = crit(xd, teacher.to(DEV), target.to(DEV))
+    assert loss2.item() == loss.item()                                                  # fixed summation order
