@@ -41,7 +41,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--rows", type=int, default=1024, help="module rows per GPU per step (weak scaling)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-rows", type=int, default=128, help="rows per step of the bounded CPU sample")
+    ap.add_argument("--cpu-rows", type=int, default=0, help="rows per step of the CPU arms (0: --impl reference steps the "
+                    "same --rows as the GPU arm, the in-line cpu_baseline of the GPU arm a bounded 128-row sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--resident-only", action="store_true", help="skip the e2e / forward-only arms (for ncu runs)")
@@ -60,45 +61,92 @@ def workload_config(rows, n):
 
 
 # --------------------------------------------------------------------------- #
-# CPU arm: the oracle (port of the reference's op order) on the host cores
+# CPU arm: the reference's own modules (baseline/_ref, unmodified) on the host cores; the oracle port when the
+# reference is not installed on this box
 # --------------------------------------------------------------------------- #
+def _reference_hot_path_modules(device="cpu"):
+    """The hot path built from the REFERENCE's classes (src.attention.TriAttention, src.tc.TCNet, src.fc.FCNet), or None."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import ref_env
+    if ref_env.import_reference() is None:
+        return None
+    import torch
+    from src.attention import TriAttention
+    from src.fc import FCNet
+    from src.tc import TCNet
+    torch.manual_seed(1204)
+    att = TriAttention(V_DIM, HID, HID, H_MM, 1, RANK, GLIMPSE, 1)
+    pools = [TCNet(V_DIM, HID, HID, H_MM, 1, RANK, 1, k=2) for _ in range(GLIMPSE)]
+    q_prj = [FCNet([HID, HID], '', .2) for _ in range(GLIMPSE)]
+    a_prj = [FCNet([HID, HID], '', .2) for _ in range(GLIMPSE)]
+    mods = torch.nn.ModuleList([att, *pools, *q_prj, *a_prj]).to(device).eval()
+    return mods, att, pools, q_prj, a_prj
+
+
+def _hot_path(att, pools, q_prj, a_prj, v, q, a):
+    """The hot-path slice of TanModel.forward (reference src/MC/base_model.py:143-150)."""
+    p_att, _ = att(v, q, a)
+    qe, ae = q, a
+    for gi in range(GLIMPSE):
+        b_emb = pools[gi].forward_with_weights(v, qe, ae, p_att[:, :, :, :, gi])
+        qe = q_prj[gi](b_emb.unsqueeze(1)) + qe
+        ae = a_prj[gi](b_emb.unsqueeze(1)) + ae
+    return qe.sum(1) + ae.sum(1)
+
+
 def cpu_rows_per_s(rows, steps, warmup):
+    """-> (rows/s, cores, s/step, kind): fwd+bwd of the hot path on all host cores, eval mode (dropout off)."""
     import torch
     from oracle import cti_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    params = {k: t.requires_grad_(True) for k, t in O.random_cti_params(glimpse=GLIMPSE, seed=1204).items()}
     v, q, a = O.synthetic_inputs(rows, K_REGIONS, Q_TOK, A_TOK, seed=1204)
     q.requires_grad_(True)
     a.requires_grad_(True)
     cot = torch.randn(rows, HID)
+    ref = _reference_hot_path_modules()
+    if ref is not None:
+        mods, att, pools, q_prj, a_prj = ref
+        leaves = list(mods.parameters()) + [q, a]
+        run = lambda: _hot_path(att, pools, q_prj, a_prj, v, q, a)
+        kind = "reference"
+    else:
+        params = {k: t.requires_grad_(True) for k, t in O.random_cti_params(glimpse=GLIMPSE, seed=1204).items()}
+        leaves = list(params.values()) + [q, a]
+        run = lambda: O.cti_hot_path(v, q, a, params, GLIMPSE)[0]
+        kind = "port"
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        for t in list(params.values()) + [q, a]:
+        for t in leaves:
             t.grad = None
-        joint, _, _ = O.cti_hot_path(v, q, a, params, GLIMPSE)
-        (joint * cot).sum().backward()
+        (run() * cot).sum().backward()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     dt = sum(times) / len(times)
-    return rows / dt, cores, dt
+    return rows / dt, cores, dt, kind
 
 
 def run_reference(args):
+    """The reference arm: the reference's own CPU implementation of the path (unmodified modules from baseline/_ref when
+    present, else the oracle port), all host threads, a bounded sample of the same workload.  Under torchrun only rank 0
+    works; the line describes ONE host process whatever --gpus says."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
-    val, cores, dt = cpu_rows_per_s(args.cpu_rows, steps, warmup)
-    sample = f"{steps} timed steps of {args.cpu_rows} rows after {warmup} warm-up (same model and shapes)"
+    args.cpu_rows = args.cpu_rows or args.rows
+    val, cores, dt, kind = cpu_rows_per_s(args.cpu_rows, steps, warmup)
+    sample = (f"{steps} timed fwd+bwd steps of {args.cpu_rows} rows after {warmup} warm-up: the GPU arm's own workload "
+              f"(same modules, shapes and rows per step), bounded in the number of steps")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.cpu_rows, 1),
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0,
+            "note": "one host process on rank 0; the other ranks of a torchrun launch exit without work"}
     print(json.dumps(line), flush=True)
 
 
@@ -245,6 +293,7 @@ def run_b200(args):
     def shared_step():                           # extension: the un-cloned features go straight in
         step(vq_d, q_d.detach(), a_d.detach())
 
+    sampler = ClockSampler(local) if rank == 0 else None      # nvidia-smi needs ~1 s to start: begin before the warm-up
     for _ in range(max(args.warmup, 3)):
         resident_step()
     # launches of one step (counted on an eager step: a graph replay issues the same kernels without Python)
@@ -278,7 +327,6 @@ def run_b200(args):
             if reducer is not None:
                 reducer.set_hooks_enabled(True)
             eager_ms["graph_capture_failed"] = repr(exc)[:200]
-    sampler = ClockSampler(local) if rank == 0 else None
     ms, w0, w1 = timed(run_resident, args.steps)
     host_ms = timed.host_ms
     launches = launches_per_step * args.steps
@@ -555,6 +603,153 @@ def run_b200(args):
         except Exception as exc:
             full = {"failed": repr(exc)[:300]}
 
+    # ---- legs for the other BASELINE configs and modes (rank 0 at N = 1; none is part of `value`) -------------------
+    def synth(rows, seed):
+        gg = torch.Generator().manual_seed(seed)
+        nq = rows // CLONE
+        vq = torch.relu(torch.randn(nq, K_REGIONS, V_DIM, generator=gg))
+        nb_ = torch.randint(10, K_REGIONS + 1, (nq,), generator=gg)
+        vq = (vq * (torch.arange(K_REGIONS)[None, :] < nb_[:, None]).float()[:, :, None]).to(dev)
+        vv = vq.unsqueeze(1).expand(nq, CLONE, K_REGIONS, V_DIM).contiguous().view(rows, K_REGIONS, V_DIM)
+        return (vv, torch.tanh(torch.randn(rows, Q_TOK, HID, generator=gg)).to(dev),
+                torch.tanh(torch.randn(rows, A_TOK, HID, generator=gg)).to(dev), torch.randn(rows, HID, generator=gg).to(dev))
+
+    def time_hot_path(vv, qq, aa, cc, label, fixed_dropout=False, with_reducer=False):
+        def fb():
+            cti_b200.prepack(mods)
+            for p in params:
+                p.grad = None
+            joint = _hot_path(att, pools, q_prj, a_prj, vv, qq.detach().requires_grad_(True), aa.detach().requires_grad_(True))
+            (joint * cc).sum().backward()
+        for _ in range(3):
+            fb()
+        run = fb
+        if use_graph:
+            gph = cti_b200.GraphedStep(fb, [mods], [vv], allow_fixed_dropout=fixed_dropout).replay
+            if with_reducer and reducer is not None:
+                reducer.forget_sources()
+
+                def run():
+                    gph()
+                    reducer.reduce_now()
+            else:
+                run = gph
+        for _ in range(3):
+            run()
+        ms_, _, _ = timed(run, args.steps, all_ranks=with_reducer)
+        rows_ = vv.shape[0]
+        return {"rows_per_gpu": rows_, "ms_per_step": ms_ / args.steps,
+                "value": (world if with_reducer else 1) * rows_ * args.steps / (ms_ / 1e3), "unit": UNIT, "note": label}
+
+    extra = {}
+    if not args.resident_only and not args.hot_only:
+        # BASELINE config 5 also asks for scaling at EQUAL GLOBAL batch: 4096 rows split over the N ranks
+        try:
+            g_rows = 4096
+            if g_rows % (world * 4) == 0:
+                vv, qq, aa, cc = synth(g_rows // world, 77 + rank)
+                extra["strong_scaling_4096"] = dict(time_hot_path(
+                    vv, qq, aa, cc, "global 4096 rows split evenly over the ranks, fwd+bwd + gradient all-reduce; "
+                    "at N = 1 this is the top of BASELINE config 2's 64-4096 row sweep", with_reducer=world > 1),
+                    global_rows=g_rows, scaling="strong")
+                del vv, qq, aa, cc
+        except Exception as exc:
+            extra["strong_scaling_4096"] = {"failed": repr(exc)[:300]}
+    if world == 1 and not args.resident_only and not args.hot_only:
+        # training mode: every dropout of the reference active, the R per-rank nets with independent masks
+        # (reference src/tc.py:29-31); timed by replaying one captured step (fixed masks: timing only)
+        try:
+            mods.train()
+            extra["train_dropout"] = time_hot_path(v_d, q_d, a_d, cot, "modules in train(): input dropout of every FCNet, "
+                                                   "independent masks per rank net (reference semantics)", fixed_dropout=True)
+        except Exception as exc:
+            extra["train_dropout"] = {"failed": repr(exc)[:300]}
+        finally:
+            mods.eval()
+
+        # the reference's own modules, eager fp32, on this GPU ("the stronger comparator")
+        try:
+            ref = _reference_hot_path_modules(dev)
+            if ref is None:
+                extra["reference_gpu_fp32"] = {"unavailable": "baseline/_ref not installed"}
+            else:
+                r_mods, r_att, r_pools, r_qp, r_ap = ref
+                r_params = list(r_mods.parameters())
+
+                def ref_step():
+                    for p in r_params:
+                        p.grad = None
+                    joint = _hot_path(r_att, r_pools, r_qp, r_ap, v_d, q_d.detach().requires_grad_(True),
+                                      a_d.detach().requires_grad_(True))
+                    (joint * cot).sum().backward()
+                for _ in range(2):
+                    ref_step()
+                n_ref = max(3, args.steps // 4)
+                ms_r, _, _ = timed(ref_step, n_ref, all_ranks=False)
+                extra["reference_gpu_fp32"] = {"rows_per_gpu": B, "ms_per_step": ms_r / n_ref, "value": B * n_ref / (ms_r / 1e3),
+                                               "unit": UNIT, "note": "unmodified reference modules (baseline/_ref), eager "
+                                               "PyTorch fp32 on the same B200, same rows / shapes, fwd+bwd, eval mode"}
+                del r_mods, r_params, ref
+        except Exception as exc:
+            extra["reference_gpu_fp32"] = {"failed": repr(exc)[:300]}
+
+        # BASELINE configs 3 and 4: whole free-form models, 256 rows, Distillation_Loss(T=5, alpha=0.005), fwd+bwd
+        def ffoe_leg(kind):
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import ref_env
+            n_ans, A_ = (3129, 0) if kind == "ban" else (1484, 3)
+            rows_ = 256
+            torch.manual_seed(1204)
+            how = "reference builder (baseline/_ref, unmodified) on the substituted modules"
+            if ref_env.import_reference() is not None:
+                import src.FFOE.base_model as ff
+                a_, ds_ = ref_env.fake_args_dataset(n_ans)
+                cti_b200.install()
+                try:
+                    model = (ff.build_ban if kind == "ban" else ff.build_cti)(a_, ds_)
+                finally:
+                    cti_b200.uninstall()
+            else:
+                from mc_model import BanStudent, CTIFreeForm
+                how = "mirror of the reference model (tools/mc_model.py)"
+                model = (BanStudent(3000, V_DIM, HID, GLIMPSE, n_ans) if kind == "ban"
+                         else CTIFreeForm(3000, V_DIM, HID, H_MM, RANK, GLIMPSE, n_ans))
+            model = model.to(dev).eval()
+            tp = [p for p in model.parameters() if p.requires_grad]
+            gg = torch.Generator().manual_seed(9)
+            vv = torch.relu(torch.randn(rows_, K_REGIONS, V_DIM, generator=gg))
+            nb_ = torch.randint(10, K_REGIONS + 1, (rows_,), generator=gg)
+            vv = (vv * (torch.arange(K_REGIONS)[None, :] < nb_[:, None]).float()[:, :, None]).to(dev)
+            bb = torch.rand(rows_, K_REGIONS, 6, generator=gg).to(dev)
+            qt = torch.randint(0, 3000, (rows_, Q_TOK), generator=gg).to(dev)
+            at = torch.randint(0, 3001, (rows_, 3), generator=gg).to(dev)
+            teacher = torch.randn(rows_, n_ans, generator=gg).half().to(dev)          # fp16, as the reference stores them
+            target = torch.zeros(rows_, n_ans)
+            target[torch.arange(rows_), torch.randint(0, n_ans, (rows_,), generator=gg)] = 1.0
+            target = target.to(dev)
+            crit = cti_b200.Distillation_Loss(5, 0.005)
+
+            def fb():
+                cti_b200.prepack(model)
+                for p in tp:
+                    p.grad = None
+                out = model(vv, bb, qt, None)[0] if kind == "ban" else model(vv, qt, at)
+                crit(out, teacher, target).backward()
+            for _ in range(3):
+                fb()
+            run = cti_b200.GraphedStep(fb, [model], [vv]).replay if use_graph else fb
+            for _ in range(3):
+                run()
+            ms_, _, _ = timed(run, args.steps, all_ranks=False)
+            return {"rows_per_gpu": rows_, "ms_per_step": ms_ / args.steps, "value": rows_ * args.steps / (ms_ / 1e3),
+                    "unit": UNIT, "classes": n_ans, "params": sum(p.numel() for p in tp), "model": how,
+                    "note": "whole model fwd + Distillation_Loss(T=5, alpha=0.005, fp16 teacher logits) + bwd, eval-mode modules"}
+        for kind, key in (("ban", "ban_config3"), ("cti", "ffoe_cti_config4")):
+            try:
+                extra[key] = ffoe_leg(kind)
+            except Exception as exc:
+                extra[key] = {"failed": repr(exc)[:300]}
+
     # ---- per-kernel CUDA-event timing of the same step (rank 0) -----------------
     roofline, kernels = None, None
     if rank == 0 and not args.no_profile:
@@ -586,33 +781,79 @@ def run_b200(args):
             ent = {"kernel": name, "tag": tag, "launches_per_step": n // n_prof, "avg_ms": avg, "share": t / total}
             if flops:
                 ent["tflops"] = flops / (avg * 1e-3) / 1e12
-                ent["frac_of_bf16_peak"] = ent["tflops"] / tf_peak
+                ent["frac_of_bf16_peak"] = ent["tflops"] / tf_burst
             if nbytes:
                 ent["gbs"] = nbytes / (avg * 1e-3) / 1e9
                 ent["frac_of_hbm_peak"] = ent["gbs"] / bw_peak
             kernels.append(ent)
-        gem = [(k, d) for k, d in agg.items() if k[0] == "cti_gemm_bf16"]
-        if gem:
-            gflops = sum(d[2] * d[0] for _, d in gem)
-            gms = sum(d[1] for _, d in gem)
-            (kname, ktag), d = max(gem, key=lambda kv: kv[1][1])
-            ach = d[2] / (d[1] / d[0] * 1e-3) / 1e12
-            roofline = {"kernel": f"gemm_bf16_kernel [{ktag}]", "bound": "tensor", "achieved": ach, "peak": tf_peak,
-                        "unit": "TFLOP/s", "frac": ach / tf_peak,
-                        # dram__bytes_read.sum + dram__bytes_write.sum of this launch in the committed ncu --set full
-                        # capture (profiles/r01_ncu_gemm_dominant.md: 214.0 + 76.9 MB); algorithmic 210 + 4 + 105 MB
-                        "traffic": 290.9e6 if ktag == "fwd M=51200 N=1024 K=2048" else None,
-                        "peak_source": which + ", sustained bf16 (kernel timed inside a long step); burst %.0f" % tf_burst,
-                        "share_of_step": d[1] / total,
-                        "all_gemm_launches": {"tflops": gflops / (gms * 1e-3) / 1e12, "share_of_step": gms / total,
-                                              "frac": gflops / (gms * 1e-3) / 1e12 / tf_peak}}
+        # dominant kernel = the kernel function with the largest share of the step (all its launches together);
+        # per-launch CUDA-event timings inside a 3 ms step run at the burst clock -> burst peak
+        by_name = {}
+        for (name, tag), (n, t, flops, nbytes) in agg.items():
+            d = by_name.setdefault(name, [0, 0.0, 0.0, 0.0])
+            d[0] += n
+            d[1] += t
+            d[2] += flops * n
+            d[3] += nbytes * n
+        traffic_tab = {}
+        tr_path = os.path.join(ROOT, "profiles", "r02_traffic.json")
+        if os.path.exists(tr_path):
+            traffic_tab = json.load(open(tr_path)).get("per_launch_dram_bytes", {})
+
+        def roof_entry(name):
+            n, t, fl, nb = by_name[name]
+            ent = {"kernel": name, "launches_per_step": n // n_prof, "avg_launch_ms": t / n, "share_of_step": t / total,
+                   "traffic": traffic_tab.get(name)}
+            if fl:
+                ach = fl / (t * 1e-3) / 1e12
+                ent.update(bound="tensor", achieved=ach, peak=tf_burst, unit="TFLOP/s", frac=ach / tf_burst)
+            else:
+                ach = nb / (t * 1e-3) / 1e9
+                ent.update(bound="hbm", achieved=ach, peak=bw_peak, unit="GB/s", frac=ach / bw_peak)
+            return ent
+        dom = max(by_name, key=lambda k: by_name[k][1])
+        roofline = roof_entry(dom)
+        roofline["peak_source"] = which + (": burst bf16 figure (per-launch CUDA-event timings inside a ~3 ms step at the "
+                                           "burst clock); sustained %.0f" % tf_peak if roofline["bound"] == "tensor" else
+                                           ": copy bandwidth")
+        roofline["traffic_source"] = ("profiles/r02_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, "
+                                      "averaged over the kernel's launches of one step)" if traffic_tab else None)
+        roofline["algorithmic"] = ("2MNK summed over the launches" if dom == "cti_gemm_bf16" else
+                                   "SURVEY 8d per-row figure x rows of the launch")
+        # the step as a whole and the ops the verdict tracks
+        step_flops = 1547.8e6 * B * (A_TOK == 6)
+        tf_step = step_flops / (ms / args.steps * 1e-3) / 1e12 if step_flops else None
+        roofline["step"] = {"flops_per_row_fwd_bwd": 1547.8e6, "tflops": tf_step, "frac_of_burst": tf_step / tf_burst if tf_step else None,
+                            "frac_of_sustained": tf_step / tf_peak if tf_step else None, "ms_per_step": ms / args.steps,
+                            "tensor_bound_floor_ms": step_flops / (tf_burst * 1e12) * 1e3 if step_flops else None}
+        if "cti_gemm_bf16" in by_name:
+            roofline["gemm_all"] = roof_entry("cti_gemm_bf16")
+        tri = [k for k in ("cti_trilinear_logits_fwd", "cti_trilinear_logits_bwd") if k in by_name]
+        if tri:
+            t_tri = sum(by_name[k][1] for k in tri)
+            f_tri = sum(by_name[k][2] for k in tri)
+            roofline["contraction"] = {"kernels": tri, "us_per_step": t_tri / n_prof * 1e3,
+                                       "flops": "3 x B x T_min (SURVEY 8d: cheapest contraction order a -> q -> v)",
+                                       "tflops": f_tri / (t_tri * 1e-3) / 1e12, "frac": f_tri / (t_tri * 1e-3) / 1e12 / tf_burst,
+                                       "share_of_step": t_tri / total, "target": 0.5}
+            for k in tri:
+                roofline["contraction"][k] = roof_entry(k)
+        longest = max(agg.items(), key=lambda kv: kv[1][1] / kv[1][0])
+        (lname, ltag), (ln, lt, lfl, lnb) = longest
+        roofline["longest_launch"] = {"kernel": lname, "tag": ltag, "avg_ms": lt / ln,
+                                      "tflops": lfl / (lt / ln * 1e-3) / 1e12 if lfl else None,
+                                      "frac": lfl / (lt / ln * 1e-3) / 1e12 / tf_burst if lfl else None}
+        roofline["hbm_kernels"] = [roof_entry(k) for k in sorted(by_name, key=lambda k: -by_name[k][1])
+                                   if not by_name[k][2] and by_name[k][3]][:6]
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        val, cores, dt = cpu_rows_per_s(args.cpu_rows, 3, 1)
-        cpu_baseline = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"3 timed fwd+bwd steps of {args.cpu_rows} rows after 1 warm-up, oracle on host cores, "
-                                  f"{dt:.2f} s/step"}
+        args.cpu_rows = args.cpu_rows or 128
+        val, cores, dt, kind = cpu_rows_per_s(args.cpu_rows, 3, 1)
+        cpu_baseline = {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+                        "sample": f"3 timed fwd+bwd steps of {args.cpu_rows} rows after 1 warm-up, "
+                                  f"{'unmodified reference modules (baseline/_ref)' if kind == 'reference' else 'oracle port'} "
+                                  f"on the host cores, {dt:.2f} s/step"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -620,7 +861,8 @@ def run_b200(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": dict(workload_config(B, world), launch="cuda_graph_replay" if use_graph else "eager"),
                 "eager": eager_ms, "e2e": e2e, "gpu_launches": launches, "gpu_launches_per_step": launches_per_step, "clocks": clocks,
-                "fwd_only": fwd, "shared_v": shared, "trainer_tail": tail, "gru": gru, "full_model": full, "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels}
+                "fwd_only": fwd, "shared_v": shared, "trainer_tail": tail, "gru": gru, "full_model": full, **extra,
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -70,7 +70,10 @@ def _check_against_emulation(name, got, ref32, ref16):
     # north_star: 3e-2.  Where bf16 operand rounding alone exceeds it (BAN: a depth-3072 contraction with logits up to
     # ~18 in front of a softmax), the kernels may not add more than 10 % to the emulated error.
     assert e_k["all"] <= max(FLAT_GRAD_TOL, 1.1 * e_e["all"]), (e_k["all"], e_e["all"])
-    bad = [(c, round(e_k[c], 4), round(e_e[c], 4)) for c in den if e_k[c] > 1.5 * e_e[c] + 1e-2]
+    # classes that carry < 1e-8 of the gradient energy are the weight-norm scalars dg = <dW, V> / ||V||: a cancelling
+    # sum whose own magnitude is not a meaningful scale (tests/test_gpu_modules.py measures those against ||dV||)
+    bad = [(c, round(e_k[c], 4), round(e_e[c], 4)) for c in den
+           if den[c] > 1e-8 * total and e_k[c] > 1.5 * e_e[c] + 1e-2]
     assert not bad, bad
 
 

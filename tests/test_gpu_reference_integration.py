@@ -179,12 +179,15 @@ def test_mc_model_one_trainer_step_matches_reference():
     den = sum(b_.pow(2).sum().item() for b_ in g_ref)
     print(f"\nMC trainer step: loss {l_ref:.5f} vs {l_new:.5f}; flat-gradient L2-rel err {(num / den) ** 0.5:.4f}")
     assert (num / den) ** 0.5 <= 3e-2
-    # the update itself: Adamax's first step moves every weight by lr * sign(g) (m / u = +-1), so compare the
-    # parameter DELTA on entries whose gradient is not within rounding of zero
-    moved = wrong = 0
-    for a_, b_, p0, gr in zip(p_new, p_ref, before, g_ref):
-        big = gr.abs() > 5e-2 * gr.abs().max()
-        d_ref, d_new = (b_.detach() - p0)[big], (a_.detach() - p0)[big]
-        moved += big.sum().item()
-        wrong += ((d_ref - d_new).abs() > 0.05 * 7e-4).sum().item()
-    assert wrong / max(moved, 1) <= 1e-3, (wrong, moved)
+    # the update itself, from EQUAL gradients: rescale + clip at 0.25 + Adamax of the reference trainer
+    # (src/MC/trainer.py:208-219,252-256) against FusedClipAdamax fed the reference's raw gradients.  (From each
+    # model's OWN gradients the first Adamax step is lr * sign(g), which turns a 2.5 % gradient error on near-zero
+    # entries into full-size sign flips -- a property of Adamax, not of the kernels; the gradient itself is held to
+    # 3e-2 above.)
+    new2 = [torch.nn.Parameter(p0.clone()) for p0 in before]
+    for p, gr in zip(new2, g_ref):
+        p.grad = gr.clone()
+    cti_b200.FusedClipAdamax(new2, lr=7e-4, clip_norm=0.25).step(grad_denom=1.0)
+    worst = max((a_.detach() - b_.detach()).abs().max().item() for a_, b_ in zip(new2, p_ref))
+    print(f"parameter max-abs difference after one trainer step from equal gradients: {worst:.2e}")
+    assert worst <= 2e-6

@@ -61,6 +61,28 @@ class MCModel(nn.Module):
         return self.classifier(q_emb.sum(1) + ans_emb.sum(1)), att
 
 
+class CTIFreeForm(MCModel):
+    """reference src/FFOE/base_model.py:96-134,177-200 (``CTIModel`` + FFOE ``build_cti``): the free-form CTI teacher --
+    the MC model with ``n_ans`` classes, the attention registered as ``t_att`` and ``forward(v, q, ans)`` -> logits."""
+
+    def __init__(self, ntoken, v_dim, num_hid, h_mm, rank, gamma, n_ans, op='c', activation='relu', dropout=0.5):
+        super().__init__(ntoken, v_dim, num_hid, h_mm, rank, gamma, op, activation, dropout)
+        args = type("Args", (), {"activation": activation, "dropout": dropout})()
+        self.classifier = cti_b200.SimpleClassifier(num_hid, num_hid * 2, n_ans, args)
+        self.t_att = self.v_att
+        del self.v_att
+
+    def forward(self, v, q, ans):
+        q_emb = self.q_emb.forward_all(self.w_emb(q))
+        ans_emb = self.ans_emb.forward_all(self.wa_emb(ans))
+        att, _ = self.t_att(v, q_emb, ans_emb)
+        for g in range(self.glimpse):
+            b_emb = self.t_net[g].forward_with_weights(v, q_emb, ans_emb, att[:, :, :, :, g])
+            q_emb = self.q_prj[g](b_emb.unsqueeze(1)) + q_emb
+            ans_emb = self.a_prj[g](b_emb.unsqueeze(1)) + ans_emb
+        return self.classifier(q_emb.sum(1) + ans_emb.sum(1))
+
+
 class BanStudent(nn.Module):
     """reference src/FFOE/base_model.py:21-66 with ``use_counter=False`` (the distillation student, README.md:49)."""
 
