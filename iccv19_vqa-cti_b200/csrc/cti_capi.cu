@@ -34,7 +34,7 @@ int check_launch(const char* what) {
 
 extern "C" {
 
-int cti_version(void) { return 101; }   // 0.1.1: v_rep (rows sharing one v sample), cti_sum_row_groups
+int cti_version(void) { return 102; }   // 0.1.1: v_rep (rows sharing one v sample), cti_sum_row_groups
 
 const char* cti_last_error(void) { return cti::g_err; }
 
@@ -187,12 +187,14 @@ int cti_masked_softmax_bwd(const float* p, const float* dp, int64_t dp_stride_b,
                                  static_cast<cudaStream_t>(stream));
 }
 
-int cti_trilinear_logits_fwd(const void* vc, const void* qc, const void* ac, const void* tpack, const uint8_t* rowmask,
-                             float* logits, int B, int K, int Q, int A, int G, int R, int v_rep, void* stream) {
+int cti_trilinear_logits_fwd(const void* vc, const void* qc, const void* ac, const void* tpack, const void* tpack_perm,
+                             const uint8_t* rowmask, float* logits, int B, int K, int Q, int A, int G, int R, int v_rep,
+                             void* stream) {
   cti::TriDims d{B, K, Q, A, G, R, v_rep};
   return cti::trilinear_fwd(static_cast<const __nv_bfloat16*>(vc), static_cast<const __nv_bfloat16*>(qc),
-                            static_cast<const __nv_bfloat16*>(ac), static_cast<const __nv_bfloat16*>(tpack), rowmask,
-                            logits, d, static_cast<cudaStream_t>(stream));
+                            static_cast<const __nv_bfloat16*>(ac), static_cast<const __nv_bfloat16*>(tpack),
+                            static_cast<const __nv_bfloat16*>(tpack_perm), rowmask, logits, d,
+                            static_cast<cudaStream_t>(stream));
 }
 
 int cti_debug_prof_read(unsigned long long* host_dst, int n) { return cti::debug_prof_read(host_dst, n); }

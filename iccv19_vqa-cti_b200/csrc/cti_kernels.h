@@ -83,7 +83,7 @@ struct TriDims {
   int VR = 1;             // v_rep: rows b of q / a / logits use row b / VR of vc and rowmask (vc has B / VR samples)
 };
 int trilinear_fwd(const __nv_bfloat16* vc, const __nv_bfloat16* qc, const __nv_bfloat16* ac, const __nv_bfloat16* tpack,
-                  const uint8_t* rowmask, float* logits, TriDims d, cudaStream_t s);
+                  const __nv_bfloat16* tpack_perm, const uint8_t* rowmask, float* logits, TriDims d, cudaStream_t s);
 size_t trilinear_bwd_workspace(TriDims d);
 int debug_prof_read(unsigned long long* host_dst, int n);   // CTI_PROF builds only (returns -1 otherwise)
 int trilinear_bwd(const __nv_bfloat16* vc, const __nv_bfloat16* qc, const __nv_bfloat16* ac, const __nv_bfloat16* tpack,

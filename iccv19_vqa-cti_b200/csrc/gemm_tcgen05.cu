@@ -453,14 +453,14 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
 // 3-D bf16 tensor map (d0 contiguous), 128-byte swizzle or none, box {box0, box1, 1}; out-of-range rows read as zero.
 // Used by the per-sample kernels to load one sample's (tokens x channels) tile with the token rows padded.
 int make_tmap_3d(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
-                 uint64_t stride2_elems, uint32_t box0, uint32_t box1, bool swizzle128) {
+                 uint64_t stride2_elems, uint32_t box0, uint32_t box1, bool swizzle128, uint32_t box2) {
   auto fn = get_encode_fn();
   CTI_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
   CTI_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand must be 16-byte aligned");
   CTI_REQUIRE((stride1_elems * 2) % 16 == 0 && (stride2_elems * 2) % 16 == 0, "TMA strides must be multiples of 16 bytes");
   cuuint64_t gdim[3] = {d0, d1, d2};
   cuuint64_t gstride[2] = {stride1_elems * 2, stride2_elems * 2};
-  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t box[3] = {box0, box1, box2};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,

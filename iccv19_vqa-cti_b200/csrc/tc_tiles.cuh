@@ -100,6 +100,6 @@ struct Ring {
 
 // host side (defined in gemm_tcgen05.cu)
 int make_tmap_3d(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
-                 uint64_t stride2_elems, uint32_t box0, uint32_t box1, bool swizzle128 = true);
+                 uint64_t stride2_elems, uint32_t box0, uint32_t box1, bool swizzle128 = true, uint32_t box2 = 1);
 
 }  // namespace cti

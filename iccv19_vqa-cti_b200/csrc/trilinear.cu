@@ -610,15 +610,15 @@ int check_dims(const TriDims& d, const char* who) {
 
 }  // namespace
 
-int trilinear_fwd_tc(const bf16* vc, const bf16* qc, const bf16* ac, const bf16* tpack, const uint8_t* rowmask,
+int trilinear_fwd_tc(const bf16* vc, const bf16* qc, const bf16* ac, const bf16* tpack_perm, const uint8_t* rowmask,
                      float* logits, TriDims d, cudaStream_t stream);   // trilinear_tc.cu
 
-int trilinear_fwd(const bf16* vc, const bf16* qc, const bf16* ac, const bf16* tpack, const uint8_t* rowmask,
-                  float* logits, TriDims d, cudaStream_t stream) {
+int trilinear_fwd(const bf16* vc, const bf16* qc, const bf16* ac, const bf16* tpack, const bf16* tpack_perm,
+                  const uint8_t* rowmask, float* logits, TriDims d, cudaStream_t stream) {
   if (int rc = check_dims(d, "trilinear_fwd")) return rc;
   if (d.B == 0) return 0;
-  {   // tcgen05 fast path (G == 2, K <= 64, A <= 8); other shapes use the generic tensor-core kernel below
-    const int rc = trilinear_fwd_tc(vc, qc, ac, tpack, rowmask, logits, d, stream);
+  {   // tcgen05 fast path (G == 2, K <= 64, A <= 6, tpack_perm given); other shapes use the generic kernel below
+    const int rc = trilinear_fwd_tc(vc, qc, ac, tpack_perm, rowmask, logits, d, stream);
     if (rc != -100) return rc;
   }
   const TriShape s = make_shape(d);

@@ -248,14 +248,34 @@ def sum_row_groups(x: torch.Tensor, rep: int, row_elems: int) -> torch.Tensor:
     return out
 
 
-def trilinear_fwd(vc, qc, ac, tpack, rowmask, B, K, Q, A, G, R, v_rep: int = 1) -> torch.Tensor:
-    """vc (and rowmask) hold B / v_rep samples: rows b*v_rep .. b*v_rep + v_rep - 1 of qc / ac share image b."""
+_PERM_IDX = {}
+
+
+def tpack_perm(tpack: torch.Tensor) -> Optional[torch.Tensor]:
+    """The packed core (R, 16, 16*G*16) with its last axis in the accumulator-lane order of the tcgen05 forward kernel
+    (include/cti_sm100.h): position (j % 4) * 128 + g * 64 + i * 4 + j / 4 holds element i * 32 + g * 16 + j.
+    G = 2 only (None otherwise: the generic kernel reads the plain pack)."""
+    if tpack.shape[-1] != 512:
+        return None
+    idx = _PERM_IDX.get(tpack.device)
+    if idx is None:
+        x = torch.arange(512)
+        t, g, i, jj = x >> 7, (x >> 6) & 1, (x >> 2) & 15, x & 3
+        idx = _PERM_IDX[tpack.device] = (i * 32 + g * 16 + 4 * jj + t).to(tpack.device)
+    return tpack.index_select(-1, idx)
+
+
+def trilinear_fwd(vc, qc, ac, tpack, rowmask, B, K, Q, A, G, R, v_rep: int = 1, tpack_p=None) -> torch.Tensor:
+    """vc (and rowmask) hold B / v_rep samples: rows b*v_rep .. b*v_rep + v_rep - 1 of qc / ac share image b.
+    tpack_p: tpack_perm(tpack) if the caller already has it (built here otherwise)."""
     for t, n in ((vc, "vc"), (qc, "qc"), (ac, "ac"), (tpack, "tpack")):
         _req(t, BF16, "trilinear_fwd." + n)
+    if tpack_p is None:
+        tpack_p = tpack_perm(tpack)
     logits = torch.empty((B, G, K, Q, A), dtype=F32, device=vc.device)
     _call("cti_trilinear_logits_fwd", _lib.load().cti_trilinear_logits_fwd,
-          (vc.data_ptr(), qc.data_ptr(), ac.data_ptr(), tpack.data_ptr(), _ptr(rowmask), logits.data_ptr(), B, K, Q, A, G,
-           R, v_rep, _stream()), flops=float(B) * trilinear_min_flops(K, Q, A, G, R))
+          (vc.data_ptr(), qc.data_ptr(), ac.data_ptr(), tpack.data_ptr(), _ptr(tpack_p), _ptr(rowmask), logits.data_ptr(),
+           B, K, Q, A, G, R, v_rep, _stream()), flops=float(B) * trilinear_min_flops(K, Q, A, G, R))
     return logits
 
 

@@ -163,6 +163,9 @@ int cti_adamax_multi(const void* p_ptrs_dev, const void* g_ptrs_dev, const void*
 /* ---- trilinear logit map ----------------------------------------------------------------------
  * vc (B,K,R*16), qc (B,Q,R*16), ac (B,A,R*16) bf16: the per-rank projections, column = r*16 + i.
  * tpack (R,16,16*G*16) bf16: T_eff[r][l][(i,g,j)] (see DESIGN.md for the T_g -> T_eff permutation).
+ * tpack_perm (forward only; may be NULL): the same core with the last axis in the accumulator-lane order of the
+ *   tcgen05 kernel, tpack_perm[r][l][(j%4)*128 + g*64 + i*4 + j/4] = tpack[r][l][i*32 + g*16 + j]  (G = 2).  With NULL,
+ *   or for shapes outside the fast path (G != 2, A > 6, K > 64), the generic tensor-core kernel reads tpack.
  * logits (B,G,K,Q,A) fp32, -inf where rowmask[b*K+k] != 0 (rowmask may be NULL).
  * v_rep >= 1 (B % v_rep == 0): rows b*v_rep .. b*v_rep+v_rep-1 share ONE image -- vc and rowmask then hold B/v_rep
  *   samples and row b reads sample b / v_rep.  This is the MC x4 candidate clone of src/MC/train.py:75-76 without the
@@ -170,8 +173,9 @@ int cti_adamax_multi(const void* p_ptrs_dev, const void* g_ptrs_dev, const void*
  *   cti_sum_row_groups before the v-side wgrad.
  * replaces: the rank loop of TCNet.forward (src/tc.py:46-52) incl. Tensor.ModeProduct
  *           (src/Tensor.py:3-19) and the masked_fill_ of src/attention.py:55-56. */
-int cti_trilinear_logits_fwd(const void* vc, const void* qc, const void* ac, const void* tpack, const uint8_t* rowmask,
-                             float* logits, int B, int K, int Q, int A, int G, int R, int v_rep, void* stream);
+int cti_trilinear_logits_fwd(const void* vc, const void* qc, const void* ac, const void* tpack, const void* tpack_perm,
+                             const uint8_t* rowmask, float* logits, int B, int K, int Q, int A, int G, int R, int v_rep,
+                             void* stream);
 size_t cti_trilinear_logits_bwd_workspace(int B, int K, int Q, int A, int G, int R);
 /* dz* are the PRE-activation gradients of the per-rank projections (ReLU masks applied);
  * db*_accum (R*16 each) and dtpack_accum (same shape as tpack, fp32) are accumulated into. */

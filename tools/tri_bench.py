@@ -96,6 +96,14 @@ if args.prof:
         units = (B + 147) // 148 * R
         res["prof_cycles_per_unit_mean_over_blocks"] = (t.mean(0) / units).round().tolist()
         res["prof_units_per_block"] = units
+        tb = (ctypes.c_ulonglong * (8 * 256))()
+        if lib.cti_debug_prof_read(tb, 8 * 256) == 0:
+            tr = torch.tensor(list(tb), dtype=torch.float64).view(8, 256)
+            t0 = tr[0, 64].item()
+            names = ["tma_issue", "f1_issue", "f2_issue", "iii_issue", "c1_start", "c2_start", "c1_done", "c2_done"]
+            print("trace (block 0, cycles relative to the TMA issue of unit 64):")
+            for u in range(64, 84):
+                print(f"  u={u:3d} " + " ".join(f"{n}={int(tr[i, u].item() - t0):6d}" for i, n in enumerate(names)))
     else:
         res["prof"] = "library not built with CTI_PROF"
 print(json.dumps(res))
