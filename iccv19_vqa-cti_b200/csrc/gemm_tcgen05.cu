@@ -469,6 +469,27 @@ int make_tmap_3d(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1, ui
   return 0;
 }
 
+// 4-D bf16 tensor map (128-byte swizzle): strides in elements for dims 1..3, one box extent per dim.
+int make_tmap_4d(CUtensorMap* map, const void* ptr, const uint64_t (&dims)[4], const uint64_t (&strides_elems)[3],
+                 const uint32_t (&box)[4]) {
+  auto fn = get_encode_fn();
+  CTI_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  CTI_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand must be 16-byte aligned");
+  cuuint64_t gdim[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t gstride[3];
+  for (int i = 0; i < 3; ++i) {
+    CTI_REQUIRE((strides_elems[i] * 2) % 16 == 0, "TMA strides must be multiples of 16 bytes");
+    gstride[i] = strides_elems[i] * 2;
+  }
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstride, bx, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CTI_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(4d) failed with CUresult %d", (int)r);
+  return 0;
+}
+
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
   CTI_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
   CTI_REQUIRE(g.out_bf16 != nullptr || g.out_f32 != nullptr, "gemm: no output buffer");

@@ -62,6 +62,14 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t bar, uint32_t smem_dst, int32_t c0,
+                                            int32_t c1, int32_t c2, int32_t c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
 // 1-D bulk copy global -> shared (bytes % 16 == 0, both 16-byte aligned), completes on an mbarrier.
 __device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -101,5 +109,8 @@ struct Ring {
 // host side (defined in gemm_tcgen05.cu)
 int make_tmap_3d(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
                  uint64_t stride2_elems, uint32_t box0, uint32_t box1, bool swizzle128 = true, uint32_t box2 = 1);
+
+int make_tmap_4d(CUtensorMap* map, const void* ptr, const uint64_t (&dims)[4], const uint64_t (&strides_elems)[3],
+                 const uint32_t (&box)[4]);
 
 }  // namespace cti

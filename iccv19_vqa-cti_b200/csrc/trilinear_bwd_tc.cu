@@ -566,12 +566,19 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
 // =========================================================================== //
 // kernel 2
 // =========================================================================== //
-constexpr int kThreads2 = 256;
-constexpr int S2_DN1 = 0, S2_AC = 16384, S2_BYTES = 18432, S2_RING = 8;      // deep ring: the kernel is a stream of small TMA boxes
-constexpr int KP2 = 8;                                   // partial accumulators of B5 (32 K steps -> chains of 4)
-constexpr uint32_t TM2_D5 = 0, TM2_D6 = 256;             // D5: 2 slots x KP2 x 16 columns
-enum { C_TTFULL = 0, C_SFULL = 1, C_SEMPTY = 1 + S2_RING, C_D5FULL = 1 + 2 * S2_RING, C_D5EMPTY = 3 + 2 * S2_RING,
-       C_D6FULL = 5 + 2 * S2_RING, C_COUNT = 6 + 2 * S2_RING };
+// Rank-outer: CTA (r, sample chunk) keeps T_r resident and streams the dN1_r rows of its samples EIGHT samples per stage:
+//   B5  dAc^T[l, (s,a)] = T_r[l, x] . dN1[(s,a), x]^T        M = 64 (16 valid rows l), N = 64 (8 samples x 8), K = x = 512
+//   B6  dT_r^T[x, l]   += dN1[(s,a), x]^T . Ac_r[(s,a), l]    4 tiles of 128 x, N = 16, K = (s,a) = 64 per stage
+// Round 1 streamed two samples per stage from ONE issuing thread: 36 MMAs per pair at ~100 cycles of issue latency each
+// made that thread the bottleneck (167 us for 1024 rows; tools/ubench).  Now four threads issue, each 8 of the 32 K steps
+// of B5 into its own partial accumulator (two partials share a column range through the 16-lane interleave of M = 64
+// accumulators) and one of the four B6 tiles: 12 MMAs per thread per 8 samples instead of 144 on one thread.
+constexpr int kThreads2 = 320;     // warp 0 TMA | warps 1, 2, 3, 9 issuers (2 also owns TMEM) | warps 4, 8 dAc epilogue | 4-7 final dT flush
+constexpr int OCT = 8;                                   // samples per stage
+constexpr int S2_DN1 = 0, S2_AC = OCT * 8192, S2_BYTES = OCT * (8192 + 1024), S2_RING = 2;
+constexpr uint32_t TM2_D5 = 0, TM2_D6 = 256;             // D5: 2 slots x 2 column ranges x 64 columns (x 2 lane halves)
+enum { C_TTFULL = 0, C_SFULL = 1, C_SEMPTY = C_SFULL + S2_RING, C_D5FULL = C_SEMPTY + S2_RING, C_D5EMPTY = C_D5FULL + 2,
+       C_D6FULL = C_D5EMPTY + 2, C_COUNT = C_D6FULL + 1 };
 
 struct Bwd2Params {
   bf16* dza;
@@ -603,13 +610,13 @@ trilinear_bwd2_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
     mbar_init(bar(C_TTFULL), 1);
     for (int s = 0; s < S2_RING; ++s) {
       mbar_init(bar(C_SFULL + s), 1);
-      mbar_init(bar(C_SEMPTY + s), 5);
+      mbar_init(bar(C_SEMPTY + s), 5);          // four issuers (commit after their last MMA on the stage) + the epilogue warp
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar(C_D5FULL + s), 1);
-      mbar_init(bar(C_D5EMPTY + s), 4);
+      mbar_init(bar(C_D5FULL + s), 4);
+      mbar_init(bar(C_D5EMPTY + s), 1);
     }
-    mbar_init(bar(C_D6FULL), 1);
+    mbar_init(bar(C_D6FULL), 4);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -624,108 +631,119 @@ trilinear_bwd2_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
   pdl_prologue_done();      // everything above touched only this CTA's shared memory / TMEM
 
   const int n_my = (p.B - chunk + p.n_chunks - 1) / p.n_chunks;      // samples chunk, chunk + n_chunks, ...
-  const int n_pairs = (n_my + 1) >> 1;
+  const int n_oct = (n_my + OCT - 1) / OCT;
 
   if (warp == 0) {
     if (lane == 0) {
       mbar_arrive_expect_tx(bar(C_TTFULL), T_BYTES);
 #pragma unroll
       for (int c = 0; c < 8; ++c) tma_load_3d(&tmap_t, bar(C_TTFULL), sT + c * 2048, c * 64, r * 16, 0);
-      for (int pi = 0; pi < n_pairs; ++pi) {
-        const int slot = pi % S2_RING;
-        mbar_wait(bar(C_SEMPTY + slot), ((pi / S2_RING) & 1) ^ 1);
+      for (int oi = 0; oi < n_oct; ++oi) {
+        const int slot = oi % S2_RING;
+        mbar_wait(bar(C_SEMPTY + slot), ((oi / S2_RING) & 1) ^ 1);
         mbar_arrive_expect_tx(bar(C_SFULL + slot), S2_BYTES);
         const uint32_t dst = sS + slot * S2_BYTES;
-        for (int s = 0; s < 2; ++s) {
-          const int b = chunk + (2 * pi + s) * p.n_chunks;            // b >= B: every box is out of range -> zeros
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            tma_load_3d(&tmap_dn1, bar(C_SFULL + slot), dst + S2_DN1 + c * 2048 + s * 1024, c * 64, 0, b * p.R + r);
+        for (int s = 0; s < OCT; ++s) {
+          const int b = chunk + (OCT * oi + s) * p.n_chunks;            // b >= B: the boxes are out of range -> zeros
+          // one box (64 x, 8 rows a, 8 chunks) per sample: lands as [chunk][8 rows][128 B] (rows a >= A zero-filled)
+          tma_load_4d(&tmap_dn1, bar(C_SFULL + slot), dst + S2_DN1 + s * 8192, 0, 0, 0, b * p.R + r);
           tma_load_3d(&tmap_a8, bar(C_SFULL + slot), dst + S2_AC + s * 1024, (r >> 2) * 64, 0, b);
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 2 || warp == 3 || warp == 9) {
     if (lane == 0) {
-      const uint32_t id_b5 = make_idesc_rt(64, 16, 0, 0);     // only rows l < 16 are valid: M = 64 halves the A-operand read
+      const int w = warp == 9 ? 3 : warp - 1;                 // issuer index: K steps 8w .. 8w+7 of B5, tile w of B6
+      const uint32_t id_b5 = make_idesc_rt(64, 64, 0, 0);     // only rows l < 16 are valid: M = 64 halves the A-operand read
       const uint32_t id_b6 = make_idesc_rt(128, 16, 1, 1);
       mbar_wait(bar(C_TTFULL), 0);
-      for (int pi = 0; pi < n_pairs; ++pi) {
-        const int slot = pi % S2_RING;
+      // partial accumulator of this issuer: column range w >> 1, lane half w & 1 (M = 64 accumulators use 16 lanes of
+      // every 32-lane quarter; the second one sits in the other 16 -- tcgen05 "interleaved" allocation)
+      const uint32_t d5_off = TM2_D5 + (w >> 1) * 64 + (static_cast<uint32_t>((w & 1) * 16) << 16);
+      for (int oi = 0; oi < n_oct; ++oi) {
+        const int slot = oi % S2_RING;
         const uint32_t st = sS + slot * S2_BYTES;
-        mbar_wait(bar(C_SFULL + slot), (pi / S2_RING) & 1);
-        mbar_wait(bar(C_D5EMPTY + (pi & 1)), ((pi >> 1) & 1) ^ 1);
+        mbar_wait(bar(C_SFULL + slot), (oi / S2_RING) & 1);
+        mbar_wait(bar(C_D5EMPTY + (oi & 1)), ((oi >> 1) & 1) ^ 1);
         tcgen05_fence_after();
-        // B5: dAc^T[l, (s,a)] = T_r[l, x] . dN1[(s,a), x]^T      (x = (i,g,j), 512 = 32 K steps)
+        // B5: dAc^T[l, (s,a)] = T_r[l, x] . dN1[(s,a), x]^T over this issuer's 128 x (chunks 2w, 2w+1).
+        // dN1 stage layout [sample][chunk][8 rows][128 B]: the 8-row groups of the N operand are 8192 B apart (SBO)
         {
-          const uint64_t da0 = desc_kmajor(sT, 0), db0 = desc_kmajor(st + S2_DN1, 0);
+          const uint64_t da0 = make_smem_desc_sw128(sT + 2 * w * 2048, 16u, 1024u);
+          const uint64_t db0 = make_smem_desc_sw128(st + S2_DN1 + 2 * w * 1024, 16u, 8192u);
 #pragma unroll
-          for (int ks = 0; ks < 32; ++ks)
-            umma_bf16_ss(tmem_base + TM2_D5 + (pi & 1) * (KP2 * 16) + (ks & (KP2 - 1)) * 16,
-                         da0 + (uint64_t)(((ks >> 2) * 2048 + (ks & 3) * 32) >> 4),
-                         db0 + (uint64_t)(((ks >> 2) * 2048 + (ks & 3) * 32) >> 4), id_b5, ks >= KP2 ? 1u : 0u);
+          for (int ks = 0; ks < 8; ++ks)
+            umma_bf16_ss(tmem_base + d5_off + (oi & 1) * 128, da0 + (uint64_t)(((ks >> 2) * 2048 + (ks & 3) * 32) >> 4),
+                         db0 + (uint64_t)(((ks >> 2) * 1024 + (ks & 3) * 32) >> 4), id_b5, ks > 0 ? 1u : 0u);
         }
-        umma_commit(bar(C_D5FULL + (pi & 1)));
-        // B6: dT_r^T[x, l] += dN1[(s,a), x]^T . Ac_r[(s,a), l]
-        for (int t = 0; t < 4; ++t)
-          umma_bf16_ss(tmem_base + TM2_D6 + t * 16, desc_mnmajor(st + S2_DN1 + 2 * t * 2048, 0, 2048),
-                       desc_mnmajor(st + S2_AC + (r & 3) * 32, 0, 0), id_b6, pi > 0 ? 1u : 0u);
+        umma_commit(bar(C_D5FULL + (oi & 1)));
+        // B6: dT_r^T[x, l] += dN1[(s,a), x]^T . Ac_r[(s,a), l], tile w (x = 128 w ..): K = (s,a) = 64 = 4 steps of 2 samples.
+        // A: MN-major, 64 x per 128-byte row (chunks 1024 B apart = LBO), 8 K-rows per atom, next sample 8192 B (SBO)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_bf16_ss(tmem_base + TM2_D6 + w * 16, make_smem_desc_sw128(st + S2_DN1 + 2 * w * 1024 + ks * 16384, 1024u, 8192u),
+                       make_smem_desc_sw128(st + S2_AC + (r & 3) * 32 + ks * 2048, 0u, 1024u), id_b6, (oi > 0 || ks > 0) ? 1u : 0u);
         umma_commit(bar(C_SEMPTY + slot));
       }
       umma_commit(bar(C_D6FULL));
     }
-  } else if (warp >= 4) {
-    const int qd = warp & 3, L = qd * 32 + lane;
-    const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
+  }
+  if (warp == 4 || warp == 8) {
+    // ---- dAc epilogue: warp 4 takes the even stages, warp 8 the odd ones (both sit on TMEM lanes 0-31).  Lanes 0-15 hold
+    // l for the partials of issuers 0 / 2, lanes 16-31 the same l for issuers 1 / 3: add the two column ranges, fold the
+    // lane halves with one shuffle, then lanes 0-15 write the even (s,a) columns and lanes 16-31 the odd ones. ----
+    const int l = lane & 15;
     float dba_acc = 0.f;
-    for (int pi = 0; pi < n_pairs; ++pi) {
-      const int slot = pi % S2_RING;
+    for (int oi = warp == 4 ? 0 : 1; oi < n_oct; oi += 2) {
+      const int slot = oi % S2_RING;
       const uint32_t st = sS + slot * S2_BYTES;
-      mbar_wait(bar(C_SFULL + slot), (pi / S2_RING) & 1);
-      mbar_wait(bar(C_D5FULL + (pi & 1)), (pi >> 1) & 1);
+      mbar_wait(bar(C_SFULL + slot), (oi / S2_RING) & 1);
+      mbar_wait(bar(C_D5FULL + (oi & 1)), (oi >> 1) & 1);
       tcgen05_fence_after();
-      uint32_t v[16];
-      {
-        float acc[16];
+      float acc[64];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+      for (int h = 0; h < 2; ++h) {
+        uint32_t w0[32], w1[32];
+        tmem_ld_32x32b_x32(tmem_base + TM2_D5 + (oi & 1) * 128 + h * 32, w0);
+        tmem_ld_32x32b_x32(tmem_base + TM2_D5 + (oi & 1) * 128 + 64 + h * 32, w1);
+        tmem_wait_ld();
 #pragma unroll
-        for (int x = 0; x < KP2; x += 2) {
-          uint32_t w0[16], w1[16];
-          tmem_ld_32x32b_x16(tmem_base + lane_addr + TM2_D5 + (pi & 1) * (KP2 * 16) + x * 16, w0);
-          tmem_ld_32x32b_x16(tmem_base + lane_addr + TM2_D5 + (pi & 1) * (KP2 * 16) + (x + 1) * 16, w1);
-          tmem_wait_ld();
-#pragma unroll
-          for (int c = 0; c < 16; ++c) acc[c] += __uint_as_float(w0[c]) + __uint_as_float(w1[c]);
-        }
-#pragma unroll
-        for (int c = 0; c < 16; ++c) v[c] = __float_as_uint(acc[c]);
+        for (int c = 0; c < 32; ++c) acc[h * 32 + c] = __uint_as_float(w0[c]) + __uint_as_float(w1[c]);
       }
       tcgen05_fence_before();
-      if (qd == 0 && lane < 16) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(C_D5EMPTY + (oi & 1)));
 #pragma unroll
-        for (int sa = 0; sa < 16; ++sa) {
-          const int s = sa >> 3, a = sa & 7;
-          const int b = chunk + (2 * pi + s) * p.n_chunks;
-          if (a < p.A && b < p.B) {
-            const int col = (r & 3) * 16 + lane;
-            const float act = bf16_bits_to_float(ld_shared_u16(st + S2_AC + sw128_off(sa, col)));
-            const float gv = act > 0.f ? __uint_as_float(v[sa]) : 0.f;
-            p.dza[((size_t)b * p.A + a) * RD + r * 16 + lane] = __float2bfloat16(gv);
-            dba_acc += gv;
-          }
+      for (int c = 0; c < 64; c += 2) {
+        // fold the lane halves; lanes 0-15 keep column c, lanes 16-31 column c + 1
+        const float mine = lane < 16 ? acc[c] : acc[c + 1];
+        const float send = lane < 16 ? acc[c + 1] : acc[c];
+        const float tot = mine + __shfl_xor_sync(0xffffffffu, send, 16);
+        const int sa = c + (lane >> 4);
+        const int s = sa >> 3, a = sa & 7;
+        const int b = chunk + (OCT * oi + s) * p.n_chunks;
+        if (a < p.A && b < p.B) {
+          const int col = (r & 3) * 16 + l;
+          const float act = bf16_bits_to_float(ld_shared_u16(st + S2_AC + s * 1024 + sw128_off(a, col)));
+          const float gv = act > 0.f ? tot : 0.f;
+          p.dza[((size_t)b * p.A + a) * RD + r * 16 + l] = __float2bfloat16(gv);
+          dba_acc += gv;
         }
       }
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(bar(C_D5EMPTY + (pi & 1)));
-        mbar_arrive(bar(C_SEMPTY + slot));
-      }
+      if (lane == 0) mbar_arrive(bar(C_SEMPTY + slot));
     }
-    if (qd == 0 && lane < 16) atomicAdd(p.dba + r * 16 + lane, dba_acc);
+    dba_acc += __shfl_xor_sync(0xffffffffu, dba_acc, 16);
+    if (lane < 16) atomicAdd(p.dba + r * 16 + l, dba_acc);
+  }
+  if (warp >= 4 && warp < 8) {
+    // ---- final flush of dT_r (accumulated over every sample of this CTA) ----
+    const int qd = warp & 3, L = qd * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
     mbar_wait(bar(C_D6FULL), 0);
     tcgen05_fence_after();
-    if (n_pairs > 0) {
+    if (n_oct > 0) {
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         uint32_t v[16];
@@ -765,7 +783,12 @@ int trilinear_bwd_tc(const bf16* vc, const bf16* qc, const bf16* ac, const bf16*
   if (int rc = make_tmap_3d(&tq, qc, RD, d.Q, d.B, RD, (uint64_t)d.Q * RD, 64, 16)) return rc;
   if (int rc = make_tmap_3d(&ta, ac, RD, d.A, d.B, RD, (uint64_t)d.A * RD, 64, 16)) return rc;
   if (int rc = make_tmap_3d(&tdl, dlm, N, d.K, d.B, N, (uint64_t)d.K * N, 64, 64)) return rc;
-  if (int rc = make_tmap_3d(&tdn, dn1, 512, d.A, (uint64_t)d.B * d.R, 512, (uint64_t)d.A * 512, 64, 8)) return rc;
+  {   // dN1 [b][r][a][512] viewed as (64 x, A rows, 8 chunks, B*R): one box (64, 8, 8, 1) per (sample, rank)
+    const uint64_t dims[4] = {64, (uint64_t)d.A, 8, (uint64_t)d.B * d.R};
+    const uint64_t strides[3] = {512, 64, (uint64_t)d.A * 512};
+    const uint32_t box[4] = {64, 8, 8, 1};
+    if (int rc = make_tmap_4d(&tdn, dn1, dims, strides, box)) return rc;
+  }
   if (int rc = make_tmap_3d(&ta8, ac, RD, d.A, d.B, RD, (uint64_t)d.A * RD, 64, 8)) return rc;
 
   static bool attr_set = false;
@@ -785,7 +808,7 @@ int trilinear_bwd_tc(const bf16* vc, const bf16* qc, const bf16* ac, const bf16*
   if (int rc = check_launch("trilinear_bwd1_tc_kernel")) return rc;
   int n_chunks = kNumSMsB200 / d.R;
   if (n_chunks < 1) n_chunks = 1;
-  if (n_chunks > (d.B + 1) / 2) n_chunks = (d.B + 1) / 2;
+  if (n_chunks > (d.B + OCT - 1) / OCT) n_chunks = (d.B + OCT - 1) / OCT;
   if (n_chunks < 1) n_chunks = 1;
   Bwd2Params p2{dza, dba, dtpack, d.B, d.A, d.R, n_chunks};
   launch_pdl(trilinear_bwd2_tc_kernel, dim3(d.R * n_chunks), dim3(kThreads2), kSmem2, stream, tt, tdn, ta8, p2);

@@ -28,7 +28,7 @@
 // Operands arrive by TMA: the packed core T_r (16 KB per rank, L2 resident, ring of 3) and, per four
 // ranks, one 64-column chunk of the sample's Vc / Qc / Ac rows (ring of 3).
 //
-// Roles (736 threads): warp 0 TMA | warps 1, 20, 21, 22 F1 issuers (one tile each) | warp 3 F2 issuer | warp 2 III issuer
+// Roles (640 threads): warp 0 TMA | warp 1 F1 issuer | warp 3 F2 issuer | warp 2 III issuer
 // (+ TMEM owner) | warps 4-7, 8-11 N1 converters (even / odd units) | warps 12-15 M converters | warps 16-19 epilogue.
 #include "cti_common.cuh"
 #include "cti_kernels.h"
@@ -62,7 +62,7 @@ __device__ unsigned long long g_trace[8 * 256];          // block 0: time at whi
 #define TRACE(role, u)
 #endif
 
-constexpr int kThreads = 736;                 // 23 warps
+constexpr int kThreads = 640;                 // 20 warps
 constexpr int T_BYTES = 16 * 1024;            // T_r: [16 l][512 x] bf16 = 8 chunks x [16 rows][128 B]
 constexpr int T_RING = 3;
 constexpr int OP_V = 0, OP_Q = 8192, OP_A = 10240, OP_BYTES = 12288;   // Vc [64][64], Qc [16][64], Ac [16][64]
@@ -132,7 +132,7 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
       mbar_init(bar(B_OPEMPTY + s), 1);
     }
     for (int s = 0; s < F1_RING; ++s) {
-      mbar_init(bar(B_F1FULL + s), 4);          // the four F1 issuers
+      mbar_init(bar(B_F1FULL + s), 1);
       mbar_init(bar(B_F1EMPTY + s), 4);
     }
     for (int s = 0; s < 2; ++s) mbar_init(bar(B_N1EMPTY + s), 1);
@@ -195,11 +195,12 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
       }
       PROF_FLUSH(0);
     }
-  } else if (warp == 1 || warp >= 20) {
-    // ------------------------------ F1 issuers: N1^T = T_r^T . Ac_r^T, one 128-row tile each (warps 1, 20, 21, 22): a
-    // thread needs ~130 cycles per tcgen05.mma in this loop, so four of them keep F1 off the critical path ----
+  } else if (warp == 1) {
+    // ------------------------------ F1 issuer: N1^T = T_r^T . Ac_r^T.  (Splitting the four tiles over several issuing
+    // threads does not help: every tcgen05.mma / tcgen05.commit is an entry of ONE in-order queue per SM that drains at
+    // ~75 cycles per entry in these kernels -- measured: the kernel time follows (MMAs + commits) per unit x 75 cycles
+    // whatever the number of issuers; more issuers only add commits.) ----
     if (lane == 0) {
-      const int t0 = warp == 1 ? 0 : warp - 19;
       const uint32_t id_f1 = make_idesc_rt(128, 16, 1, 0);
       PROF_DECL
       uint32_t tslot = 0, tph = 0, oslot = 0, oph = 0, fslot = 0, fph = 0;
@@ -217,10 +218,12 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
         PROF_ADD(2);
         PROF_T0();
         tcgen05_fence_after();
-        if (warp == 1) TRACE(1, u);
+        TRACE(1, u);
         const uint64_t db = desc_kmajor(sOp + oslot * OP_BYTES + OP_A, r & 3);
         const uint64_t da = desc_mnmajor(tt, 0, 2048);
-        umma_bf16_ss(tmem_base + TM_F1 + fslot * 64 + t0 * 16, da + (uint64_t)(2 * t0 * 2048 >> 4), db, id_f1, 0u);
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          umma_bf16_ss(tmem_base + TM_F1 + fslot * 64 + t * 16, da + (uint64_t)(2 * t * 2048 >> 4), db, id_f1, 0u);
         umma_commit(bar(B_F1FULL + fslot));
         if (++fslot == F1_RING) { fslot = 0; fph ^= 1u; }
         if (++tslot == T_RING) { tslot = 0; tph ^= 1u; }
@@ -228,7 +231,7 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
         if ((r & 3) == 0 && ++oslot == OP_RING) { oslot = 0; oph ^= 1u; }
         PROF_ADD(3);
       }
-      if (warp == 1) PROF_FLUSH(1);
+      PROF_FLUSH(1);
     }
   } else if (warp == 3) {
     // ------------------------------ F2 issuer: M = N1 . Qc_r^T.  One wait for the whole N1 quad tile, then the 8 MMAs of

@@ -22,9 +22,12 @@ __global__ void __launch_bounds__(256, 1) k_multi(Res* res, int M, int N, int n,
   if (warp >= 1 && warp <= nthreads && lane == 0) {
     const int w = warp - 1;
     const uint32_t sA = base + w * (16384 + 8192), sB = sA + 16384;
-    const uint32_t idesc = make_idesc_rt(M, N, a_mn, b_mn);
-    const uint64_t da = a_mn ? desc_mnmajor(sA, 0, 2048) : desc_kmajor(sA, 0);
-    const uint64_t db = b_mn ? desc_mnmajor(sB, 0, 2048) : desc_kmajor(sB, 0);
+    // a_mn == 2: MIXED -- issuer w uses shape / major-ness variant w (different instruction descriptors per thread)
+    const int va = a_mn == 2 ? (w & 1) : a_mn, vb = a_mn == 2 ? ((w >> 1) & 1) : b_mn;
+    const int vN = a_mn == 2 ? (w == 3 ? 64 : N) : N;
+    const uint32_t idesc = make_idesc_rt(M, vN, va, vb);
+    const uint64_t da = va ? desc_mnmajor(sA, 0, 2048) : desc_kmajor(sA, 0);
+    const uint64_t db = vb ? desc_mnmajor(sB, 0, 2048) : desc_kmajor(sB, 0);
     for (int rep = 0; rep < 3; ++rep) {
       unsigned long long t0 = clock64();
       for (int i = 0; i < n; ++i) {
@@ -75,6 +78,16 @@ int main() {
     unsigned long long mx = 0; for (int w = 0; w < T; ++w) mx = h.v[4 + w] > mx ? h.v[4 + w] : mx;
     printf("%-40s M=%3d N=%3d threads=%d: %.1f cycles/MMA SM-wide\n", c.what, c.M, c.N, T, (double)mx / (32 * T));
     fflush(stdout);
+  }
+  printf("# mixed instruction descriptors across issuers (thread w: a_mn = w&1, b_mn = (w>>1)&1, N = 64 for w = 3) vs uniform\n");
+  for (int mixed = 0; mixed < 2; ++mixed) for (int T = 2; T <= 4; ++T) {
+    cudaMemset(d, 0, sizeof(Res));
+    k_multi<<<1, 256, smem>>>(d, 128, 16, 32, T, 0, mixed ? 2 : 0, 0);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+    cudaMemcpy(&h, d, sizeof(Res), cudaMemcpyDeviceToHost);
+    unsigned long long mx = 0; for (int w = 0; w < T; ++w) mx = h.v[4 + w] > mx ? h.v[4 + w] : mx;
+    printf("%s threads=%d: %.1f cycles/MMA SM-wide\n", mixed ? "mixed  " : "uniform", T, (double)mx / (32 * T));
   }
   return 0;
 }
