@@ -31,6 +31,7 @@ SIGNATURES = {
     "cti_gru_gate_fwd": (c_int, [_P, c_int64, _P, _P, c_int64, _P, c_int64, _P, _P, _P, _P, _P, c_int64, c_int, _P]),
     "cti_gru_gate_bwd": (c_int, [_P, _P, c_int64, _P, c_int64, _P, _P, _P, _P, _P, c_int64, _P, c_int64, c_int, _P]),
     "cti_wn_pack_multi": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, c_int, _P, _P]),
+    "cti_wn_grad_multi": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, c_int, _P, _P]),
     "cti_wn_scratch_floats": (c_size_t, [c_int, c_int, c_int]),
     "cti_wn_pack": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "cti_wn_grad": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),

@@ -66,7 +66,7 @@ class BCNet(nn.Module):
                 drops = (features_f32_2d(v) if sites[0] is not None else None, *sites)
         return F_.BiLogitsFn.apply((B, K, Q, G, C), [lv.packed(), lq.packed()], drops, v_bf16,
                                    rowmask if rowmask_wanted else None, q, self._effective_h_mat(), self.h_bias,
-                                   lv.weight_v, lv.weight_g, lv.bias, lq.weight_v, lq.weight_g, lq.bias)
+                                   lv.v_in(), lv.weight_g, lv.bias, lq.v_in(), lq.weight_g, lq.bias)
 
     def forward(self, v, q):
         """v (B,K,v_dim), q (B,Q,q_dim) -> bilinear logits (B, h_out, K, Q)."""
@@ -87,8 +87,8 @@ class BCNet(nn.Module):
             sites = [F_.new_drop(p, True) for p in (pv, pq)]
             if any(d is not None for d in sites):
                 drops = (features_f32_2d(v) if sites[0] is not None else None, *sites, None)
-        out = F_.PoolFn.apply((B, K, Q, 0, C), [lv.packed(), lq.packed()], drops, v_bf16, q, None, w, lv.weight_v,
-                              lv.weight_g, lv.bias, lq.weight_v, lq.weight_g, lq.bias)
+        out = F_.PoolFn.apply((B, K, Q, 0, C), [lv.packed(), lq.packed()], drops, v_bf16, q, None, w, lv.v_in(),
+                              lv.weight_g, lv.bias, lq.v_in(), lq.weight_g, lq.bias)
         if 1 < self.k:
             out = out.view(B, -1, self.k).sum(2)                   # AvgPool1d(k) * k (src/bc.py:75-77)
         return out

@@ -40,9 +40,9 @@ class SimpleClassifier(nn.Module):
         shape = x.shape
         y = x.reshape(-1, shape[-1])
         l0, l1 = self.main[0], self.main[3]
-        h = F_.WNLinearFn.apply(y, l0.weight_v, l0.weight_g, l0.bias, self._relu, l0.packed(), None)
+        h = F_.WNLinearFn.apply(y, l0.v_in(), l0.weight_g, l0.bias, self._relu, l0.packed(), None)
         if not self._relu:
             h = self.main[1](h)
-        logits = F_.WNLinearFn.apply(h, l1.weight_v, l1.weight_g, l1.bias, False, l1.packed(),
+        logits = F_.WNLinearFn.apply(h, l1.v_in(), l1.weight_g, l1.bias, False, l1.packed(),
                                      F_.new_drop(self.main[2].p, self.training))
         return logits.view(*shape[:-1], logits.shape[-1])

@@ -79,6 +79,15 @@ int cti_wn_pack_multi(const void* v_ptrs_dev, const void* g_ptrs_dev, const void
                             n_blks, partials, static_cast<cudaStream_t>(stream));
 }
 
+int cti_wn_grad_multi(const void* dw_ptrs_dev, const void* v_ptrs_dev, const void* g_ptrs_dev, const void* sumsq_ptrs_dev,
+                      const void* dv_ptrs_dev, const void* dg_ptrs_dev, const int64_t* elems_dev, const int32_t* first_seg_dev,
+                      const int32_t* n_seg_dev, const int32_t* seg_entry_dev, const int32_t* seg_index_dev, int n_segs,
+                      const int32_t* blk_entry_dev, const int32_t* blk_index_dev, int n_blks, float* partials, void* stream) {
+  return cti::wn_grad_multi(dw_ptrs_dev, v_ptrs_dev, g_ptrs_dev, sumsq_ptrs_dev, dv_ptrs_dev, dg_ptrs_dev,
+                            reinterpret_cast<const long*>(elems_dev), first_seg_dev, n_seg_dev, seg_entry_dev, seg_index_dev,
+                            n_segs, blk_entry_dev, blk_index_dev, n_blks, partials, static_cast<cudaStream_t>(stream));
+}
+
 size_t cti_wn_scratch_floats(int n_groups, int rows_per_group, int cols) {
   return cti::wn_scratch_floats(n_groups, rows_per_group, cols);
 }

@@ -290,42 +290,72 @@ __global__ void __launch_bounds__(256) wn_grad_kernel(const float* __restrict__ 
 
 // ------------------------------------------------------------------------- //
 // dz[m,n] = dy[m,n] * (y[m,n] > 0);  dbias[n] += sum_m dz[m,n].
-// Block = 256 threads x 2 columns = 512-column slab, rows_per_block rows (chosen by the host so that the grid is a
-// few waves of 148 SMs: every block ends with one atomic per column, and 1600 blocks hammering the same 512 addresses
-// held the column-sum pass at 1.3 TB/s).
+// Round 1 gave every thread two columns (4-byte loads): 0.06 of the copy bandwidth.  Now a thread owns EIGHT consecutive
+// columns (16-byte bf16 / 2 x 16-byte fp32 loads), a block covers 8 x kAbbLanes columns x rows_per_block rows with
+// 256 / kAbbLanes row lanes, the row lanes' partial column sums meet in shared memory and each block issues one atomic
+// per column (the host sizes rows_per_block for a few waves of 148 SMs).
+constexpr int kAbbLanes = 32;                 // column lanes per block: 32 x 8 = 256 columns
+constexpr int kAbbRows = 256 / kAbbLanes;     // row lanes per block
 
 template <bool DY_BF16>
 __global__ void __launch_bounds__(256) act_bwd_bias_kernel(const void* __restrict__ dy_, const __nv_bfloat16* __restrict__ y,
                                                            __nv_bfloat16* __restrict__ dz, float* __restrict__ dbias,
                                                            long rows, int cols, int rows_per_block) {
   pdl_prologue_done();
-  const int c = (blockIdx.x * 256 + threadIdx.x) * 2;
-  if (c >= cols) return;   // cols is even (checked by the caller)
+  __shared__ float red[kAbbRows][kAbbLanes * 8 + 8];
+  const int cl = threadIdx.x % kAbbLanes, rl = threadIdx.x / kAbbLanes;
+  const int c = (blockIdx.x * kAbbLanes + cl) * 8;
   const long r0 = static_cast<long>(blockIdx.y) * rows_per_block;
   const long r1 = min(r0 + rows_per_block, rows);
-  float s0 = 0.f, s1 = 0.f;
-#pragma unroll 8
-  for (long r = r0; r < r1; ++r) {
-    const long off = r * cols + c;
-    float2 d;
-    if (DY_BF16) {
-      d = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(static_cast<const __nv_bfloat16*>(dy_) + off));
-    } else {
-      d = *reinterpret_cast<const float2*>(static_cast<const float*>(dy_) + off);
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c < cols) {                                     // cols % 8 == 0 (checked by the caller)
+#pragma unroll 4
+    for (long r = r0 + rl; r < r1; r += kAbbRows) {
+      const long off = r * cols + c;
+      float d[8];
+      if (DY_BF16) {
+        const uint4 u = __ldcs(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(dy_) + off));
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 f = unpack_bf16x2(w[t]);
+          d[2 * t] = f.x;
+          d[2 * t + 1] = f.y;
+        }
+      } else {
+        const float4 a = __ldcs(reinterpret_cast<const float4*>(static_cast<const float*>(dy_) + off));
+        const float4 b = __ldcs(reinterpret_cast<const float4*>(static_cast<const float*>(dy_) + off) + 1);
+        d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+      }
+      if (y != nullptr) {
+        const uint4 u = *reinterpret_cast<const uint4*>(y + off);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 f = unpack_bf16x2(w[t]);
+          if (!(f.x > 0.f)) d[2 * t] = 0.f;
+          if (!(f.y > 0.f)) d[2 * t + 1] = 0.f;
+        }
+      }
+      if (dz != nullptr) {
+        uint4 o;
+        o.x = pack_bf16x2(d[0], d[1]); o.y = pack_bf16x2(d[2], d[3]); o.z = pack_bf16x2(d[4], d[5]); o.w = pack_bf16x2(d[6], d[7]);
+        *reinterpret_cast<uint4*>(dz + off) = o;
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) s[t] += d[t];
     }
-    if (y != nullptr) {
-      const float2 yy = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(y + off));
-      if (!(yy.x > 0.f)) d.x = 0.f;
-      if (!(yy.y > 0.f)) d.y = 0.f;
-    }
-    if (dz != nullptr) *reinterpret_cast<uint32_t*>(dz + off) = pack_bf16x2(d.x, d.y);
-    s0 += d.x;
-    s1 += d.y;
   }
-  if (dbias != nullptr) {
-    atomicAdd(dbias + c, s0);
-    atomicAdd(dbias + c + 1, s1);
-  }
+  if (dbias == nullptr) return;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) red[rl][cl * 8 + t] = s[t];
+  __syncthreads();
+  // 256 threads, 256 columns: thread x sums column x over the row lanes
+  float tot = 0.f;
+#pragma unroll
+  for (int j = 0; j < kAbbRows; ++j) tot += red[j][threadIdx.x];
+  const int col = blockIdx.x * kAbbLanes * 8 + threadIdx.x;
+  if (col < cols) atomicAdd(dbias + col, tot);
 }
 
 // ------------------------------------------------------------------------- //
@@ -378,6 +408,65 @@ __global__ void __launch_bounds__(256) wn_multi_scale_kernel(const WnMultiTable 
   u.x = pack_bf16x2(f.x * s, f.y * s);
   u.y = pack_bf16x2(f.z * s, f.w * s);
   *reinterpret_cast<uint2*>(t.w[e] + i) = u;
+}
+
+// Backward of the fold for MANY layers in two launches (mirror of the two kernels above; same arithmetic and summation
+// order as sumsq_kernel(v, dw) + wn_grad_kernel, so the results equal the per-layer backward bit for bit).
+struct WnGradMultiTable {
+  const float* const* dw;       // [entries] dW_eff of the entry (contiguous, elems floats)
+  const float* const* v;        // [entries] weight_v
+  const float* const* g;        // [entries] scalar weight_g
+  const float* const* sumsq;    // [entries] ||V||_F^2 left by the forward fold
+  float* const* dv;             // [entries] out: gradient of weight_v
+  float* const* dg;             // [entries] out: gradient of weight_g
+  const long* elems;
+  const int* first_seg;
+  const int* n_seg;
+};
+
+__global__ void __launch_bounds__(256) wn_multi_dot_kernel(const WnGradMultiTable t, const int* __restrict__ seg_entry,
+                                                           const int* __restrict__ seg_index, float* __restrict__ partial) {
+  pdl_prologue_done();
+  const int e = seg_entry[blockIdx.x];
+  const float* v = t.v[e];
+  const float* dw = t.dw[e];
+  const long lo = static_cast<long>(seg_index[blockIdx.x]) * kSeg;
+  const long hi = min(lo + kSeg, t.elems[e]);
+  float s = 0.f;
+  for (long i = lo + threadIdx.x; i < hi; i += blockDim.x) s += dw[i] * v[i];
+  s = warp_sum(s);
+  __shared__ float part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float x = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
+    x = warp_sum(x);
+    if (threadIdx.x == 0) partial[blockIdx.x] = x;
+  }
+}
+
+__global__ void __launch_bounds__(256) wn_multi_grad_kernel(const WnGradMultiTable t, const int* __restrict__ blk_entry,
+                                                            const int* __restrict__ blk_index,
+                                                            const float* __restrict__ partial) {
+  pdl_prologue_done();
+  __shared__ float sh[9];
+  const int e = blk_entry[blockIdx.x];
+  const float dt = group_total(partial + t.first_seg[e], t.n_seg[e], 0, 0, sh);     // <dW_eff, V>, fixed order
+  const long i = static_cast<long>(blk_index[blockIdx.x]) * 1024 + threadIdx.x * 4;
+  if (i >= t.elems[e]) return;
+  const float n2 = *t.sumsq[e];
+  const float rn = rsqrtf(n2);
+  const float s = *t.g[e] * rn;          // g / ||V||
+  const float c = dt / n2;
+  const float4 a = *reinterpret_cast<const float4*>(t.dw[e] + i);
+  const float4 b = *reinterpret_cast<const float4*>(t.v[e] + i);
+  float4 o;
+  o.x = s * (a.x - c * b.x);
+  o.y = s * (a.y - c * b.y);
+  o.z = s * (a.z - c * b.z);
+  o.w = s * (a.w - c * b.w);
+  *reinterpret_cast<float4*>(t.dv[e] + i) = o;
+  if (i == 0) *t.dg[e] = dt * rn;
 }
 
 // out[g, e] = sum_{j < rep} x[g * rep + j, e]  (bf16 in / out, fp32 sum): folds the per-row gradients of rows that share
@@ -495,6 +584,26 @@ int wn_pack_multi(const void* v_ptrs, const void* g_ptrs, const void* w_ptrs, co
   return check_launch("wn_multi_scale_kernel");
 }
 
+int wn_grad_multi(const void* dw_ptrs, const void* v_ptrs, const void* g_ptrs, const void* sumsq_ptrs, const void* dv_ptrs,
+                  const void* dg_ptrs, const long* elems, const int* first_seg, const int* n_seg, const int* seg_entry,
+                  const int* seg_index, int n_segs, const int* blk_entry, const int* blk_index, int n_blks, float* partials,
+                  cudaStream_t s) {
+  CTI_REQUIRE(n_segs > 0 && n_blks > 0, "wn_grad_multi: empty table");
+  WnGradMultiTable t;
+  t.dw = static_cast<const float* const*>(dw_ptrs);
+  t.v = static_cast<const float* const*>(v_ptrs);
+  t.g = static_cast<const float* const*>(g_ptrs);
+  t.sumsq = static_cast<const float* const*>(sumsq_ptrs);
+  t.dv = static_cast<float* const*>(dv_ptrs);
+  t.dg = static_cast<float* const*>(dg_ptrs);
+  t.elems = elems; t.first_seg = first_seg; t.n_seg = n_seg;
+  launch_pdl(wn_multi_dot_kernel, dim3(n_segs), dim3(256), 0, s, t, seg_entry, seg_index, partials);
+  int rc = check_launch("wn_multi_dot_kernel");
+  if (rc) return rc;
+  launch_pdl(wn_multi_grad_kernel, dim3(n_blks), dim3(256), 0, s, t, blk_entry, blk_index, static_cast<const float*>(partials));
+  return check_launch("wn_multi_grad_kernel");
+}
+
 size_t wn_scratch_floats(int n_groups, int rows_per_group, int cols) {
   const long ge = static_cast<long>(rows_per_group) * cols;
   return static_cast<size_t>(n_groups) * (1 + (ge + kSeg - 1) / kSeg);
@@ -533,11 +642,13 @@ int wn_grad(const float* dw, const float* v, const float* g, const float* sumsq,
 
 int act_bwd_bias(const void* dy, int dy_is_bf16, const __nv_bfloat16* y, __nv_bfloat16* dz, float* dbias, long rows,
                  int cols, cudaStream_t s) {
-  CTI_REQUIRE(rows > 0 && cols > 0 && (cols % 2) == 0, "act_bwd_bias: bad shape rows=%ld cols=%d (cols must be even)", rows,
-              cols);
-  const int gx = (cols / 2 + 255) / 256;
+  CTI_REQUIRE(rows > 0 && cols > 0 && (cols % 8) == 0, "act_bwd_bias: bad shape rows=%ld cols=%d (cols must be a multiple of 8)",
+              rows, cols);
+  CTI_REQUIRE(((uintptr_t)dy & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)dz & 15) == 0,
+              "act_bwd_bias: buffers must be 16-byte aligned");
+  const int gx = (cols + kAbbLanes * 8 - 1) / (kAbbLanes * 8);
   long rpb = (rows * gx + 4 * kNumSMsB200 - 1) / (4 * kNumSMsB200);       // ~4 waves of blocks
-  rpb = rpb < 32 ? 32 : (rpb > 512 ? 512 : rpb);
+  rpb = rpb < 32 ? 32 : (rpb > 1024 ? 1024 : rpb);
   dim3 grid(gx, (unsigned)((rows + rpb - 1) / rpb));
   if (dy_is_bf16) launch_pdl(act_bwd_bias_kernel<true>, dim3(grid), dim3(256), 0, s, dy, y, dz, dbias, rows, cols, (int)rpb);
   else            launch_pdl(act_bwd_bias_kernel<false>, dim3(grid), dim3(256), 0, s, dy, y, dz, dbias, rows, cols, (int)rpb);

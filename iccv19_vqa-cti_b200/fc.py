@@ -33,16 +33,30 @@ class WNLinear(nn.Module):
         self.weight_g = nn.Parameter(v.norm().detach().clone())          # scalar, shape ()
         self.weight_v = nn.Parameter(v)
         self._pack: Optional[Tuple[tuple, F_.Packed]] = None
+        self._vproxy = None         # (key, proxy of weight_v) while prepack defers this layer's weight-norm backward
 
     def extra_repr(self) -> str:
         return f"in_features={self.in_features}, out_features={self.out_features}, bias=True"
+
+    def v_in(self) -> torch.Tensor:
+        """What the autograd functions take as this layer's ``weight_v``: the parameter itself, or -- after
+        ``prepack`` with gradients enabled -- its proxy, an alias that carries dW_eff back to prepack's backward."""
+        d = self._vproxy
+        if d is not None and torch.is_grad_enabled() and d[0] == (self.weight_v._version, self.weight_g._version,
+                                                                   self.weight_v.data_ptr()):
+            return d[1]
+        return self.weight_v
 
     def packed(self) -> F_.Packed:
         """bf16 W_eff, cached until weight_v / weight_g change (in-place updates bump ``_version``)."""
         key = (self.weight_v._version, self.weight_g._version, self.weight_v.data_ptr())
         if self._pack is None or self._pack[0] != key:
             self._pack = (key, F_.pack_layer(self.weight_v, self.weight_g, 1))
-        return self._pack[1]
+            self._vproxy = None
+        pk = self._pack[1]
+        if pk.dw is not None and (self._vproxy is None or self._vproxy[0] != key or not torch.is_grad_enabled()):
+            return F_.Packed(pk.w, pk.sumsq)         # no live proxy: the layer does its own weight-norm backward
+        return pk
 
 
 def features_f32_2d(v: torch.Tensor) -> torch.Tensor:
@@ -75,7 +89,7 @@ class FCNet(nn.Module):
         for p, idx, act in self._plan:
             lin = self.main[idx]
             fused = act in ('', 'ReLU')
-            y = F_.WNLinearFn.apply(y, lin.weight_v, lin.weight_g, lin.bias, act == 'ReLU', lin.packed(),
+            y = F_.WNLinearFn.apply(y, lin.v_in(), lin.weight_g, lin.bias, act == 'ReLU', lin.packed(),
                                     F_.new_drop(p, self.training))
             if not fused:                                 # activations other than ReLU are not on the CTI path
                 y = self.main[idx + 1](y)

@@ -21,12 +21,16 @@ F32 = torch.float32
 # one weight-normed linear layer group (reference src/fc.py:22-29): helpers, not autograd
 # --------------------------------------------------------------------------- #
 class Packed:
-    """bf16 effective weight W_eff = V g/||V|| of one layer group and the squared norms."""
-    __slots__ = ("w", "sumsq")
+    """bf16 effective weight W_eff = V g/||V|| of one layer group and the squared norms.
+    ``dw`` is set by ``prepack`` when the layer's weight-norm backward is DEFERRED: the layer's backward then writes
+    dW_eff into that persistent buffer and hands it to the proxy of ``weight_v`` instead of computing dV / dg itself --
+    one multi-tensor launch (``cti_wn_grad_multi``) finishes every layer of the model at the end of the backward pass."""
+    __slots__ = ("w", "sumsq", "dw")
 
-    def __init__(self, w: torch.Tensor, sumsq: torch.Tensor):
+    def __init__(self, w: torch.Tensor, sumsq: torch.Tensor, dw: Optional[torch.Tensor] = None):
         self.w = w
         self.sumsq = sumsq
+        self.dw = dw
 
 
 def pack_layer(V: torch.Tensor, g: torch.Tensor, n_groups: int) -> Packed:
@@ -144,18 +148,25 @@ def lin_bwd(x: torch.Tensor, dz: torch.Tensor, V: torch.Tensor, g: torch.Tensor,
     tile_n = 256 if Kin >= 256 else 128
     tiles = -(-N // 128) * -(-Kin // tile_n)
     splits = _pick_splits(tiles, -(-M // 64))
-    if dw is None:
+    deferred = pk.dw is not None
+    if deferred:
+        dw = pk.dw                                   # persistent, zeroed by prepack at the top of the step
+    elif dw is None:
         dw = torch.zeros((N, Kin), dtype=F32, device=x.device)
     K_.gemm(dz, x, N, Kin, M, a_mn=True, b_mn=True, accum_f32=dw, k_splits=splits, tile_n=tile_n, alpha=alpha)
-    dV, dg = K_.wn_grad(dw[:V.shape[0]], V.detach().contiguous(), g.detach().reshape(n_groups).contiguous(), pk.sumsq,
-                        n_groups)
+    if deferred:                                     # dW_eff goes to the proxy of weight_v; dV / dg come from prepack's backward
+        dV, dg = dw[:V.shape[0]], None
+    else:
+        dV, dg = K_.wn_grad(dw[:V.shape[0]], V.detach().contiguous(), g.detach().reshape(n_groups).contiguous(), pk.sumsq,
+                            n_groups)
+        dg = dg.reshape(g.shape)
     dx = None
     if need_dx:
         # dgrad: dx[M, K_in] = dz W_eff  (W_eff stored [N][K_in] = MN-major B operand)
         ob, of = K_.gemm(dz, pk.w, M, Kin, N, b_mn=True, relu_aux=dx_relu_aux, out_bf16=not dx_f32, out_f32=dx_f32,
                          alpha=dx_alpha)
         dx = of if dx_f32 else ob
-    return dV, dg.reshape(g.shape), dx
+    return dV, dg, dx
 
 
 # --------------------------------------------------------------------------- #
@@ -210,6 +221,9 @@ def rank_proj_bwd(y: torch.Tensor, dz: torch.Tensor, V: torch.Tensor, g: torch.T
             dw[(gi * rg + j) * d:(gi * rg + j + 1) * d] = dwt[j * d:(j + 1) * d, j * H:(j + 1) * H]
         dxt, _ = K_.gemm(dzg, wt[gi], M, rg * H, rg * d, b_mn=True)
         K_.dropout_reduce_(dxt, acc, rg, gi * rg, drop)
+    if pk.dw is not None:                            # deferred weight-norm backward (see Packed)
+        pk.dw.copy_(dw)
+        return pk.dw, None, acc
     dV, dg = K_.wn_grad(dw, V.detach().contiguous(), g.detach().reshape(R).contiguous(), pk.sumsq, R)
     return dV, dg.reshape(g.shape), acc
 
@@ -356,7 +370,15 @@ class TriLogitsFn(Function):
 
         # every split-K accumulator and bias-gradient sum of this call: one allocation, one fill kernel
         RD = R * 16
-        zs = zero_slab(yv.device, [(RD, H)] * 3 + [(H,)] * 3 + [(H, v_bf16.shape[1]), (H, xq.shape[1]), (H, xa.shape[1])])
+        # (deferred layers accumulate dW_eff in prepack's persistent buffers: only the bias sums need zeroes then)
+        dw_shapes = [(RD, H)] * 3 + [(H, v_bf16.shape[1]), (H, xq.shape[1]), (H, xa.shape[1])]
+        dw_pk = [pk[3], pk[4], pk[5], pk[0], pk[1], pk[2]]
+        need = [i for i in range(6) if dw_pk[i].dw is None]
+        slab = zero_slab(yv.device, [(H,)] * 3 + [dw_shapes[i] for i in need])
+        zs = [None] * 9
+        zs[3:6] = slab[:3]
+        for j, i in enumerate(need):
+            zs[i if i < 3 else i + 3] = slab[3 + j]
 
         def rank_nets_bwd(y, dz, V, g, pki, drop, dw_, db_):
             """-> dV, dg, pre-activation gradient of the tucker layer (bf16) and its bias gradient"""
@@ -490,7 +512,12 @@ class PoolFn(Function):
         pk = ctx.pk
         dzv, dzq, dza, dbv, dbq, dba, dw = K_.tri_pool_bwd(vp, qp, ap, wd, wd.stride(0), dout.contiguous(), B, K, Q, A,
                                                           C, ctx.vr)
-        zs = zero_slab(vp.device, [(C, v_bf16.shape[1]), (C, xq.shape[1])] + ([(C, xa.shape[1])] if A > 0 else []))
+        shapes = [(C, v_bf16.shape[1]), (C, xq.shape[1])] + ([(C, xa.shape[1])] if A > 0 else [])
+        need = [i for i in range(len(shapes)) if pk[i].dw is None]
+        slab = zero_slab(vp.device, [shapes[i] for i in need]) if need else []
+        zs = [None] * 3
+        for j, i in enumerate(need):
+            zs[i] = slab[j]
         dVv, dgv, _ = lin_bwd(v_bf16, dzv, w[0], w[1], pk[0], 1, False, dw=zs[0])
         dVq, dgq, dq = lin_bwd(xq, dzq, w[3], w[4], pk[1], 1, ctx.need[0], dx_f32=True, dw=zs[1])
         grads = [dVv, dgv, dbv, dVq, dgq, dbq]

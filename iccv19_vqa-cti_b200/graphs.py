@@ -25,8 +25,11 @@ def reset_caches(modules: Iterable[torch.nn.Module], tensors: Iterable[torch.Ten
         for m in root.modules():
             if hasattr(m, "_pack"):
                 m._pack = None
+            if hasattr(m, "_vproxy"):
+                m._vproxy = None
             if hasattr(m, "_rank_pack"):
                 m._rank_pack = None
+                m.__dict__["_rank_proxy"] = None
     for t in tensors:
         for attr in (_fc._FEAT_ATTR, "_cti_b200_tok"):
             if hasattr(t, attr):

@@ -49,80 +49,231 @@ class _Plan:
         if dev.type != "cuda":
             raise RuntimeError("prepack: the modules must live on a CUDA device (no CPU path)")
         self.device = dev
-        v_ptrs, g_ptrs, w_ptrs, s_ptrs, elems = [], [], [], [], []
-        self.single_packs, self.rank_packs = [], []
+        f32, bf16 = torch.float32, torch.bfloat16
+
+        # ---- one entry per weight-normed Linear (a per-rank net is an entry that writes into its group's stacked pack)
+        ent_v, ent_g, elems = [], [], []
+        dw_elems = []                        # size of each persistent dW_eff buffer (one per single layer / per rank GROUP)
         for lin in self.singles:
             n, k = lin.weight_v.shape
-            w = torch.zeros((-(-n // 8) * 8, k), dtype=torch.bfloat16, device=dev)      # zero rows pad odd widths
-            ss = torch.zeros((1,), dtype=torch.float32, device=dev)
-            self.single_packs.append(F_.Packed(w, ss))
-            v_ptrs.append(lin.weight_v.data_ptr()); g_ptrs.append(lin.weight_g.data_ptr())
-            w_ptrs.append(w.data_ptr()); s_ptrs.append(ss.data_ptr()); elems.append(n * k)
+            ent_v.append(lin.weight_v); ent_g.append(lin.weight_g); elems.append(n * k)
+            dw_elems.append((-(-n // 8) * 8) * k)
+        self.group_lins = []                 # [tcnet][3] -> list of the R WNLinears
         for tc in self.tcnets:
-            packs = []
+            per_tc = []
             for nets in (tc.v_net, tc.q_net, tc.a_net):
                 lins = [n.single()[0] for n in nets]
+                per_tc.append(lins)
                 d, h = lins[0].weight_v.shape
-                w = torch.zeros((len(lins) * d, h), dtype=torch.bfloat16, device=dev)
-                ss = torch.zeros((len(lins),), dtype=torch.float32, device=dev)
-                packs.append(F_.Packed(w, ss))
-                for r, lin in enumerate(lins):
-                    v_ptrs.append(lin.weight_v.data_ptr()); g_ptrs.append(lin.weight_g.data_ptr())
-                    w_ptrs.append(w.data_ptr() + 2 * r * d * h); s_ptrs.append(ss.data_ptr() + 4 * r)
-                    elems.append(d * h)
-            self.rank_packs.append(packs)
+                for lin in lins:
+                    ent_v.append(lin.weight_v); ent_g.append(lin.weight_g); elems.append(d * h)
+                dw_elems.append(len(lins) * d * h)
+            self.group_lins.append(per_tc)
         if any(e % 4 for e in elems):
             raise RuntimeError("prepack: every layer must have a multiple of 4 elements")
+        self.ent_v, self.ent_g, self.elems = ent_v, ent_g, elems
+        self.n_entries = len(elems)
+
+        # ---- persistent buffers: bf16 packs, squared norms, dW_eff accumulators (zeroed at the top of every step)
+        self.dw_slab = torch.zeros(sum(-(-e // 4) * 4 for e in dw_elems), dtype=f32, device=dev)
+        self.sumsq = torch.zeros(self.n_entries, dtype=f32, device=dev)
+        self.single_packs, self.rank_packs = [], []
+        self.rank_bias, self.rank_vproxy = [], []
+        w_ptrs, s_ptrs, dw_ptrs = [], [], []
+        o, e = 0, 0
+        for lin in self.singles:
+            n, k = lin.weight_v.shape
+            npad = -(-n // 8) * 8
+            w = torch.zeros((npad, k), dtype=bf16, device=dev)                           # zero rows pad odd widths
+            dw = self.dw_slab[o:o + npad * k].view(npad, k)
+            self.single_packs.append(F_.Packed(w, self.sumsq[e:e + 1], dw))
+            w_ptrs.append(w.data_ptr()); s_ptrs.append(self.sumsq.data_ptr() + 4 * e); dw_ptrs.append(dw.data_ptr())
+            o += -(-npad * k // 4) * 4
+            e += 1
+        for per_tc in self.group_lins:
+            packs, biases, vps = [], [], []
+            for lins in per_tc:
+                R = len(lins)
+                d, h = lins[0].weight_v.shape
+                w = torch.zeros((R * d, h), dtype=bf16, device=dev)
+                dw = self.dw_slab[o:o + R * d * h].view(R * d, h)
+                packs.append(F_.Packed(w, self.sumsq[e:e + R], dw))
+                biases.append(torch.zeros(R * d, dtype=f32, device=dev))
+                vps.append(torch.empty((R * d, h), dtype=f32, device=dev))                # gradient carrier only: never read
+                for r in range(R):
+                    w_ptrs.append(w.data_ptr() + 2 * r * d * h); s_ptrs.append(self.sumsq.data_ptr() + 4 * (e + r))
+                    dw_ptrs.append(dw.data_ptr() + 4 * r * d * h)
+                o += R * d * h
+                e += R
+            self.rank_packs.append(packs)
+            self.rank_bias.append(biases)
+            self.rank_vproxy.append(vps)
+
         first_seg, n_seg, seg_entry, seg_index, blk_entry, blk_index = [], [], [], [], [], []
-        for e, n in enumerate(elems):
+        for ei, n in enumerate(elems):
             first_seg.append(len(seg_entry))
             ns = -(-n // _SEG)
             n_seg.append(ns)
-            seg_entry += [e] * ns
+            seg_entry += [ei] * ns
             seg_index += list(range(ns))
             nb = -(-n // _BLK)
-            blk_entry += [e] * nb
+            blk_entry += [ei] * nb
             blk_index += list(range(nb))
         i64 = lambda xs: torch.tensor(xs, dtype=torch.int64, device=dev)
         i32 = lambda xs: torch.tensor(xs, dtype=torch.int32, device=dev)
-        self.tables = (i64(v_ptrs), i64(g_ptrs), i64(w_ptrs), i64(s_ptrs), i64(elems), i32(first_seg), i32(n_seg),
-                       i32(seg_entry), i32(seg_index), i32(blk_entry), i32(blk_index))
+        self.tables = (i64([t.data_ptr() for t in ent_v]), i64([t.data_ptr() for t in ent_g]), i64(w_ptrs), i64(s_ptrs),
+                       i64(elems), i32(first_seg), i32(n_seg), i32(seg_entry), i32(seg_index), i32(blk_entry), i32(blk_index))
+        self.dw_ptrs = i64(dw_ptrs)
+        # dV / dg of one backward pass live in two fresh flat buffers: their pointer tables are offsets + base
+        offs, oo = [], 0
+        for n in elems:
+            offs.append(oo)
+            oo += n
+        self.total = oo
+        self.dv_off = i64([4 * x for x in offs])
+        self.dg_off = i64([4 * x for x in range(self.n_entries)])
+        self.dv_ptrs = torch.zeros(self.n_entries, dtype=torch.int64, device=dev)
+        self.dg_ptrs = torch.zeros(self.n_entries, dtype=torch.int64, device=dev)
+        self.dv_offs_host = offs
         self.n_segs, self.n_blks = len(seg_entry), len(blk_entry)
-        self.partials = torch.empty((self.n_segs,), dtype=torch.float32, device=dev)
-        self.total = sum(elems)
-        self.ptr_key = tuple(v_ptrs)
+        self.partials = torch.empty((self.n_segs,), dtype=f32, device=dev)
+        self.ptr_key = tuple(t.data_ptr() for t in ent_v)
+        # flat argument list of the autograd node: [V, g] per entry, then the biases of the per-rank nets
+        self.fn_inputs = [t for pair in zip(ent_v, ent_g) for t in pair]
+        self.rank_bias_params = [[[lin.bias for lin in lins] for lins in per_tc] for per_tc in self.group_lins]
+        self.fn_inputs += [b for per_tc in self.rank_bias_params for grp in per_tc for b in grp]
 
     def still_valid(self) -> bool:                       # parameters re-allocated (.to(), load with assign) -> rebuild
-        ptrs = [lin.weight_v.data_ptr() for lin in self.singles]
-        for tc in self.tcnets:
-            for nets in (tc.v_net, tc.q_net, tc.a_net):
-                ptrs += [n.single()[0].weight_v.data_ptr() for n in nets]
-        return tuple(ptrs) == self.ptr_key
+        return tuple(t.data_ptr() for t in self.ent_v) == self.ptr_key
 
-    def run(self) -> None:
+    # ------------------------------------------------------------------ #
+    def pack(self) -> None:
+        """The forward fold of every entry: two launches."""
         t = self.tables
         K_._call("cti_wn_pack_multi", _lib.load().cti_wn_pack_multi,
                  (t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), t[4].data_ptr(), t[5].data_ptr(),
                   t[6].data_ptr(), t[7].data_ptr(), t[8].data_ptr(), self.n_segs, t[9].data_ptr(), t[10].data_ptr(),
                   self.n_blks, self.partials.data_ptr(), K_._stream()), kernels=2, nbytes=10.0 * self.total)
-        for lin, pk in zip(self.singles, self.single_packs):
-            lin._pack = ((lin.weight_v._version, lin.weight_g._version, lin.weight_v.data_ptr()), pk)
-        for tc, packs in zip(self.tcnets, self.rank_packs):
+
+    def grad(self, flat_dv: torch.Tensor, flat_dg: torch.Tensor) -> None:
+        """The backward of the fold for every entry: two launches, dW_eff read from the persistent accumulators."""
+        torch.add(self.dv_off, flat_dv.data_ptr(), out=self.dv_ptrs)
+        torch.add(self.dg_off, flat_dg.data_ptr(), out=self.dg_ptrs)
+        t = self.tables
+        K_._call("cti_wn_grad_multi", _lib.load().cti_wn_grad_multi,
+                 (self.dw_ptrs.data_ptr(), t[0].data_ptr(), t[1].data_ptr(), t[3].data_ptr(), self.dv_ptrs.data_ptr(),
+                  self.dg_ptrs.data_ptr(), t[4].data_ptr(), t[5].data_ptr(), t[6].data_ptr(), t[7].data_ptr(), t[8].data_ptr(),
+                  self.n_segs, t[9].data_ptr(), t[10].data_ptr(), self.n_blks, self.partials.data_ptr(), K_._stream()),
+                 kernels=2, nbytes=20.0 * self.total)
+
+    def prime(self, proxies) -> None:
+        """Point the layers' caches at the fresh packs (and, when ``proxies`` is given, at the proxies that defer their
+        weight-norm backward)."""
+        n_single = len(self.singles)
+        for i, (lin, pk) in enumerate(zip(self.singles, self.single_packs)):
+            key = (lin.weight_v._version, lin.weight_g._version, lin.weight_v.data_ptr())
+            lin._pack = (key, pk)
+            lin._vproxy = None if proxies is None else (key, proxies[i])
+        for ti, (tc, packs) in enumerate(zip(self.tcnets, self.rank_packs)):
             rank_params = tc.__dict__.get("_rank_params")
             if rank_params is None:
                 rank_params = [p for nets in (tc.v_net, tc.q_net, tc.a_net) for p in nets.parameters()]
                 tc.__dict__["_rank_params"] = rank_params
             key = tuple(p._version for p in rank_params) + (rank_params[0].data_ptr(),)
             tc._rank_pack = (key, list(packs), None)       # the stacked fp32 copies are rebuilt on demand (tc.py)
+            if proxies is None:
+                tc.__dict__["_rank_proxy"] = None
+            else:
+                base = n_single + 6 * ti
+                g_standin = self.sumsq[:1]                 # never read: dg comes from the deferred backward
+                tc.__dict__["_rank_proxy"] = (key, [(proxies[base + 2 * j], g_standin, proxies[base + 2 * j + 1])
+                                                    for j in range(3)])
+
+
+class _PackAllFn(torch.autograd.Function):
+    """One autograd node for the weight-norm re-parametrisation of EVERY layer of a model (reference src/fc.py:22,27:
+    ``weight_norm(nn.Linear(...), dim=None)``).  forward: the two-launch fold into the bf16 packs; outputs are proxies --
+    an alias of each single layer's ``weight_v``, and per group of R per-rank nets a stacked ``weight_v`` stand-in and the
+    stacked bias.  The layers' autograd functions take the proxies in place of the parameters and return dW_eff / dbias for
+    them; autograd calls backward here once every layer has done so: two launches produce all dV / dg."""
+
+    @staticmethod
+    def forward(ctx, plan, *params):
+        plan.dw_slab.zero_()
+        plan.pack()
+        outs = [lin.weight_v.detach() for lin in plan.singles]
+        with torch.no_grad():
+            for per_tc, vps, biases in zip(plan.rank_bias_params, plan.rank_vproxy, plan.rank_bias):
+                for grp, vp, bstack in zip(per_tc, vps, biases):
+                    torch.cat([b.detach() for b in grp], 0, out=bstack)
+                    outs += [vp.detach(), bstack.detach()]
+        ctx.plan = plan
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        plan = ctx.plan
+        dev = plan.device
+        n_single = len(plan.singles)
+        used = [False] * plan.n_entries
+        # incoming dW_eff normally IS the persistent accumulator (the layer wrote into it); anything else (a layer used
+        # twice, so autograd summed two gradients) is copied in
+        e = 0
+        for i, pk in enumerate(plan.single_packs):
+            g_ = grads[i]
+            if g_ is not None:
+                n = plan.singles[i].weight_v.shape[0]
+                if g_.data_ptr() != pk.dw.data_ptr():
+                    pk.dw[:n].copy_(g_)
+                used[e] = True
+            e += 1
+        gi = n_single
+        for packs in plan.rank_packs:
+            for pk in packs:
+                g_ = grads[gi]
+                R = pk.sumsq.numel()
+                if g_ is not None:
+                    if g_.data_ptr() != pk.dw.data_ptr():
+                        pk.dw.copy_(g_)
+                    for r in range(R):
+                        used[e + r] = True
+                e += R
+                gi += 2
+        flat_dv = torch.empty(plan.total, dtype=torch.float32, device=dev)
+        flat_dg = torch.empty(plan.n_entries, dtype=torch.float32, device=dev)
+        plan.grad(flat_dv, flat_dg)
+        out = [None]
+        for ei, (v, off) in enumerate(zip(plan.ent_v, plan.dv_offs_host)):
+            if used[ei]:
+                out += [flat_dv[off:off + v.numel()].view_as(v), flat_dg[ei]]
+            else:
+                out += [None, None]
+        gi = n_single
+        for per_tc in plan.rank_bias_params:
+            for grp in per_tc:
+                db = grads[gi + 1]
+                d = grp[0].numel()
+                out += [None if db is None else db[r * d:(r + 1) * d] for r in range(len(grp))]
+                gi += 2
+        return tuple(out)
 
 
 def prepack(modules) -> None:
     """Rebuild the bf16 weight packs of every weight-normed layer under ``modules`` (a module or an iterable of
     modules) in two launches and prime the layers' caches.  The packs live in persistent buffers: call it between the
-    backward pass of one step and the forward pass of the next, never in between."""
+    backward pass of one step and the forward pass of the next, never in between.
+
+    With gradients enabled the call also DEFERS the weight-norm backward of those layers: they hand dW_eff to proxies
+    of their parameters and one multi-tensor launch pair computes every dV / dg at the end of the backward pass
+    (``_PackAllFn``) -- instead of two launches per layer and, for the 3 x R per-rank nets of a TCNet, a torch.cat of 96
+    tensors in forward and its 96-way split in backward."""
     roots = [modules] if isinstance(modules, nn.Module) else list(modules)
     key = tuple(id(m) for m in roots)
     plan = _PLANS.get(key)
     if plan is None or not plan.still_valid():
         plan = _PLANS[key] = _Plan(roots)
-    plan.run()
+    if torch.is_grad_enabled() and any(t.requires_grad for t in plan.fn_inputs):
+        plan.prime(_PackAllFn.apply(plan, *plan.fn_inputs))
+    else:
+        plan.pack()
+        plan.prime(None)

@@ -106,25 +106,31 @@ class TCNet(nn.Module):
             rank_params = [p for nets in (self.v_net, self.q_net, self.a_net) for p in nets.parameters()]
             self.__dict__["_rank_params"] = rank_params
         key = tuple(p._version for p in rank_params) + (rank_params[0].data_ptr(),)
-        cache = self._rank_pack
-        if cache is not None and cache[0] == key and cache[2] is not None and not torch.is_grad_enabled():
-            (Vvn, gvn, bvn), (Vqn, gqn, bqn), (Van, gan, ban) = cache[2]
+        cache = self._rank_pack                      # (key, [Packed] * 3, detached stacks or None)
+        proxy = self.__dict__.get("_rank_proxy")     # (key, [(V proxy, g stand-in, bias proxy)] * 3): set by prepack
+        if (proxy is not None and proxy[0] == key and cache is not None and cache[0] == key
+                and torch.is_grad_enabled()):
+            # prepack deferred the weight-norm backward of the 3 x R per-rank nets: the stacked proxies stand for the 96
+            # weight_v / bias parameters (no torch.cat of 96 tensors here, no 96-way split in backward)
+            groups = proxy[1]
+            rank_packs = cache[1]
         else:
-            Vvn, gvn, bvn = self._rank_group(self.v_net)
-            Vqn, gqn, bqn = self._rank_group(self.q_net)
-            Van, gan, ban = self._rank_group(self.a_net)
-            if cache is not None and cache[0] == key and cache[2] is None:      # packs came from prepack(): add the stacks
-                stacks = [tuple(t.detach() for t in grp) for grp in ((Vvn, gvn, bvn), (Vqn, gqn, bqn), (Van, gan, ban))]
-                cache = self._rank_pack = (key, cache[1], stacks)
-        if cache is None or cache[0] != key:
-            stacks = [tuple(t.detach() for t in grp) for grp in ((Vvn, gvn, bvn), (Vqn, gqn, bqn), (Van, gan, ban))]
-            cache = self._rank_pack = (key, [F_.pack_layer(Vvn, gvn, self.rank), F_.pack_layer(Vqn, gqn, self.rank),
-                                             F_.pack_layer(Van, gan, self.rank)], stacks)
-        packs = [lv.packed(), lq.packed(), la.packed()] + cache[1]
+            if cache is not None and cache[0] == key and cache[2] is not None and not torch.is_grad_enabled():
+                groups = cache[2]
+            else:
+                groups = [self._rank_group(nets) for nets in (self.v_net, self.q_net, self.a_net)]
+            if cache is None or cache[0] != key:
+                cache = self._rank_pack = (key, [F_.pack_layer(V, g, self.rank) for V, g, _ in groups],
+                                           [tuple(t.detach() for t in grp) for grp in groups])
+            elif cache[2] is None:                   # packs came from prepack(): add the stacks
+                cache = self._rank_pack = (key, cache[1], [tuple(t.detach() for t in grp) for grp in groups])
+            rank_packs = [F_.Packed(pk.w, pk.sumsq) for pk in cache[1]]       # this path does its own weight-norm backward
+        (Vvn, gvn, bvn), (Vqn, gqn, bqn), (Van, gan, ban) = groups
+        packs = [lv.packed(), lq.packed(), la.packed()] + rank_packs
         dims = (B, K, Q, A, G, self.rank)
         return F_.TriLogitsFn.apply(dims, packs, drops, v_bf16, rowmask if rowmask_wanted else None, q, a, self.T_g,
-                                    lv.weight_v, lv.weight_g, lv.bias, lq.weight_v, lq.weight_g, lq.bias,
-                                    la.weight_v, la.weight_g, la.bias, Vvn, gvn, bvn, Vqn, gqn, bqn, Van, gan, ban)
+                                    lv.v_in(), lv.weight_g, lv.bias, lq.v_in(), lq.weight_g, lq.bias,
+                                    la.v_in(), la.weight_g, la.bias, Vvn, gvn, bvn, Vqn, gqn, bqn, Van, gan, ban)
 
     def forward(self, v, q, a):
         """v (B,K,v_dim), q (B,Q,q_dim), a (B,A,a_dim) -> trilinear logit map (B,K,Q,A,G).
@@ -146,5 +152,5 @@ class TCNet(nn.Module):
                 drops = (features_f32_2d(v) if sites[0] is not None else None, *sites)
         packs = [lv.packed(), lq.packed(), la.packed()]
         dims = (B, K, Q, A, self.h_dim)
-        return F_.PoolFn.apply(dims, packs, drops, v_bf16, q, a, w, lv.weight_v, lv.weight_g, lv.bias, lq.weight_v,
-                               lq.weight_g, lq.bias, la.weight_v, la.weight_g, la.bias)
+        return F_.PoolFn.apply(dims, packs, drops, v_bf16, q, a, w, lv.v_in(), lv.weight_g, lv.bias, lq.v_in(),
+                               lq.weight_g, lq.bias, la.v_in(), la.weight_g, la.bias)

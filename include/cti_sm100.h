@@ -77,6 +77,14 @@ int cti_wn_pack_multi(const void* v_ptrs_dev, const void* g_ptrs_dev, const void
                       const int64_t* elems_dev, const int32_t* first_seg_dev, const int32_t* n_seg_dev,
                       const int32_t* seg_entry_dev, const int32_t* seg_index_dev, int n_segs, const int32_t* blk_entry_dev,
                       const int32_t* blk_index_dev, int n_blks, float* partials, void* stream);
+/* The backward of the same fold for every entry in two launches: dv[e] = (g/||V||) (dW - <dW,V> V / ||V||^2),
+ * dg[e] = <dW,V> / ||V||, with ||V||^2 as left in sumsq[e] by cti_wn_pack_multi.  Tables as above plus dw / dv / dg
+ * pointer tables; same arithmetic and summation order as cti_wn_grad (bit-identical results).
+ * replaces: autograd through torch's weight_norm re-parametrisation (src/fc.py:22,27), all layers of a model at once. */
+int cti_wn_grad_multi(const void* dw_ptrs_dev, const void* v_ptrs_dev, const void* g_ptrs_dev, const void* sumsq_ptrs_dev,
+                      const void* dv_ptrs_dev, const void* dg_ptrs_dev, const int64_t* elems_dev, const int32_t* first_seg_dev,
+                      const int32_t* n_seg_dev, const int32_t* seg_entry_dev, const int32_t* seg_index_dev, int n_segs,
+                      const int32_t* blk_entry_dev, const int32_t* blk_index_dev, int n_blks, float* partials, void* stream);
 int cti_wn_pack(const float* v, const float* g, void* w_eff_bf16, float* sumsq, int n_groups, int rows_per_group,
                 int cols, void* stream);
 /* Backward of the fold: given dW_eff (fp32) returns dV and dg.  dot_ws: cti_wn_scratch_floats() floats of scratch;
