@@ -222,6 +222,9 @@ def run_b200(args):
     mods = torch.nn.ModuleList([att, *pools, *q_prj, *a_prj]).to(dev).eval()
     params = [p for p in mods.parameters()]
     reducer = GradAllReducer(params) if world > 1 else None
+    if reducer is not None:
+        # the deferred weight-norm backward writes dV / dg (97 % of the gradient bytes) straight into the all-reduce slab
+        cti_b200.bind_grad_buffers(mods, reducer)
 
     # multiple-choice batch: B rows = B / 4 questions x 4 answer candidates; the loader yields ONE feature tensor per
     # question and the trainer clones it per candidate on the device (reference src/MC/train.py:69-76)

@@ -18,10 +18,10 @@ from .graphs import GraphedStep, reset_caches
 from .language_model import QuestionEmbedding
 from .loss_function import Distillation_Loss
 from .optim import FusedClipAdamax
-from .prepack import prepack
+from .prepack import bind_grad_buffers, prepack
 from .tc import TCNet
 
-__all__ = ["FCNet", "WNLinear", "TCNet", "TriAttention", "BCNet", "BiAttention", "SimpleClassifier", "QuestionEmbedding", "Distillation_Loss", "FusedClipAdamax", "prepack", "install", "uninstall", "GraphedStep", "reset_caches",
+__all__ = ["FCNet", "WNLinear", "TCNet", "TriAttention", "BCNet", "BiAttention", "SimpleClassifier", "QuestionEmbedding", "Distillation_Loss", "FusedClipAdamax", "prepack", "bind_grad_buffers", "install", "uninstall", "GraphedStep", "reset_caches",
            "library_path", "version"]
 
 

@@ -190,6 +190,34 @@ __global__ void __launch_bounds__(256) dropout_reduce_kernel(const __nv_bfloat16
 // matrix; each group has its own scalar g and Frobenius norm (one group = one nn.Linear).
 constexpr int kSeg = 4096;   // elements reduced by one block
 
+// sum_{i in [lo, hi)} a[i] * b[i] of one thread of a 256-thread block, 16-byte loads (lo, hi and the bases are multiples
+// of 4 elements: every group has a multiple of 4 elements).  One fixed order for the per-layer and the multi-tensor
+// kernels: the same weights give the same sums bit for bit.
+__device__ __forceinline__ float seg_dot(const float* __restrict__ a, const float* __restrict__ b, long lo, long hi) {
+  float s = 0.f;
+  for (long i = lo + 4 * threadIdx.x; i < hi; i += 4 * 256) {
+    const float4 x = *reinterpret_cast<const float4*>(a + i);
+    const float4 y = *reinterpret_cast<const float4*>(b + i);
+    s = __fmaf_rn(x.x, y.x, s);          // explicit fma chain: the same rounding in every instantiation
+    s = __fmaf_rn(x.y, y.y, s);
+    s = __fmaf_rn(x.z, y.z, s);
+    s = __fmaf_rn(x.w, y.w, s);
+  }
+  return s;
+}
+
+__device__ __forceinline__ void seg_reduce_store(float s, float* __restrict__ partial) {
+  s = warp_sum(s);
+  __shared__ float part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < 8 ? part[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+  }
+}
+
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ v, const float* __restrict__ w2,
                                                     float* __restrict__ partial, long group_elems, int segs_per_group) {
   pdl_prologue_done();
@@ -200,17 +228,8 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ v,
   const long base = static_cast<long>(group) * group_elems;
   const long lo = static_cast<long>(seg) * kSeg;
   const long hi = min(lo + kSeg, group_elems);
-  float s = 0.f;
-  for (long i = lo + threadIdx.x; i < hi; i += blockDim.x) s += v[base + i] * w2[base + i];
-  s = warp_sum(s);
-  __shared__ float part[8];
-  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    float t = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
-    t = warp_sum(t);
-    if (threadIdx.x == 0) partial[blockIdx.x] = t;
-  }
+  const float s = seg_dot(v + base, w2 + base, lo, hi);
+  seg_reduce_store(s, partial);
 }
 
 // Total of one group's segment partials, computed redundantly (and identically) by every consumer block instead of
@@ -379,17 +398,7 @@ __global__ void __launch_bounds__(256) wn_multi_sumsq_kernel(const WnMultiTable 
   const float* v = t.v[e];
   const long lo = static_cast<long>(seg_index[blockIdx.x]) * kSeg;
   const long hi = min(lo + kSeg, t.elems[e]);
-  float s = 0.f;
-  for (long i = lo + threadIdx.x; i < hi; i += blockDim.x) s += v[i] * v[i];
-  s = warp_sum(s);
-  __shared__ float part[8];
-  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    float x = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
-    x = warp_sum(x);
-    if (threadIdx.x == 0) partial[blockIdx.x] = x;
-  }
+  seg_reduce_store(seg_dot(v, v, lo, hi), partial);
 }
 
 __global__ void __launch_bounds__(256) wn_multi_scale_kernel(const WnMultiTable t, const int* __restrict__ blk_entry,
@@ -432,17 +441,7 @@ __global__ void __launch_bounds__(256) wn_multi_dot_kernel(const WnGradMultiTabl
   const float* dw = t.dw[e];
   const long lo = static_cast<long>(seg_index[blockIdx.x]) * kSeg;
   const long hi = min(lo + kSeg, t.elems[e]);
-  float s = 0.f;
-  for (long i = lo + threadIdx.x; i < hi; i += blockDim.x) s += dw[i] * v[i];
-  s = warp_sum(s);
-  __shared__ float part[8];
-  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    float x = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
-    x = warp_sum(x);
-    if (threadIdx.x == 0) partial[blockIdx.x] = x;
-  }
+  seg_reduce_store(seg_dot(dw, v, lo, hi), partial);
 }
 
 __global__ void __launch_bounds__(256) wn_multi_grad_kernel(const WnGradMultiTable t, const int* __restrict__ blk_entry,

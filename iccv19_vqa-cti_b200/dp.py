@@ -80,6 +80,7 @@ class GradAllReducer:
             n = sum(p.numel() for p in grp)
             self.buckets.append(_Bucket(grp, None if self.slab is None else self.slab[o:o + n]))
             o += n
+        self._in_place = set()                            # params whose producer writes the gradient into the bucket view itself
         self._src = {}                                    # param -> gradient tensor produced by backward (graph-owned under replay)
         self._of = {}
         self._handles = []
@@ -132,6 +133,8 @@ class GradAllReducer:
         dsts, srcs = [], []
         for b in self.buckets:
             for p, v in zip(b.params, b.views):
+                if p in self._in_place:                                # already in the bucket (prepack.bind_grad_buffers)
+                    continue
                 g = p.grad
                 if g is not None and g.data_ptr() != v.data_ptr():
                     self._src[p] = g                                   # fresh from backward
@@ -156,6 +159,11 @@ class GradAllReducer:
             for p, v in zip(b.params, b.views):
                 p.grad = v
             b.pending = len(b.params)
+
+    def mark_in_place(self, params) -> None:
+        """These parameters' gradients are written straight into their bucket views by whoever produces them (the deferred
+        weight-norm backward): ``reduce_now`` neither copies nor zeroes them."""
+        self._in_place.update(params)
 
     def forget_sources(self) -> None:
         self._src.clear()

@@ -391,3 +391,84 @@ def test_distillation_loss_dropin_against_reference_formula(n_ans, half_teacher)
     assert (xd.grad.cpu() - xl.grad).abs().max().item() <= 1e-5 * xl.grad.abs().max().item() + 1e-9
     loss2 = crit(xd, teacher.to(DEV), target.to(DEV))
     assert loss2.item() == loss.item()                                                  # fixed summation order
+
+
+def test_prepack_deferred_weight_norm_backward_matches_per_layer_backward():
+    """prepack() with gradients enabled defers every layer's weight-norm backward to ONE autograd node
+    (cti_wn_grad_multi, two launches); without prepack each layer runs its own (cti_wn_grad).  Same gradients either way
+    (up to the order of the split-K reduce-adds of the wgrad GEMMs), every parameter gets one, and the 96 per-rank nets
+    receive theirs through the stacked proxies."""
+    from cti_b200 import kernels as KS
+    torch.manual_seed(5)
+    mods = torch.nn.ModuleList([cti_b200.TriAttention(2048, 1024, 1024, 512, 1, 32, 2, 1),
+                                cti_b200.TCNet(2048, 1024, 1024, 512, 1, 32, 1, k=2),
+                                cti_b200.FCNet([1024, 1024], '', .2)]).to(DEV).eval()
+    att, pool, prj = mods
+    v, q, a = (t.to(DEV) for t in O.synthetic_inputs(6, 20, 12, 6, seed=3))
+    cot = torch.randn(6, 1024, device=DEV)
+
+    def run(deferred):
+        cti_b200.reset_caches([mods], [v])
+        for p in mods.parameters():
+            p.grad = None
+        if deferred:
+            cti_b200.prepack(mods)
+        qq, aa = q.clone().requires_grad_(True), a.clone().requires_grad_(True)
+        p_att, _ = att(v, qq, aa)
+        b = pool.forward_with_weights(v, qq, aa, p_att[:, :, :, :, 1])
+        KS.STATS.launches = 0
+        ((prj(b) + qq.sum(1)) * cot).sum().backward()
+        n = KS.STATS.launches
+        return {k: p.grad.clone() for k, p in mods.named_parameters() if p.grad is not None}, qq.grad.clone(), n
+    g_lazy, dq_lazy, n_lazy = run(False)
+    g_def, dq_def, n_def = run(True)
+    assert sorted(g_lazy) == sorted(g_def)
+    assert len(g_def) == len([1 for k, p in mods.named_parameters() if "T_g" not in k or "0.TriAtt" in k])
+    for k in g_lazy:
+        assert g_def[k].shape == g_lazy[k].shape
+        scale = g_lazy[k].abs().max().item()
+        assert (g_def[k] - g_lazy[k]).abs().max().item() <= 1e-4 * scale + 1e-9, k
+    assert (dq_def - dq_lazy).abs().max().item() <= 1e-4 * dq_lazy.abs().max().item()
+    assert n_def < n_lazy - 15                    # 2 launches instead of 2 per layer (7 single layers + 3 rank groups)
+    # a second step re-uses the plan, and eval / no-grad calls fall back to plain packs
+    g2, _, _ = run(True)
+    assert all((g2[k] - g_def[k]).abs().max().item() <= 1e-4 * g_def[k].abs().max().item() + 1e-9 for k in g2)
+    with torch.no_grad():
+        cti_b200.prepack(mods)
+        att(v, q, a)
+
+
+def test_deferred_backward_writes_into_all_reduce_buckets():
+    """bind_grad_buffers(): dV / dg land in the GradAllReducer's bucket views (no copy), p.grad points at them, and
+    reduce_now() leaves them alone; values equal the unbound run."""
+    from cti_b200.dp import GradAllReducer
+    torch.manual_seed(6)
+    mods = torch.nn.ModuleList([cti_b200.TCNet(2048, 1024, 1024, 512, 1, 32, 1, k=2),
+                                cti_b200.FCNet([1024, 1024], '', .2)]).to(DEV).eval()
+    pool, prj = mods
+    v, q, a = (t.to(DEV) for t in O.synthetic_inputs(4, 20, 12, 6, seed=4))
+    w = torch.softmax(torch.randn(4, 20 * 12 * 6, device=DEV), 1).view(4, 20, 12, 6)
+    params = list(mods.parameters())
+
+    def run():
+        for p in params:
+            p.grad = None
+        cti_b200.prepack(mods)
+        qq = q.clone().requires_grad_(True)
+        prj(pool.forward_with_weights(v, qq, a, w)).square().sum().backward()
+    run()
+    want = {k: p.grad.clone() for k, p in mods.named_parameters()}
+    red = GradAllReducer(params)                                  # world size 1: buckets only
+    cti_b200.bind_grad_buffers(mods, red)
+    run()
+    views = {p: vw for b in red.buckets for p, vw in zip(b.params, b.views)}
+    for k, p in mods.named_parameters():
+        if k.endswith("weight_v") or k.endswith("weight_g"):
+            assert p.grad.data_ptr() == views[p].data_ptr(), k
+    red.reduce_now()
+    for k, p in mods.named_parameters():
+        assert p.grad.data_ptr() == views[p].data_ptr(), k
+        assert (p.grad - want[k]).abs().max().item() <= 1e-4 * want[k].abs().max().item() + 1e-9, k
+    cti_b200.bind_grad_buffers(mods, None)
+    run()
+    assert all(p.grad.data_ptr() != views[p].data_ptr() for p in params)
