@@ -16,12 +16,13 @@ from .dropin import install, uninstall
 from .fc import FCNet, WNLinear
 from .graphs import GraphedStep, reset_caches
 from .language_model import QuestionEmbedding
+from .loader import FeatureBatch, FeatureStoreBF16, TeacherLogits, prime_features
 from .loss_function import Distillation_Loss
 from .optim import FusedClipAdamax
 from .prepack import bind_grad_buffers, prepack
 from .tc import TCNet
 
-__all__ = ["FCNet", "WNLinear", "TCNet", "TriAttention", "BCNet", "BiAttention", "SimpleClassifier", "QuestionEmbedding", "Distillation_Loss", "FusedClipAdamax", "prepack", "bind_grad_buffers", "install", "uninstall", "GraphedStep", "reset_caches",
+__all__ = ["FCNet", "WNLinear", "TCNet", "TriAttention", "BCNet", "BiAttention", "SimpleClassifier", "QuestionEmbedding", "Distillation_Loss", "FusedClipAdamax", "prepack", "bind_grad_buffers", "FeatureStoreBF16", "FeatureBatch", "TeacherLogits", "prime_features", "install", "uninstall", "GraphedStep", "reset_caches",
            "library_path", "version"]
 
 

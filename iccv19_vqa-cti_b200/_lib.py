@@ -19,6 +19,7 @@ SIGNATURES = {
     "cti_version": (c_int, []),
     "cti_last_error": (c_char_p, []),
     "cti_cast_rows_mask": (c_int, [_P, _P, _P, c_int64, c_int, _P]),
+    "cti_rowmask_bf16": (c_int, [_P, _P, c_int64, c_int, _P]),
     "cti_cast_rows_dropout": (c_int, [_P, _P, _P, c_int64, c_int, c_float, ctypes.c_uint64, ctypes.c_uint64, _P]),
     "cti_dropout_f32": (c_int, [_P, c_int64, c_float, ctypes.c_uint64, ctypes.c_uint64, _P]),
     "cti_dropout_bf16": (c_int, [_P, _P, c_int64, c_float, ctypes.c_uint64, ctypes.c_uint64, _P]),

@@ -79,6 +79,10 @@ int cti_wn_pack_multi(const void* v_ptrs_dev, const void* g_ptrs_dev, const void
                             n_blks, partials, static_cast<cudaStream_t>(stream));
 }
 
+int cti_rowmask_bf16(const void* x_bf16, uint8_t* rowmask, int64_t rows, int cols, void* stream) {
+  return cti::rowmask_bf16(static_cast<const __nv_bfloat16*>(x_bf16), rowmask, rows, cols, static_cast<cudaStream_t>(stream));
+}
+
 int cti_wn_grad_multi(const void* dw_ptrs_dev, const void* v_ptrs_dev, const void* g_ptrs_dev, const void* sumsq_ptrs_dev,
                       const void* dv_ptrs_dev, const void* dg_ptrs_dev, const int64_t* elems_dev, const int32_t* first_seg_dev,
                       const int32_t* n_seg_dev, const int32_t* seg_entry_dev, const int32_t* seg_index_dev, int n_segs,

@@ -41,6 +41,7 @@ int dropout_expand(const __nv_bfloat16* x, __nv_bfloat16* xt, long rows, int col
 int dropout_reduce(const __nv_bfloat16* dxt, float* acc, long rows, int cols, int RG, int r0, float p, uint64_t seed,
                    uint64_t offset, cudaStream_t s);
 int sum_row_groups(const __nv_bfloat16* x, __nv_bfloat16* out, long groups, int rep, long row_elems, cudaStream_t s);
+int rowmask_bf16(const __nv_bfloat16* x, uint8_t* rowmask, long rows, int cols, cudaStream_t s);
 int wn_grad_multi(const void* dw_ptrs, const void* v_ptrs, const void* g_ptrs, const void* sumsq_ptrs, const void* dv_ptrs,
                   const void* dg_ptrs, const long* elems, const int* first_seg, const int* n_seg, const int* seg_entry,
                   const int* seg_index, int n_segs, const int* blk_entry, const int* blk_index, int n_blks, float* partials,

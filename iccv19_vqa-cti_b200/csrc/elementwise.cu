@@ -52,6 +52,25 @@ __global__ void __launch_bounds__(256) cast_rows_mask_kernel(const float* __rest
   }
 }
 
+// Zero-row mask of features that already ARE bf16 (the loader's wire format, loader.py): rowmask[r] = 1 iff every
+// element of row r is +-0.  One warp per row, 16-byte loads, read-only.
+__global__ void __launch_bounds__(256) rowmask_bf16_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ rowmask,
+                                                           long rows, int cols) {
+  pdl_prologue_done();
+  const int lane = threadIdx.x & 31;
+  const long row = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const uint4* x4 = reinterpret_cast<const uint4*>(x + row * cols);
+  uint32_t acc = 0;
+#pragma unroll 4
+  for (int i = lane; i < (cols >> 3); i += 32) {
+    const uint4 u = __ldcs(x4 + i);
+    acc |= (u.x | u.y | u.z | u.w) & 0x7FFF7FFFu;        // drop the sign bits: -0 counts as zero
+  }
+  const unsigned any = __ballot_sync(0xffffffffu, acc != 0u);
+  if (lane == 0) rowmask[row] = (any == 0u) ? 1 : 0;
+}
+
 // ------------------------------------------------------------------------- //
 // Dropout (training mode): keep mask = Philox4x32-10(seed, (element / 4, offset)) word (element % 4) >= p * 2^32,
 // kept values scaled by 1 / (1 - p).  The mask is a pure function of (seed, offset, element index), so the
@@ -507,6 +526,14 @@ int cast_rows_mask(const float* x, __nv_bfloat16* out, uint8_t* rowmask, long ro
   CTI_REQUIRE(blocks < (1l << 31), "cast_rows_mask: too many rows");
   launch_pdl(cast_rows_mask_kernel, dim3((unsigned)blocks), dim3(warps * 32), 0, s, x, out, rowmask, rows, cols);
   return check_launch("cast_rows_mask_kernel");
+}
+
+int rowmask_bf16(const __nv_bfloat16* x, uint8_t* rowmask, long rows, int cols, cudaStream_t s) {
+  CTI_REQUIRE(rows >= 0 && cols > 0 && (cols & 7) == 0, "rowmask_bf16: cols=%d must be a multiple of 8", cols);
+  if (rows == 0) return 0;
+  CTI_REQUIRE(((uintptr_t)x & 15) == 0, "rowmask_bf16: features must be 16-byte aligned");
+  launch_pdl(rowmask_bf16_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, s, x, rowmask, rows, cols);
+  return check_launch("rowmask_bf16_kernel");
 }
 
 int cast_rows_dropout(const float* x, __nv_bfloat16* out, uint8_t* rowmask, long rows, int cols, float p, uint64_t seed,

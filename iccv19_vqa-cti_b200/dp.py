@@ -27,17 +27,24 @@ def shard_rows(n_rows: int, rank: int, world: int, group: int = 1) -> slice:
     return slice(lo * group, hi * group)
 
 
+_ALIGN = 4           # every gradient view starts on a 16-byte boundary (kernels write them with 16-byte stores)
+
+
+def _padded(n: int) -> int:
+    return -(-n // _ALIGN) * _ALIGN
+
+
 class _Bucket:
     __slots__ = ("params", "flat", "views", "pending", "work")
 
     def __init__(self, params: List[torch.nn.Parameter], flat: Optional[torch.Tensor] = None):
         self.params = params
-        n = sum(p.numel() for p in params)
+        n = sum(_padded(p.numel()) for p in params)
         self.flat = flat if flat is not None else torch.zeros(n, dtype=params[0].dtype, device=params[0].device)
         self.views, o = [], 0
         for p in params:
             self.views.append(self.flat[o:o + p.numel()].view_as(p))
-            o += p.numel()
+            o += _padded(p.numel())
         self.pending = len(params)
         self.work = None
 
@@ -73,11 +80,11 @@ class GradAllReducer:
         # the hook-free path can then reduce everything with a single collective
         self.slab: Optional[torch.Tensor] = None
         if ps and all(p.dtype == ps[0].dtype and p.device == ps[0].device for p in ps):
-            self.slab = torch.zeros(sum(p.numel() for p in ps), dtype=ps[0].dtype, device=ps[0].device)
+            self.slab = torch.zeros(sum(_padded(p.numel()) for p in ps), dtype=ps[0].dtype, device=ps[0].device)
         self.buckets: List[_Bucket] = []
         o = 0
         for grp in groups:
-            n = sum(p.numel() for p in grp)
+            n = sum(_padded(p.numel()) for p in grp)
             self.buckets.append(_Bucket(grp, None if self.slab is None else self.slab[o:o + n]))
             o += n
         self._in_place = set()                            # params whose producer writes the gradient into the bucket view itself

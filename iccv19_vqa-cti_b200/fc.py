@@ -60,9 +60,10 @@ class WNLinear(nn.Module):
 
 
 def features_f32_2d(v: torch.Tensor) -> torch.Tensor:
-    """(B, K, Dv) features as a contiguous fp32 (B*K, Dv) matrix (input of the fused cast + dropout kernel)."""
+    """(B, K, Dv) features as a contiguous (B*K, Dv) matrix for the fused cast + dropout kernel: fp32, or bf16 when the
+    features arrive in the loader's bf16 wire format (the dropout kernel then works on bf16 directly)."""
     x = v.detach()
-    if x.dtype != torch.float32:
+    if x.dtype not in (torch.float32, torch.bfloat16):
         x = x.float()
     return x.reshape(-1, x.shape[-1]).contiguous()
 
@@ -119,9 +120,15 @@ def cast_features(v: torch.Tensor):
     if cached is not None and cached[0] == key:
         return cached[1], cached[2]
     x = v.detach()
-    if x.dtype != torch.float32:
-        x = x.float()
-    xb, mask = K_.cast_rows(x.reshape(-1, x.shape[-1]).contiguous(), want_mask=True)
+    if x.dtype == torch.bfloat16:
+        # loader wire format (loader.py): bf16 features need no cast; the mask comes from the loader (prime_features)
+        # or from one read-only pass
+        xb = x.reshape(-1, x.shape[-1]).contiguous()
+        mask = K_.rowmask_bf16(xb)
+    else:
+        if x.dtype != torch.float32:
+            x = x.float()
+        xb, mask = K_.cast_rows(x.reshape(-1, x.shape[-1]).contiguous(), want_mask=True)
     try:
         setattr(v, _FEAT_ATTR, (key, xb, mask))
     except Exception:

@@ -95,6 +95,14 @@ def new_drop(p: float, training: bool):
     return (float(p), torch.initial_seed() & 0x7FFFFFFFFFFFFFFF, _DROP_SITES[0])
 
 
+def drop_features(v2d: torch.Tensor, drop) -> torch.Tensor:
+    """bf16(dropout(v)) of the image features: fp32 input goes through the fused cast + dropout kernel, bf16 input (the
+    loader wire format) through the bf16 dropout kernel."""
+    if v2d.dtype == BF16:
+        return K_.dropout_bf16(v2d, drop)
+    return K_.cast_rows_dropout(v2d, drop)[0]
+
+
 def cast_in(x2d: torch.Tensor, drop):
     x2d = x2d.detach().contiguous()
     if x2d.dtype != F32:
@@ -322,7 +330,7 @@ class TriLogitsFn(Function):
         if drops is not None:
             v_f32, dv, dq, da, dvn, dqn, dan = drops
             if dv is not None:
-                v_bf16 = K_.cast_rows_dropout(v_f32, dv)[0]
+                v_bf16 = drop_features(v_f32, dv)
         # w = (V, g, b) x [v_tucker, q_tucker, a_tucker, v_net, q_net, a_net]
         groups = (1, 1, 1, R, R, R)
         pk: List[Packed] = [packs[i] if packs is not None else pack_layer(w[3 * i], w[3 * i + 1], groups[i])
@@ -485,7 +493,7 @@ class PoolFn(Function):
         if drops is not None:
             v_f32, dv, dq_drop, da_drop = drops
             if dv is not None:
-                v_bf16 = K_.cast_rows_dropout(v_f32, dv)[0]
+                v_bf16 = drop_features(v_f32, dv)
         ctx.drops = (dq_drop, da_drop)
         xq = cast_tokens(q, dq_drop)
         vp, _ = lin_fwd(v_bf16, pk[0], w[2], True)
@@ -551,7 +559,7 @@ class BiLogitsFn(Function):
         if drops is not None:
             v_f32, dv, dq_drop, datt = drops
             if dv is not None:
-                v_bf16 = K_.cast_rows_dropout(v_f32, dv)[0]
+                v_bf16 = drop_features(v_f32, dv)
         ctx.drops = (dq_drop, datt)
         xq = cast_tokens(q, dq_drop)
         vb, _ = lin_fwd(v_bf16, pk[0], w[2], True)

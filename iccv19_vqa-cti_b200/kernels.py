@@ -88,6 +88,16 @@ def cast_rows(x: torch.Tensor, want_mask: bool = False) -> Tuple[torch.Tensor, O
     return out, mask
 
 
+def rowmask_bf16(x: torch.Tensor) -> torch.Tensor:
+    """Zero-row mask (reference src/attention.py:55) of a bf16 (rows, cols) matrix."""
+    _req(x, BF16, "rowmask_bf16.x")
+    rows, cols = x.shape
+    mask = torch.empty((rows,), dtype=torch.uint8, device=x.device)
+    _call("cti_rowmask_bf16", _lib.load().cti_rowmask_bf16, (x.data_ptr(), mask.data_ptr(), rows, cols, _stream()),
+          nbytes=2.0 * rows * cols)
+    return mask
+
+
 def cast_rows_dropout(x: torch.Tensor, drop, want_mask: bool = False):
     """bf16(dropout(x)) for fp32 (rows, cols); drop = (p, seed, offset).  The zero-row mask is of the undropped rows."""
     _req(x, F32, "cast_rows_dropout.x")

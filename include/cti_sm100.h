@@ -36,6 +36,10 @@ const char* cti_last_error(void);
  * out[r,:] = bf16(x[r,:]);  rowmask[r] = (sum_c |x[r,c]| == 0)   (rowmask may be NULL)
  * replaces: src/attention.py:55 and :36  `(0 == v.abs().sum(2))`, plus the fp32->bf16 operand cast. */
 int cti_cast_rows_mask(const float* x, void* out_bf16, uint8_t* rowmask, int64_t rows, int cols, void* stream);
+/* The same mask for features that arrive as bf16 already (the loader wire format of SURVEY 8f row 5: padded
+ * (images, K, v_dim) bf16 -- half the host-to-device bytes of the reference's fp32 batches, no cast on the device):
+ * rowmask[r] = 1 iff row r is all zeros.  replaces: `v.abs().sum(2) == 0`, src/attention.py:55 / :36. */
+int cti_rowmask_bf16(const void* x_bf16, uint8_t* rowmask, int64_t rows, int cols, void* stream);
 
 /* ---- training-mode dropout -------------------------------------------------------------------
  * The keep mask is a pure function of (seed, offset, element index): Philox4x32-10 keyed by `seed`, counter
