@@ -137,6 +137,9 @@ class GradAllReducer:
         remembered, so the next call (after the next replay, which refills them) finds its sources even though
         ``p.grad`` now names the views (or was reset to None); an eager backward simply assigns fresh ``p.grad`` tensors,
         which take over.  ``forget_sources()`` drops the remembered tensors (after re-capturing a graph)."""
+        if getattr(self, "_enabled", True):
+            raise RuntimeError("reduce_now() is the hook-free path: call set_hooks_enabled(False) first (with the hooks on, "
+                               "backward already filled and reduced the buckets -- use finish())")
         dsts, srcs = [], []
         for b in self.buckets:
             for p, v in zip(b.params, b.views):

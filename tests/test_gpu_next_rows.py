@@ -459,6 +459,7 @@ def test_deferred_backward_writes_into_all_reduce_buckets():
     run()
     want = {k: p.grad.clone() for k, p in mods.named_parameters()}
     red = GradAllReducer(params)                                  # world size 1: buckets only
+    red.set_hooks_enabled(False)                                  # reduce_now() is the hook-free path
     cti_b200.bind_grad_buffers(mods, red)
     run()
     views = {p: vw for b in red.buckets for p, vw in zip(b.params, b.views)}

@@ -212,7 +212,7 @@ def test_reduce_now_leaves_gradients_on_the_bucket_views_and_remembers_sources()
     for p, s in zip(ps, src):
         p.grad = s
     red.reduce_now()
-    assert red.slab is not None and red.slab.numel() == 15
+    assert red.slab is not None and red.slab.numel() == 8 + 4 + 8       # every view starts on a 16-byte boundary
     for p, s in zip(ps, src):
         assert torch.equal(p.grad, s) and p.grad.data_ptr() != s.data_ptr()          # now a view of the slab
     for s in src:                                                                    # a "replay" refills the same tensors
