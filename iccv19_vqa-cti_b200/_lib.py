@@ -42,9 +42,10 @@ SIGNATURES = {
     "cti_kd_loss": (c_int, [_P, _P, c_int, _P, _P, _P, _P, c_int, c_int, c_float, c_float, _P]),
     "cti_masked_softmax_fwd": (c_int, [_P, _P, c_int64, c_int, _P]),
     "cti_masked_softmax_bwd": (c_int, [_P, _P, c_int64, c_int64, c_int64, _P, c_int64, c_int, c_int, _P]),
-    "cti_trilinear_logits_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "cti_trilinear_logits_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "cti_trilinear_n1_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "cti_trilinear_logits_bwd_workspace": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
-    "cti_trilinear_logits_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, c_int, c_int,
+    "cti_trilinear_logits_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, c_int, c_int,
                                          c_int, c_int, c_int, c_int, c_int, _P]),
     "cti_tri_pool_fwd": (c_int, [_P, _P, _P, _P, c_int64, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "cti_tri_pool_bwd": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int,

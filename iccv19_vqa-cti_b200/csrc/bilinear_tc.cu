@@ -115,7 +115,7 @@ bilinear_tc_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_cons
   constexpr uint32_t TM_L = 0, TM_DV = 0, TM_PT = 256;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       for (int g = 0; g < total; ++g) {
         const int b = blockIdx.x + (g / p.nchunks) * gridDim.x, ch = g % p.nchunks;
         const int st = g % STAGES;
@@ -128,7 +128,7 @@ bilinear_tc_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const uint32_t id_l = make_idesc_rt(128, NR, 0, 0);
       const uint32_t id_dv = make_idesc_rt(128, 128, 0, 1);
       const uint32_t id_pt = make_idesc_rt(128, NR, 1, 1);

@@ -201,16 +201,22 @@ int cti_masked_softmax_bwd(const float* p, const float* dp, int64_t dp_stride_b,
 }
 
 int cti_trilinear_logits_fwd(const void* vc, const void* qc, const void* ac, const void* tpack, const void* tpack_perm,
-                             const uint8_t* rowmask, float* logits, int B, int K, int Q, int A, int G, int R, int v_rep,
-                             void* stream) {
+                             const uint8_t* rowmask, float* logits, void* n1_save, int B, int K, int Q, int A, int G, int R,
+                             int v_rep, void* stream) {
   cti::TriDims d{B, K, Q, A, G, R, v_rep};
   return cti::trilinear_fwd(static_cast<const __nv_bfloat16*>(vc), static_cast<const __nv_bfloat16*>(qc),
                             static_cast<const __nv_bfloat16*>(ac), static_cast<const __nv_bfloat16*>(tpack),
-                            static_cast<const __nv_bfloat16*>(tpack_perm), rowmask, logits, d,
+                            static_cast<const __nv_bfloat16*>(tpack_perm), rowmask, logits, n1_save, d,
                             static_cast<cudaStream_t>(stream));
 }
 
+size_t cti_trilinear_n1_bytes(int B, int K, int Q, int A, int G, int R) {
+  cti::TriDims d{B, K, Q, A, G, R};
+  return cti::trilinear_n1_bytes(d);
+}
+
 int cti_debug_prof_read(unsigned long long* host_dst, int n) { return cti::debug_prof_read(host_dst, n); }
+int cti_debug_prof_read_bwd1(unsigned long long* host_dst, int n) { return cti::debug_prof_read_bwd1(host_dst, n); }
 
 size_t cti_trilinear_logits_bwd_workspace(int B, int K, int Q, int A, int G, int R) {
   cti::TriDims d{B, K, Q, A, G, R};
@@ -218,12 +224,12 @@ size_t cti_trilinear_logits_bwd_workspace(int B, int K, int Q, int A, int G, int
 }
 
 int cti_trilinear_logits_bwd(const void* vc, const void* qc, const void* ac, const void* tpack, const float* dlogits,
-                             void* dzv, void* dzq, void* dza, float* dbv_accum, float* dbq_accum, float* dba_accum,
+                             const void* n1_saved, void* dzv, void* dzq, void* dza, float* dbv_accum, float* dbq_accum, float* dba_accum,
                              float* dtpack_accum, void* workspace, size_t workspace_bytes, int B, int K, int Q, int A,
                              int G, int R, int v_rep, void* stream) {
   cti::TriDims d{B, K, Q, A, G, R, v_rep};
   return cti::trilinear_bwd(static_cast<const __nv_bfloat16*>(vc), static_cast<const __nv_bfloat16*>(qc),
-                            static_cast<const __nv_bfloat16*>(ac), static_cast<const __nv_bfloat16*>(tpack), dlogits,
+                            static_cast<const __nv_bfloat16*>(ac), static_cast<const __nv_bfloat16*>(tpack), dlogits, n1_saved,
                             static_cast<__nv_bfloat16*>(dzv), static_cast<__nv_bfloat16*>(dzq),
                             static_cast<__nv_bfloat16*>(dza), dbv_accum, dbq_accum, dba_accum, dtpack_accum, workspace,
                             workspace_bytes, d, static_cast<cudaStream_t>(stream));

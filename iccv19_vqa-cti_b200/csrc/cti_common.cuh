@@ -94,6 +94,22 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);      // errors surface in check_launch()
 }
 
+// One lane of a CONVERGED warp.  The single-thread roles (TMA producer, tcgen05.mma issuers) enter their loop through
+// this instead of `lane == 0`: with a threadIdx-derived condition ptxas cannot prove that exactly one lane is active
+// and wraps every UTCHMMA / UTMALDG / UTCBAR in an ELECT ... BRA.U.ANY waterfall loop -- 95 instead of 50 cycles per
+// tcgen05.mma from one thread (tools/ubench/tc_ubench3.cu).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // --------------------------------------------------------------------------- //
 // mbarrier
 // --------------------------------------------------------------------------- //

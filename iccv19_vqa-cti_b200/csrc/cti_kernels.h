@@ -88,12 +88,15 @@ struct TriDims {
   int VR = 1;             // v_rep: rows b of q / a / logits use row b / VR of vc and rowmask (vc has B / VR samples)
 };
 int trilinear_fwd(const __nv_bfloat16* vc, const __nv_bfloat16* qc, const __nv_bfloat16* ac, const __nv_bfloat16* tpack,
-                  const __nv_bfloat16* tpack_perm, const uint8_t* rowmask, float* logits, TriDims d, cudaStream_t s);
+                  const __nv_bfloat16* tpack_perm, const uint8_t* rowmask, float* logits, void* n1_save, TriDims d,
+                  cudaStream_t s);
+size_t trilinear_n1_bytes(TriDims d);      // size of n1_save (0: shape outside the tcgen05 path)
 size_t trilinear_bwd_workspace(TriDims d);
 int debug_prof_read(unsigned long long* host_dst, int n);   // CTI_PROF builds only (returns -1 otherwise)
+int debug_prof_read_bwd1(unsigned long long* host_dst, int n);
 int trilinear_bwd(const __nv_bfloat16* vc, const __nv_bfloat16* qc, const __nv_bfloat16* ac, const __nv_bfloat16* tpack,
-                  const float* dlogits, __nv_bfloat16* dzv, __nv_bfloat16* dzq, __nv_bfloat16* dza, float* dbv,
-                  float* dbq, float* dba, float* dtpack, void* workspace, size_t workspace_bytes, TriDims d,
+                  const float* dlogits, const void* n1_saved, __nv_bfloat16* dzv, __nv_bfloat16* dzq, __nv_bfloat16* dza,
+                  float* dbv, float* dbq, float* dba, float* dtpack, void* workspace, size_t workspace_bytes, TriDims d,
                   cudaStream_t s);
 
 // pool.cu  (A == 0 selects the bilinear pooling of BCNet.forward_with_weights)

@@ -141,7 +141,7 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ 
 
   if (warp == 0) {
     // ------------------------------ TMA producer: V tiles ------------------------------
-    if (lane == 0) {
+    if (elect_one_sync()) {
       for (int g = 0; g < total; ++g) {
         const int b = blockIdx.x + (g / p.nchunks) * gridDim.x, ch = g % p.nchunks;
         const int st = g % V_STAGES;
@@ -157,7 +157,7 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------------------
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const uint32_t id_z = make_idesc_rt(128, p.NC, 1, 1);
       const uint32_t id_dv = make_idesc_rt(128, 64, 0, 0);
       const uint32_t id_dw = make_idesc_rt(128, p.NC, 0, 1);

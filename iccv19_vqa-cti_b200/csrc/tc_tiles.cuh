@@ -76,6 +76,10 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc
                ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar)
                : "memory");
 }
+// 1-D bulk copy shared -> global (bulk-group completion; bytes % 16 == 0, both 16-byte aligned).
+__device__ __forceinline__ void bulk_store_1d(void* gdst, uint32_t smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));

@@ -611,16 +611,18 @@ int check_dims(const TriDims& d, const char* who) {
 }  // namespace
 
 int trilinear_fwd_tc(const bf16* vc, const bf16* qc, const bf16* ac, const bf16* tpack_perm, const uint8_t* rowmask,
-                     float* logits, TriDims d, cudaStream_t stream);   // trilinear_tc.cu
+                     float* logits, void* n1_save, TriDims d, cudaStream_t stream);   // trilinear_tc.cu
 
 int trilinear_fwd(const bf16* vc, const bf16* qc, const bf16* ac, const bf16* tpack, const bf16* tpack_perm,
-                  const uint8_t* rowmask, float* logits, TriDims d, cudaStream_t stream) {
+                  const uint8_t* rowmask, float* logits, void* n1_save, TriDims d, cudaStream_t stream) {
   if (int rc = check_dims(d, "trilinear_fwd")) return rc;
   if (d.B == 0) return 0;
   {   // tcgen05 fast path (G == 2, K <= 64, A <= 6, tpack_perm given); other shapes use the generic kernel below
-    const int rc = trilinear_fwd_tc(vc, qc, ac, tpack_perm, rowmask, logits, d, stream);
+    const int rc = trilinear_fwd_tc(vc, qc, ac, tpack_perm, rowmask, logits, n1_save, d, stream);
     if (rc != -100) return rc;
   }
+  CTI_REQUIRE(n1_save == nullptr, "trilinear_fwd: n1_save is only written by the tcgen05 path (pass tpack_perm; "
+                                  "cti_trilinear_n1_bytes() == 0 for shapes outside it)");
   const TriShape s = make_shape(d);
   const FwdSmem lay = fwd_smem(s);
   CTI_REQUIRE(lay.total <= 227 * 1024, "trilinear_fwd: needs %zu bytes of shared memory (> 227 KB)", lay.total);
@@ -632,9 +634,9 @@ int trilinear_fwd(const bf16* vc, const bf16* qc, const bf16* ac, const bf16* tp
 }
 
 size_t trilinear_bwd_tc_workspace(TriDims d);                                   // trilinear_bwd_tc.cu
-int trilinear_bwd_tc(const bf16* vc, const bf16* qc, const bf16* ac, const bf16* tpack, const bf16* dlm, bf16* dn1,
-                     bf16* dzv, bf16* dzq, bf16* dza, float* dbv, float* dbq, float* dba, float* dtpack, TriDims d,
-                     cudaStream_t stream);
+int trilinear_bwd_tc(const bf16* vc, const bf16* qc, const bf16* ac, const bf16* tpack, const bf16* dlm, const void* n1,
+                     bf16* dn1, bf16* dzv, bf16* dzq, bf16* dza, float* dbv, float* dbq, float* dba, float* dtpack,
+                     TriDims d, cudaStream_t stream);
 
 static size_t dlm_bytes(TriDims d) {
   const TriShape s = make_shape(d);
@@ -645,9 +647,9 @@ size_t trilinear_bwd_workspace(TriDims d) {      // dLm (bf16 matrix form of dlo
   return dlm_bytes(d) + trilinear_bwd_tc_workspace(d);
 }
 
-int trilinear_bwd(const bf16* vc, const bf16* qc, const bf16* ac, const bf16* tpack, const float* dlogits, bf16* dzv,
-                  bf16* dzq, bf16* dza, float* dbv, float* dbq, float* dba, float* dtpack, void* workspace,
-                  size_t workspace_bytes, TriDims d, cudaStream_t stream) {
+int trilinear_bwd(const bf16* vc, const bf16* qc, const bf16* ac, const bf16* tpack, const float* dlogits,
+                  const void* n1_saved, bf16* dzv, bf16* dzq, bf16* dza, float* dbv, float* dbq, float* dba, float* dtpack,
+                  void* workspace, size_t workspace_bytes, TriDims d, cudaStream_t stream) {
   if (int rc = check_dims(d, "trilinear_bwd")) return rc;
   if (d.B == 0) return 0;
   CTI_REQUIRE(workspace != nullptr && workspace_bytes >= trilinear_bwd_workspace(d),
@@ -658,9 +660,9 @@ int trilinear_bwd(const bf16* vc, const bf16* qc, const bf16* ac, const bf16* tp
   bf16* dlm = static_cast<bf16*>(workspace);
   launch_pdl(dlogits_to_dlm_kernel, dim3(kNumSMsB200 * 8), dim3(kDlmWarps * 32), 0, stream, dlogits, dlm, d);
   if (int rc = check_launch("dlogits_to_dlm_kernel")) return rc;
-  {   // tcgen05 fast path (G == 2, A <= 6, K <= 64); other shapes use the generic tensor-core kernel below
+  {   // tcgen05 fast path (G == 2, A <= 6, K <= 64, N1 tiles saved by the forward); otherwise the generic kernel below
     bf16* dn1 = reinterpret_cast<bf16*>(static_cast<uint8_t*>(workspace) + dlm_bytes(d));
-    const int rc = trilinear_bwd_tc(vc, qc, ac, tpack, dlm, dn1, dzv, dzq, dza, dbv, dbq, dba, dtpack, d, stream);
+    const int rc = trilinear_bwd_tc(vc, qc, ac, tpack, dlm, n1_saved, dn1, dzv, dzq, dza, dbv, dbq, dba, dtpack, d, stream);
     if (rc != -100) return rc;
   }
   cudaError_t e = cudaFuncSetAttribute(trilinear_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);

@@ -2,16 +2,22 @@
 //
 //   L[b,k,(a,g,q)] = sum_r sum_i Vc_r[k,i] M_r[i,(a,g,q)],   M_r = N1_r x_j Qc_r,   N1_r = T_r x_l Ac_r
 //
-// Two kernels, both built from per-sample tcgen05.mma stages with TMEM accumulators and the dual-use
-// swizzled operand tiles of tc_tiles.cuh:
+// Two kernels, both built from tcgen05.mma stages with TMEM accumulators and the dual-use swizzled operand tiles of
+// tc_tiles.cuh.  What shapes them (round 2, tools/ubench + the launch list): every tcgen05.mma / tcgen05.commit is one
+// entry of an in-order queue that drains at ~75 cycles per entry in kernels like these, whatever the tile size; the
+// first version issued 40 small MMAs + 14 commits per (sample, rank) and ran at exactly 54 x 75 cycles per unit.  So
+// the stages are batched until the instruction count, not the FLOP count, is small:
 //
-// 1. trilinear_bwd1_tc_kernel -- sample-outer, rank-inner (like the forward).  Per (sample, rank):
-//      F1, F2           recompute N1_r and M_r (same stages as the forward)
-//      B1  dVc[k,i]     = dL[k,n] . M_r[i,n]^T                      -> ReLU mask, dzv, dbv
-//      B2  D^T[n,i]     = dL[k,n]^T . Vc_r[k,i]                     -> D tile [q][(a,g,i)]
-//      B3  dQc[q,j]     = D[q,(a,g,i)] . N1_r[(a,g,i),j]            -> ReLU mask, dzq, dbq
-//      B4  dN1[(a,g,i),j] = D[q,(a,g,i)]^T . Qc_r[q,j]              -> bf16, written to the workspace
-//    dL (the gradient of the logits, bf16, [k][(a,g,q16)]) is loaded once per sample by TMA.
+// 1. trilinear_bwd1_tc_kernel -- sample-outer, one step per rank QUAD t (4 ranks = 64 operand columns):
+//      (N1 tiles of the quad come back from the forward: one 24 KB bulk copy instead of F1 + the core re-load)
+//      B2  dM[(r4,i), n]      = Vc_t[k,(r4,i)]^T . dL[k,n]            4 MMAs 128 x 192 x 16 per quad   -> Dt tile [(a,g,i)][(r4,q)]
+//      F2  M_r[(a,g,i), q]    = N1_r[(a,g,i),j] . Qc_r[q,j]^T         2 per rank                        -> M quad tile [(r4,i)][n]
+//      B1  dVc[k,(r4,i)]      = dL[k,n] . Mq[(r4,i),n]^T              12 MMAs 128 x 64 x 16 per quad    -> ReLU mask, dzv
+//      B3  X[(r4',q),(r4,j)]  = Dt[(a,g,i),(r4',q)]^T . N1[(a,g,i),(r4,j)]   12 per quad; the diagonal blocks r' = r are
+//                                                                     dQc_r[q,j] (4x redundant FLOPs, a quarter of the MMAs)
+//      B4  dN1_r[(a,g,i), j]  = Dt_r[(a,g,i),q] . Qc_r[q,j]           2 per rank                        -> bf16 workspace
+//    11 MMAs + ~3 commits per (sample, rank).  Buffers are released by the converter warps once they have seen the
+//    consuming MMAs' own completion barrier (no extra commits).  dL (bf16, [k][(a,g,q16)]) is loaded once per sample.
 // 2. trilinear_bwd2_tc_kernel -- rank-outer: CTA (r, sample chunk) keeps T_r resident and streams the
 //    dN1_r tiles of its samples (two samples per step):
 //      B5  dAc[l,(s,a)] = T_r[l,(i,g,j)] . dN1[(s,a),(i,g,j)]^T     -> ReLU mask, dza, dba
@@ -32,124 +38,104 @@ __device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
 
-// Column sums of a 16-value-per-lane tile over the 32 lanes of a warp with 16 shuffles: afterwards the
-// lanes with (lane & 1) == 0 hold the total of value index (lane >> 1).
-__device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
-  float w8[8], w4[4], w2[2];
-  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float send = b4 ? v[i] : v[i + 8], keep = b4 ? v[i + 8] : v[i];
-    w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float send = b3 ? w8[i] : w8[i + 4], keep = b3 ? w8[i + 4] : w8[i];
-    w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const float send = b2 ? w4[i] : w4[i + 2], keep = b2 ? w4[i + 2] : w4[i];
-    w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-  const float send = b1 ? w2[0] : w2[1], keep = b1 ? w2[1] : w2[0];
-  float w1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
-  return w1;      // value index = (b4 ? 8 : 0) + (b3 ? 4 : 0) + (b2 ? 2 : 0) + (b1 ? 1 : 0) = lane >> 1
-}
+// Debug build (CTI_PROF=1 python build.py): per-role cycle accounting of kernel 1, read back with cti_debug_prof_read_bwd1().
+// Slot layout: [block][role 0..15][counter 0..7].
+#ifdef CTI_PROF
+__device__ unsigned long long g_prof1[148 * 128];
+__device__ unsigned long long g_trace1[16 * 128];        // block 0: time at which event e of quad c happens
+#define TRACE(e, c) do { if (blockIdx.x == 0 && (c) < 128 && (threadIdx.x & 31) == 0) g_trace1[(e) * 128 + (c)] = clock64(); } while (0)
+#define PROF_DECL unsigned long long prof_t0 = 0, prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; (void)prof_t0;
+#define PROF_T0() (prof_t0 = clock64())
+#define PROF_ADD(i) (prof_acc[i] += clock64() - prof_t0)
+#define PROF_FLUSH(role)                                                                           \
+  do {                                                                                             \
+    if ((threadIdx.x & 31) == 0)                                                                   \
+      for (int i_ = 0; i_ < 8; ++i_) g_prof1[(blockIdx.x * 16 + (role)) * 8 + i_] = prof_acc[i_]; \
+  } while (0)
+#else
+#define PROF_DECL
+#define PROF_T0()
+#define PROF_ADD(i)
+#define PROF_FLUSH(role)
+#define TRACE(e, c)
+#endif
+#define PWAIT(i, ...) do { PROF_T0(); mbar_wait(__VA_ARGS__); PROF_ADD(i); } while (0)
 
 // =========================================================================== //
 // kernel 1
 // =========================================================================== //
-constexpr int kThreads1 = 704;     // 22 warps: TMA, 5 single-thread MMA issuers (1, 2, 3, 16, 17), 4 x 4 converter / epilogue warps
-constexpr int T_BYTES = 16 * 1024, T_RING = 2;
-constexpr int OP_V = 0, OP_Q = 8192, OP_A = 10240, OP_BYTES = 12288, OP_RING = 3;
-constexpr int N1_BYTES = 32 * 1024;
-constexpr int M_BYTES = 8 * 1024;
-constexpr int DL_CHUNKS = 3, DL_BYTES = DL_CHUNKS * 8192;     // dL tile [64 k][192 n]
-constexpr int D_BYTES = 6 * 1024;                             // D tile [16 q][192 (a,g,i)]
-constexpr int DB_FLOATS = 512;                                // bias-gradient accumulators (R * 16 <= 512)
-constexpr uint32_t TM_F1 = 0, TM_F2 = 128, TM_B1 = 192, TM_B2 = 224, TM_B3 = 288, TM_B4 = 320;   // all double buffered
+// 21 warps: 0 TMA | 1 B2 issuer | 2 F2 issuer (+ TMEM owner) | 3 B1 issuer | 4 B3 / B4 issuer |
+//           5-8 C3 (dM -> Dt tile) | 9-12 C2 (M -> M tile) | 13-16 E1 (dVc -> dzv) | 17-20 E3 / E4 (dQc -> dzq, dN1 -> workspace)
+constexpr int kThreads1 = 672;
+constexpr int T_BYTES = 16 * 1024;
+constexpr int OP_V = 0, OP_Q = 8192, OP_BYTES = 10240, OP_RING = 2;     // per quad: Vc [64 k][64 (r4,i)], Qc [16 q][64 (r4,j)]
+constexpr int N1_BYTES = 24 * 1024;                           // [(a,g,i) 192][64 (r4,j)]   (the forward's tile image)
+constexpr int DT_BYTES = 24 * 1024;                           // [(a,g,i) 192][64 (r4,q16)]
+constexpr int MQ_BYTES = 24 * 1024;                           // 3 chunks x [64 (r4,i)][64 n]
+constexpr int DL_CHUNKS = 3, DL_BYTES = DL_CHUNKS * 8192;     // dL tile: 3 chunks x [64 k][64 n]
+// TMEM columns: B2 [0,192) | F2 2 x 32 | B4 2 x 32 | B1 2 x 64 | B3 64
+constexpr uint32_t TM_B2 = 0, TM_F2 = 192, TM_B4 = 256, TM_B1 = 320, TM_B3 = 448;
 
-constexpr int N1_RING = 8;     // one 32 KB N1 tile holds the 16-column blocks of 4 consecutive ranks: 2 tiles = 8 units in flight
-enum { A_TFULL = 0, A_TEMPTY = 2, A_OPFULL = 4, A_OPEMPTY = 7, A_DLFULL = 10, A_DLEMPTY = 12, A_F1FULL = 14, A_F1EMPTY = 16,
-       A_N1FULL = 18, A_N1EMPTY = A_N1FULL + N1_RING, A_F2FULL = A_N1EMPTY + N1_RING, A_F2EMPTY = A_F2FULL + 2,
-       A_MFULL = A_F2EMPTY + 2, A_MEMPTY = A_MFULL + 2, A_B1FULL = A_MEMPTY + 2, A_B1EMPTY = A_B1FULL + 2,
-       A_B2FULL = A_B1EMPTY + 2, A_B2EMPTY = A_B2FULL + 2, A_DFULL = A_B2EMPTY + 2, A_DEMPTY = A_DFULL + 2,
-       A_B3FULL = A_DEMPTY + 2, A_B3EMPTY = A_B3FULL + 2, A_B4FULL = A_B3EMPTY + 2, A_B4EMPTY = A_B4FULL + 2,
-       A_COUNT = A_B4EMPTY + 2 };
+enum { A_OPFULL = 0, A_OPEMPTY = 2, A_N1FULL = 4, A_N1EMPTY = 6, A_DLFULL = 8, A_DLEMPTY = 10, A_B2FULL = 12, A_B2EMPTY = 13,
+       A_DTFULL = 14, A_DTEMPTY = 16, A_F2FULL = 18, A_F2EMPTY = 20, A_MFULL = 22, A_MEMPTY = 24, A_B1FULL = 26,
+       A_B1EMPTY = 28, A_B3FULL = 30, A_B3EMPTY = 31, A_B4FULL = 32, A_B4EMPTY = 34, A_COUNT = 36 };
 
 struct Bwd1Params {
+  const uint8_t* n1;         // the forward's N1 quad tiles: [b][R / 4][A * 4096 bytes]
   bf16 *dzv, *dzq, *dn1;
-  float *dbv, *dbq;
   int B, K, Q, A, R, N;
   int VR;        // rows b share the v operand of row b / VR (dzv stays per row b)
 };
 
-constexpr size_t kSmem1 = (size_t)T_RING * T_BYTES + OP_RING * OP_BYTES + 2 * N1_BYTES + 2 * M_BYTES + 2 * DL_BYTES +
-                          2 * D_BYTES + 2 * DB_FLOATS * 4 + A_COUNT * 8 + 16 + 1024;
+// Regions that are read as a 128-row A operand although they hold fewer rows (dL chunks 64, N1 / Dt tiles 192 of 256:
+// the extra accumulator lanes are never read back) come first, so the over-read stays inside this allocation.
+constexpr size_t kSmem1 = (size_t)2 * DL_BYTES + 2 * N1_BYTES + 2 * DT_BYTES + 2 * MQ_BYTES + OP_RING * OP_BYTES +
+                          A_COUNT * 8 + 16 + 1024;
 
 __global__ void __launch_bounds__(kThreads1, 1)
-trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid_constant__ CUtensorMap tmap_v,
-                         const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_a,
+trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_q,
                          const __grid_constant__ CUtensorMap tmap_dl, const Bwd1Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  // Tiles that are read as a 128-row A operand although they hold fewer rows (Vc 64, dL 64, D 16: the extra
-  // accumulator lanes are never read back) come first, so the over-read stays inside this allocation.
-  const uint32_t sT = base;
-  const uint32_t sOp = sT + T_RING * T_BYTES;
-  const uint32_t sDL = sOp + OP_RING * OP_BYTES;
-  const uint32_t sD = sDL + 2 * DL_BYTES;
-  const uint32_t sM = sD + 2 * D_BYTES;
-  const uint32_t sN1 = sM + 2 * M_BYTES;
-  const uint32_t sDb = sN1 + 2 * N1_BYTES;
-  const uint32_t sBar = sDb + 2 * DB_FLOATS * 4;
+  const uint32_t sDL = base;
+  const uint32_t sN1 = sDL + 2 * DL_BYTES;
+  const uint32_t sDT = sN1 + 2 * N1_BYTES;
+  const uint32_t sM = sDT + 2 * DT_BYTES;
+  const uint32_t sOp = sM + 2 * MQ_BYTES;
+  const uint32_t sBar = sOp + OP_RING * OP_BYTES;
   const uint32_t tmem_slot = sBar + A_COUNT * 8;
   auto bar = [&](int i) { return sBar + 8u * i; };
-  float* db_acc = reinterpret_cast<float*>(smem_raw + (sDb - smem_u32(smem_raw)));     // [0,512) dbv, [512,1024) dbq
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  for (int i = threadIdx.x; i < 2 * DB_FLOATS; i += kThreads1) db_acc[i] = 0.f;
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_t);
     tma_prefetch_desc(&tmap_v);
     tma_prefetch_desc(&tmap_q);
-    tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_dl);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar(A_TFULL + s), 1);
-      mbar_init(bar(A_TEMPTY + s), 1);
+      mbar_init(bar(A_OPFULL + s), 1);
+      mbar_init(bar(A_OPEMPTY + s), 16);      // C3 (for B2), C2 (for F2), E1 (own reads), E3/E4 (own reads + B4): 4 warps each
+      mbar_init(bar(A_N1FULL + s), 1);
+      mbar_init(bar(A_N1EMPTY + s), 8);       // C2 (for F2) + E3/E4 (for B3)
       mbar_init(bar(A_DLFULL + s), 1);
-      mbar_init(bar(A_DLEMPTY + s), 2);       // B1 and B2 issuers
-      mbar_init(bar(A_F1FULL + s), 1);
-      mbar_init(bar(A_F1EMPTY + s), 4);
+      mbar_init(bar(A_DLEMPTY + s), 8);       // C3 (for B2) + E1 (for B1), at the sample's last quad
+      mbar_init(bar(A_DTFULL + s), 4);
+      mbar_init(bar(A_DTEMPTY + s), 4);       // E3/E4 (for B3 and B4)
       mbar_init(bar(A_F2FULL + s), 1);
       mbar_init(bar(A_F2EMPTY + s), 4);
       mbar_init(bar(A_MFULL + s), 4);
-      mbar_init(bar(A_MEMPTY + s), 1);
+      mbar_init(bar(A_MEMPTY + s), 4);        // E1 (for B1)
       mbar_init(bar(A_B1FULL + s), 1);
       mbar_init(bar(A_B1EMPTY + s), 4);
-      mbar_init(bar(A_B2FULL + s), 1);
-      mbar_init(bar(A_B2EMPTY + s), 4);
-      mbar_init(bar(A_DFULL + s), 4);
-      mbar_init(bar(A_DEMPTY + s), 1);
-      mbar_init(bar(A_B3FULL + s), 1);
-      mbar_init(bar(A_B3EMPTY + s), 4);
       mbar_init(bar(A_B4FULL + s), 1);
       mbar_init(bar(A_B4EMPTY + s), 4);
     }
-    for (int s = 0; s < N1_RING; ++s) {
-      mbar_init(bar(A_N1FULL + s), 4);
-      mbar_init(bar(A_N1EMPTY + s), 2);       // F2 and B3 issuers
-    }
-    for (int s = 0; s < 3; ++s) {
-      mbar_init(bar(A_OPFULL + s), 1);
-      mbar_init(bar(A_OPEMPTY + s), 10);      // F2 and B4 issuers + the 8 epilogue warps that read Vc / Qc (ReLU masks)
-    }
+    mbar_init(bar(A_B2FULL), 1);
+    mbar_init(bar(A_B2EMPTY), 4);
+    mbar_init(bar(A_B3FULL), 1);
+    mbar_init(bar(A_B3EMPTY), 4);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -164,192 +150,189 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
   pdl_prologue_done();      // everything above touched only this CTA's shared memory / TMEM
 
   const int n_my = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int U = n_my * p.R;
+  const int NQ = p.R >> 2;                      // rank quads per sample
+  const int CQ = n_my * NQ;                     // quads of this CTA
   const int nt2 = (p.A + 3) >> 2;               // 128-row tiles over (a,g,i)
-  const int ntn = (p.N + 127) >> 7;             // 128-row tiles over n = (a,g,q16)
-  const int kn = p.N >> 4;                      // K steps over n / over (a,g,i)
-  const int ktok = (p.K + 15) >> 4;             // K steps over tokens
+  const int kn = p.N >> 4;                      // K steps over n = (a,g,q16) / over (a,g,i)
+  const int ktok = (p.K + 15) >> 4;             // K steps over regions
+  const uint32_t n1_bytes = static_cast<uint32_t>(p.A) * 4096u;
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
-      uint32_t tslot = 0, tph = 0, oslot = 0, oph = 0;
-      int r = 0, sl = 0, b = blockIdx.x;
+    if (elect_one_sync()) {
+      PROF_DECL
       auto load_dl = [&](int s_local, int bb) {
         const int slot = s_local & 1;
-        mbar_wait(bar(A_DLEMPTY + slot), ((s_local >> 1) & 1) ^ 1);
+        PWAIT(2, bar(A_DLEMPTY + slot), ((s_local >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(bar(A_DLFULL + slot), DL_BYTES);
         for (int c = 0; c < DL_CHUNKS; ++c) tma_load_3d(&tmap_dl, bar(A_DLFULL + slot), sDL + slot * DL_BYTES + c * 8192, c * 64, 0, bb);
       };
-      for (int u = 0; u < U; ++u) {
-        if (u == 0) load_dl(0, b);
-        if (r == p.R / 2 && sl + 1 < n_my) load_dl(sl + 1, b + gridDim.x);
-        if ((r & 3) == 0) {
-          mbar_wait(bar(A_OPEMPTY + oslot), oph ^ 1u);
-          mbar_arrive_expect_tx(bar(A_OPFULL + oslot), OP_BYTES);
-          const uint32_t dst = sOp + oslot * OP_BYTES;
-          tma_load_3d(&tmap_v, bar(A_OPFULL + oslot), dst + OP_V, r * 16, 0, b / p.VR);
-          tma_load_3d(&tmap_q, bar(A_OPFULL + oslot), dst + OP_Q, r * 16, 0, b);
-          tma_load_3d(&tmap_a, bar(A_OPFULL + oslot), dst + OP_A, r * 16, 0, b);
-          if (++oslot == OP_RING) { oslot = 0; oph ^= 1u; }
-        }
-        mbar_wait(bar(A_TEMPTY + tslot), tph ^ 1u);
-        mbar_arrive_expect_tx(bar(A_TFULL + tslot), T_BYTES);
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-          tma_load_3d(&tmap_t, bar(A_TFULL + tslot), sT + tslot * T_BYTES + c * 2048, c * 64, r * 16, 0);
-        if (++tslot == T_RING) { tslot = 0; tph ^= 1u; }
-        if (++r == p.R) { r = 0; ++sl; b += gridDim.x; }
+      int t = 0, sl = 0, b = blockIdx.x;
+      for (int c = 0; c < CQ; ++c) {
+        const int slot = c & 1, ph = (c >> 1) & 1;
+        if (c == 0) load_dl(0, b);
+        if (t == NQ / 2 && sl + 1 < n_my) load_dl(sl + 1, b + gridDim.x);
+        PWAIT(0, bar(A_OPEMPTY + slot), ph ^ 1);
+        TRACE(0, c);
+        mbar_arrive_expect_tx(bar(A_OPFULL + slot), OP_BYTES);
+        tma_load_3d(&tmap_v, bar(A_OPFULL + slot), sOp + slot * OP_BYTES + OP_V, t * 64, 0, b / p.VR);
+        tma_load_3d(&tmap_q, bar(A_OPFULL + slot), sOp + slot * OP_BYTES + OP_Q, t * 64, 0, b);
+        PWAIT(1, bar(A_N1EMPTY + slot), ph ^ 1);
+        mbar_arrive_expect_tx(bar(A_N1FULL + slot), n1_bytes);
+        bulk_load_1d(sN1 + slot * N1_BYTES, p.n1 + ((size_t)b * NQ + t) * n1_bytes, n1_bytes, bar(A_N1FULL + slot));
+        if (++t == NQ) { t = 0; ++sl; b += gridDim.x; }
       }
+      PROF_FLUSH(0);
     }
   } else if (warp == 1) {
-    // ------------------------------ issuer: F1 ------------------------------------
-    if (lane == 0) {
-      const uint32_t id_f1 = make_idesc_rt(128, 16, 1, 0);
-      uint32_t tslot = 0, tph = 0, oslot = 0, oph = 0;
-      int r = 0;
-      for (int u = 0; u < U; ++u) {
-        mbar_wait(bar(A_TFULL + tslot), tph);
-        if ((r & 3) == 0) mbar_wait(bar(A_OPFULL + oslot), oph);
-        mbar_wait(bar(A_F1EMPTY + (u & 1)), ((u >> 1) & 1) ^ 1);
+    // ------------------------------ issuer: B2  dM[(r4,i), n] = Vc^T dL  (depends on TMA data only, runs ahead).
+    // M = 128 with LBO = 0: accumulator lanes 64-127 repeat lanes 0-63, so all four C3 warps share the read-out ------
+    if (elect_one_sync()) {
+      const uint32_t id_b2 = make_idesc_rt(128, p.N, 1, 1);
+      PROF_DECL
+      int t = 0, sl = 0;
+      for (int c = 0; c < CQ; ++c) {
+        const int slot = c & 1, ph = (c >> 1) & 1;
+        PWAIT(0, bar(A_OPFULL + slot), ph);
+        if (t == 0) PWAIT(1, bar(A_DLFULL + (sl & 1)), (sl >> 1) & 1);
+        PWAIT(2, bar(A_B2EMPTY), (c & 1) ^ 1);
+        TRACE(1, c);
+        PROF_T0();
         tcgen05_fence_after();
-        const uint64_t db = desc_kmajor(sOp + oslot * OP_BYTES + OP_A, r & 3);
-        const uint64_t da = desc_mnmajor(sT + tslot * T_BYTES, 0, 2048);
-#pragma unroll
-        for (int t = 0; t < 4; ++t)
-          umma_bf16_ss(tmem_base + TM_F1 + (u & 1) * 64 + t * 16, da + (uint64_t)(2 * t * 2048 >> 4), db, id_f1, 0u);
-        umma_commit(bar(A_F1FULL + (u & 1)));
-        umma_commit(bar(A_TEMPTY + tslot));
-        if (++tslot == T_RING) { tslot = 0; tph ^= 1u; }
-        if (++r == p.R) r = 0;
-        if ((r & 3) == 0 && ++oslot == OP_RING) { oslot = 0; oph ^= 1u; }
+        const uint64_t da0 = desc_mnmajor(sOp + slot * OP_BYTES + OP_V, 0, 0);
+        const uint64_t db0 = desc_mnmajor(sDL + (sl & 1) * DL_BYTES, 0, 8192);
+#pragma unroll 1
+        for (int ks = 0; ks < ktok; ++ks)
+          umma_bf16_ss(tmem_base + TM_B2, da0 + (uint64_t)(ks * 2048 >> 4), db0 + (uint64_t)(ks * 2048 >> 4), id_b2, ks > 0 ? 1u : 0u);
+        umma_commit(bar(A_B2FULL));
+        PROF_ADD(3);
+        if (++t == NQ) { t = 0; ++sl; }
       }
+      PROF_FLUSH(1);
     }
   } else if (warp == 2) {
-    // ------------------------------ issuer: B2 (D^T = dL^T Vc) -- depends on TMA data only, runs ahead -------
-    if (lane == 0) {
-      const uint32_t id_b2 = make_idesc_rt(128, 16, 1, 1);
-      uint32_t oslot = 0, oph = 0;
-      int r = 0, sl = 0;
-      for (int u = 0; u < U; ++u) {
-        const uint32_t dl = sDL + (sl & 1) * DL_BYTES;
-        if ((r & 3) == 0) mbar_wait(bar(A_OPFULL + oslot), oph);
-        if (r == 0) mbar_wait(bar(A_DLFULL + (sl & 1)), (sl >> 1) & 1);
-        mbar_wait(bar(A_B2EMPTY + (u & 1)), ((u >> 1) & 1) ^ 1);
-        tcgen05_fence_after();
-        const uint64_t db0 = desc_mnmajor(sOp + oslot * OP_BYTES + OP_V + (r & 3) * 32, 0, 0);
-        for (int t = 0; t < ntn; ++t) {
-          const uint64_t da0 = desc_mnmajor(dl + 2 * t * 8192, 0, 8192);
-          for (int ks = 0; ks < ktok; ++ks)
-            umma_bf16_ss(tmem_base + TM_B2 + (u & 1) * 32 + t * 16, da0 + (uint64_t)(ks * 2048 >> 4),
-                         db0 + (uint64_t)(ks * 2048 >> 4), id_b2, ks > 0 ? 1u : 0u);
+    // ------------------------------ issuer: F2  M_r[(a,g,i), q] = N1_r Qc_r^T  (per rank) ------------------------
+    if (elect_one_sync()) {
+      const uint32_t id_f2 = make_idesc_rt(128, 16, 0, 0);
+      PROF_DECL
+      for (int c = 0; c < CQ; ++c) {
+        const int slot = c & 1, ph = (c >> 1) & 1;
+        PWAIT(0, bar(A_OPFULL + slot), ph);
+        PWAIT(1, bar(A_N1FULL + slot), ph);
+        TRACE(7, c);
+#pragma unroll 1
+        for (int s = 0; s < 4; ++s) {
+          const int u = c * 4 + s;
+          PWAIT(2, bar(A_F2EMPTY + (u & 1)), ((u >> 1) & 1) ^ 1);
+          PROF_T0();
+          tcgen05_fence_after();
+          const uint64_t da = desc_kmajor(sN1 + slot * N1_BYTES, s);
+          const uint64_t db = desc_kmajor(sOp + slot * OP_BYTES + OP_Q, s);
+#pragma unroll 1
+          for (int t2 = 0; t2 < nt2; ++t2)
+            umma_bf16_ss(tmem_base + TM_F2 + (u & 1) * 32 + t2 * 16, da + (uint64_t)(t2 * 16384 >> 4), db, id_f2, 0u);
+          umma_commit(bar(A_F2FULL + (u & 1)));
+          PROF_ADD(3);
         }
-        umma_commit(bar(A_B2FULL + (u & 1)));
-        if (r == p.R - 1) umma_commit(bar(A_DLEMPTY + (sl & 1)));
-        if (++r == p.R) { r = 0; ++sl; }
-        if ((r & 3) == 0 && ++oslot == OP_RING) { oslot = 0; oph ^= 1u; }
       }
-    }
-  } else if (warp == 16) {
-    // ------------------------------ issuer: B1 (dVc = dL M^T) ---------------------------------------------
-    if (lane == 0) {
-      const uint32_t id_b1 = make_idesc_rt(128, 16, 0, 0);
-      int r = 0, sl = 0;
-      for (int u = 0; u < U; ++u) {
-        const uint32_t dl = sDL + (sl & 1) * DL_BYTES;
-        if (r == 0) mbar_wait(bar(A_DLFULL + (sl & 1)), (sl >> 1) & 1);
-        mbar_wait(bar(A_MFULL + (u & 1)), (u >> 1) & 1);
-        mbar_wait(bar(A_B1EMPTY + (u & 1)), ((u >> 1) & 1) ^ 1);
-        tcgen05_fence_after();
-        const uint64_t da0 = desc_kmajor(dl, 0), db0 = desc_kmajor(sM + (u & 1) * M_BYTES, 0);
-        for (int ks = 0; ks < kn; ++ks)
-          umma_bf16_ss(tmem_base + TM_B1 + (u & 1) * 16, da0 + (uint64_t)(((ks >> 2) * 8192 + (ks & 3) * 32) >> 4),
-                       db0 + (uint64_t)(((ks >> 2) * 2048 + (ks & 3) * 32) >> 4), id_b1, ks > 0 ? 1u : 0u);
-        umma_commit(bar(A_B1FULL + (u & 1)));
-        umma_commit(bar(A_MEMPTY + (u & 1)));
-        if (r == p.R - 1) umma_commit(bar(A_DLEMPTY + (sl & 1)));
-        if (++r == p.R) { r = 0; ++sl; }
-      }
+      PROF_FLUSH(2);
     }
   } else if (warp == 3) {
-    // ------------------------------ issuer: F2 (M = N1 Qc^T) ------------------------------------------------
-    if (lane == 0) {
-      const uint32_t id_f2 = make_idesc_rt(128, 16, 0, 0);
-      uint32_t oslot = 0, oph = 0;
-      int r = 0;
-      for (int u = 0; u < U; ++u) {
-        if ((r & 3) == 0) mbar_wait(bar(A_OPFULL + oslot), oph);
-        mbar_wait(bar(A_N1FULL + (u & 7)), (u >> 3) & 1);
-        mbar_wait(bar(A_F2EMPTY + (u & 1)), ((u >> 1) & 1) ^ 1);
+    // ------------------------------ issuer: B1  dVc[k, (r4,i)] = dL Mq^T  (per quad) ------------------------------
+    if (elect_one_sync()) {
+      const uint32_t id_b1 = make_idesc_rt(128, 64, 0, 0);
+      PROF_DECL
+      int t = 0, sl = 0;
+      for (int c = 0; c < CQ; ++c) {
+        const int slot = c & 1, ph = (c >> 1) & 1;
+        if (t == 0) PWAIT(0, bar(A_DLFULL + (sl & 1)), (sl >> 1) & 1);
+        PWAIT(1, bar(A_MFULL + slot), ph);
+        PWAIT(2, bar(A_B1EMPTY + slot), ph ^ 1);
+        TRACE(9, c);
+        PROF_T0();
         tcgen05_fence_after();
-        const uint64_t db = desc_kmajor(sOp + oslot * OP_BYTES + OP_Q, r & 3);
-        const uint64_t da = desc_kmajor(sN1 + ((u >> 2) & 1) * N1_BYTES, u & 3);     // K step = rank within the quad tile
-        for (int t2 = 0; t2 < nt2; ++t2)
-          umma_bf16_ss(tmem_base + TM_F2 + (u & 1) * 32 + t2 * 16, da + (uint64_t)(t2 * 16384 >> 4), db, id_f2, 0u);
-        umma_commit(bar(A_F2FULL + (u & 1)));
-        umma_commit(bar(A_N1EMPTY + (u & 7)));
-        if ((r & 3) == 3) umma_commit(bar(A_OPEMPTY + oslot));
-        if (++r == p.R) r = 0;
-        if ((r & 3) == 0 && ++oslot == OP_RING) { oslot = 0; oph ^= 1u; }
+        const uint64_t da0 = desc_kmajor(sDL + (sl & 1) * DL_BYTES, 0), db0 = desc_kmajor(sM + slot * MQ_BYTES, 0);
+#pragma unroll 1
+        for (int ks = 0; ks < kn; ++ks) {
+          const uint64_t o = (uint64_t)(((ks >> 2) * 8192 + (ks & 3) * 32) >> 4);
+          umma_bf16_ss(tmem_base + TM_B1 + slot * 64, da0 + o, db0 + o, id_b1, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(bar(A_B1FULL + slot));
+        PROF_ADD(3);
+        if (++t == NQ) { t = 0; ++sl; }
       }
+      PROF_FLUSH(3);
     }
-  } else if (warp == 17) {
-    // ------------------------------ issuer: B3 (dQc = D N1), B4 (dN1 = D^T Qc) ---------------------------------
-    if (lane == 0) {
-      const uint32_t id_b3 = make_idesc_rt(128, 16, 0, 1);
-      const uint32_t id_b4 = make_idesc_rt(128, 16, 1, 1);
-      uint32_t oslot = 0, oph = 0;
-      int r = 0;
-      for (int u = 0; u < U; ++u) {
-        const uint32_t op = sOp + oslot * OP_BYTES;
-        if ((r & 3) == 0) mbar_wait(bar(A_OPFULL + oslot), oph);
-        mbar_wait(bar(A_N1FULL + (u & 7)), (u >> 3) & 1);
-        mbar_wait(bar(A_DFULL + (u & 1)), (u >> 1) & 1);
-        mbar_wait(bar(A_B3EMPTY + (u & 1)), ((u >> 1) & 1) ^ 1);
-        mbar_wait(bar(A_B4EMPTY + (u & 1)), ((u >> 1) & 1) ^ 1);
+  } else if (warp == 4) {
+    // ------------------------------ issuer: B3  dQc^T-blocks[(r4',q), (r4,j)] = Dt^T N1 (per quad; the diagonal blocks
+    // r' = r are dQc_r), B4  dN1_r[(a,g,i), j] = Dt_r Qc_r (per rank) ------------------------------------------------
+    if (elect_one_sync()) {
+      const uint32_t id_b3 = make_idesc_rt(128, 64, 1, 1);
+      const uint32_t id_b4 = make_idesc_rt(128, 16, 0, 1);
+      PROF_DECL
+      for (int c = 0; c < CQ; ++c) {
+        const int slot = c & 1, ph = (c >> 1) & 1;
+        const uint32_t dt = sDT + slot * DT_BYTES, op = sOp + slot * OP_BYTES;
+        PWAIT(0, bar(A_OPFULL + slot), ph);
+        PWAIT(1, bar(A_N1FULL + slot), ph);
+        PWAIT(2, bar(A_DTFULL + slot), ph);
+        PWAIT(3, bar(A_B3EMPTY), (c & 1) ^ 1);
+        TRACE(4, c);
+        PROF_T0();
         tcgen05_fence_after();
-        const uint32_t dt = sD + (u & 1) * D_BYTES;
-        const uint64_t da0 = desc_kmajor(dt, 0), db0 = desc_mnmajor(sN1 + ((u >> 2) & 1) * N1_BYTES + (u & 3) * 32, 0, 0);
+        const uint64_t da0 = desc_mnmajor(dt, 0, 0), db0 = desc_mnmajor(sN1 + slot * N1_BYTES, 0, 0);
+#pragma unroll 1
         for (int ks = 0; ks < kn; ++ks)
-          umma_bf16_ss(tmem_base + TM_B3 + (u & 1) * 16, da0 + (uint64_t)(((ks >> 2) * 2048 + (ks & 3) * 32) >> 4),
-                       db0 + (uint64_t)((ks * 2048) >> 4), id_b3, ks > 0 ? 1u : 0u);
-        umma_commit(bar(A_B3FULL + (u & 1)));
-        const uint64_t dq = desc_mnmajor(op + OP_Q + (r & 3) * 32, 0, 0);
-        for (int t = 0; t < nt2; ++t)
-          umma_bf16_ss(tmem_base + TM_B4 + (u & 1) * 32 + t * 16, desc_mnmajor(dt + 2 * t * 2048, 0, 2048), dq, id_b4, 0u);
-        umma_commit(bar(A_B4FULL + (u & 1)));
-        umma_commit(bar(A_DEMPTY + (u & 1)));
-        umma_commit(bar(A_N1EMPTY + (u & 7)));
-        if ((r & 3) == 3) umma_commit(bar(A_OPEMPTY + oslot));
-        if (++r == p.R) r = 0;
-        if ((r & 3) == 0 && ++oslot == OP_RING) { oslot = 0; oph ^= 1u; }
+          umma_bf16_ss(tmem_base + TM_B3, da0 + (uint64_t)(ks * 2048 >> 4), db0 + (uint64_t)(ks * 2048 >> 4), id_b3, ks > 0 ? 1u : 0u);
+        umma_commit(bar(A_B3FULL));
+        PROF_ADD(5);
+#pragma unroll 1
+        for (int s = 0; s < 4; ++s) {
+          const int u = c * 4 + s;
+          PWAIT(4, bar(A_B4EMPTY + (u & 1)), ((u >> 1) & 1) ^ 1);
+          PROF_T0();
+          tcgen05_fence_after();
+          const uint64_t dq = desc_mnmajor(op + OP_Q + s * 32, 0, 0);
+#pragma unroll 1
+          for (int t2 = 0; t2 < nt2; ++t2)
+            umma_bf16_ss(tmem_base + TM_B4 + (u & 1) * 32 + t2 * 16, desc_kmajor(dt + t2 * 16384, s), dq, id_b4, 0u);
+          umma_commit(bar(A_B4FULL + (u & 1)));
+          PROF_ADD(5);
+        }
       }
+      PROF_FLUSH(4);
     }
-  } else if (warp < 8) {
-    // ------------------------------ G1: N1^T (TMEM) -> N1 tile rows (a,g,i), columns j --------------
+  } else if (warp < 9) {
+    // ------------------------------ C3: dM (TMEM, lane (r4,i), column n = (a,g,q16)) -> Dt tile rows (a,g,i), columns
+    // (r4,q16).  Lanes 64-127 repeat lanes 0-63: warps on lanes 0-63 convert (a,g) < A, the others (a,g) >= A. ------
     const int qd = warp & 3, L = qd * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
-    const int j = L & 15, g = (L >> 4) & 1;
-    for (int u = 0; u < U; ++u) {
-      const int slot = u & 1;
-      mbar_wait(bar(A_F1FULL + slot), (u >> 1) & 1);
+    const int r4 = (L & 63) >> 4, i = L & 15, ag0 = (L >> 6) * p.A;
+    PROF_DECL
+    int t = 0, sl = 0;
+    for (int c = 0; c < CQ; ++c) {
+      const int slot = c & 1, ph = (c >> 1) & 1;
+      PWAIT(0, bar(A_B2FULL), c & 1);
       tcgen05_fence_after();
-      mbar_wait(bar(A_N1EMPTY + (u & 7)), ((u >> 3) & 1) ^ 1);
-      const uint32_t n1 = sN1 + ((u >> 2) & 1) * N1_BYTES;
-      const uint32_t sub = u & 3;                                // rank within the quad tile: columns sub * 16 + j
-      uint32_t v[4][8];
+      PWAIT(1, bar(A_DTEMPTY + slot), ph ^ 1);
+      if (warp == 5) TRACE(2, c);
+      PROF_T0();
+      const uint32_t dt = sDT + slot * DT_BYTES;
+      for (int x = 0; x < p.A; x += 2) {
+        const int ag = ag0 + x;
+        uint32_t vv[2][16];
+        tmem_ld_32x32b_x16(tmem_base + lane_addr + TM_B2 + ag * 16, vv[0]);
+        if (x + 1 < p.A) tmem_ld_32x32b_x16(tmem_base + lane_addr + TM_B2 + ag * 16 + 16, vv[1]);
+        tmem_wait_ld();
 #pragma unroll
-      for (int t = 0; t < 4; ++t) tmem_ld_32x32b_x8(tmem_base + lane_addr + TM_F1 + slot * 64 + t * 16, v[t]);
-      tmem_wait_ld();
+        for (int y2 = 0; y2 < 2; ++y2) {
+          if (x + y2 < p.A) {
+            uint32_t pk[8];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int i = 4 * t + (L >> 5);
-        const uint32_t off = (g * 2 + (i >> 3)) * 1024u + (i & 7) * 128u + (((sub * 2 + ((j >> 3) & 1)) ^ (i & 7)) << 4) + (j & 7) * 2u;
-#pragma unroll
-        for (int a = 0; a < 8; ++a) {
-          if (a < p.A) {
-            const __nv_bfloat16 h = __float2bfloat16(__uint_as_float(v[t][a]));
-            st_shared_u16(n1 + a * 4096u + off, *reinterpret_cast<const uint16_t*>(&h));
+            for (int y = 0; y < 8; ++y) pk[y] = pack_bf16x2(__uint_as_float(vv[y2][2 * y]), __uint_as_float(vv[y2][2 * y + 1]));
+            const uint32_t row = (ag + y2) * 16 + i;
+            st_shared_v4(dt + sw128_off(row, r4 * 16), pk[0], pk[1], pk[2], pk[3]);
+            st_shared_v4(dt + sw128_off(row, r4 * 16 + 8), pk[4], pk[5], pk[6], pk[7]);
           }
         }
       }
@@ -357,173 +340,219 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(bar(A_N1FULL + (u & 7)));
-        mbar_arrive(bar(A_F1EMPTY + slot));
+        mbar_arrive(bar(A_DTFULL + slot));
+        mbar_arrive(bar(A_B2EMPTY));
+        mbar_arrive(bar(A_OPEMPTY + slot));                        // B2 has retired: it no longer reads the Vc chunk ...
+        if (t == NQ - 1) mbar_arrive(bar(A_DLEMPTY + (sl & 1)));   // ... nor, after the sample's last quad, the dL tile
       }
+      PROF_ADD(2);
+      if (warp == 5) TRACE(3, c);
+      if (++t == NQ) { t = 0; ++sl; }
     }
-  } else if (warp < 12) {
-    // ------------------------------ G2: M (TMEM) -> M tile [i][(a,g,q16)].  (The D^T -> D tile conversion used to
-    // live here too and made this group the busiest stage of the pipeline; it now runs on the E1 warps, which
-    // otherwise wait for B1 most of the time.) -------
+    if (warp == 5) PROF_FLUSH(5);
+  } else if (warp < 13) {
+    // ------------------------------ C2: M_r (TMEM, lane (a,g,i), column q16) -> M quad tile rows (r4,i), columns n ------
     const int qd = warp & 3, L = qd * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
-    for (int u = 0; u < U; ++u) {
-      const int slot = u & 1;
-      {   // C2
-        mbar_wait(bar(A_F2FULL + slot), (u >> 1) & 1);
+    PROF_DECL
+    for (int c = 0; c < CQ; ++c) {
+      const int slot = c & 1, ph = (c >> 1) & 1;
+      const uint32_t mt = sM + slot * MQ_BYTES;
+#pragma unroll 1
+      for (int s = 0; s < 4; ++s) {
+        const int u = c * 4 + s;
+        PWAIT(0, bar(A_F2FULL + (u & 1)), (u >> 1) & 1);
         tcgen05_fence_after();
-        mbar_wait(bar(A_MEMPTY + slot), ((u >> 1) & 1) ^ 1);
-        const uint32_t mt = sM + slot * M_BYTES;
-        for (int t2 = 0; t2 < nt2; ++t2) {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(tmem_base + lane_addr + TM_F2 + slot * 32 + t2 * 16, v);
-          tmem_wait_ld();
+        if (s == 0) PWAIT(1, bar(A_MEMPTY + slot), ph ^ 1);
+        PROF_T0();
+        uint32_t vv[2][16];
+        tmem_ld_32x32b_x16(tmem_base + lane_addr + TM_F2 + (u & 1) * 32, vv[0]);
+        if (nt2 > 1) tmem_ld_32x32b_x16(tmem_base + lane_addr + TM_F2 + (u & 1) * 32 + 16, vv[1]);
+        tmem_wait_ld();
+#pragma unroll
+        for (int t2 = 0; t2 < 2; ++t2) {
           const int rho = t2 * 128 + L;
           const int a = rho >> 5, i = rho & 15;
-          if (a < p.A) {
+          if (t2 < nt2 && a < p.A) {
             const int ag = rho >> 4;
             uint32_t pk[8];
 #pragma unroll
-            for (int x = 0; x < 8; ++x) pk[x] = pack_bf16x2(__uint_as_float(v[2 * x]), __uint_as_float(v[2 * x + 1]));
-            const uint32_t tile = mt + (ag >> 2) * 2048u;
+            for (int y = 0; y < 8; ++y) pk[y] = pack_bf16x2(__uint_as_float(vv[t2][2 * y]), __uint_as_float(vv[t2][2 * y + 1]));
+            const uint32_t tile = mt + (ag >> 2) * 8192u;
             const uint32_t c0 = (ag & 3) * 16;
-            st_shared_v4(tile + sw128_off(i, c0), pk[0], pk[1], pk[2], pk[3]);
-            st_shared_v4(tile + sw128_off(i, c0 + 8), pk[4], pk[5], pk[6], pk[7]);
+            st_shared_v4(tile + sw128_off(s * 16 + i, c0), pk[0], pk[1], pk[2], pk[3]);
+            st_shared_v4(tile + sw128_off(s * 16 + i, c0 + 8), pk[4], pk[5], pk[6], pk[7]);
           }
         }
         fence_proxy_async_smem();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(bar(A_MFULL + slot));
-          mbar_arrive(bar(A_F2EMPTY + slot));
+          mbar_arrive(bar(A_F2EMPTY + (u & 1)));
+          if (s == 3) {
+            mbar_arrive(bar(A_MFULL + slot));
+            mbar_arrive(bar(A_N1EMPTY + slot));      // F2 of the whole quad has retired: N1 tile and Qc chunk are free of it
+            mbar_arrive(bar(A_OPEMPTY + slot));
+          }
         }
+        PROF_ADD(2);
       }
+      if (warp == 9) TRACE(8, c);
     }
-  } else if (warp < 16 || warp >= 18) {
-    // warps 12-15: E1 (dVc -> dzv); warps 18-21: E3 (dQc -> dzq) and E4 (dN1 -> workspace)
-    const bool do_e1 = warp < 16;
-    // ------------------------------ G3 / G4: epilogues  dVc -> dzv, dQc -> dzq, dN1 -> workspace -----------
+    if (warp == 9) PROF_FLUSH(6);
+  } else if (warp < 17) {
+    // ------------------------------ E1: dVc[k, (r4,i)] -> ReLU mask -> dzv (128 contiguous bytes per region) ------
     const int qd = warp & 3, L = qd * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
     const int RD = p.R * 16;
-    uint32_t oslot = 0, oph = 0;
-    int r = 0, b = blockIdx.x;
-    for (int u = 0; u < U; ++u) {
-      const int slot = u & 1;
-      const uint32_t op = sOp + oslot * OP_BYTES;
-      if ((r & 3) == 0) mbar_wait(bar(A_OPFULL + oslot), oph);
-      // activation chunk (16 values of rank r) of row `row` of an OP tile, de-swizzled
-      auto act16 = [&](uint32_t tile, int row, float (&out)[16]) {
-        uint32_t w0[4], w1[4];
-        const uint32_t rb = tile + (row >> 3) * 1024u + (row & 7) * 128u;
-        ld_shared_v4(rb + ((((r & 3) * 2) ^ (row & 7)) << 4), w0);
-        ld_shared_v4(rb + ((((r & 3) * 2 + 1) ^ (row & 7)) << 4), w1);
-#pragma unroll
-        for (int x = 0; x < 4; ++x) {
-          const float2 f0 = unpack_bf16x2(w0[x]), f1 = unpack_bf16x2(w1[x]);
-          out[2 * x] = f0.x; out[2 * x + 1] = f0.y; out[8 + 2 * x] = f1.x; out[8 + 2 * x + 1] = f1.y;
-        }
-      };
-      if (do_e1) {   // C3: D^T (TMEM) -> D tile [q][(a,g,i)]; B2 runs ahead of the chain, so this is ready early
-        mbar_wait(bar(A_B2FULL + slot), (u >> 1) & 1);
-        tcgen05_fence_after();
-        mbar_wait(bar(A_DEMPTY + slot), ((u >> 1) & 1) ^ 1);
-        const uint32_t dt = sD + slot * D_BYTES;
-        for (int t = 0; t < ntn; ++t) {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(tmem_base + lane_addr + TM_B2 + slot * 32 + t * 16, v);
-          tmem_wait_ld();
-          const int n = t * 128 + L;
-          if (n < p.N) {
-            const int ag = n >> 4, q = n & 15;
-            uint32_t pk[8];
-#pragma unroll
-            for (int x = 0; x < 8; ++x) pk[x] = pack_bf16x2(__uint_as_float(v[2 * x]), __uint_as_float(v[2 * x + 1]));
-            const uint32_t tile = dt + (ag >> 2) * 2048u;
-            const uint32_t c0 = (ag & 3) * 16;
-            st_shared_v4(tile + sw128_off(q, c0), pk[0], pk[1], pk[2], pk[3]);
-            st_shared_v4(tile + sw128_off(q, c0 + 8), pk[4], pk[5], pk[6], pk[7]);
-          }
-        }
-        fence_proxy_async_smem();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(bar(A_DFULL + slot));
-          mbar_arrive(bar(A_B2EMPTY + slot));
-        }
-      }
-      if (do_e1) {   // E1: dVc[k, i]
-        mbar_wait(bar(A_B1FULL + slot), (u >> 1) & 1);
-        tcgen05_fence_after();
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(tmem_base + lane_addr + TM_B1 + slot * 16, v);
+    PROF_DECL
+    int t = 0, sl = 0, b = blockIdx.x;
+    for (int c = 0; c < CQ; ++c) {
+      const int slot = c & 1, ph = (c >> 1) & 1;
+      PWAIT(0, bar(A_OPFULL + slot), ph);
+      PWAIT(1, bar(A_B1FULL + slot), ph);
+      if (warp == 13) TRACE(10, c);
+      PROF_T0();
+      tcgen05_fence_after();
+      const uint32_t rb = sOp + slot * OP_BYTES + OP_V + (L >> 3) * 1024u + (L & 7) * 128u;      // row k = L of the Vc chunk
+      bf16* dst = p.dzv + ((size_t)b * p.K + L) * RD + t * 64;
+#pragma unroll 1
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t v[32];
+#ifdef CTI_PROF
+        const unsigned long long tq0 = clock64();
+#endif
+        tmem_ld_32x32b_x32(tmem_base + lane_addr + TM_B1 + slot * 64 + hh * 32, v);
         tmem_wait_ld();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(A_B1EMPTY + slot));
-        float gv[16];
-        if (L < p.K) {
-          float act[16];
-          act16(op + OP_V, L, act);
+#ifdef CTI_PROF
+        prof_acc[3] += clock64() - tq0;
+#endif
 #pragma unroll
-          for (int x = 0; x < 16; ++x) gv[x] = act[x] > 0.f ? __uint_as_float(v[x]) : 0.f;
-          uint4 o0, o1;
-          o0.x = pack_bf16x2(gv[0], gv[1]); o0.y = pack_bf16x2(gv[2], gv[3]); o0.z = pack_bf16x2(gv[4], gv[5]); o0.w = pack_bf16x2(gv[6], gv[7]);
-          o1.x = pack_bf16x2(gv[8], gv[9]); o1.y = pack_bf16x2(gv[10], gv[11]); o1.z = pack_bf16x2(gv[12], gv[13]); o1.w = pack_bf16x2(gv[14], gv[15]);
-          uint4* dst = reinterpret_cast<uint4*>(p.dzv + ((size_t)b * p.K + L) * RD + r * 16);
-          dst[0] = o0;
-          dst[1] = o1;
-        } else {
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int h = hh * 2 + h2;
+          if (L < p.K) {
+            float gv[16];
+            uint32_t w0[4], w1[4];
+            ld_shared_v4(rb + (((h * 2) ^ (L & 7)) << 4), w0);
+            ld_shared_v4(rb + (((h * 2 + 1) ^ (L & 7)) << 4), w1);
 #pragma unroll
-          for (int x = 0; x < 16; ++x) gv[x] = 0.f;
-        }
-        if (qd * 32 < p.K) {          // warp-uniform: this warp holds valid regions
-          const float s = warp_colsum16(gv, lane);
-          if ((lane & 1) == 0) atomicAdd(db_acc + r * 16 + (lane >> 1), s);
-        }
-      }
-      if (!do_e1) {   // E3: dQc[q, j]
-        mbar_wait(bar(A_B3FULL + slot), (u >> 1) & 1);
-        tcgen05_fence_after();
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(tmem_base + lane_addr + TM_B3 + slot * 16, v);
-        tmem_wait_ld();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(A_B3EMPTY + slot));
-        if (qd == 0) {
-          float gv[16];
-          if (L < p.Q) {
-            float act[16];
-            act16(op + OP_Q, L, act);
-#pragma unroll
-            for (int x = 0; x < 16; ++x) gv[x] = act[x] > 0.f ? __uint_as_float(v[x]) : 0.f;
+            for (int x = 0; x < 4; ++x) {
+              const float2 f0 = unpack_bf16x2(w0[x]), f1 = unpack_bf16x2(w1[x]);
+              gv[2 * x] = f0.x > 0.f ? __uint_as_float(v[h2 * 16 + 2 * x]) : 0.f;
+              gv[2 * x + 1] = f0.y > 0.f ? __uint_as_float(v[h2 * 16 + 2 * x + 1]) : 0.f;
+              gv[8 + 2 * x] = f1.x > 0.f ? __uint_as_float(v[h2 * 16 + 8 + 2 * x]) : 0.f;
+              gv[8 + 2 * x + 1] = f1.y > 0.f ? __uint_as_float(v[h2 * 16 + 8 + 2 * x + 1]) : 0.f;
+            }
             uint4 o0, o1;
             o0.x = pack_bf16x2(gv[0], gv[1]); o0.y = pack_bf16x2(gv[2], gv[3]); o0.z = pack_bf16x2(gv[4], gv[5]); o0.w = pack_bf16x2(gv[6], gv[7]);
             o1.x = pack_bf16x2(gv[8], gv[9]); o1.y = pack_bf16x2(gv[10], gv[11]); o1.z = pack_bf16x2(gv[12], gv[13]); o1.w = pack_bf16x2(gv[14], gv[15]);
-            uint4* dst = reinterpret_cast<uint4*>(p.dzq + ((size_t)b * p.Q + L) * RD + r * 16);
-            dst[0] = o0;
-            dst[1] = o1;
-          } else {
-#pragma unroll
-            for (int x = 0; x < 16; ++x) gv[x] = 0.f;
+            reinterpret_cast<uint4*>(dst + h * 16)[0] = o0;
+            reinterpret_cast<uint4*>(dst + h * 16)[1] = o1;
           }
-          const float s = warp_colsum16(gv, lane);
-          if ((lane & 1) == 0) atomicAdd(db_acc + DB_FLOATS + r * 16 + (lane >> 1), s);
         }
       }
-      if (!do_e1) {   // E4: dN1[(a,g,i), j] -> workspace [b][r][a][(i,g,j)] bf16
-        mbar_wait(bar(A_B4FULL + slot), (u >> 1) & 1);
-        tcgen05_fence_after();
-        for (int t = 0; t < nt2; ++t) {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(tmem_base + lane_addr + TM_B4 + slot * 32 + t * 16, v);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar(A_B1EMPTY + slot));
+        mbar_arrive(bar(A_MEMPTY + slot));                         // B1 has retired: the M quad tile is free ...
+        mbar_arrive(bar(A_OPEMPTY + slot));
+        if (t == NQ - 1) mbar_arrive(bar(A_DLEMPTY + (sl & 1)));   // ... and, after the last quad, the dL tile
+      }
+      PROF_ADD(2);
+      if (warp == 13) TRACE(11, c);
+      if (++t == NQ) { t = 0; ++sl; b += gridDim.x; }
+    }
+    if (warp == 13) PROF_FLUSH(7);
+  } else {
+    // ------------------------------ E3: dQc_r[q, j] (diagonal blocks of B3) -> ReLU mask -> dzq;
+    //                                E4: dN1_r[(a,g,i), j] -> bf16 workspace [b][r][a][(i,g,j)] ------------------------
+    const int qd = warp & 3, L = qd * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
+    const int RD = p.R * 16;
+    PROF_DECL
+    int t = 0, b = blockIdx.x;
+    for (int c = 0; c < CQ; ++c) {
+      const int slot = c & 1, ph = (c >> 1) & 1;
+      PWAIT(0, bar(A_OPFULL + slot), ph);
+      PWAIT(1, bar(A_B3FULL), c & 1);
+      if (warp == 17) TRACE(5, c);
+      PROF_T0();
+      tcgen05_fence_after();
+      {
+        uint32_t v[32];
+        if (qd < 2) {
+#ifdef CTI_PROF
+          const unsigned long long tq0 = clock64();
+#endif
+          tmem_ld_32x32b_x32(tmem_base + lane_addr + TM_B3 + qd * 32, v);      // blocks r' = 2 qd (lanes 0-15), 2 qd + 1 (16-31)
           tmem_wait_ld();
-          const int rho = t * 128 + L;
+#ifdef CTI_PROF
+          prof_acc[5] += clock64() - tq0;
+#endif
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(A_B3EMPTY));
+#ifdef CTI_PROF
+        const unsigned long long tq1 = clock64();
+#endif
+        if (qd < 2) {
+          const int rr = L >> 4, q = L & 15;          // rank within the quad, question token
+          const bool hi = lane & 16;
+          if (q < p.Q) {
+            float gv[16];
+            const uint32_t rb = sOp + slot * OP_BYTES + OP_Q + (q >> 3) * 1024u + (q & 7) * 128u;
+            uint32_t w0[4], w1[4];
+            ld_shared_v4(rb + (((rr * 2) ^ (q & 7)) << 4), w0);
+            ld_shared_v4(rb + (((rr * 2 + 1) ^ (q & 7)) << 4), w1);
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+              const float2 f0 = unpack_bf16x2(w0[x]), f1 = unpack_bf16x2(w1[x]);
+              gv[2 * x] = f0.x > 0.f ? __uint_as_float(hi ? v[16 + 2 * x] : v[2 * x]) : 0.f;
+              gv[2 * x + 1] = f0.y > 0.f ? __uint_as_float(hi ? v[16 + 2 * x + 1] : v[2 * x + 1]) : 0.f;
+              gv[8 + 2 * x] = f1.x > 0.f ? __uint_as_float(hi ? v[24 + 2 * x] : v[8 + 2 * x]) : 0.f;
+              gv[8 + 2 * x + 1] = f1.y > 0.f ? __uint_as_float(hi ? v[24 + 2 * x + 1] : v[8 + 2 * x + 1]) : 0.f;
+            }
+            uint4 o0, o1;
+            o0.x = pack_bf16x2(gv[0], gv[1]); o0.y = pack_bf16x2(gv[2], gv[3]); o0.z = pack_bf16x2(gv[4], gv[5]); o0.w = pack_bf16x2(gv[6], gv[7]);
+            o1.x = pack_bf16x2(gv[8], gv[9]); o1.y = pack_bf16x2(gv[10], gv[11]); o1.z = pack_bf16x2(gv[12], gv[13]); o1.w = pack_bf16x2(gv[14], gv[15]);
+            uint4* dst = reinterpret_cast<uint4*>(p.dzq + ((size_t)b * p.Q + q) * RD + (t * 4 + rr) * 16);
+            dst[0] = o0;
+            dst[1] = o1;
+          }
+#ifdef CTI_PROF
+          prof_acc[6] += clock64() - tq1;
+#endif
+        }
+      }
+      PROF_ADD(2);
+#pragma unroll 1
+      for (int s = 0; s < 4; ++s) {
+        const int u = c * 4 + s, r = t * 4 + s;
+        PWAIT(3, bar(A_B4FULL + (u & 1)), (u >> 1) & 1);
+        PROF_T0();
+        tcgen05_fence_after();
+        uint32_t vv[2][16];
+        tmem_ld_32x32b_x16(tmem_base + lane_addr + TM_B4 + (u & 1) * 32, vv[0]);
+        if (nt2 > 1) tmem_ld_32x32b_x16(tmem_base + lane_addr + TM_B4 + (u & 1) * 32 + 16, vv[1]);
+        tmem_wait_ld();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(bar(A_B4EMPTY + (u & 1)));
+          if (s == 3) {      // the issuer's B3 and B4 of this quad have all retired
+            mbar_arrive(bar(A_DTEMPTY + slot));
+            mbar_arrive(bar(A_N1EMPTY + slot));
+            mbar_arrive(bar(A_OPEMPTY + slot));
+          }
+        }
+#pragma unroll
+        for (int t2 = 0; t2 < 2; ++t2) {
+          const uint32_t (&v)[16] = vv[t2];
+          const int rho = t2 * 128 + L;
           const int a = rho >> 5, g = (rho >> 4) & 1, i = rho & 15;
-          if (a < p.A) {
+          if (t2 < nt2 && a < p.A) {
             uint4 o0, o1;
             o0.x = pack_bf16x2(__uint_as_float(v[0]), __uint_as_float(v[1]));
             o0.y = pack_bf16x2(__uint_as_float(v[2]), __uint_as_float(v[3]));
@@ -538,25 +567,16 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
             dst[1] = o1;
           }
         }
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(A_B4EMPTY + slot));
+        PROF_ADD(4);
       }
-      if ((r & 3) == 3) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(A_OPEMPTY + oslot));
-      }
-      if (++r == p.R) { r = 0; b += gridDim.x; }
-      if ((r & 3) == 0 && ++oslot == OP_RING) { oslot = 0; oph ^= 1u; }
+      if (warp == 17) TRACE(6, c);
+      if (++t == NQ) { t = 0; b += gridDim.x; }
     }
+    if (warp == 17) PROF_FLUSH(8);
   }
 
   tcgen05_fence_before();
   __syncthreads();
-  for (int i = threadIdx.x; i < p.R * 16; i += kThreads1) {
-    atomicAdd(p.dbv + i, db_acc[i]);
-    atomicAdd(p.dbq + i, db_acc[DB_FLOATS + i]);
-  }
   if (warp == 2) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -634,7 +654,7 @@ trilinear_bwd2_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
   const int n_oct = (n_my + OCT - 1) / OCT;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_arrive_expect_tx(bar(C_TTFULL), T_BYTES);
 #pragma unroll
       for (int c = 0; c < 8; ++c) tma_load_3d(&tmap_t, bar(C_TTFULL), sT + c * 2048, c * 64, r * 16, 0);
@@ -653,7 +673,7 @@ trilinear_bwd2_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
       }
     }
   } else if (warp == 1 || warp == 2 || warp == 3 || warp == 9) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const int w = warp == 9 ? 3 : warp - 1;                 // issuer index: K steps 8w .. 8w+7 of B5, tile w of B6
       const uint32_t id_b5 = make_idesc_rt(64, 64, 0, 0);     // only rows l < 16 are valid: M = 64 halves the A-operand read
       const uint32_t id_b6 = make_idesc_rt(128, 16, 1, 1);
@@ -767,21 +787,32 @@ trilinear_bwd2_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __gri
 
 }  // namespace
 
+int debug_prof_read_bwd1(unsigned long long* host_dst, int n) {
+#ifdef CTI_PROF
+  if (n == 16 * 128) return (int)cudaMemcpyFromSymbol(host_dst, g_trace1, sizeof(unsigned long long) * 16 * 128);
+  return (int)cudaMemcpyFromSymbol(host_dst, g_prof1, sizeof(unsigned long long) * (n < 148 * 128 ? n : 148 * 128));
+#else
+  (void)host_dst; (void)n;
+  return -1;
+#endif
+}
+
 size_t trilinear_bwd_tc_workspace(TriDims d) {        // dN1 [B][R][A][512] bf16
   return (size_t)d.B * d.R * d.A * 512 * sizeof(bf16);
 }
 
-// Returns -100 when the shape is outside the fast path.  dlm: [B][K][32 A] bf16 (gradient of the logits).
-int trilinear_bwd_tc(const bf16* vc, const bf16* qc, const bf16* ac, const bf16* tpack, const bf16* dlm, bf16* dn1,
-                     bf16* dzv, bf16* dzq, bf16* dza, float* dbv, float* dbq, float* dba, float* dtpack, TriDims d,
-                     cudaStream_t stream) {
+// Returns -100 when the shape is outside the fast path (or the forward did not save its N1 tiles).
+// dlm: [B][K][32 A] bf16 (gradient of the logits); n1: the tiles written by trilinear_fwd_tc (trilinear_n1_bytes).
+int trilinear_bwd_tc(const bf16* vc, const bf16* qc, const bf16* ac, const bf16* tpack, const bf16* dlm, const void* n1,
+                     bf16* dn1, bf16* dzv, bf16* dzq, bf16* dza, float* dbv, float* dbq, float* dba, float* dtpack,
+                     TriDims d, cudaStream_t stream) {
+  if (n1 == nullptr) return -100;
   if (d.G != 2 || d.K > 64 || d.Q > 16 || d.A > 6 || (d.R & 3) != 0 || d.R > 32) return -100;
   const int RD = d.R * 16, N = 32 * d.A;
-  CUtensorMap tt, tv, tq, ta, tdl, tdn, ta8;
+  CUtensorMap tt, tv, tq, tdl, tdn, ta8;
   if (int rc = make_tmap_3d(&tt, tpack, 512, (uint64_t)d.R * 16, 1, 512, (uint64_t)d.R * 16 * 512, 64, 16)) return rc;
   if (int rc = make_tmap_3d(&tv, vc, RD, d.K, d.B / d.VR, RD, (uint64_t)d.K * RD, 64, 64)) return rc;
   if (int rc = make_tmap_3d(&tq, qc, RD, d.Q, d.B, RD, (uint64_t)d.Q * RD, 64, 16)) return rc;
-  if (int rc = make_tmap_3d(&ta, ac, RD, d.A, d.B, RD, (uint64_t)d.A * RD, 64, 16)) return rc;
   if (int rc = make_tmap_3d(&tdl, dlm, N, d.K, d.B, N, (uint64_t)d.K * N, 64, 64)) return rc;
   {   // dN1 [b][r][a][512] viewed as (64 x, A rows, 8 chunks, B*R): one box (64, 8, 8, 1) per (sample, rank)
     const uint64_t dims[4] = {64, (uint64_t)d.A, 8, (uint64_t)d.B * d.R};
@@ -802,9 +833,9 @@ int trilinear_bwd_tc(const bf16* vc, const bf16* qc, const bf16* ac, const bf16*
     }
     attr_set = true;
   }
-  Bwd1Params p1{dzv, dzq, dn1, dbv, dbq, d.B, d.K, d.Q, d.A, d.R, N, d.VR};
+  Bwd1Params p1{static_cast<const uint8_t*>(n1), dzv, dzq, dn1, d.B, d.K, d.Q, d.A, d.R, N, d.VR};
   const int grid1 = d.B < kNumSMsB200 ? d.B : kNumSMsB200;
-  launch_pdl(trilinear_bwd1_tc_kernel, dim3(grid1), dim3(kThreads1), kSmem1, stream, tt, tv, tq, ta, tdl, p1);
+  launch_pdl(trilinear_bwd1_tc_kernel, dim3(grid1), dim3(kThreads1), kSmem1, stream, tv, tq, tdl, p1);
   if (int rc = check_launch("trilinear_bwd1_tc_kernel")) return rc;
   int n_chunks = kNumSMsB200 / d.R;
   if (n_chunks < 1) n_chunks = 1;
@@ -812,7 +843,11 @@ int trilinear_bwd_tc(const bf16* vc, const bf16* qc, const bf16* ac, const bf16*
   if (n_chunks < 1) n_chunks = 1;
   Bwd2Params p2{dza, dba, dtpack, d.B, d.A, d.R, n_chunks};
   launch_pdl(trilinear_bwd2_tc_kernel, dim3(d.R * n_chunks), dim3(kThreads2), kSmem2, stream, tt, tdn, ta8, p2);
-  return check_launch("trilinear_bwd2_tc_kernel");
+  if (int rc = check_launch("trilinear_bwd2_tc_kernel")) return rc;
+  // bias gradients of the image / question side: column sums of dzv / dzq (kept out of kernel 1: the shuffle trees and
+  // atomics cost more there, in instruction-cache footprint, than two streaming passes over 65 MB)
+  if (int rc = act_bwd_bias(dzv, 1, nullptr, nullptr, dbv, (long)d.B * d.K, RD, stream)) return rc;
+  return act_bwd_bias(dzq, 1, nullptr, nullptr, dbq, (long)d.B * d.Q, RD, stream);
 }
 
 }  // namespace cti

@@ -28,8 +28,13 @@
 // Operands arrive by TMA: the packed core T_r (16 KB per rank, L2 resident, ring of 3) and, per four
 // ranks, one 64-column chunk of the sample's Vc / Qc / Ac rows (ring of 3).
 //
-// Roles (640 threads): warp 0 TMA | warp 1 F1 issuer | warp 3 F2 issuer | warp 2 III issuer
-// (+ TMEM owner) | warps 4-7, 8-11 N1 converters (even / odd units) | warps 12-15 M converters | warps 16-19 epilogue.
+// Training: with `n1_save` the bf16 N1 quad tiles (the shared-memory image, 4 KB per answer token and rank quad) are
+// also bulk-copied to HBM; the backward (trilinear_bwd_tc.cu) loads them back instead of recomputing F1 -- that takes
+// the core re-load and a quarter of the tcgen05 instructions out of the backward for 0.2 GB of traffic per 1024 rows.
+//
+// Roles (672 threads): warp 0 TMA | warp 1 F1 issuer | warp 3 F2 issuer | warp 2 III issuer
+// (+ TMEM owner) | warps 4-7, 8-11 N1 converters (even / odd units) | warps 12-15 M converters | warps 16-19 epilogue |
+// warp 20 N1 store.
 #include "cti_common.cuh"
 #include "cti_kernels.h"
 #include "tc_tiles.cuh"
@@ -62,7 +67,7 @@ __device__ unsigned long long g_trace[8 * 256];          // block 0: time at whi
 #define TRACE(role, u)
 #endif
 
-constexpr int kThreads = 640;                 // 20 warps
+constexpr int kThreads = 672;                 // 21 warps
 constexpr int T_BYTES = 16 * 1024;            // T_r: [16 l][512 x] bf16 = 8 chunks x [16 rows][128 B]
 constexpr int T_RING = 3;
 constexpr int OP_V = 0, OP_Q = 8192, OP_A = 10240, OP_BYTES = 12288;   // Vc [64][64], Qc [16][64], Ac [16][64]
@@ -83,6 +88,7 @@ enum { B_TFULL = 0, B_TEMPTY = B_TFULL + T_RING, B_OPFULL = B_TEMPTY + T_RING, B
 struct TriTcParams {
   const uint8_t* rowmask;
   float* logits;
+  uint8_t* n1_save;          // optional: [b][R / 4][A * 4096 bytes], the N1 quad tiles for the backward
   int B, K, Q, A, R, N;      // N = 32 * A columns (a, g, q16)
   int VR;                    // rows b share the v operand (and mask) of row b / VR
 };
@@ -135,7 +141,7 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
       mbar_init(bar(B_F1FULL + s), 1);
       mbar_init(bar(B_F1EMPTY + s), 4);
     }
-    for (int s = 0; s < 2; ++s) mbar_init(bar(B_N1EMPTY + s), 1);
+    for (int s = 0; s < 2; ++s) mbar_init(bar(B_N1EMPTY + s), p.n1_save != nullptr ? 2 : 1);   // F2 commit (+ the store)
     for (int s = 0; s < F2_RING; ++s) {
       mbar_init(bar(B_F2FULL + s), 1);
       mbar_init(bar(B_F2EMPTY + s), 4);
@@ -166,7 +172,7 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
+    if (elect_one_sync()) {
       PROF_DECL
       uint32_t tslot = 0, tph = 0, oslot = 0, oph = 0;
       int r = 0, b = blockIdx.x;
@@ -200,7 +206,7 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
     // threads does not help: every tcgen05.mma / tcgen05.commit is an entry of ONE in-order queue per SM that drains at
     // ~75 cycles per entry in these kernels -- measured: the kernel time follows (MMAs + commits) per unit x 75 cycles
     // whatever the number of issuers; more issuers only add commits.) ----
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const uint32_t id_f1 = make_idesc_rt(128, 16, 1, 0);
       PROF_DECL
       uint32_t tslot = 0, tph = 0, oslot = 0, oph = 0, fslot = 0, fph = 0;
@@ -237,7 +243,7 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
     // ------------------------------ F2 issuer: M = N1 . Qc_r^T.  One wait for the whole N1 quad tile, then the 8 MMAs of
     // its four ranks back to back (a single thread pays ~50 cycles per barrier wait and ~75 per MMA: per-rank hand-offs
     // made this loop 730 cycles per rank in the first version) ---------------------------------
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const uint32_t id_f2 = make_idesc_rt(128, 16, 0, 0);
       PROF_DECL
       uint32_t oslot = 0, oph = 0, fslot = 0, fph = 0;
@@ -275,7 +281,7 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
   } else if (warp == 2) {
     // ------------------------------ III issuer: L += Vc_r . M  (this warp also owns TMEM).  Per quad: one wait, four
     // MMAs, one commit that frees the M quad slot and one that frees the operand slot --------
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const uint32_t id_3 = make_idesc_rt(128, p.N, 0, 1);
       PROF_DECL
       uint32_t oslot = 0, oph = 0;
@@ -457,6 +463,24 @@ trilinear_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid
       PROF_ADD(1);
     }
     if (warp == 16) PROF_FLUSH(6);
+  } else if (warp == 20) {
+    // ------------------------------ N1 store (training): quad tile -> HBM as one bulk copy; the tile is released to the
+    // converters once the copy has READ it (and F2 has, through its own commit) ------
+    if (p.n1_save != nullptr && elect_one_sync()) {
+      const uint32_t bytes = static_cast<uint32_t>(p.A) * 4096u;
+      const int nq = p.R >> 2;
+      int qi = 0, b = blockIdx.x;
+      for (int uq = 0; uq < U; uq += 4) {
+        const int qslot = (uq >> 2) & 1, qph = (uq >> 3) & 1;
+        mbar_wait(bar(B_N1QFULL + qslot), qph);
+        bulk_store_1d(p.n1_save + ((size_t)b * nq + qi) * bytes, sN1 + qslot * N1_BYTES, bytes);
+        bulk_commit_group();
+        bulk_wait_group_read<0>();
+        mbar_arrive(bar(B_N1EMPTY + qslot));
+        if (++qi == nq) { qi = 0; b += gridDim.x; }
+      }
+      bulk_wait_group_all();
+    }
   }
 
   tcgen05_fence_before();
@@ -482,8 +506,13 @@ int debug_prof_read(unsigned long long* host_dst, int n) {
 // Returns -100 when the shape is outside the fast path (caller falls back to the generic kernel).
 // tpack_perm: the packed core with the (i,g,j) axis of every [r][l] row in the lane order x = (j % 4) * 128 + g * 64 +
 // i * 4 + j / 4 (functions.tpack_perm_index).
+size_t trilinear_n1_bytes(TriDims d) {        // 0: shape outside the fast path (nothing to save)
+  if (d.G != 2 || d.K > 64 || d.Q > 16 || d.A > 6 || (d.R & 3) != 0 || d.R > 32) return 0;
+  return (size_t)d.B * (d.R >> 2) * d.A * 4096;
+}
+
 int trilinear_fwd_tc(const bf16* vc, const bf16* qc, const bf16* ac, const bf16* tpack_perm, const uint8_t* rowmask,
-                     float* logits, TriDims d, cudaStream_t stream) {
+                     float* logits, void* n1_save, TriDims d, cudaStream_t stream) {
   if (tpack_perm == nullptr) return -100;
   if (d.G != 2 || d.K > 64 || d.Q > 16 || d.A > 6 || (d.R & 3) != 0) return -100;      // TMEM: 320 + 32 A columns
   const size_t smem = tri_tc_smem(d.K, d.Q, d.A);
@@ -494,7 +523,7 @@ int trilinear_fwd_tc(const bf16* vc, const bf16* qc, const bf16* ac, const bf16*
   if (int rc = make_tmap_3d(&tv, vc, RD, d.K, d.B / d.VR, RD, (uint64_t)d.K * RD, 64, 64)) return rc;
   if (int rc = make_tmap_3d(&tq, qc, RD, d.Q, d.B, RD, (uint64_t)d.Q * RD, 64, 16)) return rc;
   if (int rc = make_tmap_3d(&ta, ac, RD, d.A, d.B, RD, (uint64_t)d.A * RD, 64, 16)) return rc;
-  TriTcParams p{rowmask, logits, d.B, d.K, d.Q, d.A, d.R, 32 * d.A, d.VR};
+  TriTcParams p{rowmask, logits, static_cast<uint8_t*>(n1_save), d.B, d.K, d.Q, d.A, d.R, 32 * d.A, d.VR};
   static size_t smem_set = 0;          // raise the dynamic shared memory limit once per size (not a stream operation)
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(trilinear_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

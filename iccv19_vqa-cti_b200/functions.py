@@ -356,7 +356,13 @@ class TriLogitsFn(Function):
         yq, qc = rank_nets(yq, pk[4], w[14], dqn)
         ya, ac = rank_nets(ya, pk[5], w[17], dan)
         tpack = pack_core(T_g)
-        logits = K_.trilinear_fwd(vc, qc, ac, tpack, rowmask, B, K, Q, A, G, R, vr)
+        # training: the kernel also leaves its bf16 N1 intermediate in HBM, the backward picks it up instead of recomputing it
+        n1 = None
+        if any(ctx.needs_input_grad):
+            logits, n1 = K_.trilinear_fwd(vc, qc, ac, tpack, rowmask, B, K, Q, A, G, R, vr, save_n1=True)
+        else:
+            logits = K_.trilinear_fwd(vc, qc, ac, tpack, rowmask, B, K, Q, A, G, R, vr)
+        ctx.n1 = n1
         ctx.save_for_backward(v_bf16, xq, xa, yv, yq, ya, vc, qc, ac, tpack, T_g, *w)
         ctx.pk = pk
         ctx.dims = dims
@@ -370,7 +376,8 @@ class TriLogitsFn(Function):
         w = ctx.saved_tensors[11:]
         pk = ctx.pk
         dl = dlogits.permute(0, 4, 1, 2, 3).contiguous()
-        dzv, dzq, dza, dbvn, dbqn, dban, dtpack = K_.trilinear_bwd(vc, qc, ac, tpack, dl, B, K, Q, A, G, R, ctx.vr)
+        dzv, dzq, dza, dbvn, dbqn, dban, dtpack = K_.trilinear_bwd(vc, qc, ac, tpack, dl, B, K, Q, A, G, R, ctx.vr, n1=ctx.n1)
+        ctx.n1 = None
         # per-rank nets: input = tucker output (post-ReLU), so dx is masked by it -> dz of the tucker layer
         dq_drop, da_drop, dvn, dqn, dan = ctx.drops
         sc = lambda d: 1.0 if d is None else 1.0 / (1.0 - d[0])

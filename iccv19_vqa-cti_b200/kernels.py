@@ -275,23 +275,32 @@ def tpack_perm(tpack: torch.Tensor) -> Optional[torch.Tensor]:
     return tpack.index_select(-1, idx)
 
 
-def trilinear_fwd(vc, qc, ac, tpack, rowmask, B, K, Q, A, G, R, v_rep: int = 1, tpack_p=None) -> torch.Tensor:
+def trilinear_fwd(vc, qc, ac, tpack, rowmask, B, K, Q, A, G, R, v_rep: int = 1, tpack_p=None, save_n1: bool = False):
     """vc (and rowmask) hold B / v_rep samples: rows b*v_rep .. b*v_rep + v_rep - 1 of qc / ac share image b.
-    tpack_p: tpack_perm(tpack) if the caller already has it (built here otherwise)."""
+    tpack_p: tpack_perm(tpack) if the caller already has it (built here otherwise).
+    save_n1 (training): returns (logits, n1) -- n1 is the kernel's bf16 intermediate N1 = T x_l Ac (None for shapes outside
+    the tcgen05 path); trilinear_bwd(..., n1=n1) then runs the fast backward without recomputing it."""
     for t, n in ((vc, "vc"), (qc, "qc"), (ac, "ac"), (tpack, "tpack")):
         _req(t, BF16, "trilinear_fwd." + n)
     if tpack_p is None:
         tpack_p = tpack_perm(tpack)
     logits = torch.empty((B, G, K, Q, A), dtype=F32, device=vc.device)
-    _call("cti_trilinear_logits_fwd", _lib.load().cti_trilinear_logits_fwd,
+    lib = _lib.load()
+    n1 = None
+    if save_n1:
+        nbytes = lib.cti_trilinear_n1_bytes(B, K, Q, A, G, R)
+        if nbytes:
+            n1 = torch.empty((nbytes,), dtype=torch.uint8, device=vc.device)
+    _call("cti_trilinear_logits_fwd", lib.cti_trilinear_logits_fwd,
           (vc.data_ptr(), qc.data_ptr(), ac.data_ptr(), tpack.data_ptr(), _ptr(tpack_p), _ptr(rowmask), logits.data_ptr(),
-           B, K, Q, A, G, R, v_rep, _stream()), flops=float(B) * trilinear_min_flops(K, Q, A, G, R))
-    return logits
+           _ptr(n1), B, K, Q, A, G, R, v_rep, _stream()), flops=float(B) * trilinear_min_flops(K, Q, A, G, R))
+    return (logits, n1) if save_n1 else logits
 
 
-def trilinear_bwd(vc, qc, ac, tpack, dlogits, B, K, Q, A, G, R, v_rep: int = 1):
+def trilinear_bwd(vc, qc, ac, tpack, dlogits, B, K, Q, A, G, R, v_rep: int = 1, n1=None):
     """Returns dzv, dzq, dza (bf16, pre-activation), dbv, dbq, dba (fp32, R*16), dtpack (fp32).
-    v_rep > 1: the per-row dzv is folded onto the B / v_rep shared images before it is returned."""
+    v_rep > 1: the per-row dzv is folded onto the B / v_rep shared images before it is returned.
+    n1: the tensor trilinear_fwd(..., save_n1=True) returned (selects the tcgen05 backward; None: generic kernel)."""
     _req(dlogits, F32, "trilinear_bwd.dlogits")
     lib = _lib.load()
     dev = vc.device
@@ -302,7 +311,7 @@ def trilinear_bwd(vc, qc, ac, tpack, dlogits, B, K, Q, A, G, R, v_rep: int = 1):
     nbytes = lib.cti_trilinear_logits_bwd_workspace(B, K, Q, A, G, R)
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
     _call("cti_trilinear_logits_bwd", lib.cti_trilinear_logits_bwd,
-          (vc.data_ptr(), qc.data_ptr(), ac.data_ptr(), tpack.data_ptr(), dlogits.data_ptr(), dzv.data_ptr(),
+          (vc.data_ptr(), qc.data_ptr(), ac.data_ptr(), tpack.data_ptr(), dlogits.data_ptr(), _ptr(n1), dzv.data_ptr(),
            dzq.data_ptr(), dza.data_ptr(), dbv.data_ptr(), dbq.data_ptr(), dba.data_ptr(), dtpack.data_ptr(),
            ws.data_ptr(), nbytes, B, K, Q, A, G, R, v_rep, _stream()), kernels=2,
           flops=2.0 * B * trilinear_min_flops(K, Q, A, G, R))

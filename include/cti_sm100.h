@@ -184,15 +184,19 @@ int cti_adamax_multi(const void* p_ptrs_dev, const void* g_ptrs_dev, const void*
  *   copies; v_rep = 1 is the reference layout.  The backward still writes dzv per row b, (B,K,R*16): fold it with
  *   cti_sum_row_groups before the v-side wgrad.
  * replaces: the rank loop of TCNet.forward (src/tc.py:46-52) incl. Tensor.ModeProduct
- *           (src/Tensor.py:3-19) and the masked_fill_ of src/attention.py:55-56. */
+ *           (src/Tensor.py:3-19) and the masked_fill_ of src/attention.py:55-56.
+ * n1_save (may be NULL; cti_trilinear_n1_bytes() bytes, 0 = nothing to save for this shape): training.  The tcgen05
+ *   kernel also writes its bf16 intermediate N1 = T x_l Ac (per row and rank quad) there; handing it to
+ *   cti_trilinear_logits_bwd as n1_saved selects the fast backward, which does not recompute it. */
 int cti_trilinear_logits_fwd(const void* vc, const void* qc, const void* ac, const void* tpack, const void* tpack_perm,
-                             const uint8_t* rowmask, float* logits, int B, int K, int Q, int A, int G, int R, int v_rep,
-                             void* stream);
+                             const uint8_t* rowmask, float* logits, void* n1_save, int B, int K, int Q, int A, int G,
+                             int R, int v_rep, void* stream);
+size_t cti_trilinear_n1_bytes(int B, int K, int Q, int A, int G, int R);
 size_t cti_trilinear_logits_bwd_workspace(int B, int K, int Q, int A, int G, int R);
 /* dz* are the PRE-activation gradients of the per-rank projections (ReLU masks applied);
  * db*_accum (R*16 each) and dtpack_accum (same shape as tpack, fp32) are accumulated into. */
 int cti_trilinear_logits_bwd(const void* vc, const void* qc, const void* ac, const void* tpack, const float* dlogits,
-                             void* dzv, void* dzq, void* dza, float* dbv_accum, float* dbq_accum, float* dba_accum,
+                             const void* n1_saved, void* dzv, void* dzq, void* dza, float* dbv_accum, float* dbq_accum, float* dba_accum,
                              float* dtpack_accum, void* workspace, size_t workspace_bytes, int B, int K, int Q, int A,
                              int G, int R, int v_rep, void* stream);
 

@@ -173,7 +173,8 @@ def tri_inputs(B, K, Q, A, G, R, seed):
 
 
 @pytest.mark.parametrize("B,K,Q,A,G,R", [(3, 50, 12, 6, 2, 32), (2, 10, 12, 6, 2, 4), (5, 36, 12, 3, 2, 32),
-                                         (2, 50, 12, 4, 3, 8), (150, 17, 5, 2, 2, 2), (1, 1, 1, 1, 2, 1)])
+                                         (2, 50, 12, 4, 3, 8), (150, 17, 5, 2, 2, 2), (1, 1, 1, 1, 2, 1),
+                                         (151, 33, 16, 5, 2, 8), (7, 64, 1, 1, 2, 12)])
 def test_trilinear_logits_fwd_bwd(B, K, Q, A, G, R):
     from cti_b200 import functions as F_
     vc, qc, ac, tg = tri_inputs(B, K, Q, A, G, R, B * 100 + K)
@@ -184,7 +185,8 @@ def test_trilinear_logits_fwd_bwd(B, K, Q, A, G, R):
     dev = lambda t: t.to(DEV)
     tpack = F_.pack_core(dev(tg))
     vcd, qcd, acd = [bf(dev(t)).reshape(t.shape[0] * t.shape[1], R * 16).contiguous() for t in (vc, qc, ac)]
-    out = K_.trilinear_fwd(vcd, qcd, acd, tpack, dev(mask).reshape(-1).contiguous(), B, K, Q, A, G, R)
+    out, n1 = K_.trilinear_fwd(vcd, qcd, acd, tpack, dev(mask).reshape(-1).contiguous(), B, K, Q, A, G, R, save_n1=True)
+    assert (n1 is not None) == (G == 2 and A <= 6 and K <= 64 and R % 4 == 0)      # the tcgen05 path saves its N1 tiles
     out = out.permute(0, 2, 3, 4, 1).cpu()
     keep = mask == 0
     scale = ref.abs().max().item()
@@ -194,20 +196,22 @@ def test_trilinear_logits_fwd_bwd(B, K, Q, A, G, R):
     gen = torch.Generator().manual_seed(1)
     dl = torch.randn(B, G, K, Q, A, generator=gen) * keep[:, None, :, None, None]
     ref.backward(dl.permute(0, 2, 3, 4, 1))
-    dzv, dzq, dza, dbv, dbq, dba, dtp = K_.trilinear_bwd(vcd, qcd, acd, tpack, dev(dl).contiguous(), B, K, Q, A, G, R)
-
     def chk(got, grad, act, name):
         want = (grad * (act > 0)).reshape(got.shape)
         e = (got.float().cpu() - want).abs().max().item() / want.abs().max().clamp_min(1e-12).item()
         assert e < 2e-2, (name, e)
         return want
-    wv = chk(dzv, vc_.grad, vc, "dzv")
-    wq = chk(dzq, qc_.grad, qc, "dzq")
-    wa = chk(dza, ac_.grad, ac, "dza")
-    for got, want, name in ((dbv, wv, "dbv"), (dbq, wq, "dbq"), (dba, wa, "dba")):
-        assert rel_err(got.cpu(), want.sum(0)) < 2e-2, name
-    dT = F_.unpack_core_grad(dtp, dev(tg)).cpu()
-    assert rel_err(dT, tg_.grad) < 2e-2
+    # with the saved N1 tiles (tcgen05 backward) and without (generic kernel)
+    for saved in ([n1, None] if n1 is not None else [None]):
+        dzv, dzq, dza, dbv, dbq, dba, dtp = K_.trilinear_bwd(vcd, qcd, acd, tpack, dev(dl).contiguous(), B, K, Q, A, G, R,
+                                                             n1=saved)
+        wv = chk(dzv, vc_.grad, vc, "dzv")
+        wq = chk(dzq, qc_.grad, qc, "dzq")
+        wa = chk(dza, ac_.grad, ac, "dza")
+        for got, want, name in ((dbv, wv, "dbv"), (dbq, wq, "dbq"), (dba, wa, "dba")):
+            assert rel_err(got.cpu(), want.sum(0)) < 2e-2, name
+        dT = F_.unpack_core_grad(dtp, dev(tg)).cpu()
+        assert rel_err(dT, tg_.grad) < 2e-2
 
 
 # --------------------------------------------------------------------------- #

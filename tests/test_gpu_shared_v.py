@@ -53,13 +53,13 @@ def test_trilinear_kernels_with_shared_v_equal_explicit_clone(Bv, rep, K, Q, A):
     mask = (torch.rand(Bv, K, generator=g) < 0.2).to(torch.uint8).to(DEV)
     vc_cl = clone_rows(vc.view(Bv, K, -1), rep).view(B * K, -1)
     mask_cl = clone_rows(mask, rep)
-    lo = KS.trilinear_fwd(vc, qc, ac, tp, mask, B, K, Q, A, G, R, rep)
-    lo_cl = KS.trilinear_fwd(vc_cl, qc, ac, tp, mask_cl, B, K, Q, A, G, R)
-    assert torch.equal(lo, lo_cl)
+    lo, n1 = KS.trilinear_fwd(vc, qc, ac, tp, mask, B, K, Q, A, G, R, rep, save_n1=True)
+    lo_cl, n1_cl = KS.trilinear_fwd(vc_cl, qc, ac, tp, mask_cl, B, K, Q, A, G, R, save_n1=True)
+    assert torch.equal(lo, lo_cl) and torch.equal(n1, n1_cl)
     dl = torch.randn(B, G, K, Q, A, generator=g).to(DEV)
     dl = torch.where(torch.isinf(lo), torch.zeros_like(dl), dl)
-    out = KS.trilinear_bwd(vc, qc, ac, tp, dl, B, K, Q, A, G, R, rep)
-    out_cl = KS.trilinear_bwd(vc_cl, qc, ac, tp, dl, B, K, Q, A, G, R)
+    out = KS.trilinear_bwd(vc, qc, ac, tp, dl, B, K, Q, A, G, R, rep, n1=n1)
+    out_cl = KS.trilinear_bwd(vc_cl, qc, ac, tp, dl, B, K, Q, A, G, R, n1=n1_cl)
     dzv, dzv_cl = out[0], out_cl[0]
     assert dzv.shape == (Bv * K, R * 16)
     folded = dzv_cl.float().view(Bv, rep, K * R * 16).sum(1).to(BF16).view(Bv * K, R * 16)

@@ -75,14 +75,40 @@ res["fwd_scale"] = ref.abs().max().item()
 flops = B * K_.trilinear_min_flops(K, Q, A, G, R)
 med, best = timed(lambda: K_.trilinear_fwd(vc, qc, ac, tpack, mask, B, K, Q, A, G, R), args.iters)
 res["fwd_us"] = med
+med_s, _ = timed(lambda: K_.trilinear_fwd(vc, qc, ac, tpack, mask, B, K, Q, A, G, R, save_n1=True), args.iters)
+res["fwd_save_n1_us"] = med_s
 res["fwd_us_best"] = best
 res["fwd_tflops_Tmin"] = flops / med / 1e6
 if not args.no_bwd:
     dl = torch.randn(B, G, K, Q, A, generator=g, device=dev) * (mask.view(B, 1, K, 1, 1) == 0)
-    med, best = timed(lambda: K_.trilinear_bwd(vc, qc, ac, tpack, dl, B, K, Q, A, G, R), args.iters)
+    _, n1 = K_.trilinear_fwd(vc, qc, ac, tpack, mask, B, K, Q, A, G, R, save_n1=True)
+    med, best = timed(lambda: K_.trilinear_bwd(vc, qc, ac, tpack, dl, B, K, Q, A, G, R, n1=n1), args.iters)
     res["bwd_us"] = med
     res["bwd_us_best"] = best
     res["bwd_tflops_Tmin"] = 2 * flops / med / 1e6
+if args.prof and not args.no_bwd:
+    lib = _lib.load()
+    lib.cti_debug_prof_read_bwd1.restype = ctypes.c_int
+    lib.cti_debug_prof_read_bwd1.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    K_.trilinear_bwd(vc, qc, ac, tpack, dl, B, K, Q, A, G, R, n1=n1)
+    torch.cuda.synchronize()
+    buf = (ctypes.c_ulonglong * (148 * 128))()
+    if lib.cti_debug_prof_read_bwd1(buf, 148 * 128) == 0:
+        t = torch.tensor(list(buf), dtype=torch.float64).view(148, 16, 8)
+        quads = (B + 147) // 148 * (R // 4)
+        roles = ["tma: opempty n1empty dlempty", "b2: opfull dlfull b2empty issue", "f2: opfull n1full f2empty issue",
+                 "b1: dlfull mfull b1empty issue", "b34: opfull n1full dtfull b3empty b4empty issue",
+                 "c3: b2full dtempty work", "c2: f2full mempty work", "e1: opfull b1full work tmem",
+                 "e34: opfull b3full e3work b4full e4work e3tmem e3store"]
+        res["bwd1_prof_cycles_per_quad"] = {roles[i]: (t[:, i].mean(0) / quads).round().tolist() for i in range(9)}
+        tb = (ctypes.c_ulonglong * (16 * 128))()
+        if lib.cti_debug_prof_read_bwd1(tb, 16 * 128) == 0:
+            tr = torch.tensor(list(tb), dtype=torch.float64).view(16, 128)
+            names = ["tma", "b2", "c3", "c3done", "b3", "e3", "e4done", "f2", "c2done", "b1", "e1", "e1done"]
+            t0 = tr[0, 16].item()
+            print("# bwd1 timeline of block 0 (cycles relative to the TMA issue of quad 16)", file=sys.stderr)
+            for c in range(16, 34):
+                print(f"  c={c:3d} " + " ".join(f"{n}={int(tr[i, c].item() - t0):6d}" for i, n in enumerate(names)), file=sys.stderr)
 if args.prof:
     lib = _lib.load()
     lib.cti_debug_prof_read.restype = ctypes.c_int
