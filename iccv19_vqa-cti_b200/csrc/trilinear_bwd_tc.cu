@@ -64,9 +64,9 @@ __device__ unsigned long long g_trace1[16 * 128];        // block 0: time at whi
 // =========================================================================== //
 // kernel 1
 // =========================================================================== //
-// 21 warps: 0 TMA | 1 B2 issuer | 2 F2 issuer (+ TMEM owner) | 3 B1 issuer | 4 B3 / B4 issuer |
-//           5-8 C3 (dM -> Dt tile) | 9-12 C2 (M -> M tile) | 13-16 E1 (dVc -> dzv) | 17-20 E3 / E4 (dQc -> dzq, dN1 -> workspace)
-constexpr int kThreads1 = 672;
+// 24 warps: 0 TMA | 1 B2 issuer | 2 F2 issuer (+ TMEM owner) | 3 B1 issuer | 22 B3 issuer | 23 B4 issuer |
+//           4-7 C3 (dM -> Dt tile) | 8-11 C2 (M -> M tile) | 12-15 E1 (dVc -> dzv) | 16-19 E4 (dN1 -> workspace) | 20-21 E3 (dQc -> dzq)
+constexpr int kThreads1 = 768;
 constexpr int T_BYTES = 16 * 1024;
 constexpr int OP_V = 0, OP_Q = 8192, OP_BYTES = 10240, OP_RING = 2;     // per quad: Vc [64 k][64 (r4,i)], Qc [16 q][64 (r4,j)]
 constexpr int N1_BYTES = 24 * 1024;                           // [(a,g,i) 192][64 (r4,j)]   (the forward's tile image)
@@ -116,13 +116,13 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_v, const __gri
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar(A_OPFULL + s), 1);
-      mbar_init(bar(A_OPEMPTY + s), 16);      // C3 (for B2), C2 (for F2), E1 (own reads), E3/E4 (own reads + B4): 4 warps each
+      mbar_init(bar(A_OPEMPTY + s), 18);      // C3 (for B2), C2 (for F2), E1 (own reads), E4 (for B4): 4 warps each; E3 (own reads): 2
       mbar_init(bar(A_N1FULL + s), 1);
-      mbar_init(bar(A_N1EMPTY + s), 8);       // C2 (for F2) + E3/E4 (for B3)
+      mbar_init(bar(A_N1EMPTY + s), 6);       // C2 (for F2) + E3 (for B3)
       mbar_init(bar(A_DLFULL + s), 1);
       mbar_init(bar(A_DLEMPTY + s), 8);       // C3 (for B2) + E1 (for B1), at the sample's last quad
       mbar_init(bar(A_DTFULL + s), 4);
-      mbar_init(bar(A_DTEMPTY + s), 4);       // E3/E4 (for B3 and B4)
+      mbar_init(bar(A_DTEMPTY + s), 6);       // E4 (for B4) + E3 (for B3)
       mbar_init(bar(A_F2FULL + s), 1);
       mbar_init(bar(A_F2EMPTY + s), 4);
       mbar_init(bar(A_MFULL + s), 4);
@@ -135,7 +135,7 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_v, const __gri
     mbar_init(bar(A_B2FULL), 1);
     mbar_init(bar(A_B2EMPTY), 4);
     mbar_init(bar(A_B3FULL), 1);
-    mbar_init(bar(A_B3EMPTY), 4);
+    mbar_init(bar(A_B3EMPTY), 2);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -263,29 +263,39 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_v, const __gri
       }
       PROF_FLUSH(3);
     }
-  } else if (warp == 4) {
+  } else if (warp == 22) {
     // ------------------------------ issuer: B3  dQc^T-blocks[(r4',q), (r4,j)] = Dt^T N1 (per quad; the diagonal blocks
-    // r' = r are dQc_r), B4  dN1_r[(a,g,i), j] = Dt_r Qc_r (per rank) ------------------------------------------------
+    // r' = r are dQc_r) ------------------------------------------------------------------------------------------
     if (elect_one_sync()) {
       const uint32_t id_b3 = make_idesc_rt(128, 64, 1, 1);
-      const uint32_t id_b4 = make_idesc_rt(128, 16, 0, 1);
       PROF_DECL
       for (int c = 0; c < CQ; ++c) {
         const int slot = c & 1, ph = (c >> 1) & 1;
-        const uint32_t dt = sDT + slot * DT_BYTES, op = sOp + slot * OP_BYTES;
-        PWAIT(0, bar(A_OPFULL + slot), ph);
         PWAIT(1, bar(A_N1FULL + slot), ph);
         PWAIT(2, bar(A_DTFULL + slot), ph);
         PWAIT(3, bar(A_B3EMPTY), (c & 1) ^ 1);
         TRACE(4, c);
         PROF_T0();
         tcgen05_fence_after();
-        const uint64_t da0 = desc_mnmajor(dt, 0, 0), db0 = desc_mnmajor(sN1 + slot * N1_BYTES, 0, 0);
+        const uint64_t da0 = desc_mnmajor(sDT + slot * DT_BYTES, 0, 0), db0 = desc_mnmajor(sN1 + slot * N1_BYTES, 0, 0);
 #pragma unroll 1
         for (int ks = 0; ks < kn; ++ks)
           umma_bf16_ss(tmem_base + TM_B3, da0 + (uint64_t)(ks * 2048 >> 4), db0 + (uint64_t)(ks * 2048 >> 4), id_b3, ks > 0 ? 1u : 0u);
         umma_commit(bar(A_B3FULL));
         PROF_ADD(5);
+      }
+      PROF_FLUSH(4);
+    }
+  } else if (warp == 23) {
+    // ------------------------------ issuer: B4  dN1_r[(a,g,i), j] = Dt_r Qc_r (per rank) ---------------------------
+    if (elect_one_sync()) {
+      const uint32_t id_b4 = make_idesc_rt(128, 16, 0, 1);
+      PROF_DECL
+      for (int c = 0; c < CQ; ++c) {
+        const int slot = c & 1, ph = (c >> 1) & 1;
+        const uint32_t dt = sDT + slot * DT_BYTES, op = sOp + slot * OP_BYTES;
+        PWAIT(0, bar(A_OPFULL + slot), ph);
+        PWAIT(2, bar(A_DTFULL + slot), ph);
 #pragma unroll 1
         for (int s = 0; s < 4; ++s) {
           const int u = c * 4 + s;
@@ -300,9 +310,9 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_v, const __gri
           PROF_ADD(5);
         }
       }
-      PROF_FLUSH(4);
+      PROF_FLUSH(9);
     }
-  } else if (warp < 9) {
+  } else if (warp < 8) {
     // ------------------------------ C3: dM (TMEM, lane (r4,i), column n = (a,g,q16)) -> Dt tile rows (a,g,i), columns
     // (r4,q16).  Lanes 64-127 repeat lanes 0-63: warps on lanes 0-63 convert (a,g) < A, the others (a,g) >= A. ------
     const int qd = warp & 3, L = qd * 32 + lane;
@@ -315,7 +325,7 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_v, const __gri
       PWAIT(0, bar(A_B2FULL), c & 1);
       tcgen05_fence_after();
       PWAIT(1, bar(A_DTEMPTY + slot), ph ^ 1);
-      if (warp == 5) TRACE(2, c);
+      if (warp == 4) TRACE(2, c);
       PROF_T0();
       const uint32_t dt = sDT + slot * DT_BYTES;
       for (int x = 0; x < p.A; x += 2) {
@@ -346,11 +356,11 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_v, const __gri
         if (t == NQ - 1) mbar_arrive(bar(A_DLEMPTY + (sl & 1)));   // ... nor, after the sample's last quad, the dL tile
       }
       PROF_ADD(2);
-      if (warp == 5) TRACE(3, c);
+      if (warp == 4) TRACE(3, c);
       if (++t == NQ) { t = 0; ++sl; }
     }
-    if (warp == 5) PROF_FLUSH(5);
-  } else if (warp < 13) {
+    if (warp == 4) PROF_FLUSH(5);
+  } else if (warp < 12) {
     // ------------------------------ C2: M_r (TMEM, lane (a,g,i), column q16) -> M quad tile rows (r4,i), columns n ------
     const int qd = warp & 3, L = qd * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
@@ -397,10 +407,10 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_v, const __gri
         }
         PROF_ADD(2);
       }
-      if (warp == 9) TRACE(8, c);
+      if (warp == 8) TRACE(8, c);
     }
-    if (warp == 9) PROF_FLUSH(6);
-  } else if (warp < 17) {
+    if (warp == 8) PROF_FLUSH(6);
+  } else if (warp < 16) {
     // ------------------------------ E1: dVc[k, (r4,i)] -> ReLU mask -> dzv (128 contiguous bytes per region) ------
     const int qd = warp & 3, L = qd * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
@@ -411,7 +421,7 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_v, const __gri
       const int slot = c & 1, ph = (c >> 1) & 1;
       PWAIT(0, bar(A_OPFULL + slot), ph);
       PWAIT(1, bar(A_B1FULL + slot), ph);
-      if (warp == 13) TRACE(10, c);
+      if (warp == 12) TRACE(10, c);
       PROF_T0();
       tcgen05_fence_after();
       const uint32_t rb = sOp + slot * OP_BYTES + OP_V + (L >> 3) * 1024u + (L & 7) * 128u;      // row k = L of the Vc chunk
@@ -460,73 +470,18 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_v, const __gri
         if (t == NQ - 1) mbar_arrive(bar(A_DLEMPTY + (sl & 1)));   // ... and, after the last quad, the dL tile
       }
       PROF_ADD(2);
-      if (warp == 13) TRACE(11, c);
+      if (warp == 12) TRACE(11, c);
       if (++t == NQ) { t = 0; ++sl; b += gridDim.x; }
     }
-    if (warp == 13) PROF_FLUSH(7);
-  } else {
-    // ------------------------------ E3: dQc_r[q, j] (diagonal blocks of B3) -> ReLU mask -> dzq;
-    //                                E4: dN1_r[(a,g,i), j] -> bf16 workspace [b][r][a][(i,g,j)] ------------------------
+    if (warp == 12) PROF_FLUSH(7);
+  } else if (warp < 20) {
+    // ------------------------------ E4: dN1_r[(a,g,i), j] -> bf16 workspace [b][r][a][(i,g,j)] ------------------------
     const int qd = warp & 3, L = qd * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
-    const int RD = p.R * 16;
     PROF_DECL
     int t = 0, b = blockIdx.x;
     for (int c = 0; c < CQ; ++c) {
-      const int slot = c & 1, ph = (c >> 1) & 1;
-      PWAIT(0, bar(A_OPFULL + slot), ph);
-      PWAIT(1, bar(A_B3FULL), c & 1);
-      if (warp == 17) TRACE(5, c);
-      PROF_T0();
-      tcgen05_fence_after();
-      {
-        uint32_t v[32];
-        if (qd < 2) {
-#ifdef CTI_PROF
-          const unsigned long long tq0 = clock64();
-#endif
-          tmem_ld_32x32b_x32(tmem_base + lane_addr + TM_B3 + qd * 32, v);      // blocks r' = 2 qd (lanes 0-15), 2 qd + 1 (16-31)
-          tmem_wait_ld();
-#ifdef CTI_PROF
-          prof_acc[5] += clock64() - tq0;
-#endif
-        }
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(A_B3EMPTY));
-#ifdef CTI_PROF
-        const unsigned long long tq1 = clock64();
-#endif
-        if (qd < 2) {
-          const int rr = L >> 4, q = L & 15;          // rank within the quad, question token
-          const bool hi = lane & 16;
-          if (q < p.Q) {
-            float gv[16];
-            const uint32_t rb = sOp + slot * OP_BYTES + OP_Q + (q >> 3) * 1024u + (q & 7) * 128u;
-            uint32_t w0[4], w1[4];
-            ld_shared_v4(rb + (((rr * 2) ^ (q & 7)) << 4), w0);
-            ld_shared_v4(rb + (((rr * 2 + 1) ^ (q & 7)) << 4), w1);
-#pragma unroll
-            for (int x = 0; x < 4; ++x) {
-              const float2 f0 = unpack_bf16x2(w0[x]), f1 = unpack_bf16x2(w1[x]);
-              gv[2 * x] = f0.x > 0.f ? __uint_as_float(hi ? v[16 + 2 * x] : v[2 * x]) : 0.f;
-              gv[2 * x + 1] = f0.y > 0.f ? __uint_as_float(hi ? v[16 + 2 * x + 1] : v[2 * x + 1]) : 0.f;
-              gv[8 + 2 * x] = f1.x > 0.f ? __uint_as_float(hi ? v[24 + 2 * x] : v[8 + 2 * x]) : 0.f;
-              gv[8 + 2 * x + 1] = f1.y > 0.f ? __uint_as_float(hi ? v[24 + 2 * x + 1] : v[8 + 2 * x + 1]) : 0.f;
-            }
-            uint4 o0, o1;
-            o0.x = pack_bf16x2(gv[0], gv[1]); o0.y = pack_bf16x2(gv[2], gv[3]); o0.z = pack_bf16x2(gv[4], gv[5]); o0.w = pack_bf16x2(gv[6], gv[7]);
-            o1.x = pack_bf16x2(gv[8], gv[9]); o1.y = pack_bf16x2(gv[10], gv[11]); o1.z = pack_bf16x2(gv[12], gv[13]); o1.w = pack_bf16x2(gv[14], gv[15]);
-            uint4* dst = reinterpret_cast<uint4*>(p.dzq + ((size_t)b * p.Q + q) * RD + (t * 4 + rr) * 16);
-            dst[0] = o0;
-            dst[1] = o1;
-          }
-#ifdef CTI_PROF
-          prof_acc[6] += clock64() - tq1;
-#endif
-        }
-      }
-      PROF_ADD(2);
+      const int slot = c & 1;
 #pragma unroll 1
       for (int s = 0; s < 4; ++s) {
         const int u = c * 4 + s, r = t * 4 + s;
@@ -541,9 +496,8 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_v, const __gri
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(bar(A_B4EMPTY + (u & 1)));
-          if (s == 3) {      // the issuer's B3 and B4 of this quad have all retired
+          if (s == 3) {      // B4 of this quad has retired: Dt tile and Qc chunk are free of it
             mbar_arrive(bar(A_DTEMPTY + slot));
-            mbar_arrive(bar(A_N1EMPTY + slot));
             mbar_arrive(bar(A_OPEMPTY + slot));
           }
         }
@@ -569,10 +523,64 @@ trilinear_bwd1_tc_kernel(const __grid_constant__ CUtensorMap tmap_v, const __gri
         }
         PROF_ADD(4);
       }
-      if (warp == 17) TRACE(6, c);
+      if (warp == 16) TRACE(6, c);
       if (++t == NQ) { t = 0; b += gridDim.x; }
     }
-    if (warp == 17) PROF_FLUSH(8);
+    if (warp == 16) PROF_FLUSH(8);
+  } else if (warp < 22) {
+    // ------------------------------ E3 (two warps, accumulator lanes 0-63): dQc_r[q, j] (diagonal blocks of B3) ->
+    // ReLU mask -> dzq ---------------------------------------------------------------------------------------------
+    const int qd = warp & 3, L = qd * 32 + lane;                  // qd = 0, 1
+    const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
+    const int RD = p.R * 16;
+    const int rr = L >> 4, q = L & 15;          // rank within the quad, question token
+    const bool hi = lane & 16;
+    PROF_DECL
+    int t = 0, b = blockIdx.x;
+    for (int c = 0; c < CQ; ++c) {
+      const int slot = c & 1, ph = (c >> 1) & 1;
+      PWAIT(0, bar(A_OPFULL + slot), ph);
+      PWAIT(1, bar(A_B3FULL), c & 1);
+      if (warp == 20) TRACE(5, c);
+      PROF_T0();
+      tcgen05_fence_after();
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_base + lane_addr + TM_B3 + qd * 32, v);      // blocks r' = 2 qd (lanes 0-15), 2 qd + 1 (16-31)
+      tmem_wait_ld();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar(A_B3EMPTY));
+        mbar_arrive(bar(A_DTEMPTY + slot));      // B3 has retired: Dt and N1 tiles are free of it
+        mbar_arrive(bar(A_N1EMPTY + slot));
+      }
+      if (q < p.Q) {
+        float gv[16];
+        const uint32_t rb = sOp + slot * OP_BYTES + OP_Q + (q >> 3) * 1024u + (q & 7) * 128u;
+        uint32_t w0[4], w1[4];
+        ld_shared_v4(rb + (((rr * 2) ^ (q & 7)) << 4), w0);
+        ld_shared_v4(rb + (((rr * 2 + 1) ^ (q & 7)) << 4), w1);
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          const float2 f0 = unpack_bf16x2(w0[x]), f1 = unpack_bf16x2(w1[x]);
+          gv[2 * x] = f0.x > 0.f ? __uint_as_float(hi ? v[16 + 2 * x] : v[2 * x]) : 0.f;
+          gv[2 * x + 1] = f0.y > 0.f ? __uint_as_float(hi ? v[16 + 2 * x + 1] : v[2 * x + 1]) : 0.f;
+          gv[8 + 2 * x] = f1.x > 0.f ? __uint_as_float(hi ? v[24 + 2 * x] : v[8 + 2 * x]) : 0.f;
+          gv[8 + 2 * x + 1] = f1.y > 0.f ? __uint_as_float(hi ? v[24 + 2 * x + 1] : v[8 + 2 * x + 1]) : 0.f;
+        }
+        uint4 o0, o1;
+        o0.x = pack_bf16x2(gv[0], gv[1]); o0.y = pack_bf16x2(gv[2], gv[3]); o0.z = pack_bf16x2(gv[4], gv[5]); o0.w = pack_bf16x2(gv[6], gv[7]);
+        o1.x = pack_bf16x2(gv[8], gv[9]); o1.y = pack_bf16x2(gv[10], gv[11]); o1.z = pack_bf16x2(gv[12], gv[13]); o1.w = pack_bf16x2(gv[14], gv[15]);
+        uint4* dst = reinterpret_cast<uint4*>(p.dzq + ((size_t)b * p.Q + q) * RD + (t * 4 + rr) * 16);
+        dst[0] = o0;
+        dst[1] = o1;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(A_OPEMPTY + slot));      // this warp has read its Qc activations
+      PROF_ADD(2);
+      if (++t == NQ) { t = 0; b += gridDim.x; }
+    }
+    if (warp == 20) PROF_FLUSH(10);
   }
 
   tcgen05_fence_before();

@@ -97,6 +97,7 @@ def test_fused_clip_adamax_against_torch_at_model_size_and_bucket_views():
     ref_opt = torch.optim.Adamax(ref_params, lr=1e-3)
     opt = cti_b200.FusedClipAdamax(params, lr=1e-3, clip_norm=0.25)
     red = GradAllReducer(params)                                # world size 1: buckets only
+    red.set_hooks_enabled(False)                                # reduce_now() is the hook-free path
     gen = torch.Generator(device=DEV).manual_seed(1)
     for step, (scale, denom) in enumerate([(1.0, 256.0), (1e-4, 1.0), (10.0, 64.0)]):
         grads = [scale * torch.randn(p.shape, device=DEV, generator=gen) for p in params]

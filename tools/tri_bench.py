@@ -99,8 +99,9 @@ if args.prof and not args.no_bwd:
         roles = ["tma: opempty n1empty dlempty", "b2: opfull dlfull b2empty issue", "f2: opfull n1full f2empty issue",
                  "b1: dlfull mfull b1empty issue", "b34: opfull n1full dtfull b3empty b4empty issue",
                  "c3: b2full dtempty work", "c2: f2full mempty work", "e1: opfull b1full work tmem",
-                 "e34: opfull b3full e3work b4full e4work e3tmem e3store"]
-        res["bwd1_prof_cycles_per_quad"] = {roles[i]: (t[:, i].mean(0) / quads).round().tolist() for i in range(9)}
+                 "e4: - - - b4full e4work", "b4: opfull - dtfull - b4empty issue", "e3: opfull b3full work"]
+        roles[4] = "b3: - n1full dtfull b3empty - issue"
+        res["bwd1_prof_cycles_per_quad"] = {roles[i]: (t[:, i].mean(0) / quads).round().tolist() for i in range(11)}
         tb = (ctypes.c_ulonglong * (16 * 128))()
         if lib.cti_debug_prof_read_bwd1(tb, 16 * 128) == 0:
             tr = torch.tensor(list(tb), dtype=torch.float64).view(16, 128)
