@@ -15,6 +15,16 @@ LIB_PATH = os.path.join(HERE, "libcti_sm100.so")
 
 # name -> (restype, argtypes); mirrors include/cti_sm100.h one to one.
 _P = c_void_p
+
+
+class GemmDesc(ctypes.Structure):
+    """cti_gemm_desc of include/cti_sm100.h."""
+    _fields_ = [("a", _P), ("lda", c_int), ("a_mn_major", c_int), ("b", _P), ("ldb", c_int), ("b_mn_major", c_int),
+                ("M", c_int), ("N", c_int), ("K", c_int), ("alpha", c_float), ("bias", _P), ("relu", c_int),
+                ("relu_aux", _P), ("ld_aux", c_int), ("out_bf16", _P), ("out_f32", _P), ("ldc", c_int),
+                ("atomic_f32", c_int), ("k_splits", c_int), ("tile_n", c_int)]
+
+
 SIGNATURES = {
     "cti_version": (c_int, []),
     "cti_last_error": (c_char_p, []),
@@ -31,6 +41,7 @@ SIGNATURES = {
                                  c_float, _P, _P]),
     "cti_gru_gate_fwd": (c_int, [_P, c_int64, _P, _P, c_int64, _P, c_int64, _P, _P, _P, _P, _P, c_int64, c_int, _P]),
     "cti_gru_gate_bwd": (c_int, [_P, _P, c_int64, _P, c_int64, _P, _P, _P, _P, _P, c_int64, _P, c_int64, c_int, _P]),
+    "cti_gemm_bf16_pair": (c_int, [ctypes.POINTER(GemmDesc), ctypes.POINTER(GemmDesc), _P]),
     "cti_wn_pack_multi": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, c_int, _P, _P]),
     "cti_wn_grad_multi": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, c_int, _P, _P]),
     "cti_wn_scratch_floats": (c_size_t, [c_int, c_int, c_int]),

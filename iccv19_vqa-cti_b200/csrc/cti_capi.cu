@@ -132,6 +132,36 @@ int cti_gemm_bf16(const void* a, int lda, int a_mn_major, const void* b, int ldb
   return cti::gemm_bf16(g, static_cast<cudaStream_t>(stream));
 }
 
+static cti::GemmArgs gemm_args_of(const cti_gemm_desc& d) {
+  cti::GemmArgs g;
+  g.a = static_cast<const __nv_bfloat16*>(d.a);
+  g.b = static_cast<const __nv_bfloat16*>(d.b);
+  g.M = d.M; g.N = d.N; g.K = d.K;
+  g.lda = d.lda; g.ldb = d.ldb;
+  g.a_mn_major = d.a_mn_major != 0;
+  g.b_mn_major = d.b_mn_major != 0;
+  g.bias = d.bias;
+  g.relu_aux = static_cast<const __nv_bfloat16*>(d.relu_aux);
+  g.ld_aux = d.ld_aux;
+  g.out_bf16 = static_cast<__nv_bfloat16*>(d.out_bf16);
+  g.out_f32 = d.out_f32;
+  g.ldc = d.ldc;
+  g.relu = d.relu;
+  g.atomic_f32 = d.atomic_f32;
+  g.k_splits = d.k_splits;
+  g.alpha = d.alpha;
+  g.tile_n = d.tile_n;
+  return g;
+}
+
+int cti_gemm_bf16_pair(const cti_gemm_desc* d0, const cti_gemm_desc* d1, void* stream) {
+  if (d0 == nullptr || d1 == nullptr) {
+    cti::set_error("cti_gemm_bf16_pair: null descriptor");
+    return -1;
+  }
+  return cti::gemm_bf16_pair(gemm_args_of(*d0), gemm_args_of(*d1), static_cast<cudaStream_t>(stream));
+}
+
 int cti_act_bwd_bias(const void* dy, int dy_is_bf16, const void* y_bf16, void* dz_bf16, float* dbias_accum,
                      int64_t rows, int cols, void* stream) {
   return cti::act_bwd_bias(dy, dy_is_bf16, static_cast<const __nv_bfloat16*>(y_bf16),

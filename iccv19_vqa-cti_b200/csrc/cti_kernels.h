@@ -28,6 +28,7 @@ struct GemmArgs {
   int max_ctas = 0;    // 0 = one per SM
 };
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream);
+int gemm_bf16_pair(const GemmArgs& g0, const GemmArgs& g1, cudaStream_t stream);
 
 // elementwise.cu
 int cast_rows_mask(const float* x, __nv_bfloat16* out, uint8_t* rowmask, long rows, int cols, cudaStream_t s);

@@ -56,10 +56,19 @@ struct GemmDevParams {
 
 enum { kOutDirect = 0, kOutTmaBf16 = 1, kOutTmaF32 = 2, kOutTmaAddF32 = 3 };
 
+// One launch runs ONE problem or a PAIR of independent problems that share the operand layouts and the tile width
+// (gemm_bf16_pair: the question-side and answer-side projections of a step -- same weights shape, different row
+// counts -- which on their own leave SMs idle and pay the launch / pipeline-fill floor twice).  The tiles of problem 0
+// come first in the persistent tile loop, then those of problem 1.
+struct GemmMaps {
+  CUtensorMap a, b, c;
+};
+
 template <int BLOCK_N, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const __grid_constant__ CUtensorMap tmap_c, const GemmDevParams p) {
+gemm_bf16_kernel(const __grid_constant__ GemmMaps maps0, const __grid_constant__ GemmMaps maps1,
+                 const __grid_constant__ GemmDevParams prm0, const __grid_constant__ GemmDevParams prm1, const int tiles0,
+                 const int total_tiles) {
   using Cfg = GemmCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -77,9 +86,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_a);
-    tma_prefetch_desc(&tmap_b);
-    if (p.tma_out != kOutDirect) tma_prefetch_desc(&tmap_c);
+    tma_prefetch_desc(&maps0.a);
+    tma_prefetch_desc(&maps0.b);
+    if (prm0.tma_out != kOutDirect) tma_prefetch_desc(&maps0.c);
+    if (total_tiles > tiles0) {
+      tma_prefetch_desc(&maps1.a);
+      tma_prefetch_desc(&maps1.b);
+      if (prm1.tma_out != kOutDirect) tma_prefetch_desc(&maps1.c);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
@@ -103,16 +117,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   pdl_prologue_done();      // everything above touched only this CTA's shared memory / TMEM
 
-  const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
-  const int total_tiles = tiles_mn * p.k_splits;
-
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (elect_one_sync()) {
       uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int ks = tile / tiles_mn;
-        const int mn = tile - ks * tiles_mn;
+        const bool second = tile >= tiles0;
+        const GemmDevParams& p = second ? prm1 : prm0;
+        const CUtensorMap* tmap_a = second ? &maps1.a : &maps0.a;
+        const CUtensorMap* tmap_b = second ? &maps1.b : &maps0.b;
+        const int t = second ? tile - tiles0 : tile;
+        const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
+        const int ks = t / tiles_mn;
+        const int mn = t - ks * tiles_mn;
         const int m_blk = mn / p.num_n_blocks;
         const int n_blk = mn - m_blk * p.num_n_blocks;
         const int kb0 = ks * p.k_blocks_per_split;
@@ -121,18 +138,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
           if (!A_MN) {
-            tma_load_2d(&tmap_a, full_bar(stage), smem_a(stage), kb * BLOCK_K, m_blk * BLOCK_M);
+            tma_load_2d(tmap_a, full_bar(stage), smem_a(stage), kb * BLOCK_K, m_blk * BLOCK_M);
           } else {
 #pragma unroll
             for (int i = 0; i < BLOCK_M / 64; ++i)
-              tma_load_2d(&tmap_a, full_bar(stage), smem_a(stage) + i * 8192, m_blk * BLOCK_M + i * 64, kb * BLOCK_K);
+              tma_load_2d(tmap_a, full_bar(stage), smem_a(stage) + i * 8192, m_blk * BLOCK_M + i * 64, kb * BLOCK_K);
           }
           if (!B_MN) {
-            tma_load_2d(&tmap_b, full_bar(stage), smem_b(stage), kb * BLOCK_K, n_blk * BLOCK_N);
+            tma_load_2d(tmap_b, full_bar(stage), smem_b(stage), kb * BLOCK_K, n_blk * BLOCK_N);
           } else {
 #pragma unroll
             for (int i = 0; i < BLOCK_N / 64; ++i)
-              tma_load_2d(&tmap_b, full_bar(stage), smem_b(stage) + i * 8192, n_blk * BLOCK_N + i * 64, kb * BLOCK_K);
+              tma_load_2d(tmap_b, full_bar(stage), smem_b(stage) + i * 8192, n_blk * BLOCK_N + i * 64, kb * BLOCK_K);
           }
           if (++stage == Cfg::STAGES) {
             stage = 0;
@@ -147,7 +164,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int ks = tile / tiles_mn;
+        const bool second = tile >= tiles0;
+        const GemmDevParams& p = second ? prm1 : prm0;
+        const int ks = (second ? tile - tiles0 : tile) / (p.num_m_blocks * p.num_n_blocks);
         const int kb0 = ks * p.k_blocks_per_split;
         const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -195,8 +214,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     constexpr uint32_t obuf = 0;
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int ks = tile / tiles_mn;
-      const int mn = tile - ks * tiles_mn;
+      const bool second = tile >= tiles0;
+      const GemmDevParams& p = second ? prm1 : prm0;
+      const CUtensorMap* tmap_c = second ? &maps1.c : &maps0.c;
+      const int t = second ? tile - tiles0 : tile;
+      const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
+      const int ks = t / tiles_mn;
+      const int mn = t - ks * tiles_mn;
       const int m_blk = mn / p.num_n_blocks;
       const int n_blk = mn - m_blk * p.num_n_blocks;
       const bool empty_split = (ks * p.k_blocks_per_split >= p.num_k_blocks);
@@ -266,7 +290,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               fence_proxy_async_smem();
               __syncwarp();
               if (lane == 0) {
-                tma_store_2d(&tmap_c, stage0 + obuf * 4096, n0 + (c >> 1) * 64, row0);
+                tma_store_2d(tmap_c, stage0 + obuf * 4096, n0 + (c >> 1) * 64, row0);
                 bulk_commit_group();
               }
             }
@@ -302,8 +326,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              if (p.tma_out == kOutTmaAddF32) tma_reduce_add_2d(&tmap_c, stage0 + obuf * 4096, col0, row0);
-              else                            tma_store_2d(&tmap_c, stage0 + obuf * 4096, col0, row0);
+              if (p.tma_out == kOutTmaAddF32) tma_reduce_add_2d(tmap_c, stage0 + obuf * 4096, col0, row0);
+              else                            tma_store_2d(tmap_c, stage0 + obuf * 4096, col0, row0);
               bulk_commit_group();
             }
           } else if (row_ok) {
@@ -393,16 +417,15 @@ int make_tmap(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer,
   return 0;
 }
 
+// Tensor maps + device parameters of one problem for the given tile width / layouts.
 template <int BLOCK_N, bool A_MN, bool B_MN>
-int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N>;
-  CUtensorMap ta, tb;
+int build_problem(const GemmArgs& g, GemmMaps* maps, GemmDevParams* out) {
   int rc;
-  if (!A_MN) rc = make_tmap(&ta, g.a, g.K, g.M, g.lda, BLOCK_K, BLOCK_M);
-  else       rc = make_tmap(&ta, g.a, g.M, g.K, g.lda, 64, BLOCK_K);
+  if (!A_MN) rc = make_tmap(&maps->a, g.a, g.K, g.M, g.lda, BLOCK_K, BLOCK_M);
+  else       rc = make_tmap(&maps->a, g.a, g.M, g.K, g.lda, 64, BLOCK_K);
   if (rc) return rc;
-  if (!B_MN) rc = make_tmap(&tb, g.b, g.K, g.N, g.ldb, BLOCK_K, BLOCK_N);
-  else       rc = make_tmap(&tb, g.b, g.N, g.K, g.ldb, 64, BLOCK_K);
+  if (!B_MN) rc = make_tmap(&maps->b, g.b, g.K, g.N, g.ldb, BLOCK_K, BLOCK_N);
+  else       rc = make_tmap(&maps->b, g.b, g.N, g.K, g.ldb, 64, BLOCK_K);
   if (rc) return rc;
 
   GemmDevParams p;
@@ -421,15 +444,35 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   auto tma_ok = [&](const void* ptr, int esz) {
     return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (static_cast<long>(g.ldc) * esz) % 16 == 0;
   };
-  CUtensorMap tc = ta;
+  maps->c = maps->a;
   p.tma_out = kOutDirect;
   if (g.out_f32 != nullptr && tma_ok(g.out_f32, 4)) {
     p.tma_out = g.atomic_f32 ? kOutTmaAddF32 : kOutTmaF32;
-    if ((rc = make_tmap(&tc, g.out_f32, g.N, g.M, g.ldc, 32, 32, true))) return rc;
+    if ((rc = make_tmap(&maps->c, g.out_f32, g.N, g.M, g.ldc, 32, 32, true))) return rc;
   } else if (g.out_bf16 != nullptr && g.out_f32 == nullptr && tma_ok(g.out_bf16, 2)) {
     p.tma_out = kOutTmaBf16;
-    if ((rc = make_tmap(&tc, g.out_bf16, g.N, g.M, g.ldc, 64, 32))) return rc;
+    if ((rc = make_tmap(&maps->c, g.out_bf16, g.N, g.M, g.ldc, 64, 32))) return rc;
   }
+  *out = p;
+  return 0;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+int launch_gemm(const GemmArgs& g0, const GemmArgs* g1, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  GemmMaps m0, m1;
+  GemmDevParams p0, p1;
+  if (int rc = build_problem<BLOCK_N, A_MN, B_MN>(g0, &m0, &p0)) return rc;
+  const long t0 = (long)p0.num_m_blocks * p0.num_n_blocks * p0.k_splits;
+  long t1 = 0;
+  if (g1 != nullptr) {
+    if (int rc = build_problem<BLOCK_N, A_MN, B_MN>(*g1, &m1, &p1)) return rc;
+    t1 = (long)p1.num_m_blocks * p1.num_n_blocks * p1.k_splits;
+  } else {
+    m1 = m0;
+    p1 = p0;
+  }
+  CTI_REQUIRE(t0 + t1 < (1L << 30), "gemm: too many tiles");
 
   static bool attr_set = false;
   auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN>;
@@ -441,11 +484,45 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     }
     attr_set = true;
   }
-  const long total = (long)p.num_m_blocks * p.num_n_blocks * p.k_splits;
-  int sms = g.max_ctas > 0 ? g.max_ctas : kNumSMsB200;
+  const long total = t0 + t1;
+  int sms = g0.max_ctas > 0 ? g0.max_ctas : kNumSMsB200;
   const int grid = (int)(total < sms ? total : sms);
-  launch_pdl(kern, dim3(grid), dim3(kGemmThreads), Cfg::SMEM_BYTES, stream, ta, tb, tc, p);
+  launch_pdl(kern, dim3(grid), dim3(kGemmThreads), Cfg::SMEM_BYTES, stream, m0, m1, p0, p1, (int)t0, (int)total);
   return check_launch("gemm_bf16_kernel");
+}
+
+int check_gemm_args(const GemmArgs& g) {
+  CTI_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
+  CTI_REQUIRE(g.out_bf16 != nullptr || g.out_f32 != nullptr, "gemm: no output buffer");
+  CTI_REQUIRE(!g.atomic_f32 || g.out_f32 != nullptr, "gemm: split-K accumulation needs an fp32 output");
+  CTI_REQUIRE(g.atomic_f32 || g.k_splits <= 1, "gemm: k_splits > 1 needs atomic_f32");
+  return 0;
+}
+
+long tiles256_of(const GemmArgs& g) {
+  return (long)((g.M + BLOCK_M - 1) / BLOCK_M) * ((g.N + 255) / 256) * (g.k_splits < 1 ? 1 : g.k_splits);
+}
+
+int dispatch_gemm(const GemmArgs& g0, const GemmArgs* g1, cudaStream_t stream) {
+  // Small-N problems and very small grids use the 128-wide tile so more CTAs get work.  Measured (tools/tile_sweep.py):
+  // the 256-wide tile wins from ~64 tiles on (6144 x 512 x 1024: 11.3 vs 15.0 us; the GRU step 1024 x 3072 x 1024:
+  // 11.4 vs 15.4 us) even though the grid no longer fills 148 SMs -- half as many B-operand bytes per FLOP; below
+  // that (1024 x 1024 x 1024, 32 tiles) the narrow tile is ahead by ~1 us.  A pair is sized as one problem.
+  const long tiles256 = tiles256_of(g0) + (g1 ? tiles256_of(*g1) : 0);
+  const int minN = g1 ? (g0.N < g1->N ? g0.N : g1->N) : g0.N;
+  const int forced = g0.tile_n != 0 ? g0.tile_n : (g1 ? g1->tile_n : 0);
+  const bool use256 = (forced == 256) || (forced == 0 && minN >= 256 && tiles256 >= 64);
+  if (use256) {
+    if (!g0.a_mn_major && !g0.b_mn_major) return launch_gemm<256, false, false>(g0, g1, stream);
+    if (!g0.a_mn_major && g0.b_mn_major) return launch_gemm<256, false, true>(g0, g1, stream);
+    if (g0.a_mn_major && g0.b_mn_major) return launch_gemm<256, true, true>(g0, g1, stream);
+  } else {
+    if (!g0.a_mn_major && !g0.b_mn_major) return launch_gemm<128, false, false>(g0, g1, stream);
+    if (!g0.a_mn_major && g0.b_mn_major) return launch_gemm<128, false, true>(g0, g1, stream);
+    if (g0.a_mn_major && g0.b_mn_major) return launch_gemm<128, true, true>(g0, g1, stream);
+  }
+  set_error("gemm: A MN-major with B K-major is not instantiated");
+  return -1;
 }
 
 }  // namespace
@@ -491,27 +568,18 @@ int make_tmap_4d(CUtensorMap* map, const void* ptr, const uint64_t (&dims)[4], c
 }
 
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
-  CTI_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
-  CTI_REQUIRE(g.out_bf16 != nullptr || g.out_f32 != nullptr, "gemm: no output buffer");
-  CTI_REQUIRE(!g.atomic_f32 || g.out_f32 != nullptr, "gemm: split-K accumulation needs an fp32 output");
-  CTI_REQUIRE(g.atomic_f32 || g.k_splits <= 1, "gemm: k_splits > 1 needs atomic_f32");
-  // Small-N problems and very small grids use the 128-wide tile so more CTAs get work.  Measured (tools/tile_sweep.py):
-  // the 256-wide tile wins from ~64 tiles on (6144 x 512 x 1024: 11.3 vs 15.0 us; the GRU step 1024 x 3072 x 1024:
-  // 11.4 vs 15.4 us) even though the grid no longer fills 148 SMs -- half as many B-operand bytes per FLOP; below
-  // that (1024 x 1024 x 1024, 32 tiles) the narrow tile is ahead by ~1 us.
-  const long tiles256 = (long)((g.M + BLOCK_M - 1) / BLOCK_M) * ((g.N + 255) / 256) * (g.k_splits < 1 ? 1 : g.k_splits);
-  const bool use256 = (g.tile_n == 256) || (g.tile_n == 0 && g.N >= 256 && tiles256 >= 64);
-  if (use256) {
-    if (!g.a_mn_major && !g.b_mn_major) return launch_gemm<256, false, false>(g, stream);
-    if (!g.a_mn_major && g.b_mn_major) return launch_gemm<256, false, true>(g, stream);
-    if (g.a_mn_major && g.b_mn_major) return launch_gemm<256, true, true>(g, stream);
-  } else {
-    if (!g.a_mn_major && !g.b_mn_major) return launch_gemm<128, false, false>(g, stream);
-    if (!g.a_mn_major && g.b_mn_major) return launch_gemm<128, false, true>(g, stream);
-    if (g.a_mn_major && g.b_mn_major) return launch_gemm<128, true, true>(g, stream);
-  }
-  set_error("gemm: A MN-major with B K-major is not instantiated");
-  return -1;
+  if (int rc = check_gemm_args(g)) return rc;
+  return dispatch_gemm(g, nullptr, stream);
+}
+
+// Two independent problems with the same operand layouts in one launch (see gemm_bf16_kernel).
+int gemm_bf16_pair(const GemmArgs& g0, const GemmArgs& g1, cudaStream_t stream) {
+  if (int rc = check_gemm_args(g0)) return rc;
+  if (int rc = check_gemm_args(g1)) return rc;
+  CTI_REQUIRE(g0.a_mn_major == g1.a_mn_major && g0.b_mn_major == g1.b_mn_major,
+              "gemm pair: both problems must use the same operand layouts");
+  CTI_REQUIRE(g0.tile_n == g1.tile_n || g0.tile_n == 0 || g1.tile_n == 0, "gemm pair: conflicting forced tile widths");
+  return dispatch_gemm(g0, &g1, stream);
 }
 
 }  // namespace cti

@@ -200,13 +200,14 @@ def rank_proj_fwd(y: torch.Tensor, pk: Packed, bias: torch.Tensor, drop, R: int)
     N = pk.w.shape[0]
     d = N // R
     rg = RANK_GROUP if R % RANK_GROUP == 0 else 1
-    wt = _block_diag_weights(pk.w, R, rg)
     out = torch.empty((M, N), dtype=BF16, device=y.device)
     b = bias.detach()
-    for gi in range(R // rg):
-        xt = K_.dropout_expand(y, rg, gi * rg, drop)
-        K_.gemm(xt, wt[gi], M, rg * d, rg * H, bias=b[gi * rg * d:(gi + 1) * rg * d], relu=True,
-                out=out[:, gi * rg * d:(gi + 1) * rg * d])
+    with K_.gemm_unbatched():                        # torch ops below read what earlier GEMMs wrote
+        wt = _block_diag_weights(pk.w, R, rg)
+        for gi in range(R // rg):
+            xt = K_.dropout_expand(y, rg, gi * rg, drop)
+            K_.gemm(xt, wt[gi], M, rg * d, rg * H, bias=b[gi * rg * d:(gi + 1) * rg * d], relu=True,
+                    out=out[:, gi * rg * d:(gi + 1) * rg * d])
     return out
 
 
@@ -220,15 +221,16 @@ def rank_proj_bwd(y: torch.Tensor, dz: torch.Tensor, V: torch.Tensor, g: torch.T
     dw = torch.empty((N, H), dtype=F32, device=y.device)
     acc = torch.zeros((M, H), dtype=F32, device=y.device)
     splits = _pick_splits(-(-rg * d // 128) * -(-rg * H // 256), -(-M // 64))
-    for gi in range(R // rg):
-        xt = K_.dropout_expand(y, rg, gi * rg, drop)                     # same masks as the forward
-        dzg = dz[:, gi * rg * d:(gi + 1) * rg * d]
-        dwt = torch.zeros((rg * d, rg * H), dtype=F32, device=y.device)
-        K_.gemm(dzg, xt, rg * d, rg * H, M, a_mn=True, b_mn=True, accum_f32=dwt, k_splits=splits, tile_n=256)
-        for j in range(rg):
-            dw[(gi * rg + j) * d:(gi * rg + j + 1) * d] = dwt[j * d:(j + 1) * d, j * H:(j + 1) * H]
-        dxt, _ = K_.gemm(dzg, wt[gi], M, rg * H, rg * d, b_mn=True)
-        K_.dropout_reduce_(dxt, acc, rg, gi * rg, drop)
+    with K_.gemm_unbatched():                        # torch ops below read what the GEMMs wrote
+        for gi in range(R // rg):
+            xt = K_.dropout_expand(y, rg, gi * rg, drop)                     # same masks as the forward
+            dzg = dz[:, gi * rg * d:(gi + 1) * rg * d]
+            dwt = torch.zeros((rg * d, rg * H), dtype=F32, device=y.device)
+            K_.gemm(dzg, xt, rg * d, rg * H, M, a_mn=True, b_mn=True, accum_f32=dwt, k_splits=splits, tile_n=256)
+            for j in range(rg):
+                dw[(gi * rg + j) * d:(gi * rg + j + 1) * d] = dwt[j * d:(j + 1) * d, j * H:(j + 1) * H]
+            dxt, _ = K_.gemm(dzg, wt[gi], M, rg * H, rg * d, b_mn=True)
+            K_.dropout_reduce_(dxt, acc, rg, gi * rg, drop)
     if pk.dw is not None:                            # deferred weight-norm backward (see Packed)
         pk.dw.copy_(dw)
         return pk.dw, None, acc
@@ -337,9 +339,10 @@ class TriLogitsFn(Function):
                             for i in range(6)]
         xq = cast_tokens(q, dq)
         xa = cast_tokens(a, da)
-        yv, _ = lin_fwd(v_bf16, pk[0], w[2], True)
-        yq, _ = lin_fwd(xq, pk[1], w[5], True)
-        ya, _ = lin_fwd(xa, pk[2], w[8], True)
+        with K_.gemm_batch():                 # the question- and answer-side projections share one launch
+            yv, _ = lin_fwd(v_bf16, pk[0], w[2], True)
+            yq, _ = lin_fwd(xq, pk[1], w[5], True)
+            ya, _ = lin_fwd(xa, pk[2], w[8], True)
         independent = RANK_DROPOUT == "independent"
         ctx.independent = independent
         ctx.drops = (dq, da, dvn, dqn, dan)
@@ -352,9 +355,10 @@ class TriLogitsFn(Function):
             # shared mask: the dropped copy doubles as the ReLU-and-dropout mask of the dgrad epilogue
             yd = K_.dropout_bf16(y, drop)
             return yd, lin_fwd(yd, pki, bias, True)[0]
-        yv, vc = rank_nets(yv, pk[3], w[11], dvn)
-        yq, qc = rank_nets(yq, pk[4], w[14], dqn)
-        ya, ac = rank_nets(ya, pk[5], w[17], dan)
+        with K_.gemm_batch():
+            yv, vc = rank_nets(yv, pk[3], w[11], dvn)
+            yq, qc = rank_nets(yq, pk[4], w[14], dqn)
+            ya, ac = rank_nets(ya, pk[5], w[17], dan)
         tpack = pack_core(T_g)
         # training: the kernel also leaves its bf16 N1 intermediate in HBM, the backward picks it up instead of recomputing it
         n1 = None
@@ -395,19 +399,31 @@ class TriLogitsFn(Function):
         for j, i in enumerate(need):
             zs[i if i < 3 else i + 3] = slab[3 + j]
 
-        def rank_nets_bwd(y, dz, V, g, pki, drop, dw_, db_):
-            """-> dV, dg, pre-activation gradient of the tucker layer (bf16) and its bias gradient"""
+        def rank_nets_bwd(y, dz, V, g, pki, drop, dw_):
+            """-> dV, dg, pre-activation gradient of the tucker layer (bf16); None where its ReLU mask / bias sum is
+            still to be applied (independent per-rank dropout: the fp32 accumulator comes back instead)"""
             if drop is not None and ctx.independent:
                 dV_, dg_, acc = rank_proj_bwd(y, dz, V, g, pki, drop, R)
-                return dV_, dg_, K_.act_bwd_bias(acc, y, True, db_), db_
+                return dV_, dg_, None, acc
             dV_, dg_, dzt = lin_bwd(y, dz, V, g, pki, R, True, dx_relu_aux=y, dx_alpha=sc(drop), dw=dw_)
-            return dV_, dg_, dzt, _colsum(dzt, H, db_)
-        dVvn, dgvn, dzvt, dbvt = rank_nets_bwd(yv, dzv, w[9], w[10], pk[3], dvn, zs[0], zs[3])
-        dVqn, dgqn, dzqt, dbqt = rank_nets_bwd(yq, dzq, w[12], w[13], pk[4], dqn, zs[1], zs[4])
-        dVan, dgan, dzat, dbat = rank_nets_bwd(ya, dza, w[15], w[16], pk[5], dan, zs[2], zs[5])
-        dVvt, dgvt, _ = lin_bwd(v_bf16, dzvt, w[0], w[1], pk[0], 1, False, dw=zs[6])
-        dVqt, dgqt, dq = lin_bwd(xq, dzqt, w[3], w[4], pk[1], 1, ctx.need[0], dx_f32=True, dw=zs[7])
-        dVat, dgat, da = lin_bwd(xa, dzat, w[6], w[7], pk[2], 1, ctx.need[1], dx_f32=True, dw=zs[8])
+            return dV_, dg_, dzt, None
+
+        def finish(y, dzt, acc, db_):
+            if dzt is None:
+                return K_.act_bwd_bias(acc, y, True, db_), db_
+            return dzt, _colsum(dzt, H, db_)
+        # the GEMMs of the three modalities are independent: the question- and answer-side ones pair up (gemm_batch)
+        with K_.gemm_batch():
+            dVvn, dgvn, dzvt, accv = rank_nets_bwd(yv, dzv, w[9], w[10], pk[3], dvn, zs[0])
+            dVqn, dgqn, dzqt, accq = rank_nets_bwd(yq, dzq, w[12], w[13], pk[4], dqn, zs[1])
+            dVan, dgan, dzat, acca = rank_nets_bwd(ya, dza, w[15], w[16], pk[5], dan, zs[2])
+        dzvt, dbvt = finish(yv, dzvt, accv, zs[3])
+        dzqt, dbqt = finish(yq, dzqt, accq, zs[4])
+        dzat, dbat = finish(ya, dzat, acca, zs[5])
+        with K_.gemm_batch():
+            dVvt, dgvt, _ = lin_bwd(v_bf16, dzvt, w[0], w[1], pk[0], 1, False, dw=zs[6])
+            dVqt, dgqt, dq = lin_bwd(xq, dzqt, w[3], w[4], pk[1], 1, ctx.need[0], dx_f32=True, dw=zs[7])
+            dVat, dgat, da = lin_bwd(xa, dzat, w[6], w[7], pk[2], 1, ctx.need[1], dx_f32=True, dw=zs[8])
         dT = unpack_core_grad(dtpack, T_g)
         if dq is not None:
             if dq_drop is not None:
@@ -503,12 +519,14 @@ class PoolFn(Function):
                 v_bf16 = drop_features(v_f32, dv)
         ctx.drops = (dq_drop, da_drop)
         xq = cast_tokens(q, dq_drop)
-        vp, _ = lin_fwd(v_bf16, pk[0], w[2], True)
-        qp, _ = lin_fwd(xq, pk[1], w[5], True)
         xa = ap = None
         if A > 0:
             xa = cast_tokens(a, da_drop)
-            ap, _ = lin_fwd(xa, pk[2], w[8], True)
+        with K_.gemm_batch():                 # the question- and answer-side projections share one launch
+            vp, _ = lin_fwd(v_bf16, pk[0], w[2], True)
+            qp, _ = lin_fwd(xq, pk[1], w[5], True)
+            if A > 0:
+                ap, _ = lin_fwd(xa, pk[2], w[8], True)
         wd = _sample_contiguous(wts.detach())
         if wd.dtype != F32:
             wd = wd.float()
@@ -533,12 +551,14 @@ class PoolFn(Function):
         zs = [None] * 3
         for j, i in enumerate(need):
             zs[i] = slab[j]
-        dVv, dgv, _ = lin_bwd(v_bf16, dzv, w[0], w[1], pk[0], 1, False, dw=zs[0])
-        dVq, dgq, dq = lin_bwd(xq, dzq, w[3], w[4], pk[1], 1, ctx.need[0], dx_f32=True, dw=zs[1])
-        grads = [dVv, dgv, dbv, dVq, dgq, dbq]
         da = None
+        with K_.gemm_batch():
+            dVv, dgv, _ = lin_bwd(v_bf16, dzv, w[0], w[1], pk[0], 1, False, dw=zs[0])
+            dVq, dgq, dq = lin_bwd(xq, dzq, w[3], w[4], pk[1], 1, ctx.need[0], dx_f32=True, dw=zs[1])
+            if A > 0:
+                dVa, dga, da = lin_bwd(xa, dza, w[6], w[7], pk[2], 1, ctx.need[1], dx_f32=True, dw=zs[2])
+        grads = [dVv, dgv, dbv, dVq, dgq, dbq]
         if A > 0:
-            dVa, dga, da = lin_bwd(xa, dza, w[6], w[7], pk[2], 1, ctx.need[1], dx_f32=True, dw=zs[2])
             grads += [dVa, dga, dba]
             if da is not None:
                 if ctx.drops[1] is not None:

@@ -36,8 +36,83 @@ class _Stats:
 STATS = _Stats()
 
 
+# GEMMs issued inside ``with gemm_batch():`` are queued (their outputs are allocated and returned at once) and launched
+# when the block ends -- or earlier, as soon as anything that could depend on them is launched: any other kernel of the
+# library, or a GEMM that reads a queued GEMM's output.  Queued GEMMs are therefore mutually independent, and those
+# with the same operand layouts go out two per launch (cti_gemm_bf16_pair).
+_PENDING = [None]          # None outside a batch, else the list of queued GEMMs
+
+
+class gemm_batch:
+    def __enter__(self):
+        self.outer = _PENDING[0] is not None
+        if not self.outer:
+            _PENDING[0] = []
+        return self
+
+    def __exit__(self, *exc):
+        if not self.outer:
+            try:
+                if exc[0] is None:
+                    _flush_gemms()
+            finally:
+                _PENDING[0] = None
+        return False
+
+
+class gemm_unbatched:
+    """Inside a gemm_batch: launch what is queued and run the enclosed GEMMs immediately (code that hands GEMM outputs to
+    torch ops, which the queue cannot see)."""
+    def __enter__(self):
+        self.was = _PENDING[0] is not None
+        if self.was:
+            _flush_gemms()
+            _PENDING[0] = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.was:
+            _PENDING[0] = []
+        return False
+
+
+def _flush_gemms() -> None:
+    q = _PENDING[0]
+    if not q:
+        return
+    _PENDING[0] = None                       # the launches below go straight out
+    try:
+        lib = _lib.load()
+        groups = {}
+        for e in q:
+            groups.setdefault((e["desc"].a_mn_major, e["desc"].b_mn_major), []).append(e)
+        for es in groups.values():
+            es.sort(key=lambda e: e["flops"])                         # smallest first: (a, q) pair up, v goes alone
+            i = 0
+            while i < len(es):
+                if i + 1 < len(es) and (es[i]["desc"].tile_n == es[i + 1]["desc"].tile_n
+                                        or 0 in (es[i]["desc"].tile_n, es[i + 1]["desc"].tile_n)):
+                    e0, e1 = es[i + 1], es[i]                         # bigger problem first in the tile order
+                    _call("cti_gemm_bf16", lib.cti_gemm_bf16_pair, (e0["desc"], e1["desc"], _stream()),
+                          flops=e0["flops"] + e1["flops"], tag="pair " + e0["tag"] + " + " + e1["tag"])
+                    i += 2
+                else:
+                    e = es[i]
+                    _call("cti_gemm_bf16", lib.cti_gemm_bf16, e["args"], flops=e["flops"], tag=e["tag"])
+                    i += 1
+    finally:
+        _PENDING[0] = []
+        q.clear()
+
+
+def _overlaps(ranges, lo: int, hi: int) -> bool:
+    return any(lo < h and l < hi for l, h in ranges)
+
+
 def _call(name: str, fn, args, kernels: int = 1, flops: float = 0.0, nbytes: float = 0.0, tag: str = "") -> None:
     """One C-ABI call = `kernels` kernel launches on the current stream; algorithmic work for the roofline."""
+    if _PENDING[0]:
+        _flush_gemms()                       # queued GEMMs go first: this launch may read what they write
     STATS.launches += kernels
     prof = STATS.prof
     if prof is None:
@@ -207,11 +282,25 @@ def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool
     of = accum_f32 if accum_f32 is not None else (torch.empty((M, N), dtype=F32, device=a.device) if out_f32 else None)
     if relu_aux is not None:
         _req(relu_aux, BF16, "gemm.relu_aux")
-    _call("cti_gemm_bf16", _lib.load().cti_gemm_bf16, (
-        a.data_ptr(), a.stride(0), int(a_mn), b.data_ptr(), b.stride(0), int(b_mn), M, N, K, float(alpha), _ptr(bias),
-        int(relu), _ptr(relu_aux), 0 if relu_aux is None else relu_aux.shape[1], _ptr(ob), _ptr(of), ldc,
-        int(accum_f32 is not None), int(k_splits), int(tile_n), _stream()), flops=2.0 * M * N * K,
-        tag=f"{'wgrad' if a_mn else ('dgrad' if b_mn else 'fwd')} M={M} N={N} K={K}")
+    tag = f"{'wgrad' if a_mn else ('dgrad' if b_mn else 'fwd')} M={M} N={N} K={K}"
+    args = (a.data_ptr(), a.stride(0), int(a_mn), b.data_ptr(), b.stride(0), int(b_mn), M, N, K, float(alpha), _ptr(bias),
+            int(relu), _ptr(relu_aux), 0 if relu_aux is None else relu_aux.shape[1], _ptr(ob), _ptr(of), ldc,
+            int(accum_f32 is not None), int(k_splits), int(tile_n))
+    pending = _PENDING[0]
+    if pending is None:
+        _call("cti_gemm_bf16", _lib.load().cti_gemm_bf16, args + (_stream(),), flops=2.0 * M * N * K, tag=tag)
+        return ob, of
+    # queued: flush first if this GEMM touches the output of a queued one (reads it, or accumulates into it)
+    span = lambda t: (t.data_ptr(), t.data_ptr() + (t.shape[0] - 1) * t.stride(0) * t.element_size() + t.shape[1] * t.element_size()) \
+        if t.dim() == 2 else (t.data_ptr(), t.data_ptr() + t.numel() * t.element_size())
+    touched = [span(t) for t in (a, b, bias, relu_aux, ob, of) if t is not None]
+    if any(_overlaps(e["writes"], lo, hi) for e in pending for lo, hi in touched):
+        _flush_gemms()
+        pending = _PENDING[0]
+    desc = _lib.GemmDesc(*args)
+    pending.append({"desc": desc, "args": args + (_stream(),), "flops": 2.0 * M * N * K, "tag": tag,
+                    "writes": [span(t) for t in (ob, of) if t is not None],
+                    "keep": (a, b, bias, relu_aux, ob, of)})
     return ob, of
 
 

@@ -108,6 +108,19 @@ int cti_wn_grad(const float* dw_eff, const float* v, const float* g, const float
 int cti_gemm_bf16(const void* a, int lda, int a_mn_major, const void* b, int ldb, int b_mn_major, int M, int N, int K,
                   float alpha, const float* bias, int relu, const void* relu_aux, int ld_aux, void* out_bf16,
                   float* out_f32, int ldc, int atomic_f32, int k_splits, int tile_n, void* stream);
+/* Two independent problems with the same operand layouts in ONE launch (fields as the arguments of cti_gemm_bf16):
+ * the question-side and answer-side projections of a module call (q_net / a_net of src/tc.py:25-27,44-49 and their
+ * autograd) have the same weight shapes and different row counts; alone each leaves SMs idle and pays the launch and
+ * pipeline-fill floor.  The tiles of d0 are scheduled first. */
+typedef struct cti_gemm_desc {
+  const void* a; int lda; int a_mn_major;
+  const void* b; int ldb; int b_mn_major;
+  int M, N, K; float alpha;
+  const float* bias; int relu;
+  const void* relu_aux; int ld_aux;
+  void* out_bf16; float* out_f32; int ldc; int atomic_f32; int k_splits; int tile_n;
+} cti_gemm_desc;
+int cti_gemm_bf16_pair(const cti_gemm_desc* d0, const cti_gemm_desc* d1, void* stream);
 
 /* ---- activation backward + bias gradient ----------------------------------------------------
  * dz = dy * (y > 0) (y may be NULL: no activation), written as bf16 (dz may be NULL);

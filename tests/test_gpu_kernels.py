@@ -76,6 +76,48 @@ def test_gemm_wgrad_layout_splitk(rows, N, Kin, splits):
         assert rel_err(acc, ref) < 1e-4
 
 
+@pytest.mark.parametrize("Mq,Ma,N,K", [(1536, 768, 1024, 1024), (12288, 6144, 512, 512), (300, 77, 136, 72), (96, 2000, 512, 256)])
+def test_gemm_batch_pairs_independent_problems(Mq, Ma, N, K):
+    """Inside gemm_batch() two GEMMs with the same operand layouts leave in ONE launch (cti_gemm_bf16_pair); results are
+    bit-identical to the separate launches (forward, dgrad) or equal up to the split-K summation order (wgrad)."""
+    g = torch.Generator(device=DEV).manual_seed(Mq + N)
+    mk = lambda *sh: bf(torch.randn(*sh, device=DEV, generator=g))
+    xq, xa, wq, wa = mk(Mq, K), mk(Ma, K), mk(N, K) / K ** 0.5, mk(N, K) / K ** 0.5
+    bq, ba = torch.randn(N, device=DEV, generator=g), torch.randn(N, device=DEV, generator=g)
+    want_q, _ = K_.gemm(xq, wq, Mq, N, K, bias=bq, relu=True)
+    want_a, _ = K_.gemm(xa, wa, Ma, N, K, bias=ba, relu=True)
+    n0 = K_.STATS.launches
+    with K_.gemm_batch():
+        yq, _ = K_.gemm(xq, wq, Mq, N, K, bias=bq, relu=True)
+        ya, _ = K_.gemm(xa, wa, Ma, N, K, bias=ba, relu=True)
+    assert K_.STATS.launches - n0 == 1
+    assert torch.equal(yq, want_q) and torch.equal(ya, want_a)
+    assert rel_err(yq, torch.relu(xq.float() @ wq.float().t() + bq)) < 5e-3
+    # dgrad pair (B MN-major, ReLU-mask aux on one side, fp32 output on the other) + wgrad pair (split-K) in one batch:
+    # four queued GEMMs, two launches
+    dzq, dza = mk(Mq, N), mk(Ma, N)
+    aux = mk(Mq, K)
+    accq, acca = torch.zeros(N, K, device=DEV), torch.zeros(N, K, device=DEV)
+    n0 = K_.STATS.launches
+    with K_.gemm_batch():
+        K_.gemm(dzq, xq, N, K, Mq, a_mn=True, b_mn=True, accum_f32=accq, k_splits=3)
+        dxq, _ = K_.gemm(dzq, wq, Mq, K, N, b_mn=True, relu_aux=aux)
+        K_.gemm(dza, xa, N, K, Ma, a_mn=True, b_mn=True, accum_f32=acca, k_splits=2)
+        _, dxa = K_.gemm(dza, wa, Ma, K, N, b_mn=True, out_bf16=False, out_f32=True)
+    assert K_.STATS.launches - n0 == 2
+    assert rel_err(accq, dzq.float().t() @ xq.float()) < 1e-4 and rel_err(acca, dza.float().t() @ xa.float()) < 1e-4
+    assert rel_err(dxq, (dzq.float() @ wq.float()) * (aux.float() > 0)) < 5e-3
+    assert rel_err(dxa, dza.float() @ wa.float()) < 2e-5
+    # a GEMM that reads a queued GEMM's output flushes the queue first (no pairing of dependent problems)
+    n0 = K_.STATS.launches
+    with K_.gemm_batch():
+        h, _ = K_.gemm(xq, wq, Mq, N, K, bias=bq, relu=True)
+        w2 = mk(N, N) / N ** 0.5
+        y2, _ = K_.gemm(h, w2, Mq, N, N)
+    assert K_.STATS.launches - n0 == 2
+    assert rel_err(y2, want_q.float() @ w2.float().t()) < 5e-3
+
+
 def test_gemm_rejects_bad_arguments():
     a = bf(torch.randn(8, 12, device=DEV))          # pitch 24 B: not a multiple of 16
     b = bf(torch.randn(8, 12, device=DEV))

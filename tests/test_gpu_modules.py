@@ -62,7 +62,8 @@ class record_relu_outputs:
 
         def lin_fwd(x, pk, bias, relu, out_bf16=True, out_f32=False):
             res = self.orig(x, pk, bias, relu, out_bf16, out_f32)
-            self.outs.append(res[0].detach().float().cpu() if relu else None)
+            # keep the tensor, read it later: inside a gemm_batch() the launch is still queued when lin_fwd returns
+            self.outs.append(res[0].detach() if relu else None)
             return res
         F_.lin_fwd = lin_fwd
         return self
@@ -77,6 +78,7 @@ class record_relu_outputs:
         for pre, y in zip(prefixes, self.outs):
             if pre is None:
                 continue
+            y = y.float().cpu()
             if isinstance(pre, str):
                 out[pre] = (y > 0).float()
             else:
