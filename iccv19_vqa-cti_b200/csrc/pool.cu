@@ -8,7 +8,9 @@
 //             out[c]   = sum_a Ap[a,c] sum_q Qp[q,c] Z[c,(a,q)]   epilogue: a per-thread dot product
 //   backward  dQp, dAp from Z (same epilogue shape);  KRd[c,n] = do[c] Qp[q,c] Ap[a,c] written to
 //             shared memory ONCE and used by two more MMAs:
-//             dV[c,k]  = sum_n KRd[c,n] w[k,n]                     128 x 64 x 16, K = columns n
+//             dV[k,c]  = sum_n w[k,n] KRd[c,n]                     128 x 128 x 16, K = columns n, TMEM lane = token k:
+//                        every thread then owns 64 consecutive channels of one dzv row (16-byte stores; the first
+//                        version had the channel on the lane and wrote 50 two-byte values per thread and chunk)
 //             dw[k,n] += sum_c V[k,c] KRd[c,n]                     128 x NC x 16, K = channels (all chunks)
 // The (B,C,K,Q,A) broadcast product of the reference's einsum never exists; V is read from HBM
 // once per pass (TMA, 128B swizzle).  Every operand tile lives in shared memory in the TMA
@@ -32,7 +34,7 @@ namespace {
 using bf16 = __nv_bfloat16;
 
 constexpr int kThreads = 384;                 // forward
-constexpr int kThreadsBwd = 768;              // backward: warps 12-15 and 20-23 split the dV epilogue (12-15 also dw), warps 16-19 share the Z epilogue (odd chunks)
+constexpr int kThreadsBwd = 768;              // backward: warps 12, 13 / 20, 21 take the two channel halves of the dV epilogue (12, 13 also dw), warps 16-19 share the Z epilogue (odd chunks)
 constexpr int kEpiWarp0 = 4;
 constexpr int kBuildWarp0 = 8;
 constexpr int CCH = 128;                       // channels per chunk = TMEM lanes
@@ -48,7 +50,7 @@ constexpr int KRD_BYTES = 2 * CCH * 128;       // two 64-column chunks x 128 cha
 constexpr int MAX_C = 1024;
 
 // TMEM column map
-constexpr uint32_t TM_Z = 0, TM_DV = 256, TM_DW = 384;     // Z: 2 x 128, dV: 2 x 64, dw: 128
+constexpr uint32_t TM_Z = 0, TM_DV = 256, TM_DW = 384;     // Z: 2 x 128, dV: 128 (token lanes x channels), dw: 128
 
 struct PoolParams {
   const bf16* q;
@@ -106,7 +108,7 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < V_STAGES; ++s) {
       mbar_init(bar(B_VFULL + s), 1);
-      mbar_init(bar(B_VEMPTY + s), BWD ? 13 : 5);     // MMA commit + every epilogue warp that reads the stage
+      mbar_init(bar(B_VEMPTY + s), BWD ? 9 : 5);      // MMA commit + every epilogue warp that reads the stage
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar(B_WFULL + s), 128);
@@ -116,10 +118,10 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ 
       mbar_init(bar(B_KFULL + s), 4);
       mbar_init(bar(B_KEMPTY + s), 1);
       mbar_init(bar(B_DFULL + s), 1);
-      mbar_init(bar(B_DEMPTY + s), 8);
+      mbar_init(bar(B_DEMPTY + s), 4);
     }
     mbar_init(bar(B_DWFULL), 1);
-    mbar_init(bar(B_DWEMPTY), 4);
+    mbar_init(bar(B_DWEMPTY), 2);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -159,7 +161,7 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ 
     // ------------------------------ MMA issuer ------------------------------------------
     if (elect_one_sync()) {
       const uint32_t id_z = make_idesc_rt(128, p.NC, 1, 1);
-      const uint32_t id_dv = make_idesc_rt(128, 64, 0, 0);
+      const uint32_t id_dv = make_idesc_rt(128, CCH, 0, 0);
       const uint32_t id_dw = make_idesc_rt(128, p.NC, 0, 1);
       auto issue_z = [&](int g) {
         const int sl = g / p.nchunks, ch = g % p.nchunks;
@@ -187,12 +189,14 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ 
         const uint32_t krd = sK + (g & 1) * KRD_BYTES;
         const uint32_t vst = sV + (g % V_STAGES) * V_STAGE_BYTES;
         mbar_wait(bar(B_KFULL + (g & 1)), (g >> 1) & 1);
-        mbar_wait(bar(B_DEMPTY + (g & 1)), ((g >> 1) & 1) ^ 1);
+        mbar_wait(bar(B_DEMPTY), (g & 1) ^ 1);
         tcgen05_fence_after();
+        // A = w tile (rows = tokens; 64 rows per chunk, the upper 64 accumulator lanes read whatever follows and are
+        // never read back), B = KRd (rows = channels)
         for (int ks = 0; ks < kcol; ++ks)
-          umma_bf16_ss(tmem_base + TM_DV + (g & 1) * 64, desc_kmajor(krd + (ks >> 2) * (CCH * 128), ks & 3),
-                       desc_kmajor(wbuf + (ks >> 2) * (KP * 128), ks & 3), id_dv, ks > 0 ? 1u : 0u);
-        umma_commit(bar(B_DFULL + (g & 1)));
+          umma_bf16_ss(tmem_base + TM_DV, desc_kmajor(wbuf + (ks >> 2) * (KP * 128), ks & 3),
+                       desc_kmajor(krd + (ks >> 2) * (CCH * 128), ks & 3), id_dv, ks > 0 ? 1u : 0u);
+        umma_commit(bar(B_DFULL));
         if (ch == 0) {
           mbar_wait(bar(B_DWEMPTY), (sl & 1) ^ 1);
           tcgen05_fence_after();
@@ -288,42 +292,50 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ 
       s.dout = BWD ? ld_shared_f32(st + ST_DO + cl * 4) : 0.f;
     };
 
-    // two warp groups split the token blocks of the dV tile (the slowest stage of the pipeline: 64 masked 2-byte
-    // stores per thread and chunk); group 0 also drains the sample's dw tile
-    auto epi_b = [&](int h, int half) {          // dV of chunk h: ReLU mask from the V tile, dzv, bias gradient; then dw
+    // dV epilogue: TMEM lane = token k (warps on lanes 0-63), `half` = which 64 channels of the chunk.  ReLU mask from
+    // the V tile row of the same token, 128 contiguous bytes of dzv per thread; group 0 also drains the sample's dw tile.
+    // (The image-side bias gradient is the column sum of dzv: a separate streaming pass, see tri_pool_bwd.)
+    auto epi_b = [&](int h, int half) {
       const int sl = h / p.nchunks, ch = h % p.nchunks;
-      const int b = blockIdx.x + sl * gridDim.x, c = ch * CCH + cl;
-      mbar_wait(bar(B_DFULL + (h & 1)), (h >> 1) & 1);
+      const int b = blockIdx.x + sl * gridDim.x;
+      const int k = cl;                                   // token = TMEM lane
+      mbar_wait(bar(B_DFULL), h & 1);
       tcgen05_fence_after();
-      const uint32_t vst = sV + (h % V_STAGES) * V_STAGE_BYTES + (cl >> 6) * (KP * 128);
-      float colsum = 0.f;
-      const int kk_mid = (ktok + 1) >> 1;
-      for (int kk = half ? kk_mid : 0; kk < (half ? ktok : kk_mid); ++kk) {
-        uint32_t r[16];
-        tmem_ld_32x32b_x16(tmem_base + lane_addr + TM_DV + (h & 1) * 64 + kk * 16, r);
+      const uint32_t vrow = sV + (h % V_STAGES) * V_STAGE_BYTES + half * (KP * 128) + (k >> 3) * 1024u + (k & 7) * 128u;
+      bf16* dst = p.dzv + ((size_t)b * p.K + k) * p.C + ch * CCH + half * 64;
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_addr + TM_DV + half * 64 + t * 32, r);
         tmem_wait_ld();
+        if (t == 1) {                                     // every TMEM read of this tile is done
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(B_DEMPTY));
+        }
+        if (k < p.K) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int k = kk * 16 + j;
-          if (k < p.K) {
-            const float vv = bf16_bits_to_float(ld_shared_u16(vst + sw128_off(k, cl & 63)));
-            const float gv = vv > 0.f ? __uint_as_float(r[j]) : 0.f;
-            p.dzv[((size_t)b * p.K + k) * p.C + c] = __float2bfloat16(gv);
-            colsum += gv;
+          for (int j = 0; j < 4; ++j) {
+            uint32_t vv[4];
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(vv[0]), "=r"(vv[1]), "=r"(vv[2]), "=r"(vv[3])
+                         : "r"(vrow + ((((uint32_t)(t * 4 + j)) ^ (k & 7)) << 4)));
+            uint32_t o[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+              const float2 f = unpack_bf16x2(vv[x]);
+              o[x] = pack_bf16x2(f.x > 0.f ? __uint_as_float(r[j * 8 + 2 * x]) : 0.f,
+                                 f.y > 0.f ? __uint_as_float(r[j * 8 + 2 * x + 1]) : 0.f);
+            }
+            reinterpret_cast<uint4*>(dst + t * 32)[j] = make_uint4(o[0], o[1], o[2], o[3]);
           }
         }
       }
-      atomicAdd(db_acc + c, colsum);         // the two groups own the same channel
-      tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(bar(B_DEMPTY + (h & 1)));
-        mbar_arrive(bar(B_VEMPTY + h % V_STAGES));
-      }
+      if (lane == 0) mbar_arrive(bar(B_VEMPTY + h % V_STAGES));
       if (half == 0 && ch == p.nchunks - 1) {       // the sample's dw tile is complete: lane = token
         mbar_wait(bar(B_DWFULL), sl & 1);
         tcgen05_fence_after();
-        const int k = cl;
         for (int ai = 0; ai < p.An; ++ai) {
           uint32_t r[16];
           tmem_ld_32x32b_x16(tmem_base + lane_addr + TM_DW + ai * 16, r);
@@ -342,9 +354,11 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ 
 
     if (BWD && ((warp >= 12 && warp < 16) || warp >= 20)) {
       const int half = warp >= 20 ? 1 : 0;
-      for (int h = 0; h < total; ++h) {
-        mbar_wait(bar(B_VFULL + h % V_STAGES), (h / V_STAGES) & 1);      // TMA data of the stage visible to this thread
-        epi_b(h, half);
+      if (qd < 2) {                          // token lanes 0-63; the other warps of the two groups have nothing to do
+        for (int h = 0; h < total; ++h) {
+          mbar_wait(bar(B_VFULL + h % V_STAGES), (h / V_STAGES) & 1);      // TMA data of the stage visible to this thread
+          epi_b(h, half);
+        }
       }
     } else {
     Side cur;
@@ -425,7 +439,6 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ 
   __syncthreads();
   if (BWD) {
     for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
-      atomicAdd(p.dbv + c, db_acc[c]);
       atomicAdd(p.dbq + c, db_acc[MAX_C + c]);
       if (p.A > 0) atomicAdd(p.dba + c, db_acc[2 * MAX_C + c]);
     }
@@ -500,7 +513,9 @@ int tri_pool_bwd(const bf16* v, const bf16* q, const bf16* a, const float* w, lo
   if (d.B == 0) return 0;
   PoolParams p = make_params(q, a, w, w_stride_b, d);
   p.dout = dout; p.dzv = dzv; p.dzq = dzq; p.dza = dza; p.dbv = dbv; p.dbq = dbq; p.dba = dba; p.dw = dw;
-  return launch_pool<true>(v, p, stream, "tri_pool_bwd");
+  if (int rc = launch_pool<true>(v, p, stream, "tri_pool_bwd")) return rc;
+  // image-side bias gradient: column sums of dzv (token-on-lane epilogue: no cheap in-kernel reduction over tokens)
+  return act_bwd_bias(dzv, 1, nullptr, nullptr, dbv, (long)d.B * d.K, d.C, stream);
 }
 
 }  // namespace cti
