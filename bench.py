@@ -401,15 +401,19 @@ def run_b200(args):
             v_h16 = v_h.to(torch.bfloat16).pin_memory()
             m_h = (v_h.abs().sum(2) == 0).to(torch.uint8).pin_memory()
 
+            q_h16, a_h16 = q_h.to(torch.bfloat16).pin_memory(), a_h.to(torch.bfloat16).pin_memory()
+
             def pipelined(feat, share):
-                host_src = (v_h16, m_h, q_h, a_h) if feat == "bf16" else (v_h, q_h, a_h)
+                # "bf16": every input in the wire format (features + mask, question / answer token embeddings in bf16);
+                # "bf16v": bf16 features, fp32 tokens; "fp32": what the reference's loader yields
+                host_src = {"bf16": (v_h16, m_h, q_h16, a_h16), "bf16v": (v_h16, m_h, q_h, a_h)}.get(feat, (v_h, q_h, a_h))
                 bufs = [tuple(torch.empty(t.shape, dtype=t.dtype, device=dev) for t in host_src) for _ in range(2)]
                 outs = [torch.empty(B, HID).pin_memory() for _ in range(2)]
                 ev_copied = [torch.cuda.Event() for _ in range(2)]
                 ev_done = [torch.cuda.Event() for _ in range(2)]
 
                 def make_compute(i):
-                    if feat == "bf16":
+                    if feat != "fp32":
                         vb, mb, qb, ab = bufs[i]
                     else:
                         vb, qb, ab = bufs[i]
@@ -423,8 +427,7 @@ def run_b200(args):
                             vv = clone_rows(vv)
                             if mb is not None:                 # the clone of src/MC/train.py:75-76 carries the mask along
                                 cti_b200.prime_features(vv, mb.unsqueeze(1).expand(Bq, CLONE, K_REGIONS).reshape(-1))
-                        joint = step(vv, qb.detach(), ab.detach())
-                        outs[i].copy_(joint.detach(), non_blocking=True)
+                        return step(vv, qb.detach(), ab.detach()).detach()
                     return compute
                 cs = [make_compute(i) for i in range(2)]
                 if use_graph:
@@ -445,11 +448,14 @@ def run_b200(args):
                         state["primed"] = True
                     main = torch.cuda.current_stream()
                     main.wait_event(ev_copied[i])
-                    cs[i]()
+                    joint = cs[i]()
                     if reducer is not None and use_graph:
                         reducer.reduce_now()
                     ev_done[i].record(main)
-                    h2d_into(i ^ 1)                                    # prefetch the next step's inputs
+                    h2d_into(i ^ 1)                                    # prefetch the next step's inputs ...
+                    with torch.cuda.stream(copy_stream):               # ... and read this step's result back behind them
+                        copy_stream.wait_event(ev_done[i])
+                        outs[i].copy_(joint, non_blocking=True)
                     state["i"] += 1
                 for _ in range(4):
                     pipelined_step()
@@ -460,10 +466,12 @@ def run_b200(args):
                 return {"value": world * B * args.steps / (ms_p / 1e3), "unit": UNIT, "ms_per_step": ms_p / args.steps,
                         "h2d_bytes_per_step": h2d_, "d2h_bytes_per_step": out_h.numel() * 4}
             e2e = dict(pipelined("bf16", False),
-                       mode="pinned host batch in the loader wire format (bf16 features per question + zero-row mask, fp32 q / a) "
-                            "-> H2D -> x4 clone on the device (src/MC/train.py:69-76) -> modules -> D2H of the joint embedding; "
-                            "H2D of step i+1 overlapped with compute of step i (double-buffered inputs)",
+                       mode="pinned host batch in the loader wire format (bf16 features per question + zero-row mask, bf16 "
+                            "question / answer token embeddings) -> H2D -> x4 clone on the device (src/MC/train.py:69-76) -> "
+                            "modules -> D2H of the joint embedding; H2D of step i+1 overlapped with compute of step i "
+                            "(double-buffered inputs)",
                        serial_fp32=e2e_serial)
+            e2e["fp32_tokens"] = dict(pipelined("bf16v", False), note="bf16 features + mask, fp32 q / a (cast on the device)")
             e2e["fp32_features"] = dict(pipelined("fp32", False), note="same pipeline fed the fp32 batches the reference's "
                                         "loader yields (cast + mask pass on the device)")
             if CLONE > 1:

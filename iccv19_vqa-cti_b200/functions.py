@@ -132,6 +132,8 @@ def cast_tokens(t: torch.Tensor, drop) -> torch.Tensor:
     x2d = t.reshape(t.shape[0] * t.shape[1], -1)
     if drop is not None:
         return cast_in(x2d, drop)
+    if t.dtype == BF16:                  # tokens that already travel as bf16 (loader wire format): no cast pass
+        return x2d.detach().contiguous()
     key = (t._version, t.data_ptr(), tuple(t.shape))
     hit = getattr(t, _TOK_ATTR, None)
     if hit is not None and hit[0] == key:
@@ -142,6 +144,22 @@ def cast_tokens(t: torch.Tensor, drop) -> torch.Tensor:
     except Exception:
         pass
     return xb
+
+
+def _f32_dx(dtype, drop) -> bool:
+    """fp32 dgrad output unless the token tensor is bf16 (then its gradient is bf16 too and leaves the GEMM epilogue as
+    such); with input dropout the fp32 path is kept (the mask kernel works on fp32)."""
+    return dtype != BF16 or drop is not None
+
+
+def _finish_dx(dx, drop, dtype, shape):
+    if dx is None:
+        return None
+    if drop is not None:
+        K_.dropout_f32_(dx, drop)
+    if dx.dtype != dtype:
+        dx = dx.to(dtype)
+    return dx.view(shape)
 
 
 def lin_bwd(x: torch.Tensor, dz: torch.Tensor, V: torch.Tensor, g: torch.Tensor, pk: Packed, n_groups: int,
@@ -371,6 +389,7 @@ class TriLogitsFn(Function):
         ctx.pk = pk
         ctx.dims = dims
         ctx.need = (q.requires_grad, a.requires_grad)
+        ctx.tok_dtypes = (q.dtype, a.dtype)
         return logits.permute(0, 2, 3, 4, 1)
 
     @staticmethod
@@ -422,17 +441,14 @@ class TriLogitsFn(Function):
         dzat, dbat = finish(ya, dzat, acca, zs[5])
         with K_.gemm_batch():
             dVvt, dgvt, _ = lin_bwd(v_bf16, dzvt, w[0], w[1], pk[0], 1, False, dw=zs[6])
-            dVqt, dgqt, dq = lin_bwd(xq, dzqt, w[3], w[4], pk[1], 1, ctx.need[0], dx_f32=True, dw=zs[7])
-            dVat, dgat, da = lin_bwd(xa, dzat, w[6], w[7], pk[2], 1, ctx.need[1], dx_f32=True, dw=zs[8])
+            # the gradient of a token tensor has the tensor's dtype: fp32, or bf16 straight from the dgrad epilogue
+            dVqt, dgqt, dq = lin_bwd(xq, dzqt, w[3], w[4], pk[1], 1, ctx.need[0], dw=zs[7],
+                                     dx_f32=_f32_dx(ctx.tok_dtypes[0], dq_drop))
+            dVat, dgat, da = lin_bwd(xa, dzat, w[6], w[7], pk[2], 1, ctx.need[1], dw=zs[8],
+                                     dx_f32=_f32_dx(ctx.tok_dtypes[1], da_drop))
         dT = unpack_core_grad(dtpack, T_g)
-        if dq is not None:
-            if dq_drop is not None:
-                K_.dropout_f32_(dq, dq_drop)
-            dq = dq.view(B, Q, -1)
-        if da is not None:
-            if da_drop is not None:
-                K_.dropout_f32_(da, da_drop)
-            da = da.view(B, A, -1)
+        dq = _finish_dx(dq, dq_drop, ctx.tok_dtypes[0], (B, Q, -1))
+        da = _finish_dx(da, da_drop, ctx.tok_dtypes[1], (B, A, -1))
         return (None, None, None, None, None, dq, da, dT,
                 dVvt, dgvt, dbvt, dVqt, dgqt, dbqt, dVat, dgat, dbat,
                 dVvn, dgvn, dbvn.view_as(w[11]), dVqn, dgqn, dbqn.view_as(w[14]), dVan, dgan, dban.view_as(w[17]))
@@ -535,6 +551,7 @@ class PoolFn(Function):
         ctx.pk = pk
         ctx.dims = dims
         ctx.need = (q.requires_grad, a is not None and a.requires_grad, wts.requires_grad)
+        ctx.tok_dtypes = (q.dtype, a.dtype if a is not None else F32)
         return out
 
     @staticmethod
@@ -554,20 +571,16 @@ class PoolFn(Function):
         da = None
         with K_.gemm_batch():
             dVv, dgv, _ = lin_bwd(v_bf16, dzv, w[0], w[1], pk[0], 1, False, dw=zs[0])
-            dVq, dgq, dq = lin_bwd(xq, dzq, w[3], w[4], pk[1], 1, ctx.need[0], dx_f32=True, dw=zs[1])
+            dVq, dgq, dq = lin_bwd(xq, dzq, w[3], w[4], pk[1], 1, ctx.need[0], dw=zs[1],
+                                   dx_f32=_f32_dx(ctx.tok_dtypes[0], ctx.drops[0]))
             if A > 0:
-                dVa, dga, da = lin_bwd(xa, dza, w[6], w[7], pk[2], 1, ctx.need[1], dx_f32=True, dw=zs[2])
+                dVa, dga, da = lin_bwd(xa, dza, w[6], w[7], pk[2], 1, ctx.need[1], dw=zs[2],
+                                       dx_f32=_f32_dx(ctx.tok_dtypes[1], ctx.drops[1]))
         grads = [dVv, dgv, dbv, dVq, dgq, dbq]
         if A > 0:
             grads += [dVa, dga, dba]
-            if da is not None:
-                if ctx.drops[1] is not None:
-                    K_.dropout_f32_(da, ctx.drops[1])
-                da = da.view(B, A, -1)
-        if dq is not None:
-            if ctx.drops[0] is not None:
-                K_.dropout_f32_(dq, ctx.drops[0])
-            dq = dq.view(B, Q, -1)
+            da = _finish_dx(da, ctx.drops[1], ctx.tok_dtypes[1], (B, A, -1))
+        dq = _finish_dx(dq, ctx.drops[0], ctx.tok_dtypes[0], (B, Q, -1))
         return (None, None, None, None, dq, da, dw if ctx.need[2] else None, *grads)
 
 
@@ -600,6 +613,7 @@ class BiLogitsFn(Function):
         ctx.pk = pk
         ctx.dims = dims
         ctx.need_dq = q.requires_grad
+        ctx.q_dtype = q.dtype
         return logits
 
     @staticmethod
@@ -614,11 +628,8 @@ class BiLogitsFn(Function):
         dVv, dgv, _ = lin_bwd(v_bf16, dzv, w[0], w[1], pk[0], 1, False, alpha=sc)
         if datt is not None:
             dbv = dbv * sc
-        dVq, dgq, dq = lin_bwd(xq, dzq, w[3], w[4], pk[1], 1, ctx.need_dq, dx_f32=True)
-        if dq is not None:
-            if dq_drop is not None:
-                K_.dropout_f32_(dq, dq_drop)
-            dq = dq.view(B, Q, -1)
+        dVq, dgq, dq = lin_bwd(xq, dzq, w[3], w[4], pk[1], 1, ctx.need_dq, dx_f32=_f32_dx(ctx.q_dtype, dq_drop))
+        dq = _finish_dx(dq, dq_drop, ctx.q_dtype, (B, Q, -1))
         return (None, None, None, None, None, dq, dh.view_as(hmat), dhb.view_as(hbias), dVv, dgv, dbv, dVq, dgq, dbq)
 
 

@@ -55,3 +55,32 @@ def test_bf16_features_give_bit_identical_results_and_skip_the_cast():
     att.train()
     p, _ = att(vv, q, a)
     assert torch.isfinite(p).all()
+
+
+def test_bf16_token_embeddings_skip_the_cast_and_get_bf16_gradients():
+    """Question / answer token embeddings that already travel as bf16 are consumed as they are (no cast launch); the
+    forward is bit-identical to the fp32 call on the same (bf16-representable) values and dq / da come back in bf16,
+    equal to the rounded fp32 gradients."""
+    torch.manual_seed(4)
+    att = cti_b200.TriAttention(2048, 1024, 1024, 512, 1, 32, 2, 1).to(DEV).eval()
+    pool = cti_b200.TCNet(2048, 1024, 1024, 512, 1, 32, 1, k=2).to(DEV).eval()
+    v, q, a = (t.to(DEV) for t in O.synthetic_inputs(5, 50, 12, 6, seed=6))
+    q16, a16 = q.to(torch.bfloat16), a.to(torch.bfloat16)
+
+    def run(qq, aa):
+        qq, aa = qq.clone().requires_grad_(True), aa.clone().requires_grad_(True)
+        K_.STATS.launches = 0
+        p, logits = att(v, qq, aa)
+        out = pool.forward_with_weights(v, qq, aa, p[:, :, :, :, 0])
+        n = K_.STATS.launches
+        out.square().sum().backward()
+        return (p.detach(), logits.detach(), out.detach()), (qq.grad, aa.grad), n
+    run(q16.float(), a16.float())                           # builds the lazily cached weight packs
+    ref, gref, n32 = run(q16.float(), a16.float())
+    got, g16, n16 = run(q16, a16)
+    assert n16 == n32 - 2                                   # the two token casts are gone
+    for x, y in zip(ref, got):
+        assert torch.equal(x, y)
+    for g, gr in zip(g16, gref):
+        assert g.dtype == torch.bfloat16
+        assert (g.float() - gr).abs().max().item() <= 1e-2 * gr.abs().max().item()
