@@ -374,9 +374,16 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ 
       tcgen05_fence_after();
       if (BWD) mbar_wait(bar(B_KEMPTY + (g & 1)), ((g >> 1) & 1) ^ 1);
       const uint32_t krd = sK + (g & 1) * KRD_BYTES;
-      float acc = 0.f, dq[16], sum_a = 0.f;
+      // packed fp32x2 math (FFMA2 / FMUL2): pairs (q, q + 1) of this thread's channel
+      float2 qp2[8], dq2[8];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) dq[i] = 0.f;
+      for (int j = 0; j < 8; ++j) {
+        qp2[j] = make_float2(cur.qp[2 * j], cur.qp[2 * j + 1]);
+        dq2[j] = make_float2(0.f, 0.f);
+      }
+      float acc = 0.f, sum_a = 0.f;
+      const uint32_t krow = (cl >> 3) * 1024u + (cl & 7u) * 128u, kx = cl & 7u;      // this thread's KRd row (SW128)
+      bf16* dza_c = BWD && p.A > 0 ? p.dza + (size_t)b * p.A * p.C + c : nullptr;
 #pragma unroll
       for (int ai = 0; ai < 8; ++ai) {
         if (ai < p.An) {
@@ -384,28 +391,36 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ 
           tmem_ld_32x32b_x16(tmem_base + lane_addr + TM_Z + (g & 1) * 128 + ai * 16, r);
           tmem_wait_ld();
           const float apv = cur.ap[ai];
-          float s = 0.f;
+          float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int qi = 0; qi < 16; ++qi) s = fmaf(cur.qp[qi], __uint_as_float(r[qi]), s);
+          for (int j = 0; j < 8; ++j)
+            s2 = __ffma2_rn(qp2[j], make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), s2);
+          const float s = s2.x + s2.y;
           if (!BWD) {
             acc = fmaf(apv, s, acc);
           } else {
+            const float2 ap2 = make_float2(apv, apv);
 #pragma unroll
-            for (int qi = 0; qi < 16; ++qi) dq[qi] = fmaf(apv, __uint_as_float(r[qi]), dq[qi]);
+            for (int j = 0; j < 8; ++j)
+              dq2[j] = __ffma2_rn(ap2, make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), dq2[j]);
             if (p.A > 0) {
               const float ga = apv > 0.f ? cur.dout * s : 0.f;
-              p.dza[((size_t)b * p.A + ai) * p.C + c] = __float2bfloat16(ga);
+              dza_c[(size_t)ai * p.C] = __float2bfloat16(ga);
               sum_a += ga;
             }
             // KRd[c, (ai, q)] = do * Qp[q] * Ap[ai]: one 32-byte piece of this thread's operand row
             const float da = cur.dout * apv;
+            const float2 da2 = make_float2(da, da);
             uint32_t pk[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(da * cur.qp[2 * j], da * cur.qp[2 * j + 1]);
-            const uint32_t tile = krd + (ai >> 2) * (CCH * 128);
-            const uint32_t col0 = (ai & 3) * 16;
-            st_shared_v4(tile + sw128_off(cl, col0), pk[0], pk[1], pk[2], pk[3]);
-            st_shared_v4(tile + sw128_off(cl, col0 + 8), pk[4], pk[5], pk[6], pk[7]);
+            for (int j = 0; j < 8; ++j) {
+              const float2 pr = __fmul2_rn(da2, qp2[j]);
+              pk[j] = pack_bf16x2(pr.x, pr.y);
+            }
+            const uint32_t tile = krd + (ai >> 2) * (CCH * 128) + krow;
+            const uint32_t ch0 = (ai & 3) * 2;
+            st_shared_v4(tile + (((ch0) ^ kx) << 4), pk[0], pk[1], pk[2], pk[3]);
+            st_shared_v4(tile + (((ch0 + 1) ^ kx) << 4), pk[4], pk[5], pk[6], pk[7]);
           }
         }
       }
@@ -413,11 +428,19 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ 
         p.out[(size_t)b * p.C + c] = acc;
       } else {
         float sum_q = 0.f;
+        bf16* dzq_c = p.dzq + (size_t)b * p.Q * p.C + c;
+        const float2 do2 = make_float2(cur.dout, cur.dout);
 #pragma unroll
-        for (int qi = 0; qi < 16; ++qi) {
-          if (qi < p.Q) {
-            const float gq = cur.qp[qi] > 0.f ? cur.dout * dq[qi] : 0.f;
-            p.dzq[((size_t)b * p.Q + qi) * p.C + c] = __float2bfloat16(gq);
+        for (int j = 0; j < 8; ++j) {
+          const float2 gq2 = __fmul2_rn(do2, dq2[j]);
+          if (2 * j < p.Q) {
+            const float gq = qp2[j].x > 0.f ? gq2.x : 0.f;
+            dzq_c[(size_t)(2 * j) * p.C] = __float2bfloat16(gq);
+            sum_q += gq;
+          }
+          if (2 * j + 1 < p.Q) {
+            const float gq = qp2[j].y > 0.f ? gq2.y : 0.f;
+            dzq_c[(size_t)(2 * j + 1) * p.C] = __float2bfloat16(gq);
             sum_q += gq;
           }
         }
