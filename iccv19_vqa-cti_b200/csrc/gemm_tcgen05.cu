@@ -15,6 +15,7 @@
 #include "tc_tiles.cuh"
 
 #include <cudaTypedefs.h>
+#include <cstdlib>
 
 namespace cti {
 
@@ -27,12 +28,16 @@ constexpr int kGemmThreads = 384;      // warps 0-2: TMA / MMA / TMEM alloc, war
 constexpr int kEpiWarps = 8;
 constexpr int kEpiWarp0 = 4;
 
-template <int BLOCK_N>
+// CTAS = 2: a CTA PAIR (cluster of two, cta_group::2) works on one 256 x BLOCK_N tile: each CTA stages its own 128 rows
+// of A and HALF of the B tile, the leader issues tcgen05.mma M = 256 for both, each CTA's TMEM gets its 128 rows.
+// Half the B-operand shared-memory traffic per SM and 6 instead of 4 pipeline stages in the same 192 KB.
+template <int BLOCK_N, int CTAS = 1>
 struct GemmCfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int B_ROWS = BLOCK_N / CTAS;                  // B rows (N) staged by one CTA
+  static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int STAGES = (BLOCK_N == 256 && CTAS == 1) ? 4 : 6;
   static constexpr int ACC_STAGES = 2;
   static constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;            // 512 or 256 (power of two)
   static constexpr int OUT_BYTES = kEpiWarps * 4096;  // per epilogue warp: one 32-row x 128-byte staging box
@@ -56,6 +61,58 @@ struct GemmDevParams {
 
 enum { kOutDirect = 0, kOutTmaBf16 = 1, kOutTmaF32 = 2, kOutTmaAddF32 = 3 };
 
+// ---- CTA-pair (cta_group::2) forms of the PTX wrappers ------------------------------------------------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;      // shared::cluster address of the same offset in the pair's CTA 0
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are counted on the LEADER CTA's mbarrier (executed by both CTAs of the pair)
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar, uint32_t smem_dst, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs once the pair's MMAs issued so far have retired
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {      // arrive on CTA 0's copy of the barrier
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+}
+template <int CTAS>
+__device__ __forceinline__ void tmem_alloc_n(uint32_t smem_result_addr, uint32_t ncols) {      // whole warp (of each CTA)
+  if (CTAS == 1) {
+    tmem_alloc(smem_result_addr, ncols);
+    tmem_relinquish();
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result_addr), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+}
+template <int CTAS>
+__device__ __forceinline__ void tmem_dealloc_n(uint32_t taddr, uint32_t ncols) {
+  if (CTAS == 1) tmem_dealloc(taddr, ncols);
+  else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
 // One launch runs ONE problem or a PAIR of independent problems that share the operand layouts and the tile width
 // (gemm_bf16_pair: the question-side and answer-side projections of a step -- same weights shape, different row
 // counts -- which on their own leave SMs idle and pay the launch / pipeline-fill floor twice).  The tiles of problem 0
@@ -64,12 +121,18 @@ struct GemmMaps {
   CUtensorMap a, b, c;
 };
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+template <int BLOCK_N, bool A_MN, bool B_MN, int CTAS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ GemmMaps maps0, const __grid_constant__ GemmMaps maps1,
                  const __grid_constant__ GemmDevParams prm0, const __grid_constant__ GemmDevParams prm1, const int tiles0,
                  const int total_tiles) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, CTAS>;
+  // CTA pair: `unit` = the pair, `rank` = this CTA's half (rows rank * 128 .. of the 256-row tile, columns
+  // rank * BLOCK_N / 2 .. of the B tile); a single CTA is a unit of its own
+  const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
+  const int unit = CTAS == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_units = CTAS == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr int TILE_M = BLOCK_M * CTAS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_out = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;          // 1024-byte aligned
@@ -102,16 +165,14 @@ gemm_bf16_kernel(const __grid_constant__ GemmMaps maps0, const __grid_constant__
     }
     for (int s = 0; s < Cfg::ACC_STAGES; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), kEpiWarps * 32);
+      mbar_init(tempty_bar(s), kEpiWarps * 32 * CTAS);      // the leader's copy hears from both CTAs' epilogues
     }
     fence_barrier_init();
   }
-  if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
-  }
+  if (warp == 2) tmem_alloc_n<CTAS>(tmem_slot, Cfg::TMEM_COLS);
   tcgen05_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();      // the peer's barriers exist before anything arrives on them
+  else __syncthreads();
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -121,7 +182,11 @@ gemm_bf16_kernel(const __grid_constant__ GemmMaps maps0, const __grid_constant__
     // ------------------------------ TMA producer ------------------------------
     if (elect_one_sync()) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      auto load = [&](const CUtensorMap* m, uint32_t dst, int32_t c0, int32_t c1) {
+        if (CTAS == 2) tma_load_2d_pair(m, full_bar(stage), dst, c0, c1);      // bytes counted on the leader's barrier
+        else tma_load_2d(m, full_bar(stage), dst, c0, c1);
+      };
+      for (int tile = unit; tile < total_tiles; tile += n_units) {
         const bool second = tile >= tiles0;
         const GemmDevParams& p = second ? prm1 : prm0;
         const CUtensorMap* tmap_a = second ? &maps1.a : &maps0.a;
@@ -134,22 +199,22 @@ gemm_bf16_kernel(const __grid_constant__ GemmMaps maps0, const __grid_constant__
         const int n_blk = mn - m_blk * p.num_n_blocks;
         const int kb0 = ks * p.k_blocks_per_split;
         const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
+        const int m0 = m_blk * TILE_M + (int)rank * BLOCK_M;               // this CTA's rows of the tile
+        const int n0 = n_blk * BLOCK_N + (int)rank * Cfg::B_ROWS;          // this CTA's share of the B tile
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES * CTAS);
           if (!A_MN) {
-            tma_load_2d(tmap_a, full_bar(stage), smem_a(stage), kb * BLOCK_K, m_blk * BLOCK_M);
+            load(tmap_a, smem_a(stage), kb * BLOCK_K, m0);
           } else {
 #pragma unroll
-            for (int i = 0; i < BLOCK_M / 64; ++i)
-              tma_load_2d(tmap_a, full_bar(stage), smem_a(stage) + i * 8192, m_blk * BLOCK_M + i * 64, kb * BLOCK_K);
+            for (int i = 0; i < BLOCK_M / 64; ++i) load(tmap_a, smem_a(stage) + i * 8192, m0 + i * 64, kb * BLOCK_K);
           }
           if (!B_MN) {
-            tma_load_2d(tmap_b, full_bar(stage), smem_b(stage), kb * BLOCK_K, n_blk * BLOCK_N);
+            load(tmap_b, smem_b(stage), kb * BLOCK_K, n0);
           } else {
 #pragma unroll
-            for (int i = 0; i < BLOCK_N / 64; ++i)
-              tma_load_2d(tmap_b, full_bar(stage), smem_b(stage) + i * 8192, n_blk * BLOCK_N + i * 64, kb * BLOCK_K);
+            for (int i = 0; i < Cfg::B_ROWS / 64; ++i) load(tmap_b, smem_b(stage) + i * 8192, n0 + i * 64, kb * BLOCK_K);
           }
           if (++stage == Cfg::STAGES) {
             stage = 0;
@@ -160,10 +225,18 @@ gemm_bf16_kernel(const __grid_constant__ GemmMaps maps0, const __grid_constant__
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
-    if (elect_one_sync()) {
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+    if (rank == 0 && elect_one_sync()) {      // the leader issues for the pair
+      constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BLOCK_N, A_MN, B_MN);
+      auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t accum) {
+        if (CTAS == 2) umma_bf16_ss_pair(d, da, db, idesc, accum);
+        else umma_bf16_ss(d, da, db, idesc, accum);
+      };
+      auto commit = [&](uint32_t b) {
+        if (CTAS == 2) umma_commit_pair(b);
+        else umma_commit(b);
+      };
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < total_tiles; tile += n_units) {
         const bool second = tile >= tiles0;
         const GemmDevParams& p = second ? prm1 : prm0;
         const int ks = (second ? tile - tiles0 : tile) / (p.num_m_blocks * p.num_n_blocks);
@@ -183,10 +256,10 @@ gemm_bf16_kernel(const __grid_constant__ GemmMaps maps0, const __grid_constant__
                                      : make_smem_desc_sw128(smem_a(stage) + k * 32, 16, 1024);
             const uint64_t db = B_MN ? make_smem_desc_sw128(smem_b(stage) + k * 2048, 8192, 1024)
                                      : make_smem_desc_sw128(smem_b(stage) + k * 32, 16, 1024);
-            umma_bf16_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            mma(d_tmem, da, db, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));               // frees the smem slot when the MMAs retire
-          if (kb == kb1 - 1) umma_commit(tfull_bar(acc));   // accumulator complete
+          commit(empty_bar(stage));               // frees the smem slot (in both CTAs) when the MMAs retire
+          if (kb == kb1 - 1) commit(tfull_bar(acc));   // accumulator complete
           if (++stage == Cfg::STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -213,7 +286,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmMaps maps0, const __grid_constant__
     const uint32_t sw = lane & 7;
     constexpr uint32_t obuf = 0;
     uint32_t acc = 0, acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = unit; tile < total_tiles; tile += n_units) {
       const bool second = tile >= tiles0;
       const GemmDevParams& p = second ? prm1 : prm0;
       const CUtensorMap* tmap_c = second ? &maps1.c : &maps0.c;
@@ -224,7 +297,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmMaps maps0, const __grid_constant__
       const int m_blk = mn / p.num_n_blocks;
       const int n_blk = mn - m_blk * p.num_n_blocks;
       const bool empty_split = (ks * p.k_blocks_per_split >= p.num_k_blocks);
-      const int row0 = m_blk * BLOCK_M + quarter * 32;
+      const int row0 = m_blk * TILE_M + (int)rank * BLOCK_M + quarter * 32;
       const int row = row0 + lane;
       const bool row_ok = row < p.M;
       const int n0 = n_blk * BLOCK_N + chalf * (BLOCK_N / 2);
@@ -362,7 +435,8 @@ gemm_bf16_kernel(const __grid_constant__ GemmMaps maps0, const __grid_constant__
           tmem_ld_32x32b_x32(t_addr + (c + 2) * 32, ra);
         } else {
           tcgen05_fence_before();                 // every TMEM read of this tile has completed
-          mbar_arrive(tempty_bar(acc));
+          if (CTAS == 2) mbar_arrive_leader(tempty_bar(acc));      // the issuer lives in CTA 0
+          else mbar_arrive(tempty_bar(acc));
         }
         process(c + 1, rb, b1);
         b0 = nb0;
@@ -377,10 +451,11 @@ gemm_bf16_kernel(const __grid_constant__ GemmMaps maps0, const __grid_constant__
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();      // neither CTA leaves (or frees TMEM) while the peer may still touch it
+  else __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    tmem_dealloc_n<CTAS>(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -418,19 +493,19 @@ int make_tmap(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer,
 }
 
 // Tensor maps + device parameters of one problem for the given tile width / layouts.
-template <int BLOCK_N, bool A_MN, bool B_MN>
+template <int BLOCK_N, bool A_MN, bool B_MN, int CTAS>
 int build_problem(const GemmArgs& g, GemmMaps* maps, GemmDevParams* out) {
   int rc;
   if (!A_MN) rc = make_tmap(&maps->a, g.a, g.K, g.M, g.lda, BLOCK_K, BLOCK_M);
   else       rc = make_tmap(&maps->a, g.a, g.M, g.K, g.lda, 64, BLOCK_K);
   if (rc) return rc;
-  if (!B_MN) rc = make_tmap(&maps->b, g.b, g.K, g.N, g.ldb, BLOCK_K, BLOCK_N);
+  if (!B_MN) rc = make_tmap(&maps->b, g.b, g.K, g.N, g.ldb, BLOCK_K, BLOCK_N / CTAS);      // a pair's CTA stages half of B
   else       rc = make_tmap(&maps->b, g.b, g.N, g.K, g.ldb, 64, BLOCK_K);
   if (rc) return rc;
 
   GemmDevParams p;
   p.M = g.M; p.N = g.N; p.K = g.K;
-  p.num_m_blocks = (g.M + BLOCK_M - 1) / BLOCK_M;
+  p.num_m_blocks = (g.M + BLOCK_M * CTAS - 1) / (BLOCK_M * CTAS);
   p.num_n_blocks = (g.N + BLOCK_N - 1) / BLOCK_N;
   p.num_k_blocks = (g.K + BLOCK_K - 1) / BLOCK_K;
   int splits = g.k_splits < 1 ? 1 : g.k_splits;
@@ -457,16 +532,16 @@ int build_problem(const GemmArgs& g, GemmMaps* maps, GemmDevParams* out) {
   return 0;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+template <int BLOCK_N, bool A_MN, bool B_MN, int CTAS = 1>
 int launch_gemm(const GemmArgs& g0, const GemmArgs* g1, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, CTAS>;
   GemmMaps m0, m1;
   GemmDevParams p0, p1;
-  if (int rc = build_problem<BLOCK_N, A_MN, B_MN>(g0, &m0, &p0)) return rc;
+  if (int rc = build_problem<BLOCK_N, A_MN, B_MN, CTAS>(g0, &m0, &p0)) return rc;
   const long t0 = (long)p0.num_m_blocks * p0.num_n_blocks * p0.k_splits;
   long t1 = 0;
   if (g1 != nullptr) {
-    if (int rc = build_problem<BLOCK_N, A_MN, B_MN>(*g1, &m1, &p1)) return rc;
+    if (int rc = build_problem<BLOCK_N, A_MN, B_MN, CTAS>(*g1, &m1, &p1)) return rc;
     t1 = (long)p1.num_m_blocks * p1.num_n_blocks * p1.k_splits;
   } else {
     m1 = m0;
@@ -475,7 +550,7 @@ int launch_gemm(const GemmArgs& g0, const GemmArgs* g1, cudaStream_t stream) {
   CTI_REQUIRE(t0 + t1 < (1L << 30), "gemm: too many tiles");
 
   static bool attr_set = false;
-  auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN>;
+  auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, CTAS>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
@@ -486,6 +561,26 @@ int launch_gemm(const GemmArgs& g0, const GemmArgs* g1, cudaStream_t stream) {
   }
   const long total = t0 + t1;
   int sms = g0.max_ctas > 0 ? g0.max_ctas : kNumSMsB200;
+  if (CTAS == 2) {
+    // one CTA pair per TPC: cluster of 2 + programmatic dependent launch
+    const int pairs = (int)(total < sms / 2 ? total : sms / 2);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    cudaLaunchKernelEx(&cfg, kern, m0, m1, p0, p1, (int)t0, (int)total);
+    return check_launch("gemm_bf16_kernel (CTA pairs)");
+  }
   const int grid = (int)(total < sms ? total : sms);
   launch_pdl(kern, dim3(grid), dim3(kGemmThreads), Cfg::SMEM_BYTES, stream, m0, m1, p0, p1, (int)t0, (int)total);
   return check_launch("gemm_bf16_kernel");
@@ -512,6 +607,25 @@ int dispatch_gemm(const GemmArgs& g0, const GemmArgs* g1, cudaStream_t stream) {
   const int minN = g1 ? (g0.N < g1->N ? g0.N : g1->N) : g0.N;
   const int forced = g0.tile_n != 0 ? g0.tile_n : (g1 ? g1->tile_n : 0);
   const bool use256 = (forced == 256) || (forced == 0 && minN >= 256 && tiles256 >= 64);
+  // CTA pairs (256 x 256 tiles, cta_group::2) once there are enough 256-row tiles for every pair; tile_n = 512 forces
+  // them, CTI_GEMM_PAIRS=0 in the environment switches them off (A/B measurements)
+  static const bool pairs_on = [] { const char* e = getenv("CTI_GEMM_PAIRS"); return !(e && e[0] == '0'); }();
+  auto tiles512 = [](const GemmArgs& g) {
+    return (long)((g.M + 255) / 256) * ((g.N + 255) / 256) * (g.k_splits < 1 ? 1 : g.k_splits);
+  };
+  const long tp = tiles512(g0) + (g1 ? tiles512(*g1) : 0);
+  // measured (tools/gemm_pairs_bench.py): pairs win once a tile's K loop is >= 1024 deep (51200 x 1024 x 2048: 159 -> 146 us,
+  // 0.83 -> 0.90 of the burst peak; 18432 x 1024 x 1024: 31.7 -> 29.4 us) and lose a little below that and on the
+  // K = 1024 dgrad layout (shorter loops do not amortise the pair's cluster-wide hand-offs)
+  const int k_per_split = g0.K / (g0.k_splits < 1 ? 1 : g0.k_splits);
+  const bool dgrad_layout = !g0.a_mn_major && g0.b_mn_major;
+  const bool use_pairs = forced == 512 || (pairs_on && forced == 0 && use256 && tp >= 56 &&
+                                           k_per_split >= (dgrad_layout ? 2048 : 1024));
+  if (use_pairs) {
+    if (!g0.a_mn_major && !g0.b_mn_major) return launch_gemm<256, false, false, 2>(g0, g1, stream);
+    if (!g0.a_mn_major && g0.b_mn_major) return launch_gemm<256, false, true, 2>(g0, g1, stream);
+    if (g0.a_mn_major && g0.b_mn_major) return launch_gemm<256, true, true, 2>(g0, g1, stream);
+  }
   if (use256) {
     if (!g0.a_mn_major && !g0.b_mn_major) return launch_gemm<256, false, false>(g0, g1, stream);
     if (!g0.a_mn_major && g0.b_mn_major) return launch_gemm<256, false, true>(g0, g1, stream);

@@ -32,7 +32,7 @@ def rel_err(x, ref):
 # --------------------------------------------------------------------------- #
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 200, 136), (1000, 512, 2048), (50, 16, 512), (2600, 1024, 1024),
                                    (129, 264, 72)])
-@pytest.mark.parametrize("tile_n", [0, 128, 256])
+@pytest.mark.parametrize("tile_n", [0, 128, 256, 512])          # 512: CTA pairs (cta_group::2, 256 x 256 tiles)
 def test_gemm_kmajor(M, N, K, tile_n):
     g = torch.Generator(device=DEV).manual_seed(M * 7 + N)
     a = bf(torch.randn(M, K, device=DEV, generator=g))
@@ -57,7 +57,7 @@ def test_gemm_dgrad_layout(M, N, K):
     dz = bf(torch.randn(M, K, device=DEV, generator=g))
     w = bf(torch.randn(K, N, device=DEV, generator=g) / K ** 0.5)
     ref = dz.float() @ w.float()
-    for tile_n in (128, 256):
+    for tile_n in (128, 256, 512):
         _, of = K_.gemm(dz, w, M, N, K, b_mn=True, out_bf16=False, out_f32=True, tile_n=tile_n)
         assert rel_err(of, ref) < 2e-5
 
@@ -70,13 +70,14 @@ def test_gemm_wgrad_layout_splitk(rows, N, Kin, splits):
     dz = bf(torch.randn(rows, N, device=DEV, generator=g))
     x = bf(torch.randn(rows, Kin, device=DEV, generator=g))
     ref = dz.float().t() @ x.float()
-    for tile_n in (128, 256):
+    for tile_n in (128, 256, 512):
         acc = torch.zeros(N, Kin, device=DEV)
         K_.gemm(dz, x, N, Kin, rows, a_mn=True, b_mn=True, accum_f32=acc, k_splits=splits, tile_n=tile_n)
         assert rel_err(acc, ref) < 1e-4
 
 
-@pytest.mark.parametrize("Mq,Ma,N,K", [(1536, 768, 1024, 1024), (12288, 6144, 512, 512), (300, 77, 136, 72), (96, 2000, 512, 256)])
+@pytest.mark.parametrize("Mq,Ma,N,K", [(1536, 768, 1024, 1024), (12288, 6144, 512, 512), (300, 77, 136, 72), (96, 2000, 512, 256),
+                                       (12288, 6144, 1024, 1024)])          # the last one runs as CTA pairs
 def test_gemm_batch_pairs_independent_problems(Mq, Ma, N, K):
     """Inside gemm_batch() two GEMMs with the same operand layouts leave in ONE launch (cti_gemm_bf16_pair); results are
     bit-identical to the separate launches (forward, dgrad) or equal up to the split-K summation order (wgrad)."""
