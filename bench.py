@@ -222,6 +222,7 @@ def run_b200(args):
     mods = torch.nn.ModuleList([att, *pools, *q_prj, *a_prj]).to(dev).eval()
     params = [p for p in mods.parameters()]
     reducer = GradAllReducer(params) if world > 1 else None
+    CAP_MODE = "thread_local" if world > 1 else "global"      # NCCL inside the captured step (graphs.GraphedStep)
     if reducer is not None:
         # the deferred weight-norm backward writes dV / dg (97 % of the gradient bytes) straight into the all-reduce slab
         cti_b200.bind_grad_buffers(mods, reducer)
@@ -256,11 +257,17 @@ def run_b200(args):
             ae = a_prj[gi](b_emb.unsqueeze(1)) + ae
         joint = qe.sum(1) + ae.sum(1)
         (joint * cot).sum().backward()
-        if reducer is not None and not step.graphed:
-            reducer.finish()
+        if reducer is not None and step.reduce:
+            # eager: the hooks launched the bucketed all-reduces during backward; captured: the hook-free reduce is part
+            # of the graph (one fused copy of the few gradients that are not written in place + one all-reduce of the slab)
+            if step.graphed:
+                reducer.reduce_now()
+            else:
+                reducer.finish()
         return joint
 
     step.graphed = False
+    step.reduce = True                           # False: rank-0-only passes (per-kernel profile) must not issue collectives
 
     def barrier():
         if world > 1:
@@ -310,18 +317,13 @@ def run_b200(args):
         ms_eager, _, _ = timed(resident_step, max(3, args.steps // 4))
         eager_ms = {"ms_per_step": ms_eager / max(3, args.steps // 4), "host_issue_ms_per_step": timed.host_ms}
         try:
-            # multi-GPU: forward + backward are replayed from the graph, the bucketed NCCL all-reduce is issued
-            # eagerly right after (capturing NCCL launched from autograd hooks hung)
+            # multi-GPU: forward, backward AND the gradient all-reduce are replayed from the graph (hook-free reduce at the
+            # end of the step; NCCL is capturable with capture_error_mode="thread_local")
             if reducer is not None:
                 reducer.set_hooks_enabled(False)
                 step.graphed = True
-            graphed = cti_b200.GraphedStep(resident_step, [mods], [v_d])
-            if reducer is None:
-                run_resident = graphed.replay
-            else:
-                def run_resident():
-                    graphed.replay()
-                    reducer.reduce_now()
+            graphed = cti_b200.GraphedStep(resident_step, [mods], [v_d], capture_error_mode=CAP_MODE)
+            run_resident = graphed.replay
             for _ in range(3):
                 run_resident()
         except Exception as exc:
@@ -344,13 +346,8 @@ def run_b200(args):
                 shared_step()
             run_shared = shared_step
             if use_graph:
-                g_sh = cti_b200.GraphedStep(shared_step, [mods], [vq_d])
-                if reducer is None:
-                    run_shared = g_sh.replay
-                else:
-                    def run_shared():
-                        g_sh.replay()
-                        reducer.reduce_now()
+                g_sh = cti_b200.GraphedStep(shared_step, [mods], [vq_d], capture_error_mode=CAP_MODE)
+                run_shared = g_sh.replay
                 for _ in range(3):
                     run_shared()
             ms_sh, _, _ = timed(run_shared, args.steps)
@@ -375,13 +372,8 @@ def run_b200(args):
         run_e2e = e2e_step
         if use_graph:
             try:
-                g_e2e = cti_b200.GraphedStep(e2e_step, [mods], [])
-                if reducer is None:
-                    run_e2e = g_e2e.replay
-                else:
-                    def run_e2e():
-                        g_e2e.replay()
-                        reducer.reduce_now()
+                g_e2e = cti_b200.GraphedStep(e2e_step, [mods], [], capture_error_mode=CAP_MODE)
+                run_e2e = g_e2e.replay
                 for _ in range(3):
                     run_e2e()
             except Exception:
@@ -431,7 +423,7 @@ def run_b200(args):
                     return compute
                 cs = [make_compute(i) for i in range(2)]
                 if use_graph:
-                    cs = [cti_b200.GraphedStep(cs[i], [mods], []).replay for i in range(2)]
+                    cs = [cti_b200.GraphedStep(cs[i], [mods], [], capture_error_mode=CAP_MODE).replay for i in range(2)]
                 state = {"i": 0, "primed": False}
 
                 def h2d_into(i):
@@ -449,8 +441,6 @@ def run_b200(args):
                     main = torch.cuda.current_stream()
                     main.wait_event(ev_copied[i])
                     joint = cs[i]()
-                    if reducer is not None and use_graph:
-                        reducer.reduce_now()
                     ev_done[i].record(main)
                     h2d_into(i ^ 1)                                    # prefetch the next step's inputs ...
                     with torch.cuda.stream(copy_stream):               # ... and read this step's result back behind them
@@ -496,7 +486,7 @@ def run_b200(args):
         run_fwd = fwd_only
         if use_graph:
             try:
-                run_fwd = cti_b200.GraphedStep(fwd_only, [], [v_d, q_d, a_d]).replay   # inference: weight packs stay cached
+                run_fwd = cti_b200.GraphedStep(fwd_only, [], [v_d, q_d, a_d], capture_error_mode=CAP_MODE).replay   # inference: weight packs stay cached
                 for _ in range(3):
                     run_fwd()
             except Exception:
@@ -565,7 +555,7 @@ def run_b200(args):
             run_ours = ours_step
             if use_graph:
                 try:
-                    run_ours = cti_b200.GraphedStep(ours_step, [], []).replay
+                    run_ours = cti_b200.GraphedStep(ours_step, [], [], capture_error_mode=CAP_MODE).replay
                 except Exception:
                     run_ours = ours_step
             ms_o, _, _ = timed(run_ours, args.steps, all_ranks=False)
@@ -611,7 +601,7 @@ def run_b200(args):
                 for _ in range(3):
                     fb()
                     opt.step(grad_denom=1.0)
-                run_fb = cti_b200.GraphedStep(fb, [model], [vv]).replay if use_graph else fb
+                run_fb = cti_b200.GraphedStep(fb, [model], [vv], capture_error_mode=CAP_MODE).replay if use_graph else fb
 
                 def train_step():
                     run_fb()
@@ -646,7 +636,7 @@ def run_b200(args):
             fb()
         run = fb
         if use_graph:
-            gph = cti_b200.GraphedStep(fb, [mods], [vv], allow_fixed_dropout=fixed_dropout).replay
+            gph = cti_b200.GraphedStep(fb, [mods], [vv], allow_fixed_dropout=fixed_dropout, capture_error_mode=CAP_MODE).replay
             if with_reducer and reducer is not None:
                 reducer.forget_sources()
 
@@ -758,7 +748,7 @@ def run_b200(args):
                 crit(out, teacher, target).backward()
             for _ in range(3):
                 fb()
-            run = cti_b200.GraphedStep(fb, [model], [vv]).replay if use_graph else fb
+            run = cti_b200.GraphedStep(fb, [model], [vv], capture_error_mode=CAP_MODE).replay if use_graph else fb
             for _ in range(3):
                 run()
             ms_, _, _ = timed(run, args.steps, all_ranks=False)
@@ -785,9 +775,13 @@ def run_b200(args):
         n_prof = 3
         KS.STATS.prof = []
         torch.cuda.synchronize()
+        step.reduce = False                      # this pass runs on rank 0 only
+        if reducer is not None:
+            reducer.set_hooks_enabled(False)
         for _ in range(n_prof):
             resident_step()
         torch.cuda.synchronize()
+        step.reduce = True
         rec, KS.STATS.prof = KS.STATS.prof, None
         agg = {}
         for name, tag, flops, nbytes, e0, e1 in rec:
@@ -886,8 +880,13 @@ def run_b200(args):
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # graphs that captured NCCL work keep the communicator busy at teardown (destroy_process_group() hangs behind
+        # them, tools/nccl_graph_probe.py): finish the device work, agree that every rank is done, leave
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

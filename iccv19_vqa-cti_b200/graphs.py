@@ -45,7 +45,11 @@ class GraphedStep:
     casts are part of the graph."""
 
     def __init__(self, step: Callable[[], object], modules: Iterable[torch.nn.Module],
-                 static_tensors: Iterable[torch.Tensor] = (), warmup: int = 3, allow_fixed_dropout: bool = False):
+                 static_tensors: Iterable[torch.Tensor] = (), warmup: int = 3, allow_fixed_dropout: bool = False,
+                 capture_error_mode: str = "global"):
+        """capture_error_mode: "thread_local" when the step issues NCCL collectives (``GradAllReducer.reduce_now()``
+        inside the step): NCCL's watchdog thread queries events while the capture is open, which the default "global"
+        mode turns into a hang (tools/nccl_graph_probe.py)."""
         modules, static_tensors = list(modules), list(static_tensors)
         # dropout sites (p, seed, offset) are host scalars baked into the captured launches: a graph captured in
         # train() mode would replay the SAME masks on every step.  Refuse unless the caller asks for exactly that.
@@ -65,7 +69,7 @@ class GraphedStep:
         torch.cuda.synchronize()
         reset_caches(modules, static_tensors)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
             self.output = step()
 
     def replay(self):
