@@ -250,12 +250,15 @@ def run_b200(args):
         q.requires_grad_(True)
         a.requires_grad_(True)
         p_att, _ = att(v, q, a)
-        qe, ae = q, a
-        for gi in range(GLIMPSE):
-            b_emb = pools[gi].forward_with_weights(v, qe, ae, p_att[:, :, :, :, gi])
-            qe = q_prj[gi](b_emb.unsqueeze(1)) + qe
-            ae = a_prj[gi](b_emb.unsqueeze(1)) + ae
-        joint = qe.sum(1) + ae.sum(1)
+        if step.fused:                           # opt-in: the glimpse loop + token sums as one call
+            joint = cti_b200.glimpse_joint(pools, q_prj, a_prj, v, q, a, p_att)
+        else:                                    # the reference model's own lines (src/MC/base_model.py:145-150)
+            qe, ae = q, a
+            for gi in range(GLIMPSE):
+                b_emb = pools[gi].forward_with_weights(v, qe, ae, p_att[:, :, :, :, gi])
+                qe = q_prj[gi](b_emb.unsqueeze(1)) + qe
+                ae = a_prj[gi](b_emb.unsqueeze(1)) + ae
+            joint = qe.sum(1) + ae.sum(1)
         (joint * cot).sum().backward()
         if reducer is not None and step.reduce:
             # eager: the hooks launched the bucketed all-reduces during backward; captured: the hook-free reduce is part
@@ -267,6 +270,7 @@ def run_b200(args):
         return joint
 
     step.graphed = False
+    step.fused = False
     step.reduce = True                           # False: rank-0-only passes (per-kernel profile) must not issue collectives
 
     def barrier():
@@ -356,6 +360,35 @@ def run_b200(args):
                               "GEMMs once per image; needs the clone line of src/MC/train.py:75-76 removed"}
         except Exception as exc:
             shared = {"failed": repr(exc)[:200]}
+
+    # ---- same step with the caller's glue fused (cti_b200.glimpse_joint replaces src/MC/base_model.py:145-150) -------
+    fused_leg = None
+    if not args.resident_only:
+        fused_leg = {"note": "TriAttention + cti_b200.glimpse_joint (glimpse loop, residual adds and token sums as one autograd "
+                             "node: same modules, parameters and values); opt-in, needs the six glue lines of the model's "
+                             "forward replaced by one call"}
+        try:
+            step.fused = True
+            for key, fn, vv in (("cloned_v", resident_step, v_d), ("shared_v", shared_step, vq_d)):
+                if key == "shared_v" and CLONE == 1:
+                    continue
+                for _ in range(3):
+                    fn()
+                KS.STATS.launches = 0
+                fn()
+                n_launch = KS.STATS.launches
+                run_f = fn
+                if use_graph:
+                    run_f = cti_b200.GraphedStep(fn, [mods], [vv], capture_error_mode=CAP_MODE).replay
+                    for _ in range(3):
+                        run_f()
+                ms_f_, _, _ = timed(run_f, args.steps)
+                fused_leg[key] = {"value": world * B * args.steps / (ms_f_ / 1e3), "unit": UNIT, "ms_per_step": ms_f_ / args.steps,
+                                  "gpu_launches_per_step": n_launch}
+        except Exception as exc:
+            fused_leg["failed"] = repr(exc)[:300]
+        finally:
+            step.fused = False
 
     # ---- end-to-end arm: pinned host inputs -> H2D -> modules -> D2H ----------
     def e2e_step():
@@ -876,7 +909,7 @@ def run_b200(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": dict(workload_config(B, world), launch="cuda_graph_replay" if use_graph else "eager"),
                 "eager": eager_ms, "e2e": e2e, "gpu_launches": launches, "gpu_launches_per_step": launches_per_step, "clocks": clocks,
-                "fwd_only": fwd, "shared_v": shared, "trainer_tail": tail, "gru": gru, "full_model": full, **extra,
+                "fwd_only": fwd, "shared_v": shared, "fused_glimpse_loop": fused_leg, "trainer_tail": tail, "gru": gru, "full_model": full, **extra,
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels}
         print(json.dumps(line), flush=True)
     if world > 1:

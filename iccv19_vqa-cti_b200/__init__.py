@@ -14,6 +14,7 @@ from .bc import BCNet
 from .classifier import SimpleClassifier
 from .dropin import install, uninstall
 from .fc import FCNet, WNLinear
+from .glimpse import glimpse_joint
 from .graphs import GraphedStep, reset_caches
 from .language_model import QuestionEmbedding
 from .loader import FeatureBatch, FeatureStoreBF16, TeacherLogits, prime_features
@@ -22,7 +23,7 @@ from .optim import FusedClipAdamax
 from .prepack import bind_grad_buffers, prepack
 from .tc import TCNet
 
-__all__ = ["FCNet", "WNLinear", "TCNet", "TriAttention", "BCNet", "BiAttention", "SimpleClassifier", "QuestionEmbedding", "Distillation_Loss", "FusedClipAdamax", "prepack", "bind_grad_buffers", "FeatureStoreBF16", "FeatureBatch", "TeacherLogits", "prime_features", "install", "uninstall", "GraphedStep", "reset_caches",
+__all__ = ["FCNet", "WNLinear", "TCNet", "TriAttention", "BCNet", "BiAttention", "SimpleClassifier", "QuestionEmbedding", "Distillation_Loss", "FusedClipAdamax", "prepack", "bind_grad_buffers", "FeatureStoreBF16", "FeatureBatch", "TeacherLogits", "prime_features", "install", "uninstall", "GraphedStep", "reset_caches", "glimpse_joint",
            "library_path", "version"]
 
 

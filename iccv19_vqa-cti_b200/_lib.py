@@ -61,6 +61,11 @@ SIGNATURES = {
     "cti_tri_pool_fwd": (c_int, [_P, _P, _P, _P, c_int64, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "cti_tri_pool_bwd": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int,
                                  c_int, c_int, _P]),
+    "cti_tri_pool_bwd_strided": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int,
+                                         c_int, c_int, c_int, _P]),
+    "cti_glimpse_residual_cast": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, _P, c_int, _P, c_int, c_int64, c_int, _P]),
+    "cti_glimpse_token_sum": (c_int, [_P, c_int, _P, c_int, _P, c_int, _P, c_int, c_int, _P, _P, c_int64, c_int, _P]),
+    "cti_glimpse_bcast_rows": (c_int, [_P, _P, c_int, _P, c_int, c_int64, c_int, _P]),
     "cti_bilinear_logits_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "cti_bilinear_logits_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
 }

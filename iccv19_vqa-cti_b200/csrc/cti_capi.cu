@@ -280,8 +280,39 @@ int cti_tri_pool_bwd(const void* v, const void* q, const void* a, const float* w
   return cti::tri_pool_bwd(static_cast<const __nv_bfloat16*>(v), static_cast<const __nv_bfloat16*>(q),
                            static_cast<const __nv_bfloat16*>(a), w, w_stride_b, dout,
                            static_cast<__nv_bfloat16*>(dzv), static_cast<__nv_bfloat16*>(dzq),
-                           static_cast<__nv_bfloat16*>(dza), dbv_accum, dbq_accum, dba_accum, dw, d,
+                           static_cast<__nv_bfloat16*>(dza), dbv_accum, dbq_accum, dba_accum, dw, 0, d,
                            static_cast<cudaStream_t>(stream));
+}
+
+int cti_tri_pool_bwd_strided(const void* v, const void* q, const void* a, const float* w, int64_t w_stride_b,
+                             const float* dout, void* dzv, void* dzq, void* dza, float* dbv_accum, float* dbq_accum,
+                             float* dba_accum, float* dw, int64_t dw_stride_b, int B, int K, int Q, int A, int C, int v_rep,
+                             void* stream) {
+  cti::PoolDims d{B, K, Q, A, C, v_rep};
+  return cti::tri_pool_bwd(static_cast<const __nv_bfloat16*>(v), static_cast<const __nv_bfloat16*>(q),
+                           static_cast<const __nv_bfloat16*>(a), w, w_stride_b, dout,
+                           static_cast<__nv_bfloat16*>(dzv), static_cast<__nv_bfloat16*>(dzq),
+                           static_cast<__nv_bfloat16*>(dza), dbv_accum, dbq_accum, dba_accum, dw, (long)dw_stride_b, d,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int cti_glimpse_residual_cast(const void* xq, int q_is_bf16, const float* const* res_q, int Tq, void* out_q_bf16,
+                              const void* xa, int a_is_bf16, const float* const* res_a, int Ta, void* out_a_bf16,
+                              int n_res, int64_t B, int D, void* stream) {
+  return cti::glimpse_residual_cast(xq, q_is_bf16, res_q, Tq, static_cast<__nv_bfloat16*>(out_q_bf16), xa, a_is_bf16, res_a,
+                                    Ta, static_cast<__nv_bfloat16*>(out_a_bf16), n_res, (long)B, D,
+                                    static_cast<cudaStream_t>(stream));
+}
+
+int cti_glimpse_token_sum(const void* xq, int q_is_bf16, const float* const* res_q, int Tq, const void* xa, int a_is_bf16,
+                          const float* const* res_a, int Ta, int n_res, float* out, void* out_bf16, int64_t B, int D,
+                          void* stream) {
+  return cti::glimpse_token_sum(xq, q_is_bf16, res_q, Tq, xa, a_is_bf16, res_a, Ta, n_res, out,
+                                static_cast<__nv_bfloat16*>(out_bf16), (long)B, D, static_cast<cudaStream_t>(stream));
+}
+
+int cti_glimpse_bcast_rows(const float* x, float* out_q, int Tq, float* out_a, int Ta, int64_t B, int D, void* stream) {
+  return cti::glimpse_bcast_rows(x, out_q, Tq, out_a, Ta, (long)B, D, static_cast<cudaStream_t>(stream));
 }
 
 int cti_bilinear_logits_fwd(const void* vb, const void* qb, const float* hmat, const float* hbias,

@@ -58,6 +58,15 @@ int wn_grad(const float* dw, const float* v, const float* g, const float* sumsq,
 int act_bwd_bias(const void* dy, int dy_is_bf16, const __nv_bfloat16* y, __nv_bfloat16* dz, float* dbias, long rows,
                  int cols, cudaStream_t s);
 
+// glimpse.cu  (caller glue of the glimpse loop for the fused call: residual add + cast, token sums, gradient broadcast)
+int glimpse_residual_cast(const void* xq, int q_bf16, const float* const* pq, int Tq, __nv_bfloat16* oq, const void* xa,
+                          int a_bf16, const float* const* pa, int Ta, __nv_bfloat16* oa, int n_res, long B, int D,
+                          cudaStream_t s);
+int glimpse_token_sum(const void* xq, int q_bf16, const float* const* pq, int Tq, const void* xa, int a_bf16,
+                      const float* const* pa, int Ta, int n_res, float* out, __nv_bfloat16* out_bf16, long B, int D,
+                      cudaStream_t s);
+int glimpse_bcast_rows(const float* x, float* oq, int Tq, float* oa, int Ta, long B, int D, cudaStream_t s);
+
 // optim.cu  (multi-tensor trainer tail; pointer / chunk tables live in device memory)
 int grad_sumsq_multi(const float* const* g_ptrs, const long* numel, const int* chunk_tensor, const long* chunk_start,
                      int n_chunks, int chunk_elems, float* partials, float* sumsq, cudaStream_t s);
@@ -109,7 +118,7 @@ int tri_pool_fwd(const __nv_bfloat16* v, const __nv_bfloat16* q, const __nv_bflo
                  float* out, PoolDims d, cudaStream_t s);
 int tri_pool_bwd(const __nv_bfloat16* v, const __nv_bfloat16* q, const __nv_bfloat16* a, const float* w, long w_stride_b,
                  const float* dout, __nv_bfloat16* dzv, __nv_bfloat16* dzq, __nv_bfloat16* dza, float* dbv, float* dbq,
-                 float* dba, float* dw, PoolDims d, cudaStream_t s);
+                 float* dba, float* dw, long dw_stride_b, PoolDims d, cudaStream_t s);   // dw_stride_b 0 = contiguous
 
 // bilinear.cu
 struct BiDims {

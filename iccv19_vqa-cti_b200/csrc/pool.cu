@@ -61,6 +61,7 @@ struct PoolParams {
   const float* dout;     // backward
   bf16 *dzv, *dzq, *dza;
   float *dbv, *dbq, *dba, *dw;
+  long dw_stride_b;          // elements between the dw tiles of consecutive rows (K * Q * An when contiguous)
   int B, K, Q, A, An, C, NC, nchunks;
   int VR;                // rows b share the v tile of row b / VR (dzv stays per row b)
 };
@@ -343,7 +344,7 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ 
           if (k < p.K) {
 #pragma unroll
             for (int qi = 0; qi < 16; ++qi)
-              if (qi < p.Q) p.dw[(((size_t)b * p.K + k) * p.Q + qi) * p.An + ai] = __uint_as_float(r[qi]);
+              if (qi < p.Q) p.dw[(size_t)b * p.dw_stride_b + ((size_t)k * p.Q + qi) * p.An + ai] = __uint_as_float(r[qi]);
           }
         }
         tcgen05_fence_before();
@@ -530,12 +531,13 @@ int tri_pool_fwd(const bf16* v, const bf16* q, const bf16* a, const float* w, lo
 }
 
 int tri_pool_bwd(const bf16* v, const bf16* q, const bf16* a, const float* w, long w_stride_b, const float* dout,
-                 bf16* dzv, bf16* dzq, bf16* dza, float* dbv, float* dbq, float* dba, float* dw, PoolDims d,
-                 cudaStream_t stream) {
+                 bf16* dzv, bf16* dzq, bf16* dza, float* dbv, float* dbq, float* dba, float* dw, long dw_stride_b,
+                 PoolDims d, cudaStream_t stream) {
   if (int rc = check_pool(d, "tri_pool_bwd")) return rc;
   if (d.B == 0) return 0;
   PoolParams p = make_params(q, a, w, w_stride_b, d);
   p.dout = dout; p.dzv = dzv; p.dzq = dzq; p.dza = dza; p.dbv = dbv; p.dbq = dbq; p.dba = dba; p.dw = dw;
+  p.dw_stride_b = dw_stride_b > 0 ? dw_stride_b : (long)d.K * d.Q * (d.A > 0 ? d.A : 1);
   if (int rc = launch_pool<true>(v, p, stream, "tri_pool_bwd")) return rc;
   // image-side bias gradient: column sums of dzv (token-on-lane epilogue: no cheap in-kernel reduction over tokens)
   return act_bwd_bias(dzv, 1, nullptr, nullptr, dbv, (long)d.B * d.K, d.C, stream);

@@ -6,6 +6,7 @@ PyTorch is plumbing here: device memory and streams only.  No function has a fal
 """
 from __future__ import annotations
 
+import ctypes
 from typing import Optional, Tuple
 
 import torch
@@ -417,19 +418,30 @@ def tri_pool_fwd(v, q, a, w, w_stride_b, B, K, Q, A, C, v_rep: int = 1) -> torch
     return out
 
 
-def tri_pool_bwd(v, q, a, w, w_stride_b, dout, B, K, Q, A, C, v_rep: int = 1):
-    """Returns dzv, dzq, dza (bf16), dbv, dbq, dba (fp32, C), dw (B,K,Q[,A]) fp32.  A == 0: bilinear."""
+def tri_pool_bwd(v, q, a, w, w_stride_b, dout, B, K, Q, A, C, v_rep: int = 1, dw_out: Optional[torch.Tensor] = None):
+    """Returns dzv, dzq, dza (bf16), dbv, dbq, dba (fp32, C), dw (B,K,Q[,A]) fp32.  A == 0: bilinear.
+    dw_out: optional fp32 view the attention gradient is written into: row b at dw_out.stride(0), contiguous inside a row
+    (the glimpse slice of a (B, G, K*Q*A) buffer)."""
     _req(dout, F32, "tri_pool_bwd.dout")
     dev = v.device
     dzv, dzq = torch.empty((B * K, C), dtype=BF16, device=dev), torch.empty_like(q)
     dza = torch.empty_like(a) if A > 0 else None
     zeros = torch.zeros((3 * C,), dtype=F32, device=dev)
     dbv, dbq, dba = zeros[:C], zeros[C:2 * C], zeros[2 * C:]
-    dw = torch.empty((B, K, Q, A) if A > 0 else (B, K, Q), dtype=F32, device=dev)
-    _call("cti_tri_pool_bwd", _lib.load().cti_tri_pool_bwd,
-          (v.data_ptr(), q.data_ptr(), _ptr(a), w.data_ptr(), w_stride_b, dout.data_ptr(), dzv.data_ptr(), dzq.data_ptr(),
-           _ptr(dza), dbv.data_ptr(), dbq.data_ptr(), dba.data_ptr(), dw.data_ptr(), B, K, Q, A, C, v_rep, _stream()),
-          flops=2.0 * B * pool_flops(K, Q, A, C))
+    if dw_out is None:
+        dw = torch.empty((B, K, Q, A) if A > 0 else (B, K, Q), dtype=F32, device=dev)
+        _call("cti_tri_pool_bwd", _lib.load().cti_tri_pool_bwd,
+              (v.data_ptr(), q.data_ptr(), _ptr(a), w.data_ptr(), w_stride_b, dout.data_ptr(), dzv.data_ptr(), dzq.data_ptr(),
+               _ptr(dza), dbv.data_ptr(), dbq.data_ptr(), dba.data_ptr(), dw.data_ptr(), B, K, Q, A, C, v_rep, _stream()),
+              kernels=2, flops=2.0 * B * pool_flops(K, Q, A, C))
+    else:
+        dw = dw_out
+        if dw.dtype != F32 or dw.shape[0] != B or dw[0].numel() != K * Q * max(A, 1) or not dw[0].is_contiguous():
+            raise RuntimeError("tri_pool_bwd.dw_out: expected an fp32 (B, K*Q*A) view with contiguous rows")
+        _call("cti_tri_pool_bwd", _lib.load().cti_tri_pool_bwd_strided,
+              (v.data_ptr(), q.data_ptr(), _ptr(a), w.data_ptr(), w_stride_b, dout.data_ptr(), dzv.data_ptr(), dzq.data_ptr(),
+               _ptr(dza), dbv.data_ptr(), dbq.data_ptr(), dba.data_ptr(), dw.data_ptr(), dw.stride(0), B, K, Q, A, C, v_rep,
+               _stream()), kernels=2, flops=2.0 * B * pool_flops(K, Q, A, C))
     if v_rep > 1:
         dzv = sum_row_groups(dzv, v_rep, K * C)
     return dzv, dzq, dza, dbv, dbq, (dba if A > 0 else None), dw
@@ -491,3 +503,64 @@ def gru_gate_bwd(dh: torch.Tensor, dout_t: torch.Tensor, h_prev: Optional[torch.
           (dh.data_ptr(), dout_t.data_ptr(), dout_t.stride(0), _ptr(h_prev), 0 if h_prev is None else h_prev.stride(0),
            r.data_ptr(), z.data_ptr(), n.data_ptr(), ghn.data_ptr(), dgx_t.data_ptr(), dgx_t.stride(0), dgh.data_ptr(), B, H,
            _stream()), nbytes=float(B) * H * (4 * 3 + 4 * 2 + 6 * 2 + 4))
+
+
+# --------------------------------------------------------------------------- #
+# caller glue of the glimpse loop (fused call, glimpse.py)
+# --------------------------------------------------------------------------- #
+def _res_array(res):
+    arr = (ctypes.c_void_p * 4)(*([t.data_ptr() for t in res] + [None] * (4 - len(res))))
+    return arr
+
+
+def _tok(t: torch.Tensor, name: str):
+    if not t.is_cuda or t.dtype not in (F32, BF16) or t.dim() != 3 or not t.is_contiguous():
+        raise RuntimeError(f"{name}: expected a contiguous (rows, tokens, dim) fp32 / bf16 CUDA tensor")
+    return t.data_ptr(), int(t.dtype == BF16)
+
+
+def glimpse_residual_cast(q: torch.Tensor, res_q, a: Optional[torch.Tensor], res_a):
+    """bf16((q + res_q[0][:, None] + ...)) as (B*Tq, D) and the same for a: the operands of the next glimpse's q_tucker /
+    a_tucker GEMMs (reference src/MC/base_model.py:147-148 followed by the cast)."""
+    B, Tq, D = q.shape
+    for r in list(res_q) + list(res_a):
+        _req(r, F32, "glimpse_residual_cast.res")
+    qp, qb = _tok(q, "glimpse_residual_cast.q")
+    oq = torch.empty((B * Tq, D), dtype=BF16, device=q.device)
+    ap, ab, Ta, oa = None, 0, 0, None
+    if a is not None:
+        ap, ab = _tok(a, "glimpse_residual_cast.a")
+        Ta = a.shape[1]
+        oa = torch.empty((B * Ta, D), dtype=BF16, device=q.device)
+    rq, ra = _res_array(res_q), _res_array(res_a)
+    _call("cti_glimpse_glue", _lib.load().cti_glimpse_residual_cast,
+          (qp, qb, rq, Tq, oq.data_ptr(), ap, ab, ra, Ta, _ptr(oa), len(res_q), B, D, _stream()),
+          nbytes=float(B) * (Tq + Ta) * D * (q.element_size() + 2))
+    return oq, oa
+
+
+def glimpse_token_sum(q: torch.Tensor, res_q, a: Optional[torch.Tensor], res_a) -> torch.Tensor:
+    """sum_t (q[:, t] + res_q...) + sum_t (a[:, t] + res_a...) -> (B, D) fp32 (reference src/MC/base_model.py:150)."""
+    B, Tq, D = q.shape
+    qp, qb = _tok(q, "glimpse_token_sum.q")
+    ap, ab, Ta = None, 0, 0
+    if a is not None:
+        ap, ab = _tok(a, "glimpse_token_sum.a")
+        Ta = a.shape[1]
+    out = torch.empty((B, D), dtype=F32, device=q.device)
+    rq, ra = _res_array(res_q), _res_array(res_a)
+    _call("cti_glimpse_glue", _lib.load().cti_glimpse_token_sum,
+          (qp, qb, rq, Tq, ap, ab, ra, Ta, len(res_q), out.data_ptr(), None, B, D, _stream()),
+          nbytes=float(B) * (Tq + Ta) * D * q.element_size())
+    return out
+
+
+def glimpse_bcast_rows(x: torch.Tensor, Tq: int, Ta: int):
+    """x (B, D) fp32 -> (B, Tq, D), (B, Ta, D) fp32 copies of it along the token axis."""
+    _req(x, F32, "glimpse_bcast_rows.x")
+    B, D = x.shape
+    oq = torch.empty((B, Tq, D), dtype=F32, device=x.device)
+    oa = torch.empty((B, Ta, D), dtype=F32, device=x.device) if Ta > 0 else None
+    _call("cti_glimpse_glue", _lib.load().cti_glimpse_bcast_rows,
+          (x.data_ptr(), oq.data_ptr(), Tq, _ptr(oa), Ta, B, D, _stream()), nbytes=4.0 * B * (Tq + Ta + 1) * D)
+    return oq, oa

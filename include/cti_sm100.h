@@ -227,6 +227,33 @@ int cti_tri_pool_bwd(const void* v, const void* q, const void* a, const float* w
                      const float* dout, void* dzv, void* dzq, void* dza, float* dbv_accum, float* dbq_accum,
                      float* dba_accum, float* dw, int B, int K, int Q, int A, int C, int v_rep, void* stream);
 
+/* Same, with the attention gradient written at a row stride: dw[b * dw_stride_b + (k*Q + q)*A + a].  The fused glimpse
+ * loop hands in the glimpse-g slice of ONE (B, G, K*Q*A) buffer -- the layout cti_masked_softmax_bwd reads -- so the
+ * backward of `att[:, :, :, :, g]` (reference src/MC/base_model.py:146: a zero fill, a strided copy and an add per
+ * glimpse under autograd) costs nothing.  dw_stride_b = 0: contiguous. */
+int cti_tri_pool_bwd_strided(const void* v, const void* q, const void* a, const float* w, int64_t w_stride_b,
+                             const float* dout, void* dzv, void* dzq, void* dza, float* dbv_accum, float* dbq_accum,
+                             float* dba_accum, float* dw, int64_t dw_stride_b, int B, int K, int Q, int A, int C, int v_rep,
+                             void* stream);
+
+/* ---- caller glue of the glimpse loop (opt-in fused call) ------------------------------------------
+ * replaces the torch ops of src/MC/base_model.py:147-150 / src/FFOE/base_model.py:127-130:
+ *     q_emb = q_prj[g](b_emb[g].unsqueeze(1)) + q_emb ; ans_emb = a_prj[g](...) + ans_emb ; q_emb.sum(1) + ans_emb.sum(1)
+ * x* (B, T*, D) fp32 or bf16 token tensors; res_* = HOST arrays of n_res (<= 4) device pointers to (B, D) fp32 projection
+ * outputs, added in order ((x + r0) + r1) + ... exactly as the caller's loop does; D % 8 == 0; xa may be NULL.
+ * residual_cast: out_*[b,t,:] = bf16(x*[b,t,:] + sum_i res_*[i][b,:]) -- the only form of the updated q_emb / ans_emb the next
+ *     glimpse consumes (operand of its q_tucker / a_tucker GEMM).
+ * token_sum:     out[b,:] = sum_t (xq[b,t,:] + ...) + sum_t (xa[b,t,:] + ...)  (fp32 and / or bf16 output).
+ * bcast_rows:    out_*[b,t,:] = x[b,:]: the joint gradient as the initial value of d q_emb / d ans_emb, which the dgrad GEMMs
+ *     of every glimpse then accumulate into. */
+int cti_glimpse_residual_cast(const void* xq, int q_is_bf16, const float* const* res_q, int Tq, void* out_q_bf16,
+                              const void* xa, int a_is_bf16, const float* const* res_a, int Ta, void* out_a_bf16,
+                              int n_res, int64_t B, int D, void* stream);
+int cti_glimpse_token_sum(const void* xq, int q_is_bf16, const float* const* res_q, int Tq, const void* xa, int a_is_bf16,
+                          const float* const* res_a, int Ta, int n_res, float* out, void* out_bf16, int64_t B, int D,
+                          void* stream);
+int cti_glimpse_bcast_rows(const float* x, float* out_q, int Tq, float* out_a, int Ta, int64_t B, int D, void* stream);
+
 /* ---- bilinear attention logits (BAN) ------------------------------------------------------------
  * logits[b,g,k,q] = sum_c Vb[b,k,c] h[g,c] Qb[b,q,c] + hbias[g]; -inf where rowmask[b*K+k] != 0.
  * vb (B,K,C), qb (B,Q,C) bf16; hmat (G,C), hbias (G) fp32; logits (B,G,K,Q) fp32.
