@@ -63,6 +63,11 @@ SIGNATURES = {
                                  c_int, c_int, _P]),
     "cti_tri_pool_bwd_strided": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int,
                                          c_int, c_int, c_int, _P]),
+    "cti_rank_proj_dropout_scale": (c_float, [c_float]),
+    "cti_rank_proj_dropout_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_float, ctypes.c_uint64, ctypes.c_uint64, _P]),
+    "cti_rank_proj_dropout_dgrad": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_float, ctypes.c_uint64, ctypes.c_uint64, _P]),
+    "cti_rank_proj_dropout_wgrad": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_float, ctypes.c_uint64, ctypes.c_uint64, _P]),
+    "cti_rank_proj_dropout_mask": (c_int, [_P, c_int64, c_int, c_int, c_float, ctypes.c_uint64, ctypes.c_uint64, _P]),
     "cti_glimpse_residual_cast": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, _P, c_int, _P, c_int, c_int64, c_int, _P]),
     "cti_glimpse_token_sum": (c_int, [_P, c_int, _P, c_int, _P, c_int, _P, c_int, c_int, _P, _P, c_int64, c_int, _P]),
     "cti_glimpse_bcast_rows": (c_int, [_P, _P, c_int, _P, c_int, c_int64, c_int, _P]),

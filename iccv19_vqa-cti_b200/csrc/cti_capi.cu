@@ -296,6 +296,32 @@ int cti_tri_pool_bwd_strided(const void* v, const void* q, const void* a, const 
                            static_cast<cudaStream_t>(stream));
 }
 
+float cti_rank_proj_dropout_scale(float p) { return cti::rank_proj_scale(p); }
+
+int cti_rank_proj_dropout_fwd(const void* y, const void* w_eff, const float* bias, void* out, int64_t M, int H, int R, float p,
+                              uint64_t seed, uint64_t site, void* stream) {
+  return cti::rank_proj_dropout_fwd(static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(w_eff), bias,
+                                    static_cast<__nv_bfloat16*>(out), (long)M, H, R, p, seed, site,
+                                    static_cast<cudaStream_t>(stream));
+}
+
+int cti_rank_proj_dropout_dgrad(const void* dz, const void* w_eff, const void* y, void* dzt, int64_t M, int H, int R, float p,
+                                uint64_t seed, uint64_t site, void* stream) {
+  return cti::rank_proj_dropout_dgrad(static_cast<const __nv_bfloat16*>(dz), static_cast<const __nv_bfloat16*>(w_eff),
+                                      static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(dzt), (long)M, H, R, p,
+                                      seed, site, static_cast<cudaStream_t>(stream));
+}
+
+int cti_rank_proj_dropout_wgrad(const void* dz, const void* y, float* dw_accum, int64_t M, int H, int R, float p, uint64_t seed,
+                                uint64_t site, void* stream) {
+  return cti::rank_proj_dropout_wgrad(static_cast<const __nv_bfloat16*>(dz), static_cast<const __nv_bfloat16*>(y), dw_accum,
+                                      (long)M, H, R, p, seed, site, static_cast<cudaStream_t>(stream));
+}
+
+int cti_rank_proj_dropout_mask(uint8_t* keep, int64_t M, int H, int R, float p, uint64_t seed, uint64_t site, void* stream) {
+  return cti::rank_proj_dropout_mask(keep, (long)M, H, R, p, seed, site, static_cast<cudaStream_t>(stream));
+}
+
 int cti_glimpse_residual_cast(const void* xq, int q_is_bf16, const float* const* res_q, int Tq, void* out_q_bf16,
                               const void* xa, int a_is_bf16, const float* const* res_a, int Ta, void* out_a_bf16,
                               int n_res, int64_t B, int D, void* stream) {

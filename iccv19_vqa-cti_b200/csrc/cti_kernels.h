@@ -67,6 +67,16 @@ int glimpse_token_sum(const void* xq, int q_bf16, const float* const* pq, int Tq
                       cudaStream_t s);
 int glimpse_bcast_rows(const float* x, float* oq, int Tq, float* oa, int Ta, long B, int D, cudaStream_t s);
 
+// rank_proj.cu  (the R per-rank projections of a modality with per-rank input dropout, masks applied in registers)
+float rank_proj_scale(float p);
+int rank_proj_dropout_fwd(const __nv_bfloat16* y, const __nv_bfloat16* W, const float* bias, __nv_bfloat16* out, long M, int H,
+                          int R, float p, uint64_t seed, uint64_t site, cudaStream_t s);
+int rank_proj_dropout_dgrad(const __nv_bfloat16* dz, const __nv_bfloat16* W, const __nv_bfloat16* y, __nv_bfloat16* dzt, long M,
+                            int H, int R, float p, uint64_t seed, uint64_t site, cudaStream_t s);
+int rank_proj_dropout_wgrad(const __nv_bfloat16* dz, const __nv_bfloat16* y, float* dW_accum, long M, int H, int R, float p,
+                            uint64_t seed, uint64_t site, cudaStream_t s);
+int rank_proj_dropout_mask(uint8_t* keep, long M, int H, int R, float p, uint64_t seed, uint64_t site, cudaStream_t s);
+
 // optim.cu  (multi-tensor trainer tail; pointer / chunk tables live in device memory)
 int grad_sumsq_multi(const float* const* g_ptrs, const long* numel, const int* chunk_tensor, const long* chunk_start,
                      int n_chunks, int chunk_elems, float* partials, float* sumsq, cudaStream_t s);

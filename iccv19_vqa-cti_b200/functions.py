@@ -219,6 +219,8 @@ def rank_proj_fwd(y: torch.Tensor, pk: Packed, bias: torch.Tensor, drop, R: int)
     M, H = y.shape
     N = pk.w.shape[0]
     d = N // R
+    if d == 16 and K_.rank_proj_fused_ok(H, R):       # masks applied to the A fragments in registers (rank_proj.cu)
+        return K_.rank_proj_dropout_fwd(y, pk.w, bias.detach().contiguous(), R, drop)
     rg = RANK_GROUP if R % RANK_GROUP == 0 else 1
     out = torch.empty((M, N), dtype=BF16, device=y.device)
     b = bias.detach()
@@ -236,6 +238,16 @@ def rank_proj_bwd(y: torch.Tensor, dz: torch.Tensor, V: torch.Tensor, g: torch.T
     M, H = y.shape
     N = pk.w.shape[0]
     d = N // R
+    if d == 16 and K_.rank_proj_fused_ok(H, R):
+        # fused: the masks are regenerated in registers; dgrad already carries y's ReLU mask (bf16), wgrad accumulates
+        deferred = pk.dw is not None
+        dw = pk.dw if deferred else torch.zeros((N, H), dtype=F32, device=y.device)
+        K_.rank_proj_dropout_wgrad(dz, y, dw, R, drop)
+        dzt = K_.rank_proj_dropout_dgrad(dz, pk.w, y, R, drop)
+        if deferred:
+            return dw, None, dzt
+        dV, dg = K_.wn_grad(dw, V.detach().contiguous(), g.detach().reshape(R).contiguous(), pk.sumsq, R)
+        return dV, dg.reshape(g.shape), dzt
     rg = RANK_GROUP if R % RANK_GROUP == 0 else 1
     wt = _block_diag_weights(pk.w, R, rg)
     dw = torch.empty((N, H), dtype=F32, device=y.device)
@@ -425,6 +437,8 @@ class TriLogitsFn(Function):
             still to be applied (independent per-rank dropout: the fp32 accumulator comes back instead)"""
             if drop is not None and ctx.independent:
                 dV_, dg_, acc = rank_proj_bwd(y, dz, V, g, pki, drop, R)
+                if acc.dtype == BF16:                          # fused kernels: ReLU mask of y already applied
+                    return dV_, dg_, acc, None
                 return dV_, dg_, None, acc
             dV_, dg_, dzt = lin_bwd(y, dz, V, g, pki, R, True, dx_relu_aux=y, dx_alpha=sc(drop), dw=dw_)
             return dV_, dg_, dzt, None

@@ -564,3 +564,59 @@ def glimpse_bcast_rows(x: torch.Tensor, Tq: int, Ta: int):
     _call("cti_glimpse_glue", _lib.load().cti_glimpse_bcast_rows,
           (x.data_ptr(), oq.data_ptr(), Tq, _ptr(oa), Ta, B, D, _stream()), nbytes=4.0 * B * (Tq + Ta + 1) * D)
     return oq, oa
+
+
+# --------------------------------------------------------------------------- #
+# per-rank projections with per-rank input dropout, masks applied in registers (rank_proj.cu)
+# --------------------------------------------------------------------------- #
+def rank_proj_fused_ok(H: int, R: int) -> bool:
+    """Shapes the fused kernels are built for (the reference's: h_mm = 512, rank = 32)."""
+    return H == 512 and R % 16 == 0 and 16 <= R <= 64
+
+
+def rank_proj_scale(p: float) -> float:
+    """1 / (1 - p_eff): the drop rate is quantised to round(256 p) / 256 (include/cti_sm100.h)."""
+    return float(_lib.load().cti_rank_proj_dropout_scale(float(p)))
+
+
+def rank_proj_dropout_fwd(y: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, R: int, drop) -> torch.Tensor:
+    _req(y, BF16, "rank_proj_dropout_fwd.y")
+    _req(w, BF16, "rank_proj_dropout_fwd.w")
+    _req(bias, F32, "rank_proj_dropout_fwd.bias")
+    M, H = y.shape
+    out = torch.empty((M, R * 16), dtype=BF16, device=y.device)
+    _call("cti_rank_proj_dropout", _lib.load().cti_rank_proj_dropout_fwd,
+          (y.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr(), M, H, R, drop[0], drop[1], drop[2], _stream()),
+          flops=2.0 * M * H * R * 16, tag="fwd")
+    return out
+
+
+def rank_proj_dropout_dgrad(dz: torch.Tensor, w: torch.Tensor, y: torch.Tensor, R: int, drop) -> torch.Tensor:
+    """-> pre-activation gradient of the layer that produced y (bf16, y's ReLU mask applied)."""
+    _req(dz, BF16, "rank_proj_dropout_dgrad.dz")
+    _req(y, BF16, "rank_proj_dropout_dgrad.y")
+    M, H = y.shape
+    dzt = torch.empty((M, H), dtype=BF16, device=y.device)
+    _call("cti_rank_proj_dropout", _lib.load().cti_rank_proj_dropout_dgrad,
+          (dz.data_ptr(), w.data_ptr(), y.data_ptr(), dzt.data_ptr(), M, H, R, drop[0], drop[1], drop[2], _stream()),
+          flops=2.0 * M * H * R * 16, tag="dgrad")
+    return dzt
+
+
+def rank_proj_dropout_wgrad(dz: torch.Tensor, y: torch.Tensor, dw: torch.Tensor, R: int, drop) -> None:
+    """dw (R*16, H) fp32 += masked wgrad."""
+    _req(dz, BF16, "rank_proj_dropout_wgrad.dz")
+    _req(y, BF16, "rank_proj_dropout_wgrad.y")
+    _req(dw, F32, "rank_proj_dropout_wgrad.dw")
+    M, H = y.shape
+    _call("cti_rank_proj_dropout", _lib.load().cti_rank_proj_dropout_wgrad,
+          (dz.data_ptr(), y.data_ptr(), dw.data_ptr(), M, H, R, drop[0], drop[1], drop[2], _stream()),
+          flops=2.0 * M * H * R * 16, tag="wgrad")
+
+
+def rank_proj_dropout_mask(M: int, H: int, R: int, drop, device) -> torch.Tensor:
+    """keep[r, m, k] (uint8) exactly as the fused kernels regenerate it (tests)."""
+    keep = torch.empty((R, M, H), dtype=torch.uint8, device=device)
+    _call("cti_rank_proj_dropout", _lib.load().cti_rank_proj_dropout_mask,
+          (keep.data_ptr(), M, H, R, drop[0], drop[1], drop[2], _stream()))
+    return keep

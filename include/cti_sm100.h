@@ -236,6 +236,25 @@ int cti_tri_pool_bwd_strided(const void* v, const void* q, const void* a, const 
                              float* dba_accum, float* dw, int64_t dw_stride_b, int B, int K, int Q, int A, int C, int v_rep,
                              void* stream);
 
+/* ---- the R per-rank projections of one modality with PER-RANK input dropout (training mode) ---------------------------
+ * replaces: `self.v_net[r](v_tucker)` for r < rank (src/tc.py:29-31,47-49), each FCNet = Dropout(p) -> weight_norm(Linear
+ * (512, 16)) -> ReLU (src/fc.py:25-29), i.e. R independent Bernoulli masks on the same (M, 512) input.
+ *   fwd  : out[m, r*16+j] = relu(s * sum_k keep_r[m,k] y[m,k] W[r*16+j, k] + bias[r*16+j])          (bf16)
+ *   dgrad: dzt[m, k]      = (y[m,k] > 0) * s * sum_r keep_r[m,k] * sum_j dz[m, r*16+j] W[r*16+j, k]  (bf16; y's ReLU mask applied)
+ *   wgrad: dw_accum[r*16+j, k] += s * sum_m dz[m, r*16+j] keep_r[m,k] y[m,k]                          (fp32, accumulates)
+ * y (M, H) bf16, w_eff (R*16, H) bf16 (the weight-norm fold), H == 512, R a multiple of 16.  The masks are never stored:
+ * each kernel regenerates them in registers from (seed, site) with Philox4x32-7, 8 bits per decision, so the drop rate is
+ * round(256 p) / 256 and s = cti_rank_proj_dropout_scale(p) = 256 / (256 - round(256 p)).  cti_rank_proj_dropout_mask writes
+ * keep[r, m, k] (uint8, R*M*H) for tests. */
+float cti_rank_proj_dropout_scale(float p);
+int cti_rank_proj_dropout_fwd(const void* y, const void* w_eff, const float* bias, void* out, int64_t M, int H, int R, float p,
+                              uint64_t seed, uint64_t site, void* stream);
+int cti_rank_proj_dropout_dgrad(const void* dz, const void* w_eff, const void* y, void* dzt, int64_t M, int H, int R, float p,
+                                uint64_t seed, uint64_t site, void* stream);
+int cti_rank_proj_dropout_wgrad(const void* dz, const void* y, float* dw_accum, int64_t M, int H, int R, float p, uint64_t seed,
+                                uint64_t site, void* stream);
+int cti_rank_proj_dropout_mask(uint8_t* keep, int64_t M, int H, int R, float p, uint64_t seed, uint64_t site, void* stream);
+
 /* ---- caller glue of the glimpse loop (opt-in fused call) ------------------------------------------
  * replaces the torch ops of src/MC/base_model.py:147-150 / src/FFOE/base_model.py:127-130:
  *     q_emb = q_prj[g](b_emb[g].unsqueeze(1)) + q_emb ; ans_emb = a_prj[g](...) + ans_emb ; q_emb.sum(1) + ans_emb.sum(1)

@@ -134,24 +134,31 @@ def test_dropout_zero_in_train_mode_equals_eval():
     assert torch.equal(p1, p2)
 
 
-def test_per_rank_nets_draw_independent_masks_and_match_autograd():
-    """The R per-rank FCNets each own a Dropout in the reference (src/tc.py:29-31).  The masks the kernels use are
-    recovered by pushing ones through the expand kernel; forward and backward are then compared with autograd of
-    the same masked computation in fp32."""
+@pytest.mark.parametrize("M,p", [(300, 0.5), (1000, 0.2), (64, 0.5)])
+def test_per_rank_nets_draw_independent_masks_and_match_autograd(M, p):
+    """The R per-rank FCNets each own a Dropout in the reference (src/tc.py:29-31).  The fused kernels (rank_proj.cu)
+    regenerate the masks in registers; cti_rank_proj_dropout_mask writes the same masks out element by element.  Forward and
+    backward are compared with autograd of the same masked computation in fp32."""
     torch.manual_seed(0)
-    M, H, R, d, p = 300, 512, 32, 16, 0.5
+    H, R, d = 512, 32, 16
     site = (p, 99, 5)
+    assert K_.rank_proj_fused_ok(H, R)
     y = torch.relu(torch.randn(M, H, device=DEV)).to(torch.bfloat16)
     V = (torch.randn(R * d, H, device=DEV) / H ** 0.5).requires_grad_(True)
     g = V.detach().view(R, -1).norm(dim=1).clone().requires_grad_(True)
     bias = (torch.randn(R * d, device=DEV) * 0.1).requires_grad_(True)
     pk = F_.pack_layer(V, g, R)
     out = F_.rank_proj_fwd(y, pk, bias, site, R)
-    masks = torch.stack([K_.dropout_expand(torch.ones_like(y), 1, r, site) for r in range(R)], 0).float()   # (R,M,H): 0 or 2
-    assert set(masks.unique().tolist()) == {0.0, 1 / (1 - p)}
-    assert abs((masks != 0).float().mean().item() - (1 - p)) < 5e-3
-    same = ((masks[0] != 0) == (masks[1] != 0)).float().mean().item()
-    assert abs(same - 0.5) < 0.02                                          # ranks 0 and 1: independent masks
+    keep = K_.rank_proj_dropout_mask(M, H, R, site, DEV).float()                                 # (R, M, H) in {0, 1}
+    scale = K_.rank_proj_scale(p)
+    p_eff = round(p * 256) / 256
+    assert scale == pytest.approx(1 / (1 - p_eff), rel=1e-6) and abs(p_eff - p) < 2e-3
+    assert set(keep.unique().tolist()) == {0.0, 1.0}
+    assert abs(keep.mean().item() - (1 - p_eff)) < 3e-3
+    same = (keep[0] == keep[1]).float().mean().item()
+    assert abs(same - (p_eff ** 2 + (1 - p_eff) ** 2)) < 0.02                                   # ranks 0 and 1: independent masks
+    assert abs((keep[:, 0] == keep[:, 1]).float().mean().item() - (p_eff ** 2 + (1 - p_eff) ** 2)) < 0.03   # rows too
+    masks = keep * scale
     yl = y.float().requires_grad_(True)
     w_eff = (V.view(R, -1) * (g / V.view(R, -1).norm(dim=1))[:, None]).view(R, d, H)
     ref = torch.relu(torch.einsum("rmh,rdh->mrd", yl[None] * masks, w_eff.to(torch.bfloat16).float()) + bias.view(R, d))
@@ -162,9 +169,31 @@ def test_per_rank_nets_draw_independent_masks_and_match_autograd():
     dz = (cot * (out.float() > 0)).to(torch.bfloat16)
     dV, dg, dy = F_.rank_proj_bwd(y, dz, V.detach(), g.detach(), pk, site, R)
     rel = lambda a, b: ((a.float() - b.float()).abs().max() / b.float().abs().max()).item()
-    assert rel(dy, yl.grad) < 3e-2
+    assert dy.dtype == torch.bfloat16                                      # fused dgrad: ReLU mask of y applied, bf16
+    assert rel(dy, yl.grad * (y > 0)) < 3e-2
     assert rel(dV, V.grad) < 3e-2
     assert ((dg - g.grad).abs().max() / V.grad.view(R, -1).norm(dim=1).max()).item() < 3e-2
+    # same site, same masks: deterministic forward; another site, other masks
+    assert torch.equal(out, F_.rank_proj_fwd(y, pk, bias, site, R))
+    assert not torch.equal(out, F_.rank_proj_fwd(y, pk, bias, (p, 99, 6), R))
+
+
+def test_expand_path_still_serves_other_shapes():
+    """Widths the fused kernels are not built for (H != 512) go through cti_dropout_expand + block-diagonal GEMMs."""
+    torch.manual_seed(0)
+    M, H, R, d, p = 96, 256, 32, 16, 0.5
+    site = (p, 99, 5)
+    assert not K_.rank_proj_fused_ok(H, R)
+    y = torch.relu(torch.randn(M, H, device=DEV)).to(torch.bfloat16)
+    V = (torch.randn(R * d, H, device=DEV) / H ** 0.5)
+    g = V.view(R, -1).norm(dim=1).clone()
+    bias = torch.randn(R * d, device=DEV) * 0.1
+    pk = F_.pack_layer(V, g, R)
+    out = F_.rank_proj_fwd(y, pk, bias, site, R)
+    masks = torch.stack([K_.dropout_expand(torch.ones_like(y), 1, r, site) for r in range(R)], 0).float()
+    w_eff = (V.view(R, -1) * (g / V.view(R, -1).norm(dim=1))[:, None]).view(R, d, H)
+    ref = torch.relu(torch.einsum("rmh,rdh->mrd", y.float()[None] * masks, w_eff.to(torch.bfloat16).float()) + bias.view(R, d))
+    assert ((out.float() - ref.reshape(M, R * d)).abs().max() / ref.abs().max()).item() < 1e-2
 
 
 def test_rank_dropout_modes_both_run():
