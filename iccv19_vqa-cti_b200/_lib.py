@@ -25,6 +25,12 @@ class GemmDesc(ctypes.Structure):
                 ("atomic_f32", c_int), ("k_splits", c_int), ("tile_n", c_int)]
 
 
+class RankProjProblem(ctypes.Structure):
+    """cti_rank_proj_problem of include/cti_sm100.h."""
+    _fields_ = [("y", _P), ("w_eff", _P), ("bias", _P), ("out", _P), ("dz", _P), ("dzt", _P), ("dw_accum", _P),
+                ("M", c_int64), ("p", c_float), ("seed", ctypes.c_uint64), ("site", ctypes.c_uint64)]
+
+
 SIGNATURES = {
     "cti_version": (c_int, []),
     "cti_last_error": (c_char_p, []),
@@ -64,9 +70,9 @@ SIGNATURES = {
     "cti_tri_pool_bwd_strided": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int,
                                          c_int, c_int, c_int, _P]),
     "cti_rank_proj_dropout_scale": (c_float, [c_float]),
-    "cti_rank_proj_dropout_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_float, ctypes.c_uint64, ctypes.c_uint64, _P]),
-    "cti_rank_proj_dropout_dgrad": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_float, ctypes.c_uint64, ctypes.c_uint64, _P]),
-    "cti_rank_proj_dropout_wgrad": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_float, ctypes.c_uint64, ctypes.c_uint64, _P]),
+    "cti_rank_proj_dropout_fwd": (c_int, [ctypes.POINTER(RankProjProblem), c_int, c_int, c_int, _P]),
+    "cti_rank_proj_dropout_dgrad": (c_int, [ctypes.POINTER(RankProjProblem), c_int, c_int, c_int, _P]),
+    "cti_rank_proj_dropout_wgrad": (c_int, [ctypes.POINTER(RankProjProblem), c_int, c_int, c_int, _P]),
     "cti_rank_proj_dropout_mask": (c_int, [_P, c_int64, c_int, c_int, c_float, ctypes.c_uint64, ctypes.c_uint64, _P]),
     "cti_glimpse_residual_cast": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, _P, c_int, _P, c_int, c_int64, c_int, _P]),
     "cti_glimpse_token_sum": (c_int, [_P, c_int, _P, c_int, _P, c_int, _P, c_int, c_int, _P, _P, c_int64, c_int, _P]),

@@ -298,24 +298,45 @@ int cti_tri_pool_bwd_strided(const void* v, const void* q, const void* a, const 
 
 float cti_rank_proj_dropout_scale(float p) { return cti::rank_proj_scale(p); }
 
-int cti_rank_proj_dropout_fwd(const void* y, const void* w_eff, const float* bias, void* out, int64_t M, int H, int R, float p,
-                              uint64_t seed, uint64_t site, void* stream) {
-  return cti::rank_proj_dropout_fwd(static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(w_eff), bias,
-                                    static_cast<__nv_bfloat16*>(out), (long)M, H, R, p, seed, site,
-                                    static_cast<cudaStream_t>(stream));
+static int rank_proj_convert(const cti_rank_proj_problem* probs, int n, cti::RankProjProblem (&out)[4]) {
+  if (probs == nullptr || n < 1 || n > 4) {
+    cti::set_error("cti_rank_proj_dropout: 1 to 4 problems per call (got %d)", n);
+    return -1;
+  }
+  for (int i = 0; i < n; ++i) {
+    const cti_rank_proj_problem& q = probs[i];
+    cti::RankProjProblem& d = out[i];
+    d.y = static_cast<const __nv_bfloat16*>(q.y);
+    d.w_eff = static_cast<const __nv_bfloat16*>(q.w_eff);
+    d.bias = q.bias;
+    d.out = static_cast<__nv_bfloat16*>(q.out);
+    d.dz = static_cast<const __nv_bfloat16*>(q.dz);
+    d.dzt = static_cast<__nv_bfloat16*>(q.dzt);
+    d.dw_accum = q.dw_accum;
+    d.M = (long)q.M;
+    d.p = q.p;
+    d.seed = q.seed;
+    d.site = q.site;
+  }
+  return 0;
 }
 
-int cti_rank_proj_dropout_dgrad(const void* dz, const void* w_eff, const void* y, void* dzt, int64_t M, int H, int R, float p,
-                                uint64_t seed, uint64_t site, void* stream) {
-  return cti::rank_proj_dropout_dgrad(static_cast<const __nv_bfloat16*>(dz), static_cast<const __nv_bfloat16*>(w_eff),
-                                      static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(dzt), (long)M, H, R, p,
-                                      seed, site, static_cast<cudaStream_t>(stream));
+int cti_rank_proj_dropout_fwd(const cti_rank_proj_problem* probs, int n, int H, int R, void* stream) {
+  cti::RankProjProblem ps[4];
+  if (int rc = rank_proj_convert(probs, n, ps)) return rc;
+  return cti::rank_proj_dropout_fwd(ps, n, H, R, static_cast<cudaStream_t>(stream));
 }
 
-int cti_rank_proj_dropout_wgrad(const void* dz, const void* y, float* dw_accum, int64_t M, int H, int R, float p, uint64_t seed,
-                                uint64_t site, void* stream) {
-  return cti::rank_proj_dropout_wgrad(static_cast<const __nv_bfloat16*>(dz), static_cast<const __nv_bfloat16*>(y), dw_accum,
-                                      (long)M, H, R, p, seed, site, static_cast<cudaStream_t>(stream));
+int cti_rank_proj_dropout_dgrad(const cti_rank_proj_problem* probs, int n, int H, int R, void* stream) {
+  cti::RankProjProblem ps[4];
+  if (int rc = rank_proj_convert(probs, n, ps)) return rc;
+  return cti::rank_proj_dropout_dgrad(ps, n, H, R, static_cast<cudaStream_t>(stream));
+}
+
+int cti_rank_proj_dropout_wgrad(const cti_rank_proj_problem* probs, int n, int H, int R, void* stream) {
+  cti::RankProjProblem ps[4];
+  if (int rc = rank_proj_convert(probs, n, ps)) return rc;
+  return cti::rank_proj_dropout_wgrad(ps, n, H, R, static_cast<cudaStream_t>(stream));
 }
 
 int cti_rank_proj_dropout_mask(uint8_t* keep, int64_t M, int H, int R, float p, uint64_t seed, uint64_t site, void* stream) {

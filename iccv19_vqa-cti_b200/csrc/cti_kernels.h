@@ -68,13 +68,22 @@ int glimpse_token_sum(const void* xq, int q_bf16, const float* const* pq, int Tq
 int glimpse_bcast_rows(const float* x, float* oq, int Tq, float* oa, int Ta, long B, int D, cudaStream_t s);
 
 // rank_proj.cu  (the R per-rank projections of a modality with per-rank input dropout, masks applied in registers)
+struct RankProjProblem {
+  const __nv_bfloat16* y = nullptr;        // (M, H) input of the per-rank nets (post-ReLU tucker output)
+  const __nv_bfloat16* w_eff = nullptr;    // (R*16, H) weight-norm fold             (fwd, dgrad)
+  const float* bias = nullptr;             // (R*16)                                 (fwd)
+  __nv_bfloat16* out = nullptr;            // (M, R*16)                              (fwd)
+  const __nv_bfloat16* dz = nullptr;       // (M, R*16) pre-activation gradient      (dgrad, wgrad)
+  __nv_bfloat16* dzt = nullptr;            // (M, H)                                 (dgrad)
+  float* dw_accum = nullptr;               // (R*16, H)                              (wgrad)
+  long M = 0;
+  float p = 0.f;
+  uint64_t seed = 0, site = 0;
+};
 float rank_proj_scale(float p);
-int rank_proj_dropout_fwd(const __nv_bfloat16* y, const __nv_bfloat16* W, const float* bias, __nv_bfloat16* out, long M, int H,
-                          int R, float p, uint64_t seed, uint64_t site, cudaStream_t s);
-int rank_proj_dropout_dgrad(const __nv_bfloat16* dz, const __nv_bfloat16* W, const __nv_bfloat16* y, __nv_bfloat16* dzt, long M,
-                            int H, int R, float p, uint64_t seed, uint64_t site, cudaStream_t s);
-int rank_proj_dropout_wgrad(const __nv_bfloat16* dz, const __nv_bfloat16* y, float* dW_accum, long M, int H, int R, float p,
-                            uint64_t seed, uint64_t site, cudaStream_t s);
+int rank_proj_dropout_fwd(const RankProjProblem* probs, int n, int H, int R, cudaStream_t s);
+int rank_proj_dropout_dgrad(const RankProjProblem* probs, int n, int H, int R, cudaStream_t s);
+int rank_proj_dropout_wgrad(const RankProjProblem* probs, int n, int H, int R, cudaStream_t s);
 int rank_proj_dropout_mask(uint8_t* keep, long M, int H, int R, float p, uint64_t seed, uint64_t site, cudaStream_t s);
 
 // optim.cu  (multi-tensor trainer tail; pointer / chunk tables live in device memory)

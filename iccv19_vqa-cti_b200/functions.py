@@ -220,7 +220,7 @@ def rank_proj_fwd(y: torch.Tensor, pk: Packed, bias: torch.Tensor, drop, R: int)
     N = pk.w.shape[0]
     d = N // R
     if d == 16 and K_.rank_proj_fused_ok(H, R):       # masks applied to the A fragments in registers (rank_proj.cu)
-        return K_.rank_proj_dropout_fwd(y, pk.w, bias.detach().contiguous(), R, drop)
+        return K_.rank_proj_dropout_fwd([y], [pk.w], [bias.detach().contiguous()], R, [drop])[0]
     rg = RANK_GROUP if R % RANK_GROUP == 0 else 1
     out = torch.empty((M, N), dtype=BF16, device=y.device)
     b = bias.detach()
@@ -233,21 +233,36 @@ def rank_proj_fwd(y: torch.Tensor, pk: Packed, bias: torch.Tensor, drop, R: int)
     return out
 
 
+def rank_proj_fused(ys, pks, drops, R: int) -> bool:
+    """All modalities of the call go through the fused kernels (rank_proj.cu) in one batched launch per pass."""
+    return (all(dr is not None for dr in drops) and all(pk.w.shape[0] == R * 16 for pk in pks)
+            and all(K_.rank_proj_fused_ok(y.shape[1], R) for y in ys))
+
+
+def rank_proj_bwd_fused(ys, dzs, Vs, gs, pks, drops, R: int):
+    """Backward of the fused per-rank projections for a list of modalities: one wgrad and one dgrad call for all of them.
+    -> [(dV, dg, dzt)]: dzt is the bf16 pre-activation gradient of the layer that produced y (y's ReLU mask applied)."""
+    dws = [pk.dw if pk.dw is not None else torch.zeros((R * 16, y.shape[1]), dtype=F32, device=y.device)
+           for pk, y in zip(pks, ys)]
+    K_.rank_proj_dropout_wgrad(dzs, ys, dws, R, drops)
+    dzts = K_.rank_proj_dropout_dgrad(dzs, [pk.w for pk in pks], ys, R, drops)
+    out = []
+    for V, g, pk, dw, dzt in zip(Vs, gs, pks, dws, dzts):
+        if pk.dw is not None:                        # deferred weight-norm backward (see Packed)
+            out.append((dw, None, dzt))
+        else:
+            dV, dg = K_.wn_grad(dw, V.detach().contiguous(), g.detach().reshape(R).contiguous(), pk.sumsq, R)
+            out.append((dV, dg.reshape(g.shape), dzt))
+    return out
+
+
 def rank_proj_bwd(y: torch.Tensor, dz: torch.Tensor, V: torch.Tensor, g: torch.Tensor, pk: Packed, drop, R: int):
     """Backward of rank_proj_fwd.  Returns dV, dg and the fp32 gradient w.r.t. y (before y's own ReLU mask)."""
     M, H = y.shape
     N = pk.w.shape[0]
     d = N // R
     if d == 16 and K_.rank_proj_fused_ok(H, R):
-        # fused: the masks are regenerated in registers; dgrad already carries y's ReLU mask (bf16), wgrad accumulates
-        deferred = pk.dw is not None
-        dw = pk.dw if deferred else torch.zeros((N, H), dtype=F32, device=y.device)
-        K_.rank_proj_dropout_wgrad(dz, y, dw, R, drop)
-        dzt = K_.rank_proj_dropout_dgrad(dz, pk.w, y, R, drop)
-        if deferred:
-            return dw, None, dzt
-        dV, dg = K_.wn_grad(dw, V.detach().contiguous(), g.detach().reshape(R).contiguous(), pk.sumsq, R)
-        return dV, dg.reshape(g.shape), dzt
+        return rank_proj_bwd_fused([y], [dz], [V], [g], [pk], [drop], R)[0]
     rg = RANK_GROUP if R % RANK_GROUP == 0 else 1
     wt = _block_diag_weights(pk.w, R, rg)
     dw = torch.empty((N, H), dtype=F32, device=y.device)
@@ -387,10 +402,16 @@ class TriLogitsFn(Function):
             # shared mask: the dropped copy doubles as the ReLU-and-dropout mask of the dgrad epilogue
             yd = K_.dropout_bf16(y, drop)
             return yd, lin_fwd(yd, pki, bias, True)[0]
-        with K_.gemm_batch():
-            yv, vc = rank_nets(yv, pk[3], w[11], dvn)
-            yq, qc = rank_nets(yq, pk[4], w[14], dqn)
-            ya, ac = rank_nets(ya, pk[5], w[17], dan)
+        ctx.rank_fused = independent and rank_proj_fused((yv, yq, ya), pk[3:6], (dvn, dqn, dan), R)
+        if ctx.rank_fused:                    # per-rank masks applied in registers; the three modalities share the launches
+            vc, qc, ac = K_.rank_proj_dropout_fwd([yv, yq, ya], [pk[3].w, pk[4].w, pk[5].w],
+                                                  [w[11].detach().contiguous(), w[14].detach().contiguous(),
+                                                   w[17].detach().contiguous()], R, [dvn, dqn, dan])
+        else:
+            with K_.gemm_batch():
+                yv, vc = rank_nets(yv, pk[3], w[11], dvn)
+                yq, qc = rank_nets(yq, pk[4], w[14], dqn)
+                ya, ac = rank_nets(ya, pk[5], w[17], dan)
         tpack = pack_core(T_g)
         # training: the kernel also leaves its bf16 N1 intermediate in HBM, the backward picks it up instead of recomputing it
         n1 = None
@@ -448,10 +469,15 @@ class TriLogitsFn(Function):
                 return K_.act_bwd_bias(acc, y, True, db_), db_
             return dzt, _colsum(dzt, H, db_)
         # the GEMMs of the three modalities are independent: the question- and answer-side ones pair up (gemm_batch)
-        with K_.gemm_batch():
-            dVvn, dgvn, dzvt, accv = rank_nets_bwd(yv, dzv, w[9], w[10], pk[3], dvn, zs[0])
-            dVqn, dgqn, dzqt, accq = rank_nets_bwd(yq, dzq, w[12], w[13], pk[4], dqn, zs[1])
-            dVan, dgan, dzat, acca = rank_nets_bwd(ya, dza, w[15], w[16], pk[5], dan, zs[2])
+        if ctx.rank_fused:
+            (dVvn, dgvn, dzvt), (dVqn, dgqn, dzqt), (dVan, dgan, dzat) = rank_proj_bwd_fused(
+                [yv, yq, ya], [dzv, dzq, dza], [w[9], w[12], w[15]], [w[10], w[13], w[16]], pk[3:6], [dvn, dqn, dan], R)
+            accv = accq = acca = None
+        else:
+            with K_.gemm_batch():
+                dVvn, dgvn, dzvt, accv = rank_nets_bwd(yv, dzv, w[9], w[10], pk[3], dvn, zs[0])
+                dVqn, dgqn, dzqt, accq = rank_nets_bwd(yq, dzq, w[12], w[13], pk[4], dqn, zs[1])
+                dVan, dgan, dzat, acca = rank_nets_bwd(ya, dza, w[15], w[16], pk[5], dan, zs[2])
         dzvt, dbvt = finish(yv, dzvt, accv, zs[3])
         dzqt, dbqt = finish(yq, dzqt, accq, zs[4])
         dzat, dbat = finish(ya, dzat, acca, zs[5])

@@ -571,7 +571,7 @@ def glimpse_bcast_rows(x: torch.Tensor, Tq: int, Ta: int):
 # --------------------------------------------------------------------------- #
 def rank_proj_fused_ok(H: int, R: int) -> bool:
     """Shapes the fused kernels are built for (the reference's: h_mm = 512, rank = 32)."""
-    return H == 512 and R % 16 == 0 and 16 <= R <= 64
+    return H == 512 and R in (16, 32)
 
 
 def rank_proj_scale(p: float) -> float:
@@ -579,39 +579,56 @@ def rank_proj_scale(p: float) -> float:
     return float(_lib.load().cti_rank_proj_dropout_scale(float(p)))
 
 
-def rank_proj_dropout_fwd(y: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, R: int, drop) -> torch.Tensor:
-    _req(y, BF16, "rank_proj_dropout_fwd.y")
-    _req(w, BF16, "rank_proj_dropout_fwd.w")
-    _req(bias, F32, "rank_proj_dropout_fwd.bias")
-    M, H = y.shape
-    out = torch.empty((M, R * 16), dtype=BF16, device=y.device)
-    _call("cti_rank_proj_dropout", _lib.load().cti_rank_proj_dropout_fwd,
-          (y.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr(), M, H, R, drop[0], drop[1], drop[2], _stream()),
-          flops=2.0 * M * H * R * 16, tag="fwd")
-    return out
+def _rank_proj_call(fn_name: str, tag: str, probs, R: int) -> None:
+    """probs: list of dicts with the cti_rank_proj_problem fields as tensors (+ 'drop')."""
+    arr = (_lib.RankProjProblem * len(probs))()
+    flops = 0.0
+    H = probs[0]["y"].shape[1]
+    for q, d in zip(arr, probs):
+        for k in ("y", "w_eff", "bias", "out", "dz", "dzt", "dw_accum"):
+            setattr(q, k, _ptr(d.get(k)))
+        q.M = d["y"].shape[0]
+        q.p, q.seed, q.site = d["drop"]
+        flops += 2.0 * q.M * H * R * 16
+    lib = _lib.load()
+    kinds = len({d["drop"][0] == 0.5 for d in probs})          # one launch per mask kind
+    _call("cti_rank_proj_dropout", getattr(lib, fn_name), (arr, len(probs), H, R, _stream()), kernels=kinds, flops=flops,
+          tag=tag + " rows " + "+".join(str(d["y"].shape[0]) for d in probs))
 
 
-def rank_proj_dropout_dgrad(dz: torch.Tensor, w: torch.Tensor, y: torch.Tensor, R: int, drop) -> torch.Tensor:
-    """-> pre-activation gradient of the layer that produced y (bf16, y's ReLU mask applied)."""
-    _req(dz, BF16, "rank_proj_dropout_dgrad.dz")
-    _req(y, BF16, "rank_proj_dropout_dgrad.y")
-    M, H = y.shape
-    dzt = torch.empty((M, H), dtype=BF16, device=y.device)
-    _call("cti_rank_proj_dropout", _lib.load().cti_rank_proj_dropout_dgrad,
-          (dz.data_ptr(), w.data_ptr(), y.data_ptr(), dzt.data_ptr(), M, H, R, drop[0], drop[1], drop[2], _stream()),
-          flops=2.0 * M * H * R * 16, tag="dgrad")
-    return dzt
+def rank_proj_dropout_fwd(ys, ws, biases, R: int, drops):
+    """Batched over modalities: lists of y (M_i, H) bf16, w_eff, bias, drop -> list of out (M_i, R*16) bf16."""
+    probs = []
+    for y, w, b, drop in zip(ys, ws, biases, drops):
+        _req(y, BF16, "rank_proj_dropout_fwd.y")
+        _req(w, BF16, "rank_proj_dropout_fwd.w")
+        _req(b, F32, "rank_proj_dropout_fwd.bias")
+        probs.append({"y": y, "w_eff": w, "bias": b, "out": torch.empty((y.shape[0], R * 16), dtype=BF16, device=y.device),
+                      "drop": drop})
+    _rank_proj_call("cti_rank_proj_dropout_fwd", "fwd", probs, R)
+    return [d["out"] for d in probs]
 
 
-def rank_proj_dropout_wgrad(dz: torch.Tensor, y: torch.Tensor, dw: torch.Tensor, R: int, drop) -> None:
-    """dw (R*16, H) fp32 += masked wgrad."""
-    _req(dz, BF16, "rank_proj_dropout_wgrad.dz")
-    _req(y, BF16, "rank_proj_dropout_wgrad.y")
-    _req(dw, F32, "rank_proj_dropout_wgrad.dw")
-    M, H = y.shape
-    _call("cti_rank_proj_dropout", _lib.load().cti_rank_proj_dropout_wgrad,
-          (dz.data_ptr(), y.data_ptr(), dw.data_ptr(), M, H, R, drop[0], drop[1], drop[2], _stream()),
-          flops=2.0 * M * H * R * 16, tag="wgrad")
+def rank_proj_dropout_dgrad(dzs, ws, ys, R: int, drops):
+    """-> list of pre-activation gradients of the layers that produced the y (bf16, y's ReLU mask applied)."""
+    probs = []
+    for dz, w, y, drop in zip(dzs, ws, ys, drops):
+        _req(dz, BF16, "rank_proj_dropout_dgrad.dz")
+        _req(y, BF16, "rank_proj_dropout_dgrad.y")
+        probs.append({"y": y, "w_eff": w, "dz": dz, "dzt": torch.empty(y.shape, dtype=BF16, device=y.device), "drop": drop})
+    _rank_proj_call("cti_rank_proj_dropout_dgrad", "dgrad", probs, R)
+    return [d["dzt"] for d in probs]
+
+
+def rank_proj_dropout_wgrad(dzs, ys, dws, R: int, drops) -> None:
+    """dws[i] (R*16, H) fp32 += masked wgrad of problem i."""
+    probs = []
+    for dz, y, dw, drop in zip(dzs, ys, dws, drops):
+        _req(dz, BF16, "rank_proj_dropout_wgrad.dz")
+        _req(y, BF16, "rank_proj_dropout_wgrad.y")
+        _req(dw, F32, "rank_proj_dropout_wgrad.dw")
+        probs.append({"y": y, "dz": dz, "dw_accum": dw, "drop": drop})
+    _rank_proj_call("cti_rank_proj_dropout_wgrad", "wgrad", probs, R)
 
 
 def rank_proj_dropout_mask(M: int, H: int, R: int, drop, device) -> torch.Tensor:

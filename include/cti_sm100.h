@@ -236,23 +236,33 @@ int cti_tri_pool_bwd_strided(const void* v, const void* q, const void* a, const 
                              float* dba_accum, float* dw, int64_t dw_stride_b, int B, int K, int Q, int A, int C, int v_rep,
                              void* stream);
 
-/* ---- the R per-rank projections of one modality with PER-RANK input dropout (training mode) ---------------------------
+/* ---- the R per-rank projections of a modality with PER-RANK input dropout (training mode) -----------------------------
  * replaces: `self.v_net[r](v_tucker)` for r < rank (src/tc.py:29-31,47-49), each FCNet = Dropout(p) -> weight_norm(Linear
  * (512, 16)) -> ReLU (src/fc.py:25-29), i.e. R independent Bernoulli masks on the same (M, 512) input.
  *   fwd  : out[m, r*16+j] = relu(s * sum_k keep_r[m,k] y[m,k] W[r*16+j, k] + bias[r*16+j])          (bf16)
  *   dgrad: dzt[m, k]      = (y[m,k] > 0) * s * sum_r keep_r[m,k] * sum_j dz[m, r*16+j] W[r*16+j, k]  (bf16; y's ReLU mask applied)
  *   wgrad: dw_accum[r*16+j, k] += s * sum_m dz[m, r*16+j] keep_r[m,k] y[m,k]                          (fp32, accumulates)
- * y (M, H) bf16, w_eff (R*16, H) bf16 (the weight-norm fold), H == 512, R a multiple of 16.  The masks are never stored:
- * each kernel regenerates them in registers from (seed, site) with Philox4x32-7, 8 bits per decision, so the drop rate is
- * round(256 p) / 256 and s = cti_rank_proj_dropout_scale(p) = 256 / (256 - round(256 p)).  cti_rank_proj_dropout_mask writes
- * keep[r, m, k] (uint8, R*M*H) for tests. */
+ * H == 512, R == 16 or 32.  One call takes 1-4 problems (the modalities of a TCNet); problems with the same mask kind
+ * share a launch, so the question and answer sides fill one wave together.  The masks are never stored: each kernel
+ * regenerates them in registers from (seed, site) with Philox4x32-7 -- one random bit per decision when p == 0.5, else 8 bits
+ * per decision (drop rate round(256 p) / 256; s = cti_rank_proj_dropout_scale(p) = 256 / (256 - round(256 p))).
+ * cti_rank_proj_dropout_mask writes keep[r, m, k] (uint8, R*M*H) for tests.  Each pass reads only the fields it needs. */
+typedef struct cti_rank_proj_problem {
+  const void* y;        /* (M, H) bf16: input of the per-rank nets (the post-ReLU tucker output) */
+  const void* w_eff;    /* (R*16, H) bf16 weight-norm fold                       fwd, dgrad */
+  const float* bias;    /* (R*16)                                               fwd */
+  void* out;            /* (M, R*16) bf16                                       fwd */
+  const void* dz;       /* (M, R*16) bf16 pre-activation gradient               dgrad, wgrad */
+  void* dzt;            /* (M, H) bf16                                          dgrad */
+  float* dw_accum;      /* (R*16, H) fp32                                       wgrad */
+  int64_t M;
+  float p;
+  uint64_t seed, site;
+} cti_rank_proj_problem;
 float cti_rank_proj_dropout_scale(float p);
-int cti_rank_proj_dropout_fwd(const void* y, const void* w_eff, const float* bias, void* out, int64_t M, int H, int R, float p,
-                              uint64_t seed, uint64_t site, void* stream);
-int cti_rank_proj_dropout_dgrad(const void* dz, const void* w_eff, const void* y, void* dzt, int64_t M, int H, int R, float p,
-                                uint64_t seed, uint64_t site, void* stream);
-int cti_rank_proj_dropout_wgrad(const void* dz, const void* y, float* dw_accum, int64_t M, int H, int R, float p, uint64_t seed,
-                                uint64_t site, void* stream);
+int cti_rank_proj_dropout_fwd(const cti_rank_proj_problem* probs, int n, int H, int R, void* stream);
+int cti_rank_proj_dropout_dgrad(const cti_rank_proj_problem* probs, int n, int H, int R, void* stream);
+int cti_rank_proj_dropout_wgrad(const cti_rank_proj_problem* probs, int n, int H, int R, void* stream);
 int cti_rank_proj_dropout_mask(uint8_t* keep, int64_t M, int H, int R, float p, uint64_t seed, uint64_t site, void* stream);
 
 /* ---- caller glue of the glimpse loop (opt-in fused call) ------------------------------------------

@@ -178,6 +178,30 @@ def test_per_rank_nets_draw_independent_masks_and_match_autograd(M, p):
     assert not torch.equal(out, F_.rank_proj_fwd(y, pk, bias, (p, 99, 6), R))
 
 
+def test_rank_projection_batched_over_modalities_equals_single_calls():
+    """One call serves the three modalities (p = .5 image side alone, the two p = .2 sides in one launch): same masks,
+    same outputs as three single calls."""
+    torch.manual_seed(3)
+    H, R = 512, 32
+    Ms, ps = (300, 1000, 70), (0.5, 0.2, 0.2)
+    ys = [torch.relu(torch.randn(M, H, device=DEV)).to(torch.bfloat16) for M in Ms]
+    ws = [(torch.randn(R * 16, H, device=DEV) / H ** 0.5).to(torch.bfloat16) for _ in Ms]
+    bs = [torch.randn(R * 16, device=DEV) * 0.1 for _ in Ms]
+    drops = [(p, 7, 10 + i) for i, p in enumerate(ps)]
+    outs = K_.rank_proj_dropout_fwd(ys, ws, bs, R, drops)
+    dzs = [torch.randn(M, R * 16, device=DEV).to(torch.bfloat16) for M in Ms]
+    dzts = K_.rank_proj_dropout_dgrad(dzs, ws, ys, R, drops)
+    dws = [torch.zeros(R * 16, H, device=DEV) for _ in Ms]
+    K_.rank_proj_dropout_wgrad(dzs, ys, dws, R, drops)
+    for i in range(3):
+        o1 = K_.rank_proj_dropout_fwd([ys[i]], [ws[i]], [bs[i]], R, [drops[i]])[0]
+        d1 = K_.rank_proj_dropout_dgrad([dzs[i]], [ws[i]], [ys[i]], R, [drops[i]])[0]
+        w1 = torch.zeros(R * 16, H, device=DEV)
+        K_.rank_proj_dropout_wgrad([dzs[i]], [ys[i]], [w1], R, [drops[i]])
+        assert torch.equal(outs[i], o1) and torch.equal(dzts[i], d1)
+        assert ((dws[i] - w1).abs().max() / w1.abs().max()).item() < 1e-5          # fp32 red.add: order varies
+
+
 def test_expand_path_still_serves_other_shapes():
     """Widths the fused kernels are not built for (H != 512) go through cti_dropout_expand + block-diagonal GEMMs."""
     torch.manual_seed(0)
