@@ -47,26 +47,53 @@ class BCNet(nn.Module):
             return hv * (self.h_mat_g / hv.norm())                 # 2*3072 elements: parameter plumbing
         return self.h_mat
 
+    def _h_params(self):
+        """(h_mat (G, C), h_bias (G)) of the bilinear map.  h_out <= 32: the parameters themselves (src/bc.py:36-37);
+        h_out > 32: the weight-normed ``h_net`` (src/bc.py:39), whose projection of the outer products
+        ``h_net(v_ (x) q_)`` (:66) is the same bilinear form with h_mat = W_eff and h_bias = bias."""
+        if self.h_out <= self.c:
+            return self._effective_h_mat(), self.h_bias
+        hn = self.h_net
+        return hn.weight_v * (hn.weight_g / hn.weight_v.norm()), hn.bias      # (h_out, C) parameter plumbing
+
     def _logits(self, v, q, rowmask_wanted: bool):
-        if self.h_out is None or self.h_out > self.c:
-            raise NotImplementedError("BCNet.forward: only the h_out <= 32 branch (reference src/bc.py:52-58) is "
-                                      "on the accelerated CTI/BAN path")
         B, K = v.shape[0], v.shape[1]
         if q.shape[0] != B:
             raise RuntimeError(f"batch mismatch: v has {B} samples, q {q.shape[0]}")
         Q = q.shape[1]
-        G, C = self.h_out, self.h_dim * self.k
+        C = self.h_dim * self.k
         v_bf16, rowmask = cast_features(v)
         lv, pv = self.v_net.single()
         lq, pq = self.q_net.single()
+        if self.h_out is None:
+            # reference src/bc.py:42-47: sum_{k,q} v_[b,k,c] q_[b,q,c] -- the bilinear pooling with unit weights
+            drops = None
+            if self.training:
+                sites = [F_.new_drop(p, True) for p in (pv, pq)]
+                if any(d is not None for d in sites):
+                    drops = (features_f32_2d(v) if sites[0] is not None else None, *sites, None)
+            ones = torch.ones((B, K, Q), dtype=torch.float32, device=v.device)
+            out = F_.PoolFn.apply((B, K, Q, 0, C), [lv.packed(), lq.packed()], drops, v_bf16, q, None, ones, lv.v_in(),
+                                  lv.weight_g, lv.bias, lq.v_in(), lq.weight_g, lq.bias)
+            return out.unsqueeze(1)
         drops = None
         if self.training:
             sites = [F_.new_drop(p, True) for p in (pv, pq, self.dropout.p)]
             if any(d is not None for d in sites):
                 drops = (features_f32_2d(v) if sites[0] is not None else None, *sites)
-        return F_.BiLogitsFn.apply((B, K, Q, G, C), [lv.packed(), lq.packed()], drops, v_bf16,
-                                   rowmask if rowmask_wanted else None, q, self._effective_h_mat(), self.h_bias,
-                                   lv.v_in(), lv.weight_g, lv.bias, lq.v_in(), lq.weight_g, lq.bias)
+        hmat, hbias = self._h_params()
+        hmat, hbias = hmat.reshape(self.h_out, C), hbias.reshape(self.h_out)
+        outs = []
+        # one call takes up to 14 maps (tcgen05 path: 4); more maps -- h_out 15..32 and the h_net branch (src/bc.py:63-68),
+        # which no shipped builder reaches -- run in chunks of 4 that share the dropout sites, i.e. the same masks (each
+        # chunk repeats the two projections: correct, not fast)
+        step = self.h_out if self.h_out <= 14 else 4
+        for g0 in range(0, self.h_out, step):
+            G = min(step, self.h_out - g0)
+            outs.append(F_.BiLogitsFn.apply((B, K, Q, G, C), [lv.packed(), lq.packed()], drops, v_bf16,
+                                            rowmask if rowmask_wanted else None, q, hmat[g0:g0 + G], hbias[g0:g0 + G],
+                                            lv.v_in(), lv.weight_g, lv.bias, lq.v_in(), lq.weight_g, lq.bias))
+        return outs[0] if len(outs) == 1 else torch.cat(outs, 1)
 
     def forward(self, v, q):
         """v (B,K,v_dim), q (B,Q,q_dim) -> bilinear logits (B, h_out, K, Q)."""

@@ -379,7 +379,7 @@ class TriLogitsFn(Function):
         if drops is not None:
             v_f32, dv, dq, da, dvn, dqn, dan = drops
             if dv is not None:
-                v_bf16 = drop_features(v_f32, dv)
+                v_bf16 = K_.dropout_bf16(v_bf16, dv)      # the cached bf16 cast is the source: half the bytes of a cast + dropout pass over fp32 v
         # w = (V, g, b) x [v_tucker, q_tucker, a_tucker, v_net, q_net, a_net]
         groups = (1, 1, 1, R, R, R)
         pk: List[Packed] = [packs[i] if packs is not None else pack_layer(w[3 * i], w[3 * i + 1], groups[i])
@@ -574,7 +574,7 @@ class PoolFn(Function):
         if drops is not None:
             v_f32, dv, dq_drop, da_drop = drops
             if dv is not None:
-                v_bf16 = drop_features(v_f32, dv)
+                v_bf16 = K_.dropout_bf16(v_bf16, dv)      # the cached bf16 cast is the source: half the bytes of a cast + dropout pass over fp32 v
         ctx.drops = (dq_drop, da_drop)
         xq = cast_tokens(q, dq_drop)
         xa = ap = None
@@ -641,7 +641,7 @@ class BiLogitsFn(Function):
         if drops is not None:
             v_f32, dv, dq_drop, datt = drops
             if dv is not None:
-                v_bf16 = drop_features(v_f32, dv)
+                v_bf16 = K_.dropout_bf16(v_bf16, dv)      # the cached bf16 cast is the source: half the bytes of a cast + dropout pass over fp32 v
         ctx.drops = (dq_drop, datt)
         xq = cast_tokens(q, dq_drop)
         vb, _ = lin_fwd(v_bf16, pk[0], w[2], True)
