@@ -221,11 +221,15 @@ def run_b200(args):
     a_prj = [cti_b200.FCNet([HID, HID], '', .2) for _ in range(GLIMPSE)]
     mods = torch.nn.ModuleList([att, *pools, *q_prj, *a_prj]).to(dev).eval()
     params = [p for p in mods.parameters()]
-    reducer = GradAllReducer(params) if world > 1 else None
     CAP_MODE = "thread_local" if world > 1 else "global"      # NCCL inside the captured step (graphs.GraphedStep)
-    if reducer is not None:
-        # the deferred weight-norm backward writes dV / dg (97 % of the gradient bytes) straight into the all-reduce slab
-        cti_b200.bind_grad_buffers(mods, reducer)
+    reducer = None
+    if world > 1:
+        # the deferred weight-norm backward writes dV / dg (97 % of the gradient bytes) straight into the all-reduce slab,
+        # group by group in the order backward finishes them: glimpse 1's pooling + projections, glimpse 0's, the attention.
+        # Each group owns one bucket whose all-reduce starts the moment the group is done and overlaps the rest of backward.
+        grad_groups = [[pools[gi], q_prj[gi], a_prj[gi]] for gi in reversed(range(GLIMPSE))] + [[att]]
+        reducer = GradAllReducer(params, param_groups=cti_b200.weight_norm_param_groups(mods, grad_groups))
+        cti_b200.bind_grad_buffers(mods, reducer, groups=None if os.environ.get("CTI_NO_OVERLAP") else grad_groups)
 
     # multiple-choice batch: B rows = B / 4 questions x 4 answer candidates; the loader yields ONE feature tensor per
     # question and the trainer clones it per candidate on the device (reference src/MC/train.py:69-76)
@@ -665,19 +669,15 @@ def run_b200(args):
                 p.grad = None
             joint = _hot_path(att, pools, q_prj, a_prj, vv, qq.detach().requires_grad_(True), aa.detach().requires_grad_(True))
             (joint * cc).sum().backward()
+            if with_reducer and reducer is not None:              # part of the step (and of its graph), as in the main arm
+                reducer.reduce_now() if use_graph else reducer.finish()
+        if with_reducer and reducer is not None:
+            reducer.forget_sources()
         for _ in range(3):
             fb()
         run = fb
         if use_graph:
-            gph = cti_b200.GraphedStep(fb, [mods], [vv], allow_fixed_dropout=fixed_dropout, capture_error_mode=CAP_MODE).replay
-            if with_reducer and reducer is not None:
-                reducer.forget_sources()
-
-                def run():
-                    gph()
-                    reducer.reduce_now()
-            else:
-                run = gph
+            run = cti_b200.GraphedStep(fb, [mods], [vv], allow_fixed_dropout=fixed_dropout, capture_error_mode=CAP_MODE).replay
         for _ in range(3):
             run()
         ms_, _, _ = timed(run, args.steps, all_ranks=with_reducer)
@@ -811,10 +811,13 @@ def run_b200(args):
         step.reduce = False                      # this pass runs on rank 0 only
         if reducer is not None:
             reducer.set_hooks_enabled(False)
+            reducer.set_collectives_enabled(False)
         for _ in range(n_prof):
             resident_step()
         torch.cuda.synchronize()
         step.reduce = True
+        if reducer is not None:
+            reducer.set_collectives_enabled(True)
         rec, KS.STATS.prof = KS.STATS.prof, None
         agg = {}
         for name, tag, flops, nbytes, e0, e1 in rec:

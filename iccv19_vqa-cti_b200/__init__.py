@@ -20,10 +20,10 @@ from .language_model import QuestionEmbedding
 from .loader import FeatureBatch, FeatureStoreBF16, TeacherLogits, prime_features
 from .loss_function import Distillation_Loss
 from .optim import FusedClipAdamax
-from .prepack import bind_grad_buffers, prepack
+from .prepack import bind_grad_buffers, prepack, weight_norm_param_groups
 from .tc import TCNet
 
-__all__ = ["FCNet", "WNLinear", "TCNet", "TriAttention", "BCNet", "BiAttention", "SimpleClassifier", "QuestionEmbedding", "Distillation_Loss", "FusedClipAdamax", "prepack", "bind_grad_buffers", "FeatureStoreBF16", "FeatureBatch", "TeacherLogits", "prime_features", "install", "uninstall", "GraphedStep", "reset_caches", "glimpse_joint",
+__all__ = ["FCNet", "WNLinear", "TCNet", "TriAttention", "BCNet", "BiAttention", "SimpleClassifier", "QuestionEmbedding", "Distillation_Loss", "FusedClipAdamax", "prepack", "bind_grad_buffers", "weight_norm_param_groups", "FeatureStoreBF16", "FeatureBatch", "TeacherLogits", "prime_features", "install", "uninstall", "GraphedStep", "reset_caches", "glimpse_joint",
            "library_path", "version"]
 
 

@@ -35,7 +35,7 @@ def _padded(n: int) -> int:
 
 
 class _Bucket:
-    __slots__ = ("params", "flat", "views", "pending", "work")
+    __slots__ = ("params", "flat", "views", "pending", "work", "launched")
 
     def __init__(self, params: List[torch.nn.Parameter], flat: Optional[torch.Tensor] = None):
         self.params = params
@@ -47,6 +47,7 @@ class _Bucket:
             o += _padded(p.numel())
         self.pending = len(params)
         self.work = None
+        self.launched = False              # its all-reduce of this step is already in flight (launch_bucket)
 
 
 class GradAllReducer:
@@ -61,14 +62,30 @@ class GradAllReducer:
     Buckets are filled in reverse registration order (the order backward produces gradients)."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 25 << 20,
-                 process_group: Optional[dist.ProcessGroup] = None, average: bool = False):
+                 process_group: Optional[dist.ProcessGroup] = None, average: bool = False,
+                 param_groups: Optional[Sequence[Sequence[torch.nn.Parameter]]] = None):
+        """param_groups: optional explicit buckets, in the order backward completes them -- bucket i holds exactly the
+        parameters of param_groups[i] (``launch_bucket(i)`` all-reduces it as soon as its producer is done, while the rest
+        of backward runs); the remaining parameters are bucketed by size behind them."""
         self.group = process_group
         self.average = average
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         ps = [p for p in params if p.requires_grad]
         groups: List[List[torch.nn.Parameter]] = []
+        explicit = set()
+        for grp in (param_groups or ()):
+            grp = [p for p in grp if p.requires_grad]
+            if any(p in explicit for p in grp):
+                raise ValueError("GradAllReducer: a parameter appears in two param_groups")
+            explicit.update(grp)
+            groups.append(grp)
+        self.n_explicit = len(groups)
+        if any(all(p is not q for q in ps) for p in explicit):
+            raise ValueError("GradAllReducer: param_groups must be drawn from params")
         cur, cur_bytes = [], 0
         for p in reversed(ps):
+            if p in explicit:
+                continue
             if cur and (cur_bytes + p.numel() * p.element_size() > bucket_bytes or p.dtype != cur[0].dtype):
                 groups.append(cur)
                 cur, cur_bytes = [], 0
@@ -80,7 +97,8 @@ class GradAllReducer:
         # the hook-free path can then reduce everything with a single collective
         self.slab: Optional[torch.Tensor] = None
         if ps and all(p.dtype == ps[0].dtype and p.device == ps[0].device for p in ps):
-            self.slab = torch.zeros(sum(_padded(p.numel()) for p in ps), dtype=ps[0].dtype, device=ps[0].device)
+            self.slab = torch.zeros(sum(_padded(p.numel()) for grp in groups for p in grp), dtype=ps[0].dtype,
+                                    device=ps[0].device)
         self.buckets: List[_Bucket] = []
         o = 0
         for grp in groups:
@@ -115,6 +133,8 @@ class GradAllReducer:
     def finish(self) -> None:
         """Wait for every bucket; parameters that received no gradient this step count as zeros."""
         for b in self.buckets:
+            if b.launched:                                                # launch_bucket(): already in flight, in place
+                continue
             if b.pending != 0:                                            # some grads never arrived (unused params)
                 for p, v in zip(b.params, b.views):
                     if p.grad is None:
@@ -128,6 +148,19 @@ class GradAllReducer:
             if self.average and self.world > 1:
                 b.flat.div_(self.world)
             b.pending = len(b.params)
+            b.launched = False
+
+    def launch_bucket(self, i: int) -> None:
+        """Start the all-reduce of bucket ``i`` NOW, asynchronously: every gradient of the bucket has just been written
+        into its view by its producer (``prepack.bind_grad_buffers(..., groups=...)`` calls this from the backward node
+        that finishes a group of layers), so the transfer overlaps the rest of backward.  ``reduce_now()`` then handles the
+        other buckets and waits for all of them.  Capturable in a CUDA graph (capture_error_mode="thread_local")."""
+        b = self.buckets[i]
+        if any(p not in self._in_place for p in b.params):
+            raise RuntimeError("launch_bucket: only for buckets whose gradients are all written in place (mark_in_place)")
+        if self.world > 1 and getattr(self, "_collectives", True):
+            b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        b.launched = True
 
     def reduce_now(self) -> None:
         """All-reduce the gradients backward has just produced, without hooks: used after a CUDA-graph replay of
@@ -156,14 +189,29 @@ class GradAllReducer:
                     srcs.append(src)
         if dsts:
             torch._foreach_copy_(dsts, srcs)
-        if self.world > 1:
-            if self.slab is not None:
+        if self.world > 1 and getattr(self, "_collectives", True):
+            early = any(b.launched for b in self.buckets)
+            if self.slab is not None and not early:
                 dist.all_reduce(self.slab, op=dist.ReduceOp.SUM, group=self.group)
             else:
-                works = [dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True) for b in self.buckets]
-                for w in works:
-                    w.wait()
+                # buckets launched during backward (launch_bucket) are in flight; the rest -- consecutive pieces of the
+                # slab -- go out as one more collective, then everything is waited for
+                rest = [b for b in self.buckets if not b.launched]
+                if rest:
+                    if self.slab is not None and all(x.flat.data_ptr() + x.flat.numel() * x.flat.element_size() == y.flat.data_ptr()
+                                                     for x, y in zip(rest, rest[1:])):
+                        o = (rest[0].flat.data_ptr() - self.slab.data_ptr()) // self.slab.element_size()
+                        tail = self.slab[o:o + sum(b.flat.numel() for b in rest)]
+                        rest[0].work = dist.all_reduce(tail, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                    else:
+                        for b in rest:
+                            b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                for b in self.buckets:
+                    if b.work is not None:
+                        b.work.wait()
+                        b.work = None
         for b in self.buckets:
+            b.launched = False
             if self.average and self.world > 1:
                 b.flat.div_(self.world)
             for p, v in zip(b.params, b.views):
@@ -180,6 +228,11 @@ class GradAllReducer:
 
     def set_hooks_enabled(self, enabled: bool) -> None:
         self._enabled = enabled
+
+    def set_collectives_enabled(self, enabled: bool) -> None:
+        """False: ``launch_bucket`` / ``reduce_now`` do their local work but issue no collective (a pass that only one
+        rank runs, e.g. per-kernel profiling, must not wait for the others)."""
+        self._collectives = enabled
 
     def flat_grads(self) -> List[torch.Tensor]:
         return [b.flat for b in self.buckets]

@@ -34,6 +34,7 @@ class WNLinear(nn.Module):
         self.weight_v = nn.Parameter(v)
         self._pack: Optional[Tuple[tuple, F_.Packed]] = None
         self._vproxy = None         # (key, proxy of weight_v) while prepack defers this layer's weight-norm backward
+        self._vlazy = None          # (plan, group) until the layer's gradient group has its node (prepack._Plan.open_group)
 
     def extra_repr(self) -> str:
         return f"in_features={self.in_features}, out_features={self.out_features}, bias=True"
@@ -44,6 +45,10 @@ class WNLinear(nn.Module):
         d = self._vproxy
         if d is not None and torch.is_grad_enabled() and d[0] == (self.weight_v._version, self.weight_g._version,
                                                                    self.weight_v.data_ptr()):
+            lz = self.__dict__.get("_vlazy")
+            if lz is not None:                  # first layer of its gradient group to run: create the group's node now
+                lz[0].open_group(lz[1])
+                d = self._vproxy
             return d[1]
         return self.weight_v
 

@@ -21,15 +21,20 @@ from . import fc as _fc
 
 
 def reset_caches(modules: Iterable[torch.nn.Module], tensors: Iterable[torch.Tensor] = ()) -> None:
+    from .prepack import _PLANS
+    for plan in _PLANS.values():
+        plan.lazy = None                                   # proxies of an earlier step (they keep its autograd graph alive)
     for root in modules:
         for m in root.modules():
             if hasattr(m, "_pack"):
                 m._pack = None
             if hasattr(m, "_vproxy"):
                 m._vproxy = None
+                m._vlazy = None
             if hasattr(m, "_rank_pack"):
                 m._rank_pack = None
                 m.__dict__["_rank_proxy"] = None
+                m.__dict__["_rank_lazy"] = None
     for t in tensors:
         for attr in (_fc._FEAT_ATTR, "_cti_b200_tok"):
             if hasattr(t, attr):

@@ -121,6 +121,10 @@ class _Plan:
             blk_index += list(range(nb))
         i64 = lambda xs: torch.tensor(xs, dtype=torch.int64, device=dev)
         i32 = lambda xs: torch.tensor(xs, dtype=torch.int32, device=dev)
+        self._s_ptrs, self._dw_ptrs = s_ptrs, dw_ptrs
+        self.groups = None                   # set_grad_groups(): the backward of the fold split into groups of layers
+        self.lazy = None                     # (proxies, opened groups) between prepack() and the end of the forward pass
+        self.entry_group = None
         self.tables = (i64([t.data_ptr() for t in ent_v]), i64([t.data_ptr() for t in ent_g]), i64(w_ptrs), i64(s_ptrs),
                        i64(elems), i32(first_seg), i32(n_seg), i32(seg_entry), i32(seg_index), i32(blk_entry), i32(blk_index))
         self.dw_ptrs = i64(dw_ptrs)
@@ -158,6 +162,105 @@ class _Plan:
         self.dv_ptrs_static = i64([t.data_ptr() for t in self.targets[0]])
         self.dg_ptrs_static = i64([t.data_ptr() for t in self.targets[1]])
 
+    def entry_owners(self) -> List[WNLinear]:
+        """The WNLinear behind every entry, in entry order (singles, then the per-rank nets of each TCNet)."""
+        return list(self.singles) + [lin for per_tc in self.group_lins for lins in per_tc for lin in lins]
+
+    def set_grad_groups(self, module_groups, callbacks) -> None:
+        """Split the deferred weight-norm backward into groups of layers (each group = the layers under a list of modules,
+        given in the order backward finishes them): group i gets its own autograd node, which runs the two-launch dV / dg
+        pass for ITS layers as soon as they have all produced dW_eff, writes into the bound gradient targets and then calls
+        ``callbacks[i]()`` -- e.g. the all-reduce of the bucket holding exactly those gradients, which then overlaps the
+        rest of backward.  Needs ``set_grad_targets`` first.  ``module_groups = None`` returns to one node for everything."""
+        if module_groups is None:
+            self.groups = None
+            self.lazy = None
+            return
+        if self.targets is None:
+            raise RuntimeError("prepack: bind gradient targets before splitting the backward into groups")
+        owners = self.entry_owners()
+        taken = [None] * self.n_entries
+        for gi, mods in enumerate(module_groups):
+            inside = {id(m) for root in mods for m in root.modules()}
+            for e, lin in enumerate(owners):
+                if id(lin) in inside:
+                    if taken[e] is not None:
+                        raise RuntimeError("prepack: a layer belongs to two gradient groups")
+                    taken[e] = gi
+        if any(t is None for t in taken):
+            raise RuntimeError("prepack: the gradient groups must cover every weight-normed layer of the plan")
+        dev = self.device
+        i64 = lambda xs: torch.tensor(xs, dtype=torch.int64, device=dev)
+        i32 = lambda xs: torch.tensor(xs, dtype=torch.int32, device=dev)
+        n_single = len(self.singles)
+        self.entry_group = taken
+        self.groups = []
+        for gi in range(len(module_groups)):
+            ents = [e for e in range(self.n_entries) if taken[e] == gi]
+            first_seg, n_seg, seg_entry, seg_index, blk_entry, blk_index = [], [], [], [], [], []
+            for li, e in enumerate(ents):
+                n = self.elems[e]
+                first_seg.append(len(seg_entry))
+                ns = -(-n // _SEG)
+                n_seg.append(ns)
+                seg_entry += [li] * ns
+                seg_index += list(range(ns))
+                nb = -(-n // _BLK)
+                blk_entry += [li] * nb
+                blk_index += list(range(nb))
+            # proxies of the group, as positions in _PackAllFn's output tuple: single layers, then (V stand-in, bias stack)
+            # of every per-rank group whose R entries belong to this gradient group
+            outs, kinds = [], []
+            for i in range(n_single):
+                if taken[i] == gi:
+                    outs.append(i); kinds.append(("single", i))
+            e = n_single
+            for ti, per_tc in enumerate(self.group_lins):
+                for j, lins in enumerate(per_tc):
+                    mine = {taken[e + r] for r in range(len(lins))}
+                    if mine == {gi}:
+                        base = n_single + 6 * ti + 2 * j
+                        outs += [base, base + 1]
+                        kinds += [("rank", ti, j, e, len(lins)), ("bias",)]
+                    elif gi in mine:
+                        raise RuntimeError("prepack: the per-rank nets of one modality must share a gradient group")
+                    e += len(lins)
+            self.groups.append({
+                "entries": ents, "outs": outs, "kinds": kinds, "callback": callbacks[gi],
+                "tables": (i64([self._dw_ptrs[e] for e in ents]), i64([self.ent_v[e].data_ptr() for e in ents]),
+                           i64([self.ent_g[e].data_ptr() for e in ents]), i64([self._s_ptrs[e] for e in ents]),
+                           i64([self.targets[0][e].data_ptr() for e in ents]), i64([self.targets[1][e].data_ptr() for e in ents]),
+                           i64([self.elems[e] for e in ents]), i32(first_seg), i32(n_seg), i32(seg_entry), i32(seg_index),
+                           i32(blk_entry), i32(blk_index)),
+                "n_segs": len(seg_entry), "n_blks": len(blk_entry), "total": sum(self.elems[e] for e in ents),
+                "partials": torch.empty((len(seg_entry),), dtype=torch.float32, device=dev)})
+
+    def open_group(self, gi: int) -> None:
+        """Create group gi's autograd node now -- called when the forward pass first asks for a proxy of the group
+        (``WNLinear.v_in``, ``TCNet`` per-rank proxies).  The autograd engine runs ready nodes in the reverse of their
+        creation order; a node created here, right before the group's first consumer, therefore runs as soon as the
+        group's layers have all handed dW_eff back -- in the MIDDLE of backward, before the nodes of everything that
+        came earlier in the forward pass.  Created inside ``prepack`` (before the whole forward) the nodes would run
+        last, and the all-reduce they launch would overlap nothing."""
+        if self.lazy is None or gi in self.lazy[1]:
+            return
+        proxies, opened = self.lazy
+        opened.add(gi)
+        grp = self.groups[gi]
+        for pos, t in zip(grp["outs"], _GroupGradFn.apply(self, gi, *[proxies[o] for o in grp["outs"]])):
+            proxies[pos] = t
+        self.prime(proxies)
+
+    def grad_group(self, gi: int) -> None:
+        """dV / dg of the layers of group gi (two launches), into the bound gradient targets."""
+        g = self.groups[gi]
+        t = g["tables"]
+        K_._call("cti_wn_grad_multi", _lib.load().cti_wn_grad_multi,
+                 (t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), t[4].data_ptr(), t[5].data_ptr(),
+                  t[6].data_ptr(), t[7].data_ptr(), t[8].data_ptr(), t[9].data_ptr(), t[10].data_ptr(), g["n_segs"],
+                  t[11].data_ptr(), t[12].data_ptr(), g["n_blks"], g["partials"].data_ptr(), K_._stream()),
+                 kernels=2, nbytes=20.0 * g["total"])
+
     def still_valid(self) -> bool:                       # parameters re-allocated (.to(), load with assign) -> rebuild
         return tuple(t.data_ptr() for t in self.ent_v) == self.ptr_key
 
@@ -190,10 +293,15 @@ class _Plan:
         """Point the layers' caches at the fresh packs (and, when ``proxies`` is given, at the proxies that defer their
         weight-norm backward)."""
         n_single = len(self.singles)
+        pending = None                                     # gradient groups whose node does not exist yet (open_group)
+        if proxies is not None and self.groups is not None and self.lazy is not None:
+            pending = set(range(len(self.groups))) - self.lazy[1]
+        e_rank = n_single
         for i, (lin, pk) in enumerate(zip(self.singles, self.single_packs)):
             key = (lin.weight_v._version, lin.weight_g._version, lin.weight_v.data_ptr())
             lin._pack = (key, pk)
             lin._vproxy = None if proxies is None else (key, proxies[i])
+            lin._vlazy = None if pending is None or self.entry_group[i] not in pending else (self, self.entry_group[i])
         for ti, (tc, packs) in enumerate(zip(self.tcnets, self.rank_packs)):
             rank_params = tc.__dict__.get("_rank_params")
             if rank_params is None:
@@ -201,6 +309,9 @@ class _Plan:
                 tc.__dict__["_rank_params"] = rank_params
             key = tuple(p._version for p in rank_params) + (rank_params[0].data_ptr(),)
             tc._rank_pack = (key, list(packs), None)       # the stacked fp32 copies are rebuilt on demand (tc.py)
+            gi = self.entry_group[e_rank] if self.groups is not None else None
+            e_rank += sum(len(lins) for lins in self.group_lins[ti])
+            tc.__dict__["_rank_lazy"] = None if pending is None or gi not in pending else (self, gi)
             if proxies is None:
                 tc.__dict__["_rank_proxy"] = None
             else:
@@ -233,6 +344,7 @@ class _PackAllFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         plan = ctx.plan
+        plan.lazy = None                     # the step's graph is done: do not keep its nodes alive through the proxies
         dev = plan.device
         n_single = len(plan.singles)
         used = [False] * plan.n_entries
@@ -260,7 +372,9 @@ class _PackAllFn(torch.autograd.Function):
                 e += R
                 gi += 2
         out = [None]
-        if plan.targets is not None:
+        if plan.groups is not None:
+            out += [None, None] * plan.n_entries       # dV / dg were produced by the groups' own nodes (_GroupGradFn)
+        elif plan.targets is not None:
             # gradients go straight into the bound targets (all-reduce bucket views); p.grad is assigned here, autograd
             # gets None for these parameters (an AccumulateGrad node would copy, or add a buffer to itself)
             plan.grad(None, None)
@@ -287,6 +401,54 @@ class _PackAllFn(torch.autograd.Function):
         return tuple(out)
 
 
+class _GroupGradFn(torch.autograd.Function):
+    """Identity on the proxies of ONE group of layers (``_Plan.set_grad_groups``).  Its backward runs once all layers of
+    the group have handed their dW_eff back -- in the middle of the backward pass, when the group is the last glimpse or
+    the pooling of an earlier one -- finishes dV / dg for the group (two launches), assigns them as the parameters'
+    gradients (they live in the all-reduce bucket) and fires the group's callback."""
+
+    @staticmethod
+    def forward(ctx, plan, gi, *proxies):
+        ctx.plan, ctx.gi = plan, gi
+        return tuple(p.detach() for p in proxies)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        plan, grp = ctx.plan, plan_group(ctx)
+        used = set()
+        out = [None, None]
+        for kind, g_ in zip(grp["kinds"], grads):
+            if kind[0] == "bias":                   # stacked bias gradient of the per-rank nets: on to _PackAllFn.backward
+                out.append(g_)
+                continue
+            out.append(None)
+            if g_ is None:
+                continue
+            if kind[0] == "single":
+                i = kind[1]
+                pk = plan.single_packs[i]
+                if g_.data_ptr() != pk.dw.data_ptr():
+                    pk.dw[:plan.singles[i].weight_v.shape[0]].copy_(g_)
+                used.add(i)
+            else:
+                _, ti, j, e0, R = kind
+                pk = plan.rank_packs[ti][j]
+                if g_.data_ptr() != pk.dw.data_ptr():
+                    pk.dw.copy_(g_)
+                used.update(range(e0, e0 + R))
+        plan.grad_group(ctx.gi)
+        for e in grp["entries"]:
+            if e in used:
+                plan.ent_v[e].grad, plan.ent_g[e].grad = plan.targets[0][e], plan.targets[1][e]
+        if grp["callback"] is not None:
+            grp["callback"]()
+        return tuple(out)
+
+
+def plan_group(ctx):
+    return ctx.plan.groups[ctx.gi]
+
+
 def prepack(modules) -> None:
     """Rebuild the bf16 weight packs of every weight-normed layer under ``modules`` (a module or an iterable of
     modules) in two launches and prime the layers' caches.  The packs live in persistent buffers: call it between the
@@ -302,24 +464,66 @@ def prepack(modules) -> None:
     if plan is None or not plan.still_valid():
         plan = _PLANS[key] = _Plan(roots)
     if torch.is_grad_enabled() and any(t.requires_grad for t in plan.fn_inputs):
-        plan.prime(_PackAllFn.apply(plan, *plan.fn_inputs))
+        proxies = list(_PackAllFn.apply(plan, *plan.fn_inputs))
+        # with gradient groups, each group's node (_GroupGradFn) is created lazily, when the forward pass first touches
+        # one of the group's layers (open_group): see there
+        plan.lazy = None if plan.groups is None else (proxies, set())
+        plan.prime(proxies)
     else:
         plan.pack()
+        plan.lazy = None
         plan.prime(None)
 
 
-def bind_grad_buffers(modules, reducer) -> None:
+def weight_norm_param_groups(modules, groups) -> List[List[torch.nn.Parameter]]:
+    """For ``dp.GradAllReducer(params, param_groups=...)``: per group of modules (``groups``: lists of modules under
+    ``modules``, in the order backward finishes them) the weight_v / weight_g parameters of its weight-normed layers -- the
+    gradients ``bind_grad_buffers(modules, reducer, groups=groups)`` produces group by group."""
+    roots = [modules] if isinstance(modules, nn.Module) else list(modules)
+    key = tuple(id(m) for m in roots)
+    plan = _PLANS.get(key)
+    if plan is None or not plan.still_valid():
+        plan = _PLANS[key] = _Plan(roots)
+    owners = plan.entry_owners()
+    out = []
+    for mods in groups:
+        inside = {id(m) for root in mods for m in root.modules()}
+        ents = [e for e, lin in enumerate(owners) if id(lin) in inside]
+        out.append([plan.ent_v[e] for e in ents] + [plan.ent_g[e] for e in ents])
+    return out
+
+
+def bind_grad_buffers(modules, reducer, groups=None) -> None:
     """Let the deferred weight-norm backward write dV / dg of every layer under ``modules`` directly into the bucket views
     of ``reducer`` (a ``dp.GradAllReducer``): the gradient all-reduce then needs no copy of these tensors (97 % of the
-    hot path's gradient bytes).  ``reducer = None`` unbinds."""
+    hot path's gradient bytes).  ``reducer = None`` unbinds.
+
+    groups: lists of modules in the order backward finishes them (for the MC model: the last glimpse's pooling and
+    projections, ..., the first glimpse's, the attention).  The reducer must have been built with
+    ``param_groups=weight_norm_param_groups(modules, groups)``: bucket i then holds exactly group i's gradients, the
+    weight-norm backward runs per group, and each group's all-reduce starts the moment the group is finished
+    (``reducer.launch_bucket(i)``), overlapping the rest of backward."""
     roots = [modules] if isinstance(modules, nn.Module) else list(modules)
     key = tuple(id(m) for m in roots)
     plan = _PLANS.get(key)
     if plan is None or not plan.still_valid():
         plan = _PLANS[key] = _Plan(roots)
     if reducer is None:
+        plan.set_grad_groups(None, None)
         plan.set_grad_targets(None)
         return
     targets = {p: v for b in reducer.buckets for p, v in zip(b.params, b.views)}
     plan.set_grad_targets(targets)
     reducer.mark_in_place(plan.ent_v + plan.ent_g)
+    if groups is None:
+        plan.set_grad_groups(None, None)
+        return
+    want = weight_norm_param_groups(roots, groups)
+    callbacks = []
+    for gi, ps in enumerate(want):
+        b = reducer.buckets[gi] if gi < len(reducer.buckets) else None
+        if b is None or len(b.params) != len(ps) or any(x is not y for x, y in zip(b.params, ps)):
+            raise RuntimeError("bind_grad_buffers: build the reducer with param_groups=weight_norm_param_groups(modules, "
+                               "groups) so that bucket i holds exactly the gradients of group i")
+        callbacks.append((lambda i: (lambda: reducer.launch_bucket(i)))(gi))
+    plan.set_grad_groups(groups, callbacks)

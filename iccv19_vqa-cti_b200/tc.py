@@ -107,6 +107,9 @@ class TCNet(nn.Module):
             self.__dict__["_rank_params"] = rank_params
         key = tuple(p._version for p in rank_params) + (rank_params[0].data_ptr(),)
         cache = self._rank_pack                      # (key, [Packed] * 3, detached stacks or None)
+        lz = self.__dict__.get("_rank_lazy")
+        if lz is not None and torch.is_grad_enabled():
+            lz[0].open_group(lz[1])                  # gradient group's node, created at its first use (prepack.open_group)
         proxy = self.__dict__.get("_rank_proxy")     # (key, [(V proxy, g stand-in, bias proxy)] * 3): set by prepack
         if (proxy is not None and proxy[0] == key and cache is not None and cache[0] == key
                 and torch.is_grad_enabled()):

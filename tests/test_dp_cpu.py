@@ -104,3 +104,63 @@ def test_unused_parameters_are_reduced_as_zeros():
     red.finish()
     assert extra.grad is not None and torch.all(extra.grad == 0)
     assert all(p.grad is not None for p in model.parameters())
+
+
+def _worker_groups(rank, world, port, out):
+    """Explicit buckets whose gradients are produced IN PLACE and reduced early (launch_bucket), next to ordinary ones:
+    what prepack.bind_grad_buffers(..., groups=...) drives from its per-group backward nodes."""
+    import cti_b200  # noqa: F401
+    from cti_b200.dp import GradAllReducer, shard_rows
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    model = make_model()
+    x, y = full_batch()
+    sl = shard_rows(x.shape[0], rank, world, group=4)
+    ps = list(model.parameters())
+    early = [[ps[4], ps[5]], [ps[2]]]                       # last layer first: the order backward finishes them
+    red = GradAllReducer(ps, param_groups=early)
+    assert [len(b.params) for b in red.buckets[:2]] == [2, 1] and red.buckets[0].params[0] is ps[4]
+    red.mark_in_place(early[0] + early[1])
+    views = {p: v for b in red.buckets for p, v in zip(b.params, b.views)}
+    res = {}
+    for mode in ("hooks", "hook_free"):
+        red.set_hooks_enabled(mode == "hooks")
+        for step in range(2):
+            for p in ps:
+                p.grad = None
+            loss = ((model(x[sl]) - y[sl]) ** 2).sum()
+            gs = torch.autograd.grad(loss, ps)
+            # the "producers": in-place groups write their gradient into the bucket view and launch; the rest arrive as
+            # ordinary gradient tensors
+            pos = {id(p): i for i, p in enumerate(ps)}
+            in_place = {id(q) for grp in early for q in grp}
+            for gi, grp in enumerate(early):
+                for p in grp:
+                    views[p].copy_(gs[pos[id(p)]])
+                    p.grad = views[p]
+                red.launch_bucket(gi)
+            for p, g_ in zip(ps, gs):
+                if id(p) not in in_place:
+                    p.grad = g_.clone()
+            if mode == "hooks":
+                # no autograd hooks fired (gradients were assigned by hand): finish() reduces what is still pending
+                red.finish()
+            else:
+                red.reduce_now()
+        res[mode] = [p.grad.clone() for p in ps]
+    if rank == 0:
+        torch.save(res, out)
+    dist.destroy_process_group()
+
+
+def test_in_place_buckets_launched_early_give_the_full_batch_gradient(tmp_path):
+    out = str(tmp_path / "g.pt")
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_worker_groups, args=(2, port, out), nprocs=2, join=True)
+    res = torch.load(out, weights_only=False)
+    model = make_model()
+    x, y = full_batch()
+    ((model(x) - y) ** 2).sum().backward()
+    for mode in ("hooks", "hook_free"):
+        for g, p in zip(res[mode], model.parameters()):
+            assert torch.allclose(g, p.grad, rtol=1e-5, atol=1e-6), mode
