@@ -223,13 +223,19 @@ def run_b200(args):
     params = [p for p in mods.parameters()]
     CAP_MODE = "thread_local" if world > 1 else "global"      # NCCL inside the captured step (graphs.GraphedStep)
     reducer = None
-    if world > 1:
+    if world > 1 or os.environ.get("CTI_FORCE_REDUCER"):   # (diagnostic: the reducer's local work on one GPU)
         # the deferred weight-norm backward writes dV / dg (97 % of the gradient bytes) straight into the all-reduce slab,
         # group by group in the order backward finishes them: glimpse 1's pooling + projections, glimpse 0's, the attention.
         # Each group owns one bucket whose all-reduce starts the moment the group is done and overlaps the rest of backward.
         grad_groups = [[pools[gi], q_prj[gi], a_prj[gi]] for gi in reversed(range(GLIMPSE))] + [[att]]
-        reducer = GradAllReducer(params, param_groups=cti_b200.weight_norm_param_groups(mods, grad_groups))
+        # Transport: copy-engine pushes over NVLink peer memory (dp.PeerRegion) -- overlapped NCCL took SMs from the
+        # persistent kernels (3.03 ms overlapped vs 2.97 ms serial at N = 2); CTI_TRANSPORT=nccl selects NCCL.
+        TRANSPORT = os.environ.get("CTI_TRANSPORT", "peer")
+        reducer = GradAllReducer(params, param_groups=cti_b200.weight_norm_param_groups(mods, grad_groups),
+                                 transport=TRANSPORT)
         cti_b200.bind_grad_buffers(mods, reducer, groups=None if os.environ.get("CTI_NO_OVERLAP") else grad_groups)
+        if os.environ.get("CTI_NO_COLL"):                  # diagnostic: everything but the transfers themselves
+            reducer.set_collectives_enabled(False)
 
     # multiple-choice batch: B rows = B / 4 questions x 4 answer candidates; the loader yields ONE feature tensor per
     # question and the trainer clones it per candidate on the device (reference src/MC/train.py:69-76)
@@ -247,7 +253,11 @@ def run_b200(args):
     cot = torch.randn(B, HID, generator=g).to(dev)
     out_h = torch.empty(B, HID).pin_memory()
 
+    TRACE = bool(os.environ.get("CTI_PEER_TRACE")) and world > 1   # debug: timeline of the overlapped transfers
+
     def step(v, q, a):
+        if TRACE and reducer.peer is not None:
+            reducer.peer.stamp("main: step start")
         cti_b200.prepack(mods)                   # every weight-norm fold of the step in two launches (a training step
         for p in params:                         # would do this right after the optimizer update)
             p.grad = None
@@ -264,6 +274,8 @@ def run_b200(args):
                 ae = a_prj[gi](b_emb.unsqueeze(1)) + ae
             joint = qe.sum(1) + ae.sum(1)
         (joint * cot).sum().backward()
+        if TRACE and reducer.peer is not None:
+            reducer.peer.stamp("main: backward done")
         if reducer is not None and step.reduce:
             # eager: the hooks launched the bucketed all-reduces during backward; captured: the hook-free reduce is part
             # of the graph (one fused copy of the few gradients that are not written in place + one all-reduce of the slab)
@@ -330,7 +342,18 @@ def run_b200(args):
             if reducer is not None:
                 reducer.set_hooks_enabled(False)
                 step.graphed = True
-            graphed = cti_b200.GraphedStep(resident_step, [mods], [v_d], capture_error_mode=CAP_MODE)
+            if TRACE and reducer.peer is not None:
+                reducer.peer.start_trace()
+                orig_start = reducer.peer.start_trace
+                graphed = None
+
+                def one_trace():                   # labels are rebuilt by every (warm-up / capture) pass of the step
+                    reducer.peer.trace_labels = []
+                    resident_step()
+                    reducer.peer.stamp("main: step end")
+                graphed = cti_b200.GraphedStep(one_trace, [mods], [v_d], capture_error_mode=CAP_MODE)
+            else:
+                graphed = cti_b200.GraphedStep(resident_step, [mods], [v_d], capture_error_mode=CAP_MODE)
             run_resident = graphed.replay
             for _ in range(3):
                 run_resident()
@@ -341,6 +364,10 @@ def run_b200(args):
                 reducer.set_hooks_enabled(True)
             eager_ms["graph_capture_failed"] = repr(exc)[:200]
     ms, w0, w1 = timed(run_resident, args.steps)
+    if TRACE and reducer.peer is not None and use_graph:
+        torch.cuda.synchronize()
+        for lab, t in reducer.peer.read_trace():
+            print(f"[trace rank {rank}] {t / 1e3:9.1f} us  {lab}", file=sys.stderr, flush=True)
     host_ms = timed.host_ms
     launches = launches_per_step * args.steps
     clocks = sampler.stop(w0, w1) if sampler else None

@@ -79,6 +79,19 @@ SIGNATURES = {
     "cti_glimpse_bcast_rows": (c_int, [_P, _P, c_int, _P, c_int, c_int64, c_int, _P]),
     "cti_bilinear_logits_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "cti_bilinear_logits_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "cti_peer_alloc": (c_int, [c_size_t, ctypes.POINTER(_P)]),
+    "cti_peer_free": (c_int, [_P]),
+    "cti_peer_export": (c_int, [_P, _P]),
+    "cti_peer_import": (c_int, [_P, ctypes.POINTER(_P)]),
+    "cti_peer_close": (c_int, [_P]),
+    "cti_peer_barrier": (c_int, [ctypes.POINTER(_P), c_int, c_int, c_int, ctypes.c_double, _P]),
+    "cti_peer_error": (c_int, [_P, ctypes.POINTER(c_int)]),
+    "cti_peer_barrier_memops": (c_int, [ctypes.POINTER(_P), c_int, c_int, c_int, _P]),
+    "cti_peer_flag_ops": (c_int, [_P, ctypes.POINTER(c_int), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(c_int), c_int, _P]),
+    "cti_peer_flag_op": (c_int, [_P, c_int, ctypes.c_uint32, c_int, _P]),
+    "cti_peer_stamp": (c_int, [_P, _P]),
+    "cti_peer_copy": (c_int, [_P, _P, c_size_t, _P]),
+    "cti_sum_staged": (c_int, [_P, _P, c_int, c_int, c_int64, c_int64, _P]),
 }
 
 _lib = None

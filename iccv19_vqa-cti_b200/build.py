@@ -17,7 +17,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcti_sm100.so")
-SOURCES = ["cti_capi.cu", "gemm_tcgen05.cu", "elementwise.cu", "softmax.cu", "trilinear.cu", "trilinear_tc.cu", "trilinear_bwd_tc.cu", "pool.cu", "bilinear.cu", "bilinear_tc.cu", "optim.cu", "gru.cu", "loss.cu", "glimpse.cu", "rank_proj.cu"]
+SOURCES = ["cti_capi.cu", "gemm_tcgen05.cu", "elementwise.cu", "softmax.cu", "trilinear.cu", "trilinear_tc.cu", "trilinear_bwd_tc.cu", "pool.cu", "bilinear.cu", "bilinear_tc.cu", "optim.cu", "gru.cu", "loss.cu", "glimpse.cu", "rank_proj.cu", "peer.cu"]
 HEADERS = ["cti_common.cuh", "cti_kernels.h", "wmma_tiles.cuh", "tc_tiles.cuh", os.path.join("..", "..", "include", "cti_sm100.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]

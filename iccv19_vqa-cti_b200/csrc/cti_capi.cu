@@ -378,4 +378,32 @@ int cti_bilinear_logits_bwd(const void* vb, const void* qb, const float* hmat, c
                            dhmat_accum, dhbias_accum, d, static_cast<cudaStream_t>(stream));
 }
 
+int cti_peer_alloc(size_t bytes, void** ptr) { return cti::peer_alloc(bytes, ptr); }
+int cti_peer_free(void* ptr) { return cti::peer_free(ptr); }
+int cti_peer_export(void* ptr, void* handle64) { return cti::peer_export(ptr, handle64); }
+int cti_peer_import(const void* handle64, void** ptr) { return cti::peer_import(handle64, ptr); }
+int cti_peer_close(void* ptr) { return cti::peer_close(ptr); }
+int cti_peer_barrier(void* const* flag_blocks, int rank, int world, int slot, double timeout_s, void* stream) {
+  return cti::peer_barrier(flag_blocks, rank, world, slot, timeout_s, static_cast<cudaStream_t>(stream));
+}
+int cti_peer_barrier_memops(void* const* flag_blocks, int rank, int world, int slot, void* stream) {
+  return cti::peer_barrier_memops(flag_blocks, rank, world, slot, static_cast<cudaStream_t>(stream));
+}
+int cti_peer_flag_ops(void* flag_block, const int* index, const uint32_t* value, const int* wait, int count, void* stream) {
+  return cti::peer_flag_ops(flag_block, index, value, wait, count, static_cast<cudaStream_t>(stream));
+}
+int cti_peer_flag_op(void* flag_block, int index, uint32_t value, int wait, void* stream) {
+  return cti::peer_flag_op(flag_block, index, value, wait, static_cast<cudaStream_t>(stream));
+}
+int cti_peer_stamp(uint64_t* dst, void* stream) {
+  return cti::peer_stamp(reinterpret_cast<unsigned long long*>(dst), static_cast<cudaStream_t>(stream));
+}
+int cti_peer_error(const void* flag_block, int* out) { return cti::peer_error(flag_block, out); }
+int cti_peer_copy(void* dst, const void* src, size_t bytes, void* stream) {
+  return cti::peer_copy(dst, src, bytes, static_cast<cudaStream_t>(stream));
+}
+int cti_sum_staged(float* dst, const float* staged, int n_staged, int rank, int64_t n, int64_t stride, void* stream) {
+  return cti::sum_staged(dst, staged, n_staged, rank, n, stride, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

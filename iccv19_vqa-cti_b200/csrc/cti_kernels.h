@@ -149,4 +149,19 @@ int bilinear_bwd(const __nv_bfloat16* vb, const __nv_bfloat16* qb, const float* 
                  __nv_bfloat16* dzv, __nv_bfloat16* dzq, float* dbv, float* dbq, float* dhmat, float* dhbias, BiDims d,
                  cudaStream_t s);
 
+// peer.cu
+int peer_alloc(size_t bytes, void** ptr);
+int peer_free(void* ptr);
+int peer_export(void* ptr, void* handle64);
+int peer_import(const void* handle64, void** ptr);
+int peer_close(void* ptr);
+int peer_barrier(void* const* flag_blocks, int rank, int world, int slot, double timeout_s, cudaStream_t s);
+int peer_barrier_memops(void* const* flag_blocks, int rank, int world, int slot, cudaStream_t s);
+int peer_flag_ops(void* flag_block, const int* index, const uint32_t* value, const int* wait, int count, cudaStream_t s);
+int peer_flag_op(void* flag_block, int index, uint32_t value, int wait, cudaStream_t s);
+int peer_error(const void* flag_block, int* out);
+int peer_stamp(unsigned long long* dst, cudaStream_t s);
+int peer_copy(void* dst, const void* src, size_t bytes, cudaStream_t s);
+int sum_staged(float* dst, const float* staged, int n_staged, int rank, long n, long stride, cudaStream_t s);
+
 }  // namespace cti

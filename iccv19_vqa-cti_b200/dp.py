@@ -5,13 +5,21 @@ gradients, bucketed and launched from autograd hooks so it overlaps the rest of 
 This is the collective the reference's ``Trainer._all_reduce_and_rescale`` names but never issues
 (reference src/MC/trainer.py:208-219: it only flattens, divides and clips).  NCCL over NVLink 5 /
 NVSwitch on GPUs; the same code runs on gloo for the CPU tests.
+
+``transport="peer"`` moves the bytes on the copy engines over NVLink peer memory instead (``PeerRegion``,
+csrc/peer.cu): no SM-resident transfer kernel, so the transfer overlaps backward without displacing the path's
+persistent kernels.  NCCL then only carries the rendezvous (the exchange of the IPC handles).
 """
 from __future__ import annotations
 
 from typing import Iterable, List, Optional, Sequence
 
+import ctypes
+
 import torch
 import torch.distributed as dist
+
+from . import _lib
 
 
 def shard_rows(n_rows: int, rank: int, world: int, group: int = 1) -> slice:
@@ -32,6 +40,202 @@ _ALIGN = 4           # every gradient view starts on a 16-byte boundary (kernels
 
 def _padded(n: int) -> int:
     return -(-n // _ALIGN) * _ALIGN
+
+
+class _DeviceSpan:
+    """A raw device allocation presented through __cuda_array_interface__ (torch.as_tensor aliases it)."""
+
+    def __init__(self, ptr: int, n_floats: int):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+_CREDIT = 512            # flag word: "the peer's staging buffer is free" (two-rank exchange of PeerRegion.all_reduce)
+
+
+class _PeerWork:
+    def __init__(self, region: "PeerRegion"):
+        self.region = region
+
+    def wait(self) -> None:
+        self.region.stamp("main: before join")
+        torch.cuda.current_stream().wait_stream(self.region.stream)
+        self.region.stamp("main: joined")
+
+
+class PeerRegion:
+    """This rank's share of the peer-memory gradient sum: one device allocation -- flag block | slab of ``n_floats``
+    gradients | two staging buffers of the same size (+ chunk rounding) -- exported to the other ranks of the node through CUDA IPC, plus their regions
+    mapped here.  ``all_reduce(o, n)`` enqueues the sum of ``slab[o:o+n]`` over the ranks on the region's side stream:
+
+        push my copy of chunk p into rank p's staging (copy engine)  ->  barrier  ->  chunk[me] += staged copies (rank
+        order)  ->  push the reduced chunk into every peer's slab (copy engine)  ->  barrier
+
+    (two ranks: push the whole range, barrier, both ranks add -- see ``all_reduce``).
+
+    The caller orders the side stream after the producers (``stream.wait_stream``) and its consumers after the side
+    stream (``_PeerWork.wait``).  All of it is capturable in a CUDA graph; a replayed barrier needs no host argument
+    (its epoch lives in the flag block).  ``timeout_s``: a barrier whose peer does not arrive gives up and records the
+    peer (``check()`` raises) instead of spinning forever."""
+
+    def __init__(self, n_floats: int, device: torch.device, group: Optional[dist.ProcessGroup] = None,
+                 timeout_s: float = 20.0, barrier: str = "memops"):
+        """barrier: "memops" -- stream memory operations (no resident kernel: a rank waiting for a slower one holds no SM
+        resources; no timeout) or "spin" -- a one-CTA kernel that spins on the flags and gives up after ``timeout_s``."""
+        if device.type != "cuda":
+            raise RuntimeError("PeerRegion: the peer-memory transport needs CUDA devices (use transport='nccl' / gloo)")
+        self.lib = _lib.load()
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > 16:
+            raise RuntimeError("PeerRegion: at most 16 ranks (one node)")
+        if barrier not in ("memops", "spin"):
+            raise ValueError("PeerRegion: barrier must be 'memops' or 'spin'")
+        self.barrier_kind = barrier
+        self._slot = 0
+        self.n = n_floats
+        self.flag_bytes = 4096                                    # CTI_PEER_FLAG_BYTES
+        self.timeout_s = timeout_s
+        with torch.cuda.device(device):
+            ptr = ctypes.c_void_p()
+            self.n_pad = n_floats + 64 * self.world             # one staging buffer (chunk rounding: 4 floats per rank)
+            _lib.check(self.lib.cti_peer_alloc(self.flag_bytes + 4 * (n_floats + 2 * self.n_pad), ctypes.byref(ptr)),
+                       "cti_peer_alloc")
+            handle = ctypes.create_string_buffer(64)
+            _lib.check(self.lib.cti_peer_export(ptr, handle), "cti_peer_export")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, handle.raw, group=group)
+            self.bases: List[int] = []
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    self.bases.append(ptr.value)
+                else:
+                    q = ctypes.c_void_p()
+                    _lib.check(self.lib.cti_peer_import(ctypes.create_string_buffer(h, 64), ctypes.byref(q)), "cti_peer_import")
+                    self.bases.append(q.value)
+            self.stream = torch.cuda.Stream(device)
+            self.copy_streams = [torch.cuda.Stream(device) for _ in range(min(self.world - 1, 4))] if self.world > 2 else []
+        # the two-rank exchange starts with one credit: the peer's staging is free
+        torch.cuda.current_stream().synchronize()
+        if self.barrier_kind == "memops":
+            _lib.check(self.lib.cti_peer_flag_op(ptr.value, _CREDIT, 1, 0, torch.cuda.current_stream(device).cuda_stream),
+                       "cti_peer_flag_op")
+            torch.cuda.synchronize(device)
+        self.trace: Optional[torch.Tensor] = None                 # debug: int64 time stamps (start_trace / stamp)
+        self.trace_labels: List[str] = []
+        self._blocks = (ctypes.c_void_p * self.world)(*self.bases)
+        self._span = _DeviceSpan(ptr.value + self.flag_bytes, n_floats)
+        self.slab = torch.as_tensor(self._span, device=device)
+        dist.barrier(group=group)                                  # every region is mapped everywhere before first use
+
+    def _slab(self, r: int, o: int) -> int:
+        return self.bases[r] + self.flag_bytes + 4 * o
+
+    def _staging(self, r: int, o: int) -> int:
+        return self.bases[r] + self.flag_bytes + 4 * (self.n + o)
+
+    def start_trace(self, slots: int = 128) -> None:
+        """Debug: record %globaltimer at the protocol's phase boundaries (and wherever ``stamp`` is called) of the steps
+        issued -- or captured -- from now on; ``read_trace()`` returns (label, ns since the first stamp)."""
+        self.trace = torch.zeros(slots, dtype=torch.int64, device=self.slab.device)
+        self.trace_labels = []
+
+    def stamp(self, label: str, stream: Optional[torch.cuda.Stream] = None) -> None:
+        if self.trace is None or len(self.trace_labels) >= self.trace.numel():
+            return
+        st = (stream or torch.cuda.current_stream()).cuda_stream
+        _lib.check(self.lib.cti_peer_stamp(self.trace.data_ptr() + 8 * len(self.trace_labels), st), "cti_peer_stamp")
+        self.trace_labels.append(label)
+
+    def read_trace(self):
+        t = self.trace.cpu().tolist()[:len(self.trace_labels)]
+        t0 = min(x for x in t if x) if any(t) else 0
+        return sorted(((lab, x - t0) for lab, x in zip(self.trace_labels, t)), key=lambda z: z[1])
+
+    def barrier(self, slot: int = 0) -> None:
+        if self.barrier_kind == "memops":
+            self._slot = (self._slot + 1) % 8                      # consecutive barriers never share a slot
+            _lib.check(self.lib.cti_peer_barrier_memops(self._blocks, self.rank, self.world, self._slot,
+                                                        self.stream.cuda_stream), "cti_peer_barrier_memops")
+            return
+        _lib.check(self.lib.cti_peer_barrier(self._blocks, self.rank, self.world, slot, self.timeout_s,
+                                             self.stream.cuda_stream), "cti_peer_barrier")
+
+    def _copies(self, copies) -> None:
+        """Enqueue (dst, src, bytes) copies behind the side stream's work and order the side stream after them.  More
+        than one copy (more than two ranks): spread over the copy streams, so several copy engines work at once (the pieces
+        are 1 / world of a bucket -- for the last bucket of a step a latency-bound megabyte each)."""
+        copies = [c for c in copies if c[2] > 0]
+        if len(copies) <= 1 or not self.copy_streams:
+            for d, s_, b in copies:
+                _lib.check(self.lib.cti_peer_copy(d, s_, b, self.stream.cuda_stream), "cti_peer_copy")
+            return
+        start = torch.cuda.Event()
+        start.record(self.stream)
+        used = self.copy_streams[:min(len(copies), len(self.copy_streams))]
+        for cs in used:
+            cs.wait_event(start)
+        for i, (d, s_, b) in enumerate(copies):
+            _lib.check(self.lib.cti_peer_copy(d, s_, b, used[i % len(used)].cuda_stream), "cti_peer_copy")
+        for cs in used:
+            done = torch.cuda.Event()
+            done.record(cs)
+            self.stream.wait_event(done)
+
+    def all_reduce(self, o: int, n: int) -> None:
+        if o % 4 or n % 4 or o < 0 or o + n > self.n:
+            raise ValueError("PeerRegion.all_reduce: the range must be 16-byte aligned and inside the slab")
+        W, me, st, lib = self.world, self.rank, self.stream.cuda_stream, self.lib
+        if W == 1 or n == 0:
+            return
+        tag = f"ar[{o}+{n}]"
+        self.stamp(tag + " start", self.stream)
+        if W == 2 and self.barrier_kind == "memops":
+            # two ranks: the two-phase exchange moves n / 2 + n / 2 floats per direction; pushing the whole range at once
+            # moves the same n, both ranks add the two copies in rank order (bit-identical sums), and one copy phase and
+            # one barrier disappear.  The trailing barrier (the peer may not overwrite my staging before my sum has read it)
+            # becomes a credit: after its sum each rank writes "staging free" into the peer's flag block, and waits for --
+            # then takes -- its own credit before the next push.  The credit was usually written long before it is needed.
+            peer = 1 - me
+            # wait for "the peer's staging is free", take the credit: one batch
+            _lib.check(lib.cti_peer_flag_ops(self.bases[me], (ctypes.c_int * 2)(_CREDIT, _CREDIT), (ctypes.c_uint32 * 2)(1, 0),
+                                             (ctypes.c_int * 2)(1, 0), 2, st), "cti_peer_flag_ops")
+            _lib.check(lib.cti_peer_copy(self._staging(peer, 0), self._slab(me, o), 4 * n, st), "cti_peer_copy")
+            self.stamp(tag + " pushed", self.stream)
+            self.barrier()
+            self.stamp(tag + " barrier1", self.stream)
+            _lib.check(lib.cti_sum_staged(self._slab(me, o), self._staging(me, 0), 1, me, n, self.n_pad, st), "cti_sum_staged")
+            _lib.check(lib.cti_peer_flag_op(self.bases[peer], _CREDIT, 1, 0, st), "cti_peer_flag_op")   # my staging is free
+            self.stamp(tag + " done", self.stream)
+            return
+        c = -(-(-(-n // W)) // 4) * 4                              # chunk floats: ceil(n / W) rounded up to 16 bytes
+
+        def chunk(p):
+            lo = min(p * c, n)
+            return lo, min(lo + c, n) - lo
+        my_lo, my_n = chunk(me)
+        copies = []
+        for k in range(1, W):                                      # my copy of chunk p -> staging slot of rank p
+            p = (me + k) % W
+            lo, m = chunk(p)
+            slot = me if me < p else me - 1
+            copies.append((self._staging(p, slot * c), self._slab(me, o + lo), 4 * m))
+        self._copies(copies)
+        self.stamp(tag + " pushed", self.stream)
+        self.barrier()
+        self.stamp(tag + " barrier1", self.stream)
+        _lib.check(lib.cti_sum_staged(self._slab(me, o + my_lo), self._staging(me, 0), W - 1, me, my_n, c, st), "cti_sum_staged")
+        # the reduced chunk -> every peer's slab
+        self._copies([(self._slab((me + k) % W, o + my_lo), self._slab(me, o + my_lo), 4 * my_n) for k in range(1, W)])
+        self.stamp(tag + " gathered", self.stream)
+        self.barrier()
+        self.stamp(tag + " done", self.stream)
+
+    def check(self) -> None:
+        """Raise if a barrier of this rank ever timed out (call after a synchronize)."""
+        v = ctypes.c_int(0)
+        _lib.check(self.lib.cti_peer_error(self.bases[self.rank], ctypes.byref(v)), "cti_peer_error")
+        if v.value:
+            raise RuntimeError(f"PeerRegion: rank {v.value - 1} did not arrive at a barrier within {self.timeout_s} s")
 
 
 class _Bucket:
@@ -63,8 +267,11 @@ class GradAllReducer:
 
     def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 25 << 20,
                  process_group: Optional[dist.ProcessGroup] = None, average: bool = False,
-                 param_groups: Optional[Sequence[Sequence[torch.nn.Parameter]]] = None):
-        """param_groups: optional explicit buckets, in the order backward completes them -- bucket i holds exactly the
+                 param_groups: Optional[Sequence[Sequence[torch.nn.Parameter]]] = None, transport: str = "nccl"):
+        """transport: "nccl" -- ``dist.all_reduce`` of the process group's backend (NCCL on GPUs, gloo in the CPU tests);
+        "peer" -- copy-engine transfers over NVLink peer memory (``PeerRegion``; one node, CUDA, fp32 gradients).
+
+        param_groups: optional explicit buckets, in the order backward completes them -- bucket i holds exactly the
         parameters of param_groups[i] (``launch_bucket(i)`` all-reduces it as soon as its producer is done, while the rest
         of backward runs); the remaining parameters are bucketed by size behind them."""
         self.group = process_group
@@ -96,9 +303,21 @@ class GradAllReducer:
         # the buckets are consecutive pieces of ONE buffer when every gradient has the same dtype (always, on this path):
         # the hook-free path can then reduce everything with a single collective
         self.slab: Optional[torch.Tensor] = None
+        self.peer: Optional[PeerRegion] = None
+        if transport not in ("nccl", "peer"):
+            raise ValueError("GradAllReducer: transport must be 'nccl' or 'peer'")
         if ps and all(p.dtype == ps[0].dtype and p.device == ps[0].device for p in ps):
-            self.slab = torch.zeros(sum(_padded(p.numel()) for grp in groups for p in grp), dtype=ps[0].dtype,
-                                    device=ps[0].device)
+            n_slab = sum(_padded(p.numel()) for grp in groups for p in grp)
+            if transport == "peer" and self.world > 1:
+                if ps[0].dtype != torch.float32:
+                    raise RuntimeError("GradAllReducer: transport='peer' sums fp32 gradients")
+                self.peer = PeerRegion(n_slab, ps[0].device, process_group,
+                                       barrier=__import__("os").environ.get("CTI_PEER_BARRIER", "memops"))
+                self.slab = self.peer.slab
+            else:
+                self.slab = torch.zeros(n_slab, dtype=ps[0].dtype, device=ps[0].device)
+        elif transport == "peer":
+            raise RuntimeError("GradAllReducer: transport='peer' needs every gradient in one dtype on one device")
         self.buckets: List[_Bucket] = []
         o = 0
         for grp in groups:
@@ -120,7 +339,16 @@ class GradAllReducer:
         for p, v in zip(b.params, b.views):
             p.grad = v
         if self.world > 1:
-            b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            b.work = self._all_reduce_async(b.flat)
+
+    def _all_reduce_async(self, flat: torch.Tensor):
+        """Start the sum of ``flat`` (a piece of the slab) over the ranks; returns a handle with ``wait()``."""
+        if self.peer is not None:
+            self.peer.stamp("main: fork")
+            self.peer.stream.wait_stream(torch.cuda.current_stream())         # after the producers of these gradients
+            self.peer.all_reduce((flat.data_ptr() - self.slab.data_ptr()) // 4, flat.numel())
+            return _PeerWork(self.peer)
+        return dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def _on_grad(self, p: torch.nn.Parameter) -> None:
         if not getattr(self, "_enabled", True):
@@ -159,7 +387,7 @@ class GradAllReducer:
         if any(p not in self._in_place for p in b.params):
             raise RuntimeError("launch_bucket: only for buckets whose gradients are all written in place (mark_in_place)")
         if self.world > 1 and getattr(self, "_collectives", True):
-            b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            b.work = self._all_reduce_async(b.flat)
         b.launched = True
 
     def reduce_now(self) -> None:
@@ -192,20 +420,22 @@ class GradAllReducer:
         if self.world > 1 and getattr(self, "_collectives", True):
             early = any(b.launched for b in self.buckets)
             if self.slab is not None and not early:
-                dist.all_reduce(self.slab, op=dist.ReduceOp.SUM, group=self.group)
+                self._all_reduce_async(self.slab).wait()
             else:
                 # buckets launched during backward (launch_bucket) are in flight; the rest -- consecutive pieces of the
                 # slab -- go out as one more collective, then everything is waited for
                 rest = [b for b in self.buckets if not b.launched]
+                if __import__("os").environ.get("CTI_DIAG_SKIP_TAIL"):
+                    rest = []
                 if rest:
                     if self.slab is not None and all(x.flat.data_ptr() + x.flat.numel() * x.flat.element_size() == y.flat.data_ptr()
                                                      for x, y in zip(rest, rest[1:])):
                         o = (rest[0].flat.data_ptr() - self.slab.data_ptr()) // self.slab.element_size()
                         tail = self.slab[o:o + sum(b.flat.numel() for b in rest)]
-                        rest[0].work = dist.all_reduce(tail, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                        rest[0].work = self._all_reduce_async(tail)
                     else:
                         for b in rest:
-                            b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                            b.work = self._all_reduce_async(b.flat)
                 for b in self.buckets:
                     if b.work is not None:
                         b.work.wait()

@@ -339,6 +339,7 @@ class _PackAllFn(torch.autograd.Function):
                     torch.cat([b.detach() for b in grp], 0, out=bstack)
                     outs += [vp.detach(), bstack.detach()]
         ctx.plan = plan
+        ctx.set_materialize_grads(False)     # a proxy without a gradient arrives as None, not as a zero-filled tensor
         return tuple(outs)
 
     @staticmethod
@@ -410,6 +411,7 @@ class _GroupGradFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, plan, gi, *proxies):
         ctx.plan, ctx.gi = plan, gi
+        ctx.set_materialize_grads(False)
         return tuple(p.detach() for p in proxies)
 
     @staticmethod
@@ -525,5 +527,7 @@ def bind_grad_buffers(modules, reducer, groups=None) -> None:
         if b is None or len(b.params) != len(ps) or any(x is not y for x, y in zip(b.params, ps)):
             raise RuntimeError("bind_grad_buffers: build the reducer with param_groups=weight_norm_param_groups(modules, "
                                "groups) so that bucket i holds exactly the gradients of group i")
-        callbacks.append((lambda i: (lambda: reducer.launch_bucket(i)))(gi))
+        # the last group finishes with backward itself: nothing left to overlap, so its bucket travels with the remaining
+        # gradients in reduce_now()'s single transfer instead of paying for one of its own
+        callbacks.append(None if gi == len(want) - 1 else (lambda i: (lambda: reducer.launch_bucket(i)))(gi))
     plan.set_grad_groups(groups, callbacks)

@@ -293,6 +293,41 @@ int cti_bilinear_logits_bwd(const void* vb, const void* qb, const float* hmat, c
                             void* dzq, float* dbv_accum, float* dbq_accum, float* dhmat_accum, float* dhbias_accum,
                             int B, int K, int Q, int G, int C, void* stream);
 
+/* ---- gradient sum over NVLink peer memory (data-parallel training) -----------------------------------
+ * The one collective of the path: the sum of the parameter gradients over the ranks of one node, which the reference's
+ * Trainer._all_reduce_and_rescale names but never issues (src/MC/trainer.py:208-219).  Bytes move on the copy engines
+ * (peer writes over NVLink / NVSwitch), not in an SM-resident transfer kernel, so the transfer overlaps backward without
+ * displacing its persistent kernels; see csrc/peer.cu for the protocol and dp.PeerAllReducer for the host side.
+ * Every rank allocates ONE region with cti_peer_alloc (zero-filled: flag block first, CTI_PEER_FLAG_BYTES), exports it
+ * (64-byte CUDA IPC handle, exchanged by the host) and imports its peers' regions.
+ * cti_peer_barrier: one-CTA kernel on `stream`; flag_blocks = HOST array of `world` device pointers (entry `rank` = the
+ *   local region).  Orders everything enqueued before it on every rank's stream before everything after it on this rank's.
+ *   A peer that does not arrive within timeout_s is recorded (cti_peer_error returns 1 + its rank), the kernel leaves.
+ * cti_peer_barrier_memops: the same barrier as stream memory operations (cuStreamWriteValue32 / cuStreamWaitValue32): no
+ *   resident kernel, so a rank waiting for a slower one holds no SM resources (a spinning CTA keeps one SM from taking a
+ *   CTA of the path's one-CTA-per-SM kernels).  Consecutive barriers must use different slots (0..7); no timeout.
+ * cti_peer_flag_op: one stream memory operation on word `index` (< 1024; words 512.. are free for the host protocol) of a
+ *   flag block, local or a peer's: wait = 0 writes `value`, wait = 1 waits until the word is >= `value`.
+ * cti_peer_flag_ops: up to 16 such operations on one flag block as ONE batch (one graph node), executed in order.
+ * cti_peer_copy: cudaMemcpyAsync between local and peer-mapped memory (copy engine).
+ * cti_sum_staged: dst[i] = sum over ranks, in rank order, of the local copy (dst, at position `rank`) and n_staged staged
+ *   copies (staged + s * stride floats); n % 4 == 0, 16-byte aligned. */
+#define CTI_PEER_FLAG_BYTES 4096
+int cti_peer_alloc(size_t bytes, void** ptr);
+int cti_peer_free(void* ptr);
+int cti_peer_export(void* ptr, void* handle64);
+int cti_peer_import(const void* handle64, void** ptr);
+int cti_peer_close(void* ptr);
+int cti_peer_barrier(void* const* flag_blocks, int rank, int world, int slot, double timeout_s, void* stream);
+int cti_peer_barrier_memops(void* const* flag_blocks, int rank, int world, int slot, void* stream);
+int cti_peer_flag_ops(void* flag_block, const int* index, const uint32_t* value, const int* wait, int count, void* stream);
+int cti_peer_flag_op(void* flag_block, int index, uint32_t value, int wait, void* stream);
+int cti_peer_error(const void* flag_block, int* out);
+/* debug: *dst = %globaltimer (ns) when the stream reaches this point (timeline of the overlapped transfers) */
+int cti_peer_stamp(uint64_t* dst, void* stream);
+int cti_peer_copy(void* dst, const void* src, size_t bytes, void* stream);
+int cti_sum_staged(float* dst, const float* staged, int n_staged, int rank, int64_t n, int64_t stride, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
