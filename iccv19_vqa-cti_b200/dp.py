@@ -151,10 +151,14 @@ class PeerRegion:
         t0 = min(x for x in t if x) if any(t) else 0
         return sorted(((lab, x - t0) for lab, x in zip(self.trace_labels, t)), key=lambda z: z[1])
 
-    def barrier(self, slot: int = 0) -> None:
+    def barrier(self, slot: int = 0, second: bool = False) -> None:
+        """Memory-operation barriers reset their flags by the waiter, so two consecutive barriers -- in ANY order graphs
+        are replayed in -- must not share a slot: the first barrier of an exchange takes an even slot, the second
+        (``second=True``) the odd one next to it.  (The two-rank exchange has one barrier; its credit orders the re-use.)"""
         if self.barrier_kind == "memops":
-            self._slot = (self._slot + 1) % 8                      # consecutive barriers never share a slot
-            _lib.check(self.lib.cti_peer_barrier_memops(self._blocks, self.rank, self.world, self._slot,
+            if not second:
+                self._slot = (self._slot + 2) % 8
+            _lib.check(self.lib.cti_peer_barrier_memops(self._blocks, self.rank, self.world, self._slot + int(second),
                                                         self.stream.cuda_stream), "cti_peer_barrier_memops")
             return
         _lib.check(self.lib.cti_peer_barrier(self._blocks, self.rank, self.world, slot, self.timeout_s,
@@ -227,7 +231,7 @@ class PeerRegion:
         # the reduced chunk -> every peer's slab
         self._copies([(self._slab((me + k) % W, o + my_lo), self._slab(me, o + my_lo), 4 * my_n) for k in range(1, W)])
         self.stamp(tag + " gathered", self.stream)
-        self.barrier()
+        self.barrier(second=True)
         self.stamp(tag + " done", self.stream)
 
     def check(self) -> None:
