@@ -1,5 +1,4 @@
-N=${1:-2}
-B="timeout 250 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 --resident-only --hot-only --no-cpu-baseline --no-profile"
-$B > gpurun_out/d_peer_n$N.json 2> gpurun_out/d_peer_n$N.err
-grep -o '"ms_per_step": [0-9.]*' gpurun_out/d_peer_n$N.json | head -1
-tail -c 600 gpurun_out/d_peer_n$N.err
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r02_tests_final.log 2>&1; tail -3 gpurun_out/r02_tests_final.log
+timeout 900 python bench.py > gpurun_out/r02_bench_final.json 2> gpurun_out/r02_bench_final.err; echo bench rc=$?
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02_bench_reference.json 2> gpurun_out/r02_bench_reference.err; echo ref rc=$?
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke.log 2>&1; tail -2 gpurun_out/r02_smoke.log
