@@ -231,9 +231,19 @@ def run_b200(args):
         # Transport: copy-engine pushes over NVLink peer memory (dp.PeerRegion) -- overlapped NCCL took SMs from the
         # persistent kernels (3.03 ms overlapped vs 2.97 ms serial at N = 2); CTI_TRANSPORT=nccl selects NCCL.
         TRANSPORT = os.environ.get("CTI_TRANSPORT", "peer")
-        reducer = GradAllReducer(params, param_groups=cti_b200.weight_norm_param_groups(mods, grad_groups),
-                                 transport=TRANSPORT)
-        cti_b200.bind_grad_buffers(mods, reducer, groups=None if os.environ.get("CTI_NO_OVERLAP") else grad_groups)
+        try:
+            reducer = GradAllReducer(params, param_groups=cti_b200.weight_norm_param_groups(mods, grad_groups),
+                                     transport=TRANSPORT)
+        except RuntimeError as exc:          # no peer access on this box (raised on EVERY rank, dp.PeerRegion): NCCL
+            if TRANSPORT != "peer" or world == 1:
+                raise
+            print(f"[bench] peer-memory transport unavailable ({exc}); using NCCL", file=sys.stderr, flush=True)
+            TRANSPORT = "nccl"
+            reducer = GradAllReducer(params, param_groups=cti_b200.weight_norm_param_groups(mods, grad_groups),
+                                     transport=TRANSPORT)
+        cti_b200.bind_grad_buffers(mods, reducer, groups=None if (os.environ.get("CTI_NO_OVERLAP") or
+                                                    (TRANSPORT == "nccl" and not os.environ.get("CTI_NCCL_OVERLAP")))
+                                   else grad_groups)        # (overlapped NCCL measured slower than NCCL after backward)
         if os.environ.get("CTI_NO_COLL"):                  # diagnostic: everything but the transfers themselves
             reducer.set_collectives_enabled(False)
 
@@ -937,7 +947,10 @@ def run_b200(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "host_issue_ms_per_step": host_ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": dict(workload_config(B, world), launch="cuda_graph_replay" if use_graph else "eager"),
+                "config": dict(workload_config(B, world), launch="cuda_graph_replay" if use_graph else "eager",
+                               **({"gradient_exchange": ("copy engines over NVLink peer memory, overlapped with backward per "
+                                                         "gradient group (dp.PeerRegion)" if reducer.peer is not None else
+                                                         "NCCL all-reduce after backward")} if reducer is not None and world > 1 else {})),
                 "eager": eager_ms, "e2e": e2e, "gpu_launches": launches, "gpu_launches_per_step": launches_per_step, "clocks": clocks,
                 "fwd_only": fwd, "shared_v": shared, "fused_glimpse_loop": fused_leg, "trainer_tail": tail, "gru": gru, "full_model": full, **extra,
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels}

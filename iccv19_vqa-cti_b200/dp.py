@@ -95,31 +95,49 @@ class PeerRegion:
         self.n = n_floats
         self.flag_bytes = 4096                                    # CTI_PEER_FLAG_BYTES
         self.timeout_s = timeout_s
+        # Set-up is all-or-nothing ACROSS ranks: a rank whose allocation / export / import fails still takes part in the
+        # exchanges below, and every rank raises if any did (the caller can then fall back to transport="nccl" everywhere).
+        err = None
+        ptr = ctypes.c_void_p()
+        raw = None
+        self.n_pad = n_floats + 64 * self.world                 # one staging buffer (chunk rounding: 4 floats per rank)
         with torch.cuda.device(device):
-            ptr = ctypes.c_void_p()
-            self.n_pad = n_floats + 64 * self.world             # one staging buffer (chunk rounding: 4 floats per rank)
-            _lib.check(self.lib.cti_peer_alloc(self.flag_bytes + 4 * (n_floats + 2 * self.n_pad), ctypes.byref(ptr)),
-                       "cti_peer_alloc")
-            handle = ctypes.create_string_buffer(64)
-            _lib.check(self.lib.cti_peer_export(ptr, handle), "cti_peer_export")
+            try:
+                _lib.check(self.lib.cti_peer_alloc(self.flag_bytes + 4 * (n_floats + 2 * self.n_pad), ctypes.byref(ptr)),
+                           "cti_peer_alloc")
+                handle = ctypes.create_string_buffer(64)
+                _lib.check(self.lib.cti_peer_export(ptr, handle), "cti_peer_export")
+                raw = handle.raw
+            except RuntimeError as exc:
+                err = exc
             handles = [None] * self.world
-            dist.all_gather_object(handles, handle.raw, group=group)
+            dist.all_gather_object(handles, raw, group=group)
             self.bases: List[int] = []
-            for r, h in enumerate(handles):
-                if r == self.rank:
-                    self.bases.append(ptr.value)
-                else:
-                    q = ctypes.c_void_p()
-                    _lib.check(self.lib.cti_peer_import(ctypes.create_string_buffer(h, 64), ctypes.byref(q)), "cti_peer_import")
-                    self.bases.append(q.value)
+            try:
+                for r, h in enumerate(handles):
+                    if h is None:
+                        raise RuntimeError(f"PeerRegion: rank {r} could not export its region")
+                    if r == self.rank:
+                        self.bases.append(ptr.value)
+                    else:
+                        q = ctypes.c_void_p()
+                        _lib.check(self.lib.cti_peer_import(ctypes.create_string_buffer(h, 64), ctypes.byref(q)),
+                                   "cti_peer_import")
+                        self.bases.append(q.value)
+                # the two-rank exchange starts with one credit: the peer's staging is free
+                if self.barrier_kind == "memops":
+                    _lib.check(self.lib.cti_peer_flag_op(ptr.value, _CREDIT, 1, 0,
+                                                         torch.cuda.current_stream(device).cuda_stream), "cti_peer_flag_op")
+                torch.cuda.synchronize(device)
+            except RuntimeError as exc:
+                err = err or exc
+            oks = [None] * self.world
+            dist.all_gather_object(oks, err is None, group=group)
+            if not all(oks):
+                raise RuntimeError(f"PeerRegion: peer-memory set-up failed on rank(s) {[r for r, ok in enumerate(oks) if not ok]}"
+                                   + (f" (here: {err})" if err is not None else ""))
             self.stream = torch.cuda.Stream(device)
             self.copy_streams = [torch.cuda.Stream(device) for _ in range(min(self.world - 1, 4))] if self.world > 2 else []
-        # the two-rank exchange starts with one credit: the peer's staging is free
-        torch.cuda.current_stream().synchronize()
-        if self.barrier_kind == "memops":
-            _lib.check(self.lib.cti_peer_flag_op(ptr.value, _CREDIT, 1, 0, torch.cuda.current_stream(device).cuda_stream),
-                       "cti_peer_flag_op")
-            torch.cuda.synchronize(device)
         self.trace: Optional[torch.Tensor] = None                 # debug: int64 time stamps (start_trace / stamp)
         self.trace_labels: List[str] = []
         self._blocks = (ctypes.c_void_p * self.world)(*self.bases)

@@ -1,4 +1,2 @@
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r02_tests_final.log 2>&1; tail -3 gpurun_out/r02_tests_final.log
-timeout 900 python bench.py > gpurun_out/r02_bench_final.json 2> gpurun_out/r02_bench_final.err; echo bench rc=$?
-timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02_bench_reference.json 2> gpurun_out/r02_bench_reference.err; echo ref rc=$?
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke.log 2>&1; tail -2 gpurun_out/r02_smoke.log
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_ncu_launches_final.csv python bench.py --steps 1 --warmup 3 --resident-only --hot-only --no-cpu-baseline --no-profile --no-graph > gpurun_out/ncu_final.log 2>&1
+wc -l gpurun_out/r02_ncu_launches_final.csv
