@@ -90,6 +90,8 @@ SIGNATURES = {
     "cti_peer_flag_ops": (c_int, [_P, ctypes.POINTER(c_int), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(c_int), c_int, _P]),
     "cti_peer_flag_op": (c_int, [_P, c_int, ctypes.c_uint32, c_int, _P]),
     "cti_peer_stamp": (c_int, [_P, _P]),
+    "cti_peer_allreduce_fused": (c_int, [ctypes.POINTER(_P), ctypes.POINTER(_P), ctypes.POINTER(_P), c_int, c_int, c_int64,
+                                         ctypes.c_double, _P]),
     "cti_peer_copy": (c_int, [_P, _P, c_size_t, _P]),
     "cti_sum_staged": (c_int, [_P, _P, c_int, c_int, c_int64, c_int64, _P]),
 }

@@ -399,6 +399,11 @@ int cti_peer_stamp(uint64_t* dst, void* stream) {
   return cti::peer_stamp(reinterpret_cast<unsigned long long*>(dst), static_cast<cudaStream_t>(stream));
 }
 int cti_peer_error(const void* flag_block, int* out) { return cti::peer_error(flag_block, out); }
+int cti_peer_allreduce_fused(void* const* flag_blocks, void* const* slab_ranges, void* const* stagings, int rank,
+                             int world, int64_t n, double timeout_s, void* stream) {
+  return cti::peer_allreduce_fused(flag_blocks, slab_ranges, stagings, rank, world, n, timeout_s,
+                                   static_cast<cudaStream_t>(stream));
+}
 int cti_peer_copy(void* dst, const void* src, size_t bytes, void* stream) {
   return cti::peer_copy(dst, src, bytes, static_cast<cudaStream_t>(stream));
 }

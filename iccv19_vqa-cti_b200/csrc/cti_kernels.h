@@ -161,6 +161,8 @@ int peer_flag_ops(void* flag_block, const int* index, const uint32_t* value, con
 int peer_flag_op(void* flag_block, int index, uint32_t value, int wait, cudaStream_t s);
 int peer_error(const void* flag_block, int* out);
 int peer_stamp(unsigned long long* dst, cudaStream_t s);
+int peer_allreduce_fused(void* const* flag_blocks, void* const* slab_ranges, void* const* stagings, int rank, int world,
+                         long n, double timeout_s, cudaStream_t s);
 int peer_copy(void* dst, const void* src, size_t bytes, cudaStream_t s);
 int sum_staged(float* dst, const float* staged, int n_staged, int rank, long n, long stride, cudaStream_t s);
 

@@ -98,6 +98,96 @@ sum_staged_kernel(float4* __restrict__ dst, const float4* __restrict__ staged, i
 
 __global__ void stamp_kernel(unsigned long long* dst) { *dst = global_ns(); }
 
+// ---- the whole exchange of one range as ONE kernel (the last bucket of a step: nothing is left to overlap with, so the
+// SMs are free and what counts is latency -- a copy-engine node costs ~25 us inside a graph, a flag round trip ~3 us here).
+//   phase 1: my copy of chunk p -> rank p's staging, 16-byte stores over NVLink          | all 148 CTAs
+//   flag 1 : the last CTA to finish releases "arrived" into every peer's flag block; every CTA acquires the peers' flags
+//   phase 2: chunk[me] = sum of the copies in rank order -> my slab AND every peer's slab (the all-gather is the store)
+//   flag 2 : as flag 1: nobody leaves before its slab is complete, nobody's staging is overwritten while it is being read
+// Epochs live in the flag block (bumped by the last CTA to leave), so a replayed graph needs no host argument.  Every CTA
+// spins, so all of them must be resident: the grid is one CTA per SM and the kernel is issued where nothing else runs.
+constexpr int kFusedOff = 640;                  // uint32 index: [0,16) arrive1, [16,32) arrive2, 32..34 counters, 35 epoch
+struct FusedArgs {
+  uint32_t* blk[kMaxPeers];
+  float* slab[kMaxPeers];                        // start of the range in every rank's slab
+  float* stage[kMaxPeers];                       // every rank's staging buffer for this kernel
+  int rank, world;
+  long n4, c4;                                   // range / chunk length in float4
+  unsigned long long timeout_ns;
+};
+
+__device__ __forceinline__ void fused_flag_round(const FusedArgs& a, uint32_t* mine, int cnt, int arrive, uint32_t ep) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned old = atomicAdd(mine + kFusedOff + cnt, 1u);
+    if (old == gridDim.x - 1) {                  // every CTA of this rank has issued its stores
+      mine[kFusedOff + cnt] = 0u;
+      __threadfence_system();
+      for (int k = 1; k < a.world; ++k) {
+        uint32_t* theirs = a.blk[(a.rank + k) % a.world] + kFusedOff + arrive + a.rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(ep) : "memory");
+      }
+    }
+  }
+  if (threadIdx.x < a.world && static_cast<int>(threadIdx.x) != a.rank) {
+    const uint32_t* flag = mine + kFusedOff + arrive + threadIdx.x;
+    const unsigned long long t0 = global_ns();
+    for (;;) {
+      uint32_t v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+      if (static_cast<int32_t>(v - ep) >= 0) break;
+      if (global_ns() - t0 > a.timeout_ns) {
+        atomicExch(mine + kErrorOff, 1u + threadIdx.x);
+        break;
+      }
+      __nanosleep(32);
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(512) fused_allreduce_kernel(const FusedArgs a) {
+  uint32_t* mine = a.blk[a.rank];
+  const uint32_t ep = *reinterpret_cast<volatile uint32_t*>(mine + kFusedOff + 35) + 1u;
+  const int W = a.world, me = a.rank;
+  const long tid = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  const long nthr = static_cast<long>(gridDim.x) * blockDim.x;
+  for (int k = 1; k < W; ++k) {
+    const int p = (me + k) % W;
+    const long lo = min(p * a.c4, a.n4), m = min(lo + a.c4, a.n4) - lo;
+    const float4* src = reinterpret_cast<const float4*>(a.slab[me]) + lo;
+    float4* dst = reinterpret_cast<float4*>(a.stage[p]) + (me < p ? me : me - 1) * a.c4;
+    for (long i = tid; i < m; i += nthr) dst[i] = src[i];
+  }
+  fused_flag_round(a, mine, 32, 0, ep);
+  {
+    const long lo = min(me * a.c4, a.n4), m = min(lo + a.c4, a.n4) - lo;
+    const float4* staged = reinterpret_cast<const float4*>(a.stage[me]);
+    for (long i = tid; i < m; i += nthr) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int pos = 0; pos < W; ++pos) {
+        const float4 x = pos == me ? reinterpret_cast<const float4*>(a.slab[me])[lo + i]
+                                   : __ldcg(staged + (pos < me ? pos : pos - 1) * a.c4 + i);
+        if (pos == 0) {
+          acc = x;
+        } else {
+          acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+        }
+      }
+      for (int k = 0; k < W; ++k) reinterpret_cast<float4*>(a.slab[(me + k) % W])[lo + i] = acc;
+    }
+  }
+  fused_flag_round(a, mine, 33, 16, ep);
+  if (threadIdx.x == 0) {
+    const unsigned old = atomicAdd(mine + kFusedOff + 34, 1u);
+    if (old == gridDim.x - 1) {                  // the last CTA to leave: the next launch runs in the next epoch
+      mine[kFusedOff + 34] = 0u;
+      mine[kFusedOff + 35] = ep;
+    }
+  }
+}
+
 }  // namespace
 
 int peer_stamp(unsigned long long* dst, cudaStream_t s) {
@@ -285,6 +375,34 @@ int peer_error(const void* flag_block, int* out) {
   }
   *out = static_cast<int>(v);
   return 0;
+}
+
+int peer_allreduce_fused(void* const* flag_blocks, void* const* slab_ranges, void* const* stagings, int rank, int world,
+                         long n, double timeout_s, cudaStream_t s) {
+  CTI_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world && n >= 0 && (n & 3) == 0,
+              "peer_allreduce_fused: bad arguments (rank %d of %d, n=%ld)", rank, world, n);
+  if (world == 1 || n == 0) return 0;
+  FusedArgs a;
+  for (int i = 0; i < kMaxPeers; ++i) {
+    a.blk[i] = i < world ? static_cast<uint32_t*>(flag_blocks[i]) : nullptr;
+    a.slab[i] = i < world ? static_cast<float*>(slab_ranges[i]) : nullptr;
+    a.stage[i] = i < world ? static_cast<float*>(stagings[i]) : nullptr;
+    CTI_REQUIRE(i >= world || (((uintptr_t)a.slab[i] | (uintptr_t)a.stage[i]) & 15) == 0,
+                "peer_allreduce_fused: buffers must be 16-byte aligned");
+  }
+  a.rank = rank;
+  a.world = world;
+  a.n4 = n / 4;
+  a.c4 = (a.n4 + world - 1) / world;
+  a.timeout_ns = static_cast<unsigned long long>(timeout_s * 1e9);
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  fused_allreduce_kernel<<<sms, 512, 0, s>>>(a);
+  return check_launch("fused_allreduce_kernel");
 }
 
 int peer_copy(void* dst, const void* src, size_t bytes, cudaStream_t s) {

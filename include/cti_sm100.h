@@ -309,6 +309,11 @@ int cti_bilinear_logits_bwd(const void* vb, const void* qb, const float* hmat, c
  * cti_peer_flag_op: one stream memory operation on word `index` (< 1024; words 512.. are free for the host protocol) of a
  *   flag block, local or a peer's: wait = 0 writes `value`, wait = 1 waits until the word is >= `value`.
  * cti_peer_flag_ops: up to 16 such operations on one flag block as ONE batch (one graph node), executed in order.
+ * cti_peer_allreduce_fused: the whole exchange of one range as ONE kernel (one CTA per SM; 16-byte stores over NVLink into
+ *   the peers' staging, flag round, owner-side sum in rank order stored into every rank's slab, flag round): for the last
+ *   bucket of a step, where nothing is left to overlap with and latency is what counts.  slab_ranges[r] = start of the
+ *   range in rank r's slab, stagings[r] = rank r's staging buffer for this call (>= n + 4 * world floats, not shared with
+ *   the copy-engine exchanges); n % 4 == 0.  Issue it where no other kernel competes for the SMs: every CTA spins.
  * cti_peer_copy: cudaMemcpyAsync between local and peer-mapped memory (copy engine).
  * cti_sum_staged: dst[i] = sum over ranks, in rank order, of the local copy (dst, at position `rank`) and n_staged staged
  *   copies (staged + s * stride floats); n % 4 == 0, 16-byte aligned. */
@@ -325,6 +330,8 @@ int cti_peer_flag_op(void* flag_block, int index, uint32_t value, int wait, void
 int cti_peer_error(const void* flag_block, int* out);
 /* debug: *dst = %globaltimer (ns) when the stream reaches this point (timeline of the overlapped transfers) */
 int cti_peer_stamp(uint64_t* dst, void* stream);
+int cti_peer_allreduce_fused(void* const* flag_blocks, void* const* slab_ranges, void* const* stagings, int rank,
+                             int world, int64_t n, double timeout_s, void* stream);
 int cti_peer_copy(void* dst, const void* src, size_t bytes, void* stream);
 int cti_sum_staged(float* dst, const float* staged, int n_staged, int rank, int64_t n, int64_t stride, void* stream);
 

@@ -41,6 +41,18 @@ def _worker(rank, world, port, out):
         torch.cuda.synchronize()
         reg.check()
         res[("raw", step)] = reg.slab.cpu().clone()
+    # ---- the one-kernel exchange (stores over NVLink, flag rounds inside the kernel), eager and mixed with the copy-engine one
+    for step, (o, m) in enumerate([(0, n), (8, 4), (1200, 2000), (0, n)]):
+        reg.slab.copy_(_data(rank, n, 40 + step))
+        if step == 3:                                     # a copy-engine exchange of another range in flight next to it
+            reg.stream.wait_stream(torch.cuda.current_stream())
+            reg.all_reduce(0, 1000)
+            o, m = 1000, n - 1000
+        reg.all_reduce_fused(o, m)
+        torch.cuda.current_stream().wait_stream(reg.stream)
+        torch.cuda.synchronize()
+        reg.check()
+        res[("fused", step)] = reg.slab.cpu().clone()
     # ---- replayed from a graph: the barrier epochs live on the device
     src = torch.zeros(n, device=dev)
     graph = torch.cuda.CUDAGraph()
@@ -50,7 +62,8 @@ def _worker(rank, world, port, out):
         with torch.cuda.graph(graph, capture_error_mode="thread_local"):
             reg.slab.copy_(src)
             reg.stream.wait_stream(torch.cuda.current_stream())
-            reg.all_reduce(0, n)
+            reg.all_reduce(0, 2000)
+            reg.all_reduce_fused(2000, n - 2000)
             torch.cuda.current_stream().wait_stream(reg.stream)
     torch.cuda.synchronize()
     dist.barrier()
@@ -105,6 +118,12 @@ def test_peer_memory_sum_is_exact_on_every_rank(tmp_path, world):
             want = d[r].clone()
             want[o:o + m] = _total(n, step, world)[o:o + m]
             assert torch.equal(got[r][("raw", step)], want), (step, r)
+    for step, (o, m) in enumerate([(0, n), (8, 4), (1200, 2000), (0, n)]):
+        d = [_data(r, n, 40 + step) for r in range(world)]
+        for r in range(world):
+            want = d[r].clone()
+            want[o:o + m] = _total(n, 40 + step, world)[o:o + m]
+            assert torch.equal(got[r][("fused", step)], want), ("fused", step, r)
     for step in range(10, 13):
         want = _total(n, step, world)
         for r in range(world):
