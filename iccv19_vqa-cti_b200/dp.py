@@ -15,6 +15,7 @@ from __future__ import annotations
 from typing import Iterable, List, Optional, Sequence
 
 import ctypes
+import os
 
 import torch
 import torch.distributed as dist
@@ -276,6 +277,19 @@ class PeerRegion:
                                                      st.cuda_stream), "cti_peer_allreduce_fused")
         self.stamp(f"fused[{o}+{n}] done", st)
 
+    def close(self) -> None:
+        """Unmap the peers' regions and free this rank's (after a synchronize on every rank: nothing may still be in
+        flight).  The slab tensor must not be used afterwards."""
+        if not self.bases:
+            return
+        torch.cuda.synchronize(self.slab.device)
+        with torch.cuda.device(self.slab.device):
+            for r, b in enumerate(self.bases):
+                if r != self.rank:
+                    _lib.check(self.lib.cti_peer_close(b), "cti_peer_close")
+            _lib.check(self.lib.cti_peer_free(self.bases[self.rank]), "cti_peer_free")
+        self.bases = []
+
     def check(self) -> None:
         """Raise if a barrier of this rank ever timed out (call after a synchronize)."""
         v = ctypes.c_int(0)
@@ -350,7 +364,7 @@ class GradAllReducer:
         # the hook-free path can then reduce everything with a single collective
         self.slab: Optional[torch.Tensor] = None
         self.peer: Optional[PeerRegion] = None
-        self.fused_tail = not __import__("os").environ.get("CTI_PEER_NO_FUSED_TAIL")   # reduce_now: last exchange as one kernel
+        self.fused_tail = not os.environ.get("CTI_PEER_NO_FUSED_TAIL")   # reduce_now: last exchange as one kernel
         if transport not in ("nccl", "peer"):
             raise ValueError("GradAllReducer: transport must be 'nccl' or 'peer'")
         if ps and all(p.dtype == ps[0].dtype and p.device == ps[0].device for p in ps):
@@ -359,7 +373,7 @@ class GradAllReducer:
                 if ps[0].dtype != torch.float32:
                     raise RuntimeError("GradAllReducer: transport='peer' sums fp32 gradients")
                 self.peer = PeerRegion(n_slab, ps[0].device, process_group,
-                                       barrier=__import__("os").environ.get("CTI_PEER_BARRIER", "memops"))
+                                       barrier=os.environ.get("CTI_PEER_BARRIER", "memops"))
                 self.slab = self.peer.slab
             else:
                 self.slab = torch.zeros(n_slab, dtype=ps[0].dtype, device=ps[0].device)
@@ -476,8 +490,6 @@ class GradAllReducer:
                 # buckets launched during backward (launch_bucket) are in flight; the rest -- consecutive pieces of the
                 # slab -- go out as one more collective, then everything is waited for
                 rest = [b for b in self.buckets if not b.launched]
-                if __import__("os").environ.get("CTI_DIAG_SKIP_TAIL"):
-                    rest = []
                 if rest:
                     if self.slab is not None and all(x.flat.data_ptr() + x.flat.numel() * x.flat.element_size() == y.flat.data_ptr()
                                                      for x, y in zip(rest, rest[1:])):
@@ -525,6 +537,8 @@ class GradAllReducer:
                 p.grad = None
 
     def remove(self) -> None:
+        """Detach the hooks.  (A peer region stays mapped: the gradients live in it; ``self.peer.close()`` after a
+        barrier across the ranks releases it.)"""
         for h in self._handles:
             h.remove()
         self._handles = []

@@ -118,6 +118,8 @@ def _worker_groups(rank, world, port, out):
     sl = shard_rows(x.shape[0], rank, world, group=4)
     ps = list(model.parameters())
     early = [[ps[4], ps[5]], [ps[2]]]                       # last layer first: the order backward finishes them
+    with pytest.raises(RuntimeError, match="CUDA"):          # the peer-memory transport has no CPU path; raised on every rank
+        GradAllReducer(ps, param_groups=early, transport="peer")
     red = GradAllReducer(ps, param_groups=early)
     assert [len(b.params) for b in red.buckets[:2]] == [2, 1] and red.buckets[0].params[0] is ps[4]
     red.mark_in_place(early[0] + early[1])

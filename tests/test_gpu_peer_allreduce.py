@@ -93,6 +93,8 @@ def _worker(rank, world, port, out):
         res[("red", step)] = [p.grad.cpu().clone() for p in ps]
     torch.save(res, f"{out}.{rank}")
     dist.barrier()
+    reg.close()                                           # every rank is past its last exchange: unmap and free
+    dist.barrier()
     dist.destroy_process_group()
 
 
