@@ -249,7 +249,7 @@ class _Plan:
         grp = self.groups[gi]
         for pos, t in zip(grp["outs"], _GroupGradFn.apply(self, gi, *[proxies[o] for o in grp["outs"]])):
             proxies[pos] = t
-        self.prime(proxies)
+        self.prime(proxies, only=gi)
 
     def grad_group(self, gi: int) -> None:
         """dV / dg of the layers of group gi (two launches), into the bound gradient targets."""
@@ -289,20 +289,27 @@ class _Plan:
                   self.n_segs, t[9].data_ptr(), t[10].data_ptr(), self.n_blks, self.partials.data_ptr(), K_._stream()),
                  kernels=2, nbytes=20.0 * self.total)
 
-    def prime(self, proxies) -> None:
+    def prime(self, proxies, only: Optional[int] = None) -> None:
         """Point the layers' caches at the fresh packs (and, when ``proxies`` is given, at the proxies that defer their
-        weight-norm backward)."""
+        weight-norm backward).  only: just the layers of this gradient group (``open_group``)."""
         n_single = len(self.singles)
         pending = None                                     # gradient groups whose node does not exist yet (open_group)
         if proxies is not None and self.groups is not None and self.lazy is not None:
             pending = set(range(len(self.groups))) - self.lazy[1]
         e_rank = n_single
         for i, (lin, pk) in enumerate(zip(self.singles, self.single_packs)):
+            if only is not None and self.entry_group[i] != only:
+                continue
             key = (lin.weight_v._version, lin.weight_g._version, lin.weight_v.data_ptr())
             lin._pack = (key, pk)
             lin._vproxy = None if proxies is None else (key, proxies[i])
             lin._vlazy = None if pending is None or self.entry_group[i] not in pending else (self, self.entry_group[i])
         for ti, (tc, packs) in enumerate(zip(self.tcnets, self.rank_packs)):
+            if only is not None:
+                e0 = e_rank
+                if self.entry_group[e0] != only:
+                    e_rank += sum(len(lins) for lins in self.group_lins[ti])
+                    continue
             rank_params = tc.__dict__.get("_rank_params")
             if rank_params is None:
                 rank_params = [p for nets in (tc.v_net, tc.q_net, tc.a_net) for p in nets.parameters()]
